@@ -1,0 +1,459 @@
+// Per-tetrahedron hyperelastic math: energy, first Piola-Kirchhoff force, Hessian diagonal,
+// Hessian-vector product and Hessian quadratic form, for the three energies the reference ships.
+//
+// Written from the closed forms in SURVEY.md appendix A, i.e. what these reference files compute:
+//   warp/fem/func/_deformation.py:15-31   F = u^T dhdX + I, jvp = p^T dhdX, vjp = dhdX M^T
+//   warp/fem/func/_gradient.py:30-40      cof(F) = [f1 x f2 | f2 x f0 | f0 x f1]
+//   warp/fem/_stable_neo_hookean.py:17-103
+//   warp/fem/_stable_neo_hookean_muscle.py:18-114
+//   warp/fem/_arap.py:17-76  (hess_prod is the mathematically correct product, not the
+//                             reference's swapped-argument variant)
+//   warp/fem/func/_misc.py:31-70          lambdas (clamped), twist matrices Q0..Q2
+//   warp/fem/_base.py:317-320,379-380     per-entry clamp of the diagonal, per-cell clamp of p^T H p
+//
+// Layout choice (differs from the reference): only the 3x3 block D = rows 1..3 of dhdX is kept
+// (row 0 of dhdX is minus their sum), so F = I + sum_a (u_a - u_0) (x) D_a and the nodal force of
+// corner 0 is minus the sum of the other three.  Everything is a template on the scalar type and
+// is __host__ __device__ so that the same code is checked on the CPU against the oracle by
+// tests/native (test-only harness; the product only ever runs it on the GPU).
+#pragma once
+
+#include <cmath>
+
+#if defined(__CUDACC__)
+#define APL_HD __host__ __device__ __forceinline__
+#else
+#define APL_HD inline
+#endif
+
+#define APL_KIND_SNH 0
+#define APL_KIND_ARAP 1
+#define APL_KIND_SNH_MUSCLE 2
+
+#define APL_OP_FUN 1
+#define APL_OP_GRAD 2
+#define APL_OP_HESS_DIAG 4
+#define APL_OP_HESS_PROD 8
+#define APL_OP_HESS_QUAD 16
+
+namespace apl {
+
+using std::fabs;
+using std::sqrt;
+
+// Number of scalars in the per-tet static record: D[9], vol, mu, lambda, (activation[6]).
+template <int KIND>
+struct RecSize {
+    static constexpr int value = (KIND == APL_KIND_SNH_MUSCLE) ? 18 : 12;
+};
+
+template <typename T>
+APL_HD T apl_max(T a, T b) {
+    return a > b ? a : b;
+}
+
+template <typename T>
+APL_HD T apl_rsqrt(T x) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(T) == 4) {
+        // one Newton step on the hardware approximation: full fp32 accuracy
+        float r = rsqrtf((float)x);
+        r = r * (1.5f - 0.5f * (float)x * r * r);
+        return (T)r;
+    } else {
+        return (T)1 / sqrt(x);
+    }
+#else
+    return (T)1 / std::sqrt(x);
+#endif
+}
+
+// e[a][i] = w[a+1][i] - w[0][i]   (edge differences of a per-corner field)
+template <typename T>
+APL_HD void edge_diff(const T (*w)[3], T e[3][3]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) e[a][i] = w[a + 1][i] - w[0][i];
+}
+
+// M[3*i+J] = sum_a e[a][i] * D[3*a+J]      (this is  w^T dhdX  for a per-corner field w)
+template <typename T>
+APL_HD void edge_outer(const T e[3][3], const T* D, T* M) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int J = 0; J < 3; ++J)
+            M[3 * i + J] = e[0][i] * D[J] + e[1][i] * D[3 + J] + e[2][i] * D[6 + J];
+}
+
+// out[a][i] (+)= s * (dhdX M^T)[a][i]  with dhdX rows 1..3 = D and row 0 = -(sum of rows 1..3)
+template <typename T>
+APL_HD void vjp_rows(const T* D, const T* M, T s, T out[4][3]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        T r1 = D[0] * M[3 * i] + D[1] * M[3 * i + 1] + D[2] * M[3 * i + 2];
+        T r2 = D[3] * M[3 * i] + D[4] * M[3 * i + 1] + D[5] * M[3 * i + 2];
+        T r3 = D[6] * M[3 * i] + D[7] * M[3 * i + 1] + D[8] * M[3 * i + 2];
+        out[1][i] = s * r1;
+        out[2][i] = s * r2;
+        out[3][i] = s * r3;
+        out[0][i] = -s * (r1 + r2 + r3);
+    }
+}
+
+// cof(F), J = det F.  C[3*i+j] = (column j of cof)_i, columns f1xf2, f2xf0, f0xf1.
+template <typename T>
+APL_HD T cofactor(const T* F, T* C) {
+    C[0] = F[4] * F[8] - F[7] * F[5];
+    C[3] = F[7] * F[2] - F[1] * F[8];
+    C[6] = F[1] * F[5] - F[4] * F[2];
+    C[1] = F[5] * F[6] - F[8] * F[3];
+    C[4] = F[8] * F[0] - F[2] * F[6];
+    C[7] = F[2] * F[3] - F[5] * F[0];
+    C[2] = F[3] * F[7] - F[6] * F[4];
+    C[5] = F[6] * F[1] - F[0] * F[7];
+    C[8] = F[0] * F[4] - F[3] * F[1];
+    return F[0] * C[0] + F[3] * C[3] + F[6] * C[6];
+}
+
+// X(F, dF) = [f1 x p2 - f2 x p1 | f2 x p0 - f0 x p2 | f0 x p1 - f1 x p0]  (columns), the
+// directional derivative of cof(F) along dF (func/_hess_prod.py:62-77).
+template <typename T>
+APL_HD void dcofactor(const T* F, const T* P, T* X) {
+#define APL_CR(ax, ay, az, bx, by, bz, ox, oy, oz) \
+    ox = (ay) * (bz) - (az) * (by);                \
+    oy = (az) * (bx) - (ax) * (bz);                \
+    oz = (ax) * (by) - (ay) * (bx);
+    T ax, ay, az, bx, by, bz;
+    // column 0: f1 x p2 - f2 x p1
+    APL_CR(F[1], F[4], F[7], P[2], P[5], P[8], ax, ay, az)
+    APL_CR(F[2], F[5], F[8], P[1], P[4], P[7], bx, by, bz)
+    X[0] = ax - bx; X[3] = ay - by; X[6] = az - bz;
+    // column 1: f2 x p0 - f0 x p2
+    APL_CR(F[2], F[5], F[8], P[0], P[3], P[6], ax, ay, az)
+    APL_CR(F[0], F[3], F[6], P[2], P[5], P[8], bx, by, bz)
+    X[1] = ax - bx; X[4] = ay - by; X[7] = az - bz;
+    // column 2: f0 x p1 - f1 x p0
+    APL_CR(F[0], F[3], F[6], P[1], P[4], P[7], ax, ay, az)
+    APL_CR(F[1], F[4], F[7], P[0], P[3], P[6], bx, by, bz)
+    X[2] = ax - bx; X[5] = ay - by; X[8] = az - bz;
+#undef APL_CR
+}
+
+template <typename T>
+APL_HD T ddot9(const T* A, const T* B) {
+    T s = A[0] * B[0];
+#pragma unroll
+    for (int k = 1; k < 9; ++k) s += A[k] * B[k];
+    return s;
+}
+
+// |dhdX_a|^2 for a = 0..3 (row 0 = -(D0+D1+D2))
+template <typename T>
+APL_HD void row_norms(const T* D, T n[4]) {
+    T r0 = D[0] + D[3] + D[6], r1 = D[1] + D[4] + D[7], r2 = D[2] + D[5] + D[8];
+    n[0] = r0 * r0 + r1 * r1 + r2 * r2;
+    n[1] = D[0] * D[0] + D[1] * D[1] + D[2] * D[2];
+    n[2] = D[3] * D[3] + D[4] * D[4] + D[5] * D[5];
+    n[3] = D[6] * D[6] + D[7] * D[7] + D[8] * D[8];
+}
+
+// ------------------------------------------------------------------------------------------
+// 3x3 SVD, rotation-variant convention of warp/math/_rotation.py:9-13: F = U diag(s) V^T with
+// U, V proper rotations, s0 >= s1 >= |s2|, s2 carrying the sign of det F.
+// Cyclic Jacobi on F^T F for V, then modified Gram-Schmidt on F V for U and the singular values
+// (column norms of F V are more accurate than square roots of the eigenvalues).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+APL_HD void jacobi_rotate(T* A, T* V, int p, int q) {
+    // A symmetric, stored fully (row-major 3x3).  Annihilates A[p][q].
+    const T apq = A[3 * p + q];
+    const T app = A[3 * p + p], aqq = A[3 * q + q];
+    const T tiny = (sizeof(T) == 4) ? (T)1e-30 : (T)1e-280;
+    if (!(fabs(apq) > tiny)) return;
+    const T theta = (aqq - app) / ((T)2 * apq);
+    T t = (T)1 / (fabs(theta) + sqrt(theta * theta + (T)1));
+    if (theta < (T)0) t = -t;
+    const T c = apl_rsqrt(t * t + (T)1);
+    const T s = t * c;
+    const int r = 3 - p - q;  // the untouched index
+    const T arp = A[3 * r + p], arq = A[3 * r + q];
+    A[3 * p + p] = app - t * apq;
+    A[3 * q + q] = aqq + t * apq;
+    A[3 * p + q] = A[3 * q + p] = (T)0;
+    A[3 * r + p] = A[3 * p + r] = c * arp - s * arq;
+    A[3 * r + q] = A[3 * q + r] = s * arp + c * arq;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const T vp = V[3 * k + p], vq = V[3 * k + q];
+        V[3 * k + p] = c * vp - s * vq;
+        V[3 * k + q] = s * vp + c * vq;
+    }
+}
+
+template <typename T>
+APL_HD void swap_cols_neg(T* A, T* V, int a, int b) {
+    // swap eigenpairs a <-> b, negating one column to keep det V = +1
+    T t = A[3 * a + a];
+    A[3 * a + a] = A[3 * b + b];
+    A[3 * b + b] = t;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        T va = V[3 * k + a];
+        V[3 * k + a] = V[3 * k + b];
+        V[3 * k + b] = -va;
+    }
+}
+
+template <typename T>
+APL_HD void svd3_rv(const T* F, T* U, T* sig, T* V) {
+    T A[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            A[3 * i + j] = F[i] * F[j] + F[3 + i] * F[3 + j] + F[6 + i] * F[6 + j];
+    V[0] = 1; V[1] = 0; V[2] = 0;
+    V[3] = 0; V[4] = 1; V[5] = 0;
+    V[6] = 0; V[7] = 0; V[8] = 1;
+    constexpr int kSweeps = (sizeof(T) == 4) ? 5 : 8;
+#pragma unroll 1
+    for (int sweep = 0; sweep < kSweeps; ++sweep) {
+        jacobi_rotate(A, V, 0, 1);
+        jacobi_rotate(A, V, 0, 2);
+        jacobi_rotate(A, V, 1, 2);
+    }
+    // sort eigenvalues descending (det V stays +1)
+    if (A[0] < A[4]) swap_cols_neg(A, V, 0, 1);
+    if (A[0] < A[8]) swap_cols_neg(A, V, 0, 2);
+    if (A[4] < A[8]) swap_cols_neg(A, V, 1, 2);
+    // B = F V
+    T B[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            B[3 * i + j] = F[3 * i] * V[j] + F[3 * i + 1] * V[3 + j] + F[3 * i + 2] * V[6 + j];
+    const T tiny = (sizeof(T) == 4) ? (T)1e-18 : (T)1e-150;
+    // u0
+    T n0 = B[0] * B[0] + B[3] * B[3] + B[6] * B[6];
+    T u0x, u0y, u0z;
+    if (n0 > tiny) {
+        T r = apl_rsqrt(n0);
+        u0x = B[0] * r; u0y = B[3] * r; u0z = B[6] * r;
+        sig[0] = n0 * r;
+    } else {
+        u0x = 1; u0y = 0; u0z = 0;
+        sig[0] = 0;
+    }
+    // u1 = normalize(b1 - (u0.b1) u0)
+    T d = u0x * B[1] + u0y * B[4] + u0z * B[7];
+    T b1x = B[1] - d * u0x, b1y = B[4] - d * u0y, b1z = B[7] - d * u0z;
+    T n1 = b1x * b1x + b1y * b1y + b1z * b1z;
+    T u1x, u1y, u1z;
+    if (n1 > tiny) {
+        T r = apl_rsqrt(n1);
+        u1x = b1x * r; u1y = b1y * r; u1z = b1z * r;
+        sig[1] = n1 * r;
+    } else {
+        // any unit vector orthogonal to u0
+        if (fabs(u0x) < (T)0.6) { u1x = 0; u1y = -u0z; u1z = u0y; }
+        else { u1x = -u0y; u1y = u0x; u1z = 0; }
+        T r = apl_rsqrt(u1x * u1x + u1y * u1y + u1z * u1z);
+        u1x *= r; u1y *= r; u1z *= r;
+        sig[1] = 0;
+    }
+    // u2 = u0 x u1, s2 = u2 . b2 (signed)
+    T u2x = u0y * u1z - u0z * u1y, u2y = u0z * u1x - u0x * u1z, u2z = u0x * u1y - u0y * u1x;
+    sig[2] = u2x * B[2] + u2y * B[5] + u2z * B[8];
+    U[0] = u0x; U[3] = u0y; U[6] = u0z;
+    U[1] = u1x; U[4] = u1y; U[7] = u1z;
+    U[2] = u2x; U[5] = u2y; U[8] = u2z;
+}
+
+// ------------------------------------------------------------------------------------------
+// One tetrahedron, every requested operator.  rec = [D(9), vol, mu, lambda, (activation 6)].
+// Outputs (already multiplied by vol and clamped exactly like the reference kernels):
+//   psi   : Psi * vol                              (OP_FUN)
+//   g     : (dhdX P^T) * vol                       (OP_GRAD)
+//   dg    : max(diag * vol, 0) per entry           (OP_HESS_DIAG)
+//   hp    : (H p) * vol                            (OP_HESS_PROD)
+//   quad  : max(p^T H p * vol, 0)                  (OP_HESS_QUAD)
+// ------------------------------------------------------------------------------------------
+template <typename T, int KIND, int OPS>
+APL_HD void elem_eval(const T* rec, const T (*uc)[3], const T (*pc)[3], T& psi, T& quad,
+                      T g[4][3], T dg[4][3], T hp[4][3]) {
+    constexpr bool kFun = (OPS & APL_OP_FUN) != 0;
+    constexpr bool kGrad = (OPS & APL_OP_GRAD) != 0;
+    constexpr bool kDiag = (OPS & APL_OP_HESS_DIAG) != 0;
+    constexpr bool kProd = (OPS & APL_OP_HESS_PROD) != 0;
+    constexpr bool kQuad = (OPS & APL_OP_HESS_QUAD) != 0;
+    constexpr bool kNeedP = kProd || kQuad;
+
+    const T vol = rec[9], mu = rec[10];
+    T D[9];
+    T F[9];
+    {
+        T e[3][3];
+        edge_diff(uc, e);
+        if constexpr (KIND == APL_KIND_SNH_MUSCLE) {
+            // A = I + sym(a); D <- D A; F <- G = F A = A + sum_a e_a (x) (D A)_a
+            const T A[9] = {(T)1 + rec[12], rec[15], rec[16],
+                            rec[15], (T)1 + rec[13], rec[17],
+                            rec[16], rec[17], (T)1 + rec[14]};
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int J = 0; J < 3; ++J)
+                    D[3 * a + J] = rec[3 * a] * A[J] + rec[3 * a + 1] * A[3 + J] + rec[3 * a + 2] * A[6 + J];
+            edge_outer(e, D, F);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) F[k] += A[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) D[k] = rec[k];
+            edge_outer(e, D, F);
+            F[0] += (T)1; F[4] += (T)1; F[8] += (T)1;
+        }
+    }
+    T dF[9];
+    if constexpr (kNeedP) {
+        T e[3][3];
+        edge_diff(pc, e);
+        edge_outer(e, D, dF);
+    }
+
+    if constexpr (KIND == APL_KIND_SNH || KIND == APL_KIND_SNH_MUSCLE) {
+        const T la = rec[11];
+        T C[9];
+        const T J = cofactor(F, C);
+        const T Jm1 = J - (T)1;
+        const T c3 = -mu + la * Jm1;
+        if constexpr (kFun) {
+            const T I2 = ddot9(F, F);
+            psi = vol * ((T)0.5 * mu * (I2 - (T)3) - mu * Jm1 + (T)0.5 * la * Jm1 * Jm1);
+        }
+        if constexpr (kGrad) {
+            T P[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) P[k] = mu * F[k] + c3 * C[k];
+            vjp_rows(D, P, vol, g);
+        }
+        if constexpr (kDiag) {
+            T W[4][3], n[4];
+            vjp_rows(D, C, (T)1, W);
+            row_norms(D, n);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    dg[a][i] = apl_max(vol * (la * W[a][i] * W[a][i] + mu * n[a]), (T)0);
+        }
+        if constexpr (kNeedP) {
+            T X[9];
+            dcofactor(F, dF, X);
+            const T s = ddot9(C, dF);
+            if constexpr (kProd) {
+                T M[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) M[k] = la * s * C[k] + mu * dF[k] + c3 * X[k];
+                vjp_rows(D, M, vol, hp);
+            }
+            if constexpr (kQuad) {
+                const T q = la * s * s + mu * ddot9(dF, dF) + c3 * ddot9(dF, X);
+                quad = apl_max(vol * q, (T)0);
+            }
+        }
+    } else {  // ARAP
+        T U[9], V[9], sg[3];
+        svd3_rv(F, U, sg, V);
+        if constexpr (kFun) {
+            const T a = sg[0] - (T)1, b = sg[1] - (T)1, c = sg[2] - (T)1;
+            psi = vol * (T)0.5 * mu * (a * a + b * b + c * c);
+        }
+        if constexpr (kGrad) {
+            T P[9];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    P[3 * i + j] = F[3 * i + j] - (U[3 * i] * V[3 * j] + U[3 * i + 1] * V[3 * j + 1] +
+                                                   U[3 * i + 2] * V[3 * j + 2]);
+            vjp_rows(D, P, vol * mu, g);
+        }
+        if constexpr (kDiag || kNeedP) {
+            const T two = (T)2;
+            // func/_misc.py:31-43 with clamp: lambda_k = 2 / max(s_i + s_j, 2), pairs (0,1),(1,2),(2,0)
+            const T l0 = two / apl_max(sg[0] + sg[1], two);
+            const T l1 = two / apl_max(sg[1] + sg[2], two);
+            const T l2 = two / apl_max(sg[2] + sg[0], two);
+            // twist modes (func/_misc.py:56-70): Q0 = (u1 v0^T - u0 v1^T)/sqrt2,
+            // Q1 = (u1 v2^T - u2 v1^T)/sqrt2, Q2 = (u0 v2^T - u2 v0^T)/sqrt2
+            if constexpr (kDiag) {
+                // Y[a][n] = dhdX_a . v_n ; (dhdX Q^T)[a][i] = (um[i] Y[a][n] - un[i] Y[a][m]) / sqrt2
+                T Y[4][3], n[4];
+                {
+                    T Vt[9];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) Vt[3 * i + j] = V[3 * j + i];
+                    vjp_rows(D, Vt, (T)1, Y);  // Y[a][n] = sum_J dhdX[a][J] Vt[n][J] = dhdX_a . v_n
+                }
+                row_norms(D, n);
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const T w0 = U[3 * i + 1] * Y[a][0] - U[3 * i + 0] * Y[a][1];
+                        const T w1 = U[3 * i + 1] * Y[a][2] - U[3 * i + 2] * Y[a][1];
+                        const T w2 = U[3 * i + 0] * Y[a][2] - U[3 * i + 2] * Y[a][0];
+                        const T h4 = (T)0.5 * (l0 * w0 * w0 + l1 * w1 * w1 + l2 * w2 * w2);
+                        dg[a][i] = apl_max(vol * mu * (n[a] - h4), (T)0);
+                    }
+            }
+            if constexpr (kNeedP) {
+                // B = U^T dF V ; <Q0,dF> = (B10 - B01)/sqrt2, <Q1,dF> = (B12 - B21)/sqrt2,
+                // <Q2,dF> = (B02 - B20)/sqrt2
+                T Tm[9], B[9];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        Tm[3 * i + j] = U[i] * dF[j] + U[3 + i] * dF[3 + j] + U[6 + i] * dF[6 + j];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        B[3 * i + j] = Tm[3 * i] * V[j] + Tm[3 * i + 1] * V[3 + j] + Tm[3 * i + 2] * V[6 + j];
+                const T c0 = B[3] - B[1], c1 = B[5] - B[7], c2 = B[2] - B[6];  // times 1/sqrt2 each
+                if constexpr (kQuad) {
+                    const T q = ddot9(dF, dF) - (T)0.5 * (l0 * c0 * c0 + l1 * c1 * c1 + l2 * c2 * c2);
+                    quad = apl_max(vol * mu * q, (T)0);
+                }
+                if constexpr (kProd) {
+                    // M = dF - U K V^T, K = 1/2 [[0,-l0c0, l2c2],[l0c0,0,l1c1],[-l2c2,-l1c1,0]]
+                    const T k0 = (T)0.5 * l0 * c0, k1 = (T)0.5 * l1 * c1, k2 = (T)0.5 * l2 * c2;
+                    T UK[9];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        UK[3 * i + 0] = U[3 * i + 1] * k0 - U[3 * i + 2] * k2;
+                        UK[3 * i + 1] = -U[3 * i + 0] * k0 - U[3 * i + 2] * k1;
+                        UK[3 * i + 2] = U[3 * i + 0] * k2 + U[3 * i + 1] * k1;
+                    }
+                    T M[9];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+                            M[3 * i + j] = dF[3 * i + j] - (UK[3 * i] * V[3 * j] + UK[3 * i + 1] * V[3 * j + 1] +
+                                                            UK[3 * i + 2] * V[3 * j + 2]);
+                    vjp_rows(D, M, vol * mu, hp);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace apl

@@ -1,0 +1,44 @@
+// TEST-ONLY harness: compiles apple_b200/csrc/elem_math.cuh for the HOST so that the per-tet
+// closed forms can be checked against the oracle on a machine without a GPU.  It is built by
+// tests/test_elem_math_host.py into a scratch directory and is never part of the product library.
+#include "../../apple_b200/csrc/elem_math.cuh"
+
+template <typename T, int KIND>
+static void run(int n, const T* rec, const T* uc, const T* pc, T* psi, T* quad, T* g, T* dg, T* hp) {
+    constexpr int NR = apl::RecSize<KIND>::value;
+    constexpr int ALL = APL_OP_FUN | APL_OP_GRAD | APL_OP_HESS_DIAG | APL_OP_HESS_PROD | APL_OP_HESS_QUAD;
+    for (int t = 0; t < n; ++t) {
+        T G[4][3], DG[4][3], HP[4][3];
+        apl::elem_eval<T, KIND, ALL>(rec + (size_t)t * NR, (const T(*)[3])(uc + (size_t)t * 12),
+                                     (const T(*)[3])(pc + (size_t)t * 12), psi[t], quad[t], G, DG, HP);
+        for (int a = 0; a < 4; ++a)
+            for (int i = 0; i < 3; ++i) {
+                g[t * 12 + a * 3 + i] = G[a][i];
+                dg[t * 12 + a * 3 + i] = DG[a][i];
+                hp[t * 12 + a * 3 + i] = HP[a][i];
+            }
+    }
+}
+
+template <typename T>
+static void dispatch(int kind, int n, const void* rec, const void* uc, const void* pc, void* psi, void* quad,
+                     void* g, void* dg, void* hp) {
+#define CALL(K) run<T, K>(n, (const T*)rec, (const T*)uc, (const T*)pc, (T*)psi, (T*)quad, (T*)g, (T*)dg, (T*)hp)
+    if (kind == APL_KIND_SNH) CALL(APL_KIND_SNH);
+    else if (kind == APL_KIND_ARAP) CALL(APL_KIND_ARAP);
+    else CALL(APL_KIND_SNH_MUSCLE);
+#undef CALL
+}
+
+extern "C" void elem_eval_host(int kind, int is_f64, int n, const void* rec, const void* uc, const void* pc,
+                               void* psi, void* quad, void* g, void* dg, void* hp) {
+    if (is_f64) dispatch<double>(kind, n, rec, uc, pc, psi, quad, g, dg, hp);
+    else dispatch<float>(kind, n, rec, uc, pc, psi, quad, g, dg, hp);
+}
+
+extern "C" void svd3_host(int is_f64, int n, const void* F, void* U, void* s, void* V) {
+    for (int t = 0; t < n; ++t) {
+        if (is_f64) apl::svd3_rv<double>((const double*)F + 9 * t, (double*)U + 9 * t, (double*)s + 3 * t, (double*)V + 9 * t);
+        else apl::svd3_rv<float>((const float*)F + 9 * t, (float*)U + 9 * t, (float*)s + 3 * t, (float*)V + 9 * t);
+    }
+}
