@@ -1,0 +1,438 @@
+// C ABI of apple_b200: handle management, static-data packing and upload, operator dispatch.
+// Interface documentation lives in include/apple_b200.h.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+
+#include "common.h"
+#include "fem_kernels.cuh"
+
+namespace apl {
+const char* last_error_cstr();
+
+template <typename T, int KIND>
+int launch_fem(const apl_fem* fem, int ops, const FemArgs<T>& args, int scatter, cudaStream_t stream);
+
+static int rec_size(int kind) { return kind == APL_KIND_SNH_MUSCLE ? 18 : 12; }
+
+// Packs the caller-order reference arrays into [nplanes][plane_stride] 16-byte vectors in packed
+// (tile) order.  Record = D (rows 1..3 of dhdX), vol, mu, lambda, activation[6].
+template <typename T>
+static int pack_planes(apl_fem* f, const T* dhdX, const T* dV, const T* mu, const T* la, const T* act,
+                       std::vector<T>& planes) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const int64_t n = f->host.n_cells;
+    const int nrec = f->nrec;
+    planes.assign((size_t)f->nplanes * f->plane_stride * VEC, (T)0);
+    for (int64_t pos = 0; pos < n; ++pos) {
+        const int64_t c = f->host.order[(size_t)pos];
+        T rec[20] = {0};
+        if (dhdX) {
+            const T* d = dhdX + 12 * c;
+            double mx = 0, dev = 0;
+            for (int J = 0; J < 3; ++J) {
+                dev = std::max(dev, std::fabs((double)d[J] + d[3 + J] + d[6 + J] + d[9 + J]));
+                for (int a = 0; a < 4; ++a) mx = std::max(mx, std::fabs((double)d[3 * a + J]));
+            }
+            const double tol = (sizeof(T) == 4 ? 1e-3 : 1e-9) * mx;
+            if (!(dev <= tol)) {
+                set_error("dhdX rows of cell " + std::to_string(c) +
+                          " do not sum to zero (only linear tetrahedra are supported)");
+                return APL_ERR_MESH;
+            }
+            for (int k = 0; k < 9; ++k) rec[k] = d[3 + k];
+        }
+        rec[9] = dV ? dV[c] : (T)0;
+        rec[10] = mu ? mu[c] : (T)0;
+        rec[11] = la ? la[c] : (T)0;
+        if (act)
+            for (int k = 0; k < 6; ++k) rec[12 + k] = act[6 * c + k];
+        for (int k = 0; k < nrec; ++k) {
+            const int plane = k / VEC, lane = k % VEC;
+            planes[((size_t)plane * f->plane_stride + pos) * VEC + lane] = rec[k];
+        }
+    }
+    return APL_OK;
+}
+
+template <typename T>
+static int upload_planes(apl_fem* f, const void* dhdX, const void* dV, const void* mu, const void* la,
+                         const void* act) {
+    std::vector<T> planes;
+    int rc = pack_planes<T>(f, (const T*)dhdX, (const T*)dV, (const T*)mu, (const T*)la, (const T*)act, planes);
+    if (rc != APL_OK) return rc;
+    if (f->device >= 0) {
+        APL_CUDA_CHECK(cudaMemcpy(f->d_planes, planes.data(), planes.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    return APL_OK;
+}
+
+struct PncgExtras {
+    const void* axpy_p = nullptr;
+    const double* scal = nullptr;
+    int alpha_idx = 0, skip_a = -1, skip_b = -1;
+    double* fun_d = nullptr;
+    double* quad_d = nullptr;
+};
+
+template <typename T>
+static int eval_typed(apl_fem* f, int ops, const void* u, const void* p, int ld_in, void* fun, void* quad,
+                      void* grad, void* diag, void* prod, int ld_out, int scatter, cudaStream_t stream,
+                      const PncgExtras* ex = nullptr) {
+    FemArgs<T> a;
+    if (ex) {
+        a.axpy_p = (const T*)ex->axpy_p;
+        a.scal = ex->scal;
+        a.alpha_idx = ex->alpha_idx;
+        a.skip_a = ex->skip_a;
+        a.skip_b = ex->skip_b;
+        a.fun_d = (ops & APL_OP_FUN) ? ex->fun_d : nullptr;
+        a.quad_d = (ops & APL_OP_HESS_QUAD) ? ex->quad_d : nullptr;
+    }
+    a.tiles = (const int4*)f->d_tiles;
+    a.n_tiles = (int)f->host.n_tiles();
+    a.conn = (const uchar4*)f->d_conn;
+    a.slots = (const ushort4*)f->d_slots;
+    a.tile_verts = (const int*)f->d_tile_verts;
+    a.tile_voff = (const unsigned short*)f->d_tile_voff;
+    a.planes = (const uint4*)f->d_planes;
+    a.plane_stride = f->plane_stride;
+    a.u = (const T*)u;
+    a.p = (const T*)p;
+    a.ld_in = ld_in;
+    a.grad = (ops & APL_OP_GRAD) ? (T*)grad : nullptr;
+    a.diag = (ops & APL_OP_HESS_DIAG) ? (T*)diag : nullptr;
+    a.prod = (ops & APL_OP_HESS_PROD) ? (T*)prod : nullptr;
+    a.ld_out = ld_out;
+    a.fun = (ops & APL_OP_FUN) ? (T*)fun : nullptr;
+    a.quad = (ops & APL_OP_HESS_QUAD) ? (T*)quad : nullptr;
+    a.partials = f->d_partials;
+    a.counter = f->d_counter;
+    switch (f->kind) {
+        case APL_KIND_SNH: return launch_fem<T, APL_KIND_SNH>(f, ops, a, scatter, stream);
+        case APL_KIND_ARAP: return launch_fem<T, APL_KIND_ARAP>(f, ops, a, scatter, stream);
+        default: return launch_fem<T, APL_KIND_SNH_MUSCLE>(f, ops, a, scatter, stream);
+    }
+}
+
+// ---- small kernels: external force, field copy --------------------------------------------------
+
+template <typename T>
+__global__ void ext_force_kernel(int ops, long long k, const T* __restrict__ force,
+                                 const int* __restrict__ indices, const T* __restrict__ u, int ld_in, T* fun,
+                                 T* grad, int ld_out, const T* __restrict__ axpy_p, const double* scal,
+                                 int alpha_idx, int skip_a, int skip_b, double* fun_d) {
+    // warp/potential/_ext_force.py:17-39: W = -f.u[vid] (atomic to out[0]); grad[vid] -= f
+    if (scal) {
+        if (skip_a >= 0 && __ldcg(scal + skip_a) != 0.0) return;
+        if (skip_b >= 0 && __ldcg(scal + skip_b) != 0.0) return;
+    }
+    const T alpha = axpy_p ? (T)__ldcg(scal + alpha_idx) : (T)0;
+    double w = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < k;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int vid = indices[i];
+        const T fx = force[3 * i], fy = force[3 * i + 1], fz = force[3 * i + 2];
+        if (ops & APL_OP_FUN) {
+            const T* r = u + (long long)ld_in * vid;
+            T ux = r[0], uy = r[1], uz = r[2];
+            if (axpy_p) {
+                const T* d = axpy_p + (long long)ld_in * vid;
+                ux += alpha * d[0]; uy += alpha * d[1]; uz += alpha * d[2];
+            }
+            w -= (double)(fx * ux + fy * uy + fz * uz);
+        }
+        if (ops & APL_OP_GRAD) {
+            T* g = grad + (long long)ld_out * vid;
+            atomicAdd(g, -fx);
+            atomicAdd(g + 1, -fy);
+            atomicAdd(g + 2, -fz);
+        }
+    }
+    if (ops & APL_OP_FUN) {
+        w = warp_sum(w);
+        __shared__ double red[32];
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane == 0) red[wid] = w;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+            if (fun) atomicAdd(fun, (T)s);
+            if (fun_d) atomicAdd(fun_d, s);
+        }
+    }
+}
+
+template <typename T>
+__global__ void field_copy_kernel(long long n, const T* __restrict__ src, int ld_src, T* __restrict__ dst,
+                                  int ld_dst) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const T x = src[i * ld_src], y = src[i * ld_src + 1], z = src[i * ld_src + 2];
+        T* d = dst + i * ld_dst;
+        d[0] = x; d[1] = y; d[2] = z;
+        if (ld_dst == 4) d[3] = (T)0;
+    }
+}
+
+static int grid_for(long long n, int block) {
+    long long g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > 148 * 16) g = 148 * 16;
+    return (int)g;
+}
+
+// ---- entry points used by the native PNCG driver (pncg.cu) ------------------------------------------
+
+int fem_eval_pncg(apl_fem* f, int ops, const void* x, const void* p, const void* axpy_p, double* scal,
+                  int alpha_idx, int skip_a, int skip_b, double* fun_d, double* quad_d, void* grad, void* diag,
+                  int scatter, cudaStream_t stream) {
+    PncgExtras ex;
+    ex.axpy_p = axpy_p; ex.scal = scal; ex.alpha_idx = alpha_idx; ex.skip_a = skip_a; ex.skip_b = skip_b;
+    ex.fun_d = fun_d; ex.quad_d = quad_d;
+    return f->dtype == APL_F32
+               ? eval_typed<float>(f, ops, x, p, 4, nullptr, nullptr, grad, diag, nullptr, 4, scatter, stream, &ex)
+               : eval_typed<double>(f, ops, x, p, 4, nullptr, nullptr, grad, diag, nullptr, 4, scatter, stream, &ex);
+}
+
+int ext_force_pncg(int dtype, int ops, int64_t k, const void* force, const int32_t* indices, const void* x,
+                   const void* axpy_p, double* scal, int alpha_idx, int skip_a, int skip_b, double* fun_d,
+                   void* grad, cudaStream_t stream) {
+    if (k == 0) return APL_OK;
+    const int block = 256, grid = grid_for(k, block);
+    if (dtype == APL_F32)
+        ext_force_kernel<float><<<grid, block, 0, stream>>>(ops, k, (const float*)force, indices, (const float*)x, 4,
+                                                            nullptr, (float*)grad, 4, (const float*)axpy_p, scal,
+                                                            alpha_idx, skip_a, skip_b, fun_d);
+    else
+        ext_force_kernel<double><<<grid, block, 0, stream>>>(ops, k, (const double*)force, indices, (const double*)x,
+                                                             4, nullptr, (double*)grad, 4, (const double*)axpy_p, scal,
+                                                             alpha_idx, skip_a, skip_b, fun_d);
+    APL_CUDA_CHECK(cudaGetLastError());
+    return APL_OK;
+}
+
+}  // namespace apl
+
+using namespace apl;
+
+extern "C" {
+
+int apl_version(void) { return 100; }
+
+const char* apl_last_error(void) { return last_error_cstr(); }
+
+int apl_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        set_error(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+        return APL_ERR_CUDA;
+    }
+    return n;
+}
+
+void apl_fem_destroy(apl_fem_t* f) {
+    if (!f) return;
+    if (f->device >= 0) {
+        cudaFree(f->d_tiles);
+        cudaFree(f->d_conn);
+        cudaFree(f->d_slots);
+        cudaFree(f->d_tile_verts);
+        cudaFree(f->d_tile_voff);
+        cudaFree(f->d_planes);
+        cudaFree(f->d_partials);
+        cudaFree(f->d_counter);
+    }
+    delete f;
+}
+
+int apl_fem_create(int kind, int dtype, int64_t n_cells, int64_t n_points, const int32_t* cells,
+                   const void* dhdX, const void* dV, const void* mu, const void* lambda_,
+                   const void* activation, const double* points, int device, apl_fem_t** out) {
+    if (!out) { set_error("apl_fem_create: out is NULL"); return APL_ERR_INVALID; }
+    *out = nullptr;
+    if (kind < 0 || kind > 2 || (dtype != APL_F32 && dtype != APL_F64)) {
+        set_error("apl_fem_create: unknown kind or dtype");
+        return APL_ERR_INVALID;
+    }
+    if (!dhdX || !dV || !mu || (kind != APL_KIND_ARAP && !lambda_) || (kind == APL_KIND_SNH_MUSCLE && !activation)) {
+        set_error("apl_fem_create: a required array (dhdX, dV, mu, lambda_, activation) is NULL");
+        return APL_ERR_INVALID;
+    }
+    apl_fem* f = new apl_fem();
+    f->kind = kind;
+    f->dtype = dtype;
+    f->device = device;
+    f->nrec = rec_size(kind);
+    const int vec = dtype == APL_F32 ? 4 : 2;
+    f->nplanes = (f->nrec + vec - 1) / vec;
+    int rc = build_tiles(n_cells, n_points, cells, points, f->host);
+    if (rc != APL_OK) { delete f; return rc; }
+    f->plane_stride = (n_cells + 31) / 32 * 32;
+    if (f->plane_stride == 0) f->plane_stride = 32;
+    const HostTables& h = f->host;
+    const size_t plane_bytes = (size_t)f->nplanes * f->plane_stride * 16;
+    f->static_bytes = (int64_t)(plane_bytes + h.tiles.size() * 4 + h.conn.size() + h.slots.size() * 2 +
+                                h.tile_verts.size() * 4 + h.tile_voff.size() * 2);
+    if (device >= 0) {
+        auto fail = [&](int code) { apl_fem_destroy(f); return code; };
+#define APL_TRY(expr)                                                                           \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e));              \
+            return fail(APL_ERR_CUDA);                                                          \
+        }                                                                                       \
+    } while (0)
+        APL_TRY(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        APL_TRY(cudaGetDeviceProperties(&prop, device));
+        f->num_sms = prop.multiProcessorCount;
+        f->max_grid = f->num_sms * 8;
+        auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+            cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
+            if (e != cudaSuccess) return e;
+            return bytes ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+        };
+        APL_TRY(up(&f->d_tiles, h.tiles.data(), h.tiles.size() * 4));
+        APL_TRY(up(&f->d_conn, h.conn.data(), h.conn.size()));
+        APL_TRY(up(&f->d_slots, h.slots.data(), h.slots.size() * 2));
+        APL_TRY(up(&f->d_tile_verts, h.tile_verts.data(), h.tile_verts.size() * 4));
+        APL_TRY(up(&f->d_tile_voff, h.tile_voff.data(), h.tile_voff.size() * 2));
+        APL_TRY(cudaMalloc(&f->d_planes, plane_bytes));
+        APL_TRY(cudaMalloc((void**)&f->d_partials, sizeof(double) * 2 * f->max_grid));
+        APL_TRY(cudaMalloc((void**)&f->d_counter, sizeof(unsigned int)));
+        APL_TRY(cudaMemset(f->d_counter, 0, sizeof(unsigned int)));
+#undef APL_TRY
+    }
+    rc = (dtype == APL_F32) ? upload_planes<float>(f, dhdX, dV, mu, lambda_, activation)
+                            : upload_planes<double>(f, dhdX, dV, mu, lambda_, activation);
+    if (rc != APL_OK) { apl_fem_destroy(f); return rc; }
+    *out = f;
+    return APL_OK;
+}
+
+int apl_fem_info(const apl_fem_t* f, int64_t info[8]) {
+    if (!f || !info) { set_error("apl_fem_info: NULL argument"); return APL_ERR_INVALID; }
+    info[0] = f->host.n_cells;
+    info[1] = f->host.n_points;
+    info[2] = f->host.n_tiles();
+    info[3] = (int64_t)f->host.tile_verts.size();
+    info[4] = f->static_bytes;
+    info[5] = f->kind;
+    info[6] = f->dtype;
+    info[7] = f->device;
+    return APL_OK;
+}
+
+int apl_fem_host_tables(const apl_fem_t* f, int32_t* tiles, int64_t* order, uint8_t* conn, uint16_t* slots,
+                        int32_t* tile_verts, uint16_t* tile_voff) {
+    if (!f) { set_error("apl_fem_host_tables: NULL handle"); return APL_ERR_INVALID; }
+    const HostTables& h = f->host;
+    if (tiles) memcpy(tiles, h.tiles.data(), h.tiles.size() * 4);
+    if (order) memcpy(order, h.order.data(), h.order.size() * 8);
+    if (conn) memcpy(conn, h.conn.data(), h.conn.size());
+    if (slots) memcpy(slots, h.slots.data(), h.slots.size() * 2);
+    if (tile_verts) memcpy(tile_verts, h.tile_verts.data(), h.tile_verts.size() * 4);
+    if (tile_voff) memcpy(tile_voff, h.tile_voff.data(), h.tile_voff.size() * 2);
+    return APL_OK;
+}
+
+int apl_fem_set_materials(apl_fem_t* f, const void* dV, const void* mu, const void* lambda_,
+                          const void* activation) {
+    if (!f) { set_error("apl_fem_set_materials: NULL handle"); return APL_ERR_INVALID; }
+    if (f->device < 0) { set_error("apl_fem_set_materials: host-only handle"); return APL_ERR_STATE; }
+    // Read back, patch the requested columns, upload.  Setup-time path, not hot.
+    const int vec = f->dtype == APL_F32 ? 4 : 2;
+    const size_t esz = f->dtype == APL_F32 ? 4 : 8;
+    const size_t bytes = (size_t)f->nplanes * f->plane_stride * 16;
+    std::vector<unsigned char> buf(bytes);
+    APL_CUDA_CHECK(cudaSetDevice(f->device));
+    APL_CUDA_CHECK(cudaMemcpy(buf.data(), f->d_planes, bytes, cudaMemcpyDeviceToHost));
+    auto put = [&](int k, int64_t pos, const void* src, int64_t idx) {
+        const int plane = k / vec, lane = k % vec;
+        memcpy(buf.data() + (((size_t)plane * f->plane_stride + pos) * vec + lane) * esz,
+               (const unsigned char*)src + (size_t)idx * esz, esz);
+    };
+    for (int64_t pos = 0; pos < f->host.n_cells; ++pos) {
+        const int64_t c = f->host.order[(size_t)pos];
+        if (dV) put(9, pos, dV, c);
+        if (mu) put(10, pos, mu, c);
+        if (lambda_ && f->kind != APL_KIND_ARAP) put(11, pos, lambda_, c);
+        if (activation && f->kind == APL_KIND_SNH_MUSCLE)
+            for (int k = 0; k < 6; ++k) put(12 + k, pos, activation, 6 * c + k);
+    }
+    APL_CUDA_CHECK(cudaMemcpy(f->d_planes, buf.data(), bytes, cudaMemcpyHostToDevice));
+    return APL_OK;
+}
+
+int apl_fem_eval(apl_fem_t* f, int ops, const void* u, const void* p, int ld_in, void* fun, void* quad,
+                 void* grad, void* diag, void* prod, int ld_out, int scatter, void* stream) {
+    if (!f) { set_error("apl_fem_eval: NULL handle"); return APL_ERR_INVALID; }
+    if (f->device < 0) { set_error("apl_fem_eval: handle was created host-only (device = -1)"); return APL_ERR_STATE; }
+    if (ops <= 0 || ops > 31) { set_error("apl_fem_eval: ops must be a non-empty OR of APL_OP_*"); return APL_ERR_INVALID; }
+    if ((ld_in != 3 && ld_in != 4) || (ld_out != 3 && ld_out != 4)) {
+        set_error("apl_fem_eval: leading dimensions must be 3 or 4");
+        return APL_ERR_INVALID;
+    }
+    if (scatter != APL_SCATTER_TILE && scatter != APL_SCATTER_ATOMIC) {
+        set_error("apl_fem_eval: unknown scatter mode");
+        return APL_ERR_INVALID;
+    }
+    if (!u || ((ops & (APL_OP_HESS_PROD | APL_OP_HESS_QUAD)) && !p) || ((ops & APL_OP_FUN) && !fun) ||
+        ((ops & APL_OP_HESS_QUAD) && !quad) || ((ops & APL_OP_GRAD) && !grad) ||
+        ((ops & APL_OP_HESS_DIAG) && !diag) || ((ops & APL_OP_HESS_PROD) && !prod)) {
+        set_error("apl_fem_eval: an array required by `ops` is NULL");
+        return APL_ERR_INVALID;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    return f->dtype == APL_F32
+               ? eval_typed<float>(f, ops, u, p, ld_in, fun, quad, grad, diag, prod, ld_out, scatter, s)
+               : eval_typed<double>(f, ops, u, p, ld_in, fun, quad, grad, diag, prod, ld_out, scatter, s);
+}
+
+int apl_ext_force_eval(int dtype, int ops, int64_t k, const void* force, const int32_t* indices, const void* u,
+                       int ld_in, void* fun, void* grad, int ld_out, void* stream) {
+    if (k < 0 || (k > 0 && (!force || !indices))) { set_error("apl_ext_force_eval: bad arguments"); return APL_ERR_INVALID; }
+    ops &= (APL_OP_FUN | APL_OP_GRAD);
+    if (k == 0 || ops == 0) return APL_OK;
+    if (((ops & APL_OP_FUN) && (!u || !fun)) || ((ops & APL_OP_GRAD) && !grad)) {
+        set_error("apl_ext_force_eval: an array required by `ops` is NULL");
+        return APL_ERR_INVALID;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int block = 256, grid = grid_for(k, block);
+    if (dtype == APL_F32)
+        ext_force_kernel<float><<<grid, block, 0, s>>>(ops, k, (const float*)force, indices, (const float*)u, ld_in,
+                                                       (float*)fun, (float*)grad, ld_out, nullptr, nullptr, 0, -1, -1,
+                                                       nullptr);
+    else if (dtype == APL_F64)
+        ext_force_kernel<double><<<grid, block, 0, s>>>(ops, k, (const double*)force, indices, (const double*)u,
+                                                        ld_in, (double*)fun, (double*)grad, ld_out, nullptr, nullptr, 0,
+                                                        -1, -1, nullptr);
+    else { set_error("apl_ext_force_eval: unknown dtype"); return APL_ERR_INVALID; }
+    APL_CUDA_CHECK(cudaGetLastError());
+    return APL_OK;
+}
+
+int apl_field_copy(int dtype, int64_t n, const void* src, int ld_src, void* dst, int ld_dst, void* stream) {
+    if (n < 0 || (n > 0 && (!src || !dst)) || (ld_src != 3 && ld_src != 4) || (ld_dst != 3 && ld_dst != 4)) {
+        set_error("apl_field_copy: bad arguments");
+        return APL_ERR_INVALID;
+    }
+    if (n == 0) return APL_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int block = 256, grid = grid_for(n, block);
+    if (dtype == APL_F32)
+        field_copy_kernel<float><<<grid, block, 0, s>>>(n, (const float*)src, ld_src, (float*)dst, ld_dst);
+    else if (dtype == APL_F64)
+        field_copy_kernel<double><<<grid, block, 0, s>>>(n, (const double*)src, ld_src, (double*)dst, ld_dst);
+    else { set_error("apl_field_copy: unknown dtype"); return APL_ERR_INVALID; }
+    APL_CUDA_CHECK(cudaGetLastError());
+    return APL_OK;
+}
+
+}  // extern "C"

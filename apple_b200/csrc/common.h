@@ -1,0 +1,64 @@
+// Shared declarations of the apple_b200 native library (not part of the public ABI).
+#pragma once
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/apple_b200.h"
+
+namespace apl {
+
+constexpr int kTileTets = 256;   // tets per tile == threads per CTA
+constexpr int kTileVerts = 256;  // max distinct vertices per tile (uint8 local ids)
+
+void set_error(const std::string& msg);
+
+// Host-side packed mesh (built by tiling.cpp, uploaded by capi.cu).
+struct HostTables {
+    int64_t n_cells = 0, n_points = 0;
+    std::vector<int32_t> tiles;        // (n_tiles,4): tet_start, n_tets, vert_start, n_verts
+    std::vector<int64_t> order;        // packed position -> caller's cell index
+    std::vector<uint8_t> conn;         // (n_cells,4)
+    std::vector<uint16_t> slots;       // (n_cells,4)
+    std::vector<int32_t> tile_verts;   // global vertex ids, tile after tile (ascending within a tile)
+    std::vector<uint16_t> tile_voff;   // per tile n_verts+1 offsets, tile t starts at vert_start + t
+    int64_t n_tiles() const { return (int64_t)tiles.size() / 4; }
+};
+
+// cells: (n_cells,4) int32.  points: (n_points,3) double or nullptr.  Returns APL_OK or error code.
+int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const double* points,
+                HostTables& out);
+
+}  // namespace apl
+
+struct apl_fem {
+    int kind = 0, dtype = 0, device = -1;
+    int nrec = 0;      // scalars per tet record
+    int nplanes = 0;   // 16-byte planes per tet
+    apl::HostTables host;
+    int64_t plane_stride = 0;  // in 16-byte vectors (n_cells rounded up)
+    int64_t static_bytes = 0;
+    // device tables
+    void* d_tiles = nullptr;
+    void* d_conn = nullptr;
+    void* d_slots = nullptr;
+    void* d_tile_verts = nullptr;
+    void* d_tile_voff = nullptr;
+    void* d_planes = nullptr;
+    double* d_partials = nullptr;   // per-CTA scalar partials (2 per CTA)
+    unsigned int* d_counter = nullptr;
+    int max_grid = 0;
+    int num_sms = 0;
+};
+
+#define APL_CUDA_CHECK(expr)                                                                       \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            apl::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" +     \
+                           __FILE__ + ":" + std::to_string(__LINE__) + ")");                       \
+            return APL_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)

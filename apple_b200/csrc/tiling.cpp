@@ -1,0 +1,162 @@
+// Host-side mesh packing: Morton ordering of the tets and greedy tiling.
+//
+// A tile is a run of <= 256 consecutive tets (in packed order) that together touch <= 256 distinct
+// vertices.  For every tile we store
+//   * the sorted list of the global vertex ids it touches            (tile_verts)
+//   * per tet, the tile-local id of each corner as one byte          (conn)
+//   * per tet corner, a slot in [0, 4*n_tets): slots are grouped by local vertex, so the element
+//     kernel can write every corner contribution to its own shared-memory slot (no atomics) and a
+//     second phase sums each vertex's contiguous slot range                     (slots, tile_voff)
+// This replaces the reference's per-tet global connectivity (`cells`, warp/fem/_base.py:59-74) and
+// its 12 global atomics per tet per field (warp/fem/_base.py:288-289).
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "common.h"
+
+namespace apl {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+const char* last_error_cstr() { return g_last_error.c_str(); }
+
+static inline uint64_t spread21(uint64_t x) {
+    x &= 0x1fffffULL;
+    x = (x | (x << 32)) & 0x1f00000000ffffULL;
+    x = (x | (x << 16)) & 0x1f0000ff0000ffULL;
+    x = (x | (x << 8)) & 0x100f00f00f00f00fULL;
+    x = (x | (x << 4)) & 0x10c30c30c30c30c3ULL;
+    x = (x | (x << 2)) & 0x1249249249249249ULL;
+    return x;
+}
+
+static void morton_order(int64_t n_cells, int64_t n_points, const int32_t* cells, const double* points,
+                         std::vector<int64_t>& order) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int64_t v = 0; v < n_points; ++v)
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = std::min(lo[k], points[3 * v + k]);
+            hi[k] = std::max(hi[k], points[3 * v + k]);
+        }
+    double ext = 0;
+    for (int k = 0; k < 3; ++k) ext = std::max(ext, hi[k] - lo[k]);
+    const double scale = ext > 0 ? (double)((1 << 21) - 1) / ext : 0.0;
+    std::vector<std::pair<uint64_t, int64_t>> keyed((size_t)n_cells);
+    bool sorted = true;
+    uint64_t prev = 0;
+    for (int64_t c = 0; c < n_cells; ++c) {
+        uint64_t q[3];
+        for (int k = 0; k < 3; ++k) {
+            double s = 0;
+            for (int a = 0; a < 4; ++a) s += points[3 * (int64_t)cells[4 * c + a] + k];
+            q[k] = (uint64_t)((0.25 * s - lo[k]) * scale);
+        }
+        const uint64_t code = spread21(q[0]) | (spread21(q[1]) << 1) | (spread21(q[2]) << 2);
+        keyed[(size_t)c] = {code, c};
+        if (code < prev) sorted = false;
+        prev = code;
+    }
+    if (!sorted) std::stable_sort(keyed.begin(), keyed.end());
+    for (int64_t c = 0; c < n_cells; ++c) order[(size_t)c] = keyed[(size_t)c].second;
+}
+
+int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const double* points,
+                HostTables& out) {
+    if (n_cells < 0 || n_points <= 0 || (!cells && n_cells > 0)) {
+        set_error("build_tiles: bad sizes");
+        return APL_ERR_INVALID;
+    }
+    for (int64_t i = 0; i < 4 * n_cells; ++i)
+        if (cells[i] < 0 || cells[i] >= n_points) {
+            set_error("cells[" + std::to_string(i / 4) + "] references vertex " + std::to_string(cells[i]) +
+                      " outside [0, n_points)");
+            return APL_ERR_MESH;
+        }
+    out = HostTables();
+    out.n_cells = n_cells;
+    out.n_points = n_points;
+    out.order.resize((size_t)n_cells);
+    if (points) morton_order(n_cells, n_points, cells, points, out.order);
+    else std::iota(out.order.begin(), out.order.end(), (int64_t)0);
+    out.conn.resize((size_t)n_cells * 4);
+    out.slots.resize((size_t)n_cells * 4);
+    out.tiles.reserve((size_t)(n_cells / kTileTets + 1) * 4);
+    out.tile_verts.reserve((size_t)(n_cells / 2 + 16));
+
+    std::vector<int32_t> stamp((size_t)n_points, -1);  // tile that last touched the vertex
+    std::vector<int32_t> lid((size_t)n_points, 0);     // its local id in that tile
+    std::vector<int32_t> verts;                        // distinct vertices of the open tile
+    verts.reserve(kTileVerts);
+    int32_t cnt[kTileVerts];
+    int32_t off[kTileVerts + 1];
+    int64_t tile_start = 0;
+    int32_t tile_id = 0;
+
+    auto close_tile = [&](int64_t tile_end) {
+        const int nt = (int)(tile_end - tile_start);
+        if (nt == 0) return;
+        const int nv = (int)verts.size();
+        std::sort(verts.begin(), verts.end());
+        for (int l = 0; l < nv; ++l) {
+            lid[(size_t)verts[l]] = l;
+            cnt[l] = 0;
+        }
+        for (int64_t pos = tile_start; pos < tile_end; ++pos) {
+            const int32_t* c = cells + 4 * out.order[(size_t)pos];
+            for (int a = 0; a < 4; ++a) {
+                const int l = lid[(size_t)c[a]];
+                out.conn[(size_t)pos * 4 + a] = (uint8_t)l;
+                ++cnt[l];
+            }
+        }
+        off[0] = 0;
+        for (int l = 0; l < nv; ++l) off[l + 1] = off[l] + cnt[l];
+        const int32_t vert_start = (int32_t)out.tile_verts.size();
+        out.tiles.push_back((int32_t)tile_start);
+        out.tiles.push_back(nt);
+        out.tiles.push_back(vert_start);
+        out.tiles.push_back(nv);
+        for (int l = 0; l < nv; ++l) out.tile_verts.push_back(verts[l]);
+        for (int l = 0; l <= nv; ++l) out.tile_voff.push_back((uint16_t)off[l]);
+        for (int l = 0; l < nv; ++l) cnt[l] = 0;  // reuse as fill cursor
+        for (int64_t pos = tile_start; pos < tile_end; ++pos)
+            for (int a = 0; a < 4; ++a) {
+                const int l = out.conn[(size_t)pos * 4 + a];
+                out.slots[(size_t)pos * 4 + a] = (uint16_t)(off[l] + cnt[l]++);
+            }
+        verts.clear();
+        tile_start = tile_end;
+        ++tile_id;
+    };
+
+    if (n_cells > (int64_t)INT32_MAX) {
+        set_error("n_cells exceeds int32 range");
+        return APL_ERR_INVALID;
+    }
+    for (int64_t pos = 0; pos < n_cells; ++pos) {
+        const int32_t* c = cells + 4 * out.order[(size_t)pos];
+        int n_new = 0;
+        for (int a = 0; a < 4; ++a) {
+            bool is_new = stamp[(size_t)c[a]] != tile_id;
+            for (int b = 0; b < a; ++b) is_new = is_new && (c[b] != c[a]);
+            n_new += is_new;
+        }
+        if (pos - tile_start == kTileTets || (int)verts.size() + n_new > kTileVerts) {
+            close_tile(pos);
+        }
+        for (int a = 0; a < 4; ++a)
+            if (stamp[(size_t)c[a]] != tile_id) {
+                stamp[(size_t)c[a]] = tile_id;
+                verts.push_back(c[a]);
+            }
+    }
+    close_tile(n_cells);
+    if (out.tile_verts.size() + (size_t)out.n_tiles() > (size_t)INT32_MAX) {
+        set_error("tile vertex table exceeds int32 range");
+        return APL_ERR_INVALID;
+    }
+    return APL_OK;
+}
+
+}  // namespace apl

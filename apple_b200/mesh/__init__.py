@@ -1,0 +1,19 @@
+"""Tetrahedral mesh container and synthetic mesh generators.
+
+``pyvista`` is not available in this environment, so ``TetMesh`` provides the small part of the
+``pv.UnstructuredGrid`` surface the reference touches (``points``, ``cells_dict``-like ``cells``,
+``point_data``, ``cell_data``, ``n_points``, ``n_cells``).  Every ``from_pyvista`` constructor in this
+package accepts either a ``TetMesh`` or a real ``pyvista.UnstructuredGrid``.
+"""
+
+from ._mesh import TetMesh, as_tet_arrays
+from ._generate import cube_tet_mesh, embedded_tetra_mesh, morton_reorder, lumped_vertex_volume
+
+__all__ = [
+    "TetMesh",
+    "as_tet_arrays",
+    "cube_tet_mesh",
+    "embedded_tetra_mesh",
+    "lumped_vertex_volume",
+    "morton_reorder",
+]

@@ -1,0 +1,10 @@
+"""Optimizer layer: the part of ``liblaf.peach.optim`` the reference uses (``Problem``, ``Optimizer``,
+``PNCG``, ``Result``).  peach itself is an external, un-vendored dependency of the reference
+(``pyproject.toml:39,172``); its call sites are ``forward/_forward.py:22-30,52-56`` and
+``forward/_problem.py:18-59``."""
+
+from ._base import Optimizer, Problem, Result, Solution
+from ._pncg import PNCG
+from . import pncg
+
+__all__ = ["PNCG", "Optimizer", "Problem", "Result", "Solution", "pncg"]

@@ -1,0 +1,184 @@
+from __future__ import annotations
+
+import ctypes
+from collections.abc import Sequence
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from apple_b200 import _lib, config
+from apple_b200.common import ACTIVATION, FRACTION, LAMBDA, MU
+from apple_b200.fem import Region
+from apple_b200.warp.model import WarpPotential
+
+
+def get_fraction(region: Region) -> np.ndarray:
+    """``warp/fem/utils/_material.py:19-23``: cell_data["Fraction"] or ones."""
+    fraction = region.cell_data.get(FRACTION.vtk)
+    if fraction is None:
+        return np.ones(region.n_cells)
+    return np.asarray(fraction, dtype=np.float64)
+
+
+def get_mu(region: Region) -> np.ndarray:  # _material.py:30-31
+    return np.asarray(region.cell_data[MU.vtk], dtype=np.float64)
+
+
+def get_lambda(region: Region) -> np.ndarray:  # _material.py:26-27
+    return np.asarray(region.cell_data[LAMBDA.vtk], dtype=np.float64)
+
+
+def get_activation(region: Region) -> np.ndarray:  # _material.py:15-16
+    return np.asarray(region.cell_data[str(ACTIVATION)], dtype=np.float64).reshape(-1, 6)
+
+
+class WarpPotentialFem(WarpPotential):
+    """FEM potential over linear tets, mirror of ``warp/fem/_base.py:39-194``.
+
+    Holds the region arrays (``region.cells``, ``region.dhdX``, ``region.dV``) and ``materials`` in
+    the reference's layout on the host, and a native handle (``apl_fem_t``) with the packed, tiled
+    device copy the kernels read.  The five operators launch one CUDA kernel each; ``eval`` fuses any
+    subset into a single pass."""
+
+    KIND: int = -1
+    MATERIAL_NAMES: tuple[str, ...] = ()
+
+    def __init__(self, region: SimpleNamespace, materials: SimpleNamespace, *, points=None, n_points=None,
+                 dtype: torch.dtype | None = None, device=None, name: str | None = None,
+                 requires_grad: Sequence[str] = (), scatter: int | None = None):
+        super().__init__(name=name, requires_grad=requires_grad)
+        self.dtype = dtype or config.default_dtype
+        self.device = torch.device(device if device is not None else config.default_device())
+        self.scatter = scatter
+        npdt = _lib.np_dtype(self.dtype)
+        self.region = SimpleNamespace(
+            cells=np.ascontiguousarray(region.cells, dtype=np.int32),
+            dhdX=np.ascontiguousarray(region.dhdX, dtype=npdt),
+            dV=np.ascontiguousarray(region.dV, dtype=npdt),
+        )
+        self.materials = SimpleNamespace(
+            **{k: np.ascontiguousarray(getattr(materials, k), dtype=npdt) for k in self.MATERIAL_NAMES}
+        )
+        n_cells = self.region.cells.shape[0]
+        self.n_points = int(n_points if n_points is not None else (self.region.cells.max() + 1 if n_cells else 1))
+        if self.device.type != "cuda":
+            raise _lib.NativeError("apple_b200 potentials live on a CUDA device (there is no CPU path)")
+        handle = ctypes.c_void_p()
+        pts = None if points is None else np.ascontiguousarray(points, dtype=np.float64)
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _lib.check(
+            _lib.lib().apl_fem_create(
+                self.KIND, _lib.dtype_code(self.dtype), n_cells, self.n_points,
+                _lib.host_ptr(self.region.cells), _lib.host_ptr(self.region.dhdX.reshape(n_cells, 4, 3)),
+                _lib.host_ptr(self.region.dV.reshape(n_cells)),
+                _lib.host_ptr(getattr(self.materials, "mu", None)),
+                _lib.host_ptr(getattr(self.materials, "lambda_", None)),
+                _lib.host_ptr(getattr(self.materials, "activation", None)),
+                _lib.host_ptr(pts), dev_index, ctypes.byref(handle),
+            )
+        )
+        self._handle = handle
+
+    def __del__(self):
+        handle = getattr(self, "_handle", None)
+        if handle is not None and handle.value:
+            try:
+                _lib.lib().apl_fem_destroy(handle)
+            except Exception:  # interpreter shutdown
+                pass
+            self._handle = None
+
+    # ---- constructors (``_base.py:76-111``) ----
+    @classmethod
+    def from_pyvista(cls, obj, **kwargs):
+        region = Region.from_pyvista(obj, grad=True)
+        return cls.from_region(region, **kwargs)
+
+    @classmethod
+    def from_region(cls, region: Region, *, requires_grad: Sequence[str] = (), **kwargs):
+        fraction = get_fraction(region)
+        region_np = SimpleNamespace(
+            cells=region.cells_global,
+            dhdX=region.dhdX,  # (cells, quadrature=1, 4, 3)
+            dV=fraction[:, None] * region.dV,  # _base.py:104
+        )
+        kwargs.setdefault("points", region.points)
+        kwargs.setdefault("n_points", region.points.shape[0])
+        return cls(region_np, cls.materials_from_region(region, requires_grad), requires_grad=requires_grad, **kwargs)
+
+    @classmethod
+    def materials_from_region(cls, region: Region, requires_grad: Sequence[str]) -> SimpleNamespace:
+        raise NotImplementedError
+
+    @property
+    def launch_dim(self) -> tuple[int, int]:
+        return tuple(self.region.dhdX.shape[:2])
+
+    @property
+    def info(self) -> dict:
+        buf = (ctypes.c_int64 * 8)()
+        _lib.check(_lib.lib().apl_fem_info(self._handle, buf))
+        keys = ("n_cells", "n_points", "n_tiles", "n_tile_verts", "static_bytes", "kind", "dtype", "device")
+        return dict(zip(keys, list(buf)))
+
+    def set_materials(self, *, dV=None, **materials) -> None:
+        """Replace per-cell materials (and/or ``dV``) without rebuilding the tiling."""
+        npdt = _lib.np_dtype(self.dtype)
+        arrs = {}
+        if dV is not None:
+            self.region.dV = np.ascontiguousarray(dV, dtype=npdt).reshape(self.region.dV.shape)
+            arrs["dV"] = self.region.dV
+        for k, v in materials.items():
+            if k not in self.MATERIAL_NAMES:
+                raise KeyError(f"{type(self).__name__} has no material {k!r}")
+            setattr(self.materials, k, np.ascontiguousarray(v, dtype=npdt))
+            arrs[k] = getattr(self.materials, k)
+        _lib.check(
+            _lib.lib().apl_fem_set_materials(
+                self._handle, _lib.host_ptr(arrs.get("dV")), _lib.host_ptr(arrs.get("mu")),
+                _lib.host_ptr(arrs.get("lambda_")), _lib.host_ptr(arrs.get("activation")),
+            )
+        )
+
+    # ---- operators ----
+    def eval(self, ops: int, u, p=None, *, fun=None, quad=None, grad=None, diag=None, prod=None, scatter=None) -> None:
+        ld_in = _lib.field_ld(u, self.n_points, self.dtype, "u")
+        if ops & (_lib.OP_HESS_PROD | _lib.OP_HESS_QUAD):
+            if p is None or _lib.field_ld(p, self.n_points, self.dtype, "p") != ld_in:
+                raise ValueError("p must be given with the same layout as u for hess_prod / hess_quad")
+        ld_out = None
+        for name, out, bit in (("grad", grad, _lib.OP_GRAD), ("diag", diag, _lib.OP_HESS_DIAG), ("prod", prod, _lib.OP_HESS_PROD)):
+            if ops & bit:
+                ld = _lib.field_ld(out, self.n_points, self.dtype, name)
+                if ld_out is not None and ld != ld_out:
+                    raise ValueError("all output fields of one call must share a layout")
+                ld_out = ld
+        for name, out, bit in (("fun", fun, _lib.OP_FUN), ("quad", quad, _lib.OP_HESS_QUAD)):
+            if ops & bit and (out is None or out.dtype != self.dtype or out.numel() < 1):
+                raise ValueError(f"{name}: expected a ({self.dtype}) tensor with one element")
+        if scatter is None:
+            scatter = self.scatter if self.scatter is not None else config.scatter
+        with torch.cuda.device(self.device):
+            _lib.check(
+                _lib.lib().apl_fem_eval(
+                    self._handle, ops, _lib.dev_ptr(u), _lib.dev_ptr(p), ld_in, _lib.dev_ptr(fun), _lib.dev_ptr(quad),
+                    _lib.dev_ptr(grad), _lib.dev_ptr(diag), _lib.dev_ptr(prod), ld_out or 3, scatter,
+                    _lib.stream_ptr(self.device),
+                )
+            )
+
+    def fun(self, u, output) -> None:  # _base.py:151-158
+        self.eval(_lib.OP_FUN, u, fun=output)
+
+    def grad(self, u, output) -> None:  # _base.py:160-167
+        self.eval(_lib.OP_GRAD, u, grad=output)
+
+    def hess_diag(self, u, output) -> None:  # _base.py:169-176
+        self.eval(_lib.OP_HESS_DIAG, u, diag=output)
+
+    def hess_prod(self, u, p, output) -> None:  # _base.py:178-185
+        self.eval(_lib.OP_HESS_PROD, u, p, prod=output)
+
+    def hess_quad(self, u, p, output) -> None:  # _base.py:187-194
+        self.eval(_lib.OP_HESS_QUAD, u, p, quad=output)

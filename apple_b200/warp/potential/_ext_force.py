@@ -1,0 +1,64 @@
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from apple_b200 import _lib, config
+from apple_b200.common import FORCE, GLOBAL_POINT_ID
+from apple_b200.warp.model import WarpPotential
+
+
+class ExternalForce(WarpPotential):
+    """W = -sum_k f_k . u[idx_k]; grad[idx_k] -= f_k; zero Hessian.
+    Mirror of ``warp/potential/_ext_force.py:42-90``."""
+
+    def __init__(self, indices, force, *, dtype=None, device=None, name=None):
+        super().__init__(name=name)
+        self.dtype = dtype or config.default_dtype
+        self.device = torch.device(device if device is not None else config.default_device())
+        if self.device.type != "cuda":
+            raise _lib.NativeError("apple_b200 potentials live on a CUDA device (there is no CPU path)")
+        self.indices = torch.as_tensor(np.asarray(indices, dtype=np.int32), device=self.device).contiguous()
+        self.materials = SimpleNamespace(
+            force=torch.as_tensor(np.asarray(force, dtype=_lib.np_dtype(self.dtype)), device=self.device).contiguous()
+        )
+        if self.materials.force.shape != (self.indices.shape[0], 3):
+            raise ValueError("force must have shape (len(indices), 3)")
+
+    @classmethod
+    def from_pyvista(cls, obj, **kwargs):  # :55-61
+        force = np.asarray(obj.point_data[FORCE.vtk])
+        indices = np.asarray(obj.point_data[GLOBAL_POINT_ID.vtk])
+        return cls(indices, force, **kwargs)
+
+    def eval(self, ops: int, u, p=None, *, fun=None, quad=None, grad=None, diag=None, prod=None, scatter=None) -> None:
+        ops &= _lib.OP_FUN | _lib.OP_GRAD  # Hessian operators are no-ops (:80-90)
+        if not ops:
+            return
+        ld_in = int(u.shape[1])
+        ld_out = int(grad.shape[1]) if (ops & _lib.OP_GRAD) else 3
+        with torch.cuda.device(self.device):
+            _lib.check(
+                _lib.lib().apl_ext_force_eval(
+                    _lib.dtype_code(self.dtype), ops, self.indices.shape[0], _lib.dev_ptr(self.materials.force),
+                    _lib.dev_ptr(self.indices), _lib.dev_ptr(u), ld_in, _lib.dev_ptr(fun) if ops & _lib.OP_FUN else None,
+                    _lib.dev_ptr(grad) if ops & _lib.OP_GRAD else None, ld_out, _lib.stream_ptr(self.device),
+                )
+            )
+
+    def fun(self, u, output) -> None:  # :63-70
+        self.eval(_lib.OP_FUN, u, fun=output)
+
+    def grad(self, u, output) -> None:  # :72-78
+        self.eval(_lib.OP_GRAD, u, grad=output)
+
+    def hess_diag(self, u, output) -> None:  # :80-82
+        pass
+
+    def hess_prod(self, u, p, output) -> None:  # :84-86
+        pass
+
+    def hess_quad(self, u, p, output) -> None:  # :88-90
+        pass

@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""Benchmark of the FEM-elasticity hot path (see BASELINE.json / DESIGN.md section "Measurement").
+
+Workload (N = 1): BASELINE.json configs[1] -- synthetic 58^3 x 5 = 975,560-tet cube, Stable
+Neo-Hookean + ARAP on the same mesh, fp32.  One *step* = one fused energy + gradient +
+Hessian-vector-product evaluation of the whole model (every potential, one pass each).
+
+  value      tets/s, inputs resident in HBM, L2 flushed between timed steps
+  e2e        same metric through WarpModelAdapter.fun_grad_hess_prod with HOST (pinned) u, p:
+             H2D copies, kernels, D2H of energy + gradient + HVP inside the timed region
+  roofline   dominant kernel: algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
+  pncg       200 fused PNCG iterations on the same model (iterations/s)
+  cpu_baseline  the oracle (numpy restatement of the reference) on a bounded sample, host cores
+
+`--impl reference` times the CPU restatement of the reference (the reference itself needs Warp/JAX,
+which are not installable here) on the same workload definition.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "tets_per_s_fused_energy_grad_hvp"
+UNIT = "tets/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=58, help="hexes per cube edge (5 tets per hex)")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--scatter", default="tile", choices=["tile", "atomic"])
+    ap.add_argument("--potentials", default="snh,arap")
+    ap.add_argument("--pncg-iters", type=int, default=200)
+    ap.add_argument("--no-pncg", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="also time every operator / variant (stderr table)")
+    return ap.parse_args()
+
+
+def build_mesh(n, seed=0):
+    from apple_b200.common import lame_converter
+    from apple_b200.mesh import cube_tet_mesh
+
+    mesh = cube_tet_mesh(n, morton=True)
+    rng = np.random.default_rng(seed)
+    T = mesh.n_cells
+    E = 10.0 ** rng.uniform(4.0, 5.0, T)
+    nu = rng.uniform(0.3, 0.45, T)
+    la, mu = lame_converter(E, nu)
+    mesh.cell_data["mu"] = mu
+    mesh.cell_data["lambda"] = la
+    h = 1.0 / n
+    X = mesh.points
+    u = 0.05 * h * np.sin(7.0 * X[:, [1, 2, 0]] + 0.3) + 0.02 * h * rng.uniform(-1, 1, X.shape)
+    p = rng.uniform(-1, 1, X.shape)
+    return mesh, u, p
+
+
+def algorithmic_bytes_per_tet(kind, w, v_over_t, per_vertex_words):
+    m = {"snh": 2, "arap": 1, "muscle": 8}[kind]
+    return 16 + 9 * w + w + m * w + v_over_t * per_vertex_words * w
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self._stop, self.index = [], threading.Event(), index
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            if len(s) < 9:
+                continue
+            try:
+                sm.append(float(s[1])); mx = max(mx, float(s[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------ reference arm
+
+
+def oracle_model(mesh, kinds, n_tets=None):
+    from helpers import oracle_potential
+    from apple_b200.mesh import TetMesh
+    from oracle import fem as ofem
+
+    if n_tets is not None and n_tets < mesh.n_cells:
+        sub = TetMesh(mesh.points, mesh.cells[:n_tets], cell_data={k: v[:n_tets] for k, v in mesh.cell_data.items()})
+    else:
+        sub = mesh
+    pots = [oracle_potential(k, sub) for k in kinds]
+    return ofem.Model(pots, mesh.n_points), sub.n_cells
+
+
+def time_oracle(mesh, u, p, kinds, sample_tets, steps, warmup):
+    model, T = oracle_model(mesh, kinds, sample_tets)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        model.fun(u); model.grad(u); model.hess_prod(u, p)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return T * len(times) / sum(times), T, float(np.mean(times))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kinds = args.potentials.split(",")
+    mesh, u, p = build_mesh(args.n)
+    sample = min(mesh.n_cells, 60_000)
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    value, T, dt = time_oracle(mesh, u, p, kinds, sample, steps, warmup)
+    cores = 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"cube {args.n}^3x5 = {mesh.n_cells} tets, {'+'.join(kinds)}, fused energy+grad+HVP",
+                   "note": "CPU restatement of the reference (oracle/, numpy fp64); Warp/JAX not installable here"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"first {T} tets of the Morton-ordered mesh, {steps} evaluations"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+
+    from apple_b200 import _lib, config
+    from apple_b200.mesh import TetMesh
+    from apple_b200.warp.model import WarpModel, WarpModelAdapter
+    from helpers import cuda_potential
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.float32 if args.dtype == "f32" else torch.float64
+    w = 4 if args.dtype == "f32" else 8
+    config.scatter = _lib.SCATTER_TILE if args.scatter == "tile" else _lib.SCATTER_ATOMIC
+    kinds = args.potentials.split(",")
+
+    mesh, u, p = build_mesh(args.n)
+    T_total, V = mesh.n_cells, mesh.n_points
+    # strong scaling: rank r owns a contiguous chunk of the Morton-ordered tets
+    lo, hi = rank * T_total // world, (rank + 1) * T_total // world
+    shard = mesh if world == 1 else TetMesh(mesh.points, mesh.cells[lo:hi],
+                                            cell_data={k: v[lo:hi] for k, v in mesh.cell_data.items()})
+    pots = {k: cuda_potential(k, shard, dtype, name=k) for k in kinds}
+    model = WarpModel(pots)
+    adapter = WarpModelAdapter(model, n_points=V)
+    ud = torch.as_tensor(u, dtype=dtype, device=dev).contiguous()
+    pd = torch.as_tensor(p, dtype=dtype, device=dev).contiguous()
+    fun = torch.zeros(1, dtype=dtype, device=dev)
+    grad = torch.zeros((V, 3), dtype=dtype, device=dev)
+    prod = torch.zeros((V, 3), dtype=dtype, device=dev)
+    OPS = _lib.OP_FUN | _lib.OP_GRAD | _lib.OP_HESS_PROD
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def flush():
+        if not args.no_flush:
+            flush_buf.fill_(1)
+
+    def step():
+        model.eval(OPS, ud, pd, fun=fun, grad=grad, prod=prod)
+        if world > 1:  # halo sum (v0: dense all-reduce of the nodal fields) + scalar all-reduce
+            dist.all_reduce(grad); dist.all_reduce(prod); dist.all_reduce(fun)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        flush(); step()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        for a, b in ev:
+            flush()
+            a.record(); step(); b.record()
+        barrier()
+    t_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_ms = float(t.item())
+    ms_per_step = t_ms / args.steps
+    value = T_total * args.steps / (t_ms * 1e-3)
+
+    # ---- per-kernel roofline (each potential's fused kernel timed alone, L2 flushed) ----
+    peak, peak_src = measured_peak_gbs()
+    v_over_t = V / T_total
+    kern = {}
+    for k, pot in pots.items():
+        ts = []
+        for _ in range(max(5, min(args.steps, 20))):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); pot.eval(OPS, ud, pd, fun=fun, grad=grad, prod=prod); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        dt = float(np.mean(ts)) * 1e-3
+        bpt = algorithmic_bytes_per_tet(k, w, v_over_t, 12)
+        kern[k] = {"ms": dt * 1e3, "bytes_per_tet": bpt, "gbs": bpt * (hi - lo) / dt / 1e9,
+                   "gtets_per_s": (hi - lo) / dt / 1e9}
+    dom = max(kern, key=lambda k: kern[k]["ms"])
+    roofline = {"bound": "hbm", "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kern[dom]["gbs"] / peak, "traffic": None, "kernel": f"fem_tile_kernel<{args.dtype},{dom},fun|grad|hess_prod>",
+                "peak_source": peak_src, "frac_of_nominal_8TBs": kern[dom]["gbs"] / 8000.0, "per_kernel": kern}
+
+    # ---- e2e: host buffers through the public adapter API ----
+    e2e = None
+    if world == 1:
+        uh = torch.as_tensor(u, dtype=dtype).pin_memory()
+        ph = torch.as_tensor(p, dtype=dtype).pin_memory()
+        gh = torch.empty((V, 3), dtype=dtype).pin_memory()
+        hh = torch.empty((V, 3), dtype=dtype).pin_memory()
+        fh = torch.empty(1, dtype=dtype).pin_memory()
+
+        def e2e_step():
+            u_d = uh.to(dev, non_blocking=True); p_d = ph.to(dev, non_blocking=True)
+            f, g, h = adapter.fun_grad_hess_prod(u_d, p_d)
+            fh.copy_(f.reshape(1), non_blocking=True); gh.copy_(g, non_blocking=True); hh.copy_(h, non_blocking=True)
+
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize()
+        tt = 0.0
+        for _ in range(args.steps):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); e2e_step(); b.record()
+            torch.cuda.synchronize()
+            tt += a.elapsed_time(b)
+        e2e = {"value": T_total * args.steps / (tt * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(2 * V * 3 * w), "d2h_bytes_per_step": int(2 * V * 3 * w + w),
+               "ms_per_step": tt / args.steps}
+
+    # ---- PNCG iterations/s on the same model (config 1/2 style solve: fixed base, fused path) ----
+    pncg = None
+    if world == 1 and not args.no_pncg:
+        pncg = bench_pncg(args, mesh, pots, dtype, dev, w)
+
+    # ---- CPU baseline: the oracle on a bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, Ts, dt = time_oracle(mesh, u, p, kinds, min(T_total, 60_000), 3, 1)
+        cpu = {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"first {Ts} tets of the same mesh, 3 fused evaluations, numpy fp64 oracle"}
+
+    if args.sweep and rank == 0 and world == 1:
+        sweep(args, mesh, u, p, dtype, dev, flush)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"cube {args.n}^3x5 = {T_total} tets / {V} verts, {'+'.join(kinds)}, "
+                                   f"fused energy+grad+HVP ({args.scatter} assembly)",
+                       "l2": "256 MiB flush write between timed steps" if not args.no_flush else "no flush",
+                       "parallelism": f"{world} x Morton chunk of tets" if world > 1 else "1 GPU"},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": args.steps * len(pots),
+            "roofline": roofline, "cpu_baseline": cpu, "pncg": pncg,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_pncg(args, mesh, pots, dtype, dev, w):
+    import torch
+
+    from apple_b200.common import FIXED_MASK, FIXED_VALUE
+    from apple_b200.forward import Forward, ModelBuilder
+    from apple_b200.optim import PNCG
+    from apple_b200.optim.pncg import ConvergenceCriteria
+
+    V, T = mesh.n_points, mesh.n_cells
+    builder = ModelBuilder(dtype=dtype, device=dev)
+    builder.add_vertices(mesh)
+    fixed = np.zeros((V, 3), dtype=bool); fixed[mesh.points[:, 2] == 0.0] = True
+    mesh.point_data[FIXED_MASK.vtk] = fixed
+    mesh.point_data[FIXED_VALUE.vtk] = np.zeros((V, 3))
+    builder.add_fixed(mesh)
+    for pot in pots.values():
+        builder.add_potential(pot)
+    model = builder.finalize()
+    h = 1.0 / args.n
+    X = mesh.points
+    u0 = 0.05 * h * np.sin(7.0 * X[:, [1, 2, 0]] + 0.3)
+    u0[fixed] = 0.0
+    out = {}
+    for graph in (True, False):
+        iters = args.pncg_iters
+        crit = ConvergenceCriteria(max_steps=iters, target_relative_gradient_norm=0.0)
+        fwd = Forward(model, optimizer=PNCG(criteria=crit, check_every=iters, use_graph=graph))
+        fwd.state.u = torch.as_tensor(u0, dtype=dtype, device=dev)
+        # warm-up (graph capture, clocks), then the timed solve from the same start
+        warm = Forward(model, optimizer=PNCG(criteria=ConvergenceCriteria(max_steps=10, target_relative_gradient_norm=0.0),
+                                             check_every=10, use_graph=graph))
+        warm.state.u = torch.as_tensor(u0, dtype=dtype, device=dev)
+        warm.step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sol = fwd.step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        n_free = model.n_free
+        n_pots = len(pots)
+        per_tet = sum(16 + 9 * w + w + {"snh": 2, "arap": 1, "muscle": 8}[k] * w for k in pots)
+        alg = 2 * T * per_tet + n_pots * 15 * V * w + 8 * n_free * w
+        out["graph" if graph else "eager"] = {
+            "iters": sol.stats["n_steps"], "accepted": sol.stats["n_accepted"], "seconds": dt,
+            "iters_per_s": sol.stats["n_steps"] / dt, "energy": sol.stats["fun"],
+            "rel_grad_norm": sol.stats["relative_grad_norm"],
+            "algorithmic_gbs": alg * sol.stats["n_steps"] / dt / 1e9,
+        }
+    out["note"] = "wall clock incl. setup of the workspace and the initial pass; no L2 flush (iterations run back to back)"
+    return out
+
+
+def sweep(args, mesh, u, p, dtype, dev, flush):
+    """Per-operator / per-variant timings (stderr): evidence for the assembly-strategy choice."""
+    import torch
+
+    from apple_b200 import _lib
+    from helpers import cuda_potential
+
+    V, T = mesh.n_points, mesh.n_cells
+    rows = []
+    for dt_name, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        for kind in ("snh", "arap"):
+            pot = cuda_potential(kind, mesh, dt)
+            for ld in (3, 4):
+                ud = torch.zeros((V, ld), dtype=dt, device=dev); ud[:, :3] = torch.as_tensor(u, dtype=dt)
+                pd = torch.zeros((V, ld), dtype=dt, device=dev); pd[:, :3] = torch.as_tensor(p, dtype=dt)
+                outs = {k: torch.zeros((V, ld), dtype=dt, device=dev) for k in ("grad", "diag", "prod")}
+                fun = torch.zeros(1, dtype=dt, device=dev); quad = torch.zeros(1, dtype=dt, device=dev)
+                for ops in (1, 2, 4, 8, 16, 7, 11, 15):
+                    for scatter in (0, 1):
+                        ts = []
+                        for i in range(8):
+                            flush()
+                            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            a.record()
+                            pot.eval(ops, ud, pd, fun=fun, quad=quad, grad=outs["grad"], diag=outs["diag"],
+                                     prod=outs["prod"], scatter=scatter)
+                            b.record(); torch.cuda.synchronize()
+                            if i >= 2:
+                                ts.append(a.elapsed_time(b))
+                        ms = float(np.mean(ts))
+                        rows.append((dt_name, kind, ld, ops, "tile" if scatter == 0 else "atomic", ms, T / ms / 1e6))
+    print("dtype kind ld ops scatter ms Gtets/s", file=sys.stderr)
+    for r in rows:
+        print(f"{r[0]} {r[1]} {r[2]} {r[3]:2d} {r[4]:6s} {r[5]:8.4f} {r[6]:8.2f}", file=sys.stderr)
+
+
+if __name__ == "__main__":
+    main()

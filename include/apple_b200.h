@@ -1,0 +1,190 @@
+/* apple_b200 -- C ABI of the B200-native FEM-elasticity hot path.
+ *
+ * This is the drop-in boundary for liblaf/apple's Warp backend.  Every
+ * entry point names the reference interface it replaces; paths are relative to
+ * /root/reference/src/liblaf/apple.  Plain pointers and sizes only -- no torch, Warp or JAX types.
+ *
+ * Conventions
+ *  - Every function returns APL_OK (0) or a negative APL_ERR_* code; the message is available from
+ *    apl_last_error() (thread-local).  No exceptions cross the ABI, no call synchronises the host
+ *    with the device unless its comment says so.
+ *  - `dtype` selects fp32 / fp64 for every `void*` floating-point array of that call (the reference
+ *    is dtype-generic through the JAX x64 flag, warp/fem/_base.py:100-104).
+ *  - Nodal fields (u, p, grad, diag, prod) are device arrays of n_points rows with a leading
+ *    dimension `ld` of 3 (the reference's vec3 arrays) or 4 (16-byte padded rows; the 4th column is
+ *    ignored on input and receives +0 on output).  ld == 4 arrays must be 16-byte aligned.
+ *  - Operators ACCUMULATE into caller-zeroed outputs, exactly like WarpPotential
+ *    (warp/model/_potential.py:19-32; zeroing by the caller, warp/model/_model.py:14,19,24,29,34).
+ *  - Calls are stream-ordered on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *    stream).  A handle may be used from one host thread and one stream at a time.
+ *  - Device buffers passed in are owned by the caller; handles own only their packed mesh tables.
+ */
+#ifndef APPLE_B200_H
+#define APPLE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APL_OK 0
+#define APL_ERR_INVALID (-1)  /* bad argument */
+#define APL_ERR_CUDA (-2)     /* a CUDA runtime call failed (no device, OOM, launch error) */
+#define APL_ERR_MESH (-3)     /* mesh violates an assumption (index range, dhdX rows not summing to 0) */
+#define APL_ERR_STATE (-4)    /* handle not in a state that allows the call */
+
+#define APL_F32 0
+#define APL_F64 1
+
+/* energies: warp/fem/_stable_neo_hookean.py, warp/fem/_arap.py, warp/fem/_stable_neo_hookean_muscle.py */
+#define APL_KIND_SNH 0
+#define APL_KIND_ARAP 1
+#define APL_KIND_SNH_MUSCLE 2
+
+/* operator bit mask; any OR of these is evaluated in ONE pass over the elements */
+#define APL_OP_FUN 1        /* WarpPotentialFem.fun        warp/fem/_base.py:151-158, kernel :243-263 */
+#define APL_OP_GRAD 2       /* WarpPotentialFem.grad       warp/fem/_base.py:160-167, kernel :265-291 */
+#define APL_OP_HESS_DIAG 4  /* WarpPotentialFem.hess_diag  warp/fem/_base.py:169-176, kernel :293-324 */
+#define APL_OP_HESS_PROD 8  /* WarpPotentialFem.hess_prod  warp/fem/_base.py:178-185, kernel :326-351 */
+#define APL_OP_HESS_QUAD 16 /* WarpPotentialFem.hess_quad  warp/fem/_base.py:187-194, kernel :353-383 */
+
+/* assembly strategy */
+#define APL_SCATTER_TILE 0   /* shared-memory tile gather, in-tile slot reduction, one RED per tile vertex */
+#define APL_SCATTER_ATOMIC 1 /* one thread per tet, direct gathers and 12 REDs per field (reference-like) */
+
+typedef struct apl_fem apl_fem_t;   /* one FEM potential: replaces WarpPotentialFem (warp/fem/_base.py:39) */
+typedef struct apl_pncg apl_pncg_t; /* fused PNCG workspace (liblaf.peach.optim.PNCG, external to the reference) */
+
+int apl_version(void);
+const char* apl_last_error(void);
+/* number of CUDA devices visible, or a negative error code (never throws; usable as a probe) */
+int apl_device_count(void);
+
+/* ---- setup: replaces WarpPotentialFem.from_region (warp/fem/_base.py:93-111) ---------------------
+ * HOST arrays in the reference's own layout:
+ *   cells   int32  (n_cells,4)   region.cells_global
+ *   dhdX    dtype  (n_cells,4,3) region.dhdX[:,0]      (rows must sum to zero: linear tetrahedra)
+ *   dV      dtype  (n_cells,)    Fraction * region.dV[:,0]
+ *   mu, lambda_ dtype (n_cells,) materials (lambda_ ignored for ARAP, may be NULL)
+ *   activation dtype (n_cells,6) SNH-muscle only (warp/fem/func/_misc.py:46-53 ordering), else NULL
+ *   points  double (n_points,3)  optional rest positions, used only to order the tets along a Morton
+ *                                curve; NULL keeps the given cell order
+ * The tets are packed into tiles of <= 256 tets touching <= 256 distinct vertices, static data is
+ * stored as planes of 16-byte vectors, and everything is uploaded to `device`.
+ * device = -1 builds the host tables only (no CUDA call; for inspection and CPU tests). */
+int apl_fem_create(int kind, int dtype, int64_t n_cells, int64_t n_points, const int32_t* cells,
+                   const void* dhdX, const void* dV, const void* mu, const void* lambda_,
+                   const void* activation, const double* points, int device, apl_fem_t** out);
+void apl_fem_destroy(apl_fem_t* fem);
+
+/* info[0..7] = n_cells, n_points, n_tiles, sum of tile vertex counts, static device bytes,
+ *              kind, dtype, device */
+int apl_fem_info(const apl_fem_t* fem, int64_t info[8]);
+
+/* Copies of the host tables (sizes from apl_fem_info); any pointer may be NULL.
+ *   tiles      int32 (n_tiles,4): tet_start, n_tets, vert_start, n_verts
+ *   order      int64 (n_cells,)  : packed position -> caller's cell index
+ *   conn       uint8 (n_cells,4) : tile-local vertex id per corner (packed order)
+ *   slots      uint16(n_cells,4) : in-tile reduction slot per corner (packed order)
+ *   tile_verts int32 (sum verts) : global vertex id per tile-local id
+ *   tile_voff  uint16(sum verts + n_tiles): per tile, n_verts+1 slot offsets */
+int apl_fem_host_tables(const apl_fem_t* fem, int32_t* tiles, int64_t* order, uint8_t* conn,
+                        uint16_t* slots, int32_t* tile_verts, uint16_t* tile_voff);
+
+/* Replace per-cell materials in place (HOST arrays in the caller's cell order; NULL = keep).
+ * Replaces re-creating the Materials struct (warp/fem/utils/_material.py:15-31). */
+int apl_fem_set_materials(apl_fem_t* fem, const void* dV, const void* mu, const void* lambda_,
+                          const void* activation);
+
+/* ---- the operators: replace the wp.launch calls at warp/fem/_base.py:151-194 ---------------------
+ * ops   OR of APL_OP_*; everything requested is computed in one pass over the elements.
+ * u, p  device nodal fields with leading dimension ld_in (p may be NULL unless HESS_PROD/HESS_QUAD).
+ * fun, quad          device scalars (dtype[1]);      fun += sum Psi dV,  quad += sum max(p.Hp dV, 0)
+ * grad, diag, prod   device nodal fields, ld_out;    accumulated (diag clamped >= 0 per entry and cell)
+ * Outputs whose op bit is not set are ignored (may be NULL). */
+int apl_fem_eval(apl_fem_t* fem, int ops, const void* u, const void* p, int ld_in, void* fun,
+                 void* quad, void* grad, void* diag, void* prod, int ld_out, int scatter,
+                 void* stream);
+
+/* ---- ExternalForce: replaces warp/potential/_ext_force.py:17-39 ------------------------------------
+ * force dtype (k,3) and indices int32 (k,) are DEVICE arrays.  ops may contain FUN and/or GRAD:
+ *   fun[0] -= sum_k force_k . u[indices_k]        grad[indices_k] -= force_k                     */
+int apl_ext_force_eval(int dtype, int ops, int64_t k, const void* force, const int32_t* indices,
+                       const void* u, int ld_in, void* fun, void* grad, int ld_out, void* stream);
+
+/* ---- nodal-field helpers --------------------------------------------------------------------------
+ * dst(n,ld_dst) = src(n,ld_src) for the first 3 columns; padding columns of dst are zeroed. */
+int apl_field_copy(int dtype, int64_t n, const void* src, int ld_src, void* dst, int ld_dst,
+                   void* stream);
+
+/* ---- fused PNCG workspace -------------------------------------------------------------------------
+ * The optimizer the reference uses (liblaf.peach.optim.PNCG) is external to /root/reference; what is
+ * restated here are the recurrences of the reference's own PNCG-like benchmark,
+ * benches/bench_pncg_branching_backends.py:254-329,407-410,606-610,663-679, with the problem glue of
+ * forward/_problem.py:24-59 folded in (fixed DOFs are masked, not gathered/scattered).
+ *
+ * All vectors are DEVICE arrays of n_points rows x 4 columns (16-byte rows, 4th column unused),
+ * allocated and owned by the caller: x, two direction buffers p0/p1, two gradient buffers g0/g1, two
+ * Hessian-diagonal buffers d0/d1.  `mask` is uint8 (n_points,4): bit 0 = free DOF, bit 1 = counted in
+ * reductions (clear on ghost copies when a mesh is sharded).  `scal` is a device array of
+ * APL_PNCG_NSCAL doubles holding every scalar of the iteration; the host never has to read it
+ * between iterations.  Buffer roles (current / trial, current / previous) flip every iteration;
+ * apl_pncg_current() tells which index is current (always scal[APL_S_K] % 2). */
+#define APL_PNCG_NSCAL 96
+#define APL_S_F 0            /* energy at the current iterate */
+#define APL_S_F_PREV 1       /* energy before the last accepted step */
+#define APL_S_GP 2           /* g . p */
+#define APL_S_PHP 3          /* hess_quad(x, p) */
+#define APL_S_ALPHA 4        /* step length of the last iteration */
+#define APL_S_BETA 5
+#define APL_S_GNORM2 6       /* |g|^2 over free DOFs at the start of the last iteration */
+#define APL_S_GNORM2_FIRST 7
+#define APL_S_ACCEPTED 8     /* 1 if the last line search accepted a trial point */
+#define APL_S_LS_STEPS 9     /* halvings used by the last line search */
+#define APL_S_K 10           /* iterations performed */
+#define APL_S_N_ACCEPTED 11
+#define APL_S_DIAG_MEAN 12   /* mean of the positive |hess_diag| entries */
+#define APL_S_GPG 13         /* g . P g */
+#define APL_S_DONE 15        /* 0 running, 1 gradient criterion met, 2 max_steps, 3 stagnation, 4 non-finite */
+#define APL_S_FAILS 16       /* consecutive failed line searches */
+#define APL_S_F_NEW 17
+#define APL_S_SUMS 20        /* 11 reduction results of APL_PHASE_REDUCE */
+#define APL_S_ALPHA_J 32     /* per-trial step lengths      [16] */
+#define APL_S_ACC_J 48       /* per-trial line-search state [16]: 1 accepted, 0 live, -1 gave up */
+#define APL_S_FT_J 64        /* per-trial energies          [16] */
+
+#define APL_PHASE_INIT 0      /* f, g, diag at x; resets scal and the buffer roles */
+#define APL_PHASE_REDUCE 1    /* 11 masked sums over (g, g_prev, diag, p_prev) -> scal[APL_S_SUMS..] */
+#define APL_PHASE_FINALIZE 2  /* termination tests, Dai-Kou beta, descent guard */
+#define APL_PHASE_DIRECTION 3 /* p = -P g + beta p_prev; scal[GP]; zero the trial buffers */
+#define APL_PHASE_PASS_B 4    /* scal[PHP] += hess_quad(x, p) over the registered potentials */
+#define APL_PHASE_ALPHA 5     /* alpha_0 */
+#define APL_PHASE_TRIAL 6     /* (j) f', g', diag' at x + alpha_j p (skipped once accepted) */
+#define APL_PHASE_LS 7        /* (j) Armijo test of trial j; halve and re-zero on failure */
+#define APL_PHASE_COMMIT 8    /* x += alpha p or restore g', diag'; k += 1 */
+
+int apl_pncg_create(int dtype, int64_t n_points, int device, void* x, void* p0, void* p1, void* g0,
+                    void* g1, void* d0, void* d1, const uint8_t* mask, double* scal, apl_pncg_t** out);
+void apl_pncg_destroy(apl_pncg_t* ws);
+/* potentials summed by the workspace's passes (WarpModel, warp/model/_model.py:9-36) */
+int apl_pncg_add_fem(apl_pncg_t* ws, apl_fem_t* fem);
+int apl_pncg_add_ext_force(apl_pncg_t* ws, int64_t k, const void* force, const int32_t* indices);
+/* max_steps: iteration budget (forward/_forward.py:26-27); rtol_g / atol_g: stop when
+ * |g| <= rtol_g |g_0| or |g| <= atol_g; max_fails: consecutive failed line searches tolerated;
+ * overstep, max_step, c1, max_halvings: line search (bench :606-610, :413-456; _problem.py:29-34);
+ * scatter: APL_SCATTER_*; use_graph: replay each iteration as a CUDA graph. */
+int apl_pncg_set_params(apl_pncg_t* ws, double max_steps, double rtol_g, double atol_g, double max_fails,
+                        double overstep, double max_step, double c1, int max_halvings, int scatter,
+                        int use_graph);
+int apl_pncg_current(const apl_pncg_t* ws);
+int apl_pncg_flip(apl_pncg_t* ws);
+/* Enqueue one phase (for callers that interleave collectives between phases: sharded meshes). */
+int apl_pncg_phase(apl_pncg_t* ws, int phase, int j, void* stream);
+/* Enqueue n_iters complete iterations (phases 1..8 and the role flip); never synchronises. */
+int apl_pncg_iterate(apl_pncg_t* ws, int n_iters, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APPLE_B200_H */

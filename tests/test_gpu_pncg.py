@@ -1,0 +1,159 @@
+"""GPU: the reference's known-answer test re-hosted, and PNCG solves against the oracle."""
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_case, oracle_potential, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _kat_model(dtype, **pncg_kw):
+    from apple_b200.common import FIXED_MASK, FIXED_VALUE, MU
+    from apple_b200.forward import Forward, ModelBuilder
+    from apple_b200.mesh import embedded_tetra_mesh
+    from apple_b200.optim import PNCG
+    from apple_b200.warp.fem import Arap
+
+    mesh = embedded_tetra_mesh()
+    mesh.cell_data[MU.vtk] = np.ones(mesh.n_cells)
+    builder = ModelBuilder()
+    builder.add_vertices(mesh)
+    fixed_mask = np.zeros((mesh.n_points, 3), dtype=bool)
+    fixed_value = np.zeros((mesh.n_points, 3))
+    fixed_mask[:4, :] = True
+    fixed_value[3] = np.array([0.2, -0.1, 0.15])
+    mesh.point_data[FIXED_MASK.vtk] = fixed_mask
+    mesh.point_data[FIXED_VALUE.vtk] = fixed_value
+    builder.add_fixed(mesh)
+    builder.add_potential(Arap.from_pyvista(mesh, dtype=dtype))
+    model = builder.finalize()
+    optimizer = PNCG(**pncg_kw) if pncg_kw else None
+    return model, Forward(model, optimizer=optimizer), fixed_value
+
+
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "generic"])
+def test_forward_static_simulation_end_to_end(native_lib, fused):
+    """tests/forward/test_static_simulation.py:58-93 of the reference, same asserts (fp64)."""
+    model, forward, fixed_value = _kat_model(torch.float64, fused=fused)
+    initial_energy = float(forward.problem.fun(forward.state))
+    solution = forward.step()
+    final_energy = float(forward.problem.fun(forward.state))
+
+    assert solution.result.name == "PRIMARY_SUCCESS"
+    assert solution.stats["fused"] == fused
+    assert model.n_free == 3
+    assert np.isfinite(initial_energy)
+    assert np.isfinite(final_energy)
+    assert final_energy < initial_energy
+    # derived goldens
+    assert abs(initial_energy - 0.010475610401894953) < 1e-14
+    assert abs(final_energy - 0.004108894646378555) < 1e-12
+
+    u_full = forward.state.u.cpu().numpy()
+    np.testing.assert_allclose(u_full[:4], fixed_value[:4])
+    np.testing.assert_allclose(u_full[4], [0.05, -0.025, 0.0375], atol=1e-8)
+
+
+def test_stepping_protocol_and_state_fields(native_lib):
+    """init / step / terminate / postprocess with the state fields the reference's drivers log."""
+    from apple_b200.optim import Result
+
+    model, forward, _ = _kat_model(torch.float64)
+    problem, state = forward.problem, forward.state
+    opt_state = forward.optimizer.init(problem, state, forward.free)
+    result = Result.UNKNOWN_ERROR
+    energies = []
+    for _ in range(100):
+        state, opt_state = forward.optimizer.step(problem, state, opt_state)
+        ls, cs, hd = opt_state.line_search_state, opt_state.convergence_state, opt_state.hess_damping_state
+        assert np.isfinite(ls.alpha) and np.isfinite(ls.f_alpha) and isinstance(ls.ok, bool)
+        assert cs.grad_norm_first > 0 and hd.hess_diag_mean > 0
+        assert opt_state.direction.shape == (3,)
+        energies.append(ls.f_alpha)
+        done, result = forward.optimizer.terminate(problem, state, opt_state)
+        if done:
+            break
+    solution = forward.optimizer.postprocess(problem, state, opt_state, result)
+    assert solution.success and result is Result.PRIMARY_SUCCESS
+    assert all(b <= a + 1e-15 for a, b in zip(energies, energies[1:]))  # monotone energy
+
+
+def _cube_problem(dtype, n=8, kinds=("snh",), gravity=True):
+    from apple_b200.common import FIXED_MASK, FIXED_VALUE
+    from apple_b200.forward import ModelBuilder
+    from apple_b200.mesh import lumped_vertex_volume
+    from apple_b200.warp.fem import Arap, StableNeoHookean
+    from apple_b200.warp.potential import ExternalForce
+    from oracle import fem as ofem, pncg as opncg, region as oregion
+
+    mesh, _, _ = make_case(n=n, seed=11, grading=1.0)
+    mesh.cell_data.pop("Fraction")
+    V = mesh.n_points
+    builder = ModelBuilder()
+    builder.add_vertices(mesh)
+    fixed = np.zeros((V, 3), dtype=bool); fixed[mesh.points[:, 2] == 0.0] = True
+    mesh.point_data[FIXED_MASK.vtk] = fixed
+    mesh.point_data[FIXED_VALUE.vtk] = np.zeros((V, 3))
+    builder.add_fixed(mesh)
+    cls = {"snh": StableNeoHookean, "arap": Arap}
+    opots = []
+    for k in kinds:
+        builder.add_potential(cls[k].from_pyvista(mesh, dtype=dtype, name=k))
+        opots.append(oracle_potential(k, mesh))
+    if gravity:
+        idx = np.flatnonzero(~fixed[:, 0])
+        force = np.zeros((idx.size, 3)); force[:, 0] = 40.0 * lumped_vertex_volume(mesh)[idx]
+        builder.add_potential(ExternalForce(idx, force, dtype=dtype, name="gravity"))
+        opots.append(ofem.ExternalForce(force, idx))
+    model = builder.finalize()
+    oproblem = opncg.ForwardProblem(ofem.Model(opots, V), oregion.DofMap(fixed, np.zeros((V, 3))))
+    return model, oproblem
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-8), (torch.float32, 1e-4)], ids=["f64", "f32"])
+def test_fixed_iteration_count_matches_oracle(native_lib, dtype, tol):
+    """Config-1 style solve (SNH cube, fixed base, body force): displacements after a fixed number
+    of PNCG iterations agree with the oracle's PNCG within 1e-4 relative (north star)."""
+    from apple_b200.forward import Forward
+    from apple_b200.optim import PNCG
+    from apple_b200.optim.pncg import ConvergenceCriteria
+    from oracle import pncg as opncg
+
+    model, oproblem = _cube_problem(dtype)
+    iters = 40
+    crit = ConvergenceCriteria(max_steps=iters, target_relative_gradient_norm=0.0)
+    forward = Forward(model, optimizer=PNCG(criteria=crit, check_every=8))
+    solution = forward.step()
+    assert solution.stats["n_steps"] == iters and solution.stats["fused"]
+    x_ref, info = opncg.minimize(oproblem, np.zeros(oproblem.dof_map.n_free), max_steps=iters)
+    u_ref = oproblem.dof_map.to_full(x_ref)
+    assert rel_err(forward.state.u.cpu(), u_ref) < tol
+    assert rel_err(solution.stats["fun"], info["fun"]) < 10 * tol
+    assert solution.stats["n_accepted"] == info["n_accepted"]
+
+
+def test_generic_and_fused_paths_agree(native_lib):
+    from apple_b200.forward import Forward
+    from apple_b200.optim import PNCG
+    from apple_b200.optim.pncg import ConvergenceCriteria
+
+    model, _ = _cube_problem(torch.float64, n=5, kinds=("snh", "arap"))
+    crit = ConvergenceCriteria(max_steps=25, target_relative_gradient_norm=0.0)
+    a = Forward(model, optimizer=PNCG(criteria=crit, fused=True)); a.step()
+    b = Forward(model, optimizer=PNCG(criteria=crit, fused=False)); b.step()
+    assert rel_err(a.state.u.cpu(), b.state.u.cpu()) < 1e-9
+
+
+def test_graph_replay_equals_eager_launches(native_lib):
+    from apple_b200.forward import Forward
+    from apple_b200.optim import PNCG
+    from apple_b200.optim.pncg import ConvergenceCriteria
+
+    model, _ = _cube_problem(torch.float32, n=6)
+    crit = ConvergenceCriteria(max_steps=30, target_relative_gradient_norm=0.0)
+    a = Forward(model, optimizer=PNCG(criteria=crit, use_graph=True, check_every=30)); sa = a.step()
+    b = Forward(model, optimizer=PNCG(criteria=crit, use_graph=False, check_every=7)); sb = b.step()
+    assert sa.stats["n_steps"] == sb.stats["n_steps"] == 30
+    assert rel_err(a.state.u.cpu(), b.state.u.cpu()) < 1e-4
