@@ -353,6 +353,7 @@ struct apl_pncg {
     struct Ext { const void* force; const int32_t* idx; int64_t k; };
     std::vector<Ext> exts;
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    cudaStream_t capture_stream = nullptr;  // graphs are captured here (the legacy stream cannot capture)
     bool use_graph = false;
 };
 
@@ -507,6 +508,7 @@ int apl_pncg_create(int dtype, int64_t n_points, int device, void* x, void* p0, 
 void apl_pncg_destroy(apl_pncg_t* w) {
     if (!w) return;
     drop_graphs(w);
+    if (w->capture_stream) cudaStreamDestroy(w->capture_stream);
     cudaFree(w->partials);
     cudaFree(w->counter);
     delete w;
@@ -564,9 +566,11 @@ int apl_pncg_iterate(apl_pncg_t* w, int n_iters, void* stream) {
             if (!w->graph[w->cur]) {
                 // capture one iteration for this buffer parity
                 cudaGraph_t graph = nullptr;
-                APL_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-                int rc = one_iteration(w, s);
-                cudaError_t e = cudaStreamEndCapture(s, &graph);
+                if (!w->capture_stream)
+                    APL_CUDA_CHECK(cudaStreamCreateWithFlags(&w->capture_stream, cudaStreamNonBlocking));
+                APL_CUDA_CHECK(cudaStreamBeginCapture(w->capture_stream, cudaStreamCaptureModeThreadLocal));
+                int rc = one_iteration(w, w->capture_stream);
+                cudaError_t e = cudaStreamEndCapture(w->capture_stream, &graph);
                 if (rc != APL_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
                 if (e != cudaSuccess) { set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e)); return APL_ERR_CUDA; }
                 e = cudaGraphInstantiate(&w->graph[w->cur], graph, 0);

@@ -25,26 +25,31 @@ class WarpModelAdapter:
         return torch.empty((self.n_points, 3), dtype=u.dtype, device=u.device)
 
     def fun(self, u: torch.Tensor) -> torch.Tensor:
+        u = u.contiguous()
         output = self._scalar(u)
         self.__wrapped__.fun(u, output)
         return output[0]
 
     def grad(self, u: torch.Tensor) -> torch.Tensor:
+        u = u.contiguous()
         output = self._field(u)
         self.__wrapped__.grad(u, output)
         return output
 
     def hess_diag(self, u: torch.Tensor) -> torch.Tensor:
+        u = u.contiguous()
         output = self._field(u)
         self.__wrapped__.hess_diag(u, output)
         return output
 
     def hess_prod(self, u: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
+        u, p = u.contiguous(), p.contiguous()
         output = self._field(u)
         self.__wrapped__.hess_prod(u, p, output)
         return output
 
     def hess_quad(self, u: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
+        u, p = u.contiguous(), p.contiguous()
         output = self._scalar(u)
         self.__wrapped__.hess_quad(u, p, output)
         return output[0]
@@ -52,6 +57,7 @@ class WarpModelAdapter:
     # ---- fused forms (one pass over the elements per potential) ----
     def fun_grad_hess_prod(self, u: torch.Tensor, p: torch.Tensor, *, scatter=None):
         """(energy, gradient, Hessian-vector product): the fused evaluation of the headline metric."""
+        u, p = u.contiguous(), p.contiguous()
         fun, grad, prod = self._scalar(u), self._field(u), self._field(u)
         self.__wrapped__.eval(
             _lib.OP_FUN | _lib.OP_GRAD | _lib.OP_HESS_PROD, u, p, fun=fun, grad=grad, prod=prod, scatter=scatter
@@ -60,6 +66,7 @@ class WarpModelAdapter:
 
     def fun_grad_hess_diag(self, u: torch.Tensor, *, scatter=None):
         """(energy, gradient, Hessian diagonal): PNCG's pass A."""
+        u = u.contiguous()
         fun, grad, diag = self._scalar(u), self._field(u), self._field(u)
         self.__wrapped__.eval(
             _lib.OP_FUN | _lib.OP_GRAD | _lib.OP_HESS_DIAG, u, None, fun=fun, grad=grad, diag=diag, scatter=scatter

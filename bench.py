@@ -71,7 +71,7 @@ def build_mesh(n, seed=0):
     X = mesh.points
     u = 0.05 * h * np.sin(7.0 * X[:, [1, 2, 0]] + 0.3) + 0.02 * h * rng.uniform(-1, 1, X.shape)
     p = rng.uniform(-1, 1, X.shape)
-    return mesh, u, p
+    return mesh, np.ascontiguousarray(u), np.ascontiguousarray(p)
 
 
 def algorithmic_bytes_per_tet(kind, w, v_over_t, per_vertex_words):
@@ -361,7 +361,7 @@ def bench_pncg(args, mesh, pots, dtype, dev, w):
     model = builder.finalize()
     h = 1.0 / args.n
     X = mesh.points
-    u0 = 0.05 * h * np.sin(7.0 * X[:, [1, 2, 0]] + 0.3)
+    u0 = np.ascontiguousarray(0.05 * h * np.sin(7.0 * X[:, [1, 2, 0]] + 0.3))
     u0[fixed] = 0.0
     out = {}
     for graph in (True, False):

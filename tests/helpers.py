@@ -31,7 +31,7 @@ def make_case(n=6, seed=0, *, grading=1.02, heterogeneous=True, amp=0.05, morton
     X = mesh.points
     u = amp * h * (np.sin(3.0 * X[:, [1, 2, 0]] + 0.3) + 0.5 * rng.uniform(-1, 1, (V, 3)))
     p = rng.uniform(-1, 1, (V, 3))
-    return mesh, u, p
+    return mesh, np.ascontiguousarray(u), np.ascontiguousarray(p)
 
 
 def oracle_potential(kind: str, mesh: TetMesh, dtype=np.float64):

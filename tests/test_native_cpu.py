@@ -1,0 +1,191 @@
+"""CPU: the native library loads and exports its ABI; host-side tiling; the per-tet math header
+compiled for the host against the oracle.  No CUDA call is made here."""
+
+import ctypes
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import KINDS, make_case, oracle_potential
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol(native_lib):
+    from apple_b200 import _lib
+
+    header = (ROOT / "include" / "apple_b200.h").read_text()
+    declared = set(re.findall(r"\b(apl_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(native_lib, name), name
+    assert native_lib.apl_version() >= 100
+
+
+def test_no_gpu_means_loud_failure(native_lib):
+    """On a machine without a GPU every product entry point must raise, never fall back."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from apple_b200 import NativeError
+    from apple_b200.mesh import embedded_tetra_mesh
+    from apple_b200.warp.fem import Arap
+
+    mesh = embedded_tetra_mesh()
+    mesh.cell_data["mu"] = np.ones(4)
+    with pytest.raises(NativeError):
+        Arap.from_pyvista(mesh)
+    assert native_lib.apl_device_count() < 0
+
+
+def _host_tables(native_lib, mesh, kind=0, with_points=True):
+    from apple_b200 import _lib
+    from oracle import region
+
+    dhdX, dV = region.compute_grad(mesh.points, mesh.cells)
+    T, V = mesh.n_cells, mesh.n_points
+    mu = np.ones(T); la = np.ones(T); act = np.zeros((T, 6))
+    h = ctypes.c_void_p()
+    P = _lib.host_ptr
+    cells = np.ascontiguousarray(mesh.cells, dtype=np.int32)
+    pts = np.ascontiguousarray(mesh.points) if with_points else None
+    rc = native_lib.apl_fem_create(kind, _lib.F64, T, V, P(cells), P(dhdX), P(dV), P(mu), P(la), P(act), P(pts), -1,
+                                   ctypes.byref(h))
+    assert rc == 0, native_lib.apl_last_error()
+    info = (ctypes.c_int64 * 8)()
+    native_lib.apl_fem_info(h, info)
+    nt, nv = info[2], info[3]
+    tiles = np.zeros((nt, 4), np.int32); order = np.zeros(T, np.int64)
+    conn = np.zeros((T, 4), np.uint8); slots = np.zeros((T, 4), np.uint16)
+    tv = np.zeros(nv, np.int32); voff = np.zeros(nv + nt, np.uint16)
+    native_lib.apl_fem_host_tables(h, P(tiles), P(order), P(conn), P(slots), P(tv), P(voff))
+    native_lib.apl_fem_destroy(h)
+    return tiles, order, conn, slots, tv, voff
+
+
+@pytest.mark.parametrize("with_points", [True, False])
+def test_tiling_invariants(native_lib, with_points):
+    mesh, _, _ = make_case(n=9, seed=0, morton=False)
+    tiles, order, conn, slots, tv, voff = _host_tables(native_lib, mesh, with_points=with_points)
+    T = mesh.n_cells
+    assert sorted(order.tolist()) == list(range(T))          # a permutation of the cells
+    if not with_points:
+        assert (order == np.arange(T)).all()                 # NULL points keeps the caller's order
+    assert tiles[:, 1].sum() == T and (tiles[:, 1] <= 256).all() and (tiles[:, 3] <= 256).all()
+    assert (tiles[1:, 0] == tiles[:-1, 0] + tiles[:-1, 1]).all()
+    for t, (ts, n, vs, nv) in enumerate(tiles):
+        gl = tv[vs:vs + nv]
+        assert (np.diff(gl) > 0).all()                       # sorted, distinct
+        assert np.array_equal(gl[conn[ts:ts + n]], mesh.cells[order[ts:ts + n]])   # connectivity round trip
+        off = voff[vs + t: vs + t + nv + 1].astype(int)
+        assert off[0] == 0 and off[-1] == 4 * n
+        s = slots[ts:ts + n].ravel().astype(int); l = conn[ts:ts + n].ravel().astype(int)
+        assert sorted(s.tolist()) == list(range(4 * n))      # every corner owns exactly one slot
+        assert ((s >= off[l]) & (s < off[l + 1])).all()      # ... inside its vertex's range
+
+
+def test_tiling_splits_on_vertex_budget(native_lib):
+    """Disconnected tets: 4 new vertices each, so a tile closes at 64 tets (256 vertices)."""
+    from apple_b200.mesh import TetMesh
+
+    n = 300
+    pts = np.random.default_rng(0).random((4 * n, 3))
+    mesh = TetMesh(pts, np.arange(4 * n).reshape(n, 4))
+    X = mesh.points[mesh.cells]
+    vol = np.einsum("ci,ci->c", np.cross(X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]), X[:, 3] - X[:, 0])
+    mesh.cells[vol < 0] = mesh.cells[vol < 0][:, [0, 2, 1, 3]]
+    tiles, *_ = _host_tables(native_lib, mesh, with_points=False)
+    assert (tiles[:, 3] <= 256).all() and (tiles[:-1, 1] == 64).all()
+
+
+def test_setup_rejects_bad_meshes(native_lib):
+    from apple_b200 import _lib
+    from oracle import region
+
+    mesh, _, _ = make_case(n=2, seed=0)
+    dhdX, dV = region.compute_grad(mesh.points, mesh.cells)
+    T, V = mesh.n_cells, mesh.n_points
+    ones = np.ones(T)
+    P = _lib.host_ptr
+    h = ctypes.c_void_p()
+    bad = mesh.cells.copy(); bad[3, 2] = V
+    assert native_lib.apl_fem_create(0, 1, T, V, P(bad), P(dhdX), P(dV), P(ones), P(ones), None, None, -1,
+                                     ctypes.byref(h)) == -3
+    assert b"outside" in native_lib.apl_last_error()
+    d2 = dhdX.copy(); d2[5, 0, 1] += 1.0
+    assert native_lib.apl_fem_create(0, 1, T, V, P(mesh.cells), P(d2), P(dV), P(ones), P(ones), None, None, -1,
+                                     ctypes.byref(h)) == -3
+    assert b"sum to zero" in native_lib.apl_last_error()
+    assert native_lib.apl_fem_create(2, 1, T, V, P(mesh.cells), P(dhdX), P(dV), P(ones), P(ones), None, None, -1,
+                                     ctypes.byref(h)) == -1  # muscle without activation
+
+
+@pytest.fixture(scope="module")
+def host_math(tmp_path_factory):
+    out = tmp_path_factory.mktemp("native") / "elem_host.so"
+    src = ROOT / "tests" / "native" / "elem_host.cpp"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(out), str(src)], check=True)
+    return ctypes.CDLL(str(out))
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-11), (np.float32, 2e-5)], ids=["f64", "f32"])
+@pytest.mark.parametrize("kind", KINDS)
+def test_per_tet_math_header_matches_oracle(host_math, kind, dtype, tol):
+    """apple_b200/csrc/elem_math.cuh (the code the kernels inline) == oracle, element by element."""
+    mesh, u, p = make_case(n=5, seed=2, amp=0.15)
+    ora = oracle_potential(kind, mesh)
+    T = mesh.n_cells
+    nrec = 18 if kind == "muscle" else 12
+    rec = np.zeros((T, nrec), dtype)
+    rec[:, :9] = ora.dhdX[:, 1:4].reshape(T, 9)
+    rec[:, 9] = ora.dV
+    rec[:, 10] = ora.materials["mu"]
+    if kind != "arap":
+        rec[:, 11] = ora.materials["lambda_"]
+    if kind == "muscle":
+        rec[:, 12:] = ora.materials["activation"]
+    uc = np.ascontiguousarray(u[mesh.cells], dtype); pc = np.ascontiguousarray(p[mesh.cells], dtype)
+    psi = np.zeros(T, dtype); quad = np.zeros(T, dtype)
+    g, dg, hp = (np.zeros((T, 4, 3), dtype) for _ in range(3))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    host_math.elem_eval_host(KINDS.index(kind), int(dtype == np.float64), T, P(rec), P(uc), P(pc), P(psi), P(quad),
+                             P(g), P(dg), P(hp))
+
+    def rel(a, b):
+        a = a.reshape(T, -1).astype(np.float64); b = b.reshape(T, -1)
+        return (np.abs(a - b).max(1) / np.abs(b).max(1)).max()
+
+    assert rel(g, ora.elem_grad(u)) < tol
+    assert rel(dg, ora.elem_hess_diag(u)) < tol
+    assert rel(hp, ora.elem_hess_prod(u, p)) < tol
+    e, q = ora.elem_fun(u), ora.elem_hess_quad(u, p)
+    assert np.abs(psi - e).max() < tol * np.abs(e).max() * 10
+    assert np.abs(quad - q).max() < tol * np.abs(q).max() * 10
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 5e-6)], ids=["f64", "f32"])
+def test_svd3_rotation_variant_convention(host_math, dtype, tol):
+    """U, V proper rotations, s0 >= s1 >= |s2|, sign(s2) = sign(det F), F == U diag(s) V^T."""
+    rng = np.random.default_rng(3)
+    n = 4000
+    F = np.eye(3)[None] + 0.5 * rng.standard_normal((n, 3, 3))
+    F[:50] = np.eye(3)                                     # repeated singular values
+    F[50:100, :, 2] *= 1e-3                                # nearly flat
+    F = np.ascontiguousarray(F, dtype)
+    U = np.zeros_like(F); V = np.zeros_like(F); s = np.zeros((n, 3), dtype)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    host_math.svd3_host(int(dtype == np.float64), n, P(F), P(U), P(s), P(V))
+    U64, V64, s64 = U.astype(float), V.astype(float), s.astype(float)
+    np.testing.assert_allclose(np.linalg.det(U64), 1.0, atol=10 * tol)
+    np.testing.assert_allclose(np.linalg.det(V64), 1.0, atol=10 * tol)
+    rec = np.einsum("nij,nj,nkj->nik", U64, s64, V64)
+    assert np.abs(rec - F).max() < 20 * tol
+    assert (s64[:, 0] >= s64[:, 1] - tol).all() and (s64[:, 1] >= np.abs(s64[:, 2]) - tol).all()
+    assert (np.sign(s64[:, 2]) == np.sign(np.linalg.det(F.astype(float))))[100:].all()
+    ref = np.linalg.svd(F.astype(float), compute_uv=False)
+    assert np.abs(np.abs(s64) - ref).max() < 20 * tol
