@@ -297,7 +297,18 @@ int apl_fem_create(int kind, int dtype, int64_t n_cells, int64_t n_points, const
             if (e != cudaSuccess) return e;
             return bytes ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
         };
-        APL_TRY(up(&f->d_tiles, h.tiles.data(), h.tiles.size() * 4));
+        {
+            // device tile header: tet_start, n_tets | n_verts << 16, vert_start, voff_start
+            std::vector<int32_t> hdr((size_t)h.n_tiles() * 4);
+            for (int64_t t = 0; t < h.n_tiles(); ++t) {
+                const int32_t* src = h.tiles.data() + 6 * t;
+                hdr[4 * t] = src[0];
+                hdr[4 * t + 1] = src[1] | (src[3] << 16);
+                hdr[4 * t + 2] = src[2];
+                hdr[4 * t + 3] = src[4];
+            }
+            APL_TRY(up(&f->d_tiles, hdr.data(), hdr.size() * 4));
+        }
         APL_TRY(up(&f->d_conn, h.conn.data(), h.conn.size()));
         APL_TRY(up(&f->d_slots, h.slots.data(), h.slots.size() * 2));
         APL_TRY(up(&f->d_tile_verts, h.tile_verts.data(), h.tile_verts.size() * 4));
@@ -315,7 +326,7 @@ int apl_fem_create(int kind, int dtype, int64_t n_cells, int64_t n_points, const
     return APL_OK;
 }
 
-int apl_fem_info(const apl_fem_t* f, int64_t info[8]) {
+int apl_fem_info(const apl_fem_t* f, int64_t info[10]) {
     if (!f || !info) { set_error("apl_fem_info: NULL argument"); return APL_ERR_INVALID; }
     info[0] = f->host.n_cells;
     info[1] = f->host.n_points;
@@ -325,6 +336,8 @@ int apl_fem_info(const apl_fem_t* f, int64_t info[8]) {
     info[5] = f->kind;
     info[6] = f->dtype;
     info[7] = f->device;
+    info[8] = (int64_t)f->host.tile_voff.size();
+    info[9] = 0;
     return APL_OK;
 }
 

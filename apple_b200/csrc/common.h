@@ -18,13 +18,13 @@ void set_error(const std::string& msg);
 // Host-side packed mesh (built by tiling.cpp, uploaded by capi.cu).
 struct HostTables {
     int64_t n_cells = 0, n_points = 0;
-    std::vector<int32_t> tiles;        // (n_tiles,4): tet_start, n_tets, vert_start, n_verts
+    std::vector<int32_t> tiles;        // (n_tiles,6): tet_start, n_tets, vert_start, n_verts, voff_start, 0
     std::vector<int64_t> order;        // packed position -> caller's cell index
     std::vector<uint8_t> conn;         // (n_cells,4)
     std::vector<uint16_t> slots;       // (n_cells,4)
-    std::vector<int32_t> tile_verts;   // global vertex ids, tile after tile (ascending within a tile)
-    std::vector<uint16_t> tile_voff;   // per tile n_verts+1 offsets, tile t starts at vert_start + t
-    int64_t n_tiles() const { return (int64_t)tiles.size() / 4; }
+    std::vector<int32_t> tile_verts;   // global vertex ids per tile, by decreasing valence (padded to x4)
+    std::vector<uint16_t> tile_voff;   // per tile n_verts+1 slot offsets, starting at voff_start (x8)
+    int64_t n_tiles() const { return (int64_t)tiles.size() / 6; }
 };
 
 // cells: (n_cells,4) int32.  points: (n_points,3) double or nullptr.  Returns APL_OK or error code.

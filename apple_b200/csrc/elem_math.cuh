@@ -102,6 +102,21 @@ APL_HD void vjp_rows(const T* D, const T* M, T s, T out[4][3]) {
     }
 }
 
+// out[a][i] = (dhdX M^T)[a][i] without a scale factor (the caller folds it into M)
+template <typename T>
+APL_HD void vjp_rows1(const T* D, const T* M, T out[4][3]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const T r1 = D[0] * M[3 * i] + D[1] * M[3 * i + 1] + D[2] * M[3 * i + 2];
+        const T r2 = D[3] * M[3 * i] + D[4] * M[3 * i + 1] + D[5] * M[3 * i + 2];
+        const T r3 = D[6] * M[3 * i] + D[7] * M[3 * i + 1] + D[8] * M[3 * i + 2];
+        out[1][i] = r1;
+        out[2][i] = r2;
+        out[3][i] = r3;
+        out[0][i] = -r1 - r2 - r3;
+    }
+}
+
 // cof(F), J = det F.  C[3*i+j] = (column j of cof)_i, columns f1xf2, f2xf0, f0xf1.
 template <typename T>
 APL_HD T cofactor(const T* F, T* C) {
@@ -165,17 +180,36 @@ APL_HD void row_norms(const T* D, T n[4]) {
 // Cyclic Jacobi on F^T F for V, then modified Gram-Schmidt on F V for U and the singular values
 // (column norms of F V are more accurate than square roots of the eigenvalues).
 // ------------------------------------------------------------------------------------------
+// Fast reciprocal for quantities that only steer convergence (rotation angles), not accuracy.
+template <typename T>
+APL_HD T apl_rcp_fast(T x) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(T) == 4) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)x));
+        return (T)r;
+    } else {
+        return (T)1 / x;
+    }
+#else
+    return (T)1 / x;
+#endif
+}
+
 template <typename T>
 APL_HD void jacobi_rotate(T* A, T* V, int p, int q) {
-    // A symmetric, stored fully (row-major 3x3).  Annihilates A[p][q].
+    // A symmetric, stored fully (row-major 3x3).  Annihilates A[p][q] with the rotation
+    // tan(theta) = t = sgn(d) 2 a_pq / (|d| + sqrt(d^2 + 4 a_pq^2)),  d = a_qq - a_pp  (|theta| <= pi/4).
     const T apq = A[3 * p + q];
-    const T app = A[3 * p + p], aqq = A[3 * q + q];
     const T tiny = (sizeof(T) == 4) ? (T)1e-30 : (T)1e-280;
     if (!(fabs(apq) > tiny)) return;
-    const T theta = (aqq - app) / ((T)2 * apq);
-    T t = (T)1 / (fabs(theta) + sqrt(theta * theta + (T)1));
-    if (theta < (T)0) t = -t;
-    const T c = apl_rsqrt(t * t + (T)1);
+    const T app = A[3 * p + p], aqq = A[3 * q + q];
+    const T d = aqq - app, b = (T)2 * apq;
+    const T h2 = d * d + b * b;
+    const T h = h2 * apl_rsqrt(h2);
+    T t = b * apl_rcp_fast(fabs(d) + h);
+    if (d < (T)0) t = -t;
+    const T c = apl_rsqrt(t * t + (T)1);  // full precision: keeps V orthonormal
     const T s = t * c;
     const int r = 3 - p - q;  // the untouched index
     const T arp = A[3 * r + p], arq = A[3 * r + q];
@@ -190,6 +224,15 @@ APL_HD void jacobi_rotate(T* A, T* V, int p, int q) {
         V[3 * k + p] = c * vp - s * vq;
         V[3 * k + q] = s * vp + c * vq;
     }
+}
+
+// true when every lane of the warp has converged (host: this element has converged)
+APL_HD bool apl_all_done(bool done) {
+#if defined(__CUDA_ARCH__)
+    return __all_sync(__activemask(), done);
+#else
+    return done;
+#endif
 }
 
 template <typename T>
@@ -217,12 +260,19 @@ APL_HD void svd3_rv(const T* F, T* U, T* sig, T* V) {
     V[0] = 1; V[1] = 0; V[2] = 0;
     V[3] = 0; V[4] = 1; V[5] = 0;
     V[6] = 0; V[7] = 0; V[8] = 1;
-    constexpr int kSweeps = (sizeof(T) == 4) ? 5 : 8;
+    // Cyclic Jacobi converges quadratically; stop when the off-diagonal mass is below rounding level
+    // relative to the trace (checked per warp so that the loop stays convergent).
+    constexpr int kMaxSweeps = (sizeof(T) == 4) ? 6 : 10;
+    const T tr = A[0] + A[4] + A[8];
+    const T eps = (sizeof(T) == 4) ? (T)2.4e-7 : (T)8.9e-16;
+    const T tol = eps * eps * tr * tr;
 #pragma unroll 1
-    for (int sweep = 0; sweep < kSweeps; ++sweep) {
+    for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
         jacobi_rotate(A, V, 0, 1);
         jacobi_rotate(A, V, 0, 2);
         jacobi_rotate(A, V, 1, 2);
+        const T off = A[1] * A[1] + A[2] * A[2] + A[5] * A[5];
+        if (apl_all_done(off <= tol)) break;
     }
     // sort eigenvalues descending (det V stays +1)
     if (A[0] < A[4]) swap_cols_neg(A, V, 0, 1);
@@ -336,9 +386,10 @@ APL_HD void elem_eval(const T* rec, const T (*uc)[3], const T (*pc)[3], T& psi, 
         }
         if constexpr (kGrad) {
             T P[9];
+            const T a = vol * mu, b = vol * c3;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) P[k] = mu * F[k] + c3 * C[k];
-            vjp_rows(D, P, vol, g);
+            for (int k = 0; k < 9; ++k) P[k] = a * F[k] + b * C[k];
+            vjp_rows1(D, P, g);
         }
         if constexpr (kDiag) {
             T W[4][3], n[4];
@@ -356,9 +407,10 @@ APL_HD void elem_eval(const T* rec, const T (*uc)[3], const T (*pc)[3], T& psi, 
             const T s = ddot9(C, dF);
             if constexpr (kProd) {
                 T M[9];
+                const T a = vol * la * s, b = vol * mu, c = vol * c3;
 #pragma unroll
-                for (int k = 0; k < 9; ++k) M[k] = la * s * C[k] + mu * dF[k] + c3 * X[k];
-                vjp_rows(D, M, vol, hp);
+                for (int k = 0; k < 9; ++k) M[k] = a * C[k] + b * dF[k] + c * X[k];
+                vjp_rows1(D, M, hp);
             }
             if constexpr (kQuad) {
                 const T q = la * s * s + mu * ddot9(dF, dF) + c3 * ddot9(dF, X);
@@ -374,13 +426,14 @@ APL_HD void elem_eval(const T* rec, const T (*uc)[3], const T (*pc)[3], T& psi, 
         }
         if constexpr (kGrad) {
             T P[9];
+            const T a = vol * mu;
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
-                    P[3 * i + j] = F[3 * i + j] - (U[3 * i] * V[3 * j] + U[3 * i + 1] * V[3 * j + 1] +
-                                                   U[3 * i + 2] * V[3 * j + 2]);
-            vjp_rows(D, P, vol * mu, g);
+                    P[3 * i + j] = a * (F[3 * i + j] - (U[3 * i] * V[3 * j] + U[3 * i + 1] * V[3 * j + 1] +
+                                                        U[3 * i + 2] * V[3 * j + 2]));
+            vjp_rows1(D, P, g);
         }
         if constexpr (kDiag || kNeedP) {
             const T two = (T)2;
@@ -443,13 +496,14 @@ APL_HD void elem_eval(const T* rec, const T (*uc)[3], const T (*pc)[3], T& psi, 
                         UK[3 * i + 2] = U[3 * i + 0] * k2 + U[3 * i + 1] * k1;
                     }
                     T M[9];
+                    const T a = vol * mu;
 #pragma unroll
                     for (int i = 0; i < 3; ++i)
 #pragma unroll
                         for (int j = 0; j < 3; ++j)
-                            M[3 * i + j] = dF[3 * i + j] - (UK[3 * i] * V[3 * j] + UK[3 * i + 1] * V[3 * j + 1] +
-                                                            UK[3 * i + 2] * V[3 * j + 2]);
-                    vjp_rows(D, M, vol * mu, hp);
+                            M[3 * i + j] = a * (dF[3 * i + j] - (UK[3 * i] * V[3 * j] + UK[3 * i + 1] * V[3 * j + 1] +
+                                                                 UK[3 * i + 2] * V[3 * j + 2]));
+                    vjp_rows1(D, M, hp);
                 }
             }
         }

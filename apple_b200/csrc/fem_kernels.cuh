@@ -208,8 +208,10 @@ struct TileCfg {
     static constexpr bool kQuad = (OPS & APL_OP_HESS_QUAD) != 0;
     static constexpr bool kNeedP = kProd || kQuad;
     static constexpr int NOUT = (kGrad ? 1 : 0) + (kDiag ? 1 : 0) + (kProd ? 1 : 0);
-    // slot stride in scalars: 3*NOUT rounded so that every slot is 8-byte (fp32) / 16-byte (fp64) aligned
-    static constexpr int SS = (NOUT == 0) ? 0 : (NOUT == 1 ? 4 : (NOUT == 2 ? 6 : 10));
+    // slot stride in scalars: 3*NOUT rounded up so that a slot is a whole number of 16-byte vectors
+    static constexpr int SS = (NOUT == 0) ? 0
+                              : (NOUT == 1) ? 4
+                              : (sizeof(T) == 4) ? (NOUT == 2 ? 8 : 12) : (NOUT == 2 ? 6 : 10);
     static constexpr int kNSlots = 4 * kTileTets;
     static constexpr size_t kUsBytes = (size_t)4 * kTileVerts * sizeof(T);
     static constexpr size_t kPsBytes = kNeedP ? kUsBytes : 0;
@@ -281,9 +283,18 @@ __global__ void __launch_bounds__(kTileTets, (sizeof(T) == 4 ? 2 : 1)) fem_tile_
     const bool axpy = a.axpy_p != nullptr;
     const T alpha = axpy ? (T)__ldcg(a.scal + a.alpha_idx) : (T)0;
 
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int4 h = __ldg(a.tiles + tile);  // tet_start, n_tets, vert_start, n_verts
-        const bool active = tid < h.y;
+    // Software prefetch of the INDICES one tile ahead (tile header, then this thread's vertex id), so
+    // that the per-tile critical path is one memory round trip (static planes + vertex gather issued
+    // together) instead of three dependent ones.
+    int tile = blockIdx.x;
+    int4 h = tile < a.n_tiles ? __ldg(a.tiles + tile) : make_int4(0, 0, 0, 0);
+    int gv = (tid < (h.y >> 16)) ? __ldg(a.tile_verts + h.z + tid) : 0;
+    for (; tile < a.n_tiles; tile += gridDim.x) {
+        // header: tet_start, n_tets | n_verts << 16, vert_start, voff_start
+        const int n_tets = h.y & 0xffff, n_verts = h.y >> 16;
+        const int next = tile + gridDim.x;
+        const int4 hn = next < a.n_tiles ? __ldg(a.tiles + next) : make_int4(0, 0, 0, 0);
+        const bool active = tid < n_tets;
         const long long t = (long long)h.x + tid;
         uchar4 lc = make_uchar4(0, 0, 0, 0);
         ushort4 s4 = make_ushort4(0, 0, 0, 0);
@@ -294,9 +305,7 @@ __global__ void __launch_bounds__(kTileTets, (sizeof(T) == 4 ? 2 : 1)) fem_tile_
 #pragma unroll
             for (int k = 0; k < Rec<T, NREC>::NPL; ++k) rec.q[k] = __ldg(a.planes + k * a.plane_stride + t);
         }
-        int gv = 0;
-        if (tid < h.w) {
-            gv = __ldg(a.tile_verts + h.z + tid);
+        if (tid < n_verts) {
             load_row<T>(a.u, gv, a.ld_in, us + 4 * tid);
             if constexpr (Cfg::kNeedP) load_row<T>(a.p, gv, a.ld_in, ps + 4 * tid);
             if (axpy) {  // trial point of the line search, never materialised in global memory
@@ -308,9 +317,10 @@ __global__ void __launch_bounds__(kTileTets, (sizeof(T) == 4 ? 2 : 1)) fem_tile_
             }
         }
         if constexpr (NOUT > 0) {
-            for (int i = tid; i <= h.w; i += kTileTets) voff[i] = __ldg(a.tile_voff + h.z + tile + i);
+            for (int i = tid; i <= n_verts; i += kTileTets) voff[i] = __ldg(a.tile_voff + h.w + i);
         }
         __syncthreads();
+        const int gvn = (tid < (hn.y >> 16)) ? __ldg(a.tile_verts + hn.z + tid) : 0;
 
         if (active) {
             T uc[4][3], pc[4][3];
@@ -347,7 +357,7 @@ __global__ void __launch_bounds__(kTileTets, (sizeof(T) == 4 ? 2 : 1)) fem_tile_
         }
         if constexpr (NOUT > 0) {
             __syncthreads();
-            if (tid < h.w) {
+            if (tid < n_verts) {
                 const int s0 = voff[tid], s1 = voff[tid + 1];
                 T acc[3 * NOUT];
 #pragma unroll
@@ -365,6 +375,8 @@ __global__ void __launch_bounds__(kTileTets, (sizeof(T) == 4 ? 2 : 1)) fem_tile_
             }
         }
         __syncthreads();
+        h = hn;
+        gv = gvn;
     }
     if constexpr (Cfg::kFun || Cfg::kQuad)
         finish_scalars<T, kTileTets>(e_acc, q_acc, a.partials, a.counter, Cfg::kFun ? a.fun : nullptr,
@@ -385,7 +397,7 @@ __global__ void __launch_bounds__(kTileTets) fem_atomic_kernel(const FemArgs<T> 
     const T alpha = axpy ? (T)__ldcg(a.scal + a.alpha_idx) : (T)0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int4 h = __ldg(a.tiles + tile);
-        if (tid < h.y) {
+        if (tid < (h.y & 0xffff)) {
             const long long t = (long long)h.x + tid;
             const uchar4 lc = __ldg(a.conn + t);
             Rec<T, NREC> rec;

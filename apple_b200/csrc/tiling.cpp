@@ -2,7 +2,7 @@
 //
 // A tile is a run of <= 256 consecutive tets (in packed order) that together touch <= 256 distinct
 // vertices.  For every tile we store
-//   * the sorted list of the global vertex ids it touches            (tile_verts)
+//   * the list of the global vertex ids it touches, by decreasing valence   (tile_verts)
 //   * per tet, the tile-local id of each corner as one byte          (conn)
 //   * per tet corner, a slot in [0, 4*n_tets): slots are grouped by local vertex, so the element
 //     kernel can write every corner contribution to its own shared-memory slot (no atomics) and a
@@ -81,50 +81,67 @@ int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const d
     else std::iota(out.order.begin(), out.order.end(), (int64_t)0);
     out.conn.resize((size_t)n_cells * 4);
     out.slots.resize((size_t)n_cells * 4);
-    out.tiles.reserve((size_t)(n_cells / kTileTets + 1) * 4);
+    out.tiles.reserve((size_t)(n_cells / kTileTets + 1) * 6);
     out.tile_verts.reserve((size_t)(n_cells / 2 + 16));
 
     std::vector<int32_t> stamp((size_t)n_points, -1);  // tile that last touched the vertex
     std::vector<int32_t> lid((size_t)n_points, 0);     // its local id in that tile
-    std::vector<int32_t> verts;                        // distinct vertices of the open tile
+    std::vector<int32_t> verts;                        // distinct vertices of the open tile (first-touch order)
     verts.reserve(kTileVerts);
     int32_t cnt[kTileVerts];
     int32_t off[kTileVerts + 1];
+    int32_t perm[kTileVerts];
     int64_t tile_start = 0;
     int32_t tile_id = 0;
 
+    // Closes the tile [tile_start, tile_end).  Local vertex ids are ordered by DECREASING valence
+    // (ties: ascending global id) so that the per-vertex slot reduction of the kernel has nearly
+    // uniform trip counts within a warp.  The vertex list starts at a multiple of 4 entries and the
+    // offset list at a multiple of 8 entries (16-byte aligned for bulk copies).
     auto close_tile = [&](int64_t tile_end) {
         const int nt = (int)(tile_end - tile_start);
         if (nt == 0) return;
         const int nv = (int)verts.size();
-        std::sort(verts.begin(), verts.end());
         for (int l = 0; l < nv; ++l) {
             lid[(size_t)verts[l]] = l;
             cnt[l] = 0;
+            perm[l] = l;
         }
+        for (int64_t pos = tile_start; pos < tile_end; ++pos) {
+            const int32_t* c = cells + 4 * out.order[(size_t)pos];
+            for (int a = 0; a < 4; ++a) ++cnt[lid[(size_t)c[a]]];
+        }
+        std::sort(perm, perm + nv, [&](int a, int b) {
+            if (cnt[a] != cnt[b]) return cnt[a] > cnt[b];
+            return verts[a] < verts[b];
+        });
+        while (out.tile_verts.size() % 4) out.tile_verts.push_back(0);
+        while (out.tile_voff.size() % 8) out.tile_voff.push_back(0);
+        const int32_t vert_start = (int32_t)out.tile_verts.size();
+        const int32_t voff_start = (int32_t)out.tile_voff.size();
+        off[0] = 0;
+        for (int l = 0; l < nv; ++l) {
+            const int old = perm[l];
+            lid[(size_t)verts[old]] = l;
+            out.tile_verts.push_back(verts[old]);
+            off[l + 1] = off[l] + cnt[old];
+        }
+        for (int l = 0; l <= nv; ++l) out.tile_voff.push_back((uint16_t)off[l]);
+        out.tiles.push_back((int32_t)tile_start);
+        out.tiles.push_back(nt);
+        out.tiles.push_back(vert_start);
+        out.tiles.push_back(nv);
+        out.tiles.push_back(voff_start);
+        out.tiles.push_back(0);
+        for (int l = 0; l < nv; ++l) cnt[l] = 0;  // reuse as fill cursor
         for (int64_t pos = tile_start; pos < tile_end; ++pos) {
             const int32_t* c = cells + 4 * out.order[(size_t)pos];
             for (int a = 0; a < 4; ++a) {
                 const int l = lid[(size_t)c[a]];
                 out.conn[(size_t)pos * 4 + a] = (uint8_t)l;
-                ++cnt[l];
-            }
-        }
-        off[0] = 0;
-        for (int l = 0; l < nv; ++l) off[l + 1] = off[l] + cnt[l];
-        const int32_t vert_start = (int32_t)out.tile_verts.size();
-        out.tiles.push_back((int32_t)tile_start);
-        out.tiles.push_back(nt);
-        out.tiles.push_back(vert_start);
-        out.tiles.push_back(nv);
-        for (int l = 0; l < nv; ++l) out.tile_verts.push_back(verts[l]);
-        for (int l = 0; l <= nv; ++l) out.tile_voff.push_back((uint16_t)off[l]);
-        for (int l = 0; l < nv; ++l) cnt[l] = 0;  // reuse as fill cursor
-        for (int64_t pos = tile_start; pos < tile_end; ++pos)
-            for (int a = 0; a < 4; ++a) {
-                const int l = out.conn[(size_t)pos * 4 + a];
                 out.slots[(size_t)pos * 4 + a] = (uint16_t)(off[l] + cnt[l]++);
             }
+        }
         verts.clear();
         tile_start = tile_end;
         ++tile_id;
@@ -136,13 +153,11 @@ int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const d
     }
     for (int64_t pos = 0; pos < n_cells; ++pos) {
         const int32_t* c = cells + 4 * out.order[(size_t)pos];
-        int n_new = 0;
-        for (int a = 0; a < 4; ++a) {
-            bool is_new = stamp[(size_t)c[a]] != tile_id;
-            for (int b = 0; b < a; ++b) is_new = is_new && (c[b] != c[a]);
-            n_new += is_new;
-        }
-        if (pos - tile_start == kTileTets || (int)verts.size() + n_new > kTileVerts) {
+        // A tile closes when it is full.  Vertex budget: tiles must start at multiples of 4 tets
+        // (16-byte aligned byte-wide connectivity), so the budget is checked every 4 tets with room
+        // for the worst case of 16 new vertices in the next 4.
+        const int64_t in_tile = pos - tile_start;
+        if (in_tile == kTileTets || (in_tile % 4 == 0 && in_tile > 0 && (int)verts.size() + 16 > kTileVerts)) {
             close_tile(pos);
         }
         for (int a = 0; a < 4; ++a)
@@ -152,7 +167,10 @@ int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const d
             }
     }
     close_tile(n_cells);
-    if (out.tile_verts.size() + (size_t)out.n_tiles() > (size_t)INT32_MAX) {
+    // pad the tables so that 16-byte granular bulk copies of the last tile stay in bounds
+    for (int k = 0; k < 8; ++k) out.tile_verts.push_back(0);
+    for (int k = 0; k < 16; ++k) out.tile_voff.push_back(0);
+    if (out.tile_verts.size() > (size_t)INT32_MAX || out.tile_voff.size() > (size_t)INT32_MAX) {
         set_error("tile vertex table exceeds int32 range");
         return APL_ERR_INVALID;
     }

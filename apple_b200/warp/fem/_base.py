@@ -117,9 +117,10 @@ class WarpPotentialFem(WarpPotential):
 
     @property
     def info(self) -> dict:
-        buf = (ctypes.c_int64 * 8)()
+        buf = (ctypes.c_int64 * 10)()
         _lib.check(_lib.lib().apl_fem_info(self._handle, buf))
-        keys = ("n_cells", "n_points", "n_tiles", "n_tile_verts", "static_bytes", "kind", "dtype", "device")
+        keys = ("n_cells", "n_points", "n_tiles", "n_tile_verts", "static_bytes", "kind", "dtype", "device",
+                "n_tile_voff")
         return dict(zip(keys, list(buf)))
 
     def set_materials(self, *, dV=None, **materials) -> None:

@@ -78,17 +78,18 @@ int apl_fem_create(int kind, int dtype, int64_t n_cells, int64_t n_points, const
                    const void* activation, const double* points, int device, apl_fem_t** out);
 void apl_fem_destroy(apl_fem_t* fem);
 
-/* info[0..7] = n_cells, n_points, n_tiles, sum of tile vertex counts, static device bytes,
- *              kind, dtype, device */
-int apl_fem_info(const apl_fem_t* fem, int64_t info[8]);
+/* info[0..9] = n_cells, n_points, n_tiles, length of tile_verts, static device bytes,
+ *              kind, dtype, device, length of tile_voff, 0 */
+int apl_fem_info(const apl_fem_t* fem, int64_t info[10]);
 
 /* Copies of the host tables (sizes from apl_fem_info); any pointer may be NULL.
- *   tiles      int32 (n_tiles,4): tet_start, n_tets, vert_start, n_verts
+ *   tiles      int32 (n_tiles,6): tet_start, n_tets, vert_start, n_verts, voff_start, 0
  *   order      int64 (n_cells,)  : packed position -> caller's cell index
  *   conn       uint8 (n_cells,4) : tile-local vertex id per corner (packed order)
  *   slots      uint16(n_cells,4) : in-tile reduction slot per corner (packed order)
- *   tile_verts int32 (sum verts) : global vertex id per tile-local id
- *   tile_voff  uint16(sum verts + n_tiles): per tile, n_verts+1 slot offsets */
+ *   tile_verts int32 (info[3])   : global vertex id per tile-local id, starting at vert_start;
+ *                                  local ids are ordered by decreasing valence within the tile
+ *   tile_voff  uint16(info[8])   : per tile, n_verts+1 slot offsets starting at voff_start */
 int apl_fem_host_tables(const apl_fem_t* fem, int32_t* tiles, int64_t* order, uint8_t* conn,
                         uint16_t* slots, int32_t* tile_verts, uint16_t* tile_voff);
 

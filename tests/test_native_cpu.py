@@ -57,12 +57,12 @@ def _host_tables(native_lib, mesh, kind=0, with_points=True):
     rc = native_lib.apl_fem_create(kind, _lib.F64, T, V, P(cells), P(dhdX), P(dV), P(mu), P(la), P(act), P(pts), -1,
                                    ctypes.byref(h))
     assert rc == 0, native_lib.apl_last_error()
-    info = (ctypes.c_int64 * 8)()
+    info = (ctypes.c_int64 * 10)()
     native_lib.apl_fem_info(h, info)
-    nt, nv = info[2], info[3]
-    tiles = np.zeros((nt, 4), np.int32); order = np.zeros(T, np.int64)
+    nt, nv, nvo = info[2], info[3], info[8]
+    tiles = np.zeros((nt, 6), np.int32); order = np.zeros(T, np.int64)
     conn = np.zeros((T, 4), np.uint8); slots = np.zeros((T, 4), np.uint16)
-    tv = np.zeros(nv, np.int32); voff = np.zeros(nv + nt, np.uint16)
+    tv = np.zeros(nv, np.int32); voff = np.zeros(nvo, np.uint16)
     native_lib.apl_fem_host_tables(h, P(tiles), P(order), P(conn), P(slots), P(tv), P(voff))
     native_lib.apl_fem_destroy(h)
     return tiles, order, conn, slots, tv, voff
@@ -78,12 +78,14 @@ def test_tiling_invariants(native_lib, with_points):
         assert (order == np.arange(T)).all()                 # NULL points keeps the caller's order
     assert tiles[:, 1].sum() == T and (tiles[:, 1] <= 256).all() and (tiles[:, 3] <= 256).all()
     assert (tiles[1:, 0] == tiles[:-1, 0] + tiles[:-1, 1]).all()
-    for t, (ts, n, vs, nv) in enumerate(tiles):
+    assert (tiles[:, 0] % 4 == 0).all() and (tiles[:, 2] % 4 == 0).all() and (tiles[:, 4] % 8 == 0).all()
+    for t, (ts, n, vs, nv, vo, _) in enumerate(tiles):
         gl = tv[vs:vs + nv]
-        assert (np.diff(gl) > 0).all()                       # sorted, distinct
+        assert len(set(gl.tolist())) == nv                   # distinct
         assert np.array_equal(gl[conn[ts:ts + n]], mesh.cells[order[ts:ts + n]])   # connectivity round trip
-        off = voff[vs + t: vs + t + nv + 1].astype(int)
+        off = voff[vo: vo + nv + 1].astype(int)
         assert off[0] == 0 and off[-1] == 4 * n
+        assert (np.diff(np.diff(off)) <= 0).all()            # local ids ordered by decreasing valence
         s = slots[ts:ts + n].ravel().astype(int); l = conn[ts:ts + n].ravel().astype(int)
         assert sorted(s.tolist()) == list(range(4 * n))      # every corner owns exactly one slot
         assert ((s >= off[l]) & (s < off[l + 1])).all()      # ... inside its vertex's range
