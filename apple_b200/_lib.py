@@ -19,7 +19,7 @@ OK = 0
 F32, F64 = 0, 1
 KIND_SNH, KIND_ARAP, KIND_SNH_MUSCLE = 0, 1, 2
 OP_FUN, OP_GRAD, OP_HESS_DIAG, OP_HESS_PROD, OP_HESS_QUAD = 1, 2, 4, 8, 16
-SCATTER_TILE, SCATTER_ATOMIC = 0, 1
+SCATTER_TILE, SCATTER_ATOMIC, SCATTER_TILE_SIMPLE = 0, 1, 2
 PNCG_NSCAL = 96
 S_F, S_F_PREV, S_GP, S_PHP, S_ALPHA, S_BETA, S_GNORM2, S_GNORM2_FIRST = 0, 1, 2, 3, 4, 5, 6, 7
 S_ACCEPTED, S_LS_STEPS, S_K, S_N_ACCEPTED, S_DIAG_MEAN, S_GPG, S_DONE, S_FAILS, S_F_NEW = 8, 9, 10, 11, 12, 13, 15, 16, 17
@@ -36,7 +36,7 @@ SIGNATURES = {
                                c_void_p, c_void_p, c_int, POINTER(c_void_p)]),
     "apl_fem_destroy": (None, [c_void_p]),
     "apl_fem_info": (c_int, [c_void_p, POINTER(c_int64)]),
-    "apl_fem_host_tables": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "apl_fem_host_tables": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "apl_fem_set_materials": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "apl_fem_eval": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_int, c_int, c_void_p]),

@@ -96,6 +96,7 @@ static int eval_typed(apl_fem* f, int ops, const void* u, const void* p, int ld_
     a.slots = (const ushort4*)f->d_slots;
     a.tile_verts = (const int*)f->d_tile_verts;
     a.tile_voff = (const unsigned short*)f->d_tile_voff;
+    a.tile_vperm = (const unsigned char*)f->d_tile_vperm;
     a.planes = (const uint4*)f->d_planes;
     a.plane_stride = f->plane_stride;
     a.u = (const T*)u;
@@ -242,6 +243,7 @@ void apl_fem_destroy(apl_fem_t* f) {
         cudaFree(f->d_slots);
         cudaFree(f->d_tile_verts);
         cudaFree(f->d_tile_voff);
+        cudaFree(f->d_tile_vperm);
         cudaFree(f->d_planes);
         cudaFree(f->d_partials);
         cudaFree(f->d_counter);
@@ -275,8 +277,8 @@ int apl_fem_create(int kind, int dtype, int64_t n_cells, int64_t n_points, const
     if (f->plane_stride == 0) f->plane_stride = 32;
     const HostTables& h = f->host;
     const size_t plane_bytes = (size_t)f->nplanes * f->plane_stride * 16;
-    f->static_bytes = (int64_t)(plane_bytes + h.tiles.size() * 4 + h.conn.size() + h.slots.size() * 2 +
-                                h.tile_verts.size() * 4 + h.tile_voff.size() * 2);
+    f->static_bytes = (int64_t)(plane_bytes + h.n_tiles() * 16 + h.conn.size() + h.slots.size() * 2 +
+                                h.tile_verts.size() * 5 + h.tile_voff.size() * 2);
     if (device >= 0) {
         auto fail = [&](int code) { apl_fem_destroy(f); return code; };
 #define APL_TRY(expr)                                                                           \
@@ -309,10 +311,17 @@ int apl_fem_create(int kind, int dtype, int64_t n_cells, int64_t n_points, const
             }
             APL_TRY(up(&f->d_tiles, hdr.data(), hdr.size() * 4));
         }
-        APL_TRY(up(&f->d_conn, h.conn.data(), h.conn.size()));
-        APL_TRY(up(&f->d_slots, h.slots.data(), h.slots.size() * 2));
+        {   // +64 bytes of slack: 16-byte granular bulk copies of the last tile stay in bounds
+            std::vector<uint8_t> conn(h.conn.size() + 64, 0);
+            memcpy(conn.data(), h.conn.data(), h.conn.size());
+            std::vector<uint16_t> slots(h.slots.size() + 32, 0);
+            memcpy(slots.data(), h.slots.data(), h.slots.size() * 2);
+            APL_TRY(up(&f->d_conn, conn.data(), conn.size()));
+            APL_TRY(up(&f->d_slots, slots.data(), slots.size() * 2));
+        }
         APL_TRY(up(&f->d_tile_verts, h.tile_verts.data(), h.tile_verts.size() * 4));
         APL_TRY(up(&f->d_tile_voff, h.tile_voff.data(), h.tile_voff.size() * 2));
+        APL_TRY(up(&f->d_tile_vperm, h.tile_vperm.data(), h.tile_vperm.size()));
         APL_TRY(cudaMalloc(&f->d_planes, plane_bytes));
         APL_TRY(cudaMalloc((void**)&f->d_partials, sizeof(double) * 2 * f->max_grid));
         APL_TRY(cudaMalloc((void**)&f->d_counter, sizeof(unsigned int)));
@@ -342,7 +351,7 @@ int apl_fem_info(const apl_fem_t* f, int64_t info[10]) {
 }
 
 int apl_fem_host_tables(const apl_fem_t* f, int32_t* tiles, int64_t* order, uint8_t* conn, uint16_t* slots,
-                        int32_t* tile_verts, uint16_t* tile_voff) {
+                        int32_t* tile_verts, uint16_t* tile_voff, uint8_t* tile_vperm) {
     if (!f) { set_error("apl_fem_host_tables: NULL handle"); return APL_ERR_INVALID; }
     const HostTables& h = f->host;
     if (tiles) memcpy(tiles, h.tiles.data(), h.tiles.size() * 4);
@@ -351,6 +360,7 @@ int apl_fem_host_tables(const apl_fem_t* f, int32_t* tiles, int64_t* order, uint
     if (slots) memcpy(slots, h.slots.data(), h.slots.size() * 2);
     if (tile_verts) memcpy(tile_verts, h.tile_verts.data(), h.tile_verts.size() * 4);
     if (tile_voff) memcpy(tile_voff, h.tile_voff.data(), h.tile_voff.size() * 2);
+    if (tile_vperm) memcpy(tile_vperm, h.tile_vperm.data(), h.tile_vperm.size());
     return APL_OK;
 }
 
@@ -391,7 +401,7 @@ int apl_fem_eval(apl_fem_t* f, int ops, const void* u, const void* p, int ld_in,
         set_error("apl_fem_eval: leading dimensions must be 3 or 4");
         return APL_ERR_INVALID;
     }
-    if (scatter != APL_SCATTER_TILE && scatter != APL_SCATTER_ATOMIC) {
+    if (scatter != APL_SCATTER_TILE && scatter != APL_SCATTER_ATOMIC && scatter != APL_SCATTER_TILE_SIMPLE) {
         set_error("apl_fem_eval: unknown scatter mode");
         return APL_ERR_INVALID;
     }

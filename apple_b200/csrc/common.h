@@ -22,7 +22,8 @@ struct HostTables {
     std::vector<int64_t> order;        // packed position -> caller's cell index
     std::vector<uint8_t> conn;         // (n_cells,4)
     std::vector<uint16_t> slots;       // (n_cells,4)
-    std::vector<int32_t> tile_verts;   // global vertex ids per tile, by decreasing valence (padded to x4)
+    std::vector<int32_t> tile_verts;   // global vertex ids per tile, ascending (tile start padded to x16)
+    std::vector<uint8_t> tile_vperm;   // same indexing: local ids by decreasing valence
     std::vector<uint16_t> tile_voff;   // per tile n_verts+1 slot offsets, starting at voff_start (x8)
     int64_t n_tiles() const { return (int64_t)tiles.size() / 6; }
 };
@@ -46,6 +47,7 @@ struct apl_fem {
     void* d_slots = nullptr;
     void* d_tile_verts = nullptr;
     void* d_tile_voff = nullptr;
+    void* d_tile_vperm = nullptr;
     void* d_planes = nullptr;
     double* d_partials = nullptr;   // per-CTA scalar partials (2 per CTA)
     unsigned int* d_counter = nullptr;

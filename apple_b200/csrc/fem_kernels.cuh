@@ -33,6 +33,7 @@ struct FemArgs {
     const ushort4* slots;
     const int* tile_verts;
     const unsigned short* tile_voff;
+    const unsigned char* tile_vperm;
     const uint4* planes;
     long long plane_stride;
     const T* u;
@@ -213,25 +214,26 @@ struct TileCfg {
                               : (NOUT == 1) ? 4
                               : (sizeof(T) == 4) ? (NOUT == 2 ? 8 : 12) : (NOUT == 2 ? 6 : 10);
     static constexpr int kNSlots = 4 * kTileTets;
-    static constexpr size_t kUsBytes = (size_t)4 * kTileVerts * sizeof(T);
-    static constexpr size_t kPsBytes = kNeedP ? kUsBytes : 0;
+    // per-vertex buffer: u (4 scalars) and p (4 scalars) during compute, then reused for the 3*NOUT
+    // reduced sums of each vertex between the reduce and the flush phase
+    static constexpr int VB = (3 * NOUT > 8) ? 12 : 8;
+    static constexpr size_t kVbufBytes = (size_t)kTileVerts * VB * sizeof(T);
     static constexpr size_t kSlotBytes = (size_t)kNSlots * SS * sizeof(T);
-    static constexpr size_t kVoffBytes = NOUT ? (size_t)((kTileVerts + 1) * 2 + 14) / 16 * 16 : 0;
-    static constexpr size_t kSmemBytes = kUsBytes + kPsBytes + kSlotBytes + kVoffBytes;
+    static constexpr size_t kVoffBytes = NOUT ? 528 : 0;  // 257 uint16, rounded to 16 bytes
+    static constexpr size_t kVpermBytes = NOUT ? 256 : 0;
+    // simple (unpipelined) kernel
+    static constexpr size_t kSmemBytes = kVbufBytes + kSlotBytes + kVoffBytes + kVpermBytes;
 };
 
 template <typename T, int SS>
 __device__ __forceinline__ void store_slot(T* dst, const T* v) {
     if constexpr (sizeof(T) == 4) {
-        if constexpr (SS % 4 == 0) {
+        static_assert(SS % 4 == 0, "fp32 slots are whole float4s");
 #pragma unroll
-            for (int k = 0; k < SS / 4; ++k)
-                reinterpret_cast<float4*>(dst)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < SS / 2; ++k) reinterpret_cast<float2*>(dst)[k] = make_float2(v[2 * k], v[2 * k + 1]);
-        }
+        for (int k = 0; k < SS / 4; ++k)
+            reinterpret_cast<float4*>(dst)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
     } else {
+        static_assert(SS % 2 == 0, "fp64 slots are whole double2s");
 #pragma unroll
         for (int k = 0; k < SS / 2; ++k) reinterpret_cast<double2*>(dst)[k] = make_double2(v[2 * k], v[2 * k + 1]);
     }
@@ -240,18 +242,10 @@ __device__ __forceinline__ void store_slot(T* dst, const T* v) {
 template <typename T, int SS>
 __device__ __forceinline__ void load_slot(const T* src, T* v) {
     if constexpr (sizeof(T) == 4) {
-        if constexpr (SS % 4 == 0) {
 #pragma unroll
-            for (int k = 0; k < SS / 4; ++k) {
-                const float4 q = reinterpret_cast<const float4*>(src)[k];
-                v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < SS / 2; ++k) {
-                const float2 q = reinterpret_cast<const float2*>(src)[k];
-                v[2 * k] = q.x; v[2 * k + 1] = q.y;
-            }
+        for (int k = 0; k < SS / 4; ++k) {
+            const float4 q = reinterpret_cast<const float4*>(src)[k];
+            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
         }
     } else {
 #pragma unroll
@@ -262,20 +256,107 @@ __device__ __forceinline__ void load_slot(const T* src, T* v) {
     }
 }
 
-// ---- TILE kernel ----------------------------------------------------------------------------------
+// ---- the three per-tile phases shared by the simple and the pipelined kernel -----------------------
+
+// One tet: gather its corners from the shared vertex buffer, evaluate, write one slot per corner.
+template <typename T, int KIND, int OPS>
+__device__ __forceinline__ void tile_compute(const T* rec, uchar4 lc, ushort4 s4, const T* us, const T* ps, bool axpy,
+                                             T alpha, T* sl, double& e_acc, double& q_acc) {
+    using Cfg = TileCfg<T, OPS>;
+    constexpr int NOUT = Cfg::NOUT, SS = Cfg::SS;
+    T uc[4][3], pc[4][3];
+    const int l[4] = {lc.x, lc.y, lc.z, lc.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        T tmp[4];
+        load_slot<T, 4>(us + 4 * l[c], tmp);
+        uc[c][0] = tmp[0]; uc[c][1] = tmp[1]; uc[c][2] = tmp[2];
+        if constexpr (Cfg::kNeedP) {
+            load_slot<T, 4>(ps + 4 * l[c], tmp);
+            pc[c][0] = tmp[0]; pc[c][1] = tmp[1]; pc[c][2] = tmp[2];
+        } else {
+            if (axpy) {  // line-search trial point x + alpha p, never materialised in global memory
+                load_slot<T, 4>(ps + 4 * l[c], tmp);
+                uc[c][0] += alpha * tmp[0]; uc[c][1] += alpha * tmp[1]; uc[c][2] += alpha * tmp[2];
+            }
+        }
+    }
+    T psi = 0, quad = 0;
+    T g[4][3], dg[4][3], hp[4][3];
+    elem_eval<T, KIND, OPS>(rec, uc, pc, psi, quad, g, dg, hp);
+    if constexpr (Cfg::kFun) e_acc += (double)psi;
+    if constexpr (Cfg::kQuad) q_acc += (double)quad;
+    if constexpr (NOUT > 0) {
+        const int sidx[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            T v[SS];
+            int k = 0;
+            if constexpr (Cfg::kGrad) { v[k] = g[c][0]; v[k + 1] = g[c][1]; v[k + 2] = g[c][2]; k += 3; }
+            if constexpr (Cfg::kDiag) { v[k] = dg[c][0]; v[k + 1] = dg[c][1]; v[k + 2] = dg[c][2]; k += 3; }
+            if constexpr (Cfg::kProd) { v[k] = hp[c][0]; v[k + 1] = hp[c][1]; v[k + 2] = hp[c][2]; k += 3; }
+#pragma unroll
+            for (int j = 3 * NOUT; j < SS; ++j) v[j] = (T)0;
+            store_slot<T, SS>(sl + sidx[c] * SS, v);
+        }
+    }
+}
+
+// Thread `tid` sums the slot range of the tid-th vertex in valence order (balanced trip counts per
+// warp) and parks the 3*NOUT sums in the vertex buffer at the vertex's ascending local id.
+template <typename T, int OPS>
+__device__ __forceinline__ void tile_reduce(int tid, int n_verts, const unsigned char* vperm,
+                                            const unsigned short* voff, const T* sl, T* vbuf) {
+    using Cfg = TileCfg<T, OPS>;
+    constexpr int NOUT = Cfg::NOUT, SS = Cfg::SS;
+    if (tid < n_verts) {
+        const int v = vperm[tid];
+        const int s0 = voff[v], s1 = voff[v + 1];
+        T acc[3 * NOUT];
+#pragma unroll
+        for (int j = 0; j < 3 * NOUT; ++j) acc[j] = (T)0;
+        for (int s = s0; s < s1; ++s) {
+            T val[SS];
+            load_slot<T, SS>(sl + s * SS, val);
+#pragma unroll
+            for (int j = 0; j < 3 * NOUT; ++j) acc[j] += val[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 3 * NOUT; ++j) vbuf[v * (3 * NOUT) + j] = acc[j];
+    }
+}
+
+// Thread `tid` adds the sums of local vertex tid (ascending global id: neighbouring lanes hit
+// neighbouring addresses) to global memory with one vector RED per field.
+template <typename T, int OPS>
+__device__ __forceinline__ void tile_flush(int tid, int n_verts, int gv, const T* vbuf, const FemArgs<T>& a) {
+    using Cfg = TileCfg<T, OPS>;
+    constexpr int NOUT = Cfg::NOUT;
+    if (tid < n_verts) {
+        T acc[3 * NOUT];
+#pragma unroll
+        for (int j = 0; j < 3 * NOUT; ++j) acc[j] = vbuf[tid * (3 * NOUT) + j];
+        int k = 0;
+        if constexpr (Cfg::kGrad) { if (a.grad) red_row(a.grad, gv, a.ld_out, acc + k); k += 3; }
+        if constexpr (Cfg::kDiag) { if (a.diag) red_row(a.diag, gv, a.ld_out, acc + k); k += 3; }
+        if constexpr (Cfg::kProd) { if (a.prod) red_row(a.prod, gv, a.ld_out, acc + k); k += 3; }
+    }
+}
+
+// ---- TILE kernel, unpipelined (APL_SCATTER_TILE_SIMPLE) ---------------------------------------------
 
 template <typename T, int KIND, int OPS>
 __global__ void __launch_bounds__(kTileTets, (sizeof(T) == 4 ? 2 : 1)) fem_tile_kernel(const FemArgs<T> a) {
     using Cfg = TileCfg<T, OPS>;
     constexpr int NOUT = Cfg::NOUT;
-    constexpr int SS = Cfg::SS;
     constexpr int NREC = RecSize<KIND>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* us = reinterpret_cast<T*>(smem_raw);
-    T* ps = reinterpret_cast<T*>(smem_raw + Cfg::kUsBytes);
-    T* sl = reinterpret_cast<T*>(smem_raw + Cfg::kUsBytes + Cfg::kPsBytes);
-    unsigned short* voff =
-        reinterpret_cast<unsigned short*>(smem_raw + Cfg::kUsBytes + Cfg::kPsBytes + Cfg::kSlotBytes);
+    T* vbuf = reinterpret_cast<T*>(smem_raw);
+    T* us = vbuf;
+    T* ps = vbuf + 4 * kTileVerts;
+    T* sl = reinterpret_cast<T*>(smem_raw + Cfg::kVbufBytes);
+    unsigned short* voff = reinterpret_cast<unsigned short*>(smem_raw + Cfg::kVbufBytes + Cfg::kSlotBytes);
+    unsigned char* vperm = smem_raw + Cfg::kVbufBytes + Cfg::kSlotBytes + Cfg::kVoffBytes;
 
     const int tid = threadIdx.x;
     double e_acc = 0.0, q_acc = 0.0;
@@ -308,13 +389,8 @@ __global__ void __launch_bounds__(kTileTets, (sizeof(T) == 4 ? 2 : 1)) fem_tile_
         if (tid < n_verts) {
             load_row<T>(a.u, gv, a.ld_in, us + 4 * tid);
             if constexpr (Cfg::kNeedP) load_row<T>(a.p, gv, a.ld_in, ps + 4 * tid);
-            if (axpy) {  // trial point of the line search, never materialised in global memory
-                T d[4];
-                load_row<T>(a.axpy_p, gv, a.ld_in, d);
-                us[4 * tid] += alpha * d[0];
-                us[4 * tid + 1] += alpha * d[1];
-                us[4 * tid + 2] += alpha * d[2];
-            }
+            else if (axpy) load_row<T>(a.axpy_p, gv, a.ld_in, ps + 4 * tid);
+            if constexpr (NOUT > 0) vperm[tid] = __ldg(a.tile_vperm + h.z + tid);
         }
         if constexpr (NOUT > 0) {
             for (int i = tid; i <= n_verts; i += kTileTets) voff[i] = __ldg(a.tile_voff + h.w + i);
@@ -322,57 +398,12 @@ __global__ void __launch_bounds__(kTileTets, (sizeof(T) == 4 ? 2 : 1)) fem_tile_
         __syncthreads();
         const int gvn = (tid < (hn.y >> 16)) ? __ldg(a.tile_verts + hn.z + tid) : 0;
 
-        if (active) {
-            T uc[4][3], pc[4][3];
-            const int l[4] = {lc.x, lc.y, lc.z, lc.w};
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                T tmp[4];
-                load_slot<T, 4>(us + 4 * l[c], tmp);
-                uc[c][0] = tmp[0]; uc[c][1] = tmp[1]; uc[c][2] = tmp[2];
-                if constexpr (Cfg::kNeedP) {
-                    load_slot<T, 4>(ps + 4 * l[c], tmp);
-                    pc[c][0] = tmp[0]; pc[c][1] = tmp[1]; pc[c][2] = tmp[2];
-                }
-            }
-            T psi = 0, quad = 0;
-            T g[4][3], dg[4][3], hp[4][3];
-            elem_eval<T, KIND, OPS>(rec.s, uc, pc, psi, quad, g, dg, hp);
-            if constexpr (Cfg::kFun) e_acc += (double)psi;
-            if constexpr (Cfg::kQuad) q_acc += (double)quad;
-            if constexpr (NOUT > 0) {
-                const int sidx[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    T v[SS];
-                    int k = 0;
-                    if constexpr (Cfg::kGrad) { v[k] = g[c][0]; v[k + 1] = g[c][1]; v[k + 2] = g[c][2]; k += 3; }
-                    if constexpr (Cfg::kDiag) { v[k] = dg[c][0]; v[k + 1] = dg[c][1]; v[k + 2] = dg[c][2]; k += 3; }
-                    if constexpr (Cfg::kProd) { v[k] = hp[c][0]; v[k + 1] = hp[c][1]; v[k + 2] = hp[c][2]; k += 3; }
-#pragma unroll
-                    for (int j = 3 * NOUT; j < SS; ++j) v[j] = (T)0;
-                    store_slot<T, SS>(sl + sidx[c] * SS, v);
-                }
-            }
-        }
+        if (active) tile_compute<T, KIND, OPS>(rec.s, lc, s4, us, ps, axpy, alpha, sl, e_acc, q_acc);
         if constexpr (NOUT > 0) {
             __syncthreads();
-            if (tid < n_verts) {
-                const int s0 = voff[tid], s1 = voff[tid + 1];
-                T acc[3 * NOUT];
-#pragma unroll
-                for (int j = 0; j < 3 * NOUT; ++j) acc[j] = (T)0;
-                for (int s = s0; s < s1; ++s) {
-                    T v[SS];
-                    load_slot<T, SS>(sl + s * SS, v);
-#pragma unroll
-                    for (int j = 0; j < 3 * NOUT; ++j) acc[j] += v[j];
-                }
-                int k = 0;
-                if constexpr (Cfg::kGrad) { if (a.grad) red_row(a.grad, gv, a.ld_out, acc + k); k += 3; }
-                if constexpr (Cfg::kDiag) { if (a.diag) red_row(a.diag, gv, a.ld_out, acc + k); k += 3; }
-                if constexpr (Cfg::kProd) { if (a.prod) red_row(a.prod, gv, a.ld_out, acc + k); k += 3; }
-            }
+            tile_reduce<T, OPS>(tid, n_verts, vperm, voff, sl, vbuf);
+            __syncthreads();
+            tile_flush<T, OPS>(tid, n_verts, gv, vbuf, a);
         }
         __syncthreads();
         h = hn;
@@ -382,6 +413,221 @@ __global__ void __launch_bounds__(kTileTets, (sizeof(T) == 4 ? 2 : 1)) fem_tile_
         finish_scalars<T, kTileTets>(e_acc, q_acc, a.partials, a.counter, Cfg::kFun ? a.fun : nullptr,
                                      Cfg::kQuad ? a.quad : nullptr, Cfg::kFun ? a.fun_d : nullptr,
                                      Cfg::kQuad ? a.quad_d : nullptr);
+}
+
+// ---- PIPELINED kernel (APL_SCATTER_TILE, the product path) ------------------------------------------
+//
+// 9 warps per CTA.  Warp 8 is the PRODUCER: for every tile it issues TMA bulk copies
+// (cp.async.bulk, completion on an mbarrier) of the tile's static planes, connectivity, slots and
+// vertex tables into the next free shared-memory stage, waits for the vertex table, and gathers the
+// tile's vertices with cp.async (LDGSTS) into the same stage.  Warps 0-7 are CONSUMERS (one thread
+// per tet): wait for the stage, compute, write slots, reduce, flush with vector REDs, release the
+// stage.  kStages tiles are in flight per CTA, so global-memory latency is off the critical path.
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async(unsigned dst, const void* src) {
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(unsigned bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <typename T>
+__device__ __forceinline__ void gather_row_async(unsigned dst, const T* base, int v, int ld) {
+    if (ld == 4) {
+        const char* src = reinterpret_cast<const char*>(base) + (size_t)v * 4 * sizeof(T);
+        cp_async<16>(dst, src);
+        if constexpr (sizeof(T) == 8) cp_async<16>(dst + 16, src + 16);
+    } else {
+        const T* src = base + 3ll * v;
+        cp_async<sizeof(T)>(dst, src);
+        cp_async<sizeof(T)>(dst + sizeof(T), src + 1);
+        cp_async<sizeof(T)>(dst + 2 * sizeof(T), src + 2);
+    }
+}
+
+constexpr int kPipeThreads = kTileTets + 32;
+
+template <typename T, int KIND, int OPS>
+struct PipeCfg {
+    using Cfg = TileCfg<T, OPS>;
+    static constexpr int NREC = RecSize<KIND>::value;
+    static constexpr int NPL = Rec<T, NREC>::NPL;
+    // one stage (all offsets multiples of 16 bytes)
+    static constexpr size_t oPlanes = 0;
+    static constexpr size_t oConn = oPlanes + (size_t)NPL * kTileTets * 16;
+    static constexpr size_t oSlots = oConn + (size_t)kTileTets * 4;
+    static constexpr size_t oVerts = oSlots + (size_t)kTileTets * 8;
+    static constexpr size_t oVperm = oVerts + (size_t)kTileVerts * 4;
+    static constexpr size_t oVoff = oVperm + 256;
+    static constexpr size_t oVbuf = oVoff + 528;
+    static constexpr size_t oHdr = oVbuf + Cfg::kVbufBytes;
+    static constexpr size_t kStageBytes = oHdr + 16;
+    static constexpr size_t kFixedBytes = Cfg::kSlotBytes + 128;  // slots + mbarriers
+    // as many stages as fit two CTAs per SM (>= 2 always, <= 4)
+    static constexpr size_t kBudget = 113 * 1024;
+    static constexpr int kFit = (int)((kBudget > kFixedBytes ? kBudget - kFixedBytes : 0) / kStageBytes);
+    static constexpr int kStages = kFit < 2 ? 2 : (kFit > 4 ? 4 : kFit);
+    static constexpr size_t kSmemBytes = kFixedBytes + (size_t)kStages * kStageBytes;
+};
+
+template <typename T, int KIND, int OPS>
+__global__ void __launch_bounds__(kPipeThreads, (sizeof(T) == 4 ? 2 : 1)) fem_pipe_kernel(const FemArgs<T> a) {
+    using Cfg = TileCfg<T, OPS>;
+    using PC = PipeCfg<T, KIND, OPS>;
+    constexpr int NOUT = Cfg::NOUT;
+    constexpr int S = PC::kStages;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // [0,128): mbarriers full[S], vfull[S], empty[S];  then the slot buffer;  then S stages
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw);
+    T* sl = reinterpret_cast<T*>(smem_raw + 128);
+    unsigned char* stages = smem_raw + PC::kFixedBytes;
+    const unsigned bar0 = smem_u32(bars);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto vfull = [&](int s) { return bar0 + 8u * (S + s); };
+    auto empty = [&](int s) { return bar0 + 8u * (2 * S + s); };
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    double e_acc = 0.0, q_acc = 0.0;
+    if (fem_skip(a)) return;
+    const bool axpy = a.axpy_p != nullptr;
+    const T alpha = axpy ? (T)__ldcg(a.scal + a.alpha_idx) : (T)0;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full(s), 33);         // 32 gather lanes + the expect_tx arrival
+            mbar_init(vfull(s), 1);
+            mbar_init(empty(s), kTileTets);  // every consumer thread releases the stage
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp == kTileTets / 32) {
+        // ================================= producer warp =================================
+        for (int it = 0; it < my_tiles; ++it) {
+            const int s = it % S;
+            const unsigned ph = (unsigned)(it / S) & 1u;
+            const int tile = blockIdx.x + it * gridDim.x;
+            unsigned char* st = stages + (size_t)s * PC::kStageBytes;
+            const unsigned st32 = smem_u32(st);
+            mbar_wait(empty(s), ph ^ 1u);
+            int4 h = make_int4(0, 0, 0, 0);
+            if (lane == 0) h = __ldg(a.tiles + tile);
+            h.x = __shfl_sync(0xffffffffu, h.x, 0);
+            h.y = __shfl_sync(0xffffffffu, h.y, 0);
+            h.z = __shfl_sync(0xffffffffu, h.z, 0);
+            h.w = __shfl_sync(0xffffffffu, h.w, 0);
+            const int n_tets = h.y & 0xffff, n_verts = h.y >> 16;
+            if (lane == 0) {
+                *reinterpret_cast<int4*>(st + PC::oHdr) = h;
+                // vertex tables first: the gather below depends on them
+                const unsigned bv = ((unsigned)n_verts * 4u + 15u) & ~15u;
+                unsigned vbytes = bv;
+                if constexpr (NOUT > 0) vbytes += (((unsigned)n_verts + 15u) & ~15u) + ((((unsigned)n_verts + 1u) * 2u + 15u) & ~15u);
+                mbar_expect_tx(vfull(s), vbytes);
+                bulk_g2s(st32 + (unsigned)PC::oVerts, a.tile_verts + h.z, bv, vfull(s));
+                if constexpr (NOUT > 0) {
+                    bulk_g2s(st32 + (unsigned)PC::oVperm, a.tile_vperm + h.z, ((unsigned)n_verts + 15u) & ~15u, vfull(s));
+                    bulk_g2s(st32 + (unsigned)PC::oVoff, a.tile_voff + h.w, (((unsigned)n_verts + 1u) * 2u + 15u) & ~15u,
+                             vfull(s));
+                }
+                // static per-tet data
+                const unsigned bp = (unsigned)n_tets * 16u;
+                const unsigned bc = ((unsigned)n_tets * 4u + 15u) & ~15u;
+                const unsigned bs = ((unsigned)n_tets * 8u + 15u) & ~15u;
+                mbar_expect_tx(full(s), (unsigned)PC::NPL * bp + bc + (NOUT > 0 ? bs : 0u));
+#pragma unroll
+                for (int k = 0; k < PC::NPL; ++k)
+                    bulk_g2s(st32 + (unsigned)(PC::oPlanes + (size_t)k * kTileTets * 16),
+                             a.planes + k * a.plane_stride + h.x, bp, full(s));
+                bulk_g2s(st32 + (unsigned)PC::oConn, a.conn + h.x, bc, full(s));
+                if constexpr (NOUT > 0) bulk_g2s(st32 + (unsigned)PC::oSlots, a.slots + h.x, bs, full(s));
+            }
+            // gather this tile's vertices as soon as its vertex table has landed
+            mbar_wait(vfull(s), ph);
+            const int* verts = reinterpret_cast<const int*>(st + PC::oVerts);
+            const unsigned us32 = st32 + (unsigned)PC::oVbuf;
+            const unsigned ps32 = us32 + 4u * kTileVerts * (unsigned)sizeof(T);
+            for (int v = lane; v < n_verts; v += 32) {
+                const int gv = verts[v];
+                gather_row_async<T>(us32 + (unsigned)v * 4u * (unsigned)sizeof(T), a.u, gv, a.ld_in);
+                if constexpr (Cfg::kNeedP) gather_row_async<T>(ps32 + (unsigned)v * 4u * (unsigned)sizeof(T), a.p, gv, a.ld_in);
+                else if (axpy) gather_row_async<T>(ps32 + (unsigned)v * 4u * (unsigned)sizeof(T), a.axpy_p, gv, a.ld_in);
+            }
+            cp_async_arrive_noinc(full(s));
+        }
+    } else {
+        // ================================= consumer warps ================================
+        for (int it = 0; it < my_tiles; ++it) {
+            const int s = it % S;
+            const unsigned ph = (unsigned)(it / S) & 1u;
+            unsigned char* st = stages + (size_t)s * PC::kStageBytes;
+            mbar_wait(full(s), ph);
+            const int4 h = *reinterpret_cast<const int4*>(st + PC::oHdr);
+            const int n_tets = h.y & 0xffff, n_verts = h.y >> 16;
+            T* vbuf = reinterpret_cast<T*>(st + PC::oVbuf);
+            const T* us = vbuf;
+            const T* ps = vbuf + 4 * kTileVerts;
+            if (tid < n_tets) {
+                Rec<T, PC::NREC> rec;
+#pragma unroll
+                for (int k = 0; k < PC::NPL; ++k)
+                    rec.q[k] = reinterpret_cast<const uint4*>(st + PC::oPlanes + (size_t)k * kTileTets * 16)[tid];
+                const uchar4 lc = reinterpret_cast<const uchar4*>(st + PC::oConn)[tid];
+                ushort4 s4 = make_ushort4(0, 0, 0, 0);
+                if constexpr (NOUT > 0) s4 = reinterpret_cast<const ushort4*>(st + PC::oSlots)[tid];
+                tile_compute<T, KIND, OPS>(rec.s, lc, s4, us, ps, axpy, alpha, sl, e_acc, q_acc);
+            }
+            if constexpr (NOUT > 0) {
+                consumer_sync();
+                tile_reduce<T, OPS>(tid, n_verts, st + PC::oVperm, reinterpret_cast<const unsigned short*>(st + PC::oVoff),
+                                    sl, vbuf);
+                consumer_sync();
+                const int gv = tid < n_verts ? reinterpret_cast<const int*>(st + PC::oVerts)[tid] : 0;
+                tile_flush<T, OPS>(tid, n_verts, gv, vbuf, a);
+            }
+            mbar_arrive(empty(s));
+        }
+    }
+    if constexpr (Cfg::kFun || Cfg::kQuad)
+        finish_scalars<T, kPipeThreads>(e_acc, q_acc, a.partials, a.counter, Cfg::kFun ? a.fun : nullptr,
+                                        Cfg::kQuad ? a.quad : nullptr, Cfg::kFun ? a.fun_d : nullptr,
+                                        Cfg::kQuad ? a.quad_d : nullptr);
 }
 
 // ---- ATOMIC kernel (baseline) -----------------------------------------------------------------------
@@ -454,6 +700,21 @@ int launch_one(const apl_fem* fem, const FemArgs<T>& args, int scatter, cudaStre
     using Cfg = TileCfg<T, OPS>;
     if (args.n_tiles == 0) return APL_OK;
     if (scatter == APL_SCATTER_TILE) {
+        using PC = PipeCfg<T, KIND, OPS>;
+        static int blocks_per_sm = -1;
+        auto kern = fem_pipe_kernel<T, KIND, OPS>;
+        if (blocks_per_sm < 0) {
+            APL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)PC::kSmemBytes));
+            int b = 0;
+            APL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kPipeThreads, PC::kSmemBytes));
+            blocks_per_sm = b > 0 ? b : 1;
+        }
+        int grid = fem->num_sms * blocks_per_sm;
+        if (grid > args.n_tiles) grid = args.n_tiles;
+        if (grid > fem->max_grid) grid = fem->max_grid;
+        kern<<<grid, kPipeThreads, PC::kSmemBytes, stream>>>(args);
+    } else if (scatter == APL_SCATTER_TILE_SIMPLE) {
         static int blocks_per_sm = -1;
         auto kern = fem_tile_kernel<T, KIND, OPS>;
         if (blocks_per_sm < 0) {

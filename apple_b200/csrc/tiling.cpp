@@ -2,7 +2,8 @@
 //
 // A tile is a run of <= 256 consecutive tets (in packed order) that together touch <= 256 distinct
 // vertices.  For every tile we store
-//   * the list of the global vertex ids it touches, by decreasing valence   (tile_verts)
+//   * the ascending list of the global vertex ids it touches           (tile_verts)
+//   * the same local ids ordered by decreasing valence                 (tile_vperm)
 //   * per tet, the tile-local id of each corner as one byte          (conn)
 //   * per tet corner, a slot in [0, 4*n_tets): slots are grouped by local vertex, so the element
 //     kernel can write every corner contribution to its own shared-memory slot (no atomics) and a
@@ -94,10 +95,11 @@ int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const d
     int64_t tile_start = 0;
     int32_t tile_id = 0;
 
-    // Closes the tile [tile_start, tile_end).  Local vertex ids are ordered by DECREASING valence
-    // (ties: ascending global id) so that the per-vertex slot reduction of the kernel has nearly
-    // uniform trip counts within a warp.  The vertex list starts at a multiple of 4 entries and the
-    // offset list at a multiple of 8 entries (16-byte aligned for bulk copies).
+    // Closes the tile [tile_start, tile_end).  Local vertex ids ascend with the global id (coalesced
+    // gathers and REDs); tile_vperm lists the local ids by DECREASING valence so that the per-vertex
+    // slot reduction of the kernel has nearly uniform trip counts within a warp.  The vertex list
+    // starts at a multiple of 16 entries and the offset list at a multiple of 8 entries, i.e. every
+    // per-tile table is 16-byte aligned for bulk copies.
     auto close_tile = [&](int64_t tile_end) {
         const int nt = (int)(tile_end - tile_start);
         if (nt == 0) return;
@@ -111,22 +113,27 @@ int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const d
             const int32_t* c = cells + 4 * out.order[(size_t)pos];
             for (int a = 0; a < 4; ++a) ++cnt[lid[(size_t)c[a]]];
         }
-        std::sort(perm, perm + nv, [&](int a, int b) {
-            if (cnt[a] != cnt[b]) return cnt[a] > cnt[b];
-            return verts[a] < verts[b];
-        });
-        while (out.tile_verts.size() % 4) out.tile_verts.push_back(0);
+        std::sort(perm, perm + nv, [&](int a, int b) { return verts[a] < verts[b]; });
+        while (out.tile_verts.size() % 16) {
+            out.tile_verts.push_back(0);
+            out.tile_vperm.push_back(0);
+        }
         while (out.tile_voff.size() % 8) out.tile_voff.push_back(0);
         const int32_t vert_start = (int32_t)out.tile_verts.size();
         const int32_t voff_start = (int32_t)out.tile_voff.size();
         off[0] = 0;
+        int32_t cnt_new[kTileVerts];
         for (int l = 0; l < nv; ++l) {
             const int old = perm[l];
             lid[(size_t)verts[old]] = l;
             out.tile_verts.push_back(verts[old]);
+            cnt_new[l] = cnt[old];
             off[l + 1] = off[l] + cnt[old];
         }
         for (int l = 0; l <= nv; ++l) out.tile_voff.push_back((uint16_t)off[l]);
+        for (int l = 0; l < nv; ++l) perm[l] = l;
+        std::stable_sort(perm, perm + nv, [&](int a, int b) { return cnt_new[a] > cnt_new[b]; });
+        for (int l = 0; l < nv; ++l) out.tile_vperm.push_back((uint8_t)perm[l]);
         out.tiles.push_back((int32_t)tile_start);
         out.tiles.push_back(nt);
         out.tiles.push_back(vert_start);
@@ -168,7 +175,10 @@ int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const d
     }
     close_tile(n_cells);
     // pad the tables so that 16-byte granular bulk copies of the last tile stay in bounds
-    for (int k = 0; k < 8; ++k) out.tile_verts.push_back(0);
+    for (int k = 0; k < 16; ++k) {
+        out.tile_verts.push_back(0);
+        out.tile_vperm.push_back(0);
+    }
     for (int k = 0; k < 16; ++k) out.tile_voff.push_back(0);
     if (out.tile_verts.size() > (size_t)INT32_MAX || out.tile_voff.size() > (size_t)INT32_MAX) {
         set_error("tile vertex table exceeds int32 range");

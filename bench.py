@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=58, help="hexes per cube edge (5 tets per hex)")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--scatter", default="tile", choices=["tile", "atomic"])
+    ap.add_argument("--scatter", default="tile", choices=["tile", "atomic", "tile_simple"])
     ap.add_argument("--potentials", default="snh,arap")
     ap.add_argument("--pncg-iters", type=int, default=200)
     ap.add_argument("--no-pncg", action="store_true")
@@ -208,7 +208,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     dtype = torch.float32 if args.dtype == "f32" else torch.float64
     w = 4 if args.dtype == "f32" else 8
-    config.scatter = _lib.SCATTER_TILE if args.scatter == "tile" else _lib.SCATTER_ATOMIC
+    config.scatter = {"tile": _lib.SCATTER_TILE, "atomic": _lib.SCATTER_ATOMIC,
+                      "tile_simple": _lib.SCATTER_TILE_SIMPLE}[args.scatter]
     kinds = args.potentials.split(",")
 
     mesh, u, p = build_mesh(args.n)
@@ -411,7 +412,7 @@ def sweep(args, mesh, u, p, dtype, dev, flush):
                 outs = {k: torch.zeros((V, ld), dtype=dt, device=dev) for k in ("grad", "diag", "prod")}
                 fun = torch.zeros(1, dtype=dt, device=dev); quad = torch.zeros(1, dtype=dt, device=dev)
                 for ops in (1, 2, 4, 8, 16, 7, 11, 15):
-                    for scatter in (0, 1):
+                    for scatter in (0, 2, 1):
                         ts = []
                         for i in range(8):
                             flush()
@@ -423,7 +424,7 @@ def sweep(args, mesh, u, p, dtype, dev, flush):
                             if i >= 2:
                                 ts.append(a.elapsed_time(b))
                         ms = float(np.mean(ts))
-                        rows.append((dt_name, kind, ld, ops, "tile" if scatter == 0 else "atomic", ms, T / ms / 1e6))
+                        rows.append((dt_name, kind, ld, ops, {0: "tile", 1: "atomic", 2: "simple"}[scatter], ms, T / ms / 1e6))
     print("dtype kind ld ops scatter ms Gtets/s", file=sys.stderr)
     for r in rows:
         print(f"{r[0]} {r[1]} {r[2]} {r[3]:2d} {r[4]:6s} {r[5]:8.4f} {r[6]:8.2f}", file=sys.stderr)

@@ -50,8 +50,10 @@ extern "C" {
 #define APL_OP_HESS_QUAD 16 /* WarpPotentialFem.hess_quad  warp/fem/_base.py:187-194, kernel :353-383 */
 
 /* assembly strategy */
-#define APL_SCATTER_TILE 0   /* shared-memory tile gather, in-tile slot reduction, one RED per tile vertex */
+#define APL_SCATTER_TILE 0   /* TMA/mbarrier-pipelined tiles: shared-memory gather, in-tile slot reduction, one
+                                vector RED per tile vertex and field (the product path) */
 #define APL_SCATTER_ATOMIC 1 /* one thread per tet, direct gathers and 12 REDs per field (reference-like) */
+#define APL_SCATTER_TILE_SIMPLE 2 /* same tiles without the producer warp / bulk-copy pipeline */
 
 typedef struct apl_fem apl_fem_t;   /* one FEM potential: replaces WarpPotentialFem (warp/fem/_base.py:39) */
 typedef struct apl_pncg apl_pncg_t; /* fused PNCG workspace (liblaf.peach.optim.PNCG, external to the reference) */
@@ -87,11 +89,11 @@ int apl_fem_info(const apl_fem_t* fem, int64_t info[10]);
  *   order      int64 (n_cells,)  : packed position -> caller's cell index
  *   conn       uint8 (n_cells,4) : tile-local vertex id per corner (packed order)
  *   slots      uint16(n_cells,4) : in-tile reduction slot per corner (packed order)
- *   tile_verts int32 (info[3])   : global vertex id per tile-local id, starting at vert_start;
- *                                  local ids are ordered by decreasing valence within the tile
- *   tile_voff  uint16(info[8])   : per tile, n_verts+1 slot offsets starting at voff_start */
+ *   tile_verts int32 (info[3])   : global vertex id per tile-local id (ascending), from vert_start
+ *   tile_voff  uint16(info[8])   : per tile, n_verts+1 slot offsets starting at voff_start
+ *   tile_vperm uint8 (info[3])   : per tile, the local ids ordered by decreasing valence */
 int apl_fem_host_tables(const apl_fem_t* fem, int32_t* tiles, int64_t* order, uint8_t* conn,
-                        uint16_t* slots, int32_t* tile_verts, uint16_t* tile_voff);
+                        uint16_t* slots, int32_t* tile_verts, uint16_t* tile_voff, uint8_t* tile_vperm);
 
 /* Replace per-cell materials in place (HOST arrays in the caller's cell order; NULL = keep).
  * Replaces re-creating the Materials struct (warp/fem/utils/_material.py:15-31). */

@@ -24,7 +24,7 @@ def _dev(a, dtype, ld=3):
     return t.contiguous()
 
 
-@pytest.mark.parametrize("scatter", [0, 1], ids=["tile", "atomic"])
+@pytest.mark.parametrize("scatter", [0, 1, 2], ids=["tile", "atomic", "tile_simple"])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
 @pytest.mark.parametrize("kind", KINDS)
 def test_five_operators_match_oracle(native_lib, case, kind, dtype, scatter):
@@ -52,10 +52,11 @@ def test_five_operators_match_oracle(native_lib, case, kind, dtype, scatter):
         assert rel_err(out.cpu(), ref) < tol, name
 
 
+@pytest.mark.parametrize("scatter", [0, 2], ids=["tile", "tile_simple"])
 @pytest.mark.parametrize("ld", [3, 4])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
 @pytest.mark.parametrize("kind", KINDS)
-def test_fused_pass_matches_separate_operators(native_lib, case, kind, dtype, ld):
+def test_fused_pass_matches_separate_operators(native_lib, case, kind, dtype, ld, scatter):
     """One pass computing {fun, grad, hess_diag, hess_prod} + hess_quad == five separate calls,
     for both nodal layouts (vec3 rows and 16-byte padded rows); outputs accumulate."""
     from apple_b200 import _lib
@@ -63,7 +64,7 @@ def test_fused_pass_matches_separate_operators(native_lib, case, kind, dtype, ld
     mesh, u, p = case
     V = mesh.n_points
     ora = oracle_potential(kind, mesh)
-    pot = cuda_potential(kind, mesh, dtype)
+    pot = cuda_potential(kind, mesh, dtype, scatter=scatter)
     ud, pd = _dev(u, dtype, ld), _dev(p, dtype, ld)
     fun = torch.full((1,), 2.0, dtype=dtype, device="cuda")       # accumulate semantics: start non-zero
     quad = torch.zeros(1, dtype=dtype, device="cuda")

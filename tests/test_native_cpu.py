@@ -62,30 +62,32 @@ def _host_tables(native_lib, mesh, kind=0, with_points=True):
     nt, nv, nvo = info[2], info[3], info[8]
     tiles = np.zeros((nt, 6), np.int32); order = np.zeros(T, np.int64)
     conn = np.zeros((T, 4), np.uint8); slots = np.zeros((T, 4), np.uint16)
-    tv = np.zeros(nv, np.int32); voff = np.zeros(nvo, np.uint16)
-    native_lib.apl_fem_host_tables(h, P(tiles), P(order), P(conn), P(slots), P(tv), P(voff))
+    tv = np.zeros(nv, np.int32); voff = np.zeros(nvo, np.uint16); vperm = np.zeros(nv, np.uint8)
+    native_lib.apl_fem_host_tables(h, P(tiles), P(order), P(conn), P(slots), P(tv), P(voff), P(vperm))
     native_lib.apl_fem_destroy(h)
-    return tiles, order, conn, slots, tv, voff
+    return tiles, order, conn, slots, tv, voff, vperm
 
 
 @pytest.mark.parametrize("with_points", [True, False])
 def test_tiling_invariants(native_lib, with_points):
     mesh, _, _ = make_case(n=9, seed=0, morton=False)
-    tiles, order, conn, slots, tv, voff = _host_tables(native_lib, mesh, with_points=with_points)
+    tiles, order, conn, slots, tv, voff, vperm = _host_tables(native_lib, mesh, with_points=with_points)
     T = mesh.n_cells
     assert sorted(order.tolist()) == list(range(T))          # a permutation of the cells
     if not with_points:
         assert (order == np.arange(T)).all()                 # NULL points keeps the caller's order
     assert tiles[:, 1].sum() == T and (tiles[:, 1] <= 256).all() and (tiles[:, 3] <= 256).all()
     assert (tiles[1:, 0] == tiles[:-1, 0] + tiles[:-1, 1]).all()
-    assert (tiles[:, 0] % 4 == 0).all() and (tiles[:, 2] % 4 == 0).all() and (tiles[:, 4] % 8 == 0).all()
+    assert (tiles[:, 0] % 4 == 0).all() and (tiles[:, 2] % 16 == 0).all() and (tiles[:, 4] % 8 == 0).all()
     for t, (ts, n, vs, nv, vo, _) in enumerate(tiles):
         gl = tv[vs:vs + nv]
-        assert len(set(gl.tolist())) == nv                   # distinct
+        assert (np.diff(gl) > 0).all()                       # ascending, distinct
         assert np.array_equal(gl[conn[ts:ts + n]], mesh.cells[order[ts:ts + n]])   # connectivity round trip
         off = voff[vo: vo + nv + 1].astype(int)
         assert off[0] == 0 and off[-1] == 4 * n
-        assert (np.diff(np.diff(off)) <= 0).all()            # local ids ordered by decreasing valence
+        perm = vperm[vs:vs + nv].astype(int)
+        assert sorted(perm.tolist()) == list(range(nv))      # a permutation of the local ids ...
+        assert (np.diff(np.diff(off)[perm]) <= 0).all()      # ... by decreasing valence
         s = slots[ts:ts + n].ravel().astype(int); l = conn[ts:ts + n].ravel().astype(int)
         assert sorted(s.tolist()) == list(range(4 * n))      # every corner owns exactly one slot
         assert ((s >= off[l]) & (s < off[l + 1])).all()      # ... inside its vertex's range
