@@ -31,6 +31,10 @@ COMMON = [
     "-Xcompiler",
     "-O3",
 ]
+if os.environ.get("APL_PROFILE_KNOBS"):  # profiling-only kernel knobs (never set for the product build)
+    COMMON.append("-DAPL_PROFILE_KNOBS")
+if os.environ.get("APL_TILE_TETS"):
+    COMMON.append("-DAPL_TILE_TETS=" + os.environ["APL_TILE_TETS"])
 
 
 def _units():

@@ -293,7 +293,7 @@ int apl_fem_create(int kind, int dtype, int64_t n_cells, int64_t n_points, const
         cudaDeviceProp prop;
         APL_TRY(cudaGetDeviceProperties(&prop, device));
         f->num_sms = prop.multiProcessorCount;
-        f->max_grid = f->num_sms * 8;
+        f->max_grid = f->num_sms * 16;
         auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
             cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
             if (e != cudaSuccess) return e;

@@ -10,8 +10,11 @@
 
 namespace apl {
 
-constexpr int kTileTets = 256;   // tets per tile == threads per CTA
-constexpr int kTileVerts = 256;  // max distinct vertices per tile (uint8 local ids)
+#ifndef APL_TILE_TETS
+#define APL_TILE_TETS 256
+#endif
+constexpr int kTileTets = APL_TILE_TETS;   // tets per tile == consumer threads per CTA
+constexpr int kTileVerts = APL_TILE_TETS * 3 / 4;  // max distinct vertices per tile (uint8 local ids, <= 256)
 
 void set_error(const std::string& msg);
 

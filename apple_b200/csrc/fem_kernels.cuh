@@ -20,6 +20,8 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "common.h"
 #include "elem_math.cuh"
 
@@ -54,6 +56,9 @@ struct FemArgs {
     int skip_a = -1, skip_b = -1;    // the launch is a no-op if scal[skip_a] != 0 or scal[skip_b] != 0
     double* fun_d = nullptr;         // double-precision sinks for the energy / quadratic form
     double* quad_d = nullptr;
+#ifdef APL_PROFILE_KNOBS
+    int knobs = 0;  // profiling only: 1 skip REDs, 2 plain stores instead of REDs, 4 skip reduce, 8 skip slot stores
+#endif
 };
 
 template <typename T>
@@ -63,6 +68,10 @@ __device__ __forceinline__ bool fem_skip(const FemArgs<T>& a) {
     if (a.skip_b >= 0 && __ldcg(a.scal + a.skip_b) != 0.0) return true;
     return false;
 }
+
+#ifdef APL_PROFILE_KNOBS
+__device__ int g_knobs = 0;
+#endif
 
 // ---- small device helpers --------------------------------------------------------------------
 
@@ -209,21 +218,73 @@ struct TileCfg {
     static constexpr bool kQuad = (OPS & APL_OP_HESS_QUAD) != 0;
     static constexpr bool kNeedP = kProd || kQuad;
     static constexpr int NOUT = (kGrad ? 1 : 0) + (kDiag ? 1 : 0) + (kProd ? 1 : 0);
-    // slot stride in scalars: 3*NOUT rounded up so that a slot is a whole number of 16-byte vectors
+    // scalars per slot: 3*NOUT rounded up to whole 16-byte planes plus, for fp32, one 8-byte tail plane
     static constexpr int SS = (NOUT == 0) ? 0
                               : (NOUT == 1) ? 4
-                              : (sizeof(T) == 4) ? (NOUT == 2 ? 8 : 12) : (NOUT == 2 ? 6 : 10);
-    static constexpr int kNSlots = 4 * kTileTets;
+                              : (sizeof(T) == 4) ? (NOUT == 2 ? 6 : 10) : (NOUT == 2 ? 6 : 10);
+    static constexpr int kNSlots = 4 * kTileTets + kTileVerts;
     // per-vertex buffer: u (4 scalars) and p (4 scalars) during compute, then reused for the 3*NOUT
     // reduced sums of each vertex between the reduce and the flush phase
     static constexpr int VB = (3 * NOUT > 8) ? 12 : 8;
     static constexpr size_t kVbufBytes = (size_t)kTileVerts * VB * sizeof(T);
     static constexpr size_t kSlotBytes = (size_t)kNSlots * SS * sizeof(T);
-    static constexpr size_t kVoffBytes = NOUT ? 528 : 0;  // 257 uint16, rounded to 16 bytes
-    static constexpr size_t kVpermBytes = NOUT ? 256 : 0;
+    static constexpr size_t kVoffRaw = ((size_t)(kTileVerts + 1) * 2 + 15) / 16 * 16;  // n_verts+1 uint16
+    static constexpr size_t kVoffBytes = NOUT ? kVoffRaw : 0;
+    static constexpr size_t kVpermBytes = NOUT ? (size_t)kTileVerts : 0;
     // simple (unpipelined) kernel
     static constexpr size_t kSmemBytes = kVbufBytes + kSlotBytes + kVoffBytes + kVpermBytes;
 };
+
+// real slots of a tile (4 per tet) plus one padding slot per vertex with an even valence
+constexpr int kSlotsAlloc = 4 * kTileTets + kTileVerts;
+
+// The slot buffer is split into 16-byte planes: vector q of slot s lives at sl + (q * kNSlots + s) * 16 B.
+// One thread reading consecutive slots of "its" vertex and a warp of such threads then touch
+// neighbouring 16-byte words (see tile_reduce), instead of words a whole slot stride apart.
+template <typename T, int SS>
+__device__ __forceinline__ void store_slot_planes(T* sl, int s, const T* v) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int NQ = SS / VEC;  // full 16-byte planes; fp32 may add one 8-byte tail plane
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        uint4 w;
+        if constexpr (sizeof(T) == 4) {
+            w = make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
+                           __float_as_uint(v[4 * q + 3]));
+        } else {
+            const unsigned long long a = (unsigned long long)__double_as_longlong(v[2 * q]);
+            const unsigned long long b = (unsigned long long)__double_as_longlong(v[2 * q + 1]);
+            w = make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
+        }
+        reinterpret_cast<uint4*>(sl)[q * kSlotsAlloc + s] = w;
+    }
+    if constexpr (sizeof(T) == 4 && SS % 4 == 2) {
+        float2* tail = reinterpret_cast<float2*>(reinterpret_cast<uint4*>(sl) + NQ * kSlotsAlloc);
+        tail[s] = make_float2((float)v[4 * NQ], (float)v[4 * NQ + 1]);
+    }
+}
+
+template <typename T, int SS>
+__device__ __forceinline__ void load_slot_planes(const T* sl, int s, T* v) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int NQ = SS / VEC;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const uint4 w = reinterpret_cast<const uint4*>(sl)[q * kSlotsAlloc + s];
+        if constexpr (sizeof(T) == 4) {
+            v[4 * q] = __uint_as_float(w.x); v[4 * q + 1] = __uint_as_float(w.y);
+            v[4 * q + 2] = __uint_as_float(w.z); v[4 * q + 3] = __uint_as_float(w.w);
+        } else {
+            v[2 * q] = __longlong_as_double((long long)(((unsigned long long)w.y << 32) | w.x));
+            v[2 * q + 1] = __longlong_as_double((long long)(((unsigned long long)w.w << 32) | w.z));
+        }
+    }
+    if constexpr (sizeof(T) == 4 && SS % 4 == 2) {
+        const float2* tail = reinterpret_cast<const float2*>(reinterpret_cast<const uint4*>(sl) + NQ * kSlotsAlloc);
+        const float2 w = tail[s];
+        v[4 * NQ] = (T)w.x; v[4 * NQ + 1] = (T)w.y;
+    }
+}
 
 template <typename T, int SS>
 __device__ __forceinline__ void store_slot(T* dst, const T* v) {
@@ -297,32 +358,50 @@ __device__ __forceinline__ void tile_compute(const T* rec, uchar4 lc, ushort4 s4
             if constexpr (Cfg::kProd) { v[k] = hp[c][0]; v[k + 1] = hp[c][1]; v[k + 2] = hp[c][2]; k += 3; }
 #pragma unroll
             for (int j = 3 * NOUT; j < SS; ++j) v[j] = (T)0;
-            store_slot<T, SS>(sl + sidx[c] * SS, v);
+#ifdef APL_PROFILE_KNOBS
+            if (g_knobs & 8) continue;
+#endif
+            store_slot_planes<T, SS>(sl, sidx[c], v);
         }
     }
 }
 
-// Thread `tid` sums the slot range of the tid-th vertex in valence order (balanced trip counts per
-// warp) and parks the 3*NOUT sums in the vertex buffer at the vertex's ascending local id.
+// Threads 2t and 2t+1 together sum the slot range of the t-th vertex in valence order (balanced trip
+// counts per warp, all consumer warps busy), combine with one shuffle, and the even thread parks the
+// 3*NOUT sums in the vertex buffer at the vertex's ascending local id.
 template <typename T, int OPS>
 __device__ __forceinline__ void tile_reduce(int tid, int n_verts, const unsigned char* vperm,
                                             const unsigned short* voff, const T* sl, T* vbuf) {
     using Cfg = TileCfg<T, OPS>;
     constexpr int NOUT = Cfg::NOUT, SS = Cfg::SS;
-    if (tid < n_verts) {
-        const int v = vperm[tid];
-        const int s0 = voff[v], s1 = voff[v + 1];
+    const int half = tid & 1;
+    for (int t = tid >> 1; t < ((n_verts + 15) & ~15); t += kTileTets / 2) {
+        // (the bound is rounded up so that both threads of a pair, and whole half-warps, stay together
+        //  for the shuffle below; out-of-range pairs have cnt = 0)
+        int v = 0, s0 = 0, cnt = 0;
+        if (t < n_verts) {
+            v = vperm[t];
+            // voff is in reduce order; ranges are padded to odd lengths (bit 15 flags a padded range),
+            // so neighbouring pairs read slots an odd distance apart: conflict-free 16/8-byte loads.
+            const unsigned a0 = voff[t], a1 = voff[t + 1];
+            s0 = (int)(a0 & 0x7fffu);
+            cnt = (int)(a1 & 0x7fffu) - s0 - (int)(a0 >> 15);
+        }
         T acc[3 * NOUT];
 #pragma unroll
         for (int j = 0; j < 3 * NOUT; ++j) acc[j] = (T)0;
-        for (int s = s0; s < s1; ++s) {
+        for (int i = half; i < cnt; i += 2) {
             T val[SS];
-            load_slot<T, SS>(sl + s * SS, val);
+            load_slot_planes<T, SS>(sl, s0 + i, val);
 #pragma unroll
             for (int j = 0; j < 3 * NOUT; ++j) acc[j] += val[j];
         }
 #pragma unroll
-        for (int j = 0; j < 3 * NOUT; ++j) vbuf[v * (3 * NOUT) + j] = acc[j];
+        for (int j = 0; j < 3 * NOUT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+        if (half == 0 && t < n_verts) {
+#pragma unroll
+            for (int j = 0; j < 3 * NOUT; ++j) vbuf[v * (3 * NOUT) + j] = acc[j];
+        }
     }
 }
 
@@ -337,6 +416,15 @@ __device__ __forceinline__ void tile_flush(int tid, int n_verts, int gv, const T
 #pragma unroll
         for (int j = 0; j < 3 * NOUT; ++j) acc[j] = vbuf[tid * (3 * NOUT) + j];
         int k = 0;
+#ifdef APL_PROFILE_KNOBS
+        if (g_knobs & 1) return;
+        if (g_knobs & 2) {
+            if constexpr (Cfg::kGrad) { T* q = a.grad + (long long)a.ld_out * gv; q[0] = acc[k]; q[1] = acc[k + 1]; q[2] = acc[k + 2]; k += 3; }
+            if constexpr (Cfg::kDiag) { T* q = a.diag + (long long)a.ld_out * gv; q[0] = acc[k]; q[1] = acc[k + 1]; q[2] = acc[k + 2]; k += 3; }
+            if constexpr (Cfg::kProd) { T* q = a.prod + (long long)a.ld_out * gv; q[0] = acc[k]; q[1] = acc[k + 1]; q[2] = acc[k + 2]; k += 3; }
+            return;
+        }
+#endif
         if constexpr (Cfg::kGrad) { if (a.grad) red_row(a.grad, gv, a.ld_out, acc + k); k += 3; }
         if constexpr (Cfg::kDiag) { if (a.diag) red_row(a.diag, gv, a.ld_out, acc + k); k += 3; }
         if constexpr (Cfg::kProd) { if (a.prod) red_row(a.prod, gv, a.ld_out, acc + k); k += 3; }
@@ -461,7 +549,7 @@ __device__ __forceinline__ void cp_async(unsigned dst, const void* src) {
 __device__ __forceinline__ void cp_async_arrive_noinc(unsigned bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kTileTets) : "memory"); }
 
 template <typename T>
 __device__ __forceinline__ void gather_row_async(unsigned dst, const T* base, int v, int ld) {
@@ -484,39 +572,50 @@ struct PipeCfg {
     using Cfg = TileCfg<T, OPS>;
     static constexpr int NREC = RecSize<KIND>::value;
     static constexpr int NPL = Rec<T, NREC>::NPL;
-    // one stage (all offsets multiples of 16 bytes)
+    // one stage: per-tet static data + the gathered vertex fields (all offsets multiples of 16 bytes)
     static constexpr size_t oPlanes = 0;
     static constexpr size_t oConn = oPlanes + (size_t)NPL * kTileTets * 16;
     static constexpr size_t oSlots = oConn + (size_t)kTileTets * 4;
-    static constexpr size_t oVerts = oSlots + (size_t)kTileTets * 8;
-    static constexpr size_t oVperm = oVerts + (size_t)kTileVerts * 4;
-    static constexpr size_t oVoff = oVperm + 256;
-    static constexpr size_t oVbuf = oVoff + 528;
+    static constexpr size_t oVbuf = oSlots + (size_t)kTileTets * 8;
     static constexpr size_t oHdr = oVbuf + Cfg::kVbufBytes;
     static constexpr size_t kStageBytes = oHdr + 16;
-    static constexpr size_t kFixedBytes = Cfg::kSlotBytes + 128;  // slots + mbarriers
-    // as many stages as fit two CTAs per SM (>= 2 always, <= 4)
-    static constexpr size_t kBudget = 113 * 1024;
-    static constexpr int kFit = (int)((kBudget > kFixedBytes ? kBudget - kFixedBytes : 0) / kStageBytes);
+    // one vertex-table slot (requested one tile ahead of its stage): global ids, reduce order, slot offsets
+    static constexpr size_t oVerts = 0;
+    static constexpr size_t oVperm = oVerts + (size_t)kTileVerts * 4;
+    static constexpr size_t oVoff = oVperm + (size_t)kTileVerts;
+    static constexpr size_t kVtabBytes = oVoff + Cfg::kVoffRaw;
+    static constexpr size_t kBarBytes = 128;
+    // as many stages as fit the target number of CTAs per SM (>= 2 always, <= 4); vertex ring = stages + 1
+    static constexpr size_t kBudget = (size_t)(sizeof(T) == 4 ? 74 : 113) * 1024 * kTileTets / 256;
+    static constexpr size_t kFixedBytes = Cfg::kSlotBytes + kBarBytes + kVtabBytes;
+    static constexpr int kFit =
+        (int)((kBudget > kFixedBytes ? kBudget - kFixedBytes : 0) / (kStageBytes + kVtabBytes));
     static constexpr int kStages = kFit < 2 ? 2 : (kFit > 4 ? 4 : kFit);
-    static constexpr size_t kSmemBytes = kFixedBytes + (size_t)kStages * kStageBytes;
+    static constexpr int kVring = kStages + 1;
+    static constexpr size_t oSlotBuf = kBarBytes;
+    static constexpr size_t oVring = oSlotBuf + Cfg::kSlotBytes;
+    static constexpr size_t oStages = oVring + (size_t)kVring * kVtabBytes;
+    static constexpr size_t kSmemBytes = oStages + (size_t)kStages * kStageBytes;
 };
 
 template <typename T, int KIND, int OPS>
-__global__ void __launch_bounds__(kPipeThreads, (sizeof(T) == 4 ? 2 : 1)) fem_pipe_kernel(const FemArgs<T> a) {
+__global__ void __launch_bounds__(kPipeThreads, (sizeof(T) == 4 ? 3 : 1) * (256 / kTileTets))
+    fem_pipe_kernel(const FemArgs<T> a) {
     using Cfg = TileCfg<T, OPS>;
     using PC = PipeCfg<T, KIND, OPS>;
     constexpr int NOUT = Cfg::NOUT;
-    constexpr int S = PC::kStages;
+    constexpr int S = PC::kStages, SV = PC::kVring;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // [0,128): mbarriers full[S], vfull[S], empty[S];  then the slot buffer;  then S stages
+    // [0,128): mbarriers full[S], empty[S], vfull[SV];  slot buffer;  SV vertex-table slots;  S stages
+    static_assert(8 * (2 * S + SV) <= (int)PC::kBarBytes, "mbarrier area too small");
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw);
-    T* sl = reinterpret_cast<T*>(smem_raw + 128);
-    unsigned char* stages = smem_raw + PC::kFixedBytes;
+    T* sl = reinterpret_cast<T*>(smem_raw + PC::oSlotBuf);
+    unsigned char* vring = smem_raw + PC::oVring;
+    unsigned char* stages = smem_raw + PC::oStages;
     const unsigned bar0 = smem_u32(bars);
     auto full = [&](int s) { return bar0 + 8u * s; };
-    auto vfull = [&](int s) { return bar0 + 8u * (S + s); };
-    auto empty = [&](int s) { return bar0 + 8u * (2 * S + s); };
+    auto empty = [&](int s) { return bar0 + 8u * (S + s); };
+    auto vfull = [&](int s) { return bar0 + 8u * (2 * S + s); };
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -527,10 +626,10 @@ __global__ void __launch_bounds__(kPipeThreads, (sizeof(T) == 4 ? 2 : 1)) fem_pi
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full(s), 33);         // 32 gather lanes + the expect_tx arrival
-            mbar_init(vfull(s), 1);
+            mbar_init(full(s), 33);          // 32 gather lanes + the expect_tx arrival
             mbar_init(empty(s), kTileTets);  // every consumer thread releases the stage
         }
+        for (int s = 0; s < SV; ++s) mbar_init(vfull(s), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -539,34 +638,47 @@ __global__ void __launch_bounds__(kPipeThreads, (sizeof(T) == 4 ? 2 : 1)) fem_pi
 
     if (warp == kTileTets / 32) {
         // ================================= producer warp =================================
+        // Iteration `it`: wait until stage it % S is free, issue the bulk copies of tile `it`'s static
+        // data, request the vertex tables of tile `it + 1`, then gather tile `it`'s vertices (its
+        // tables were requested one iteration ago).  Headers are prefetched two iterations ahead, so
+        // the producer never waits on a fresh global load in steady state.
+        auto load_hdr = [&](int it) {
+            int4 h = make_int4(0, 0, 0, 0);
+            if (lane == 0 && it < my_tiles) h = __ldg(a.tiles + (blockIdx.x + it * gridDim.x));
+            return h;
+        };
+        auto request_vtab = [&](int it, const int4& h) {  // lane 0 only
+            const int sv = it % SV;
+            const unsigned vt32 = smem_u32(vring + (size_t)sv * PC::kVtabBytes);
+            const unsigned n_verts = (unsigned)(h.y >> 16);
+            const unsigned bv = (n_verts * 4u + 15u) & ~15u;
+            const unsigned bp = (n_verts + 15u) & ~15u, bo = ((n_verts + 1u) * 2u + 15u) & ~15u;
+            mbar_expect_tx(vfull(sv), bv + (NOUT > 0 ? bp + bo : 0u));
+            bulk_g2s(vt32 + (unsigned)PC::oVerts, a.tile_verts + h.z, bv, vfull(sv));
+            if constexpr (NOUT > 0) {
+                bulk_g2s(vt32 + (unsigned)PC::oVperm, a.tile_vperm + h.z, bp, vfull(sv));
+                bulk_g2s(vt32 + (unsigned)PC::oVoff, a.tile_voff + h.w, bo, vfull(sv));
+            }
+        };
+        int4 h_cur = load_hdr(0), h_nxt = load_hdr(1);
+        if (lane == 0) request_vtab(0, h_cur);
         for (int it = 0; it < my_tiles; ++it) {
             const int s = it % S;
             const unsigned ph = (unsigned)(it / S) & 1u;
-            const int tile = blockIdx.x + it * gridDim.x;
             unsigned char* st = stages + (size_t)s * PC::kStageBytes;
             const unsigned st32 = smem_u32(st);
-            mbar_wait(empty(s), ph ^ 1u);
-            int4 h = make_int4(0, 0, 0, 0);
-            if (lane == 0) h = __ldg(a.tiles + tile);
-            h.x = __shfl_sync(0xffffffffu, h.x, 0);
-            h.y = __shfl_sync(0xffffffffu, h.y, 0);
-            h.z = __shfl_sync(0xffffffffu, h.z, 0);
-            h.w = __shfl_sync(0xffffffffu, h.w, 0);
+            const int4 h_nn = load_hdr(it + 2);
+            int4 h;
+            h.x = __shfl_sync(0xffffffffu, h_cur.x, 0);
+            h.y = __shfl_sync(0xffffffffu, h_cur.y, 0);
+            h.z = __shfl_sync(0xffffffffu, h_cur.z, 0);
+            h.w = __shfl_sync(0xffffffffu, h_cur.w, 0);
             const int n_tets = h.y & 0xffff, n_verts = h.y >> 16;
+            // stage s free <=> the consumers are done with tile it - S, which also frees vertex slot
+            // (it + 1) % SV (last used by tile it + 1 - SV = it - S)
+            mbar_wait(empty(s), ph ^ 1u);
             if (lane == 0) {
                 *reinterpret_cast<int4*>(st + PC::oHdr) = h;
-                // vertex tables first: the gather below depends on them
-                const unsigned bv = ((unsigned)n_verts * 4u + 15u) & ~15u;
-                unsigned vbytes = bv;
-                if constexpr (NOUT > 0) vbytes += (((unsigned)n_verts + 15u) & ~15u) + ((((unsigned)n_verts + 1u) * 2u + 15u) & ~15u);
-                mbar_expect_tx(vfull(s), vbytes);
-                bulk_g2s(st32 + (unsigned)PC::oVerts, a.tile_verts + h.z, bv, vfull(s));
-                if constexpr (NOUT > 0) {
-                    bulk_g2s(st32 + (unsigned)PC::oVperm, a.tile_vperm + h.z, ((unsigned)n_verts + 15u) & ~15u, vfull(s));
-                    bulk_g2s(st32 + (unsigned)PC::oVoff, a.tile_voff + h.w, (((unsigned)n_verts + 1u) * 2u + 15u) & ~15u,
-                             vfull(s));
-                }
-                // static per-tet data
                 const unsigned bp = (unsigned)n_tets * 16u;
                 const unsigned bc = ((unsigned)n_tets * 4u + 15u) & ~15u;
                 const unsigned bs = ((unsigned)n_tets * 8u + 15u) & ~15u;
@@ -577,10 +689,12 @@ __global__ void __launch_bounds__(kPipeThreads, (sizeof(T) == 4 ? 2 : 1)) fem_pi
                              a.planes + k * a.plane_stride + h.x, bp, full(s));
                 bulk_g2s(st32 + (unsigned)PC::oConn, a.conn + h.x, bc, full(s));
                 if constexpr (NOUT > 0) bulk_g2s(st32 + (unsigned)PC::oSlots, a.slots + h.x, bs, full(s));
+                if (it + 1 < my_tiles) request_vtab(it + 1, h_nxt);
             }
-            // gather this tile's vertices as soon as its vertex table has landed
-            mbar_wait(vfull(s), ph);
-            const int* verts = reinterpret_cast<const int*>(st + PC::oVerts);
+            // gather: the tables of tile `it` were requested one iteration ago
+            const int sv = it % SV;
+            mbar_wait(vfull(sv), (unsigned)(it / SV) & 1u);
+            const int* verts = reinterpret_cast<const int*>(vring + (size_t)sv * PC::kVtabBytes + PC::oVerts);
             const unsigned us32 = st32 + (unsigned)PC::oVbuf;
             const unsigned ps32 = us32 + 4u * kTileVerts * (unsigned)sizeof(T);
             for (int v = lane; v < n_verts; v += 32) {
@@ -590,6 +704,8 @@ __global__ void __launch_bounds__(kPipeThreads, (sizeof(T) == 4 ? 2 : 1)) fem_pi
                 else if (axpy) gather_row_async<T>(ps32 + (unsigned)v * 4u * (unsigned)sizeof(T), a.axpy_p, gv, a.ld_in);
             }
             cp_async_arrive_noinc(full(s));
+            h_cur = h_nxt;
+            h_nxt = h_nn;
         }
     } else {
         // ================================= consumer warps ================================
@@ -597,12 +713,16 @@ __global__ void __launch_bounds__(kPipeThreads, (sizeof(T) == 4 ? 2 : 1)) fem_pi
             const int s = it % S;
             const unsigned ph = (unsigned)(it / S) & 1u;
             unsigned char* st = stages + (size_t)s * PC::kStageBytes;
+            const unsigned char* vt = vring + (size_t)(it % SV) * PC::kVtabBytes;
             mbar_wait(full(s), ph);
             const int4 h = *reinterpret_cast<const int4*>(st + PC::oHdr);
             const int n_tets = h.y & 0xffff, n_verts = h.y >> 16;
             T* vbuf = reinterpret_cast<T*>(st + PC::oVbuf);
             const T* us = vbuf;
             const T* ps = vbuf + 4 * kTileVerts;
+#ifdef APL_PROFILE_KNOBS
+            if (g_knobs & 32) { mbar_arrive(empty(s)); continue; }
+#endif
             if (tid < n_tets) {
                 Rec<T, PC::NREC> rec;
 #pragma unroll
@@ -614,11 +734,17 @@ __global__ void __launch_bounds__(kPipeThreads, (sizeof(T) == 4 ? 2 : 1)) fem_pi
                 tile_compute<T, KIND, OPS>(rec.s, lc, s4, us, ps, axpy, alpha, sl, e_acc, q_acc);
             }
             if constexpr (NOUT > 0) {
+#ifdef APL_PROFILE_KNOBS
+                if (!(g_knobs & 16))
+#endif
                 consumer_sync();
-                tile_reduce<T, OPS>(tid, n_verts, st + PC::oVperm, reinterpret_cast<const unsigned short*>(st + PC::oVoff),
+                tile_reduce<T, OPS>(tid, n_verts, vt + PC::oVperm, reinterpret_cast<const unsigned short*>(vt + PC::oVoff),
                                     sl, vbuf);
+#ifdef APL_PROFILE_KNOBS
+                if (!(g_knobs & 16))
+#endif
                 consumer_sync();
-                const int gv = tid < n_verts ? reinterpret_cast<const int*>(st + PC::oVerts)[tid] : 0;
+                const int gv = tid < n_verts ? reinterpret_cast<const int*>(vt + PC::oVerts)[tid] : 0;
                 tile_flush<T, OPS>(tid, n_verts, gv, vbuf, a);
             }
             mbar_arrive(empty(s));
@@ -699,6 +825,13 @@ template <typename T, int KIND, int OPS>
 int launch_one(const apl_fem* fem, const FemArgs<T>& args, int scatter, cudaStream_t stream) {
     using Cfg = TileCfg<T, OPS>;
     if (args.n_tiles == 0) return APL_OK;
+#ifdef APL_PROFILE_KNOBS
+    {
+        const char* e = getenv("APL_KNOBS");
+        const int k = e ? atoi(e) : 0;
+        cudaMemcpyToSymbolAsync(g_knobs, &k, sizeof(int), 0, cudaMemcpyHostToDevice, stream);
+    }
+#endif
     if (scatter == APL_SCATTER_TILE) {
         using PC = PipeCfg<T, KIND, OPS>;
         static int blocks_per_sm = -1;

@@ -121,32 +121,68 @@ int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const d
         while (out.tile_voff.size() % 8) out.tile_voff.push_back(0);
         const int32_t vert_start = (int32_t)out.tile_verts.size();
         const int32_t voff_start = (int32_t)out.tile_voff.size();
-        off[0] = 0;
         int32_t cnt_new[kTileVerts];
         for (int l = 0; l < nv; ++l) {
             const int old = perm[l];
             lid[(size_t)verts[old]] = l;
             out.tile_verts.push_back(verts[old]);
             cnt_new[l] = cnt[old];
-            off[l + 1] = off[l] + cnt[old];
         }
-        for (int l = 0; l <= nv; ++l) out.tile_voff.push_back((uint16_t)off[l]);
+        // reduce order: local ids by decreasing valence
         for (int l = 0; l < nv; ++l) perm[l] = l;
         std::stable_sort(perm, perm + nv, [&](int a, int b) { return cnt_new[a] > cnt_new[b]; });
         for (int l = 0; l < nv; ++l) out.tile_vperm.push_back((uint8_t)perm[l]);
+        // Slot ranges are laid out in REDUCE order and padded to odd lengths: reduce thread t reads
+        // start[t] + i, so neighbouring lanes are an odd number of slots apart and their 16-byte
+        // (and 8-byte) reads fall into distinct banks.  Bit 15 of an entry flags a padded range.
+        int32_t start[kTileVerts + 1];
+        start[0] = 0;
+        for (int t = 0; t < nv; ++t) {
+            const int c = cnt_new[perm[t]];
+            const int padded = c | 1;
+            start[t + 1] = start[t] + padded;
+            off[perm[t]] = start[t];
+            out.tile_voff.push_back((uint16_t)(start[t] | ((padded != c) ? 0x8000 : 0)));
+        }
+        out.tile_voff.push_back((uint16_t)start[nv]);
         out.tiles.push_back((int32_t)tile_start);
         out.tiles.push_back(nt);
         out.tiles.push_back(vert_start);
         out.tiles.push_back(nv);
         out.tiles.push_back(voff_start);
-        out.tiles.push_back(0);
-        for (int l = 0; l < nv; ++l) cnt[l] = 0;  // reuse as fill cursor
-        for (int64_t pos = tile_start; pos < tile_end; ++pos) {
-            const int32_t* c = cells + 4 * out.order[(size_t)pos];
+        out.tiles.push_back(start[nv]);
+        // Positions inside a vertex's range are free: choose them so that the 32 stores of one
+        // warp-wide STS (same corner of 32 consecutive tets) spread over the banks.  Bank of a slot
+        // in a 16-byte plane = slot mod 8 per quarter warp; mod 16 per half warp for the 8-byte plane.
+        uint8_t taken[4 * kTileTets + kTileVerts];
+        memset(taken, 0, sizeof(taken));
+        for (int64_t w0 = tile_start; w0 < tile_end; w0 += 32) {
+            const int64_t w1 = std::min(w0 + 32, tile_end);
             for (int a = 0; a < 4; ++a) {
-                const int l = lid[(size_t)c[a]];
-                out.conn[(size_t)pos * 4 + a] = (uint8_t)l;
-                out.slots[(size_t)pos * 4 + a] = (uint16_t)(off[l] + cnt[l]++);
+                int used_h[2][16], used_q[4][8];
+                memset(used_h, 0, sizeof(used_h));
+                memset(used_q, 0, sizeof(used_q));
+                for (int64_t pos = w0; pos < w1; ++pos) {
+                    const int32_t* c = cells + 4 * out.order[(size_t)pos];
+                    const int l = lid[(size_t)c[a]];
+                    const int half = (int)((pos - w0) >> 4), quarter = (int)((pos - w0) >> 3);
+                    const int base = off[l], n = cnt_new[l];
+                    int best = -1, best_cost = 1 << 30;
+                    for (int k = 0; k < n; ++k) {
+                        if (taken[base + k]) continue;
+                        const int cost = 4 * used_q[quarter][(base + k) & 7] + used_h[half][(base + k) & 15];
+                        if (cost < best_cost) {
+                            best_cost = cost;
+                            best = base + k;
+                            if (cost == 0) break;
+                        }
+                    }
+                    taken[best] = 1;
+                    ++used_h[half][best & 15];
+                    ++used_q[quarter][best & 7];
+                    out.conn[(size_t)pos * 4 + a] = (uint8_t)l;
+                    out.slots[(size_t)pos * 4 + a] = (uint16_t)best;
+                }
             }
         }
         verts.clear();

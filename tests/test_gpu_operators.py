@@ -167,7 +167,7 @@ def test_edge_cases(native_lib):
     mesh2, u2, p2 = make_case(n=4, seed=1)
     sub = TetMesh(mesh2.points, mesh2.cells[:257], cell_data={k: v[:257] for k, v in mesh2.cell_data.items()})
     pot2 = cuda_potential("arap", sub, torch.float64); ora2 = oracle_potential("arap", sub)
-    assert pot2.info["n_tiles"] == 2
+    assert pot2.info["n_tiles"] >= 2
     g = torch.zeros((sub.n_points, 3), dtype=torch.float64, device="cuda")
     pot2.grad(torch.as_tensor(u2, device="cuda"), g)
     ref = np.zeros((sub.n_points, 3)); ora2.grad(u2, ref)

@@ -77,20 +77,26 @@ def test_tiling_invariants(native_lib, with_points):
     if not with_points:
         assert (order == np.arange(T)).all()                 # NULL points keeps the caller's order
     assert tiles[:, 1].sum() == T and (tiles[:, 1] <= 256).all() and (tiles[:, 3] <= 256).all()
+    assert (tiles[:, 1] == 256).sum() >= len(tiles) - 2       # a regular mesh fills its tiles
     assert (tiles[1:, 0] == tiles[:-1, 0] + tiles[:-1, 1]).all()
     assert (tiles[:, 0] % 4 == 0).all() and (tiles[:, 2] % 16 == 0).all() and (tiles[:, 4] % 8 == 0).all()
     for t, (ts, n, vs, nv, vo, _) in enumerate(tiles):
         gl = tv[vs:vs + nv]
         assert (np.diff(gl) > 0).all()                       # ascending, distinct
         assert np.array_equal(gl[conn[ts:ts + n]], mesh.cells[order[ts:ts + n]])   # connectivity round trip
-        off = voff[vo: vo + nv + 1].astype(int)
-        assert off[0] == 0 and off[-1] == 4 * n
+        raw = voff[vo: vo + nv + 1].astype(int)
+        start, padded = raw & 0x7fff, raw[:-1] >> 15          # reduce order, bit 15 = padded range
+        cnt = np.diff(start) - padded                         # valence of the t-th vertex in reduce order
         perm = vperm[vs:vs + nv].astype(int)
         assert sorted(perm.tolist()) == list(range(nv))      # a permutation of the local ids ...
-        assert (np.diff(np.diff(off)[perm]) <= 0).all()      # ... by decreasing valence
+        assert (np.diff(cnt) <= 0).all() and cnt.sum() == 4 * n   # ... by decreasing valence
+        assert (np.diff(start) % 2 == 1).all()               # odd strides between neighbouring ranges
         s = slots[ts:ts + n].ravel().astype(int); l = conn[ts:ts + n].ravel().astype(int)
-        assert sorted(s.tolist()) == list(range(4 * n))      # every corner owns exactly one slot
-        assert ((s >= off[l]) & (s < off[l + 1])).all()      # ... inside its vertex's range
+        assert len(set(s.tolist())) == 4 * n                 # every corner owns exactly one slot
+        rank = np.empty(nv, int); rank[perm] = np.arange(nv)  # local id -> reduce-order position
+        t = rank[l]
+        assert ((s >= start[t]) & (s < start[t] + cnt[t])).all()   # ... inside its vertex's range
+        assert np.array_equal(np.bincount(l, minlength=nv)[perm], cnt)
 
 
 def test_tiling_splits_on_vertex_budget(native_lib):
@@ -104,7 +110,8 @@ def test_tiling_splits_on_vertex_budget(native_lib):
     vol = np.einsum("ci,ci->c", np.cross(X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]), X[:, 3] - X[:, 0])
     mesh.cells[vol < 0] = mesh.cells[vol < 0][:, [0, 2, 1, 3]]
     tiles, *_ = _host_tables(native_lib, mesh, with_points=False)
-    assert (tiles[:, 3] <= 256).all() and (tiles[:-1, 1] == 64).all()
+    limit = tiles[:, 3].max()
+    assert limit <= 256 and (tiles[:-1, 3] == limit).all() and (tiles[:-1, 1] == limit // 4).all()
 
 
 def test_setup_rejects_bad_meshes(native_lib):

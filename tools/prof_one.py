@@ -1,0 +1,33 @@
+"""Runs one operator configuration a few times (for ncu captures).
+usage: python tools/prof_one.py --kind snh --dtype f32 --ops 11 --scatter 0 --ld 3 --n 58 --reps 3"""
+import argparse, sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import numpy as np, torch
+from bench import build_mesh
+from helpers import cuda_potential
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--kind", default="snh"); ap.add_argument("--dtype", default="f32")
+ap.add_argument("--ops", type=int, default=11); ap.add_argument("--scatter", type=int, default=0)
+ap.add_argument("--ld", type=int, default=3); ap.add_argument("--n", type=int, default=58)
+ap.add_argument("--reps", type=int, default=3)
+a = ap.parse_args()
+dt = torch.float32 if a.dtype == "f32" else torch.float64
+mesh, u, p = build_mesh(a.n)
+V = mesh.n_points
+pot = cuda_potential(a.kind, mesh, dt)
+ud = torch.zeros((V, a.ld), dtype=dt, device="cuda"); ud[:, :3] = torch.as_tensor(u, dtype=dt)
+pd = torch.zeros((V, a.ld), dtype=dt, device="cuda"); pd[:, :3] = torch.as_tensor(p, dtype=dt)
+outs = {k: torch.zeros((V, a.ld), dtype=dt, device="cuda") for k in ("grad", "diag", "prod")}
+fun = torch.zeros(1, dtype=dt, device="cuda"); quad = torch.zeros(1, dtype=dt, device="cuda")
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+ts = []
+for i in range(a.reps):
+    flush.fill_(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pot.eval(a.ops, ud, pd, fun=fun, quad=quad, grad=outs["grad"], diag=outs["diag"], prod=outs["prod"], scatter=a.scatter)
+    e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+print(a, "ms:", ts, "Gtets/s:", mesh.n_cells / min(ts) / 1e6)
