@@ -366,18 +366,20 @@ __device__ __forceinline__ void tile_compute(const T* rec, uchar4 lc, ushort4 s4
     }
 }
 
-// Threads 2t and 2t+1 together sum the slot range of the t-th vertex in valence order (balanced trip
-// counts per warp, all consumer warps busy), combine with one shuffle, and the even thread parks the
-// 3*NOUT sums in the vertex buffer at the vertex's ascending local id.
+// Two threads (lanes l and l+16 of a warp) together sum the slot range of one vertex, taken in valence
+// order (balanced trip counts, all consumer warps busy), combine with one shuffle, and the lower lane
+// parks the 3*NOUT sums in the vertex buffer at the vertex's ascending local id.  The 16 lanes of a
+// half warp handle 16 consecutive vertices whose ranges are an odd number of slots apart, so their
+// 16- and 8-byte reads hit distinct banks.
 template <typename T, int OPS>
 __device__ __forceinline__ void tile_reduce(int tid, int n_verts, const unsigned char* vperm,
                                             const unsigned short* voff, const T* sl, T* vbuf) {
     using Cfg = TileCfg<T, OPS>;
     constexpr int NOUT = Cfg::NOUT, SS = Cfg::SS;
-    const int half = tid & 1;
-    for (int t = tid >> 1; t < ((n_verts + 15) & ~15); t += kTileTets / 2) {
-        // (the bound is rounded up so that both threads of a pair, and whole half-warps, stay together
-        //  for the shuffle below; out-of-range pairs have cnt = 0)
+    const int half = (tid >> 4) & 1;
+    for (int t = (tid >> 5) * 16 + (tid & 15); t < ((n_verts + 15) & ~15); t += kTileTets / 2) {
+        // (the bound is rounded up to 16 so that whole warps stay together for the shuffle below;
+        //  out-of-range lanes have cnt = 0)
         int v = 0, s0 = 0, cnt = 0;
         if (t < n_verts) {
             v = vperm[t];
@@ -397,7 +399,7 @@ __device__ __forceinline__ void tile_reduce(int tid, int n_verts, const unsigned
             for (int j = 0; j < 3 * NOUT; ++j) acc[j] += val[j];
         }
 #pragma unroll
-        for (int j = 0; j < 3 * NOUT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+        for (int j = 0; j < 3 * NOUT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
         if (half == 0 && t < n_verts) {
 #pragma unroll
             for (int j = 0; j < 3 * NOUT; ++j) vbuf[v * (3 * NOUT) + j] = acc[j];

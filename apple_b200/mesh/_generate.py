@@ -37,15 +37,26 @@ def morton_codes(xyz: np.ndarray) -> np.ndarray:
     return _part1by2(q[:, 0]) | (_part1by2(q[:, 1]) << np.uint64(1)) | (_part1by2(q[:, 2]) << np.uint64(2))
 
 
-def morton_reorder(mesh: TetMesh) -> TetMesh:
-    """Renumbers vertices and tets along a Morton curve (data arrays are permuted with them)."""
-    vperm = np.argsort(morton_codes(mesh.points), kind="stable")
-    inv = np.empty_like(vperm)
+def morton_reorder(mesh: TetMesh, *, first_touch: bool = True) -> TetMesh:
+    """Orders the tets along a Morton curve and renumbers the vertices to match (data arrays are
+    permuted with them).  ``first_touch=True`` numbers vertices in the order the Morton-sorted tets
+    first reference them, so that the vertices a run of consecutive tets touches for the first time
+    are contiguous in memory (fewer cache lines per gather); otherwise vertices follow their own
+    Morton code."""
+    cperm = np.argsort(morton_codes(mesh.points[mesh.cells].mean(axis=1)), kind="stable")
+    cells = mesh.cells[cperm]
+    if first_touch:
+        flat = cells.reshape(-1)
+        _, first = np.unique(flat, return_index=True)       # first occurrence of every referenced vertex
+        touched = flat[np.sort(first)]
+        rest = np.setdiff1d(np.arange(mesh.n_points), touched, assume_unique=False)
+        vperm = np.concatenate([touched, rest])
+    else:
+        vperm = np.argsort(morton_codes(mesh.points), kind="stable")
+    inv = np.empty(mesh.n_points, dtype=np.int64)
     inv[vperm] = np.arange(vperm.size)
     points = mesh.points[vperm]
-    cells = inv[mesh.cells].astype(np.int32)
-    cperm = np.argsort(morton_codes(points[cells].mean(axis=1)), kind="stable")
-    cells = cells[cperm]
+    cells = inv[cells].astype(np.int32)
     point_data = {k: np.asarray(v)[vperm] for k, v in mesh.point_data.items()}
     cell_data = {k: np.asarray(v)[cperm] for k, v in mesh.cell_data.items()}
     return TetMesh(points, cells, point_data, cell_data)
