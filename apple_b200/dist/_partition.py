@@ -1,0 +1,65 @@
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from apple_b200.mesh import TetMesh
+
+
+@dataclass
+class Shard:
+    """One rank's part of a partitioned mesh."""
+
+    rank: int
+    world: int
+    mesh: TetMesh                    # local mesh (local vertex numbering), cell/point data carried over
+    l2g: np.ndarray                  # (n_local,) local -> global vertex id (ascending)
+    owned: np.ndarray                # (n_local,) bool: this rank owns the vertex (lowest rank touching it)
+    cell_range: tuple[int, int]      # [lo, hi) of the global (ordered) cells held here
+    # halo plan: for every other rank s that shares vertices with this rank, the LOCAL indices of the
+    # shared vertices, sorted by global id (both sides list them in the same order)
+    neighbors: dict[int, np.ndarray] = field(default_factory=dict)
+    n_global_points: int = 0
+    n_global_cells: int = 0
+
+    @property
+    def n_local(self) -> int:
+        return self.l2g.size
+
+
+def partition_mesh(mesh: TetMesh, world: int, rank: int) -> Shard:
+    """Contiguous chunks of the cell order (use a Morton-ordered mesh, ``mesh.morton_reorder``).
+
+    Deterministic and identical on every rank (each rank computes the full ownership table from the
+    connectivity; at 64M tets this is a few seconds of numpy and is setup-time work)."""
+    T, V = mesh.n_cells, mesh.n_points
+    bounds = [r * T // world for r in range(world + 1)]
+    lo, hi = bounds[rank], bounds[rank + 1]
+    cells = mesh.cells[lo:hi]
+    l2g = np.unique(cells)
+    g2l = np.full(V, -1, dtype=np.int64)
+    g2l[l2g] = np.arange(l2g.size)
+    local = TetMesh(
+        mesh.points[l2g],
+        g2l[cells].astype(np.int32),
+        point_data={k: np.asarray(v)[l2g] for k, v in mesh.point_data.items()},
+        cell_data={k: np.asarray(v)[lo:hi] for k, v in mesh.cell_data.items()},
+    )
+    # which ranks touch each vertex: bit mask per vertex (world <= 64)
+    touch = np.zeros(V, dtype=np.uint64)
+    for r in range(world):
+        vr = np.unique(mesh.cells[bounds[r]:bounds[r + 1]])
+        touch[vr] |= np.uint64(1) << np.uint64(r)
+    mine = touch[l2g]
+    low_bit = mine & (~mine + np.uint64(1))          # lowest set bit = owner
+    owned = low_bit == (np.uint64(1) << np.uint64(rank))
+    neighbors = {}
+    for s in range(world):
+        if s == rank:
+            continue
+        shared = np.flatnonzero((mine >> np.uint64(s)) & np.uint64(1))
+        if shared.size:
+            neighbors[s] = shared.astype(np.int64)   # l2g ascending => sorted by global id
+    return Shard(rank=rank, world=world, mesh=local, l2g=l2g, owned=owned, cell_range=(lo, hi),
+                 neighbors=neighbors, n_global_points=V, n_global_cells=T)

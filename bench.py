@@ -214,18 +214,6 @@ def main():
 
     mesh, u, p = build_mesh(args.n)
     T_total, V = mesh.n_cells, mesh.n_points
-    # strong scaling: rank r owns a contiguous chunk of the Morton-ordered tets
-    lo, hi = rank * T_total // world, (rank + 1) * T_total // world
-    shard = mesh if world == 1 else TetMesh(mesh.points, mesh.cells[lo:hi],
-                                            cell_data={k: v[lo:hi] for k, v in mesh.cell_data.items()})
-    pots = {k: cuda_potential(k, shard, dtype, name=k) for k in kinds}
-    model = WarpModel(pots)
-    adapter = WarpModelAdapter(model, n_points=V)
-    ud = torch.as_tensor(u, dtype=dtype, device=dev).contiguous()
-    pd = torch.as_tensor(p, dtype=dtype, device=dev).contiguous()
-    fun = torch.zeros(1, dtype=dtype, device=dev)
-    grad = torch.zeros((V, 3), dtype=dtype, device=dev)
-    prod = torch.zeros((V, 3), dtype=dtype, device=dev)
     OPS = _lib.OP_FUN | _lib.OP_GRAD | _lib.OP_HESS_PROD
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
@@ -233,10 +221,36 @@ def main():
         if not args.no_flush:
             flush_buf.fill_(1)
 
-    def step():
-        model.eval(OPS, ud, pd, fun=fun, grad=grad, prod=prod)
-        if world > 1:  # halo sum (v0: dense all-reduce of the nodal fields) + scalar all-reduce
-            dist.all_reduce(grad); dist.all_reduce(prod); dist.all_reduce(fun)
+    if world == 1:
+        lo, hi = 0, T_total
+        pots = {k: cuda_potential(k, mesh, dtype, name=k) for k in kinds}
+        model = WarpModel(pots)
+        adapter = WarpModelAdapter(model, n_points=V)
+        ud = torch.as_tensor(u, dtype=dtype, device=dev).contiguous()
+        pd = torch.as_tensor(p, dtype=dtype, device=dev).contiguous()
+        fun = torch.zeros(1, dtype=dtype, device=dev)
+        grad = torch.zeros((V, 3), dtype=dtype, device=dev)
+        prod = torch.zeros((V, 3), dtype=dtype, device=dev)
+
+        def step():
+            model.eval(OPS, ud, pd, fun=fun, grad=grad, prod=prod)
+    else:
+        # strong scaling: rank r owns a contiguous chunk of the Morton-ordered tets and a local copy of
+        # the vertices they touch; one halo sum (all-to-all of the shared rows) + one scalar all-reduce
+        from apple_b200.dist import ShardedOperators, partition_mesh
+
+        shard = partition_mesh(mesh, world, rank)
+        lo, hi = shard.cell_range
+        pots = {k: cuda_potential(k, shard.mesh, dtype, name=k) for k in kinds}
+        sharded = ShardedOperators(WarpModel(pots), shard, dev, dtype)
+        ud = torch.as_tensor(u[shard.l2g], dtype=dtype, device=dev).contiguous()
+        pd = torch.as_tensor(p[shard.l2g], dtype=dtype, device=dev).contiguous()
+        fun = torch.zeros(1, dtype=dtype, device=dev)
+        grad = torch.zeros((shard.n_local, 3), dtype=dtype, device=dev)
+        prod = torch.zeros((shard.n_local, 3), dtype=dtype, device=dev)
+
+        def step():
+            sharded.eval(OPS, ud, pd)
 
     def barrier():
         if world > 1:
@@ -263,7 +277,7 @@ def main():
 
     # ---- per-kernel roofline (each potential's fused kernel timed alone, L2 flushed) ----
     peak, peak_src = measured_peak_gbs()
-    v_over_t = V / T_total
+    v_over_t = (V if world == 1 else shard.n_local) / max(hi - lo, 1)
     kern = {}
     for k, pot in pots.items():
         ts = []
@@ -333,7 +347,9 @@ def main():
             "config": {"workload": f"cube {args.n}^3x5 = {T_total} tets / {V} verts, {'+'.join(kinds)}, "
                                    f"fused energy+grad+HVP ({args.scatter} assembly)",
                        "l2": "256 MiB flush write between timed steps" if not args.no_flush else "no flush",
-                       "parallelism": f"{world} x Morton chunk of tets" if world > 1 else "1 GPU"},
+                       "parallelism": (f"{world} ranks x contiguous Morton chunk of tets; halo sum of grad+HVP "
+                                       f"(NCCL all-to-all of shared rows) + scalar all-reduce per step")
+                       if world > 1 else "1 GPU"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": args.steps * len(pots),
             "roofline": roofline, "cpu_baseline": cpu, "pncg": pncg,
         }

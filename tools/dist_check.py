@@ -1,0 +1,69 @@
+"""Multi-GPU parity check (run under torchrun, one rank per GPU):
+   sharded fused evaluation and sharded PNCG vs the single-GPU path on rank 0.
+   torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py"""
+import os, sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import numpy as np, torch, torch.distributed as dist
+from helpers import make_case, cuda_potential, rel_err
+from apple_b200 import _lib
+from apple_b200.dist import ShardedOperators, ShardedPNCG, partition_mesh
+from apple_b200.warp.model import WarpModel
+from apple_b200.optim.pncg import ConvergenceCriteria
+
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
+dist.init_process_group("nccl", device_id=dev)
+ok = True
+for dtype, tol in ((torch.float64, 1e-10), (torch.float32, 1e-5)):
+    mesh, u, p = make_case(n=10, seed=5, grading=1.0)
+    mesh.cell_data.pop("Fraction")
+    shard = partition_mesh(mesh, world, rank)
+    pots = {k: cuda_potential(k, shard.mesh, dtype, name=k) for k in ("snh", "arap")}
+    ops = ShardedOperators(WarpModel(pots), shard, dev, dtype)
+    ul = torch.as_tensor(u[shard.l2g], dtype=dtype, device=dev).contiguous()
+    pl = torch.as_tensor(p[shard.l2g], dtype=dtype, device=dev).contiguous()
+    f, g, h = ops.fun_grad_hess_prod(ul, pl)
+    # reference: the whole mesh on this rank's GPU
+    full = {k: cuda_potential(k, mesh, dtype, name=k) for k in ("snh", "arap")}
+    from apple_b200.warp.model import WarpModelAdapter
+    ad = WarpModelAdapter(WarpModel(full), mesh.n_points)
+    fr, gr, hr = ad.fun_grad_hess_prod(torch.as_tensor(u, dtype=dtype, device=dev), torch.as_tensor(p, dtype=dtype, device=dev))
+    idx = torch.as_tensor(shard.l2g, device=dev)
+    errs = (rel_err(f.cpu(), fr.cpu()), float((g - gr[idx]).abs().max() / gr.abs().max()), float((h - hr[idx]).abs().max() / hr.abs().max()))
+    good = max(errs) < 5 * tol
+    ok &= good
+    print(f"rank {rank} {dtype} fused eval vs 1-GPU: energy/grad/hvp rel err {errs[0]:.2e} {errs[1]:.2e} {errs[2]:.2e} {'OK' if good else 'FAIL'}", flush=True)
+
+    # PNCG: sharded vs single-GPU fused, fixed iteration count
+    from apple_b200.common import FIXED_MASK, FIXED_VALUE
+    from apple_b200.forward import Forward, ModelBuilder
+    from apple_b200.optim import PNCG
+    V = mesh.n_points
+    fixed = np.zeros((V, 3), bool); fixed[mesh.points[:, 2] == 0.0] = True
+    iters = 30
+    crit = ConvergenceCriteria(max_steps=iters, target_relative_gradient_norm=0.0)
+    b = ModelBuilder(dtype=dtype, device=dev); b.add_vertices(mesh)
+    mesh.point_data[FIXED_MASK.vtk] = fixed; mesh.point_data[FIXED_VALUE.vtk] = np.zeros((V, 3))
+    b.add_fixed(mesh)
+    for pot in full.values(): b.add_potential(pot)
+    fwd = Forward(b.finalize(), optimizer=PNCG(criteria=crit, check_every=iters))
+    X = mesh.points
+    u0 = np.ascontiguousarray(0.02 * np.sin(5.0 * X[:, [1, 2, 0]])); u0[fixed] = 0.0
+    fwd.state.u = torch.as_tensor(u0, dtype=dtype, device=dev)
+    sol = fwd.step()
+    free_local = torch.as_tensor(~fixed[shard.l2g], device=dev)
+    sp = ShardedPNCG(list(pots.values()), [], shard, free_local, torch.as_tensor(u0[shard.l2g], dtype=dtype, device=dev), criteria=crit)
+    res = sp.solve(check_every=iters)
+    eu = float((sp.u_local - fwd.state.u[idx]).abs().max() / fwd.state.u.abs().max())
+    ptol = 1e-8 if dtype == torch.float64 else 2e-4
+    good = eu < ptol and res["n_steps"] == sol.stats["n_steps"] and abs(res["fun"] - sol.stats["fun"]) <= 10 * ptol * abs(sol.stats["fun"])
+    ok &= good
+    print(f"rank {rank} {dtype} PNCG {res['n_steps']} its: |u-u1|/|u1| = {eu:.2e}, f = {res['fun']:.10e} vs {sol.stats['fun']:.10e}, accepted {res['n_accepted']} vs {sol.stats['n_accepted']} {'OK' if good else 'FAIL'}", flush=True)
+flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+dist.destroy_process_group()
+if rank == 0:
+    print("DIST_CHECK " + ("PASS" if flag.item() == 1.0 else "FAIL"), flush=True)
+sys.exit(0 if flag.item() == 1.0 else 1)
