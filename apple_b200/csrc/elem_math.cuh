@@ -201,9 +201,15 @@ APL_HD void jacobi_rotate(T* A, T* V, int p, int q) {
     // A symmetric, stored fully (row-major 3x3).  Annihilates A[p][q] with the rotation
     // tan(theta) = t = sgn(d) 2 a_pq / (|d| + sqrt(d^2 + 4 a_pq^2)),  d = a_qq - a_pp  (|theta| <= pi/4).
     const T apq = A[3 * p + q];
-    const T tiny = (sizeof(T) == 4) ? (T)1e-30 : (T)1e-280;
-    if (!(fabs(apq) > tiny)) return;
     const T app = A[3 * p + p], aqq = A[3 * q + q];
+    // Skip when the off-diagonal entry is below rounding level relative to the diagonal (or absolutely
+    // tiny): rotating further cannot improve the result, and b*b below would underflow to zero.
+    const T tiny = (sizeof(T) == 4) ? (T)1e-18 : (T)1e-150;
+    const T rel = (sizeof(T) == 4) ? (T)1e-16 : (T)1e-34;
+    if (!(fabs(apq) > tiny) || !(apq * apq > rel * fabs(app * aqq))) {
+        A[3 * p + q] = A[3 * q + p] = (T)0;
+        return;
+    }
     const T d = aqq - app, b = (T)2 * apq;
     const T h2 = d * d + b * b;
     const T h = h2 * apl_rsqrt(h2);

@@ -182,3 +182,36 @@ def test_edge_cases(native_lib):
     bad.cells[0, 3] = 9
     with pytest.raises((NativeError, IndexError)):
         cuda_potential("snh", bad, torch.float64)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("kind", KINDS)
+def test_rest_state_and_isotropic_scaling(native_lib, kind, dtype):
+    """Degenerate spectra: F = I (rest) and F = s I (all singular values equal) -- the states PNCG
+    starts from.  Everything must be finite and match the oracle (repeated singular values make the
+    individual SVD factors arbitrary but every assembled quantity is still well defined)."""
+    mesh, _, p = make_case(n=5, seed=9)
+    V = mesh.n_points
+    ora = oracle_potential(kind, mesh)
+    pot = cuda_potential(kind, mesh, dtype)
+    pd = _dev(p, dtype)
+    tol = 10 * TOL[dtype]
+    for u in (np.zeros((V, 3)), 0.1 * mesh.points, -0.05 * mesh.points):
+        ud = _dev(u, dtype)
+        fun = torch.zeros(1, dtype=dtype, device="cuda"); quad = torch.zeros(1, dtype=dtype, device="cuda")
+        grad, diag, prod = (torch.zeros((V, 3), dtype=dtype, device="cuda") for _ in range(3))
+        pot.eval(31, ud, pd, fun=fun, quad=quad, grad=grad, diag=diag, prod=prod)
+        for t in (fun, quad, grad, diag, prod):
+            assert bool(torch.isfinite(t).all())
+        e = np.zeros(1); ora.fun(u, e)
+        q = np.zeros(1); ora.hess_quad(u, p, q)
+        scale = float(np.abs(mesh.cell_data["mu"]).max())
+        assert abs(float(fun) - e[0]) <= tol * max(abs(e[0]), 1e-3 * scale)
+        assert rel_err(quad.cpu(), q) < tol
+        for name, got, oargs in (("hess_diag", diag, (u,)), ("hess_prod", prod, (u, p))):
+            ref = np.zeros((V, 3)); getattr(ora, name)(*oargs, ref)
+            assert rel_err(got.cpu(), ref) < tol, name
+        ref = np.zeros((V, 3)); ora.grad(u, ref)
+        dref = np.zeros((V, 3)); ora.hess_diag(u, dref)
+        # gradient may vanish identically (rest state): compare against the force scale diag * h
+        assert np.abs(grad.cpu().numpy() - ref).max() <= tol * max(np.abs(ref).max(), np.abs(dref).max() * 0.2)
