@@ -136,28 +136,41 @@ def measured_peak_gbs():
 
 
 def oracle_model(mesh, kinds, n_tets=None):
+    """The reference's operators restated in C (oracle/c, all host threads), one pass per operator per
+    potential exactly like WarpModel (warp/model/_model.py:13-36)."""
     from helpers import oracle_potential
     from apple_b200.mesh import TetMesh
-    from oracle import fem as ofem
+    from oracle import cbind
 
     if n_tets is not None and n_tets < mesh.n_cells:
         sub = TetMesh(mesh.points, mesh.cells[:n_tets], cell_data={k: v[:n_tets] for k, v in mesh.cell_data.items()})
     else:
         sub = mesh
-    pots = [oracle_potential(k, sub) for k in kinds]
-    return ofem.Model(pots, mesh.n_points), sub.n_cells
+    pots = []
+    for k in kinds:
+        ref = oracle_potential(k, sub)  # numpy oracle: only used here to assemble dhdX / dV / materials
+        pots.append(cbind.CPotential(k, ref.cells, ref.dhdX, ref.dV, ref.materials["mu"], ref.materials.get("lambda_"),
+                                     ref.materials.get("activation")))
+    return pots, sub.n_cells, cbind.num_threads()
 
 
 def time_oracle(mesh, u, p, kinds, sample_tets, steps, warmup):
-    model, T = oracle_model(mesh, kinds, sample_tets)
+    pots, T, threads = oracle_model(mesh, kinds, sample_tets)
+    V = mesh.n_points
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        model.fun(u); model.grad(u); model.hess_prod(u, p)
+        e, g, h = np.zeros(1), np.zeros((V, 3)), np.zeros((V, 3))
+        for pot in pots:  # fun, grad, hess_prod: three passes per potential, as the reference launches them
+            pot.fun(u, e)
+        for pot in pots:
+            pot.grad(u, g)
+        for pot in pots:
+            pot.hess_prod(u, p, h)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return T * len(times) / sum(times), T, float(np.mean(times))
+    return T * len(times) / sum(times), T, float(np.mean(times)), threads
 
 
 def run_reference(args):
@@ -166,17 +179,18 @@ def run_reference(args):
         return
     kinds = args.potentials.split(",")
     mesh, u, p = build_mesh(args.n)
-    sample = min(mesh.n_cells, 60_000)
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    value, T, dt = time_oracle(mesh, u, p, kinds, sample, steps, warmup)
-    cores = 1
+    sample = min(mesh.n_cells, 1_000_000)
+    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
+    value, T, dt, threads = time_oracle(mesh, u, p, kinds, sample, steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"cube {args.n}^3x5 = {mesh.n_cells} tets, {'+'.join(kinds)}, fused energy+grad+HVP",
-                   "note": "CPU restatement of the reference (oracle/, numpy fp64); Warp/JAX not installable here"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "config": {"workload": f"cube {args.n}^3x5 = {mesh.n_cells} tets / {mesh.n_points} verts, {'+'.join(kinds)}, "
+                               "energy + gradient + HVP (three operator passes per potential, as the reference runs them)",
+                   "note": "CPU restatement of the reference's Warp kernels in C (oracle/c, pthreads, fp64); the "
+                           "reference itself needs warp-lang/JAX, which cannot be installed here"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"first {T} tets of the Morton-ordered mesh, {steps} evaluations"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -292,8 +306,15 @@ def main():
         kern[k] = {"ms": dt * 1e3, "bytes_per_tet": bpt, "gbs": bpt * (hi - lo) / dt / 1e9,
                    "gtets_per_s": (hi - lo) / dt / 1e9}
     dom = max(kern, key=lambda k: kern[k]["ms"])
+    traffic = None
+    tf = ROOT / "profiles" / "traffic.json"
+    if tf.exists() and world == 1:
+        try:
+            traffic = json.loads(tf.read_text()).get(f"{args.dtype}:{dom}:n{args.n}")
+        except Exception:
+            traffic = None
     roofline = {"bound": "hbm", "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["gbs"] / peak, "traffic": None, "kernel": f"fem_tile_kernel<{args.dtype},{dom},fun|grad|hess_prod>",
+                "frac": kern[dom]["gbs"] / peak, "traffic": traffic, "kernel": f"fem_pipe_kernel<{args.dtype},{dom},fun|grad|hess_prod>",
                 "peak_source": peak_src, "frac_of_nominal_8TBs": kern[dom]["gbs"] / 8000.0, "per_kernel": kern}
 
     # ---- e2e: host buffers through the public adapter API ----
@@ -332,9 +353,10 @@ def main():
     # ---- CPU baseline: the oracle on a bounded sample ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        val, Ts, dt = time_oracle(mesh, u, p, kinds, min(T_total, 60_000), 3, 1)
-        cpu = {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"first {Ts} tets of the same mesh, 3 fused evaluations, numpy fp64 oracle"}
+        val, Ts, dt, threads = time_oracle(mesh, u, p, kinds, min(T_total, 1_000_000), 5, 1)
+        cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"first {Ts} tets of the same mesh, 5 evaluations (fun, grad, hess_prod passes per "
+                         f"potential), C restatement of the reference kernels (oracle/c), fp64"}
 
     if args.sweep and rank == 0 and world == 1:
         sweep(args, mesh, u, p, dtype, dev, flush)
