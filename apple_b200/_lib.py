@@ -43,6 +43,9 @@ SIGNATURES = {
     "apl_ext_force_eval": (c_int, [c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                    c_int, c_void_p]),
     "apl_field_copy": (c_int, [c_int, c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "apl_halo_pack": (c_int, [c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "apl_halo_unpack": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                c_int, c_void_p, c_void_p]),
     "apl_pncg_create": (c_int, [c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
     "apl_pncg_destroy": (None, [c_void_p]),

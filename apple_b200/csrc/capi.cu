@@ -178,6 +178,46 @@ __global__ void field_copy_kernel(long long n, const T* __restrict__ src, int ld
     }
 }
 
+// ---- halo exchange helpers (sharded meshes) ---------------------------------------------------------
+// pack:   send[i, f*3 + c] = field_f[send_index[i], c]                       (rows shared with other ranks)
+// unpack: for every shared vertex, sum its partials in ascending RANK order (own partial in its own
+//         position), so that all replicas end up bit-identical, and write the total back.
+template <typename T>
+__global__ void halo_pack_kernel(long long n, const long long* __restrict__ index, int nf, const T* f0, const T* f1,
+                                 const T* f2, int ld, T* __restrict__ send) {
+    const T* f[3] = {f0, f1, f2};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long v = index[i];
+        for (int k = 0; k < nf; ++k) {
+            const T* r = f[k] + v * ld;
+            T* d = send + (i * nf + k) * 3;
+            d[0] = r[0]; d[1] = r[1]; d[2] = r[2];
+        }
+    }
+}
+
+template <typename T>
+__global__ void halo_unpack_kernel(long long n_shared, const long long* __restrict__ shared,
+                                   const int* __restrict__ row_ptr, const long long* __restrict__ src, int nf, T* f0,
+                                   T* f1, T* f2, int ld, const T* __restrict__ recv) {
+    T* f[3] = {f0, f1, f2};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_shared;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long v = shared[i];
+        for (int k = 0; k < nf; ++k) {
+            T* own = f[k] + v * ld;
+            T a0 = 0, a1 = 0, a2 = 0;
+            for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
+                const long long j = src[e];  // -1: this rank's own partial, else a row of the receive buffer
+                const T* r = j < 0 ? own : recv + (j * nf + k) * 3;
+                a0 += r[0]; a1 += r[1]; a2 += r[2];
+            }
+            own[0] = a0; own[1] = a1; own[2] = a2;
+        }
+    }
+}
+
 static int grid_for(long long n, int block) {
     long long g = (n + block - 1) / block;
     if (g < 1) g = 1;
@@ -437,6 +477,47 @@ int apl_ext_force_eval(int dtype, int ops, int64_t k, const void* force, const i
                                                         ld_in, (double*)fun, (double*)grad, ld_out, nullptr, nullptr, 0,
                                                         -1, -1, nullptr);
     else { set_error("apl_ext_force_eval: unknown dtype"); return APL_ERR_INVALID; }
+    APL_CUDA_CHECK(cudaGetLastError());
+    return APL_OK;
+}
+
+int apl_halo_pack(int dtype, int64_t n, const int64_t* index, int nf, const void* f0, const void* f1, const void* f2,
+                  int ld, void* send, void* stream) {
+    if (n < 0 || nf < 1 || nf > 3 || (n > 0 && (!index || !f0 || !send)) || (ld != 3 && ld != 4)) {
+        set_error("apl_halo_pack: bad arguments");
+        return APL_ERR_INVALID;
+    }
+    if (n == 0) return APL_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int block = 256, grid = grid_for(n, block);
+    if (dtype == APL_F32)
+        halo_pack_kernel<float><<<grid, block, 0, s>>>(n, (const long long*)index, nf, (const float*)f0, (const float*)f1,
+                                                       (const float*)f2, ld, (float*)send);
+    else
+        halo_pack_kernel<double><<<grid, block, 0, s>>>(n, (const long long*)index, nf, (const double*)f0,
+                                                        (const double*)f1, (const double*)f2, ld, (double*)send);
+    APL_CUDA_CHECK(cudaGetLastError());
+    return APL_OK;
+}
+
+int apl_halo_unpack(int dtype, int64_t n_shared, const int64_t* shared, const int32_t* row_ptr, const int64_t* src,
+                    int nf, void* f0, void* f1, void* f2, int ld, const void* recv, void* stream) {
+    if (n_shared < 0 || nf < 1 || nf > 3 || (n_shared > 0 && (!shared || !row_ptr || !src || !f0 || !recv)) ||
+        (ld != 3 && ld != 4)) {
+        set_error("apl_halo_unpack: bad arguments");
+        return APL_ERR_INVALID;
+    }
+    if (n_shared == 0) return APL_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int block = 256, grid = grid_for(n_shared, block);
+    if (dtype == APL_F32)
+        halo_unpack_kernel<float><<<grid, block, 0, s>>>(n_shared, (const long long*)shared, row_ptr,
+                                                         (const long long*)src, nf, (float*)f0, (float*)f1, (float*)f2, ld,
+                                                         (const float*)recv);
+    else
+        halo_unpack_kernel<double><<<grid, block, 0, s>>>(n_shared, (const long long*)shared, row_ptr,
+                                                          (const long long*)src, nf, (double*)f0, (double*)f1, (double*)f2,
+                                                          ld, (const double*)recv);
     APL_CUDA_CHECK(cudaGetLastError());
     return APL_OK;
 }

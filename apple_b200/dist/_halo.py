@@ -1,7 +1,10 @@
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.distributed as dist
+
+from apple_b200 import _lib
 
 from ._partition import Shard
 
@@ -9,51 +12,92 @@ from ._partition import Shard
 class HaloExchange:
     """Sums partial nodal values over all ranks that share a vertex.
 
-    One ``all_to_all_single`` per call (NCCL over NVLink on GPUs, gloo in the CPU tests) moves only
-    the shared rows.  Every rank then adds the partials of a vertex in ascending RANK order (its own
-    partial in its own position), so all replicas of a vertex end up bit-identical."""
+    Per call: one pack kernel, one ``all_to_all_single`` of the shared rows only (NCCL over NVLink on
+    GPUs, gloo in the CPU tests), one unpack kernel.  Every rank adds the partials of a vertex in
+    ascending RANK order (its own partial in its own position), so all replicas of a vertex end up
+    bit-identical.  On CUDA tensors pack/unpack are the ``apl_halo_*`` kernels of the native library;
+    the torch index-op implementation below is kept for the CPU (gloo) tests of the sharding logic."""
 
     def __init__(self, shard: Shard, device, group=None):
         self.shard = shard
         self.group = group
         self.world, self.rank = shard.world, shard.rank
         self.device = torch.device(device)
-        self.idx = {s: torch.as_tensor(ix, dtype=torch.int64, device=self.device) for s, ix in shard.neighbors.items()}
-        self.counts = [int(shard.neighbors[s].size) if s in shard.neighbors else 0 for s in range(self.world)]
+        nb = shard.neighbors
+        self.idx = {s: torch.as_tensor(ix, dtype=torch.int64, device=self.device) for s, ix in nb.items()}
+        self.counts = [int(nb[s].size) if s in nb else 0 for s in range(self.world)]
         self.total = sum(self.counts)
         offs = [0]
         for c in self.counts:
             offs.append(offs[-1] + c)
         self.offs = offs
-        if self.total:
-            self.send_index = torch.cat([self.idx[s] for s in range(self.world) if s in self.idx])
-            shared = torch.unique(self.send_index)
-        else:
-            self.send_index = torch.zeros(0, dtype=torch.int64, device=self.device)
-            shared = self.send_index
-        self.shared = shared  # local ids of all vertices shared with anybody
+        send_index = np.concatenate([nb[s] for s in range(self.world) if s in nb]) if self.total else np.zeros(0, np.int64)
+        shared = np.unique(send_index)
+        # CSR over shared vertices: contributions in ascending rank order, -1 marks this rank's own partial
+        entries = [[] for _ in range(shared.size)]
+        pos = {int(v): i for i, v in enumerate(shared)}
+        for s in range(self.world):
+            if s == self.rank:
+                for i in range(shared.size):
+                    entries[i].append(-1)
+            elif s in nb:
+                for k, v in enumerate(nb[s]):
+                    entries[pos[int(v)]].append(offs[s] + k)
+        row_ptr = np.zeros(shared.size + 1, np.int32)
+        row_ptr[1:] = np.cumsum([len(e) for e in entries])
+        src = np.array([j for e in entries for j in e], dtype=np.int64)
+        t = lambda a, dt: torch.as_tensor(a, dtype=dt, device=self.device)  # noqa: E731
+        self.send_index = t(send_index, torch.int64)
+        self.shared = t(shared, torch.int64)
+        self.row_ptr = t(row_ptr, torch.int32)
+        self.src = t(src, torch.int64)
+        self._buf = {}
+
+    def _buffers(self, nf, dtype):
+        key = (nf, dtype)
+        if key not in self._buf:
+            self._buf[key] = (torch.empty((self.total, nf * 3), dtype=dtype, device=self.device),
+                              torch.empty((self.total, nf * 3), dtype=dtype, device=self.device))
+        return self._buf[key]
 
     def sum_(self, *fields: torch.Tensor) -> None:
-        """In place: every field (n_local, k) gets, on shared rows, the sum over all sharers."""
-        if self.world == 1 or not fields:
+        """In place: the first three columns of every field (n_local, 3|4) get, on shared rows, the
+        sum over all sharers."""
+        if self.world == 1 or not fields or self.total == 0:
             return
-        width = [f.shape[1] for f in fields]
-        cat = fields[0] if len(fields) == 1 else torch.cat(fields, dim=1)
-        send = cat.index_select(0, self.send_index).contiguous()
-        recv = torch.empty_like(send)
-        splits = self.counts
-        dist.all_to_all_single(recv, send, output_split_sizes=splits, input_split_sizes=splits, group=self.group)
-        own = cat.index_select(0, self.shared)
-        acc = torch.zeros_like(cat)
-        for s in range(self.world):  # ascending rank order on every rank
-            if s == self.rank:
-                acc.index_add_(0, self.shared, own)
-            elif self.counts[s]:
-                acc.index_add_(0, self.idx[s], recv[self.offs[s]:self.offs[s + 1]])
-        col = 0
-        for f, w in zip(fields, width):
-            f.index_copy_(0, self.shared, acc.index_select(0, self.shared)[:, col:col + w])
-            col += w
+        if len(fields) > 3:
+            self.sum_(*fields[:3])
+            self.sum_(*fields[3:])
+            return
+        nf, dtype, ld = len(fields), fields[0].dtype, int(fields[0].shape[1])
+        send, recv = self._buffers(nf, dtype)
+        if fields[0].is_cuda:
+            L = _lib.lib()
+            f = [_lib.dev_ptr(x) for x in fields] + [None] * (3 - nf)
+            with torch.cuda.device(self.device):
+                st = _lib.stream_ptr(self.device)
+                _lib.check(L.apl_halo_pack(_lib.dtype_code(dtype), self.total, _lib.dev_ptr(self.send_index), nf, f[0], f[1],
+                                           f[2], ld, _lib.dev_ptr(send), st))
+                dist.all_to_all_single(recv, send, output_split_sizes=self.counts, input_split_sizes=self.counts,
+                                       group=self.group)
+                _lib.check(L.apl_halo_unpack(_lib.dtype_code(dtype), self.shared.numel(), _lib.dev_ptr(self.shared),
+                                             _lib.dev_ptr(self.row_ptr), _lib.dev_ptr(self.src), nf, f[0], f[1], f[2], ld,
+                                             _lib.dev_ptr(recv), st))
+            return
+        # CPU tensors (gloo tests of the sharding logic): same arithmetic with torch index ops
+        for k, x in enumerate(fields):
+            send[:, 3 * k:3 * k + 3] = x[:, :3].index_select(0, self.send_index)
+        dist.all_to_all_single(recv, send, output_split_sizes=self.counts, input_split_sizes=self.counts,
+                               group=self.group)
+        for k, x in enumerate(fields):
+            own = x[:, :3].index_select(0, self.shared)
+            acc = torch.zeros_like(x[:, :3])
+            for s in range(self.world):  # ascending rank order on every rank
+                if s == self.rank:
+                    acc.index_add_(0, self.shared, own)
+                elif self.counts[s]:
+                    acc.index_add_(0, self.idx[s], recv[self.offs[s]:self.offs[s + 1], 3 * k:3 * k + 3])
+            x[:, :3].index_copy_(0, self.shared, acc.index_select(0, self.shared))
 
     def all_reduce_(self, t: torch.Tensor) -> None:
         if self.world > 1:

@@ -43,7 +43,12 @@ class ShardedOperators:
         fields = [out[k] for k in ("grad", "diag", "prod") if k in out]
         self.halo.sum_(*fields)
         scalars = [out[k] for k in ("fun", "quad") if k in out]
-        if scalars:
+        if len(scalars) == 1:
+            self.halo.all_reduce_(scalars[0])
+            for k in ("fun", "quad"):
+                if k in out:
+                    out[k] = out[k][0]
+        elif scalars:
             s = torch.cat(scalars)
             self.halo.all_reduce_(s)
             for i, k in enumerate(k for k in ("fun", "quad") if k in out):

@@ -43,7 +43,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=58, help="hexes per cube edge (5 tets per hex)")
+    ap.add_argument("--n", type=int, default=0, help="hexes per cube edge (5 tets per hex); 0 = 58 * gpus^(1/3)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1 with --n 0: weak = ~975k tets per GPU (mesh grows with N), strong = the 58^3 mesh")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--scatter", default="tile", choices=["tile", "atomic", "tile_simple"])
     ap.add_argument("--potentials", default="snh,arap")
@@ -52,7 +54,13 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="also time every operator / variant (stderr table)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.n == 0:
+        args.n = 58 if (world == 1 or args.scaling == "strong") else int(round(58 * world ** (1.0 / 3.0)))
+    else:
+        args.scaling = "strong" if world > 1 else args.scaling
+    return args
 
 
 def build_mesh(n, seed=0):
@@ -364,13 +372,15 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": args.scaling if world > 1 else "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"cube {args.n}^3x5 = {T_total} tets / {V} verts, {'+'.join(kinds)}, "
                                    f"fused energy+grad+HVP ({args.scatter} assembly)",
                        "l2": "256 MiB flush write between timed steps" if not args.no_flush else "no flush",
-                       "parallelism": (f"{world} ranks x contiguous Morton chunk of tets; halo sum of grad+HVP "
-                                       f"(NCCL all-to-all of shared rows) + scalar all-reduce per step")
+                       "parallelism": (f"{world} ranks x contiguous Morton chunk of tets (~{T_total // world} tets per "
+                                       f"GPU, {args.scaling} scaling); halo sum of grad+HVP (NCCL all-to-all of "
+                                       f"shared rows) + scalar all-reduce per step")
                        if world > 1 else "1 GPU"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": args.steps * len(pots),
             "roofline": roofline, "cpu_baseline": cpu, "pncg": pncg,

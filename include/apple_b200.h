@@ -121,6 +121,20 @@ int apl_ext_force_eval(int dtype, int ops, int64_t k, const void* force, const i
 int apl_field_copy(int dtype, int64_t n, const void* src, int ld_src, void* dst, int ld_dst,
                    void* stream);
 
+/* ---- halo sums for sharded meshes (new functionality: the reference is single-GPU) ------------------
+ * Between pack and unpack the caller moves `send` to the other ranks (one all-to-all of the shared rows,
+ * e.g. ncclSend/ncclRecv groups or torch.distributed.all_to_all_single) into `recv`.
+ *   pack:   send[i, f, 0:3] = field_f[index[i], 0:3]        (i < n rows shared with other ranks)
+ *   unpack: for each of the n_shared shared vertices, field_f[shared[i]] = sum over its CSR entries
+ *           src[row_ptr[i] .. row_ptr[i+1]) taken in order: -1 = this rank's own partial, j >= 0 = row j
+ *           of recv.  Listing the entries in ascending rank order makes all replicas bit-identical.
+ * All arrays are DEVICE arrays; up to 3 fields (f1, f2 may be NULL) of leading dimension ld. */
+int apl_halo_pack(int dtype, int64_t n, const int64_t* index, int nf, const void* f0, const void* f1,
+                  const void* f2, int ld, void* send, void* stream);
+int apl_halo_unpack(int dtype, int64_t n_shared, const int64_t* shared, const int32_t* row_ptr,
+                    const int64_t* src, int nf, void* f0, void* f1, void* f2, int ld, const void* recv,
+                    void* stream);
+
 /* ---- fused PNCG workspace -------------------------------------------------------------------------
  * The optimizer the reference uses (liblaf.peach.optim.PNCG) is external to /root/reference; what is
  * restated here are the recurrences of the reference's own PNCG-like benchmark,
