@@ -17,7 +17,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libapple_b200.so"
 # constants of include/apple_b200.h
 OK = 0
 F32, F64 = 0, 1
-KIND_SNH, KIND_ARAP, KIND_SNH_MUSCLE = 0, 1, 2
+KIND_SNH, KIND_ARAP, KIND_SNH_MUSCLE, KIND_SNH_ARAP = 0, 1, 2, 3
 OP_FUN, OP_GRAD, OP_HESS_DIAG, OP_HESS_PROD, OP_HESS_QUAD = 1, 2, 4, 8, 16
 SCATTER_TILE, SCATTER_ATOMIC, SCATTER_TILE_SIMPLE = 0, 1, 2
 PNCG_NSCAL = 96
@@ -34,6 +34,8 @@ SIGNATURES = {
     "apl_device_count": (c_int, []),
     "apl_fem_create": (c_int, [c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_int, POINTER(c_void_p)]),
+    "apl_fem_create_snh_arap": (c_int, [c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_int, POINTER(c_void_p)]),
     "apl_fem_destroy": (None, [c_void_p]),
     "apl_fem_info": (c_int, [c_void_p, POINTER(c_int64)]),
     "apl_fem_host_tables": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

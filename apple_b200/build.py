@@ -44,7 +44,7 @@ def _units():
         ("pncg", "pncg.cu", []),
     ]
     for tname, t in (("f32", "float"), ("f64", "double")):
-        for kind in (0, 1, 2):
+        for kind in (0, 1, 2, 3):
             units.append((f"fem_{tname}_k{kind}", "fem_inst.cu", [f"-DAPL_INST_T={t}", f"-DAPL_INST_KIND={kind}"]))
     return units
 

@@ -14,13 +14,13 @@ const char* last_error_cstr();
 template <typename T, int KIND>
 int launch_fem(const apl_fem* fem, int ops, const FemArgs<T>& args, int scatter, cudaStream_t stream);
 
-static int rec_size(int kind) { return kind == APL_KIND_SNH_MUSCLE ? 18 : 12; }
+static int rec_size(int kind) { return kind == APL_KIND_SNH_MUSCLE ? 18 : (kind == APL_KIND_SNH_ARAP ? 14 : 12); }
 
 // Packs the caller-order reference arrays into [nplanes][plane_stride] 16-byte vectors in packed
 // (tile) order.  Record = D (rows 1..3 of dhdX), vol, mu, lambda, activation[6].
 template <typename T>
 static int pack_planes(apl_fem* f, const T* dhdX, const T* dV, const T* mu, const T* la, const T* act,
-                       std::vector<T>& planes) {
+                       const T* dV2, const T* mu2, std::vector<T>& planes) {
     constexpr int VEC = 16 / (int)sizeof(T);
     const int64_t n = f->host.n_cells;
     const int nrec = f->nrec;
@@ -48,6 +48,10 @@ static int pack_planes(apl_fem* f, const T* dhdX, const T* dV, const T* mu, cons
         rec[11] = la ? la[c] : (T)0;
         if (act)
             for (int k = 0; k < 6; ++k) rec[12 + k] = act[6 * c + k];
+        if (f->kind == APL_KIND_SNH_ARAP) {  // second potential on the same cells
+            rec[12] = dV2 ? dV2[c] : (T)0;
+            rec[13] = mu2 ? mu2[c] : (T)0;
+        }
         for (int k = 0; k < nrec; ++k) {
             const int plane = k / VEC, lane = k % VEC;
             planes[((size_t)plane * f->plane_stride + pos) * VEC + lane] = rec[k];
@@ -58,9 +62,10 @@ static int pack_planes(apl_fem* f, const T* dhdX, const T* dV, const T* mu, cons
 
 template <typename T>
 static int upload_planes(apl_fem* f, const void* dhdX, const void* dV, const void* mu, const void* la,
-                         const void* act) {
+                         const void* act, const void* dV2 = nullptr, const void* mu2 = nullptr) {
     std::vector<T> planes;
-    int rc = pack_planes<T>(f, (const T*)dhdX, (const T*)dV, (const T*)mu, (const T*)la, (const T*)act, planes);
+    int rc = pack_planes<T>(f, (const T*)dhdX, (const T*)dV, (const T*)mu, (const T*)la, (const T*)act,
+                            (const T*)dV2, (const T*)mu2, planes);
     if (rc != APL_OK) return rc;
     if (f->device >= 0) {
         APL_CUDA_CHECK(cudaMemcpy(f->d_planes, planes.data(), planes.size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -113,6 +118,7 @@ static int eval_typed(apl_fem* f, int ops, const void* u, const void* p, int ld_
     switch (f->kind) {
         case APL_KIND_SNH: return launch_fem<T, APL_KIND_SNH>(f, ops, a, scatter, stream);
         case APL_KIND_ARAP: return launch_fem<T, APL_KIND_ARAP>(f, ops, a, scatter, stream);
+        case APL_KIND_SNH_ARAP: return launch_fem<T, APL_KIND_SNH_ARAP>(f, ops, a, scatter, stream);
         default: return launch_fem<T, APL_KIND_SNH_MUSCLE>(f, ops, a, scatter, stream);
     }
 }
@@ -291,16 +297,18 @@ void apl_fem_destroy(apl_fem_t* f) {
     delete f;
 }
 
-int apl_fem_create(int kind, int dtype, int64_t n_cells, int64_t n_points, const int32_t* cells,
-                   const void* dhdX, const void* dV, const void* mu, const void* lambda_,
-                   const void* activation, const double* points, int device, apl_fem_t** out) {
+static int fem_create_impl(int kind, int dtype, int64_t n_cells, int64_t n_points, const int32_t* cells,
+                           const void* dhdX, const void* dV, const void* mu, const void* lambda_,
+                           const void* activation, const void* dV2, const void* mu2, const double* points, int device,
+                           apl_fem_t** out) {
     if (!out) { set_error("apl_fem_create: out is NULL"); return APL_ERR_INVALID; }
     *out = nullptr;
-    if (kind < 0 || kind > 2 || (dtype != APL_F32 && dtype != APL_F64)) {
+    if (kind < 0 || kind > 3 || (dtype != APL_F32 && dtype != APL_F64)) {
         set_error("apl_fem_create: unknown kind or dtype");
         return APL_ERR_INVALID;
     }
-    if (!dhdX || !dV || !mu || (kind != APL_KIND_ARAP && !lambda_) || (kind == APL_KIND_SNH_MUSCLE && !activation)) {
+    if (!dhdX || !dV || !mu || (kind != APL_KIND_ARAP && !lambda_) || (kind == APL_KIND_SNH_MUSCLE && !activation) ||
+        (kind == APL_KIND_SNH_ARAP && (!dV2 || !mu2))) {
         set_error("apl_fem_create: a required array (dhdX, dV, mu, lambda_, activation) is NULL");
         return APL_ERR_INVALID;
     }
@@ -368,11 +376,29 @@ int apl_fem_create(int kind, int dtype, int64_t n_cells, int64_t n_points, const
         APL_TRY(cudaMemset(f->d_counter, 0, sizeof(unsigned int)));
 #undef APL_TRY
     }
-    rc = (dtype == APL_F32) ? upload_planes<float>(f, dhdX, dV, mu, lambda_, activation)
-                            : upload_planes<double>(f, dhdX, dV, mu, lambda_, activation);
+    rc = (dtype == APL_F32) ? upload_planes<float>(f, dhdX, dV, mu, lambda_, activation, dV2, mu2)
+                            : upload_planes<double>(f, dhdX, dV, mu, lambda_, activation, dV2, mu2);
     if (rc != APL_OK) { apl_fem_destroy(f); return rc; }
     *out = f;
     return APL_OK;
+}
+
+int apl_fem_create(int kind, int dtype, int64_t n_cells, int64_t n_points, const int32_t* cells,
+                   const void* dhdX, const void* dV, const void* mu, const void* lambda_,
+                   const void* activation, const double* points, int device, apl_fem_t** out) {
+    if (kind == APL_KIND_SNH_ARAP) {
+        set_error("apl_fem_create: use apl_fem_create_snh_arap for the fused kind");
+        return APL_ERR_INVALID;
+    }
+    return fem_create_impl(kind, dtype, n_cells, n_points, cells, dhdX, dV, mu, lambda_, activation, nullptr, nullptr,
+                           points, device, out);
+}
+
+int apl_fem_create_snh_arap(int dtype, int64_t n_cells, int64_t n_points, const int32_t* cells, const void* dhdX,
+                            const void* dV_snh, const void* mu_snh, const void* lambda_snh, const void* dV_arap,
+                            const void* mu_arap, const double* points, int device, apl_fem_t** out) {
+    return fem_create_impl(APL_KIND_SNH_ARAP, dtype, n_cells, n_points, cells, dhdX, dV_snh, mu_snh, lambda_snh,
+                           nullptr, dV_arap, mu_arap, points, device, out);
 }
 
 int apl_fem_info(const apl_fem_t* f, int64_t info[10]) {
@@ -408,6 +434,7 @@ int apl_fem_set_materials(apl_fem_t* f, const void* dV, const void* mu, const vo
                           const void* activation) {
     if (!f) { set_error("apl_fem_set_materials: NULL handle"); return APL_ERR_INVALID; }
     if (f->device < 0) { set_error("apl_fem_set_materials: host-only handle"); return APL_ERR_STATE; }
+    if (f->kind == APL_KIND_SNH_ARAP) { set_error("apl_fem_set_materials: not supported for fused potentials"); return APL_ERR_STATE; }
     // Read back, patch the requested columns, upload.  Setup-time path, not hot.
     const int vec = f->dtype == APL_F32 ? 4 : 2;
     const size_t esz = f->dtype == APL_F32 ? 4 : 8;

@@ -29,6 +29,7 @@
 #define APL_KIND_SNH 0
 #define APL_KIND_ARAP 1
 #define APL_KIND_SNH_MUSCLE 2
+#define APL_KIND_SNH_ARAP 3  // two potentials on the same cells fused into one pass
 
 #define APL_OP_FUN 1
 #define APL_OP_GRAD 2
@@ -44,7 +45,7 @@ using std::sqrt;
 // Number of scalars in the per-tet static record: D[9], vol, mu, lambda, (activation[6]).
 template <int KIND>
 struct RecSize {
-    static constexpr int value = (KIND == APL_KIND_SNH_MUSCLE) ? 18 : 12;
+    static constexpr int value = (KIND == APL_KIND_SNH_MUSCLE) ? 18 : (KIND == APL_KIND_SNH_ARAP ? 14 : 12);
 };
 
 template <typename T>
@@ -329,25 +330,176 @@ APL_HD void svd3_rv(const T* F, T* U, T* sig, T* V) {
 }
 
 // ------------------------------------------------------------------------------------------
-// One tetrahedron, every requested operator.  rec = [D(9), vol, mu, lambda, (activation 6)].
-// Outputs (already multiplied by vol and clamped exactly like the reference kernels):
-//   psi   : Psi * vol                              (OP_FUN)
-//   g     : (dhdX P^T) * vol                       (OP_GRAD)
-//   dg    : max(diag * vol, 0) per entry           (OP_HESS_DIAG)
-//   hp    : (H p) * vol                            (OP_HESS_PROD)
-//   quad  : max(p^T H p * vol, 0)                  (OP_HESS_QUAD)
+// Energy terms.  Each writes (ACC = false) or adds (ACC = true) its contribution, already multiplied
+// by the cell volume and clamped exactly like the reference kernels, to
+//   psi   : Psi * vol                                  (OP_FUN)
+//   P     : vol * first Piola-Kirchhoff stress (3x3)   (OP_GRAD;      nodal forces = dhdX P^T)
+//   dg    : max(diag * vol, 0) per entry               (OP_HESS_DIAG)
+//   M     : vol * dP[dF]  (3x3)                        (OP_HESS_PROD; H p = dhdX M^T)
+//   quad  : max(p^T H p * vol, 0)                      (OP_HESS_QUAD)
+// Keeping P and M as 3x3 matrices lets several energies on the same cell share one dhdX-product.
+// ------------------------------------------------------------------------------------------
+template <bool ACC, typename T>
+APL_HD void put(T& dst, T v) {
+    if constexpr (ACC) dst += v;
+    else dst = v;
+}
+
+// Stable Neo-Hookean (warp/fem/_stable_neo_hookean.py:17-103) on F with dhdX block D.
+template <typename T, int OPS, bool ACC>
+APL_HD void snh_terms(const T* F, const T* dF, const T* D, T vol, T mu, T la, T& psi, T& quad, T* P, T* M,
+                      T dg[4][3]) {
+    constexpr bool kFun = (OPS & APL_OP_FUN) != 0, kGrad = (OPS & APL_OP_GRAD) != 0;
+    constexpr bool kDiag = (OPS & APL_OP_HESS_DIAG) != 0, kProd = (OPS & APL_OP_HESS_PROD) != 0;
+    constexpr bool kQuad = (OPS & APL_OP_HESS_QUAD) != 0;
+    T C[9];
+    const T J = cofactor(F, C);
+    const T Jm1 = J - (T)1;
+    const T c3 = -mu + la * Jm1;
+    if constexpr (kFun) {
+        const T I2 = ddot9(F, F);
+        put<ACC>(psi, vol * ((T)0.5 * mu * (I2 - (T)3) - mu * Jm1 + (T)0.5 * la * Jm1 * Jm1));
+    }
+    if constexpr (kGrad) {
+        const T a = vol * mu, b = vol * c3;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) put<ACC>(P[k], a * F[k] + b * C[k]);
+    }
+    if constexpr (kDiag) {
+        T W[4][3], n[4];
+        vjp_rows(D, C, (T)1, W);
+        row_norms(D, n);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                put<ACC>(dg[a][i], apl_max(vol * (la * W[a][i] * W[a][i] + mu * n[a]), (T)0));
+    }
+    if constexpr (kProd || kQuad) {
+        T X[9];
+        dcofactor(F, dF, X);
+        const T s = ddot9(C, dF);
+        if constexpr (kProd) {
+            const T a = vol * la * s, b = vol * mu, c = vol * c3;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) put<ACC>(M[k], a * C[k] + b * dF[k] + c * X[k]);
+        }
+        if constexpr (kQuad) {
+            const T q = la * s * s + mu * ddot9(dF, dF) + c3 * ddot9(dF, X);
+            put<ACC>(quad, apl_max(vol * q, (T)0));
+        }
+    }
+}
+
+// ARAP (warp/fem/_arap.py:17-76) on F with dhdX block D.
+template <typename T, int OPS, bool ACC>
+APL_HD void arap_terms(const T* F, const T* dF, const T* D, T vol, T mu, T& psi, T& quad, T* P, T* M, T dg[4][3]) {
+    constexpr bool kFun = (OPS & APL_OP_FUN) != 0, kGrad = (OPS & APL_OP_GRAD) != 0;
+    constexpr bool kDiag = (OPS & APL_OP_HESS_DIAG) != 0, kProd = (OPS & APL_OP_HESS_PROD) != 0;
+    constexpr bool kQuad = (OPS & APL_OP_HESS_QUAD) != 0;
+    T U[9], V[9], sg[3];
+    svd3_rv(F, U, sg, V);
+    if constexpr (kFun) {
+        const T a = sg[0] - (T)1, b = sg[1] - (T)1, c = sg[2] - (T)1;
+        put<ACC>(psi, vol * (T)0.5 * mu * (a * a + b * b + c * c));
+    }
+    if constexpr (kGrad) {
+        const T a = vol * mu;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                put<ACC>(P[3 * i + j], a * (F[3 * i + j] - (U[3 * i] * V[3 * j] + U[3 * i + 1] * V[3 * j + 1] +
+                                                            U[3 * i + 2] * V[3 * j + 2])));
+    }
+    if constexpr (kDiag || kProd || kQuad) {
+        const T two = (T)2;
+        // func/_misc.py:31-43 with clamp: lambda_k = 2 / max(s_i + s_j, 2), pairs (0,1),(1,2),(2,0)
+        const T l0 = two / apl_max(sg[0] + sg[1], two);
+        const T l1 = two / apl_max(sg[1] + sg[2], two);
+        const T l2 = two / apl_max(sg[2] + sg[0], two);
+        // twist modes (func/_misc.py:56-70): Q0 = (u1 v0^T - u0 v1^T)/sqrt2,
+        // Q1 = (u1 v2^T - u2 v1^T)/sqrt2, Q2 = (u0 v2^T - u2 v0^T)/sqrt2
+        if constexpr (kDiag) {
+            // Y[a][n] = dhdX_a . v_n ; (dhdX Q^T)[a][i] = (um[i] Y[a][n] - un[i] Y[a][m]) / sqrt2
+            T Y[4][3], n[4];
+            {
+                T Vt[9];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) Vt[3 * i + j] = V[3 * j + i];
+                vjp_rows(D, Vt, (T)1, Y);  // Y[a][n] = sum_J dhdX[a][J] Vt[n][J] = dhdX_a . v_n
+            }
+            row_norms(D, n);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const T w0 = U[3 * i + 1] * Y[a][0] - U[3 * i + 0] * Y[a][1];
+                    const T w1 = U[3 * i + 1] * Y[a][2] - U[3 * i + 2] * Y[a][1];
+                    const T w2 = U[3 * i + 0] * Y[a][2] - U[3 * i + 2] * Y[a][0];
+                    const T h4 = (T)0.5 * (l0 * w0 * w0 + l1 * w1 * w1 + l2 * w2 * w2);
+                    put<ACC>(dg[a][i], apl_max(vol * mu * (n[a] - h4), (T)0));
+                }
+        }
+        if constexpr (kProd || kQuad) {
+            // B = U^T dF V ; <Q0,dF> = (B10 - B01)/sqrt2, <Q1,dF> = (B12 - B21)/sqrt2,
+            // <Q2,dF> = (B02 - B20)/sqrt2
+            T Tm[9], B[9];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    Tm[3 * i + j] = U[i] * dF[j] + U[3 + i] * dF[3 + j] + U[6 + i] * dF[6 + j];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    B[3 * i + j] = Tm[3 * i] * V[j] + Tm[3 * i + 1] * V[3 + j] + Tm[3 * i + 2] * V[6 + j];
+            const T c0 = B[3] - B[1], c1 = B[5] - B[7], c2 = B[2] - B[6];  // times 1/sqrt2 each
+            if constexpr (kQuad) {
+                const T q = ddot9(dF, dF) - (T)0.5 * (l0 * c0 * c0 + l1 * c1 * c1 + l2 * c2 * c2);
+                put<ACC>(quad, apl_max(vol * mu * q, (T)0));
+            }
+            if constexpr (kProd) {
+                // M = dF - U K V^T, K = 1/2 [[0,-l0c0, l2c2],[l0c0,0,l1c1],[-l2c2,-l1c1,0]]
+                const T k0 = (T)0.5 * l0 * c0, k1 = (T)0.5 * l1 * c1, k2 = (T)0.5 * l2 * c2;
+                T UK[9];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    UK[3 * i + 0] = U[3 * i + 1] * k0 - U[3 * i + 2] * k2;
+                    UK[3 * i + 1] = -U[3 * i + 0] * k0 - U[3 * i + 2] * k1;
+                    UK[3 * i + 2] = U[3 * i + 0] * k2 + U[3 * i + 1] * k1;
+                }
+                const T a = vol * mu;
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        put<ACC>(M[3 * i + j], a * (dF[3 * i + j] - (UK[3 * i] * V[3 * j] + UK[3 * i + 1] * V[3 * j + 1] +
+                                                                     UK[3 * i + 2] * V[3 * j + 2])));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// One tetrahedron, every requested operator, every energy of the cell's record:
+//   SNH / ARAP / SNH_MUSCLE : rec = [D(9), vol, mu, lambda, (activation 6)]
+//   SNH_ARAP (two potentials sharing the cell, WarpModel sum fused into one pass):
+//                             rec = [D(9), vol_snh, mu_snh, lambda_snh, vol_arap, mu_arap]
+// Outputs: psi, quad (scalars), g = dhdX P^T, dg, hp = dhdX M^T, all volume-weighted and clamped as in
+// warp/fem/_base.py:243-383 (diag per entry, quad per cell -- per potential for the fused kind).
 // ------------------------------------------------------------------------------------------
 template <typename T, int KIND, int OPS>
-APL_HD void elem_eval(const T* rec, const T (*uc)[3], const T (*pc)[3], T& psi, T& quad,
-                      T g[4][3], T dg[4][3], T hp[4][3]) {
-    constexpr bool kFun = (OPS & APL_OP_FUN) != 0;
+APL_HD void elem_eval(const T* rec, const T (*uc)[3], const T (*pc)[3], T& psi, T& quad, T g[4][3], T dg[4][3],
+                      T hp[4][3]) {
     constexpr bool kGrad = (OPS & APL_OP_GRAD) != 0;
-    constexpr bool kDiag = (OPS & APL_OP_HESS_DIAG) != 0;
     constexpr bool kProd = (OPS & APL_OP_HESS_PROD) != 0;
     constexpr bool kQuad = (OPS & APL_OP_HESS_QUAD) != 0;
     constexpr bool kNeedP = kProd || kQuad;
 
-    const T vol = rec[9], mu = rec[10];
     T D[9];
     T F[9];
     {
@@ -379,141 +531,18 @@ APL_HD void elem_eval(const T* rec, const T (*uc)[3], const T (*pc)[3], T& psi, 
         edge_diff(pc, e);
         edge_outer(e, D, dF);
     }
-
+    T P[9], M[9];
     if constexpr (KIND == APL_KIND_SNH || KIND == APL_KIND_SNH_MUSCLE) {
-        const T la = rec[11];
-        T C[9];
-        const T J = cofactor(F, C);
-        const T Jm1 = J - (T)1;
-        const T c3 = -mu + la * Jm1;
-        if constexpr (kFun) {
-            const T I2 = ddot9(F, F);
-            psi = vol * ((T)0.5 * mu * (I2 - (T)3) - mu * Jm1 + (T)0.5 * la * Jm1 * Jm1);
-        }
-        if constexpr (kGrad) {
-            T P[9];
-            const T a = vol * mu, b = vol * c3;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) P[k] = a * F[k] + b * C[k];
-            vjp_rows1(D, P, g);
-        }
-        if constexpr (kDiag) {
-            T W[4][3], n[4];
-            vjp_rows(D, C, (T)1, W);
-            row_norms(D, n);
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-                    dg[a][i] = apl_max(vol * (la * W[a][i] * W[a][i] + mu * n[a]), (T)0);
-        }
-        if constexpr (kNeedP) {
-            T X[9];
-            dcofactor(F, dF, X);
-            const T s = ddot9(C, dF);
-            if constexpr (kProd) {
-                T M[9];
-                const T a = vol * la * s, b = vol * mu, c = vol * c3;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) M[k] = a * C[k] + b * dF[k] + c * X[k];
-                vjp_rows1(D, M, hp);
-            }
-            if constexpr (kQuad) {
-                const T q = la * s * s + mu * ddot9(dF, dF) + c3 * ddot9(dF, X);
-                quad = apl_max(vol * q, (T)0);
-            }
-        }
-    } else {  // ARAP
-        T U[9], V[9], sg[3];
-        svd3_rv(F, U, sg, V);
-        if constexpr (kFun) {
-            const T a = sg[0] - (T)1, b = sg[1] - (T)1, c = sg[2] - (T)1;
-            psi = vol * (T)0.5 * mu * (a * a + b * b + c * c);
-        }
-        if constexpr (kGrad) {
-            T P[9];
-            const T a = vol * mu;
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j)
-                    P[3 * i + j] = a * (F[3 * i + j] - (U[3 * i] * V[3 * j] + U[3 * i + 1] * V[3 * j + 1] +
-                                                        U[3 * i + 2] * V[3 * j + 2]));
-            vjp_rows1(D, P, g);
-        }
-        if constexpr (kDiag || kNeedP) {
-            const T two = (T)2;
-            // func/_misc.py:31-43 with clamp: lambda_k = 2 / max(s_i + s_j, 2), pairs (0,1),(1,2),(2,0)
-            const T l0 = two / apl_max(sg[0] + sg[1], two);
-            const T l1 = two / apl_max(sg[1] + sg[2], two);
-            const T l2 = two / apl_max(sg[2] + sg[0], two);
-            // twist modes (func/_misc.py:56-70): Q0 = (u1 v0^T - u0 v1^T)/sqrt2,
-            // Q1 = (u1 v2^T - u2 v1^T)/sqrt2, Q2 = (u0 v2^T - u2 v0^T)/sqrt2
-            if constexpr (kDiag) {
-                // Y[a][n] = dhdX_a . v_n ; (dhdX Q^T)[a][i] = (um[i] Y[a][n] - un[i] Y[a][m]) / sqrt2
-                T Y[4][3], n[4];
-                {
-                    T Vt[9];
-#pragma unroll
-                    for (int i = 0; i < 3; ++i)
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) Vt[3 * i + j] = V[3 * j + i];
-                    vjp_rows(D, Vt, (T)1, Y);  // Y[a][n] = sum_J dhdX[a][J] Vt[n][J] = dhdX_a . v_n
-                }
-                row_norms(D, n);
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        const T w0 = U[3 * i + 1] * Y[a][0] - U[3 * i + 0] * Y[a][1];
-                        const T w1 = U[3 * i + 1] * Y[a][2] - U[3 * i + 2] * Y[a][1];
-                        const T w2 = U[3 * i + 0] * Y[a][2] - U[3 * i + 2] * Y[a][0];
-                        const T h4 = (T)0.5 * (l0 * w0 * w0 + l1 * w1 * w1 + l2 * w2 * w2);
-                        dg[a][i] = apl_max(vol * mu * (n[a] - h4), (T)0);
-                    }
-            }
-            if constexpr (kNeedP) {
-                // B = U^T dF V ; <Q0,dF> = (B10 - B01)/sqrt2, <Q1,dF> = (B12 - B21)/sqrt2,
-                // <Q2,dF> = (B02 - B20)/sqrt2
-                T Tm[9], B[9];
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int j = 0; j < 3; ++j)
-                        Tm[3 * i + j] = U[i] * dF[j] + U[3 + i] * dF[3 + j] + U[6 + i] * dF[6 + j];
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int j = 0; j < 3; ++j)
-                        B[3 * i + j] = Tm[3 * i] * V[j] + Tm[3 * i + 1] * V[3 + j] + Tm[3 * i + 2] * V[6 + j];
-                const T c0 = B[3] - B[1], c1 = B[5] - B[7], c2 = B[2] - B[6];  // times 1/sqrt2 each
-                if constexpr (kQuad) {
-                    const T q = ddot9(dF, dF) - (T)0.5 * (l0 * c0 * c0 + l1 * c1 * c1 + l2 * c2 * c2);
-                    quad = apl_max(vol * mu * q, (T)0);
-                }
-                if constexpr (kProd) {
-                    // M = dF - U K V^T, K = 1/2 [[0,-l0c0, l2c2],[l0c0,0,l1c1],[-l2c2,-l1c1,0]]
-                    const T k0 = (T)0.5 * l0 * c0, k1 = (T)0.5 * l1 * c1, k2 = (T)0.5 * l2 * c2;
-                    T UK[9];
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        UK[3 * i + 0] = U[3 * i + 1] * k0 - U[3 * i + 2] * k2;
-                        UK[3 * i + 1] = -U[3 * i + 0] * k0 - U[3 * i + 2] * k1;
-                        UK[3 * i + 2] = U[3 * i + 0] * k2 + U[3 * i + 1] * k1;
-                    }
-                    T M[9];
-                    const T a = vol * mu;
-#pragma unroll
-                    for (int i = 0; i < 3; ++i)
-#pragma unroll
-                        for (int j = 0; j < 3; ++j)
-                            M[3 * i + j] = a * (dF[3 * i + j] - (UK[3 * i] * V[3 * j] + UK[3 * i + 1] * V[3 * j + 1] +
-                                                                 UK[3 * i + 2] * V[3 * j + 2]));
-                    vjp_rows1(D, M, hp);
-                }
-            }
-        }
+        snh_terms<T, OPS, false>(F, dF, D, rec[9], rec[10], rec[11], psi, quad, P, M, dg);
+    } else if constexpr (KIND == APL_KIND_ARAP) {
+        arap_terms<T, OPS, false>(F, dF, D, rec[9], rec[10], psi, quad, P, M, dg);
+    } else {
+        static_assert(KIND == APL_KIND_SNH_ARAP, "unknown energy kind");
+        snh_terms<T, OPS, false>(F, dF, D, rec[9], rec[10], rec[11], psi, quad, P, M, dg);
+        arap_terms<T, OPS, true>(F, dF, D, rec[12], rec[13], psi, quad, P, M, dg);
     }
+    if constexpr (kGrad) vjp_rows1(D, P, g);
+    if constexpr (kProd) vjp_rows1(D, M, hp);
 }
 
 }  // namespace apl

@@ -25,7 +25,9 @@ class ModelBuilder:
     def add_vertices(self, obj) -> None:
         self.dof.add_vertices(obj)
 
-    def finalize(self) -> Model:
+    def finalize(self, *, fuse: bool = True) -> Model:
+        """``fuse=True`` evaluates potentials that share their cells in one pass (same results as the
+        reference's sum over potentials, ``warp/model/_model.py:13-36``)."""
         collision = None
         if self.collision is not None:
             collision = self.collision.finalize()
@@ -35,6 +37,11 @@ class ModelBuilder:
         if self.potentials and device is None:
             device = getattr(self.potentials[0], "device", None)
         dof_map = self.dof.finalize(dtype=dtype, device=device)
-        warp_model = WarpModel({potential.name: potential for potential in self.potentials})
+        potentials = {potential.name: potential for potential in self.potentials}
+        if fuse:
+            from apple_b200.warp.fem import fuse_potentials
+
+            potentials = fuse_potentials(potentials)
+        warp_model = WarpModel(potentials)
         adapter = WarpModelAdapter(warp_model, n_points=dof_map.n_points)
         return Model(dof_map=dof_map, warp_model=adapter, collision=collision)

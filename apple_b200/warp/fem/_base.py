@@ -64,8 +64,12 @@ class WarpPotentialFem(WarpPotential):
         self.n_points = int(n_points if n_points is not None else (self.region.cells.max() + 1 if n_cells else 1))
         if self.device.type != "cuda":
             raise _lib.NativeError("apple_b200 potentials live on a CUDA device (there is no CPU path)")
+        self.points = None if points is None else np.ascontiguousarray(points, dtype=np.float64)
+        self._handle = self._create_handle()
+
+    def _create_handle(self) -> ctypes.c_void_p:
         handle = ctypes.c_void_p()
-        pts = None if points is None else np.ascontiguousarray(points, dtype=np.float64)
+        n_cells = self.region.cells.shape[0]
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         _lib.check(
             _lib.lib().apl_fem_create(
@@ -75,10 +79,10 @@ class WarpPotentialFem(WarpPotential):
                 _lib.host_ptr(getattr(self.materials, "mu", None)),
                 _lib.host_ptr(getattr(self.materials, "lambda_", None)),
                 _lib.host_ptr(getattr(self.materials, "activation", None)),
-                _lib.host_ptr(pts), dev_index, ctypes.byref(handle),
+                _lib.host_ptr(self.points), dev_index, ctypes.byref(handle),
             )
         )
-        self._handle = handle
+        return handle
 
     def __del__(self):
         handle = getattr(self, "_handle", None)

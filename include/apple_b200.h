@@ -41,6 +41,7 @@ extern "C" {
 #define APL_KIND_SNH 0
 #define APL_KIND_ARAP 1
 #define APL_KIND_SNH_MUSCLE 2
+#define APL_KIND_SNH_ARAP 3 /* an SNH and an ARAP potential on the SAME cells, summed in one pass (see below) */
 
 /* operator bit mask; any OR of these is evaluated in ONE pass over the elements */
 #define APL_OP_FUN 1        /* WarpPotentialFem.fun        warp/fem/_base.py:151-158, kernel :243-263 */
@@ -78,6 +79,14 @@ int apl_device_count(void);
 int apl_fem_create(int kind, int dtype, int64_t n_cells, int64_t n_points, const int32_t* cells,
                    const void* dhdX, const void* dV, const void* mu, const void* lambda_,
                    const void* activation, const double* points, int device, apl_fem_t** out);
+/* Two potentials that share their cells -- what WarpModel (warp/model/_model.py:13-36) would evaluate as
+ * two kernel launches per operator, each re-reading the mesh and re-gathering the vertices -- fused
+ * into ONE handle whose passes return the SUM of a Stable Neo-Hookean and an ARAP potential (each with
+ * its own dV = Fraction * dV and materials; clamps applied per potential exactly as in the reference). */
+int apl_fem_create_snh_arap(int dtype, int64_t n_cells, int64_t n_points, const int32_t* cells,
+                            const void* dhdX, const void* dV_snh, const void* mu_snh, const void* lambda_snh,
+                            const void* dV_arap, const void* mu_arap, const double* points, int device,
+                            apl_fem_t** out);
 void apl_fem_destroy(apl_fem_t* fem);
 
 /* info[0..9] = n_cells, n_points, n_tiles, length of tile_verts, static device bytes,

@@ -215,3 +215,39 @@ def test_rest_state_and_isotropic_scaling(native_lib, kind, dtype):
         dref = np.zeros((V, 3)); ora.hess_diag(u, dref)
         # gradient may vanish identically (rest state): compare against the force scale diag * h
         assert np.abs(grad.cpu().numpy() - ref).max() <= tol * max(np.abs(ref).max(), np.abs(dref).max() * 0.2)
+
+
+@pytest.mark.parametrize("scatter", [0, 1, 2], ids=["tile", "atomic", "tile_simple"])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_fused_snh_arap_equals_sum_of_potentials(native_lib, case, dtype, scatter):
+    """Two potentials on the same cells fused into one pass == WarpModel's sum over potentials
+    (warp/model/_model.py:13-36), with different Fraction / materials per potential and the clamps
+    applied per potential."""
+    from apple_b200.warp.fem import FusedSnhArap, fuse_potentials
+    from oracle import fem as ofem
+
+    mesh, u, p = case
+    V = mesh.n_points
+    m2 = mesh.copy()
+    m2.cell_data["Fraction"] = 1.0 - 0.5 * mesh.cell_data["Fraction"]
+    m2.cell_data["mu"] = mesh.cell_data["mu"][::-1].copy()
+    snh = cuda_potential("snh", mesh, dtype, name="snh", scatter=scatter)
+    arap = cuda_potential("arap", m2, dtype, name="arap", scatter=scatter)
+    fused = fuse_potentials({"snh": snh, "arap": arap})
+    assert list(fused) == ["snh+arap"] and isinstance(fused["snh+arap"], FusedSnhArap)
+    pot = fused["snh+arap"]
+    ora = ofem.Model([oracle_potential("snh", mesh), oracle_potential("arap", m2)], V)
+    ud, pd = _dev(3.0 * u, dtype), _dev(p, dtype)      # large deformation: some cells have clamped p.Hp
+    u3 = 3.0 * u
+    fun = torch.zeros(1, dtype=dtype, device="cuda"); quad = torch.zeros(1, dtype=dtype, device="cuda")
+    grad, diag, prod = (torch.zeros((V, 3), dtype=dtype, device="cuda") for _ in range(3))
+    pot.eval(31, ud, pd, fun=fun, quad=quad, grad=grad, diag=diag, prod=prod)
+    tol = 2 * TOL[dtype]
+    assert rel_err(fun.cpu(), ora.fun(u3)) < tol
+    assert rel_err(quad.cpu(), ora.hess_quad(u3, p)) < tol
+    assert rel_err(grad.cpu(), ora.grad(u3)) < tol
+    assert rel_err(diag.cpu(), ora.hess_diag(u3)) < tol
+    assert rel_err(prod.cpu(), ora.hess_prod(u3, p)) < tol
+    # potentials over different cells are left alone
+    other = cuda_potential("arap", make_case(n=3, seed=1)[0], dtype, name="other")
+    assert set(fuse_potentials({"snh": snh, "other": other})) == {"snh", "other"}
