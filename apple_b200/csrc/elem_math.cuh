@@ -53,12 +53,32 @@ APL_HD T apl_max(T a, T b) {
     return a > b ? a : b;
 }
 
+// Raw hardware approximations (one MUFU each, ~1 ulp, flush-to-zero) for the fp32 Jacobi rotation.
+APL_HD float apl_rsqrt_raw(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / std::sqrt(x);
+#endif
+}
+APL_HD float apl_rcp_raw(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+
 template <typename T>
 APL_HD T apl_rsqrt(T x) {
 #if defined(__CUDA_ARCH__)
     if constexpr (sizeof(T) == 4) {
         // one Newton step on the hardware approximation: full fp32 accuracy
-        float r = rsqrtf((float)x);
+        float r = apl_rsqrt_raw((float)x);
         r = r * (1.5f - 0.5f * (float)x * r * r);
         return (T)r;
     } else {
@@ -181,48 +201,49 @@ APL_HD void row_norms(const T* D, T n[4]) {
 // Cyclic Jacobi on F^T F for V, then modified Gram-Schmidt on F V for U and the singular values
 // (column norms of F V are more accurate than square roots of the eigenvalues).
 // ------------------------------------------------------------------------------------------
-// Fast reciprocal for quantities that only steer convergence (rotation angles), not accuracy.
-template <typename T>
-APL_HD T apl_rcp_fast(T x) {
-#if defined(__CUDA_ARCH__)
-    if constexpr (sizeof(T) == 4) {
-        float r;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)x));
-        return (T)r;
-    } else {
-        return (T)1 / x;
-    }
-#else
-    return (T)1 / x;
-#endif
-}
-
 template <typename T>
 APL_HD void jacobi_rotate(T* A, T* V, int p, int q) {
     // A symmetric, stored fully (row-major 3x3).  Annihilates A[p][q] with the rotation
     // tan(theta) = t = sgn(d) 2 a_pq / (|d| + sqrt(d^2 + 4 a_pq^2)),  d = a_qq - a_pp  (|theta| <= pi/4).
     const T apq = A[3 * p + q];
     const T app = A[3 * p + p], aqq = A[3 * q + q];
-    // Skip when the off-diagonal entry is below rounding level relative to the diagonal (or absolutely
-    // tiny): rotating further cannot improve the result, and b*b below would underflow to zero.
-    const T tiny = (sizeof(T) == 4) ? (T)1e-18 : (T)1e-150;
-    const T rel = (sizeof(T) == 4) ? (T)1e-16 : (T)1e-34;
-    if (!(fabs(apq) > tiny) || !(apq * apq > rel * fabs(app * aqq))) {
-        A[3 * p + q] = A[3 * q + p] = (T)0;
-        return;
-    }
-    const T d = aqq - app, b = (T)2 * apq;
-    const T h2 = d * d + b * b;
-    const T h = h2 * apl_rsqrt(h2);
-    T t = b * apl_rcp_fast(fabs(d) + h);
-    if (d < (T)0) t = -t;
-    const T c = apl_rsqrt(t * t + (T)1);  // full precision: keeps V orthonormal
-    const T s = t * c;
     const int r = 3 - p - q;  // the untouched index
+    T c, s, t;
+    if constexpr (sizeof(T) == 4) {
+        // Branch-free: an off-diagonal entry below rounding level relative to the diagonal (or so small
+        // that b*b underflows) gets t = 0, i.e. the identity rotation.  The angle only steers
+        // convergence, so approximate reciprocals are fine; c gets one Newton step so that
+        // c^2 + s^2 = 1 to fp32 accuracy and V stays orthonormal.
+        const float d = aqq - app, b = 2.0f * apq;
+        const float h2 = d * d + b * b;
+        const float h = h2 * apl_rsqrt_raw(fmaxf(h2, 1e-36f));
+        float tt = b * apl_rcp_raw(fabsf(d) + h + 1e-30f);
+        tt = d < 0.0f ? -tt : tt;
+        const bool negligible = !(apq * apq > 1e-16f * fabsf(app * aqq)) || !(fabsf(apq) > 1e-18f);
+        tt = negligible ? 0.0f : tt;
+        const float x = tt * tt + 1.0f;
+        float cc = apl_rsqrt_raw(x);
+        cc = cc * (1.5f - 0.5f * x * cc * cc);
+        t = tt; c = cc; s = tt * cc;
+        A[3 * p + q] = A[3 * q + p] = 0.0f;
+    } else {
+        // Skip when the off-diagonal entry is below rounding level relative to the diagonal (or
+        // absolutely tiny): rotating further cannot improve the result, and b*b would underflow.
+        if (!(fabs(apq) > (T)1e-150) || !(apq * apq > (T)1e-34 * fabs(app * aqq))) {
+            A[3 * p + q] = A[3 * q + p] = (T)0;
+            return;
+        }
+        const T d = aqq - app, b = (T)2 * apq;
+        const T h = sqrt(d * d + b * b);
+        t = b / (fabs(d) + h);
+        if (d < (T)0) t = -t;
+        c = (T)1 / sqrt(t * t + (T)1);
+        s = t * c;
+        A[3 * p + q] = A[3 * q + p] = (T)0;
+    }
     const T arp = A[3 * r + p], arq = A[3 * r + q];
     A[3 * p + p] = app - t * apq;
     A[3 * q + q] = aqq + t * apq;
-    A[3 * p + q] = A[3 * q + p] = (T)0;
     A[3 * r + p] = A[3 * p + r] = c * arp - s * arq;
     A[3 * r + q] = A[3 * q + r] = s * arp + c * arq;
 #pragma unroll
@@ -243,16 +264,17 @@ APL_HD bool apl_all_done(bool done) {
 }
 
 template <typename T>
-APL_HD void swap_cols_neg(T* A, T* V, int a, int b) {
-    // swap eigenpairs a <-> b, negating one column to keep det V = +1
-    T t = A[3 * a + a];
-    A[3 * a + a] = A[3 * b + b];
-    A[3 * b + b] = t;
+APL_HD void swap_cols_neg(T* A, T* V, int a, int b, bool doit) {
+    // conditional (select-based, branch-free) swap of eigenpairs a <-> b, negating one column to keep
+    // det V = +1
+    const T ea = A[3 * a + a], eb = A[3 * b + b];
+    A[3 * a + a] = doit ? eb : ea;
+    A[3 * b + b] = doit ? ea : eb;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        T va = V[3 * k + a];
-        V[3 * k + a] = V[3 * k + b];
-        V[3 * k + b] = -va;
+        const T va = V[3 * k + a], vb = V[3 * k + b];
+        V[3 * k + a] = doit ? vb : va;
+        V[3 * k + b] = doit ? -va : vb;
     }
 }
 
@@ -282,9 +304,9 @@ APL_HD void svd3_rv(const T* F, T* U, T* sig, T* V) {
         if (apl_all_done(off <= tol)) break;
     }
     // sort eigenvalues descending (det V stays +1)
-    if (A[0] < A[4]) swap_cols_neg(A, V, 0, 1);
-    if (A[0] < A[8]) swap_cols_neg(A, V, 0, 2);
-    if (A[4] < A[8]) swap_cols_neg(A, V, 1, 2);
+    swap_cols_neg(A, V, 0, 1, A[0] < A[4]);
+    swap_cols_neg(A, V, 0, 2, A[0] < A[8]);
+    swap_cols_neg(A, V, 1, 2, A[4] < A[8]);
     // B = F V
     T B[9];
 #pragma unroll

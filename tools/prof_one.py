@@ -17,7 +17,11 @@ a = ap.parse_args()
 dt = torch.float32 if a.dtype == "f32" else torch.float64
 mesh, u, p = build_mesh(a.n)
 V = mesh.n_points
-pot = cuda_potential(a.kind, mesh, dt)
+if a.kind == "fused":
+    from apple_b200.warp.fem import fuse_potentials
+    pot = list(fuse_potentials({k: cuda_potential(k, mesh, dt, name=k) for k in ("snh", "arap")}).values())[0]
+else:
+    pot = cuda_potential(a.kind, mesh, dt)
 ud = torch.zeros((V, a.ld), dtype=dt, device="cuda"); ud[:, :3] = torch.as_tensor(u, dtype=dt)
 pd = torch.zeros((V, a.ld), dtype=dt, device="cuda"); pd[:, :3] = torch.as_tensor(p, dtype=dt)
 outs = {k: torch.zeros((V, a.ld), dtype=dt, device="cuda") for k in ("grad", "diag", "prod")}
