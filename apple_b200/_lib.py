@@ -22,7 +22,7 @@ OP_FUN, OP_GRAD, OP_HESS_DIAG, OP_HESS_PROD, OP_HESS_QUAD = 1, 2, 4, 8, 16
 SCATTER_TILE, SCATTER_ATOMIC, SCATTER_TILE_SIMPLE = 0, 1, 2
 PNCG_NSCAL = 96
 S_F, S_F_PREV, S_GP, S_PHP, S_ALPHA, S_BETA, S_GNORM2, S_GNORM2_FIRST = 0, 1, 2, 3, 4, 5, 6, 7
-S_ACCEPTED, S_LS_STEPS, S_K, S_N_ACCEPTED, S_DIAG_MEAN, S_GPG, S_DONE, S_FAILS, S_F_NEW = 8, 9, 10, 11, 12, 13, 15, 16, 17
+S_ACCEPTED, S_LS_STEPS, S_K, S_N_ACCEPTED, S_DIAG_MEAN, S_GPG, S_DONE, S_FAILS, S_F_NEW, S_J = 8, 9, 10, 11, 12, 13, 15, 16, 17, 18
 S_SUMS, S_ALPHA_J, S_ACC_J, S_FT_J = 20, 32, 48, 64
 (PHASE_INIT, PHASE_REDUCE, PHASE_FINALIZE, PHASE_DIRECTION, PHASE_PASS_B, PHASE_ALPHA, PHASE_TRIAL, PHASE_LS,
  PHASE_COMMIT) = range(9)

@@ -76,7 +76,7 @@ static int upload_planes(apl_fem* f, const void* dhdX, const void* dV, const voi
 struct PncgExtras {
     const void* axpy_p = nullptr;
     const double* scal = nullptr;
-    int alpha_idx = 0, skip_a = -1, skip_b = -1;
+    int alpha_idx = 0, skip_a = -1, skip_b = -1, dyn_j = 0;
     double* fun_d = nullptr;
     double* quad_d = nullptr;
 };
@@ -92,6 +92,7 @@ static int eval_typed(apl_fem* f, int ops, const void* u, const void* p, int ld_
         a.alpha_idx = ex->alpha_idx;
         a.skip_a = ex->skip_a;
         a.skip_b = ex->skip_b;
+        a.dyn_j = ex->dyn_j;
         a.fun_d = (ops & APL_OP_FUN) ? ex->fun_d : nullptr;
         a.quad_d = (ops & APL_OP_HESS_QUAD) ? ex->quad_d : nullptr;
     }
@@ -129,13 +130,15 @@ template <typename T>
 __global__ void ext_force_kernel(int ops, long long k, const T* __restrict__ force,
                                  const int* __restrict__ indices, const T* __restrict__ u, int ld_in, T* fun,
                                  T* grad, int ld_out, const T* __restrict__ axpy_p, const double* scal,
-                                 int alpha_idx, int skip_a, int skip_b, double* fun_d) {
+                                 int alpha_idx, int skip_a, int skip_b, double* fun_d, int dyn_j) {
     // warp/potential/_ext_force.py:17-39: W = -f.u[vid] (atomic to out[0]); grad[vid] -= f
+    const int joff = (scal && dyn_j) ? (int)__ldcg(scal + APL_S_J) : 0;
     if (scal) {
         if (skip_a >= 0 && __ldcg(scal + skip_a) != 0.0) return;
-        if (skip_b >= 0 && __ldcg(scal + skip_b) != 0.0) return;
+        if (skip_b >= 0 && __ldcg(scal + skip_b + joff) != 0.0) return;
     }
-    const T alpha = axpy_p ? (T)__ldcg(scal + alpha_idx) : (T)0;
+    const T alpha = axpy_p ? (T)__ldcg(scal + alpha_idx + joff) : (T)0;
+    if (fun_d) fun_d += joff;
     double w = 0.0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < k;
          i += (long long)gridDim.x * blockDim.x) {
@@ -235,9 +238,10 @@ static int grid_for(long long n, int block) {
 
 int fem_eval_pncg(apl_fem* f, int ops, const void* x, const void* p, const void* axpy_p, double* scal,
                   int alpha_idx, int skip_a, int skip_b, double* fun_d, double* quad_d, void* grad, void* diag,
-                  int scatter, cudaStream_t stream) {
+                  int scatter, cudaStream_t stream, int dyn_j) {
     PncgExtras ex;
     ex.axpy_p = axpy_p; ex.scal = scal; ex.alpha_idx = alpha_idx; ex.skip_a = skip_a; ex.skip_b = skip_b;
+    ex.dyn_j = dyn_j;
     ex.fun_d = fun_d; ex.quad_d = quad_d;
     return f->dtype == APL_F32
                ? eval_typed<float>(f, ops, x, p, 4, nullptr, nullptr, grad, diag, nullptr, 4, scatter, stream, &ex)
@@ -246,17 +250,17 @@ int fem_eval_pncg(apl_fem* f, int ops, const void* x, const void* p, const void*
 
 int ext_force_pncg(int dtype, int ops, int64_t k, const void* force, const int32_t* indices, const void* x,
                    const void* axpy_p, double* scal, int alpha_idx, int skip_a, int skip_b, double* fun_d,
-                   void* grad, cudaStream_t stream) {
+                   void* grad, cudaStream_t stream, int dyn_j) {
     if (k == 0) return APL_OK;
     const int block = 256, grid = grid_for(k, block);
     if (dtype == APL_F32)
         ext_force_kernel<float><<<grid, block, 0, stream>>>(ops, k, (const float*)force, indices, (const float*)x, 4,
                                                             nullptr, (float*)grad, 4, (const float*)axpy_p, scal,
-                                                            alpha_idx, skip_a, skip_b, fun_d);
+                                                            alpha_idx, skip_a, skip_b, fun_d, dyn_j);
     else
         ext_force_kernel<double><<<grid, block, 0, stream>>>(ops, k, (const double*)force, indices, (const double*)x,
                                                              4, nullptr, (double*)grad, 4, (const double*)axpy_p, scal,
-                                                             alpha_idx, skip_a, skip_b, fun_d);
+                                                             alpha_idx, skip_a, skip_b, fun_d, dyn_j);
     APL_CUDA_CHECK(cudaGetLastError());
     return APL_OK;
 }
@@ -498,11 +502,11 @@ int apl_ext_force_eval(int dtype, int ops, int64_t k, const void* force, const i
     if (dtype == APL_F32)
         ext_force_kernel<float><<<grid, block, 0, s>>>(ops, k, (const float*)force, indices, (const float*)u, ld_in,
                                                        (float*)fun, (float*)grad, ld_out, nullptr, nullptr, 0, -1, -1,
-                                                       nullptr);
+                                                       nullptr, 0);
     else if (dtype == APL_F64)
         ext_force_kernel<double><<<grid, block, 0, s>>>(ops, k, (const double*)force, indices, (const double*)u,
                                                         ld_in, (double*)fun, (double*)grad, ld_out, nullptr, nullptr, 0,
-                                                        -1, -1, nullptr);
+                                                        -1, -1, nullptr, 0);
     else { set_error("apl_ext_force_eval: unknown dtype"); return APL_ERR_INVALID; }
     APL_CUDA_CHECK(cudaGetLastError());
     return APL_OK;

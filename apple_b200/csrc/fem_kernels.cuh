@@ -54,6 +54,7 @@ struct FemArgs {
     const double* scal = nullptr;    // device scalars of the PNCG workspace
     int alpha_idx = 0;
     int skip_a = -1, skip_b = -1;    // the launch is a no-op if scal[skip_a] != 0 or scal[skip_b] != 0
+    int dyn_j = 0;                   // add the device-side trial counter scal[APL_S_J] to alpha_idx, skip_b, fun_d
     double* fun_d = nullptr;         // double-precision sinks for the energy / quadratic form
     double* quad_d = nullptr;
 #ifdef APL_PROFILE_KNOBS
@@ -62,10 +63,15 @@ struct FemArgs {
 };
 
 template <typename T>
-__device__ __forceinline__ bool fem_skip(const FemArgs<T>& a) {
+__device__ __forceinline__ int fem_joff(const FemArgs<T>& a) {
+    return (a.scal != nullptr && a.dyn_j) ? (int)__ldcg(a.scal + APL_S_J) : 0;
+}
+
+template <typename T>
+__device__ __forceinline__ bool fem_skip(const FemArgs<T>& a, int joff) {
     if (a.scal == nullptr) return false;
     if (a.skip_a >= 0 && __ldcg(a.scal + a.skip_a) != 0.0) return true;
-    if (a.skip_b >= 0 && __ldcg(a.scal + a.skip_b) != 0.0) return true;
+    if (a.skip_b >= 0 && __ldcg(a.scal + a.skip_b + joff) != 0.0) return true;
     return false;
 }
 
@@ -450,9 +456,10 @@ __global__ void __launch_bounds__(kTileTets, (sizeof(T) == 4 ? 2 : 1)) fem_tile_
 
     const int tid = threadIdx.x;
     double e_acc = 0.0, q_acc = 0.0;
-    if (fem_skip(a)) return;
+    const int joff = fem_joff(a);
+    if (fem_skip(a, joff)) return;
     const bool axpy = a.axpy_p != nullptr;
-    const T alpha = axpy ? (T)__ldcg(a.scal + a.alpha_idx) : (T)0;
+    const T alpha = axpy ? (T)__ldcg(a.scal + a.alpha_idx + joff) : (T)0;
 
     // Software prefetch of the INDICES one tile ahead (tile header, then this thread's vertex id), so
     // that the per-tile critical path is one memory round trip (static planes + vertex gather issued
@@ -501,7 +508,7 @@ __global__ void __launch_bounds__(kTileTets, (sizeof(T) == 4 ? 2 : 1)) fem_tile_
     }
     if constexpr (Cfg::kFun || Cfg::kQuad)
         finish_scalars<T, kTileTets>(e_acc, q_acc, a.partials, a.counter, Cfg::kFun ? a.fun : nullptr,
-                                     Cfg::kQuad ? a.quad : nullptr, Cfg::kFun ? a.fun_d : nullptr,
+                                     Cfg::kQuad ? a.quad : nullptr, (Cfg::kFun && a.fun_d) ? a.fun_d + joff : nullptr,
                                      Cfg::kQuad ? a.quad_d : nullptr);
 }
 
@@ -622,9 +629,10 @@ __global__ void __launch_bounds__(kPipeThreads, (sizeof(T) == 4 ? 3 : 1) * (256 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     double e_acc = 0.0, q_acc = 0.0;
-    if (fem_skip(a)) return;
+    const int joff = fem_joff(a);
+    if (fem_skip(a, joff)) return;
     const bool axpy = a.axpy_p != nullptr;
-    const T alpha = axpy ? (T)__ldcg(a.scal + a.alpha_idx) : (T)0;
+    const T alpha = axpy ? (T)__ldcg(a.scal + a.alpha_idx + joff) : (T)0;
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
@@ -754,7 +762,7 @@ __global__ void __launch_bounds__(kPipeThreads, (sizeof(T) == 4 ? 3 : 1) * (256 
     }
     if constexpr (Cfg::kFun || Cfg::kQuad)
         finish_scalars<T, kPipeThreads>(e_acc, q_acc, a.partials, a.counter, Cfg::kFun ? a.fun : nullptr,
-                                        Cfg::kQuad ? a.quad : nullptr, Cfg::kFun ? a.fun_d : nullptr,
+                                        Cfg::kQuad ? a.quad : nullptr, (Cfg::kFun && a.fun_d) ? a.fun_d + joff : nullptr,
                                         Cfg::kQuad ? a.quad_d : nullptr);
 }
 
@@ -766,9 +774,10 @@ __global__ void __launch_bounds__(kTileTets) fem_atomic_kernel(const FemArgs<T> 
     constexpr int NREC = RecSize<KIND>::value;
     const int tid = threadIdx.x;
     double e_acc = 0.0, q_acc = 0.0;
-    if (fem_skip(a)) return;
+    const int joff = fem_joff(a);
+    if (fem_skip(a, joff)) return;
     const bool axpy = a.axpy_p != nullptr;
-    const T alpha = axpy ? (T)__ldcg(a.scal + a.alpha_idx) : (T)0;
+    const T alpha = axpy ? (T)__ldcg(a.scal + a.alpha_idx + joff) : (T)0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int4 h = __ldg(a.tiles + tile);
         if (tid < (h.y & 0xffff)) {
@@ -813,7 +822,7 @@ __global__ void __launch_bounds__(kTileTets) fem_atomic_kernel(const FemArgs<T> 
     }
     if constexpr (Cfg::kFun || Cfg::kQuad)
         finish_scalars<T, kTileTets>(e_acc, q_acc, a.partials, a.counter, Cfg::kFun ? a.fun : nullptr,
-                                     Cfg::kQuad ? a.quad : nullptr, Cfg::kFun ? a.fun_d : nullptr,
+                                     Cfg::kQuad ? a.quad : nullptr, (Cfg::kFun && a.fun_d) ? a.fun_d + joff : nullptr,
                                      Cfg::kQuad ? a.quad_d : nullptr);
 }
 

@@ -30,10 +30,10 @@ namespace apl {
 
 int fem_eval_pncg(apl_fem* f, int ops, const void* x, const void* p, const void* axpy_p, double* scal,
                   int alpha_idx, int skip_a, int skip_b, double* fun_d, double* quad_d, void* grad, void* diag,
-                  int scatter, cudaStream_t stream);
+                  int scatter, cudaStream_t stream, int dyn_j = 0);
 int ext_force_pncg(int dtype, int ops, int64_t k, const void* force, const int32_t* indices, const void* x,
                    const void* axpy_p, double* scal, int alpha_idx, int skip_a, int skip_b, double* fun_d,
-                   void* grad, cudaStream_t stream);
+                   void* grad, cudaStream_t stream, int dyn_j = 0);
 
 constexpr int kVecThreads = 256;
 constexpr int kNSums = 11;
@@ -189,6 +189,7 @@ __global__ void pncg_finalize_kernel(double* scal, PncgParams prm) {
     scal[APL_S_BETA] = beta;
     scal[APL_S_PHP] = 0.0;
     scal[APL_S_F_NEW] = 0.0;
+    scal[APL_S_J] = 0.0;
     for (int j = 0; j < 16; ++j) {
         scal[APL_S_ALPHA_J + j] = 0.0;
         scal[APL_S_ACC_J + j] = 0.0;
@@ -246,10 +247,22 @@ __global__ void pncg_alpha_kernel(double* scal, PncgParams prm) {
 
 // Armijo test of trial j (bench :413-456).  State for trial j+1 goes to slot j+1, so every thread
 // of the grid reads slot j while thread 0 writes slot j+1: no intra-kernel race.
+__global__ void pncg_bump_j_kernel(double* scal) {
+    if (scal[APL_S_DONE] != 0.0) return;
+    scal[APL_S_J] += 1.0;
+}
+
+// j < 0: the trial index is the device-side counter scal[APL_S_J] - 1 (the trial that just ran) and the
+// outcome drives a CUDA-graph WHILE node: condition 1 = run another trial.
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads) pncg_ls_kernel(long long rows, int j, int last, T* __restrict__ gz,
-                                                             T* __restrict__ dz, double* scal, PncgParams prm) {
+                                                             T* __restrict__ dz, double* scal, PncgParams prm,
+                                                             cudaGraphConditionalHandle cond, int use_cond) {
     if (__ldcg(scal + APL_S_DONE) != 0.0) return;
+    if (j < 0) {
+        j = (int)__ldcg(scal + APL_S_J) - 1;
+        last = (j >= prm.max_halvings) ? 1 : 0;
+    }
     const double acc = __ldcg(scal + APL_S_ACC_J + j);
     const double alpha = __ldcg(scal + APL_S_ALPHA_J + j);
     const double ft = __ldcg(scal + APL_S_FT_J + j);
@@ -269,6 +282,7 @@ __global__ void __launch_bounds__(kVecThreads) pncg_ls_kernel(long long rows, in
         scal[APL_S_ACC_J + j + 1] = accepted ? 1.0 : (retry ? 0.0 : -1.0);
         scal[APL_S_ALPHA_J + j + 1] = retry ? alpha * 0.5 : alpha;
         if (newly) scal[APL_S_F_NEW] = ft;
+        if (use_cond) cudaGraphSetConditional(cond, retry ? 1u : 0u);
     }
     if (!retry) return;
     const T zero[4] = {(T)0, (T)0, (T)0, (T)0};
@@ -285,6 +299,7 @@ __global__ void __launch_bounds__(kVecThreads) pncg_commit_kernel(long long rows
                                                                  T* __restrict__ gz, const T* __restrict__ diag,
                                                                  T* __restrict__ dz, double* scal) {
     if (__ldcg(scal + APL_S_DONE) != 0.0) return;
+    if (jfinal < 0) jfinal = (int)__ldcg(scal + APL_S_J);  // conditional-graph line search: trials run so far
     const bool accepted = __ldcg(scal + APL_S_ACC_J + jfinal) > 0.0;
     const double alpha = __ldcg(scal + APL_S_ALPHA_J + jfinal);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -353,6 +368,8 @@ struct apl_pncg {
     struct Ext { const void* force; const int32_t* idx; int64_t k; };
     std::vector<Ext> exts;
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    cudaGraphConditionalHandle cond[2] = {0, 0};
+    int graph_mode = 0;  // 0 none, 1 static trials, 2 conditional WHILE
     cudaStream_t capture_stream = nullptr;  // graphs are captured here (the legacy stream cannot capture)
     bool use_graph = false;
 };
@@ -394,29 +411,39 @@ int phase_typed(apl_pncg* w, int phase, int j, cudaStream_t s) {
             pncg_alpha_kernel<<<1, 1, 0, s>>>(w->scal, w->prm);
             break;
         case APL_PHASE_TRIAL: {
-            if (j < 0 || j > J) { set_error("apl_pncg_phase: trial index out of range"); return APL_ERR_INVALID; }
+            // j == -1: trial index taken from the device-side counter (conditional-graph line search)
+            if (j < -1 || j > J) { set_error("apl_pncg_phase: trial index out of range"); return APL_ERR_INVALID; }
+            const int dyn = j < 0 ? 1 : 0, jj = dyn ? 0 : j;
             for (apl_fem* f : w->fems) {
                 int rc = fem_eval_pncg(f, APL_OP_FUN | APL_OP_GRAD | APL_OP_HESS_DIAG, x, nullptr, p, w->scal,
-                                       APL_S_ALPHA_J + j, APL_S_DONE, APL_S_ACC_J + j, w->scal + APL_S_FT_J + j,
-                                       nullptr, gz, dz, w->scatter, s);
+                                       APL_S_ALPHA_J + jj, APL_S_DONE, APL_S_ACC_J + jj, w->scal + APL_S_FT_J + jj,
+                                       nullptr, gz, dz, w->scatter, s, dyn);
                 if (rc != APL_OK) return rc;
             }
             for (const auto& e : w->exts) {
                 int rc = ext_force_pncg(w->dtype, APL_OP_FUN | APL_OP_GRAD, e.k, e.force, e.idx, x, p, w->scal,
-                                        APL_S_ALPHA_J + j, APL_S_DONE, APL_S_ACC_J + j, w->scal + APL_S_FT_J + j, gz, s);
+                                        APL_S_ALPHA_J + jj, APL_S_DONE, APL_S_ACC_J + jj, w->scal + APL_S_FT_J + jj, gz, s,
+                                        dyn);
                 if (rc != APL_OK) return rc;
             }
+            if (dyn) pncg_bump_j_kernel<<<1, 1, 0, s>>>(w->scal);
             break;
         }
         case APL_PHASE_LS: {
-            if (j < 0 || j > J) { set_error("apl_pncg_phase: trial index out of range"); return APL_ERR_INVALID; }
-            const int last = (j == J) ? 1 : 0;
-            pncg_ls_kernel<T><<<last ? 1 : w->grid, last ? 32 : kVecThreads, 0, s>>>(w->rows, j, last, gz, dz, w->scal,
-                                                                                   w->prm);
+            if (j < -1 || j > J) { set_error("apl_pncg_phase: trial index out of range"); return APL_ERR_INVALID; }
+            if (j < 0) {
+                pncg_ls_kernel<T><<<w->grid, kVecThreads, 0, s>>>(w->rows, -1, 0, gz, dz, w->scal, w->prm,
+                                                                   w->cond[w->cur], 1);
+            } else {
+                const int last = (j == J) ? 1 : 0;
+                pncg_ls_kernel<T><<<last ? 1 : w->grid, last ? 32 : kVecThreads, 0, s>>>(w->rows, j, last, gz, dz,
+                                                                                       w->scal, w->prm, 0, 0);
+            }
             break;
         }
         case APL_PHASE_COMMIT:
-            pncg_commit_kernel<T><<<w->grid, kVecThreads, 0, s>>>(w->rows, J + 1, x, p, g, gz, dg, dz, w->scal);
+            pncg_commit_kernel<T><<<w->grid, kVecThreads, 0, s>>>(w->rows, j < 0 ? -1 : J + 1, x, p, g, gz, dg, dz,
+                                                                  w->scal);
             break;
         case APL_PHASE_INIT: {
             // f, g, diag at x into the CURRENT buffers; resets every scalar
@@ -445,6 +472,65 @@ int phase_typed(apl_pncg* w, int phase, int j, cudaStream_t s) {
 
 int run_phase(apl_pncg* w, int phase, int j, cudaStream_t s) {
     return w->dtype == APL_F32 ? phase_typed<float>(w, phase, j, s) : phase_typed<double>(w, phase, j, s);
+}
+
+// One iteration as a CUDA graph whose backtracking is a conditional WHILE node:
+//   head: REDUCE .. ALPHA, TRIAL(0), LS            (LS sets the loop condition: 1 = Armijo failed, retry)
+//   WHILE (condition) { TRIAL(j), LS }              (device-side loop, at most max_halvings times)
+//   tail: COMMIT
+int build_conditional_graph(apl_pncg* w, cudaStream_t cs) {
+    const int c = w->cur;
+    cudaGraph_t g = nullptr;
+    APL_CUDA_CHECK(cudaGraphCreate(&g, 0));
+    auto fail = [&](int rc) { cudaGraphDestroy(g); return rc; };
+    cudaError_t e = cudaGraphConditionalHandleCreate(&w->cond[c], g, 0, cudaGraphCondAssignDefault);
+    if (e != cudaSuccess) { set_error(std::string("cudaGraphConditionalHandleCreate: ") + cudaGetErrorString(e)); return fail(APL_ERR_CUDA); }
+    static const int head[] = {APL_PHASE_REDUCE, APL_PHASE_FINALIZE, APL_PHASE_DIRECTION, APL_PHASE_PASS_B,
+                               APL_PHASE_ALPHA, APL_PHASE_TRIAL, APL_PHASE_LS};
+    e = cudaStreamBeginCaptureToGraph(cs, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { set_error(std::string("cudaStreamBeginCaptureToGraph: ") + cudaGetErrorString(e)); return fail(APL_ERR_CUDA); }
+    int rc = APL_OK;
+    for (int ph : head) {
+        rc = run_phase(w, ph, -1, cs);
+        if (rc != APL_OK) break;
+    }
+    std::vector<cudaGraphNode_t> deps;
+    if (rc == APL_OK) {
+        cudaStreamCaptureStatus st;
+        const cudaGraphNode_t* d = nullptr;
+        size_t nd = 0;
+        e = cudaStreamGetCaptureInfo_v2(cs, &st, nullptr, nullptr, &d, &nd);
+        if (e == cudaSuccess) deps.assign(d, d + nd);
+    }
+    cudaGraph_t tmp = nullptr;
+    cudaError_t e2 = cudaStreamEndCapture(cs, &tmp);
+    if (rc != APL_OK) return fail(rc);
+    if (e != cudaSuccess || e2 != cudaSuccess) { set_error("conditional graph: capturing the head failed"); return fail(APL_ERR_CUDA); }
+    cudaGraphNodeParams prm = {cudaGraphNodeTypeConditional};
+    prm.conditional.handle = w->cond[c];
+    prm.conditional.type = cudaGraphCondTypeWhile;
+    prm.conditional.size = 1;
+    cudaGraphNode_t cond_node = nullptr;
+    e = cudaGraphAddNode(&cond_node, g, deps.data(), deps.size(), &prm);
+    if (e != cudaSuccess) { set_error(std::string("cudaGraphAddNode(conditional): ") + cudaGetErrorString(e)); return fail(APL_ERR_CUDA); }
+    cudaGraph_t body = prm.conditional.phGraph_out[0];
+    e = cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { set_error(std::string("capture of the WHILE body: ") + cudaGetErrorString(e)); return fail(APL_ERR_CUDA); }
+    rc = run_phase(w, APL_PHASE_TRIAL, -1, cs);
+    if (rc == APL_OK) rc = run_phase(w, APL_PHASE_LS, -1, cs);
+    e = cudaStreamEndCapture(cs, &tmp);
+    if (rc != APL_OK) return fail(rc);
+    if (e != cudaSuccess) { set_error(std::string("end capture of the WHILE body: ") + cudaGetErrorString(e)); return fail(APL_ERR_CUDA); }
+    e = cudaStreamBeginCaptureToGraph(cs, g, &cond_node, nullptr, 1, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { set_error(std::string("capture of the tail: ") + cudaGetErrorString(e)); return fail(APL_ERR_CUDA); }
+    rc = run_phase(w, APL_PHASE_COMMIT, -1, cs);
+    e = cudaStreamEndCapture(cs, &tmp);
+    if (rc != APL_OK) return fail(rc);
+    if (e != cudaSuccess) { set_error(std::string("end capture of the tail: ") + cudaGetErrorString(e)); return fail(APL_ERR_CUDA); }
+    e = cudaGraphInstantiate(&w->graph[c], g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { set_error(std::string("cudaGraphInstantiate(conditional): ") + cudaGetErrorString(e)); return APL_ERR_CUDA; }
+    return APL_OK;
 }
 
 int one_iteration(apl_pncg* w, cudaStream_t s) {
@@ -540,6 +626,7 @@ int apl_pncg_set_params(apl_pncg_t* w, double max_steps, double rtol_g, double a
     w->prm.overstep = overstep; w->prm.max_step = max_step; w->prm.c1 = c1; w->prm.max_halvings = max_halvings;
     w->scatter = scatter;
     w->use_graph = use_graph != 0;
+    w->graph_mode = use_graph;
     drop_graphs(w);
     return APL_OK;
 }
@@ -563,11 +650,15 @@ int apl_pncg_iterate(apl_pncg_t* w, int n_iters, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     for (int it = 0; it < n_iters; ++it) {
         if (w->use_graph) {
+            if (!w->capture_stream)
+                APL_CUDA_CHECK(cudaStreamCreateWithFlags(&w->capture_stream, cudaStreamNonBlocking));
+            if (!w->graph[w->cur] && w->graph_mode == 2) {
+                int rc = build_conditional_graph(w, w->capture_stream);
+                if (rc != APL_OK) return rc;
+            }
             if (!w->graph[w->cur]) {
-                // capture one iteration for this buffer parity
+                // capture one iteration (all max_halvings + 1 flag-guarded trials) for this buffer parity
                 cudaGraph_t graph = nullptr;
-                if (!w->capture_stream)
-                    APL_CUDA_CHECK(cudaStreamCreateWithFlags(&w->capture_stream, cudaStreamNonBlocking));
                 APL_CUDA_CHECK(cudaStreamBeginCapture(w->capture_stream, cudaStreamCaptureModeThreadLocal));
                 int rc = one_iteration(w, w->capture_stream);
                 cudaError_t e = cudaStreamEndCapture(w->capture_stream, &graph);

@@ -59,7 +59,7 @@ class LineSearch:
 
 class PNCG(Optimizer):
     def __init__(self, criteria: ConvergenceCriteria | None = None, line_search: LineSearch | None = None, *,
-                 fused: bool = True, check_every: int | None = None, use_graph: bool = True,
+                 fused: bool = True, check_every: int | None = None, use_graph: bool | int = 2,
                  scatter: int | None = None):
         self.criteria = criteria if criteria is not None else ConvergenceCriteria()
         self.line_search = line_search if line_search is not None else LineSearch()
@@ -209,7 +209,7 @@ class _FusedState(_StateBase):
         _lib.check(L.apl_pncg_set_params(
             handle, float(c.max_steps), float(c.target_relative_gradient_norm), float(c.absolute_gradient_norm),
             float(c.max_failed_line_searches), float(ls.overstep), 1.0, float(ls.armijo), int(ls.max_steps),
-            int(scatter), int(bool(opt.use_graph))))
+            int(scatter), int(opt.use_graph) if opt.use_graph in (0, 1, 2) else int(bool(opt.use_graph))))
         with torch.cuda.device(self.device):
             _lib.check(L.apl_pncg_phase(handle, _lib.PHASE_INIT, 0, _lib.stream_ptr(self.device)))
 

@@ -175,6 +175,7 @@ int apl_halo_unpack(int dtype, int64_t n_shared, const int64_t* shared, const in
 #define APL_S_DONE 15        /* 0 running, 1 gradient criterion met, 2 max_steps, 3 stagnation, 4 non-finite */
 #define APL_S_FAILS 16       /* consecutive failed line searches */
 #define APL_S_F_NEW 17
+#define APL_S_J 18           /* trials evaluated so far in the current line search (device-side counter) */
 #define APL_S_SUMS 20        /* 11 reduction results of APL_PHASE_REDUCE */
 #define APL_S_ALPHA_J 32     /* per-trial step lengths      [16] */
 #define APL_S_ACC_J 48       /* per-trial line-search state [16]: 1 accepted, 0 live, -1 gave up */
@@ -199,7 +200,9 @@ int apl_pncg_add_ext_force(apl_pncg_t* ws, int64_t k, const void* force, const i
 /* max_steps: iteration budget (forward/_forward.py:26-27); rtol_g / atol_g: stop when
  * |g| <= rtol_g |g_0| or |g| <= atol_g; max_fails: consecutive failed line searches tolerated;
  * overstep, max_step, c1, max_halvings: line search (bench :606-610, :413-456; _problem.py:29-34);
- * scatter: APL_SCATTER_*; use_graph: replay each iteration as a CUDA graph. */
+ * scatter: APL_SCATTER_*; use_graph: 0 = plain launches, 1 = replay each iteration as a CUDA graph with
+ * all max_halvings + 1 flag-guarded trials, 2 = CUDA graph whose backtracking is a conditional WHILE
+ * node (device-side loop: trials beyond the first cost nothing unless the Armijo test fails). */
 int apl_pncg_set_params(apl_pncg_t* ws, double max_steps, double rtol_g, double atol_g, double max_fails,
                         double overstep, double max_step, double c1, int max_halvings, int scatter,
                         int use_graph);

@@ -147,13 +147,44 @@ def test_generic_and_fused_paths_agree(native_lib):
 
 
 def test_graph_replay_equals_eager_launches(native_lib):
+    """Plain launches, the static CUDA graph and the graph with a conditional WHILE node for the line
+    search run the same recurrences."""
     from apple_b200.forward import Forward
     from apple_b200.optim import PNCG
     from apple_b200.optim.pncg import ConvergenceCriteria
 
     model, _ = _cube_problem(torch.float32, n=6)
     crit = ConvergenceCriteria(max_steps=30, target_relative_gradient_norm=0.0)
-    a = Forward(model, optimizer=PNCG(criteria=crit, use_graph=True, check_every=30)); sa = a.step()
-    b = Forward(model, optimizer=PNCG(criteria=crit, use_graph=False, check_every=7)); sb = b.step()
-    assert sa.stats["n_steps"] == sb.stats["n_steps"] == 30
-    assert rel_err(a.state.u.cpu(), b.state.u.cpu()) < 1e-4
+    runs = {}
+    for mode, every in ((0, 7), (1, 30), (2, 30)):
+        f = Forward(model, optimizer=PNCG(criteria=crit, use_graph=mode, check_every=every))
+        runs[mode] = (f, f.step())
+    for mode in (1, 2):
+        assert runs[mode][1].stats["n_steps"] == runs[0][1].stats["n_steps"] == 30
+        assert runs[mode][1].stats["n_accepted"] == runs[0][1].stats["n_accepted"]
+        assert rel_err(runs[mode][0].state.u.cpu(), runs[0][0].state.u.cpu()) < 1e-4
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2], ids=["eager", "graph", "graph_while"])
+def test_backtracking_line_search_matches_host_driven_pncg(native_lib, mode):
+    """An over-long initial step (overstep 16) makes the Armijo test fail, so trials are halved: the
+    device-side line search (flag-guarded launches or the WHILE node) must take the same decisions as
+    the host-driven generic PNCG."""
+    from apple_b200.forward import Forward
+    from apple_b200.optim import PNCG
+    from apple_b200.optim.pncg import ConvergenceCriteria, LineSearch
+
+    model, _ = _cube_problem(torch.float64, n=5, kinds=("snh", "arap"))
+    crit = ConvergenceCriteria(max_steps=12, target_relative_gradient_norm=0.0)
+    ls = LineSearch(overstep=16.0)
+    a = Forward(model, optimizer=PNCG(criteria=crit, line_search=ls, fused=True, use_graph=mode, check_every=1))
+    b = Forward(model, optimizer=PNCG(criteria=crit, line_search=ls, fused=False))
+    halvings = []
+    problem, state = a.problem, a.state
+    opt_state = a.optimizer.init(problem, state, a.free)
+    for _ in range(12):
+        state, opt_state = a.optimizer.step(problem, state, opt_state)
+        halvings.append(opt_state.line_search_state.step)
+    b.step()
+    assert max(halvings) >= 2                        # the loop really ran
+    assert rel_err(state.u.cpu(), b.state.u.cpu()) < 1e-9
