@@ -167,16 +167,16 @@ def test_graph_replay_equals_eager_launches(native_lib):
 
 @pytest.mark.parametrize("mode", [0, 1, 2], ids=["eager", "graph", "graph_while"])
 def test_backtracking_line_search_matches_host_driven_pncg(native_lib, mode):
-    """An over-long initial step (overstep 16) makes the Armijo test fail, so trials are halved: the
-    device-side line search (flag-guarded launches or the WHILE node) must take the same decisions as
-    the host-driven generic PNCG."""
+    """A strict sufficient-decrease constant (c1 = 0.9) makes the Newton step fail the Armijo test, so
+    trials are halved: the device-side line search (flag-guarded launches or the WHILE node) must take
+    the same decisions as the host-driven generic PNCG."""
     from apple_b200.forward import Forward
     from apple_b200.optim import PNCG
     from apple_b200.optim.pncg import ConvergenceCriteria, LineSearch
 
     model, _ = _cube_problem(torch.float64, n=5, kinds=("snh", "arap"))
     crit = ConvergenceCriteria(max_steps=12, target_relative_gradient_norm=0.0)
-    ls = LineSearch(overstep=16.0)
+    ls = LineSearch(armijo=0.9)
     a = Forward(model, optimizer=PNCG(criteria=crit, line_search=ls, fused=True, use_graph=mode, check_every=1))
     b = Forward(model, optimizer=PNCG(criteria=crit, line_search=ls, fused=False))
     halvings = []
