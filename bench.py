@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--potentials", default="snh,arap")
     ap.add_argument("--pncg-iters", type=int, default=200)
     ap.add_argument("--no-fuse", action="store_true", help="one pass per potential (the reference's structure)")
+    ap.add_argument("--graph", action="store_true", help="N>1, experimental: replay each step as one CUDA graph")
     ap.add_argument("--no-pncg", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
@@ -277,8 +278,27 @@ def main():
         grad = torch.zeros((shard.n_local, 3), dtype=dtype, device=dev)
         prod = torch.zeros((shard.n_local, 3), dtype=dtype, device=dev)
 
+        def eager_step():
+            return sharded.eval(OPS, ud, pd)
+
+        # EXPERIMENTAL, opt-in (--graph): replay the step (kernels + the two NCCL collectives) as one CUDA
+        # graph.  Not validated: the one attempt on 8 GPUs hung during capture, so the default is plain
+        # launches.
+        graph = None
+        if args.graph:
+            for _ in range(3):
+                eager_step()
+            torch.cuda.synchronize()
+            dist.barrier()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                graph_out = eager_step()
+
         def step():
-            sharded.eval(OPS, ud, pd)
+            if graph is not None:
+                graph.replay()
+            else:
+                eager_step()
 
     def barrier():
         if world > 1:
@@ -387,7 +407,8 @@ def main():
                        "l2": "256 MiB flush write between timed steps" if not args.no_flush else "no flush",
                        "parallelism": (f"{world} ranks x contiguous Morton chunk of tets (~{T_total // world} tets per "
                                        f"GPU, {args.scaling} scaling); halo sum of grad+HVP (NCCL all-to-all of "
-                                       f"shared rows) + scalar all-reduce per step")
+                                       f"shared rows) + scalar all-reduce per step, "
+                                       f"{'replayed as one CUDA graph' if args.graph else 'plain launches'}")
                        if world > 1 else "1 GPU"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": args.steps * len(pots),
             "roofline": roofline, "cpu_baseline": cpu, "pncg": pncg,
