@@ -39,6 +39,7 @@ SIGNATURES = {
     "apl_fem_destroy": (None, [c_void_p]),
     "apl_fem_info": (c_int, [c_void_p, POINTER(c_int64)]),
     "apl_fem_host_tables": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "apl_fem_host_planes": (c_int, [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64)]),
     "apl_fem_set_materials": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "apl_fem_eval": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_int, c_int, c_void_p]),

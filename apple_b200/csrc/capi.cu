@@ -69,6 +69,9 @@ static int upload_planes(apl_fem* f, const void* dhdX, const void* dV, const voi
     if (rc != APL_OK) return rc;
     if (f->device >= 0) {
         APL_CUDA_CHECK(cudaMemcpy(f->d_planes, planes.data(), planes.size() * sizeof(T), cudaMemcpyHostToDevice));
+    } else {  // host-only handle: keep the packed planes for inspection (apl_fem_host_planes)
+        const unsigned char* b = reinterpret_cast<const unsigned char*>(planes.data());
+        f->host_planes.assign(b, b + planes.size() * sizeof(T));
     }
     return APL_OK;
 }
@@ -431,6 +434,15 @@ int apl_fem_host_tables(const apl_fem_t* f, int32_t* tiles, int64_t* order, uint
     if (tile_verts) memcpy(tile_verts, h.tile_verts.data(), h.tile_verts.size() * 4);
     if (tile_voff) memcpy(tile_voff, h.tile_voff.data(), h.tile_voff.size() * 2);
     if (tile_vperm) memcpy(tile_vperm, h.tile_vperm.data(), h.tile_vperm.size());
+    return APL_OK;
+}
+
+int apl_fem_host_planes(const apl_fem_t* f, void* planes, int64_t* n_planes, int64_t* plane_stride) {
+    if (!f) { set_error("apl_fem_host_planes: NULL handle"); return APL_ERR_INVALID; }
+    if (f->device >= 0) { set_error("apl_fem_host_planes: only for host-only handles (device = -1)"); return APL_ERR_STATE; }
+    if (n_planes) *n_planes = f->nplanes;
+    if (plane_stride) *plane_stride = f->plane_stride;
+    if (planes) memcpy(planes, f->host_planes.data(), f->host_planes.size());
     return APL_OK;
 }
 

@@ -42,6 +42,7 @@ struct apl_fem {
     int nrec = 0;      // scalars per tet record
     int nplanes = 0;   // 16-byte planes per tet
     apl::HostTables host;
+    std::vector<unsigned char> host_planes;  // packed static planes, kept only by host-only handles
     int64_t plane_stride = 0;  // in 16-byte vectors (n_cells rounded up)
     int64_t static_bytes = 0;
     // device tables

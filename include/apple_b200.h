@@ -104,6 +104,11 @@ int apl_fem_info(const apl_fem_t* fem, int64_t info[10]);
 int apl_fem_host_tables(const apl_fem_t* fem, int32_t* tiles, int64_t* order, uint8_t* conn,
                         uint16_t* slots, int32_t* tile_verts, uint16_t* tile_voff, uint8_t* tile_vperm);
 
+/* Host-only handles (device = -1): copy of the packed static planes, [n_planes][plane_stride] 16-byte
+ * vectors in packed cell order (record = Dm^-1 (9), dV, mu, lambda, activation (6) / second potential);
+ * `planes` may be NULL to query the sizes. */
+int apl_fem_host_planes(const apl_fem_t* fem, void* planes, int64_t* n_planes, int64_t* plane_stride);
+
 /* Replace per-cell materials in place (HOST arrays in the caller's cell order; NULL = keep).
  * Replaces re-creating the Materials struct (warp/fem/utils/_material.py:15-31). */
 int apl_fem_set_materials(apl_fem_t* fem, const void* dV, const void* mu, const void* lambda_,

@@ -26,6 +26,7 @@ static void dispatch(int kind, int n, const void* rec, const void* uc, const voi
 #define CALL(K) run<T, K>(n, (const T*)rec, (const T*)uc, (const T*)pc, (T*)psi, (T*)quad, (T*)g, (T*)dg, (T*)hp)
     if (kind == APL_KIND_SNH) CALL(APL_KIND_SNH);
     else if (kind == APL_KIND_ARAP) CALL(APL_KIND_ARAP);
+    else if (kind == APL_KIND_SNH_ARAP) CALL(APL_KIND_SNH_ARAP);
     else CALL(APL_KIND_SNH_MUSCLE);
 #undef CALL
 }

@@ -200,3 +200,88 @@ def test_svd3_rotation_variant_convention(host_math, dtype, tol):
     assert (np.sign(s64[:, 2]) == np.sign(np.linalg.det(F.astype(float))))[100:].all()
     ref = np.linalg.svd(F.astype(float), compute_uv=False)
     assert np.abs(np.abs(s64) - ref).max() < 20 * tol
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("kind", ["snh", "arap", "muscle", "snh+arap"])
+def test_static_planes_hold_the_reference_arrays(native_lib, kind, dtype):
+    """The packed planes the kernels stream are exactly the reference's region / material arrays:
+    rows 1..3 of dhdX, Fraction * dV, mu, lambda, activation -- in packed (tile) order."""
+    from apple_b200 import _lib
+    from oracle import region
+
+    mesh, _, _ = make_case(n=5, seed=3)
+    T, V = mesh.n_cells, mesh.n_points
+    dhdX, dV = region.compute_grad(mesh.points, mesh.cells, mesh.cell_data["Fraction"], dtype=dtype)
+    mu = mesh.cell_data["mu"].astype(dtype); la = mesh.cell_data["lambda"].astype(dtype)
+    act = mesh.cell_data["activation"].astype(dtype)
+    dV2 = (0.5 * dV).astype(dtype); mu2 = (2.0 * mu).astype(dtype)
+    P = _lib.host_ptr
+    h = ctypes.c_void_p()
+    code = _lib.F32 if dtype == np.float32 else _lib.F64
+    cells = np.ascontiguousarray(mesh.cells, dtype=np.int32); pts = np.ascontiguousarray(mesh.points)
+    if kind == "snh+arap":
+        rc = native_lib.apl_fem_create_snh_arap(code, T, V, P(cells), P(dhdX), P(dV), P(mu), P(la), P(dV2), P(mu2), P(pts),
+                                                -1, ctypes.byref(h))
+    else:
+        k = {"snh": 0, "arap": 1, "muscle": 2}[kind]
+        rc = native_lib.apl_fem_create(k, code, T, V, P(cells), P(dhdX), P(dV), P(mu), P(la), P(act), P(pts), -1,
+                                       ctypes.byref(h))
+    assert rc == 0, native_lib.apl_last_error()
+    npl, stride = ctypes.c_int64(), ctypes.c_int64()
+    native_lib.apl_fem_host_planes(h, None, ctypes.byref(npl), ctypes.byref(stride))
+    vec = 16 // np.dtype(dtype).itemsize
+    planes = np.zeros((npl.value, stride.value, vec), dtype)
+    native_lib.apl_fem_host_planes(h, P(planes), None, None)
+    order = np.zeros(T, np.int64)
+    native_lib.apl_fem_host_tables(h, None, P(order), None, None, None, None, None)
+    native_lib.apl_fem_destroy(h)
+    rec = planes.transpose(1, 0, 2).reshape(stride.value, npl.value * vec)[:T]      # (T, padded record)
+    np.testing.assert_array_equal(rec[:, :9], dhdX[order][:, 1:4].reshape(T, 9))
+    np.testing.assert_array_equal(rec[:, 9], dV[order])
+    np.testing.assert_array_equal(rec[:, 10], mu[order])
+    if kind != "arap":
+        np.testing.assert_array_equal(rec[:, 11], la[order])
+    if kind == "muscle":
+        np.testing.assert_array_equal(rec[:, 12:18], act[order])
+    if kind == "snh+arap":
+        np.testing.assert_array_equal(rec[:, 12], dV2[order])
+        np.testing.assert_array_equal(rec[:, 13], mu2[order])
+    assert npl.value == -(-{"snh": 12, "arap": 12, "muscle": 18, "snh+arap": 14}[kind] // vec)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-11), (np.float32, 3e-5)], ids=["f64", "f32"])
+def test_fused_record_equals_sum_of_two_potentials(host_math, dtype, tol):
+    """KIND SNH_ARAP (two potentials of one cell in one evaluation) == SNH + ARAP of the oracle, with
+    per-potential volumes/materials and per-potential clamps."""
+    from oracle import fem as ofem
+
+    mesh, u, p = make_case(n=4, seed=8, amp=0.6)   # large deformation: some clamps are active
+    m2 = mesh.copy()
+    m2.cell_data["Fraction"] = 1.0 - 0.5 * mesh.cell_data["Fraction"]
+    m2.cell_data["mu"] = mesh.cell_data["mu"][::-1].copy()
+    a, b = oracle_potential("snh", mesh), oracle_potential("arap", m2)
+    T = mesh.n_cells
+    rec = np.zeros((T, 14), dtype)
+    rec[:, :9] = a.dhdX[:, 1:4].reshape(T, 9)
+    rec[:, 9], rec[:, 10], rec[:, 11] = a.dV, a.materials["mu"], a.materials["lambda_"]
+    rec[:, 12], rec[:, 13] = b.dV, b.materials["mu"]
+    uc = np.ascontiguousarray(u[mesh.cells], dtype); pc = np.ascontiguousarray(p[mesh.cells], dtype)
+    psi = np.zeros(T, dtype); quad = np.zeros(T, dtype)
+    g, dg, hp = (np.zeros((T, 4, 3), dtype) for _ in range(3))
+    P = lambda x: x.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    host_math.elem_eval_host(3, int(dtype == np.float64), T, P(rec), P(uc), P(pc), P(psi), P(quad), P(g), P(dg), P(hp))
+
+    def rel(x, y):
+        x = x.reshape(T, -1).astype(np.float64); y = y.reshape(T, -1)
+        return (np.abs(x - y).max(1) / np.abs(y).max(1)).max()
+
+    assert rel(g, a.elem_grad(u) + b.elem_grad(u)) < tol
+    assert rel(dg, a.elem_hess_diag(u) + b.elem_hess_diag(u)) < tol
+    assert rel(hp, a.elem_hess_prod(u, p) + b.elem_hess_prod(u, p)) < tol
+    q = a.elem_hess_quad(u, p) + b.elem_hess_quad(u, p)
+    e = a.elem_fun(u) + b.elem_fun(u)
+    assert np.abs(quad - q).max() < 10 * tol * np.abs(q).max()
+    assert np.abs(psi - e).max() < 10 * tol * np.abs(e).max()
+    qa = a.elem_hess_quad(u, p); a.clamp_hess_quad = False
+    assert (a.elem_hess_quad(u, p) < 0).any() and (qa >= 0).all()    # the per-potential clamp is exercised
