@@ -34,18 +34,20 @@ class HaloExchange:
         send_index = np.concatenate([nb[s] for s in range(self.world) if s in nb]) if self.total else np.zeros(0, np.int64)
         shared = np.unique(send_index)
         # CSR over shared vertices: contributions in ascending rank order, -1 marks this rank's own partial
-        entries = [[] for _ in range(shared.size)]
-        pos = {int(v): i for i, v in enumerate(shared)}
+        verts = [shared]
+        ranks = [np.full(shared.size, self.rank, np.int64)]
+        srcs = [np.full(shared.size, -1, np.int64)]
         for s in range(self.world):
-            if s == self.rank:
-                for i in range(shared.size):
-                    entries[i].append(-1)
-            elif s in nb:
-                for k, v in enumerate(nb[s]):
-                    entries[pos[int(v)]].append(offs[s] + k)
+            if s != self.rank and s in nb:
+                verts.append(nb[s])
+                ranks.append(np.full(nb[s].size, s, np.int64))
+                srcs.append(offs[s] + np.arange(nb[s].size, dtype=np.int64))
+        verts, ranks, srcs = np.concatenate(verts), np.concatenate(ranks), np.concatenate(srcs)
+        order = np.lexsort((ranks, verts))              # by vertex, then by rank
+        src = srcs[order]
+        counts = np.bincount(np.searchsorted(shared, verts), minlength=shared.size)
         row_ptr = np.zeros(shared.size + 1, np.int32)
-        row_ptr[1:] = np.cumsum([len(e) for e in entries])
-        src = np.array([j for e in entries for j in e], dtype=np.int64)
+        row_ptr[1:] = np.cumsum(counts)
         t = lambda a, dt: torch.as_tensor(a, dtype=dt, device=self.device)  # noqa: E731
         self.send_index = t(send_index, torch.int64)
         self.shared = t(shared, torch.int64)
@@ -84,20 +86,26 @@ class HaloExchange:
                                              _lib.dev_ptr(self.row_ptr), _lib.dev_ptr(self.src), nf, f[0], f[1], f[2], ld,
                                              _lib.dev_ptr(recv), st))
             return
-        # CPU tensors (gloo tests of the sharding logic): same arithmetic with torch index ops
+        # CPU tensors (gloo tests of the sharding logic): the same pack / CSR-ordered unpack as the kernels,
+        # written with torch index ops
         for k, x in enumerate(fields):
             send[:, 3 * k:3 * k + 3] = x[:, :3].index_select(0, self.send_index)
         dist.all_to_all_single(recv, send, output_split_sizes=self.counts, input_split_sizes=self.counts,
                                group=self.group)
+        n_shared = self.shared.numel()
+        counts = (self.row_ptr[1:] - self.row_ptr[:-1]).to(torch.int64)
+        entry_row = torch.repeat_interleave(torch.arange(n_shared), counts)
+        pos = torch.arange(self.src.numel()) - self.row_ptr[:-1].to(torch.int64)[entry_row]
+        own_entry = self.src < 0
         for k, x in enumerate(fields):
-            own = x[:, :3].index_select(0, self.shared)
-            acc = torch.zeros_like(x[:, :3])
-            for s in range(self.world):  # ascending rank order on every rank
-                if s == self.rank:
-                    acc.index_add_(0, self.shared, own)
-                elif self.counts[s]:
-                    acc.index_add_(0, self.idx[s], recv[self.offs[s]:self.offs[s + 1], 3 * k:3 * k + 3])
-            x[:, :3].index_copy_(0, self.shared, acc.index_select(0, self.shared))
+            contrib = torch.empty((self.src.numel(), 3), dtype=dtype)
+            contrib[own_entry] = x[:, :3].index_select(0, self.shared[entry_row[own_entry]])
+            contrib[~own_entry] = recv[self.src[~own_entry], 3 * k:3 * k + 3]
+            acc = torch.zeros((n_shared, 3), dtype=dtype)
+            for j in range(int(counts.max()) if n_shared else 0):   # entry j of every row: ascending rank order
+                sel = pos == j
+                acc.index_add_(0, entry_row[sel], contrib[sel])
+            x[:, :3].index_copy_(0, self.shared, acc)
 
     def all_reduce_(self, t: torch.Tensor) -> None:
         if self.world > 1:

@@ -54,17 +54,21 @@ class Region:
         return self.mesh.cell_data
 
     def compute_grad(self) -> None:
+        """Closed form of ``Region.compute_grad`` for the linear tetrahedron: ``dXdr`` has the edge vectors
+        ``X_a - X_0`` as columns, ``drdX`` is its inverse written with cross products, ``dV = det / 6`` and
+        ``dhdX = dhdr . drdX`` (rows 1..3 are the rows of the inverse, row 0 minus their sum)."""
         X = self.points[self.cells_global]  # (c, a, I)
-        dXdr = np.einsum("caI,aJ->cIJ", X, _DHDR)
-        det = np.linalg.det(dXdr)
+        e1, e2, e3 = X[:, 1] - X[:, 0], X[:, 2] - X[:, 0], X[:, 3] - X[:, 0]
+        c23, c31, c12 = np.cross(e2, e3), np.cross(e3, e1), np.cross(e1, e2)
+        det = np.einsum("ci,ci->c", e1, c23)
         if np.any(det == 0.0):
             raise ValueError("degenerate tetrahedron (zero rest volume)")
-        drdX = np.linalg.inv(dXdr)
+        inv = np.stack([c23, c31, c12], axis=1) / det[:, None, None]  # rows of (dXdr)^-1
         dV = det * _WEIGHT
         if np.any(dV <= 0):
             logger.warning("dV <= 0")
-        dhdX = np.einsum("aI,cIJ->caJ", _DHDR, drdX)
-        self.dXdr = dXdr[:, None]
-        self.drdX = drdX[:, None]
+        dhdX = np.concatenate([-inv.sum(axis=1, keepdims=True), inv], axis=1)
+        self.dXdr = np.stack([e1, e2, e3], axis=2)[:, None]
+        self.drdX = inv[:, None]
         self.dV = dV[:, None]
         self.dhdX = dhdX[:, None]

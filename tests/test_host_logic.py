@@ -90,3 +90,18 @@ def test_termination_classes():
     assert _classify(2.0, 1e-1, c) is Result.MAX_STEPS_REACHED
     assert _classify(3.0, 1e-1, c) is Result.STAGNATION
     assert _classify(4.0, 1e-9, c) is Result.NAN_ENCOUNTERED
+
+
+def test_region_matches_oracle_restatement():
+    """apple_b200.fem.Region (closed form) == the oracle's literal restatement of Region.compute_grad
+    (jax/fem/region/_region.py:84-108), including the reference's (cells, quadrature, ...) shapes."""
+    from apple_b200.fem import Region
+    from oracle import region as oregion
+
+    mesh = cube_tet_mesh(5, grading=1.07)
+    r = Region.from_pyvista(mesh, grad=True)
+    dhdX, dV = oregion.compute_grad(mesh.points, mesh.cells)
+    assert r.dhdX.shape == (mesh.n_cells, 1, 4, 3) and r.dV.shape == (mesh.n_cells, 1)
+    np.testing.assert_allclose(r.dhdX[:, 0], dhdX, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(r.dV[:, 0], dV, rtol=1e-13)
+    np.testing.assert_allclose(np.einsum("cqij,cqjk->cqik", r.dXdr, r.drdX), np.broadcast_to(np.eye(3), (mesh.n_cells, 1, 3, 3)), atol=1e-12)
