@@ -4,7 +4,8 @@
 ``forward/_problem.py:18-59``."""
 
 from ._base import Optimizer, Problem, Result, Solution
+from ._pcg import PcgInfo, adjoint_solve, pcg
 from ._pncg import PNCG
 from . import pncg
 
-__all__ = ["PNCG", "Optimizer", "Problem", "Result", "Solution", "pncg"]
+__all__ = ["PNCG", "Optimizer", "PcgInfo", "Problem", "Result", "Solution", "adjoint_solve", "pcg", "pncg"]

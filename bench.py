@@ -90,23 +90,61 @@ def algorithmic_bytes_per_tet(kind, w, v_over_t, per_vertex_words):
 
 
 class ClockSampler:
+    """Samples SM clock and clock-event (throttle) reasons while the benchmark runs: NVML every 2 ms when
+    `pynvml` works, else the profiling recipe's `nvidia-smi --query-gpu` line back to back.  `summary`
+    reports the median over the samples that fall inside the timed windows."""
+
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, index=0):
-        self.samples, self._stop, self.index = [], threading.Event(), index
+        self.samples, self._stop, self.index = [], threading.Event(), index  # (t, sm_mhz, max_mhz, [reasons])
+        self.windows = []
+        self.backend = "nvidia-smi"
+        self._nvml = None
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            int(get_reasons(h))
+            self._nvml = (pynvml, h, mx, get_reasons)
+            self.backend = "nvml"
+        except Exception:
+            self._nvml = None
         self._thread = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
         while not self._stop.is_set():
+            t = time.perf_counter()
             try:
+                if self._nvml is not None:
+                    pynvml, h, mx, get_reasons = self._nvml
+                    sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                    mask = int(get_reasons(h))
+                    self.samples.append((t, sm, mx, [n for n, bit in self.REASONS if mask & bit]))
+                    self._stop.wait(0.002)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.samples.append([x.strip() for x in out.strip().split(",")])
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 9:
+                    names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+                    self.samples.append((t, float(f[1]), float(f[2]),
+                                         [n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
             except Exception:
-                pass
-            self._stop.wait(0.1)
+                self._stop.wait(0.05)
 
     def __enter__(self):
         self._thread.start()
@@ -116,20 +154,16 @@ class ClockSampler:
         self._stop.set()
         self._thread.join(timeout=6)
 
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
+
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        for s in self.samples:
-            if len(s) < 9:
-                continue
-            try:
-                sm.append(float(s[1])); mx = max(mx, float(s[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        inside = [s for s in self.samples if any(a <= s[0] <= b for a, b in self.windows)]
+        use = inside or self.samples
+        reasons = sorted({r for s in use for r in s[3]})
+        return {"sm_mhz": float(np.median([s[1] for s in use])) if use else None,
+                "sm_max_mhz": max((s[2] for s in use), default=None), "reasons": reasons,
+                "samples": len(use), "samples_in_timed_region": len(inside), "source": self.backend}
 
 
 def measured_peak_gbs():
@@ -305,16 +339,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks / throttle reasons are sampled from before the warm-up until after the last timed GPU phase
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()
     for _ in range(args.warmup):
         flush(); step()
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local_rank) as clocks:
-        barrier()
-        for a, b in ev:
-            flush()
-            a.record(); step(); b.record()
-        barrier()
+    barrier()
+    t_w0 = time.perf_counter()
+    for a, b in ev:
+        flush()
+        a.record(); step(); b.record()
+    barrier()
+    clocks.window(t_w0, time.perf_counter())
     t_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([t_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -384,6 +422,8 @@ def main():
     pncg = None
     if world == 1 and not args.no_pncg:
         pncg = bench_pncg(args, mesh, pots, dtype, dev, w)
+
+    clocks.__exit__(None, None, None)
 
     # ---- CPU baseline: the oracle on a bounded sample ----
     cpu = None

@@ -285,3 +285,33 @@ def test_fused_record_equals_sum_of_two_potentials(host_math, dtype, tol):
     assert np.abs(psi - e).max() < 10 * tol * np.abs(e).max()
     qa = a.elem_hess_quad(u, p); a.clamp_hess_quad = False
     assert (a.elem_hess_quad(u, p) < 0).any() and (qa >= 0).all()    # the per-potential clamp is exercised
+
+
+def test_tile_tables_assemble_the_oracle_gradient(native_lib):
+    """Emulates, in numpy, exactly how the element kernels interpret the tables (gather through conn /
+    tile_verts, one slot per corner, per-vertex slot ranges from tile_voff in tile_vperm order with the
+    bit-15 padding flag, flush to tile_verts) and checks that the assembled field is the oracle's."""
+    mesh, u, _ = make_case(n=6, seed=5, morton=False)
+    ora = oracle_potential("snh", mesh)
+    tiles, order, conn, slots, tv, voff, vperm = _host_tables(native_lib, mesh)
+    elem = ora.elem_grad(u)[order]                      # per-corner contributions in packed order
+    uq = u[mesh.cells[order]]                           # what a gather through the global ids must return
+    out = np.zeros_like(u)
+    for (ts, n, vs, nv, vo, nslots) in tiles:
+        verts = tv[vs:vs + nv]
+        c = conn[ts:ts + n].astype(int)
+        assert np.array_equal(u[verts][c], uq[ts:ts + n])          # phase 2: shared-memory gather
+        buf = np.full((nslots, 3), np.nan)
+        buf[slots[ts:ts + n].astype(int).ravel()] = elem[ts:ts + n].reshape(-1, 3)   # phase 3: slot stores
+        raw = voff[vo:vo + nv + 1].astype(int)
+        start, padded = raw & 0x7fff, raw[:-1] >> 15
+        assert start[-1] == nslots
+        acc = np.zeros((nv, 3))
+        for t in range(nv):                                        # phase 4: reduce in tile_vperm order
+            cnt = start[t + 1] - start[t] - padded[t]
+            rows = buf[start[t]:start[t] + cnt]
+            assert not np.isnan(rows).any()                        # only real slots are read
+            acc[vperm[vs + t]] = rows.sum(axis=0)
+        np.add.at(out, verts, acc)                                 # phase 5: one RED per tile vertex
+    ref = np.zeros_like(u); ora.grad(u, ref)
+    np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
