@@ -449,15 +449,22 @@ int apl_fem_host_planes(const apl_fem_t* f, void* planes, int64_t* n_planes, int
 int apl_fem_set_materials(apl_fem_t* f, const void* dV, const void* mu, const void* lambda_,
                           const void* activation) {
     if (!f) { set_error("apl_fem_set_materials: NULL handle"); return APL_ERR_INVALID; }
-    if (f->device < 0) { set_error("apl_fem_set_materials: host-only handle"); return APL_ERR_STATE; }
     if (f->kind == APL_KIND_SNH_ARAP) { set_error("apl_fem_set_materials: not supported for fused potentials"); return APL_ERR_STATE; }
-    // Read back, patch the requested columns, upload.  Setup-time path, not hot.
+    // Read back (device handles) or take the kept copy (host-only handles), patch the requested columns,
+    // upload / keep.  Setup-time path, not hot.
     const int vec = f->dtype == APL_F32 ? 4 : 2;
     const size_t esz = f->dtype == APL_F32 ? 4 : 8;
     const size_t bytes = (size_t)f->nplanes * f->plane_stride * 16;
-    std::vector<unsigned char> buf(bytes);
-    APL_CUDA_CHECK(cudaSetDevice(f->device));
-    APL_CUDA_CHECK(cudaMemcpy(buf.data(), f->d_planes, bytes, cudaMemcpyDeviceToHost));
+    std::vector<unsigned char> tmp;
+    std::vector<unsigned char>& buf = f->device >= 0 ? tmp : f->host_planes;
+    if (f->device >= 0) {
+        tmp.resize(bytes);
+        APL_CUDA_CHECK(cudaSetDevice(f->device));
+        APL_CUDA_CHECK(cudaMemcpy(buf.data(), f->d_planes, bytes, cudaMemcpyDeviceToHost));
+    } else if (buf.size() != bytes) {
+        set_error("apl_fem_set_materials: host-only handle without packed planes");
+        return APL_ERR_STATE;
+    }
     auto put = [&](int k, int64_t pos, const void* src, int64_t idx) {
         const int plane = k / vec, lane = k % vec;
         memcpy(buf.data() + (((size_t)plane * f->plane_stride + pos) * vec + lane) * esz,
@@ -471,7 +478,7 @@ int apl_fem_set_materials(apl_fem_t* f, const void* dV, const void* mu, const vo
         if (activation && f->kind == APL_KIND_SNH_MUSCLE)
             for (int k = 0; k < 6; ++k) put(12 + k, pos, activation, 6 * c + k);
     }
-    APL_CUDA_CHECK(cudaMemcpy(f->d_planes, buf.data(), bytes, cudaMemcpyHostToDevice));
+    if (f->device >= 0) APL_CUDA_CHECK(cudaMemcpy(f->d_planes, buf.data(), bytes, cudaMemcpyHostToDevice));
     return APL_OK;
 }
 

@@ -315,3 +315,40 @@ def test_tile_tables_assemble_the_oracle_gradient(native_lib):
         np.add.at(out, verts, acc)                                 # phase 5: one RED per tile vertex
     ref = np.zeros_like(u); ora.grad(u, ref)
     np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+
+
+def test_set_materials_patches_only_the_requested_columns(native_lib):
+    """apl_fem_set_materials (replaces re-creating the Materials struct, warp/fem/utils/_material.py:15-31):
+    on a host-only handle the patched planes equal those of a handle created with the new arrays."""
+    from apple_b200 import _lib
+    from oracle import region
+
+    mesh, _, _ = make_case(n=4, seed=12)
+    T, V = mesh.n_cells, mesh.n_points
+    dhdX, dV = region.compute_grad(mesh.points, mesh.cells, mesh.cell_data["Fraction"])
+    mu, la, act = mesh.cell_data["mu"], mesh.cell_data["lambda"], mesh.cell_data["activation"]
+    rng = np.random.default_rng(0)
+    act2, mu2 = 0.2 * rng.standard_normal((T, 6)), mu * 3.0
+    P = _lib.host_ptr
+    cells = np.ascontiguousarray(mesh.cells, dtype=np.int32); pts = np.ascontiguousarray(mesh.points)
+
+    def create(mu_, act_):
+        h = ctypes.c_void_p()
+        assert native_lib.apl_fem_create(2, _lib.F64, T, V, P(cells), P(dhdX), P(dV), P(np.ascontiguousarray(mu_)), P(la),
+                                         P(np.ascontiguousarray(act_)), P(pts), -1, ctypes.byref(h)) == 0
+        return h
+
+    def planes(h):
+        npl, stride = ctypes.c_int64(), ctypes.c_int64()
+        native_lib.apl_fem_host_planes(h, None, ctypes.byref(npl), ctypes.byref(stride))
+        out = np.zeros((npl.value, stride.value, 2))
+        native_lib.apl_fem_host_planes(h, P(out), None, None)
+        return out
+
+    a, b = create(mu, act), create(mu2, act2)
+    before = planes(a)
+    assert native_lib.apl_fem_set_materials(a, None, P(np.ascontiguousarray(mu2)), None, P(np.ascontiguousarray(act2))) == 0
+    after = planes(a)
+    np.testing.assert_array_equal(after, planes(b))
+    assert not np.array_equal(before, after)
+    native_lib.apl_fem_destroy(a); native_lib.apl_fem_destroy(b)
