@@ -326,7 +326,7 @@ static int fem_create_impl(int kind, int dtype, int64_t n_cells, int64_t n_point
     f->nrec = rec_size(kind);
     const int vec = dtype == APL_F32 ? 4 : 2;
     f->nplanes = (f->nrec + vec - 1) / vec;
-    int rc = build_tiles(n_cells, n_points, cells, points, f->host);
+    int rc = build_tiles(n_cells, n_points, cells, points, dtype == APL_F32 ? 4 : 8, f->host);
     if (rc != APL_OK) { delete f; return rc; }
     f->plane_stride = (n_cells + 31) / 32 * 32;
     if (f->plane_stride == 0) f->plane_stride = 32;

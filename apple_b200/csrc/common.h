@@ -25,14 +25,16 @@ struct HostTables {
     std::vector<int64_t> order;        // packed position -> caller's cell index
     std::vector<uint8_t> conn;         // (n_cells,4)
     std::vector<uint16_t> slots;       // (n_cells,4)
-    std::vector<int32_t> tile_verts;   // global vertex ids per tile, ascending (tile start padded to x16)
-    std::vector<uint8_t> tile_vperm;   // same indexing: local ids by decreasing valence
+    std::vector<int32_t> tile_verts;   // global vertex id of every tile-local id (tile start padded to x16)
+    std::vector<uint8_t> tile_vperm;   // same indexing: local ids in reduce order (about decreasing valence)
     std::vector<uint16_t> tile_voff;   // per tile n_verts+1 slot offsets, starting at voff_start (x8)
     int64_t n_tiles() const { return (int64_t)tiles.size() / 6; }
 };
 
-// cells: (n_cells,4) int32.  points: (n_points,3) double or nullptr.  Returns APL_OK or error code.
-int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const double* points,
+// cells: (n_cells,4) int32.  points: (n_points,3) double or nullptr.  elem_bytes: 4 (fp32) or 8 (fp64), the
+// scalar size of the nodal rows the kernels keep in shared memory (decides which local ids collide).
+// Returns APL_OK or error code.
+int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const double* points, int elem_bytes,
                 HostTables& out);
 
 }  // namespace apl

@@ -389,11 +389,12 @@ __device__ __forceinline__ void tile_reduce(int tid, int n_verts, const unsigned
         int v = 0, s0 = 0, cnt = 0;
         if (t < n_verts) {
             v = vperm[t];
-            // voff is in reduce order; ranges are padded to odd lengths (bit 15 flags a padded range),
-            // so neighbouring pairs read slots an odd distance apart: conflict-free 16/8-byte loads.
+            // voff is in reduce order: bits 0..11 = first slot of the range, bits 12..15 = unused pad slots
+            // after it (tiling.cpp chooses order and pads so that the 16 lanes of a group start in
+            // distinct bank groups: conflict-free 16/8-byte loads).
             const unsigned a0 = voff[t], a1 = voff[t + 1];
-            s0 = (int)(a0 & 0x7fffu);
-            cnt = (int)(a1 & 0x7fffu) - s0 - (int)(a0 >> 15);
+            s0 = (int)(a0 & 0x0fffu);
+            cnt = (int)(a1 & 0x0fffu) - s0 - (int)(a0 >> 12);
         }
         T acc[3 * NOUT];
 #pragma unroll

@@ -1,16 +1,35 @@
 // Host-side mesh packing: Morton ordering of the tets and greedy tiling.
 //
-// A tile is a run of <= 256 consecutive tets (in packed order) that together touch <= 256 distinct
+// A tile is a run of <= 256 consecutive tets (in packed order) that together touch <= 192 distinct
 // vertices.  For every tile we store
-//   * the ascending list of the global vertex ids it touches           (tile_verts)
-//   * the same local ids ordered by decreasing valence                 (tile_vperm)
-//   * per tet, the tile-local id of each corner as one byte          (conn)
-//   * per tet corner, a slot in [0, 4*n_tets): slots are grouped by local vertex, so the element
-//     kernel can write every corner contribution to its own shared-memory slot (no atomics) and a
-//     second phase sums each vertex's contiguous slot range                     (slots, tile_voff)
+//   * the global ids of the vertices it touches, indexed by tile-local id   (tile_verts)
+//   * the local ids in REDUCE order (about decreasing valence)             (tile_vperm)
+//   * per tet, the tile-local id of each corner as one byte                (conn)
+//   * per tet corner, a slot: slots are grouped by local vertex, so the element kernel can write
+//     every corner contribution to its own shared-memory slot (no atomics) and a second phase sums
+//     each vertex's contiguous slot range                                     (slots, tile_voff)
 // This replaces the reference's per-tet global connectivity (`cells`, warp/fem/_base.py:59-74) and
 // its 12 global atomics per tet per field (warp/fem/_base.py:288-289).
+//
+// Everything that is free in this encoding is chosen to keep the kernels' warp-wide shared-memory
+// accesses free of bank conflicts (a warp-wide 16-byte access is served per quarter warp, an 8-byte
+// access per half warp; lanes that touch different addresses in the same bank group serialise):
+//   * LOCAL VERTEX IDS.  The corner gather of 8 consecutive tets reads row `16 B * local id`: the
+//     ids are a balanced colouring (id mod 8; mod 4 for 32-byte fp64 rows) of the graph "vertices
+//     gathered by the same quarter warp for the same corner", so that those rows fall into distinct
+//     bank groups.  Within a colour class ids ascend with the global id, which keeps the tile's
+//     vertex list almost ascending (neighbouring lanes gather / RED neighbouring rows).
+//   * REDUCE ORDER AND PADDING.  16 consecutive vertices of the reduce order are summed by one warp,
+//     lane j reading slot start[j] + i: within every group of 16 the order and the optional one-slot
+//     pads are searched so that the starts are distinct mod 16 (8-byte plane) and, within each half
+//     of the group, distinct mod 8 (16-byte planes).
+//   * SLOT POSITIONS inside a vertex's range: greedy + local search so that the 8 (16) stores of a
+//     quarter (half) warp for one corner hit distinct slots mod 8 (mod 16).
+// tools/smem_model.py replays the kernels' access pattern on these tables and counts wavefronts.
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <thread>
 #include <cstring>
 #include <numeric>
 
@@ -62,10 +81,361 @@ static void morton_order(int64_t n_cells, int64_t n_points, const int32_t* cells
     for (int64_t c = 0; c < n_cells; ++c) order[(size_t)c] = keyed[(size_t)c].second;
 }
 
-int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const double* points,
+namespace {
+
+// Deterministic per-tile random numbers for the local searches (the tables must not depend on the
+// machine or the run).
+struct Lcg {
+    uint32_t s;
+    explicit Lcg(uint32_t seed) : s(seed * 2654435761u + 12345u) {}
+    uint32_t next() {
+        s = s * 1664525u + 1013904223u;
+        return s >> 8;
+    }
+    int below(int n) { return (int)(next() % (uint32_t)n); }
+};
+
+constexpr int kGroupsQ = (kTileTets / 8) * 4;    // (quarter warp, corner) groups of a tile
+constexpr int kGroupsH = (kTileTets / 16) * 4;   // (half warp, corner) groups
+constexpr int kSlotCap = 4 * kTileTets + kTileVerts;
+static_assert(kSlotCap < 4096, "tile_voff keeps the slot offset in 12 bits");
+
+// Occupancy of the bank groups by one warp-wide access: c[r] lanes (distinct addresses) fall into bank
+// group r, the access takes m = max c[r] wavefronts, nmax bank groups are that full.
+struct Banks {
+    uint8_t c[16];
+    uint8_t m, nmax;
+    void clear() { memset(this, 0, sizeof(*this)); }
+    void rescan(int R) {
+        m = 0; nmax = 0;
+        for (int r = 0; r < R; ++r) {
+            if (c[r] > m) { m = c[r]; nmax = 1; }
+            else if (c[r] == m) ++nmax;
+        }
+    }
+    // change of m when one lane moves from bank group r1 to r2
+    int delta(int r1, int r2) const {
+        if (r1 == r2) return 0;
+        if (c[r2] + 1 > m) return 1;
+        if (c[r1] == m && nmax == 1 && c[r2] + 1 < m) return -1;
+        return 0;
+    }
+    void apply(int r1, int r2, int R) {
+        --c[r1]; ++c[r2];
+        rescan(R);
+    }
+};
+
+// Scratch of one tile (allocated once per build_tiles call).
+struct TileScratch {
+    // global id -> provisional local id
+    static constexpr int kHash = 512;
+    static_assert(kHash >= 2 * kTileVerts, "hash table too small");
+    int32_t hkey[kHash];
+    uint8_t hval[kHash];
+    // colouring
+    uint8_t gmem[kGroupsQ][8];
+    uint8_t gsz[kGroupsQ];
+    Banks gb[kGroupsQ];
+    int vptr[kTileVerts + 2];
+    int vgrp[4 * kTileTets];
+    int mark[kGroupsQ];
+    // slots
+    Banks bq[kGroupsQ], bh[kGroupsH];
+    int16_t owner[kSlotCap];
+    int16_t slot_of[4 * kTileTets];
+};
+
+// ---- 1. local vertex ids: balanced colouring of the gather-conflict graph -----------------------
+// tl[t][a]: provisional local id (first-touch order) of corner a of the tile's t-th tet.  Vertices read
+// by the same quarter warp for the same corner should differ in (id mod M).  new_id[provisional] is a
+// bijection onto [0, nv) with id = M * k + colour and k ascending with the global id inside a colour.
+void color_local_ids(TileScratch& ws, int nt, int nv, const uint8_t (*tl)[4], const int32_t* gid, int M,
+                     uint32_t seed, int* new_id) {
+    const int nq = (nt + 7) / 8, ng = nq * 4;
+    auto& gmem = ws.gmem;
+    auto& gsz = ws.gsz;
+    auto& gb = ws.gb;
+    int* vptr = ws.vptr;
+    int* vgrp = ws.vgrp;
+    int col[kTileVerts];
+    for (int v = 0; v <= nv + 1; ++v) vptr[v] = 0;
+    for (int q = 0; q < nq; ++q)
+        for (int a = 0; a < 4; ++a) {
+            const int g = 4 * q + a;
+            gb[g].clear();
+            ws.mark[g] = -1;
+            int n = 0;
+            for (int t = 8 * q; t < std::min(8 * q + 8, nt); ++t) {
+                const uint8_t v = tl[t][a];
+                bool seen = false;
+                for (int k = 0; k < n; ++k) seen |= (gmem[g][k] == v);
+                if (!seen) gmem[g][n++] = v;
+            }
+            gsz[g] = (uint8_t)n;
+            for (int k = 0; k < n; ++k) ++vptr[gmem[g][k] + 2];
+        }
+    for (int v = 0; v < nv; ++v) vptr[v + 2] += vptr[v + 1];
+    for (int g = 0; g < ng; ++g)
+        for (int k = 0; k < gsz[g]; ++k) vgrp[vptr[gmem[g][k] + 1]++] = g;
+    // the groups of v are now vgrp[vptr[v] .. vptr[v+1])
+    int cap[8], used[8];
+    for (int c = 0; c < M; ++c) {
+        cap[c] = c < nv ? (nv - c + M - 1) / M : 0;
+        used[c] = 0;
+    }
+    int order[kTileVerts];
+    for (int v = 0; v < nv; ++v) order[v] = v;
+    std::stable_sort(order, order + nv,
+                     [&](int a, int b) { return vptr[a + 1] - vptr[a] > vptr[b + 1] - vptr[b]; });
+    for (int i = 0; i < nv; ++i) {
+        const int v = order[i];
+        int best = -1, best_inc = 1 << 30, best_sec = 1 << 30, best_fill = 1 << 30;
+        for (int c = 0; c < M; ++c) {
+            if (used[c] >= cap[c]) continue;
+            int inc = 0, sec = 0;
+            for (int e = vptr[v]; e < vptr[v + 1]; ++e) {
+                const Banks& b = gb[vgrp[e]];
+                inc += (b.c[c] + 1 > b.m) && b.m >= 1;   // one more wavefront for this group
+                sec += b.c[c];
+            }
+            const int fill = used[c] - cap[c];
+            if (inc < best_inc || (inc == best_inc && (sec < best_sec || (sec == best_sec && fill < best_fill)))) {
+                best = c; best_inc = inc; best_sec = sec; best_fill = fill;
+            }
+        }
+        col[v] = best;
+        ++used[best];
+        for (int e = vptr[v]; e < vptr[v + 1]; ++e) {
+            Banks& b = gb[vgrp[e]];
+            ++b.c[best];
+            b.rescan(M);
+        }
+    }
+    // local search: swap the colours of two vertices (class sizes are preserved) when the number of
+    // wavefronts does not grow
+    Lcg rng(seed);
+    int stamp = 0;
+    auto try_swap = [&](int v, int w) {
+        const int a = col[v], b = col[w];
+        ++stamp;
+        for (int e = vptr[w]; e < vptr[w + 1]; ++e) ws.mark[vgrp[e]] = stamp;
+        int d = 0;
+        for (int e = vptr[v]; e < vptr[v + 1]; ++e) {
+            const int g = vgrp[e];
+            if (ws.mark[g] == stamp) ws.mark[g] = -stamp - 1;   // contains both: unchanged
+            else d += gb[g].delta(a, b);
+        }
+        for (int e = vptr[w]; e < vptr[w + 1]; ++e) {
+            const int g = vgrp[e];
+            if (ws.mark[g] == stamp) d += gb[g].delta(b, a);
+        }
+        if (d > 0) return false;
+        for (int e = vptr[w]; e < vptr[w + 1]; ++e) {
+            const int g = vgrp[e];
+            if (ws.mark[g] == stamp) gb[g].apply(b, a, M);
+        }
+        for (int e = vptr[v]; e < vptr[v + 1]; ++e) {
+            const int g = vgrp[e];
+            if (ws.mark[g] != -stamp - 1) gb[g].apply(a, b, M);
+        }
+        col[v] = b; col[w] = a;
+        return true;
+    };
+    for (int pass = 0; pass < 1; ++pass) {
+        int nbad = 0;
+        for (int g = 0; g < ng; ++g) {
+            if (gb[g].m <= 1) continue;
+            ++nbad;
+            for (int i = 0; i < gsz[g] && gb[g].m > 1; ++i) {
+                const int v = gmem[g][i];
+                if (gb[g].c[col[v]] < gb[g].m) continue;
+                for (int tries = 0; tries < 16; ++tries) {
+                    const int w = rng.below(nv);
+                    if (col[w] != col[v] && try_swap(v, w)) break;
+                }
+            }
+        }
+        if (nbad == 0) break;
+    }
+    // ids: colour classes interleaved, ascending global id inside a class
+    for (int c = 0; c < M; ++c) {
+        int members[kTileVerts], n = 0;
+        for (int v = 0; v < nv; ++v)
+            if (col[v] == c) members[n++] = v;
+        std::sort(members, members + n, [&](int a, int b) { return gid[a] < gid[b]; });
+        for (int k = 0; k < n; ++k) new_id[members[k]] = M * k + c;
+    }
+}
+
+// ---- 2. reduce order: conflict-free slot-range starts within every group of 16 vertices ------------
+// cnt[0..n): valences of the group's vertices (about descending).  Finds an order and per-vertex pads
+// (0..kMaxPad unused slots after the range, at most pad_budget in total) such that the n range starts are
+// distinct mod 16 (8-byte plane; skipped when !mod16) and distinct mod 8 within positions 0..7 and 8..15
+// (16-byte planes).  Returns false when the bounded search fails.
+constexpr int kMaxPad = 3;
+struct GroupSearch {
+    int n, budget, pad_budget, target;
+    bool mod16;
+    int cnt[16];
+    bool taken[16];
+    int order[16], pad[16];
+    bool dfs(int j, int s, unsigned used16, unsigned used8, int pads_left) {
+        if (j == n) return true;
+        if (--budget < 0) return false;
+        if (j == 8) used8 = 0;
+        if (mod16 && (used16 >> (s & 15) & 1u)) return false;
+        if (used8 >> (s & 7) & 1u) return false;
+        used16 |= 1u << (s & 15);
+        used8 |= 1u << (s & 7);
+        int last = -1;
+        for (int i = 0; i < n; ++i) {
+            if (taken[i] || cnt[i] == last) continue;   // equal valences are interchangeable
+            last = cnt[i];
+            taken[i] = true;
+            order[j] = i;
+            // a constant odd stride never collides: first the pad that reaches the group's target stride
+            const int want = std::min(std::max(target - cnt[i], 0), kMaxPad);
+            for (int k = -1; k <= kMaxPad; ++k) {
+                const int pd = k < 0 ? want : k;
+                if ((k >= 0 && pd == want) || pd > pads_left) continue;
+                pad[j] = pd;
+                if (dfs(j + 1, s + cnt[i] + pd, used16, used8, pads_left - pd)) return true;
+                if (budget < 0) break;
+            }
+            taken[i] = false;
+            if (budget < 0) return false;
+        }
+        return false;
+    }
+};
+
+// ---- 3. slot positions -------------------------------------------------------------------------------
+// Bank group of a slot in a 16-byte plane = slot mod 8 per quarter warp; mod 16 per half warp for the
+// 8-byte tail plane of fp32 slots.  Greedy, then local search over swaps of two slots of the same vertex
+// (all slots of a vertex are equivalent for the reduction; pad slots are never used).
+void place_slots(TileScratch& ws, int nt, const uint8_t (*tl)[4], const int* cnt, const int* off, int n_slots,
+                 bool f64, uint32_t seed) {
+    auto& bq = ws.bq;
+    auto& bh = ws.bh;
+    int16_t* owner = ws.owner;
+    int16_t* slot_of = ws.slot_of;
+    const int nq = ((nt + 7) / 8) * 4, nh = ((nt + 15) / 16) * 4;
+    const bool half = !f64;
+    for (int g = 0; g < nq; ++g) bq[g].clear();
+    for (int g = 0; g < nh; ++g) bh[g].clear();
+    for (int s = 0; s < n_slots; ++s) owner[s] = -1;
+    // most constrained first: corners of low-valence vertices have the fewest slots to choose from
+    int16_t corder[4 * kTileTets];
+    {
+        int bucket[4 * kTileTets + 2];
+        const int nb = 4 * nt + 2;
+        for (int i = 0; i < nb; ++i) bucket[i] = 0;
+        for (int x = 0; x < 4 * nt; ++x) ++bucket[cnt[tl[x >> 2][x & 3]] + 1];
+        for (int i = 1; i < nb; ++i) bucket[i] += bucket[i - 1];
+        for (int x = 0; x < 4 * nt; ++x) corder[bucket[cnt[tl[x >> 2][x & 3]]]++] = (int16_t)x;
+    }
+    for (int i = 0; i < 4 * nt; ++i) {
+        const int x = corder[i], t = x >> 2, a = x & 3;
+        const int l = tl[t][a];
+        Banks& q = bq[(t >> 3) * 4 + a];
+        Banks& h = bh[(t >> 4) * 4 + a];
+        int best = -1, best_cost = 1 << 30;
+        for (int k = 0; k < cnt[l]; ++k) {
+            const int s = off[l] + k;
+            if (owner[s] >= 0) continue;
+            const int cost = 4 * q.c[s & 7] + (half ? h.c[s & 15] : 0);
+            if (cost < best_cost) {
+                best_cost = cost;
+                best = s;
+                if (cost == 0) break;
+            }
+        }
+        owner[best] = (int16_t)x;
+        slot_of[x] = (int16_t)best;
+        ++q.c[best & 7];
+        ++h.c[best & 15];
+    }
+    for (int g = 0; g < nq; ++g) bq[g].rescan(8);
+    for (int g = 0; g < nh; ++g) bh[g].rescan(16);
+    auto gq_of = [](int x) { return ((x >> 2) >> 3) * 4 + (x & 3); };
+    auto gh_of = [](int x) { return ((x >> 2) >> 4) * 4 + (x & 3); };
+    // wavefront change when corner x moves s -> s2 and the owner y of s2 (if any) moves s2 -> s
+    auto swap_delta = [&](int x, int y, int s, int s2) {
+        int d = 0;
+        const int qx = gq_of(x), hx = gh_of(x);
+        if (y < 0) {
+            d += bq[qx].delta(s & 7, s2 & 7);
+            if (half) d += bh[hx].delta(s & 15, s2 & 15);
+            return d;
+        }
+        const int qy = gq_of(y), hy = gh_of(y);
+        if (qx != qy) d += bq[qx].delta(s & 7, s2 & 7) + bq[qy].delta(s2 & 7, s & 7);
+        if (half && hx != hy) d += bh[hx].delta(s & 15, s2 & 15) + bh[hy].delta(s2 & 15, s & 15);
+        return d;
+    };
+    auto do_swap = [&](int x, int y, int s, int s2) {
+        bq[gq_of(x)].apply(s & 7, s2 & 7, 8);
+        bh[gh_of(x)].apply(s & 15, s2 & 15, 16);
+        if (y >= 0) {
+            bq[gq_of(y)].apply(s2 & 7, s & 7, 8);
+            bh[gh_of(y)].apply(s2 & 15, s & 15, 16);
+            slot_of[y] = (int16_t)s;
+        }
+        owner[s2] = (int16_t)x;
+        owner[s] = (int16_t)y;
+        slot_of[x] = (int16_t)s2;
+    };
+    Lcg rng(seed ^ 0x9e3779b9u);
+    auto improve = [&](int x) {
+        const int l = tl[x >> 2][x & 3];
+        const int len = cnt[l];
+        if (len < 2) return;
+        const int s = slot_of[x];
+        int best_s2 = -1, best_delta = 1;
+        const int r0 = rng.below(len);
+        for (int k = 0; k < len; ++k) {
+            const int s2 = off[l] + (r0 + k) % len;
+            if (s2 == s) continue;
+            const int d = swap_delta(x, owner[s2], s, s2);
+            if (d < best_delta) {
+                best_delta = d;
+                best_s2 = s2;
+                if (d < 0) break;
+            }
+        }
+        if (best_s2 >= 0) do_swap(x, owner[best_s2], s, best_s2);
+    };
+    for (int pass = 0; pass < 2; ++pass) {
+        int nbad = 0;
+        for (int g = 0; g < nq; ++g) {
+            if (bq[g].m <= 1) continue;
+            ++nbad;
+            const int a = g & 3, t0 = (g >> 2) * 8, t1 = std::min(t0 + 8, nt);
+            for (int t = t0; t < t1; ++t)
+                if (bq[g].m > 1 && bq[g].c[slot_of[4 * t + a] & 7] == bq[g].m) improve(4 * t + a);
+        }
+        for (int g = 0; g < nh && half; ++g) {
+            if (bh[g].m <= 1) continue;
+            ++nbad;
+            const int a = g & 3, t0 = (g >> 2) * 16, t1 = std::min(t0 + 16, nt);
+            for (int t = t0; t < t1; ++t)
+                if (bh[g].m > 1 && bh[g].c[slot_of[4 * t + a] & 15] == bh[g].m) improve(4 * t + a);
+        }
+        if (nbad == 0) break;
+    }
+}
+
+}  // namespace
+
+int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const double* points, int elem_bytes,
                 HostTables& out) {
     if (n_cells < 0 || n_points <= 0 || (!cells && n_cells > 0)) {
         set_error("build_tiles: bad sizes");
+        return APL_ERR_INVALID;
+    }
+    if (n_cells > (int64_t)INT32_MAX) {
+        set_error("n_cells exceeds int32 range");
         return APL_ERR_INVALID;
     }
     for (int64_t i = 0; i < 4 * n_cells; ++i)
@@ -74,6 +444,8 @@ int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const d
                       " outside [0, n_points)");
             return APL_ERR_MESH;
         }
+    const bool f64 = elem_bytes == 8;
+    const int gather_mod = f64 ? 4 : 8;   // nodal rows in shared memory are 4 scalars: 16 B (fp32) / 32 B (fp64)
     out = HostTables();
     out.n_cells = n_cells;
     out.n_points = n_points;
@@ -82,143 +454,181 @@ int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const d
     else std::iota(out.order.begin(), out.order.end(), (int64_t)0);
     out.conn.resize((size_t)n_cells * 4);
     out.slots.resize((size_t)n_cells * 4);
-    out.tiles.reserve((size_t)(n_cells / kTileTets + 1) * 6);
-    out.tile_verts.reserve((size_t)(n_cells / 2 + 16));
 
-    std::vector<int32_t> stamp((size_t)n_points, -1);  // tile that last touched the vertex
-    std::vector<int32_t> lid((size_t)n_points, 0);     // its local id in that tile
-    std::vector<int32_t> verts;                        // distinct vertices of the open tile (first-touch order)
-    verts.reserve(kTileVerts);
-    int32_t cnt[kTileVerts];
-    int32_t off[kTileVerts + 1];
-    int32_t perm[kTileVerts];
-    int64_t tile_start = 0;
-    int32_t tile_id = 0;
-
-    // Closes the tile [tile_start, tile_end).  Local vertex ids ascend with the global id (coalesced
-    // gathers and REDs); tile_vperm lists the local ids by DECREASING valence so that the per-vertex
-    // slot reduction of the kernel has nearly uniform trip counts within a warp.  The vertex list
-    // starts at a multiple of 16 entries and the offset list at a multiple of 8 entries, i.e. every
-    // per-tile table is 16-byte aligned for bulk copies.
-    auto close_tile = [&](int64_t tile_end) {
-        const int nt = (int)(tile_end - tile_start);
-        if (nt == 0) return;
-        const int nv = (int)verts.size();
-        for (int l = 0; l < nv; ++l) {
-            lid[(size_t)verts[l]] = l;
-            cnt[l] = 0;
-            perm[l] = l;
-        }
-        for (int64_t pos = tile_start; pos < tile_end; ++pos) {
-            const int32_t* c = cells + 4 * out.order[(size_t)pos];
-            for (int a = 0; a < 4; ++a) ++cnt[lid[(size_t)c[a]]];
-        }
-        std::sort(perm, perm + nv, [&](int a, int b) { return verts[a] < verts[b]; });
-        while (out.tile_verts.size() % 16) {
-            out.tile_verts.push_back(0);
-            out.tile_vperm.push_back(0);
-        }
-        while (out.tile_voff.size() % 8) out.tile_voff.push_back(0);
-        const int32_t vert_start = (int32_t)out.tile_verts.size();
-        const int32_t voff_start = (int32_t)out.tile_voff.size();
-        int32_t cnt_new[kTileVerts];
-        for (int l = 0; l < nv; ++l) {
-            const int old = perm[l];
-            lid[(size_t)verts[old]] = l;
-            out.tile_verts.push_back(verts[old]);
-            cnt_new[l] = cnt[old];
-        }
-        // reduce order: local ids by decreasing valence
-        for (int l = 0; l < nv; ++l) perm[l] = l;
-        std::stable_sort(perm, perm + nv, [&](int a, int b) { return cnt_new[a] > cnt_new[b]; });
-        for (int l = 0; l < nv; ++l) out.tile_vperm.push_back((uint8_t)perm[l]);
-        // Slot ranges are laid out in REDUCE order and padded to odd lengths: reduce thread t reads
-        // start[t] + i, so neighbouring lanes are an odd number of slots apart and their 16-byte
-        // (and 8-byte) reads fall into distinct banks.  Bit 15 of an entry flags a padded range.
-        int32_t start[kTileVerts + 1];
-        start[0] = 0;
-        for (int t = 0; t < nv; ++t) {
-            const int c = cnt_new[perm[t]];
-            const int padded = c | 1;
-            start[t + 1] = start[t] + padded;
-            off[perm[t]] = start[t];
-            out.tile_voff.push_back((uint16_t)(start[t] | ((padded != c) ? 0x8000 : 0)));
-        }
-        out.tile_voff.push_back((uint16_t)start[nv]);
-        out.tiles.push_back((int32_t)tile_start);
-        out.tiles.push_back(nt);
-        out.tiles.push_back(vert_start);
-        out.tiles.push_back(nv);
-        out.tiles.push_back(voff_start);
-        out.tiles.push_back(start[nv]);
-        // Positions inside a vertex's range are free: choose them so that the 32 stores of one
-        // warp-wide STS (same corner of 32 consecutive tets) spread over the banks.  Bank of a slot
-        // in a 16-byte plane = slot mod 8 per quarter warp; mod 16 per half warp for the 8-byte plane.
-        uint8_t taken[4 * kTileTets + kTileVerts];
-        memset(taken, 0, sizeof(taken));
-        for (int64_t w0 = tile_start; w0 < tile_end; w0 += 32) {
-            const int64_t w1 = std::min(w0 + 32, tile_end);
-            for (int a = 0; a < 4; ++a) {
-                int used_h[2][16], used_q[4][8];
-                memset(used_h, 0, sizeof(used_h));
-                memset(used_q, 0, sizeof(used_q));
-                for (int64_t pos = w0; pos < w1; ++pos) {
-                    const int32_t* c = cells + 4 * out.order[(size_t)pos];
-                    const int l = lid[(size_t)c[a]];
-                    const int half = (int)((pos - w0) >> 4), quarter = (int)((pos - w0) >> 3);
-                    const int base = off[l], n = cnt_new[l];
-                    int best = -1, best_cost = 1 << 30;
-                    for (int k = 0; k < n; ++k) {
-                        if (taken[base + k]) continue;
-                        const int cost = 4 * used_q[quarter][(base + k) & 7] + used_h[half][(base + k) & 15];
-                        if (cost < best_cost) {
-                            best_cost = cost;
-                            best = base + k;
-                            if (cost == 0) break;
-                        }
-                    }
-                    taken[best] = 1;
-                    ++used_h[half][best & 15];
-                    ++used_q[quarter][best & 7];
-                    out.conn[(size_t)pos * 4 + a] = (uint8_t)l;
-                    out.slots[(size_t)pos * 4 + a] = (uint16_t)best;
-                }
-            }
-        }
-        verts.clear();
-        tile_start = tile_end;
-        ++tile_id;
+    // ---- pass 1 (serial): tile boundaries, the distinct vertices of every tile in first-touch order, and
+    //      where each tile's tables start (vertex lists at multiples of 16 entries, offset lists at multiples
+    //      of 8 entries: every per-tile table is 16-byte aligned for bulk copies)
+    struct TileRange {
+        int64_t tet_start;
+        int32_t nt, nv;
+        int64_t first_touch;   // into `touched`
+        int64_t vert_start, voff_start;
     };
-
-    if (n_cells > (int64_t)INT32_MAX) {
-        set_error("n_cells exceeds int32 range");
-        return APL_ERR_INVALID;
-    }
-    for (int64_t pos = 0; pos < n_cells; ++pos) {
-        const int32_t* c = cells + 4 * out.order[(size_t)pos];
-        // A tile closes when it is full.  Vertex budget: tiles must start at multiples of 4 tets
-        // (16-byte aligned byte-wide connectivity), so the budget is checked every 4 tets with room
-        // for the worst case of 16 new vertices in the next 4.
-        const int64_t in_tile = pos - tile_start;
-        if (in_tile == kTileTets || (in_tile % 4 == 0 && in_tile > 0 && (int)verts.size() + 16 > kTileVerts)) {
-            close_tile(pos);
+    std::vector<TileRange> ranges;
+    ranges.reserve((size_t)(n_cells / kTileTets + 1));
+    std::vector<int32_t> touched;   // concatenated first-touch vertex lists
+    touched.reserve((size_t)(n_cells / 2 + 16));
+    {
+        std::vector<int32_t> stamp((size_t)n_points, -1);  // tile that last touched the vertex
+        int64_t tile_start = 0, first = 0, vert_end = 0, voff_end = 0;
+        int32_t tile_id = 0;
+        auto close_tile = [&](int64_t tile_end) {
+            const int nt = (int)(tile_end - tile_start);
+            if (nt == 0) return;
+            const int nv = (int)((int64_t)touched.size() - first);
+            vert_end = (vert_end + 15) / 16 * 16;
+            voff_end = (voff_end + 7) / 8 * 8;
+            ranges.push_back({tile_start, nt, nv, first, vert_end, voff_end});
+            vert_end += nv;
+            voff_end += nv + 1;
+            first = (int64_t)touched.size();
+            tile_start = tile_end;
+            ++tile_id;
+        };
+        for (int64_t pos = 0; pos < n_cells; ++pos) {
+            const int32_t* c = cells + 4 * out.order[(size_t)pos];
+            // A tile closes when it is full.  Vertex budget: tiles must start at multiples of 4 tets
+            // (16-byte aligned byte-wide connectivity), so the budget is checked every 4 tets with room
+            // for the worst case of 16 new vertices in the next 4.
+            const int64_t in_tile = pos - tile_start;
+            const int nv_open = (int)((int64_t)touched.size() - first);
+            if (in_tile == kTileTets || (in_tile % 4 == 0 && in_tile > 0 && nv_open + 16 > kTileVerts)) close_tile(pos);
+            for (int a = 0; a < 4; ++a)
+                if (stamp[(size_t)c[a]] != tile_id) {
+                    stamp[(size_t)c[a]] = tile_id;
+                    touched.push_back(c[a]);
+                }
         }
-        for (int a = 0; a < 4; ++a)
-            if (stamp[(size_t)c[a]] != tile_id) {
-                stamp[(size_t)c[a]] = tile_id;
-                verts.push_back(c[a]);
+        close_tile(n_cells);
+        // + padding so that 16-byte granular bulk copies of the last tile stay in bounds
+        if (vert_end + 16 > (int64_t)INT32_MAX || voff_end + 16 > (int64_t)INT32_MAX) {
+            set_error("tile vertex table exceeds int32 range");
+            return APL_ERR_INVALID;
+        }
+        out.tile_verts.assign((size_t)vert_end + 16, 0);
+        out.tile_vperm.assign((size_t)vert_end + 16, 0);
+        out.tile_voff.assign((size_t)voff_end + 16, 0);
+    }
+    const int64_t n_tiles = (int64_t)ranges.size();
+    out.tiles.assign((size_t)n_tiles * 6, 0);
+
+    // ---- pass 2 (parallel over tiles): local ids, reduce order, slots
+    auto pack_tile = [&](TileScratch& ws, int64_t tile) {
+        const TileRange& r = ranges[(size_t)tile];
+        const int nt = r.nt, nv = r.nv;
+        const int32_t* verts = touched.data() + r.first_touch;
+        // provisional (first-touch) local ids of every corner
+        uint8_t tl[kTileTets][4];
+        for (int i = 0; i < TileScratch::kHash; ++i) ws.hkey[i] = -1;
+        auto hslot = [](int32_t v) { return (int)(((uint32_t)v * 2654435761u) >> 23) & (TileScratch::kHash - 1); };
+        for (int l = 0; l < nv; ++l) {
+            int h = hslot(verts[l]);
+            while (ws.hkey[h] >= 0) h = (h + 1) & (TileScratch::kHash - 1);
+            ws.hkey[h] = verts[l];
+            ws.hval[h] = (uint8_t)l;
+        }
+        for (int t = 0; t < nt; ++t) {
+            const int32_t* c = cells + 4 * out.order[(size_t)(r.tet_start + t)];
+            for (int a = 0; a < 4; ++a) {
+                int h = hslot(c[a]);
+                while (ws.hkey[h] != c[a]) h = (h + 1) & (TileScratch::kHash - 1);
+                tl[t][a] = ws.hval[h];
             }
-    }
-    close_tile(n_cells);
-    // pad the tables so that 16-byte granular bulk copies of the last tile stay in bounds
-    for (int k = 0; k < 16; ++k) {
-        out.tile_verts.push_back(0);
-        out.tile_vperm.push_back(0);
-    }
-    for (int k = 0; k < 16; ++k) out.tile_voff.push_back(0);
-    if (out.tile_verts.size() > (size_t)INT32_MAX || out.tile_voff.size() > (size_t)INT32_MAX) {
-        set_error("tile vertex table exceeds int32 range");
-        return APL_ERR_INVALID;
+        }
+        // 1. final local ids
+        int new_id[kTileVerts];
+        color_local_ids(ws, nt, nv, tl, verts, gather_mod, (uint32_t)tile, new_id);
+        int cnt[kTileVerts];
+        for (int l = 0; l < nv; ++l) {
+            out.tile_verts[(size_t)r.vert_start + new_id[l]] = verts[l];
+            cnt[l] = 0;
+        }
+        for (int t = 0; t < nt; ++t)
+            for (int a = 0; a < 4; ++a) {
+                tl[t][a] = (uint8_t)new_id[tl[t][a]];
+                ++cnt[tl[t][a]];
+            }
+        // 2. reduce order: decreasing valence (balanced trip counts within a warp), then per group of 16
+        //    the order / pads that make the range starts conflict-free
+        int perm[kTileVerts];
+        for (int l = 0; l < nv; ++l) perm[l] = l;
+        std::stable_sort(perm, perm + nv, [&](int a, int b) { return cnt[a] > cnt[b]; });
+        int start[kTileVerts + 1], padv[kTileVerts], off[kTileVerts];
+        start[0] = 0;
+        int pads_left = kSlotCap - 4 * nt;   // >= nv: one pad per vertex is always affordable
+        for (int g0 = 0; g0 < nv; g0 += 16) {
+            GroupSearch gs;
+            gs.n = std::min(16, nv - g0);
+            const int allowed = pads_left - (nv - g0 - gs.n);   // keep one pad for every later vertex
+            int grp[16];
+            for (int i = 0; i < gs.n; ++i) {
+                grp[i] = perm[g0 + i];
+                gs.cnt[i] = cnt[grp[i]];
+            }
+            gs.target = gs.cnt[0] | 1;
+            bool found = false;
+            for (int attempt = 0; attempt < 2 && !found; ++attempt) {   // all planes, then the 16-byte planes only
+                if (attempt == 1 && f64) break;
+                gs.mod16 = !f64 && attempt == 0;
+                gs.budget = 1500;
+                gs.pad_budget = allowed;
+                for (int i = 0; i < gs.n; ++i) gs.taken[i] = false;
+                found = gs.dfs(0, start[g0], 0u, 0u, allowed);
+            }
+            if (found) {
+                for (int j = 0; j < gs.n; ++j) {
+                    perm[g0 + j] = grp[gs.order[j]];
+                    padv[g0 + j] = gs.pad[j];
+                }
+            } else {
+                for (int j = 0; j < gs.n; ++j) padv[g0 + j] = (cnt[grp[j]] & 1) ? 0 : 1;   // odd strides
+            }
+            for (int j = 0; j < gs.n; ++j) {
+                start[g0 + j + 1] = start[g0 + j] + cnt[perm[g0 + j]] + padv[g0 + j];
+                pads_left -= padv[g0 + j];
+            }
+        }
+        for (int t = 0; t < nv; ++t) {
+            off[perm[t]] = start[t];
+            out.tile_vperm[(size_t)r.vert_start + t] = (uint8_t)perm[t];
+            out.tile_voff[(size_t)r.voff_start + t] = (uint16_t)(start[t] | (padv[t] << 12));
+        }
+        out.tile_voff[(size_t)r.voff_start + nv] = (uint16_t)start[nv];
+        int32_t* hdr = out.tiles.data() + 6 * tile;
+        hdr[0] = (int32_t)r.tet_start;
+        hdr[1] = nt;
+        hdr[2] = (int32_t)r.vert_start;
+        hdr[3] = nv;
+        hdr[4] = (int32_t)r.voff_start;
+        hdr[5] = start[nv];
+        // 3. slot positions
+        place_slots(ws, nt, tl, cnt, off, start[nv], f64, (uint32_t)tile);
+        for (int t = 0; t < nt; ++t)
+            for (int a = 0; a < 4; ++a) {
+                out.conn[(size_t)(r.tet_start + t) * 4 + a] = tl[t][a];
+                out.slots[(size_t)(r.tet_start + t) * 4 + a] = (uint16_t)ws.slot_of[4 * t + a];
+            }
+    };
+    int n_threads = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("APL_TILING_THREADS")) n_threads = atoi(e);
+    n_threads = std::max(1, std::min(n_threads, 32));
+    if (n_tiles < 64) n_threads = 1;
+    if (n_threads == 1) {
+        std::vector<TileScratch> ws(1);
+        for (int64_t t = 0; t < n_tiles; ++t) pack_tile(ws[0], t);
+    } else {
+        std::atomic<int64_t> next{0};
+        std::vector<std::thread> pool;
+        for (int i = 0; i < n_threads; ++i)
+            pool.emplace_back([&] {
+                std::vector<TileScratch> ws(1);
+                for (;;) {
+                    const int64_t t0 = next.fetch_add(16);
+                    if (t0 >= n_tiles) break;
+                    for (int64_t t = t0; t < std::min(t0 + 16, n_tiles); ++t) pack_tile(ws[0], t);
+                }
+            });
+        for (auto& th : pool) th.join();
     }
     return APL_OK;
 }

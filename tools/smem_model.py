@@ -1,0 +1,133 @@
+"""Shared-memory wavefront model of fem_pipe_kernel (fp32, grad+prod slots: NOUT=2, SS=6).
+
+Reads the packed tables of a host-only handle (no GPU) and counts, for every warp-wide LDS/STS of the
+consumer warps, the number of wavefronts = max over the 32 banks of distinct 4-byte words touched
+(identical words are broadcast).  Prints wavefronts per 32 tets, split by access class, so that the
+table layout (tiling.cpp) can be tuned offline and compared with ncu's
+l1tex__data_pipe_lsu_wavefronts_mem_shared_op_{ld,st}.sum.
+
+usage: python tools/smem_model.py [--n 58] [--tiles 400] [--quarter]
+"""
+import argparse, ctypes, sys
+from pathlib import Path
+import numpy as np
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+
+KSLOTS = 4 * 256 + 192
+
+def wavefronts(addr, nbytes, active=None, quarter=False):
+    """addr: (..., 32) byte addresses per lane; nbytes in {1,2,4,8,16}.  Returns (...) wavefront counts."""
+    addr = np.asarray(addr, dtype=np.int64)
+    if active is None:
+        active = np.ones(addr.shape, bool)
+    nw = max(nbytes // 4, 1)
+    words = (addr // 4)[..., None] + np.arange(nw)           # (..., 32, nw)
+    act = np.broadcast_to(active[..., None], words.shape)
+    def count(words, act):
+        lead = words.shape[:-2]
+        w = words.reshape(*lead, -1); a = act.reshape(*lead, -1)
+        w = np.where(a, w, -1)
+        w = np.sort(w, axis=-1)
+        first = np.ones(w.shape, bool); first[..., 1:] = w[..., 1:] != w[..., :-1]
+        first &= w >= 0
+        bank = np.where(first, w % 32, 32)
+        out = np.zeros(lead, np.int64)
+        for b in range(32):
+            out = np.maximum(out, (bank == b).sum(-1))
+        return out
+    if not quarter or nbytes < 8:
+        return count(words, act)
+    g = 32 // (nbytes // 4)     # lanes per group: 8 for 16 B, 16 for 8 B
+    tot = 0
+    for k in range(32 // g):
+        tot = tot + count(words[..., k * g:(k + 1) * g, :], act[..., k * g:(k + 1) * g, :])
+    return tot
+
+def host_tables(n):
+    from apple_b200 import _lib, build
+    from bench import build_mesh
+    from oracle import region
+    build.build(); L = _lib.lib()
+    mesh, _, _ = build_mesh(n)
+    dhdX, dV = region.compute_grad(mesh.points, mesh.cells)
+    T, V = mesh.n_cells, mesh.n_points
+    one = np.ones(T); P = _lib.host_ptr; h = ctypes.c_void_p()
+    cells = np.ascontiguousarray(mesh.cells, dtype=np.int32); pts = np.ascontiguousarray(mesh.points)
+    rc = L.apl_fem_create(0, _lib.F32, T, V, P(cells), P(dhdX.astype(np.float32)), P(dV.astype(np.float32)),
+                          P(one.astype(np.float32)), P(one.astype(np.float32)), None, P(pts), -1, ctypes.byref(h))
+    assert rc == 0, L.apl_last_error()
+    info = (ctypes.c_int64 * 10)(); L.apl_fem_info(h, info)
+    nt, nv, nvo = info[2], info[3], info[8]
+    tiles = np.zeros((nt, 6), np.int32); order = np.zeros(T, np.int64)
+    conn = np.zeros((T, 4), np.uint8); slots = np.zeros((T, 4), np.uint16)
+    tv = np.zeros(nv, np.int32); voff = np.zeros(nvo, np.uint16); vperm = np.zeros(nv, np.uint8)
+    L.apl_fem_host_tables(h, P(tiles), P(order), P(conn), P(slots), P(tv), P(voff), P(vperm))
+    L.apl_fem_destroy(h)
+    return tiles, conn, slots, tv, voff, vperm
+
+def model(tiles, conn, slots, voff, vperm, quarter=False, max_tiles=None):
+    acc = dict(static=0, gather=0, slot_st=0, red_small=0, red_ld=0, vbuf_st=0, flush_ld=0)
+    ideal = dict(acc)
+    ntets = 0
+    sel = tiles if max_tiles is None else tiles[np.linspace(0, len(tiles) - 1, max_tiles).astype(int)]
+    for (ts, n, vs, nv, vo, nslots) in sel:
+        ntets += n
+        nw = (n + 31) // 32
+        lane_t = np.arange(nw * 32).reshape(nw, 32)
+        act = lane_t < n
+        c = np.zeros((nw * 32, 4), np.int64); c[:n] = conn[ts:ts + n]
+        s = np.zeros((nw * 32, 4), np.int64); s[:n] = slots[ts:ts + n]
+        c = c.reshape(nw, 32, 4); s = s.reshape(nw, 32, 4)
+        acc["static"] += nw * (1 + 1 + 12 + 2); ideal["static"] += nw * 16
+        for k in range(4):
+            g = wavefronts(c[:, :, k] * 16, 16, act, quarter).sum()
+            acc["gather"] += 2 * g; ideal["gather"] += 2 * 4 * nw
+            acc["slot_st"] += wavefronts(s[:, :, k] * 16, 16, act, quarter).sum() + wavefronts(s[:, :, k] * 8, 8, act, quarter).sum()
+            ideal["slot_st"] += 6 * nw
+        # reduce: warp w, lanes j (half 0) and j+16 (half 1) share vertex t = 16 w + j (+128)
+        raw = voff[vo:vo + nv + 1].astype(np.int64)
+        start = raw & 0x0fff; padded = raw[:-1] >> 12
+        cnt = np.diff(start) - padded
+        perm = vperm[vs:vs + nv].astype(np.int64)
+        for base in (0, 128):
+            for w in range(8):
+                t = base + 16 * w + np.arange(16)
+                if t[0] >= ((nv + 15) & ~15): continue
+                ok = t < nv
+                tt = np.where(ok, t, 0)
+                s0 = np.where(ok, start[tt], 0); cn = np.where(ok, cnt[tt], 0)
+                acc["red_small"] += 3; ideal["red_small"] += 3
+                trips = int(np.ceil(cn.max() / 2)) if cn.max() > 0 else 0
+                for m in range(trips):
+                    i0 = 2 * m
+                    a = np.concatenate([s0 + i0, s0 + i0 + 1]); on = np.concatenate([i0 < cn, i0 + 1 < cn])
+                    acc["red_ld"] += wavefronts(a[None] * 16, 16, on[None], quarter)[0] + wavefronts(a[None] * 8, 8, on[None], quarter)[0]
+                for m in range(trips):      # conflict-free bound: one wavefront per quarter / half warp with an active lane
+                    on = np.concatenate([2 * m < cn, 2 * m + 1 < cn])
+                    ideal["red_ld"] += on.reshape(4, 8).any(1).sum() + on.reshape(2, 16).any(1).sum()
+                v = np.where(ok, perm[tt], 0)
+                on = np.concatenate([ok, np.zeros(16, bool)]); a = np.concatenate([v * 24, np.zeros(16, np.int64)])
+                for k in range(3):
+                    acc["vbuf_st"] += wavefronts((a + 8 * k)[None], 8, on[None], quarter)[0]
+                ideal["vbuf_st"] += 3
+        for w in range((nv + 31) // 32):
+            lanes = 32 * w + np.arange(32); on = lanes < nv
+            for k in range(3):
+                acc["flush_ld"] += wavefronts((lanes * 24 + 8 * k)[None], 8, on[None], quarter)[0]
+            acc["flush_ld"] += 1; ideal["flush_ld"] += 7
+    per = {k: 32.0 * v / ntets for k, v in acc.items()}
+    per_i = {k: 32.0 * v / ntets for k, v in ideal.items()}
+    return per, per_i
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser(); ap.add_argument("--n", type=int, default=58)
+    ap.add_argument("--tiles", type=int, default=400); ap.add_argument("--quarter", action="store_true")
+    a = ap.parse_args()
+    tiles, conn, slots, tv, voff, vperm = host_tables(a.n)
+    print("tiles", len(tiles), "mean tets", tiles[:, 1].mean(), "mean verts", tiles[:, 3].mean(), "mean slots", tiles[:, 5].mean())
+    per, ideal = model(tiles, conn, slots, voff, vperm, a.quarter, a.tiles)
+    ld = per["static"] + per["gather"] + per["red_small"] + per["red_ld"] + per["flush_ld"]
+    st = per["slot_st"] + per["vbuf_st"]
+    for k in per: print(f"{k:10s} {per[k]:7.2f}   ideal {ideal[k]:7.2f}")
+    print(f"ld {ld:.1f} (ncu 143)  st {st:.1f} (ncu 56)   per 32 tets")
