@@ -89,6 +89,34 @@ APL_HD T apl_rsqrt(T x) {
 #endif
 }
 
+// 1/x: hardware approximation plus one Newton step in fp32 on the device (~1 ulp, no IEEE-division
+// slow path), a true division otherwise.
+template <typename T>
+APL_HD T apl_rcp(T x) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(T) == 4) {
+        float r = apl_rcp_raw((float)x);
+        const float e = fmaf(-(float)x, r, 1.0f);
+        return (T)fmaf(r, e, r);
+    } else {
+        return (T)1 / x;
+    }
+#else
+    return (T)1 / x;
+#endif
+}
+
+// sqrt(x) for x >= 0 through the reciprocal square root (0 for x = 0)
+template <typename T>
+APL_HD T apl_sqrt_pos(T x) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(T) == 4) return x * apl_rsqrt(apl_max(x, (T)1e-36));
+    else return sqrt(x);
+#else
+    return std::sqrt(x);
+#endif
+}
+
 // e[a][i] = w[a+1][i] - w[0][i]   (edge differences of a per-corner field)
 template <typename T>
 APL_HD void edge_diff(const T (*w)[3], T e[3][3]) {
@@ -413,14 +441,171 @@ APL_HD void snh_terms(const T* F, const T* dF, const T* D, T vol, T mu, T la, T&
     }
 }
 
-// ARAP (warp/fem/_arap.py:17-76) on F with dhdX block D.
+// ------------------------------------------------------------------------------------------
+// ARAP kinematics without an iterative SVD.
+//
+// Everything the ARAP terms need from F = U diag(s) V^T (rotation-variant convention) is
+//   R   = U V^T                                   the rotation of the polar decomposition F = R S,
+//   s   = the three singular values               (energy),
+//   Lam = sum_k lambda_k w_k w_k^T                with the twist axes w = (v2, v0, v1) of the modes
+//         Q0, Q1, Q2 (func/_misc.py:56-70: Q_k = R [w_k]_x / sqrt2) and their clamped rates lambda_k
+//         (func/_misc.py:31-43), i.e. Lam = f(tr(S) 1 - S) with f(m) = 2 / max(m, 2).
+// With S^2 = C = F^T F, Cayley-Hamilton gives S and R from the invariants of S alone:
+//   S = (I1 I3 1 + (I1^2 - I2) C - C^2) / (I1 I2 - I3),   R = (I1 F - F S + cof F) / I2,
+//   I1 = s0 + s1 + s2, I2 = s0 s1 + s1 s2 + s2 s0, I3 = s0 s1 s2 = det F,
+// the two larger singular values come from the trigonometric eigenvalues of C and the smallest one
+// (signed) from det F / (s0 s1), and f(M) is the Newton interpolation polynomial of f on the three
+// eigenvalues of M = I1 1 - S (exact for a 3x3 matrix function), with the isolated eigenvalue taken
+// first so that the divided differences of the two close ones are never amplified.  Errors stay at a few
+// ulps of F while I2 is not small; strongly compressed / inverted elements (I2 <= 0.5 s0^2) take the
+// Jacobi SVD above instead (rare, warp-divergent).  Lam is returned as [xx, yy, zz, xy, xz, yz].
+// ------------------------------------------------------------------------------------------
+#ifndef APL_ARAP_CLOSED_FORM
+#define APL_ARAP_CLOSED_FORM 1
+#endif
+
+template <typename T>
+APL_HD T apl_acos(T x) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(T) == 4) return acosf(x);
+    else return acos(x);
+#else
+    return std::acos(x);
+#endif
+}
+template <typename T>
+APL_HD T apl_cos(T x) {  // |x| <= pi
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(T) == 4) return __cosf(x);   // absolute error 2^-21, scaled by the eigenvalue spread
+    else return cos(x);
+#else
+    return std::cos(x);
+#endif
+}
+
+template <typename T>
+APL_HD void polar_twist_svd(const T* F, T* R, T* L, T* sg) {
+    T U[9], V[9];
+    svd3_rv(F, U, sg, V);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            R[3 * i + j] = U[3 * i] * V[3 * j] + U[3 * i + 1] * V[3 * j + 1] + U[3 * i + 2] * V[3 * j + 2];
+    const T two = (T)2;
+    const T l2 = two / apl_max(sg[0] + sg[1], two);   // axis v2
+    const T l0 = two / apl_max(sg[1] + sg[2], two);   // axis v0
+    const T l1 = two / apl_max(sg[2] + sg[0], two);   // axis v1
+    L[0] = l0 * V[0] * V[0] + l1 * V[1] * V[1] + l2 * V[2] * V[2];
+    L[1] = l0 * V[3] * V[3] + l1 * V[4] * V[4] + l2 * V[5] * V[5];
+    L[2] = l0 * V[6] * V[6] + l1 * V[7] * V[7] + l2 * V[8] * V[8];
+    L[3] = l0 * V[0] * V[3] + l1 * V[1] * V[4] + l2 * V[2] * V[5];
+    L[4] = l0 * V[0] * V[6] + l1 * V[1] * V[7] + l2 * V[2] * V[8];
+    L[5] = l0 * V[3] * V[6] + l1 * V[4] * V[7] + l2 * V[5] * V[8];
+}
+
+template <typename T>
+APL_HD void polar_twist(const T* F, T* R, T* L, T* sg) {
+#if !APL_ARAP_CLOSED_FORM
+    polar_twist_svd(F, R, L, sg);
+#else
+    // C = F^T F as [xx, yy, zz, xy, xz, yz]
+    T C[6];
+    C[0] = F[0] * F[0] + F[3] * F[3] + F[6] * F[6];
+    C[1] = F[1] * F[1] + F[4] * F[4] + F[7] * F[7];
+    C[2] = F[2] * F[2] + F[5] * F[5] + F[8] * F[8];
+    C[3] = F[0] * F[1] + F[3] * F[4] + F[6] * F[7];
+    C[4] = F[0] * F[2] + F[3] * F[5] + F[6] * F[8];
+    C[5] = F[1] * F[2] + F[4] * F[5] + F[7] * F[8];
+    T cof[9];
+    const T J = cofactor(F, cof);
+    // two largest eigenvalues of C (trigonometric form on the deviator)
+    const T q = (C[0] + C[1] + C[2]) * (T)(1.0 / 3.0);
+    const T b0 = C[0] - q, b1 = C[1] - q, b2 = C[2] - q;
+    const T p2 = (b0 * b0 + b1 * b1 + b2 * b2 + (T)2 * (C[3] * C[3] + C[4] * C[4] + C[5] * C[5])) * (T)(1.0 / 6.0);
+    const T detB = b0 * (b1 * b2 - C[5] * C[5]) - C[3] * (C[3] * b2 - C[5] * C[4]) + C[4] * (C[3] * C[5] - b1 * C[4]);
+    const T tiny = (sizeof(T) == 4) ? (T)1e-30 : (T)1e-280;
+    const T rs = apl_rsqrt(apl_max(p2, tiny));   // 1 / p
+    const T p = p2 * rs;
+    T r = (T)0.5 * detB * rs * rs * rs;          // det(B / p) / 2
+    r = r > (T)1 ? (T)1 : (r < (T)-1 ? (T)-1 : r);   // (a NaN from an underflow maps to -1: p is ~0 then)
+    const T phi = apl_acos(r) * (T)(1.0 / 3.0);
+    const T e0 = q + (T)2 * p * apl_cos(phi);
+    const T e1 = q + (T)2 * p * apl_cos(phi - (T)2.0943951023931954923);
+    const T s0 = apl_sqrt_pos(apl_max(e0, (T)0)), s1 = apl_sqrt_pos(apl_max(e1, (T)0));
+    const T s01 = s0 * s1;
+    const T s2 = s01 > tiny ? J * apl_rcp(s01) : (T)0;
+    const T I1 = s0 + s1 + s2, I2 = s01 + s2 * (s0 + s1);
+    if (!(I2 > (T)0.5 * e0)) {   // strongly compressed / inverted / degenerate (also NaN): robust path
+        polar_twist_svd(F, R, L, sg);
+        return;
+    }
+    sg[0] = s0; sg[1] = s1; sg[2] = s2;
+    // S = (I1 I3 + (I1^2 - I2) C - C^2) / (I1 I2 - I3)
+    const T inv_den = apl_rcp(I1 * I2 - J);
+    const T kc = (I1 * I1 - I2) * inv_den, k0 = I1 * J * inv_den;
+    T S[6];
+    S[0] = k0 + kc * C[0] - inv_den * (C[0] * C[0] + C[3] * C[3] + C[4] * C[4]);
+    S[1] = k0 + kc * C[1] - inv_den * (C[3] * C[3] + C[1] * C[1] + C[5] * C[5]);
+    S[2] = k0 + kc * C[2] - inv_den * (C[4] * C[4] + C[5] * C[5] + C[2] * C[2]);
+    S[3] = kc * C[3] - inv_den * (C[0] * C[3] + C[3] * C[1] + C[4] * C[5]);
+    S[4] = kc * C[4] - inv_den * (C[0] * C[4] + C[3] * C[5] + C[4] * C[2]);
+    S[5] = kc * C[5] - inv_den * (C[3] * C[4] + C[1] * C[5] + C[5] * C[2]);
+    // R = (I1 F - F S + cof F) / I2
+    const T inv_I2 = apl_rcp(I2);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const T f0 = F[3 * i], f1 = F[3 * i + 1], f2 = F[3 * i + 2];
+        R[3 * i + 0] = (I1 * f0 - (f0 * S[0] + f1 * S[3] + f2 * S[4]) + cof[3 * i + 0]) * inv_I2;
+        R[3 * i + 1] = (I1 * f1 - (f0 * S[3] + f1 * S[1] + f2 * S[5]) + cof[3 * i + 1]) * inv_I2;
+        R[3 * i + 2] = (I1 * f2 - (f0 * S[4] + f1 * S[5] + f2 * S[2]) + cof[3 * i + 2]) * inv_I2;
+    }
+    // Lam = f(M), M = I1 - S, eigenvalues m = (s1 + s2) <= (s0 + s2) <= (s0 + s1), f(m) = 2 / max(m, 2).
+    // Newton form on the nodes (a, b, c) = (isolated end, other end, middle):
+    //   f(M) = f_a + f[a,b] (M - a) + f[a,b,c] (M - a)(M - b)
+    const T two = (T)2;
+    const T m_lo = s1 + s2, m_mid = s0 + s2, m_hi = s0 + s1;
+    const bool hi_first = (m_hi - m_mid) >= (m_mid - m_lo);
+    const T ma = hi_first ? m_hi : m_lo, mb = hi_first ? m_lo : m_hi, mc = m_mid;
+    const T fa = two * apl_rcp(apl_max(ma, two)), fb = two * apl_rcp(apl_max(mb, two));
+    const T fc = two * apl_rcp(apl_max(mc, two));
+    const T dab = mb - ma, dbc = mc - mb, dac = mc - ma;
+    const T fab = fabs(dab) > tiny ? (fb - fa) * apl_rcp(dab) : (T)0;
+    const T fbc = fabs(dbc) > tiny ? (fc - fb) * apl_rcp(dbc) : (T)0;
+    const T fabc = fabs(dac) > tiny ? (fbc - fab) * apl_rcp(dac) : (T)0;
+    // A = M - a, B = M - b (symmetric, same off-diagonals = -S_offdiag)
+    const T A0 = I1 - S[0] - ma, A1 = I1 - S[1] - ma, A2 = I1 - S[2] - ma;
+    const T B0 = I1 - S[0] - mb, B1 = I1 - S[1] - mb, B2 = I1 - S[2] - mb;
+    const T o3 = -S[3], o4 = -S[4], o5 = -S[5];
+    L[0] = fa + fab * A0 + fabc * (A0 * B0 + o3 * o3 + o4 * o4);
+    L[1] = fa + fab * A1 + fabc * (o3 * o3 + A1 * B1 + o5 * o5);
+    L[2] = fa + fab * A2 + fabc * (o4 * o4 + o5 * o5 + A2 * B2);
+    L[3] = fab * o3 + fabc * (A0 * o3 + o3 * B1 + o4 * o5);
+    L[4] = fab * o4 + fabc * (A0 * o4 + o3 * o5 + o4 * B2);
+    L[5] = fab * o5 + fabc * (o3 * o4 + A1 * o5 + o5 * B2);
+#endif
+}
+
+// y = Lam x for the packed symmetric Lam
+template <typename T>
+APL_HD void sym_mul(const T* L, T x0, T x1, T x2, T& y0, T& y1, T& y2) {
+    y0 = L[0] * x0 + L[3] * x1 + L[4] * x2;
+    y1 = L[3] * x0 + L[1] * x1 + L[5] * x2;
+    y2 = L[4] * x0 + L[5] * x1 + L[2] * x2;
+}
+
+// ARAP (warp/fem/_arap.py:17-76) on F with dhdX block D, in terms of (R, Lam, s):
+//   Psi  = mu/2 sum (s_i - 1)^2,   P = mu (F - R),
+//   <Q_k, dF> = w_k . a / sqrt2 with a = axial vector of (R^T dF) - (R^T dF)^T, hence
+//   p^T H p = mu (|dF|^2 - a^T Lam a / 2),   H p = mu (dF - R [b]_x),  b = Lam a / 2  (row i of R [b]_x = r_i x b),
+//   (dhdX Q_k^T)[a][i] = w_k . (D_a x r_i) / sqrt2, hence diag[a][i] = mu (|D_a|^2 - z^T Lam z / 2), z = D_a x r_i.
 template <typename T, int OPS, bool ACC>
 APL_HD void arap_terms(const T* F, const T* dF, const T* D, T vol, T mu, T& psi, T& quad, T* P, T* M, T dg[4][3]) {
     constexpr bool kFun = (OPS & APL_OP_FUN) != 0, kGrad = (OPS & APL_OP_GRAD) != 0;
     constexpr bool kDiag = (OPS & APL_OP_HESS_DIAG) != 0, kProd = (OPS & APL_OP_HESS_PROD) != 0;
     constexpr bool kQuad = (OPS & APL_OP_HESS_QUAD) != 0;
-    T U[9], V[9], sg[3];
-    svd3_rv(F, U, sg, V);
+    T R[9], L[6], sg[3];
+    polar_twist(F, R, L, sg);
     if constexpr (kFun) {
         const T a = sg[0] - (T)1, b = sg[1] - (T)1, c = sg[2] - (T)1;
         put<ACC>(psi, vol * (T)0.5 * mu * (a * a + b * b + c * c));
@@ -428,79 +613,49 @@ APL_HD void arap_terms(const T* F, const T* dF, const T* D, T vol, T mu, T& psi,
     if constexpr (kGrad) {
         const T a = vol * mu;
 #pragma unroll
+        for (int k = 0; k < 9; ++k) put<ACC>(P[k], a * (F[k] - R[k]));
+    }
+    if constexpr (kDiag) {
+        T n[4];
+        row_norms(D, n);
+        const T Dr[4][3] = {{-(D[0] + D[3] + D[6]), -(D[1] + D[4] + D[7]), -(D[2] + D[5] + D[8])},
+                            {D[0], D[1], D[2]}, {D[3], D[4], D[5]}, {D[6], D[7], D[8]}};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const T z0 = Dr[a][1] * R[3 * i + 2] - Dr[a][2] * R[3 * i + 1];
+                const T z1 = Dr[a][2] * R[3 * i + 0] - Dr[a][0] * R[3 * i + 2];
+                const T z2 = Dr[a][0] * R[3 * i + 1] - Dr[a][1] * R[3 * i + 0];
+                T y0, y1, y2;
+                sym_mul(L, z0, z1, z2, y0, y1, y2);
+                const T h4 = (T)0.5 * (z0 * y0 + z1 * y1 + z2 * y2);
+                put<ACC>(dg[a][i], apl_max(vol * mu * (n[a] - h4), (T)0));
+            }
+    }
+    if constexpr (kProd || kQuad) {
+        // A = R^T dF; a = (A21 - A12, A02 - A20, A10 - A01)
+        T A[9];
+#pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j)
-                put<ACC>(P[3 * i + j], a * (F[3 * i + j] - (U[3 * i] * V[3 * j] + U[3 * i + 1] * V[3 * j + 1] +
-                                                            U[3 * i + 2] * V[3 * j + 2])));
-    }
-    if constexpr (kDiag || kProd || kQuad) {
-        const T two = (T)2;
-        // func/_misc.py:31-43 with clamp: lambda_k = 2 / max(s_i + s_j, 2), pairs (0,1),(1,2),(2,0)
-        const T l0 = two / apl_max(sg[0] + sg[1], two);
-        const T l1 = two / apl_max(sg[1] + sg[2], two);
-        const T l2 = two / apl_max(sg[2] + sg[0], two);
-        // twist modes (func/_misc.py:56-70): Q0 = (u1 v0^T - u0 v1^T)/sqrt2,
-        // Q1 = (u1 v2^T - u2 v1^T)/sqrt2, Q2 = (u0 v2^T - u2 v0^T)/sqrt2
-        if constexpr (kDiag) {
-            // Y[a][n] = dhdX_a . v_n ; (dhdX Q^T)[a][i] = (um[i] Y[a][n] - un[i] Y[a][m]) / sqrt2
-            T Y[4][3], n[4];
-            {
-                T Vt[9];
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) Vt[3 * i + j] = V[3 * j + i];
-                vjp_rows(D, Vt, (T)1, Y);  // Y[a][n] = sum_J dhdX[a][J] Vt[n][J] = dhdX_a . v_n
-            }
-            row_norms(D, n);
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const T w0 = U[3 * i + 1] * Y[a][0] - U[3 * i + 0] * Y[a][1];
-                    const T w1 = U[3 * i + 1] * Y[a][2] - U[3 * i + 2] * Y[a][1];
-                    const T w2 = U[3 * i + 0] * Y[a][2] - U[3 * i + 2] * Y[a][0];
-                    const T h4 = (T)0.5 * (l0 * w0 * w0 + l1 * w1 * w1 + l2 * w2 * w2);
-                    put<ACC>(dg[a][i], apl_max(vol * mu * (n[a] - h4), (T)0));
-                }
+            for (int j = 0; j < 3; ++j) A[3 * i + j] = R[i] * dF[j] + R[3 + i] * dF[3 + j] + R[6 + i] * dF[6 + j];
+        const T a0 = A[7] - A[5], a1 = A[2] - A[6], a2 = A[3] - A[1];
+        T b0, b1, b2;
+        sym_mul(L, a0, a1, a2, b0, b1, b2);
+        b0 *= (T)0.5; b1 *= (T)0.5; b2 *= (T)0.5;
+        if constexpr (kQuad) {
+            const T q = ddot9(dF, dF) - (a0 * b0 + a1 * b1 + a2 * b2);
+            put<ACC>(quad, apl_max(vol * mu * q, (T)0));
         }
-        if constexpr (kProd || kQuad) {
-            // B = U^T dF V ; <Q0,dF> = (B10 - B01)/sqrt2, <Q1,dF> = (B12 - B21)/sqrt2,
-            // <Q2,dF> = (B02 - B20)/sqrt2
-            T Tm[9], B[9];
+        if constexpr (kProd) {
+            const T s = vol * mu;
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j)
-                    Tm[3 * i + j] = U[i] * dF[j] + U[3 + i] * dF[3 + j] + U[6 + i] * dF[6 + j];
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j)
-                    B[3 * i + j] = Tm[3 * i] * V[j] + Tm[3 * i + 1] * V[3 + j] + Tm[3 * i + 2] * V[6 + j];
-            const T c0 = B[3] - B[1], c1 = B[5] - B[7], c2 = B[2] - B[6];  // times 1/sqrt2 each
-            if constexpr (kQuad) {
-                const T q = ddot9(dF, dF) - (T)0.5 * (l0 * c0 * c0 + l1 * c1 * c1 + l2 * c2 * c2);
-                put<ACC>(quad, apl_max(vol * mu * q, (T)0));
-            }
-            if constexpr (kProd) {
-                // M = dF - U K V^T, K = 1/2 [[0,-l0c0, l2c2],[l0c0,0,l1c1],[-l2c2,-l1c1,0]]
-                const T k0 = (T)0.5 * l0 * c0, k1 = (T)0.5 * l1 * c1, k2 = (T)0.5 * l2 * c2;
-                T UK[9];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    UK[3 * i + 0] = U[3 * i + 1] * k0 - U[3 * i + 2] * k2;
-                    UK[3 * i + 1] = -U[3 * i + 0] * k0 - U[3 * i + 2] * k1;
-                    UK[3 * i + 2] = U[3 * i + 0] * k2 + U[3 * i + 1] * k1;
-                }
-                const T a = vol * mu;
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int j = 0; j < 3; ++j)
-                        put<ACC>(M[3 * i + j], a * (dF[3 * i + j] - (UK[3 * i] * V[3 * j] + UK[3 * i + 1] * V[3 * j + 1] +
-                                                                     UK[3 * i + 2] * V[3 * j + 2])));
+            for (int i = 0; i < 3; ++i) {
+                const T r0 = R[3 * i], r1 = R[3 * i + 1], r2 = R[3 * i + 2];
+                put<ACC>(M[3 * i + 0], s * (dF[3 * i + 0] - (r1 * b2 - r2 * b1)));
+                put<ACC>(M[3 * i + 1], s * (dF[3 * i + 1] - (r2 * b0 - r0 * b2)));
+                put<ACC>(M[3 * i + 2], s * (dF[3 * i + 2] - (r0 * b1 - r1 * b0)));
             }
         }
     }

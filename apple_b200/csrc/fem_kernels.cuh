@@ -606,10 +606,16 @@ struct PipeCfg {
     static constexpr size_t oVring = oSlotBuf + Cfg::kSlotBytes;
     static constexpr size_t oStages = oVring + (size_t)kVring * kVtabBytes;
     static constexpr size_t kSmemBytes = oStages + (size_t)kStages * kStageBytes;
+    // CTAs per SM the shared memory allows (227 KB per SM, 1 KB reserved per CTA): the register budget of
+    // __launch_bounds__ follows it, so that a kernel that is shared-memory-limited to 2 CTAs does not
+    // spill to fit a third one
+    static constexpr int kSmemCtas = (int)((size_t)227 * 1024 / (kSmemBytes + 1024));
+    static constexpr int kWantCtas = (sizeof(T) == 4 ? 3 : 1) * (256 / kTileTets);
+    static constexpr int kMinCtas = kSmemCtas < 1 ? 1 : (kSmemCtas < kWantCtas ? kSmemCtas : kWantCtas);
 };
 
 template <typename T, int KIND, int OPS>
-__global__ void __launch_bounds__(kPipeThreads, (sizeof(T) == 4 ? 3 : 1) * (256 / kTileTets))
+__global__ void __launch_bounds__(kPipeThreads, PipeCfg<T, KIND, OPS>::kMinCtas)
     fem_pipe_kernel(const FemArgs<T> a) {
     using Cfg = TileCfg<T, OPS>;
     using PC = PipeCfg<T, KIND, OPS>;

@@ -43,3 +43,19 @@ extern "C" void svd3_host(int is_f64, int n, const void* F, void* U, void* s, vo
         else apl::svd3_rv<float>((const float*)F + 9 * t, (float*)U + 9 * t, (float*)s + 3 * t, (float*)V + 9 * t);
     }
 }
+
+// R (rotation-variant polar factor), Lam = sum_k lambda_k w_k w_k^T packed [xx,yy,zz,xy,xz,yz], singular values;
+// path 0 = product path (closed form with SVD fallback), 1 = Jacobi SVD only
+extern "C" void polar_twist_host(int is_f64, int path, int n, const void* F, void* R, void* L, void* s) {
+    for (int t = 0; t < n; ++t) {
+        if (is_f64) {
+            const double* f = (const double*)F + 9 * t;
+            if (path == 0) apl::polar_twist<double>(f, (double*)R + 9 * t, (double*)L + 6 * t, (double*)s + 3 * t);
+            else apl::polar_twist_svd<double>(f, (double*)R + 9 * t, (double*)L + 6 * t, (double*)s + 3 * t);
+        } else {
+            const float* f = (const float*)F + 9 * t;
+            if (path == 0) apl::polar_twist<float>(f, (float*)R + 9 * t, (float*)L + 6 * t, (float*)s + 3 * t);
+            else apl::polar_twist_svd<float>(f, (float*)R + 9 * t, (float*)L + 6 * t, (float*)s + 3 * t);
+        }
+    }
+}

@@ -221,6 +221,56 @@ def test_svd3_rotation_variant_convention(host_math, dtype, tol):
     assert np.abs(np.abs(s64) - ref).max() < 20 * tol
 
 
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 2e-6)], ids=["f64", "f32"])
+def test_arap_closed_form_polar_and_twist_operator(host_math, dtype, tol):
+    """polar_twist (no iterative SVD: invariants of S from the trigonometric eigenvalues of F^T F,
+    R = (I1 F - F S + cof F) / I2, Lam = f(tr(S) - S) by Newton interpolation) against numpy's SVD in the
+    rotation-variant convention of warp/math/_rotation.py:9-22 and the clamped twist rates of
+    warp/fem/func/_misc.py:31-43 -- rest state, isotropic scaling, small / large strain, flat and inverted
+    elements (which take the Jacobi fallback), and agreement of the two paths."""
+    rng = np.random.default_rng(11)
+    n = 3000
+    Q, _ = np.linalg.qr(rng.standard_normal((n, 3, 3)))
+    Q[np.linalg.det(Q) < 0, :, 0] *= -1
+    cases = {
+        "identity": np.repeat(np.eye(3)[None], 64, 0),
+        "isotropic": np.eye(3)[None] * rng.uniform(0.5, 2.0, (256, 1, 1)),
+        "strain 1e-4": np.eye(3) + 1e-4 * rng.standard_normal((n, 3, 3)),
+        "strain 3e-2": Q @ (np.eye(3) + 3e-2 * rng.standard_normal((n, 3, 3))),
+        "strain 0.2": Q @ (np.eye(3) + 0.2 * rng.standard_normal((n, 3, 3))),
+        "flat": (np.eye(3) + 0.1 * rng.standard_normal((n, 3, 3))) @ np.diag([1.0, 1.0, 1e-3]),
+        "inverted": (np.eye(3) + 0.2 * rng.standard_normal((n, 3, 3))) @ np.diag([1.0, 1.0, -0.3]),
+    }
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    for name, F64 in cases.items():
+        F = np.ascontiguousarray(F64, dtype)
+        Ft = F.astype(np.float64)
+        U, s, Vt = np.linalg.svd(Ft)
+        flip = np.linalg.det(U) < 0; U[flip, :, 2] *= -1; s[flip, 2] *= -1
+        flip = np.linalg.det(Vt) < 0; Vt[flip, 2, :] *= -1; s[flip, 2] *= -1
+        R_ref = U @ Vt
+        lam = 2.0 / np.maximum(np.stack([s[:, 1] + s[:, 2], s[:, 0] + s[:, 2], s[:, 0] + s[:, 1]], 1), 2.0)
+        L_ref = np.einsum("nki,nk,nkj->nij", Vt, lam, Vt)          # sum_k lam_k v_k v_k^T, axis k <-> s_i + s_j, i,j != k
+        out = {}
+        for path in (0, 1):
+            R = np.zeros_like(F); L = np.zeros((len(F), 6), dtype); sg = np.zeros((len(F), 3), dtype)
+            host_math.polar_twist_host(int(dtype == np.float64), path, len(F), P(F), P(R), P(L), P(sg))
+            out[path] = (R.astype(float), L.astype(float), sg.astype(float))
+        # well-posed elements: the two smallest singular values do not cancel (R is unique)
+        ok = (s[:, 1] + s[:, 2]) > 0.2 * s[:, 0]
+        assert ok.mean() > 0.7, name
+        for path, (R, L, sg) in out.items():
+            Lm = np.stack([L[:, [0, 3, 4]], L[:, [3, 1, 5]], L[:, [4, 5, 2]]], 1)
+            scale = s[:, 0][ok]
+            assert (np.abs(R - R_ref).max((1, 2))[ok] < 40 * tol).all(), (name, path)
+            assert (np.abs(Lm - L_ref).max((1, 2))[ok] < 40 * tol).all(), (name, path)
+            assert (np.abs(np.sort(sg, 1) - np.sort(s, 1)).max(1)[ok] < 400 * tol * scale).all(), (name, path)
+            assert np.isfinite(R).all() and np.isfinite(L).all()
+        if name in ("strain 3e-2", "strain 1e-4", "identity", "isotropic"):
+            # the regime of elasticity solves: a few ulps
+            assert np.abs(out[0][0] - R_ref).max() < 4 * tol and np.abs(out[0][1] - out[1][1]).max() < 8 * tol, name
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
 @pytest.mark.parametrize("kind", ["snh", "arap", "muscle", "snh+arap"])
 def test_static_planes_hold_the_reference_arrays(native_lib, kind, dtype):
