@@ -474,12 +474,13 @@ APL_HD T apl_acos(T x) {
 #endif
 }
 template <typename T>
-APL_HD T apl_cos(T x) {  // |x| <= pi
+APL_HD void apl_sincos(T x, T& sn, T& cs) {
 #if defined(__CUDA_ARCH__)
-    if constexpr (sizeof(T) == 4) return __cosf(x);   // absolute error 2^-21, scaled by the eigenvalue spread
-    else return cos(x);
+    if constexpr (sizeof(T) == 4) sincosf(x, &sn, &cs);
+    else sincos(x, &sn, &cs);
 #else
-    return std::cos(x);
+    sn = std::sin(x);
+    cs = std::cos(x);
 #endif
 }
 
@@ -530,8 +531,10 @@ APL_HD void polar_twist(const T* F, T* R, T* L, T* sg) {
     T r = (T)0.5 * detB * rs * rs * rs;          // det(B / p) / 2
     r = r > (T)1 ? (T)1 : (r < (T)-1 ? (T)-1 : r);   // (a NaN from an underflow maps to -1: p is ~0 then)
     const T phi = apl_acos(r) * (T)(1.0 / 3.0);
-    const T e0 = q + (T)2 * p * apl_cos(phi);
-    const T e1 = q + (T)2 * p * apl_cos(phi - (T)2.0943951023931954923);
+    T sn, cs;
+    apl_sincos(phi, sn, cs);                     // phi in [0, pi/3]
+    const T e0 = q + (T)2 * p * cs;
+    const T e1 = q + p * ((T)1.7320508075688772935 * sn - cs);   // q + 2 p cos(phi - 2 pi / 3)
     const T s0 = apl_sqrt_pos(apl_max(e0, (T)0)), s1 = apl_sqrt_pos(apl_max(e1, (T)0));
     const T s01 = s0 * s1;
     const T s2 = s01 > tiny ? J * apl_rcp(s01) : (T)0;
@@ -595,7 +598,7 @@ APL_HD void sym_mul(const T* L, T x0, T x1, T x2, T& y0, T& y1, T& y2) {
 }
 
 // ARAP (warp/fem/_arap.py:17-76) on F with dhdX block D, in terms of (R, Lam, s):
-//   Psi  = mu/2 sum (s_i - 1)^2,   P = mu (F - R),
+//   Psi  = mu/2 |F - R|^2,   P = mu (F - R),
 //   <Q_k, dF> = w_k . a / sqrt2 with a = axial vector of (R^T dF) - (R^T dF)^T, hence
 //   p^T H p = mu (|dF|^2 - a^T Lam a / 2),   H p = mu (dF - R [b]_x),  b = Lam a / 2  (row i of R [b]_x = r_i x b),
 //   (dhdX Q_k^T)[a][i] = w_k . (D_a x r_i) / sqrt2, hence diag[a][i] = mu (|D_a|^2 - z^T Lam z / 2), z = D_a x r_i.
@@ -606,14 +609,18 @@ APL_HD void arap_terms(const T* F, const T* dF, const T* D, T vol, T mu, T& psi,
     constexpr bool kQuad = (OPS & APL_OP_HESS_QUAD) != 0;
     T R[9], L[6], sg[3];
     polar_twist(F, R, L, sg);
-    if constexpr (kFun) {
-        const T a = sg[0] - (T)1, b = sg[1] - (T)1, c = sg[2] - (T)1;
-        put<ACC>(psi, vol * (T)0.5 * mu * (a * a + b * b + c * c));
-    }
-    if constexpr (kGrad) {
-        const T a = vol * mu;
+    if constexpr (kFun || kGrad) {
+        // Psi = mu/2 |F - R|^2 as the reference writes it (_arap.py:17-24); more accurate than sum (s_i - 1)^2
+        // from the trigonometric singular values, whose individual errors only cancel in symmetric functions
+        T E[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) put<ACC>(P[k], a * (F[k] - R[k]));
+        for (int k = 0; k < 9; ++k) E[k] = F[k] - R[k];
+        if constexpr (kFun) put<ACC>(psi, vol * (T)0.5 * mu * ddot9(E, E));
+        if constexpr (kGrad) {
+            const T a = vol * mu;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) put<ACC>(P[k], a * E[k]);
+        }
     }
     if constexpr (kDiag) {
         T n[4];
