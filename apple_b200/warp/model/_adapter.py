@@ -64,6 +64,71 @@ class WarpModelAdapter:
         )
         return fun[0], grad, prod
 
+    def fun_grad_hess_prod_host(self, u: torch.Tensor, p: torch.Tensor, out=None, *, scatter=None):
+        """Host-buffer form of :meth:`fun_grad_hess_prod`: ``u`` and ``p`` are HOST tensors ``(n_points, 3)``
+        (pinned memory makes the copies asynchronous), the results land in the host tensors
+        ``out = (fun (1,), grad (n_points, 3), prod (n_points, 3))`` (allocated pinned and reused when
+        ``None``).  This is what a caller whose state lives in host memory pays per evaluation, so the
+        two PCIe directions are overlapped with the element passes instead of running
+        copy-in -> kernel -> copy-out back to back:
+
+            copy stream in :  u ---------> p --------->
+            compute stream :              [fun+grad(u)]   [hess_prod(u, p)]
+            copy stream out:                           grad, fun ------>     prod ------>
+
+        Energy and gradient need only ``u`` and start while ``p`` is still in flight; the gradient
+        travels back while the Hessian-vector pass runs.  Two element passes cost more GPU time than
+        the fused one, but they hide behind the interconnect, which is the bottleneck of this call.
+        Everything is ordered after prior work on the current stream, and the current stream waits for
+        the last copy: synchronising it (or any later work on it) sees the host results."""
+        model = self.__wrapped__
+        st = self._host_state(u.dtype)
+        dev = st["device"]
+        n = self.n_points
+        if out is None:
+            out = st["out"]
+        fun_h, grad_h, prod_h = out
+        cur = torch.cuda.current_stream(dev)
+        s_in, s_out = st["s_in"], st["s_out"]
+        s_in.wait_stream(cur)     # earlier kernels on the current stream may still read the staging buffers
+        with torch.cuda.stream(s_in):
+            st["u"].copy_(u.reshape(n, 3), non_blocking=True)
+            ev_u = s_in.record_event()
+            st["p"].copy_(p.reshape(n, 3), non_blocking=True)
+            ev_p = s_in.record_event()
+        with torch.cuda.device(dev):
+            cur.wait_event(ev_u)
+            model.eval(_lib.OP_FUN | _lib.OP_GRAD, st["u"], None, fun=st["fun"], grad=st["grad"], scatter=scatter)
+            s_out.wait_stream(cur)
+            with torch.cuda.stream(s_out):
+                grad_h.copy_(st["grad"], non_blocking=True)
+                fun_h.copy_(st["fun"], non_blocking=True)
+            cur.wait_event(ev_p)
+            model.eval(_lib.OP_HESS_PROD, st["u"], st["p"], prod=st["prod"], scatter=scatter)
+            s_out.wait_stream(cur)
+            with torch.cuda.stream(s_out):
+                prod_h.copy_(st["prod"], non_blocking=True)
+            cur.wait_stream(s_out)
+        return fun_h, grad_h, prod_h
+
+    def _host_state(self, dtype: torch.dtype) -> dict:
+        cache = self.__dict__.setdefault("_host_cache", {})
+        if dtype not in cache:
+            pots = list(self.__wrapped__.potentials.values())
+            dev = torch.device(getattr(pots[0], "device", "cuda")) if pots else torch.device("cuda")
+            if dev.type != "cuda":
+                raise _lib.NativeError("fun_grad_hess_prod_host needs a model on a CUDA device (there is no CPU path)")
+            n = self.n_points
+            field = lambda: torch.empty((n, 3), dtype=dtype, device=dev)  # noqa: E731
+            cache[dtype] = {
+                "device": dev, "u": field(), "p": field(), "grad": field(), "prod": field(),
+                "fun": torch.empty(1, dtype=dtype, device=dev),
+                "s_in": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
+                "out": (torch.empty(1, dtype=dtype).pin_memory(), torch.empty((n, 3), dtype=dtype).pin_memory(),
+                        torch.empty((n, 3), dtype=dtype).pin_memory()),
+            }
+        return cache[dtype]
+
     def fun_grad_hess_diag(self, u: torch.Tensor, *, scatter=None):
         """(energy, gradient, Hessian diagonal): PNCG's pass A."""
         u = u.contiguous()

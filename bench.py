@@ -6,7 +6,7 @@ Neo-Hookean + ARAP on the same mesh, fp32.  One *step* = one fused energy + grad
 Hessian-vector-product evaluation of the whole model (every potential, one pass each).
 
   value      tets/s, inputs resident in HBM, L2 flushed between timed steps
-  e2e        same metric through WarpModelAdapter.fun_grad_hess_prod with HOST (pinned) u, p:
+  e2e        same metric through WarpModelAdapter.fun_grad_hess_prod_host with HOST (pinned) u, p:
              H2D copies, kernels, D2H of energy + gradient + HVP inside the timed region
   roofline   dominant kernel: algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
   pncg       200 fused PNCG iterations on the same model (iterations/s)
@@ -82,6 +82,12 @@ def build_mesh(n, seed=0):
     u = 0.05 * h * np.sin(7.0 * X[:, [1, 2, 0]] + 0.3) + 0.02 * h * rng.uniform(-1, 1, X.shape)
     p = rng.uniform(-1, 1, X.shape)
     return mesh, np.ascontiguousarray(u), np.ascontiguousarray(p)
+
+
+def workload_name(args, mesh, kinds):
+    """config.workload, shared by both arms."""
+    return (f"cube {args.n}^3x5 = {mesh.n_cells} tets / {mesh.n_points} verts, {'+'.join(kinds)}, "
+            f"fused energy+grad+HVP")
 
 
 def algorithmic_bytes_per_tet(kind, w, v_over_t, per_vertex_words):
@@ -228,12 +234,14 @@ def run_reference(args):
     value, T, dt, threads = time_oracle(mesh, u, p, kinds, sample, steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": args.scaling if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"cube {args.n}^3x5 = {mesh.n_cells} tets / {mesh.n_points} verts, {'+'.join(kinds)}, "
-                               "energy + gradient + HVP (three operator passes per potential, as the reference runs them)",
-                   "note": "CPU restatement of the reference's Warp kernels in C (oracle/c, pthreads, fp64); the "
-                           "reference itself needs warp-lang/JAX, which cannot be installed here"},
+        "config": {"workload": workload_name(args, mesh, kinds),
+                   "reference_arm": "energy + gradient + HVP as three operator passes per potential, exactly as the "
+                                    "reference launches them (warp/model/_model.py:13-36); CPU restatement of the "
+                                    "reference's Warp kernels in C (oracle/c, pthreads, fp64) -- the reference itself needs "
+                                    "warp-lang / JAX, which cannot be installed here"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"first {T} tets of the Morton-ordered mesh, {steps} evaluations"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -399,24 +407,54 @@ def main():
         hh = torch.empty((V, 3), dtype=dtype).pin_memory()
         fh = torch.empty(1, dtype=dtype).pin_memory()
 
-        def e2e_step():
+        def step_streamed():
+            # the host-buffer entry point of the plugin: H2D of u, p and D2H of energy, gradient, HVP are
+            # inside, overlapped with two element passes on side streams (see its docstring)
+            adapter.fun_grad_hess_prod_host(uh, ph, out=(fh, gh, hh))
+
+        def step_serial():
+            # the same call sequence a caller with host state would write by hand: copy in, one fused
+            # pass, copy out, all on the current stream
             u_d = uh.to(dev, non_blocking=True); p_d = ph.to(dev, non_blocking=True)
             f, g, h = adapter.fun_grad_hess_prod(u_d, p_d)
             fh.copy_(f.reshape(1), non_blocking=True); gh.copy_(g, non_blocking=True); hh.copy_(h, non_blocking=True)
 
-        for _ in range(3):
-            e2e_step()
-        torch.cuda.synchronize()
-        tt = 0.0
-        for _ in range(args.steps):
-            flush()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); e2e_step(); b.record()
+        def time_e2e(fn):
+            for _ in range(3):
+                fn()
             torch.cuda.synchronize()
-            tt += a.elapsed_time(b)
+            tt = 0.0
+            for _ in range(args.steps):
+                flush()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                torch.cuda.synchronize()
+                tt += a.elapsed_time(b)
+            return tt
+
+        # the serial form is timed first and kept as the check of the streamed one (same energy / gradient /
+        # HVP in the host buffers) and as the fallback should the streamed entry point fail on this box
+        tt_serial = time_e2e(step_serial)
+        ref = (fh.clone(), gh.clone(), hh.clone())
+        api, note, launches = "serial", None, len(pots)
+        tt = tt_serial
+        try:
+            fh.zero_(); gh.zero_(); hh.zero_()
+            tt_streamed = time_e2e(step_streamed)
+            err = max(float((x - y).abs().max() / y.abs().max()) for x, y in zip((fh, gh, hh), ref))
+            if err < 1e-4:
+                api, tt, launches = "streamed", tt_streamed, 2 * len(pots)
+            else:
+                note = f"streamed entry point disagreed with the serial one (rel. err {err:.2e}); serial number reported"
+        except Exception as exc:  # pragma: no cover - robustness of the benchmark line
+            note = f"streamed entry point failed ({type(exc).__name__}: {exc}); serial number reported"
         e2e = {"value": T_total * args.steps / (tt * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(2 * V * 3 * w), "d2h_bytes_per_step": int(2 * V * 3 * w + w),
-               "ms_per_step": tt / args.steps}
+               "ms_per_step": tt / args.steps,
+               "api": {"streamed": "WarpModelAdapter.fun_grad_hess_prod_host(u_host, p_host, out=host tensors): copies "
+                                   "overlapped with a fun+grad pass and a hess_prod pass on side streams",
+                       "serial": "u.to(device); p.to(device); WarpModelAdapter.fun_grad_hess_prod; copy_ to host"}[api],
+               "gpu_launches_per_step": launches, "serial_ms_per_step": tt_serial / args.steps, "note": note}
 
     # ---- PNCG iterations/s on the same model (config 1/2 style solve: fixed base, fused path) ----
     pncg = None
@@ -442,8 +480,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": args.scaling if world > 1 else "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"cube {args.n}^3x5 = {T_total} tets / {V} verts, {'+'.join(kinds)}, "
-                                   f"fused energy+grad+HVP ({args.scatter} assembly)",
+            "config": {"workload": workload_name(args, mesh, kinds), "assembly": args.scatter,
                        "l2": "256 MiB flush write between timed steps" if not args.no_flush else "no flush",
                        "parallelism": (f"{world} ranks x contiguous Morton chunk of tets (~{T_total // world} tets per "
                                        f"GPU, {args.scaling} scaling); halo sum of grad+HVP (NCCL all-to-all of "
