@@ -28,6 +28,8 @@ S_SUMS, S_ALPHA_J, S_ACC_J, S_FT_J = 20, 32, 48, 64
  PHASE_COMMIT) = range(9)
 
 # every symbol include/apple_b200.h declares: name -> (restype, argtypes)
+PART_ALL, PART_BOUNDARY, PART_INTERIOR = 0, 1, 2
+
 SIGNATURES = {
     "apl_version": (c_int, []),
     "apl_last_error": (c_char_p, []),
@@ -43,6 +45,9 @@ SIGNATURES = {
     "apl_fem_set_materials": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "apl_fem_eval": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_int, c_int, c_void_p]),
+    "apl_fem_eval_part": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "apl_fem_mark_boundary": (c_int, [c_void_p, c_void_p, POINTER(c_int64)]),
     "apl_ext_force_eval": (c_int, [c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                    c_int, c_void_p]),
     "apl_field_copy": (c_int, [c_int, c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p]),

@@ -2,6 +2,8 @@
 // Interface documentation lives in include/apple_b200.h.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include <cmath>
 #include <cstring>
 
@@ -87,7 +89,7 @@ struct PncgExtras {
 template <typename T>
 static int eval_typed(apl_fem* f, int ops, const void* u, const void* p, int ld_in, void* fun, void* quad,
                       void* grad, void* diag, void* prod, int ld_out, int scatter, cudaStream_t stream,
-                      const PncgExtras* ex = nullptr) {
+                      const PncgExtras* ex = nullptr, int part = APL_PART_ALL) {
     FemArgs<T> a;
     if (ex) {
         a.axpy_p = (const T*)ex->axpy_p;
@@ -99,8 +101,13 @@ static int eval_typed(apl_fem* f, int ops, const void* u, const void* p, int ld_
         a.fun_d = (ops & APL_OP_FUN) ? ex->fun_d : nullptr;
         a.quad_d = (ops & APL_OP_HESS_QUAD) ? ex->quad_d : nullptr;
     }
-    a.tiles = (const int4*)f->d_tiles;
-    a.n_tiles = (int)f->host.n_tiles();
+    {
+        const int64_t nt = f->host.n_tiles(), nb = f->n_boundary_tiles;
+        const int64_t begin = part == APL_PART_INTERIOR ? nb : 0;
+        const int64_t count = part == APL_PART_ALL ? nt : (part == APL_PART_BOUNDARY ? nb : nt - nb);
+        a.tiles = (const int4*)f->d_tiles + begin;
+        a.n_tiles = (int)count;
+    }
     a.conn = (const uchar4*)f->d_conn;
     a.slots = (const ushort4*)f->d_slots;
     a.tile_verts = (const int*)f->d_tile_verts;
@@ -482,10 +489,14 @@ int apl_fem_set_materials(apl_fem_t* f, const void* dV, const void* mu, const vo
     return APL_OK;
 }
 
-int apl_fem_eval(apl_fem_t* f, int ops, const void* u, const void* p, int ld_in, void* fun, void* quad,
-                 void* grad, void* diag, void* prod, int ld_out, int scatter, void* stream) {
+int apl_fem_eval_part(apl_fem_t* f, int part, int ops, const void* u, const void* p, int ld_in, void* fun, void* quad,
+                      void* grad, void* diag, void* prod, int ld_out, int scatter, void* stream) {
     if (!f) { set_error("apl_fem_eval: NULL handle"); return APL_ERR_INVALID; }
     if (f->device < 0) { set_error("apl_fem_eval: handle was created host-only (device = -1)"); return APL_ERR_STATE; }
+    if (part != APL_PART_ALL && part != APL_PART_BOUNDARY && part != APL_PART_INTERIOR) {
+        set_error("apl_fem_eval_part: unknown part");
+        return APL_ERR_INVALID;
+    }
     if (ops <= 0 || ops > 31) { set_error("apl_fem_eval: ops must be a non-empty OR of APL_OP_*"); return APL_ERR_INVALID; }
     if ((ld_in != 3 && ld_in != 4) || (ld_out != 3 && ld_out != 4)) {
         set_error("apl_fem_eval: leading dimensions must be 3 or 4");
@@ -503,8 +514,54 @@ int apl_fem_eval(apl_fem_t* f, int ops, const void* u, const void* p, int ld_in,
     }
     cudaStream_t s = (cudaStream_t)stream;
     return f->dtype == APL_F32
-               ? eval_typed<float>(f, ops, u, p, ld_in, fun, quad, grad, diag, prod, ld_out, scatter, s)
-               : eval_typed<double>(f, ops, u, p, ld_in, fun, quad, grad, diag, prod, ld_out, scatter, s);
+               ? eval_typed<float>(f, ops, u, p, ld_in, fun, quad, grad, diag, prod, ld_out, scatter, s, nullptr, part)
+               : eval_typed<double>(f, ops, u, p, ld_in, fun, quad, grad, diag, prod, ld_out, scatter, s, nullptr, part);
+}
+
+int apl_fem_eval(apl_fem_t* f, int ops, const void* u, const void* p, int ld_in, void* fun, void* quad,
+                 void* grad, void* diag, void* prod, int ld_out, int scatter, void* stream) {
+    return apl_fem_eval_part(f, APL_PART_ALL, ops, u, p, ld_in, fun, quad, grad, diag, prod, ld_out, scatter, stream);
+}
+
+int apl_fem_mark_boundary(apl_fem_t* f, const uint8_t* vertex_flags, int64_t* n_boundary) {
+    if (!f) { set_error("apl_fem_mark_boundary: NULL handle"); return APL_ERR_INVALID; }
+    HostTables& h = f->host;
+    const int64_t nt = h.n_tiles();
+    // stable partition of the 6-int tile headers: tiles touching a flagged vertex first
+    // (in packed order, whatever an earlier call left: the result only depends on the flags)
+    std::vector<int64_t> by_start((size_t)nt);
+    for (int64_t t = 0; t < nt; ++t) by_start[(size_t)t] = t;
+    std::sort(by_start.begin(), by_start.end(),
+              [&](int64_t a, int64_t b) { return h.tiles[(size_t)(6 * a)] < h.tiles[(size_t)(6 * b)]; });
+    std::vector<int32_t> front, back;
+    front.reserve(h.tiles.size());
+    back.reserve(h.tiles.size());
+    for (int64_t i = 0; i < nt; ++i) {
+        const int32_t* hdr = h.tiles.data() + 6 * by_start[(size_t)i];
+        bool touches = false;
+        if (vertex_flags)
+            for (int32_t k = 0; k < hdr[3] && !touches; ++k) touches = vertex_flags[h.tile_verts[(size_t)hdr[2] + k]] != 0;
+        std::vector<int32_t>& dst = touches ? front : back;
+        dst.insert(dst.end(), hdr, hdr + 6);
+    }
+    f->n_boundary_tiles = (int64_t)front.size() / 6;
+    front.insert(front.end(), back.begin(), back.end());
+    h.tiles.swap(front);
+    if (n_boundary) *n_boundary = f->n_boundary_tiles;
+    if (f->device >= 0 && nt > 0) {
+        std::vector<int32_t> hdr((size_t)nt * 4);
+        for (int64_t t = 0; t < nt; ++t) {
+            const int32_t* src = h.tiles.data() + 6 * t;
+            hdr[4 * t] = src[0];
+            hdr[4 * t + 1] = src[1] | (src[3] << 16);
+            hdr[4 * t + 2] = src[2];
+            hdr[4 * t + 3] = src[4];
+        }
+        APL_CUDA_CHECK(cudaSetDevice(f->device));
+        APL_CUDA_CHECK(cudaDeviceSynchronize());   // setup-time call: no launch may still read the old order
+        APL_CUDA_CHECK(cudaMemcpy(f->d_tiles, hdr.data(), hdr.size() * 4, cudaMemcpyHostToDevice));
+    }
+    return APL_OK;
 }
 
 int apl_ext_force_eval(int dtype, int ops, int64_t k, const void* force, const int32_t* indices, const void* u,

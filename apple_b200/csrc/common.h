@@ -59,6 +59,7 @@ struct apl_fem {
     unsigned int* d_counter = nullptr;
     int max_grid = 0;
     int num_sms = 0;
+    int64_t n_boundary_tiles = 0;   // tile headers [0, n_boundary_tiles) touch a flagged (shared) vertex
 };
 
 #define APL_CUDA_CHECK(expr)                                                                       \

@@ -16,43 +16,62 @@ class ShardedOperators:
     the CPU tests substitute the oracle).  Inputs and outputs are local nodal fields whose shared rows
     are kept consistent across ranks; scalars are global."""
 
-    def __init__(self, local_model, shard: Shard, device, dtype, group=None):
+    def __init__(self, local_model, shard: Shard, device, dtype, group=None, overlap: bool = True):
         self.model = local_model
         self.shard = shard
         self.halo = HaloExchange(shard, device, group)
         self.device, self.dtype = torch.device(device), dtype
         self.n_local = shard.n_local
+        # Split evaluation: element tiles that touch a shared vertex first, then the halo exchange of their
+        # results on a side stream WHILE the interior tiles (which touch no shared vertex) are evaluated.
+        self._split = hasattr(local_model, "mark_boundary")
+        self.overlap = False
+        self.n_boundary_tiles = 0
+        if overlap and self._split and shard.world > 1 and self.halo.total > 0:
+            import numpy as np
+
+            flags = np.zeros(shard.n_local, np.uint8)
+            for idx in shard.neighbors.values():
+                flags[idx] = 1
+            self.n_boundary_tiles = int(local_model.mark_boundary(flags))
+            self.overlap = True
+        self._side = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
 
     def eval(self, ops: int, u, p=None):
         """Returns a dict with the requested results: fun / quad (0-d tensors, global), grad / diag /
         prod ((n_local, 3), halo-summed)."""
         n = self.n_local
-        new = lambda: torch.zeros((n, 3), dtype=self.dtype, device=self.device)  # noqa: E731
+        names = [k for k, bit in (("grad", _lib.OP_GRAD), ("diag", _lib.OP_HESS_DIAG), ("prod", _lib.OP_HESS_PROD)) if ops & bit]
+        snames = [k for k, bit in (("fun", _lib.OP_FUN), ("quad", _lib.OP_HESS_QUAD)) if ops & bit]
         out = {}
-        if ops & _lib.OP_FUN:
-            out["fun"] = torch.zeros(1, dtype=self.dtype, device=self.device)
-        if ops & _lib.OP_HESS_QUAD:
-            out["quad"] = torch.zeros(1, dtype=self.dtype, device=self.device)
-        if ops & _lib.OP_GRAD:
-            out["grad"] = new()
-        if ops & _lib.OP_HESS_DIAG:
-            out["diag"] = new()
-        if ops & _lib.OP_HESS_PROD:
-            out["prod"] = new()
-        self.model.eval(ops, u, p, **out)
-        fields = [out[k] for k in ("grad", "diag", "prod") if k in out]
-        self.halo.sum_(*fields)
-        scalars = [out[k] for k in ("fun", "quad") if k in out]
-        if len(scalars) == 1:
-            self.halo.all_reduce_(scalars[0])
-            for k in ("fun", "quad"):
-                if k in out:
-                    out[k] = out[k][0]
-        elif scalars:
-            s = torch.cat(scalars)
-            self.halo.all_reduce_(s)
-            for i, k in enumerate(k for k in ("fun", "quad") if k in out):
-                out[k] = s[i]
+        if names:   # one allocation + one memset for all fields
+            block = torch.zeros((len(names), n, 3), dtype=self.dtype, device=self.device)
+            for i, k in enumerate(names):
+                out[k] = block[i]
+        scal = torch.zeros(max(len(snames), 1), dtype=self.dtype, device=self.device)
+        for i, k in enumerate(snames):
+            out[k] = scal[i:i + 1]
+        fields = [out[k] for k in names]
+        kw = {"zero": False} if self._split else {}    # the outputs above are already zero
+        if self.overlap and fields:
+            self.model.eval(ops, u, p, part=_lib.PART_BOUNDARY, **out, **kw)
+            if self._side is not None:
+                cur = torch.cuda.current_stream(self.device)
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    self.halo.sum_(*fields)            # pack, all-to-all, unpack: shared rows only
+                self.model.eval(ops, u, p, part=_lib.PART_INTERIOR, **out, **kw)
+                cur.wait_stream(self._side)
+            else:                                      # CPU (gloo tests): same order, no overlap
+                self.halo.sum_(*fields)
+                self.model.eval(ops, u, p, part=_lib.PART_INTERIOR, **out, **kw)
+        else:
+            self.model.eval(ops, u, p, **out, **kw)
+            self.halo.sum_(*fields)
+        if snames:
+            self.halo.all_reduce_(scal)
+            for i, k in enumerate(snames):
+                out[k] = scal[i]
         return out
 
     def fun_grad_hess_prod(self, u, p):

@@ -146,8 +146,20 @@ class WarpPotentialFem(WarpPotential):
             )
         )
 
+    def mark_boundary(self, vertex_flags) -> int:
+        """Tiles touching a vertex with a non-zero flag become the BOUNDARY part (``eval(..., part=1)``), the
+        others the INTERIOR part (``part=2``); returns the number of boundary tiles.  Used by the sharded
+        operators to overlap the halo exchange with the interior pass (``apple_b200/dist/_model.py``)."""
+        n = ctypes.c_int64()
+        flags = None if vertex_flags is None else np.ascontiguousarray(vertex_flags, dtype=np.uint8)
+        if flags is not None and flags.size != self.n_points:
+            raise ValueError("vertex_flags must have one entry per point")
+        _lib.check(_lib.lib().apl_fem_mark_boundary(self._handle, _lib.host_ptr(flags), ctypes.byref(n)))
+        return int(n.value)
+
     # ---- operators ----
-    def eval(self, ops: int, u, p=None, *, fun=None, quad=None, grad=None, diag=None, prod=None, scatter=None) -> None:
+    def eval(self, ops: int, u, p=None, *, fun=None, quad=None, grad=None, diag=None, prod=None, scatter=None,
+             part: int = 0) -> None:
         ld_in = _lib.field_ld(u, self.n_points, self.dtype, "u")
         if ops & (_lib.OP_HESS_PROD | _lib.OP_HESS_QUAD):
             if p is None or _lib.field_ld(p, self.n_points, self.dtype, "p") != ld_in:
@@ -166,8 +178,8 @@ class WarpPotentialFem(WarpPotential):
             scatter = self.scatter if self.scatter is not None else config.scatter
         with torch.cuda.device(self.device):
             _lib.check(
-                _lib.lib().apl_fem_eval(
-                    self._handle, ops, _lib.dev_ptr(u), _lib.dev_ptr(p), ld_in, _lib.dev_ptr(fun), _lib.dev_ptr(quad),
+                _lib.lib().apl_fem_eval_part(
+                    self._handle, int(part), ops, _lib.dev_ptr(u), _lib.dev_ptr(p), ld_in, _lib.dev_ptr(fun), _lib.dev_ptr(quad),
                     _lib.dev_ptr(grad), _lib.dev_ptr(diag), _lib.dev_ptr(prod), ld_out or 3, scatter,
                     _lib.stream_ptr(self.device),
                 )

@@ -39,10 +39,25 @@ class WarpModel:
         for potential in self.potentials.values():
             potential.hess_quad(u, p, output)
 
-    def eval(self, ops: int, u, p=None, *, fun=None, quad=None, grad=None, diag=None, prod=None, scatter=None) -> None:
-        """Fused form: every requested operator of every potential in one pass per potential."""
-        for out in (fun, quad, grad, diag, prod):
-            if out is not None:
-                out.zero_()
+    def mark_boundary(self, vertex_flags) -> int:
+        """Forwards to every potential that has element tiles; returns the total number of boundary tiles."""
+        total = 0
         for potential in self.potentials.values():
-            potential.eval(ops, u, p, fun=fun, quad=quad, grad=grad, diag=diag, prod=prod, scatter=scatter)
+            if hasattr(potential, "mark_boundary"):
+                total += int(potential.mark_boundary(vertex_flags))
+        return total
+
+    def eval(self, ops: int, u, p=None, *, fun=None, quad=None, grad=None, diag=None, prod=None, scatter=None,
+             part: int = 0, zero: bool = True) -> None:
+        """Fused form: every requested operator of every potential in one pass per potential.  ``part`` / ``zero``
+        serve split evaluations (boundary tiles first, interior tiles while the halo exchange runs): the second
+        call passes ``zero=False`` and accumulates."""
+        if zero:
+            for out in (fun, quad, grad, diag, prod):
+                if out is not None:
+                    out.zero_()
+        for potential in self.potentials.values():
+            if part:
+                potential.eval(ops, u, p, fun=fun, quad=quad, grad=grad, diag=diag, prod=prod, scatter=scatter, part=part)
+            else:
+                potential.eval(ops, u, p, fun=fun, quad=quad, grad=grad, diag=diag, prod=prod, scatter=scatter)

@@ -33,9 +33,10 @@ class ExternalForce(WarpPotential):
         indices = np.asarray(obj.point_data[GLOBAL_POINT_ID.vtk])
         return cls(indices, force, **kwargs)
 
-    def eval(self, ops: int, u, p=None, *, fun=None, quad=None, grad=None, diag=None, prod=None, scatter=None) -> None:
+    def eval(self, ops: int, u, p=None, *, fun=None, quad=None, grad=None, diag=None, prod=None, scatter=None,
+             part: int = 0) -> None:
         ops &= _lib.OP_FUN | _lib.OP_GRAD  # Hessian operators are no-ops (:80-90)
-        if not ops:
+        if not ops or part == _lib.PART_INTERIOR:   # a split evaluation applies the loads with the boundary part
             return
         ld_in = int(u.shape[1])
         ld_out = int(grad.shape[1]) if (ops & _lib.OP_GRAD) else 3

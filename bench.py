@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--pncg-iters", type=int, default=200)
     ap.add_argument("--no-fuse", action="store_true", help="one pass per potential (the reference's structure)")
     ap.add_argument("--graph", action="store_true", help="N>1, experimental: replay each step as one CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N>1: do not overlap the halo exchange with the interior tiles (one launch, then exchange)")
     ap.add_argument("--no-pncg", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
@@ -313,7 +315,7 @@ def main():
         pots = {k: cuda_potential(k, shard.mesh, dtype, name=k) for k in kinds}
         if not args.no_fuse:
             pots = fuse_potentials(pots)
-        sharded = ShardedOperators(WarpModel(pots), shard, dev, dtype)
+        sharded = ShardedOperators(WarpModel(pots), shard, dev, dtype, overlap=not args.no_overlap)
         ud = torch.as_tensor(u[shard.l2g], dtype=dtype, device=dev).contiguous()
         pd = torch.as_tensor(p[shard.l2g], dtype=dtype, device=dev).contiguous()
         fun = torch.zeros(1, dtype=dtype, device=dev)
@@ -322,6 +324,23 @@ def main():
 
         def eager_step():
             return sharded.eval(OPS, ud, pd)
+
+        # The split evaluation (boundary tiles -> halo exchange overlapped with the interior tiles) must give
+        # what the plain sequence gives; if it does not on this box, the plain sequence is benchmarked.
+        overlap_note = None
+        if sharded.overlap:
+            r_split = eager_step()
+            sharded.overlap = False
+            r_plain = eager_step()
+            sharded.overlap = True
+            torch.cuda.synchronize()
+            err = max(float((r_split[k] - r_plain[k]).abs().max() / r_plain[k].abs().max().clamp_min(1e-30))
+                      for k in ("fun", "grad", "prod"))
+            bad = torch.tensor([1.0 if not (err < 1e-4) else 0.0], device=dev)
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+            if float(bad.item()) > 0:
+                sharded.overlap = False
+                overlap_note = f"split evaluation disagreed with the plain one (rel. err {err:.2e} on rank {rank}); disabled"
 
         # EXPERIMENTAL, opt-in (--graph): replay the step (kernels + the two NCCL collectives) as one CUDA
         # graph.  Not validated: the one attempt on 8 GPUs hung during capture, so the default is plain
@@ -485,9 +504,14 @@ def main():
                        "parallelism": (f"{world} ranks x contiguous Morton chunk of tets (~{T_total // world} tets per "
                                        f"GPU, {args.scaling} scaling); halo sum of grad+HVP (NCCL all-to-all of "
                                        f"shared rows) + scalar all-reduce per step, "
-                                       f"{'replayed as one CUDA graph' if args.graph else 'plain launches'}")
+                                       f"{'replayed as one CUDA graph' if args.graph else 'plain launches'}; "
+                                       + (f"boundary tiles ({sharded.n_boundary_tiles} on rank 0) first, exchange "
+                                          f"overlapped with the interior tiles" if sharded.overlap else
+                                          "one element launch, then the exchange") +
+                                       (f" [{overlap_note}]" if overlap_note else ""))
                        if world > 1 else "1 GPU"},
-            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": args.steps * len(pots),
+            "clocks": clocks.summary(), "e2e": e2e,
+            "gpu_launches": args.steps * len(pots) * (2 if (world > 1 and sharded.overlap) else 1),
             "roofline": roofline, "cpu_baseline": cpu, "pncg": pncg,
         }
         print(json.dumps(line))

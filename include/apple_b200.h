@@ -98,9 +98,10 @@ int apl_fem_info(const apl_fem_t* fem, int64_t info[10]);
  *   order      int64 (n_cells,)  : packed position -> caller's cell index
  *   conn       uint8 (n_cells,4) : tile-local vertex id per corner (packed order)
  *   slots      uint16(n_cells,4) : in-tile reduction slot per corner (packed order)
- *   tile_verts int32 (info[3])   : global vertex id per tile-local id (ascending), from vert_start
- *   tile_voff  uint16(info[8])   : per tile, n_verts+1 slot offsets starting at voff_start
- *   tile_vperm uint8 (info[3])   : per tile, the local ids ordered by decreasing valence */
+ *   tile_verts int32 (info[3])   : global vertex id per tile-local id, from vert_start
+ *   tile_voff  uint16(info[8])   : per tile, n_verts+1 entries starting at voff_start: bits 0..11 first slot of
+ *                                  the vertex's range (reduce order), bits 12..15 unused pad slots after it
+ *   tile_vperm uint8 (info[3])   : per tile, the local ids in reduce order (groups of 16 by decreasing valence) */
 int apl_fem_host_tables(const apl_fem_t* fem, int32_t* tiles, int64_t* order, uint8_t* conn,
                         uint16_t* slots, int32_t* tile_verts, uint16_t* tile_voff, uint8_t* tile_vperm);
 
@@ -123,6 +124,21 @@ int apl_fem_set_materials(apl_fem_t* fem, const void* dV, const void* mu, const 
 int apl_fem_eval(apl_fem_t* fem, int ops, const void* u, const void* p, int ld_in, void* fun,
                  void* quad, void* grad, void* diag, void* prod, int ld_out, int scatter,
                  void* stream);
+
+/* ---- multi-GPU overlap (no reference counterpart: the reference is single-GPU) -----------------------
+ * apl_fem_mark_boundary: tiles that touch a vertex with vertex_flags[v] != 0 (HOST array, n_points
+ * bytes; a sharded caller flags the vertices it shares with other ranks) become "boundary" tiles and
+ * their headers are moved to the front of the tile list (no element data moves).  *n_boundary receives
+ * their number.  NULL flags restore "no boundary tiles".
+ * apl_fem_eval_part: apl_fem_eval over a part of the tiles -- APL_PART_ALL, APL_PART_BOUNDARY or
+ * APL_PART_INTERIOR.  Interior tiles touch no flagged vertex, so the halo exchange of the boundary
+ * results can run while the interior pass is still accumulating.  Both parts ADD to fun / quad. */
+#define APL_PART_ALL 0
+#define APL_PART_BOUNDARY 1
+#define APL_PART_INTERIOR 2
+int apl_fem_mark_boundary(apl_fem_t* fem, const uint8_t* vertex_flags, int64_t* n_boundary);
+int apl_fem_eval_part(apl_fem_t* fem, int part, int ops, const void* u, const void* p, int ld_in, void* fun,
+                      void* quad, void* grad, void* diag, void* prod, int ld_out, int scatter, void* stream);
 
 /* ---- ExternalForce: replaces warp/potential/_ext_force.py:17-39 ------------------------------------
  * force dtype (k,3) and indices int32 (k,) are DEVICE arrays.  ops may contain FUN and/or GRAD:

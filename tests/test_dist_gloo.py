@@ -15,26 +15,56 @@ from helpers import make_case, oracle_potential
 
 
 class _OracleLocalModel:
-    """Adapts oracle potentials (numpy) to the ``eval`` interface ShardedOperators drives."""
+    """Adapts oracle potentials (numpy) to the ``eval`` interface ShardedOperators drives, including the
+    split evaluation (``mark_boundary`` / ``part``): here the boundary part is the set of CELLS touching a
+    flagged vertex (the CUDA potentials split by tiles; either way the interior part touches no flagged
+    vertex, which is the property the overlap relies on)."""
 
     def __init__(self, pots, n_points):
         from oracle import fem as ofem
 
-        self.m = ofem.Model(pots, n_points)
+        self.pots, self.n_points = pots, n_points
+        self.m = {0: ofem.Model(pots, n_points)}
 
-    def eval(self, ops, u, p=None, *, fun=None, quad=None, grad=None, diag=None, prod=None, scatter=None):
+    def mark_boundary(self, flags):
+        import copy
+
+        from oracle import fem as ofem
+
+        flags = np.asarray(flags).astype(bool)
+        parts = {1: [], 2: []}
+        n_boundary = 0
+        for pot in self.pots:
+            touch = flags[pot.cells].any(axis=1)
+            n_boundary += int(touch.sum())
+            for part, sel in ((1, touch), (2, ~touch)):
+                sub = copy.copy(pot)
+                sub.cells, sub.dhdX, sub.dV = pot.cells[sel], pot.dhdX[sel], pot.dV[sel]
+                sub.materials = {k: np.asarray(v)[sel] for k, v in pot.materials.items()}
+                parts[part].append(sub)
+        self.m[1] = ofem.Model(parts[1], self.n_points)
+        self.m[2] = ofem.Model(parts[2], self.n_points)
+        return n_boundary
+
+    def eval(self, ops, u, p=None, *, fun=None, quad=None, grad=None, diag=None, prod=None, scatter=None, part=0,
+             zero=True):
+        m = self.m[part]
         un = u.numpy()
         pn = None if p is None else p.numpy()
+        if zero:
+            for o in (fun, quad, grad, diag, prod):
+                if o is not None:
+                    o.zero_()
         if fun is not None:
-            fun += float(self.m.fun(un))
+            fun += float(m.fun(un))
         if quad is not None:
-            quad += float(self.m.hess_quad(un, pn))
+            quad += float(m.hess_quad(un, pn))
         if grad is not None:
-            grad += torch.from_numpy(self.m.grad(un))
+            grad += torch.from_numpy(m.grad(un))
         if diag is not None:
-            diag += torch.from_numpy(self.m.hess_diag(un))
+            diag += torch.from_numpy(m.hess_diag(un))
         if prod is not None:
-            prod += torch.from_numpy(self.m.hess_prod(un, pn))
+            prod += torch.from_numpy(m.hess_prod(un, pn))
 
 
 def _free_port():
@@ -43,7 +73,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, overlap):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -53,7 +83,8 @@ def _worker(rank, world, port, out):
         mesh, u, p = make_case(n=5, seed=4)
         shard = partition_mesh(mesh, world, rank)
         pots = [oracle_potential(k, shard.mesh) for k in ("snh", "arap")]
-        ops = ShardedOperators(_OracleLocalModel(pots, shard.n_local), shard, "cpu", torch.float64)
+        ops = ShardedOperators(_OracleLocalModel(pots, shard.n_local), shard, "cpu", torch.float64, overlap=overlap)
+        assert ops.overlap == overlap and (ops.n_boundary_tiles > 0) == overlap
         ul = torch.from_numpy(u[shard.l2g]).contiguous()
         pl = torch.from_numpy(p[shard.l2g]).contiguous()
         r = ops.eval(_lib.OP_FUN | _lib.OP_GRAD | _lib.OP_HESS_DIAG | _lib.OP_HESS_PROD | _lib.OP_HESS_QUAD, ul, pl)
@@ -67,11 +98,12 @@ def _worker(rank, world, port, out):
 
 
 @pytest.mark.timeout(600)
+@pytest.mark.parametrize("overlap", [False, True], ids=["serial", "split"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_sharding_matches_single_rank(world):
+def test_sharding_matches_single_rank(world, overlap):
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, overlap), nprocs=world, join=True)
     from oracle import fem as ofem
 
     mesh, u, p = make_case(n=5, seed=4)

@@ -421,3 +421,44 @@ def test_set_materials_patches_only_the_requested_columns(native_lib):
     np.testing.assert_array_equal(after, planes(b))
     assert not np.array_equal(before, after)
     native_lib.apl_fem_destroy(a); native_lib.apl_fem_destroy(b)
+
+
+def test_mark_boundary_partitions_the_tile_headers(native_lib):
+    """apl_fem_mark_boundary (multi-GPU overlap): tiles touching a flagged vertex move to the front of the
+    header list, nothing else changes -- the interior part touches no flagged vertex, the headers are a
+    permutation of the original ones, NULL flags restore a single part."""
+    from apple_b200 import _lib
+    from oracle import region
+
+    mesh, _, _ = make_case(n=9, seed=0, morton=True)
+    dhdX, dV = region.compute_grad(mesh.points, mesh.cells)
+    T, V = mesh.n_cells, mesh.n_points
+    one = np.ones(T)
+    P = _lib.host_ptr
+    h = ctypes.c_void_p()
+    cells = np.ascontiguousarray(mesh.cells, dtype=np.int32); pts = np.ascontiguousarray(mesh.points)
+    assert native_lib.apl_fem_create(0, _lib.F64, T, V, P(cells), P(dhdX), P(dV), P(one), P(one), None, P(pts), -1,
+                                     ctypes.byref(h)) == 0
+    info = (ctypes.c_int64 * 10)(); native_lib.apl_fem_info(h, info)
+    nt, nv = info[2], info[3]
+
+    def tables():
+        tiles = np.zeros((nt, 6), np.int32); tv = np.zeros(nv, np.int32)
+        native_lib.apl_fem_host_tables(h, P(tiles), None, None, None, P(tv), None, None)
+        return tiles, tv
+
+    before, tv = tables()
+    flags = np.zeros(V, np.uint8); flags[mesh.points[:, 0] == 0.0] = 1      # one face of the cube is "shared"
+    nb = ctypes.c_int64()
+    assert native_lib.apl_fem_mark_boundary(h, P(flags), ctypes.byref(nb)) == 0
+    after, tv2 = tables()
+    assert np.array_equal(tv, tv2) and 0 < nb.value < nt
+    touches = np.array([flags[tv[vs:vs + n]].any() for (_, _, vs, n, _, _) in after])
+    assert touches[:nb.value].all() and not touches[nb.value:].any()
+    assert sorted(map(tuple, before.tolist())) == sorted(map(tuple, after.tolist()))
+    # stable: each part keeps the packed (Morton) order
+    assert (np.diff(after[:nb.value, 0]) > 0).all() and (np.diff(after[nb.value:, 0]) > 0).all()
+    assert native_lib.apl_fem_mark_boundary(h, None, ctypes.byref(nb)) == 0 and nb.value == 0
+    assert np.array_equal(tables()[0], before)
+    assert native_lib.apl_fem_eval_part(h, 3, 1, None, None, 3, None, None, None, None, None, 3, 0, None) != 0  # bad part
+    native_lib.apl_fem_destroy(h)

@@ -33,6 +33,14 @@ for dtype, tol in ((torch.float64, 1e-10), (torch.float32, 1e-5)):
     idx = torch.as_tensor(shard.l2g, device=dev)
     errs = (rel_err(f.cpu(), fr.cpu()), float((g - gr[idx]).abs().max() / gr.abs().max()), float((h - hr[idx]).abs().max() / hr.abs().max()))
     good = max(errs) < 5 * tol
+    # split evaluation (boundary tiles, exchange overlapped with interior tiles) vs the plain sequence
+    assert ops.overlap and ops.n_boundary_tiles > 0
+    ops.overlap = False
+    f2, g2, h2 = ops.fun_grad_hess_prod(ul, pl)
+    ops.overlap = True
+    e2 = (rel_err(f.cpu(), f2.cpu()), float((g - g2).abs().max() / g2.abs().max()), float((h - h2).abs().max() / h2.abs().max()))
+    good = good and max(e2) < 5 * tol
+    print(f"rank {rank} {dtype} split vs plain evaluation: {e2[0]:.2e} {e2[1]:.2e} {e2[2]:.2e}, {ops.n_boundary_tiles} boundary tiles", flush=True)
     ok &= good
     print(f"rank {rank} {dtype} fused eval vs 1-GPU: energy/grad/hvp rel err {errs[0]:.2e} {errs[1]:.2e} {errs[2]:.2e} {'OK' if good else 'FAIL'}", flush=True)
 
