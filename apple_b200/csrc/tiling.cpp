@@ -149,7 +149,8 @@ struct TileScratch {
 // ---- 1. local vertex ids: balanced colouring of the gather-conflict graph -----------------------
 // tl[t][a]: provisional local id (first-touch order) of corner a of the tile's t-th tet.  Vertices read
 // by the same quarter warp for the same corner should differ in (id mod M).  new_id[provisional] is a
-// bijection onto [0, nv) with id = M * k + colour and k ascending with the global id inside a colour.
+// bijection onto [0, nv) with id = 32 w + M k + colour: w = the vertex's window of 32 in ascending global id,
+// k ascending with the global id inside a (window, colour) class.
 void color_local_ids(TileScratch& ws, int nt, int nv, const uint8_t (*tl)[4], const int32_t* gid, int M,
                      uint32_t seed, int* new_id) {
     const int nq = (nt + 7) / 8, ng = nq * 4;
@@ -179,10 +180,24 @@ void color_local_ids(TileScratch& ws, int nt, int nv, const uint8_t (*tl)[4], co
     for (int g = 0; g < ng; ++g)
         for (int k = 0; k < gsz[g]; ++k) vgrp[vptr[gmem[g][k] + 1]++] = g;
     // the groups of v are now vgrp[vptr[v] .. vptr[v+1])
-    int cap[8], used[8];
-    for (int c = 0; c < M; ++c) {
-        cap[c] = c < nv ? (nv - c + M - 1) / M : 0;
-        used[c] = 0;
+    // Windows of 32 vertices in ascending global id: lanes 32 w .. 32 w + 31 of the gather / flush loops get
+    // exactly the vertices of window w (the same global-memory lines per warp-wide access as an ascending
+    // list), and the colours are balanced inside every window: id = 32 w + M k + colour.
+    constexpr int kWin = 32, kMaxWin = (kTileVerts + kWin - 1) / kWin;
+    int win[kTileVerts];
+    {
+        int by_gid[kTileVerts];
+        for (int v = 0; v < nv; ++v) by_gid[v] = v;
+        std::sort(by_gid, by_gid + nv, [&](int a, int b) { return gid[a] < gid[b]; });
+        for (int r = 0; r < nv; ++r) win[by_gid[r]] = r / kWin;
+    }
+    int cap[kMaxWin][8], used[kMaxWin][8];
+    for (int w = 0; w < kMaxWin; ++w) {
+        const int m = std::max(0, std::min(kWin, nv - w * kWin));   // vertices in this window
+        for (int c = 0; c < M; ++c) {
+            cap[w][c] = c < m ? (m - c + M - 1) / M : 0;
+            used[w][c] = 0;
+        }
     }
     int order[kTileVerts];
     for (int v = 0; v < nv; ++v) order[v] = v;
@@ -192,28 +207,28 @@ void color_local_ids(TileScratch& ws, int nt, int nv, const uint8_t (*tl)[4], co
         const int v = order[i];
         int best = -1, best_inc = 1 << 30, best_sec = 1 << 30, best_fill = 1 << 30;
         for (int c = 0; c < M; ++c) {
-            if (used[c] >= cap[c]) continue;
+            if (used[win[v]][c] >= cap[win[v]][c]) continue;
             int inc = 0, sec = 0;
             for (int e = vptr[v]; e < vptr[v + 1]; ++e) {
                 const Banks& b = gb[vgrp[e]];
                 inc += (b.c[c] + 1 > b.m) && b.m >= 1;   // one more wavefront for this group
                 sec += b.c[c];
             }
-            const int fill = used[c] - cap[c];
+            const int fill = used[win[v]][c] - cap[win[v]][c];
             if (inc < best_inc || (inc == best_inc && (sec < best_sec || (sec == best_sec && fill < best_fill)))) {
                 best = c; best_inc = inc; best_sec = sec; best_fill = fill;
             }
         }
         col[v] = best;
-        ++used[best];
+        ++used[win[v]][best];
         for (int e = vptr[v]; e < vptr[v + 1]; ++e) {
             Banks& b = gb[vgrp[e]];
             ++b.c[best];
             b.rescan(M);
         }
     }
-    // local search: swap the colours of two vertices (class sizes are preserved) when the number of
-    // wavefronts does not grow
+    // local search: swap the colours of two vertices of one window (class sizes are preserved) when the
+    // number of wavefronts does not grow
     Lcg rng(seed);
     int stamp = 0;
     auto try_swap = [&](int v, int w) {
@@ -250,22 +265,23 @@ void color_local_ids(TileScratch& ws, int nt, int nv, const uint8_t (*tl)[4], co
             for (int i = 0; i < gsz[g] && gb[g].m > 1; ++i) {
                 const int v = gmem[g][i];
                 if (gb[g].c[col[v]] < gb[g].m) continue;
-                for (int tries = 0; tries < 16; ++tries) {
+                for (int tries = 0; tries < 24; ++tries) {
                     const int w = rng.below(nv);
-                    if (col[w] != col[v] && try_swap(v, w)) break;
+                    if (win[w] == win[v] && col[w] != col[v] && try_swap(v, w)) break;
                 }
             }
         }
         if (nbad == 0) break;
     }
-    // ids: colour classes interleaved, ascending global id inside a class
-    for (int c = 0; c < M; ++c) {
-        int members[kTileVerts], n = 0;
-        for (int v = 0; v < nv; ++v)
-            if (col[v] == c) members[n++] = v;
-        std::sort(members, members + n, [&](int a, int b) { return gid[a] < gid[b]; });
-        for (int k = 0; k < n; ++k) new_id[members[k]] = M * k + c;
-    }
+    // ids: inside a window the colour classes are interleaved, ascending global id inside a class
+    for (int w = 0; w * kWin < nv; ++w)
+        for (int c = 0; c < M; ++c) {
+            int members[kWin], n = 0;
+            for (int v = 0; v < nv; ++v)
+                if (win[v] == w && col[v] == c) members[n++] = v;
+            std::sort(members, members + n, [&](int a, int b) { return gid[a] < gid[b]; });
+            for (int k = 0; k < n; ++k) new_id[members[k]] = w * kWin + M * k + c;
+        }
 }
 
 // ---- 2. reduce order: conflict-free slot-range starts within every group of 16 vertices ------------

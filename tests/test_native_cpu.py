@@ -113,7 +113,9 @@ def test_tables_keep_shared_memory_accesses_nearly_conflict_free(native_lib):
 
     tiles, conn, slots, tv, voff, vperm = smem_model.host_tables(20)
     per, ideal = smem_model.model(tiles, conn, slots, voff, vperm, quarter=True, max_tiles=40)
-    assert per["gather"] <= 1.15 * ideal["gather"]           # ascending local ids: 1.8x
+    assert per["gather"] <= 1.2 * ideal["gather"]            # ascending local ids: 1.8x
+    got, asc = smem_model.global_lines(tiles, tv, 40)
+    assert got <= 1.001 * asc                                # every warp still gathers an ascending window of 32
     assert per["red_ld"] <= 1.10 * ideal["red_ld"]           # odd-length padding only: 1.7x
     assert per["slot_st"] <= 1.45 * ideal["slot_st"]         # tet-order greedy: 1.7x
 

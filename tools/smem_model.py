@@ -66,6 +66,27 @@ def host_tables(n):
     L.apl_fem_destroy(h)
     return tiles, conn, slots, tv, voff, vperm
 
+def global_lines(tiles, tv, max_tiles=None, row_bytes=12):
+    """Distinct 128-byte lines per warp-wide LDGSTS.32 of the producer's vertex gather (ld = 3 rows, three
+    4-byte copies per row): the global-memory side of the same LSU pipe.  Returns (lines per instruction with
+    the tables' local-id order, with an ascending vertex list)."""
+    sel = tiles if max_tiles is None else tiles[np.linspace(0, len(tiles) - 1, max_tiles).astype(int)]
+    got = asc = n = 0
+    for (ts, nt, vs, nv, vo, ns) in sel:
+        gl = tv[vs:vs + nv].astype(np.int64)
+        for order, acc in ((gl, 0), (np.sort(gl), 1)):
+            tot = 0
+            for g in range(0, nv, 32):
+                for off in (0, 4, 8):
+                    tot += len(np.unique((row_bytes * order[g:g + 32] + off) // 128))
+            if acc == 0:
+                got += tot
+            else:
+                asc += tot
+        n += 3 * ((nv + 31) // 32)
+    return got / n, asc / n
+
+
 def model(tiles, conn, slots, voff, vperm, quarter=False, max_tiles=None):
     acc = dict(static=0, gather=0, slot_st=0, red_small=0, red_ld=0, vbuf_st=0, flush_ld=0)
     ideal = dict(acc)
@@ -131,3 +152,5 @@ if __name__ == "__main__":
     st = per["slot_st"] + per["vbuf_st"]
     for k in per: print(f"{k:10s} {per[k]:7.2f}   ideal {ideal[k]:7.2f}")
     print(f"ld {ld:.1f} (ncu 143)  st {st:.1f} (ncu 56)   per 32 tets")
+    got, asc = global_lines(tiles, tv, a.tiles)
+    print(f"global side: {got:.2f} lines per warp-wide LDGSTS.32 of the vertex gather (ascending list: {asc:.2f})")
