@@ -329,18 +329,23 @@ def main():
         # what the plain sequence gives; if it does not on this box, the plain sequence is benchmarked.
         overlap_note = None
         if sharded.overlap:
-            r_split = eager_step()
+            try:
+                r_split = eager_step()
+            except Exception as exc:  # pragma: no cover - a host-side error is the same on every rank
+                r_split, overlap_note = None, f"split evaluation failed ({type(exc).__name__}: {exc}); disabled"
             sharded.overlap = False
             r_plain = eager_step()
-            sharded.overlap = True
+            sharded.overlap = r_split is not None
             torch.cuda.synchronize()
-            err = max(float((r_split[k] - r_plain[k]).abs().max() / r_plain[k].abs().max().clamp_min(1e-30))
-                      for k in ("fun", "grad", "prod"))
+            err = float("inf") if r_split is None else max(
+                float((r_split[k] - r_plain[k]).abs().max() / r_plain[k].abs().max().clamp_min(1e-30))
+                for k in ("fun", "grad", "prod"))
             bad = torch.tensor([1.0 if not (err < 1e-4) else 0.0], device=dev)
             dist.all_reduce(bad, op=dist.ReduceOp.MAX)
             if float(bad.item()) > 0:
                 sharded.overlap = False
-                overlap_note = f"split evaluation disagreed with the plain one (rel. err {err:.2e} on rank {rank}); disabled"
+                overlap_note = overlap_note or (f"split evaluation disagreed with the plain one on some rank (rel. err "
+                                                f"{err:.2e} on rank 0); disabled")
 
         # EXPERIMENTAL, opt-in (--graph): replay the step (kernels + the two NCCL collectives) as one CUDA
         # graph.  Not validated: the one attempt on 8 GPUs hung during capture, so the default is plain
