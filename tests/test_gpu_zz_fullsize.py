@@ -137,4 +137,4 @@ def test_full_size_pncg_iterations_decrease_the_energy(native_lib, config2):
         assert opt.n_steps == 200 and opt.n_accepted >= 190
         assert opt.relative_grad_norm < 0.05
         runs[mode] = energies
-    assert abs(runs[2][0] - runs[0][0]) <= 1e-3 * abs(runs[0][0])      # same trajectory after 20 iterations
+    assert abs(runs[2][0] - runs[0][0]) <= 5e-3 * abs(runs[0][0])      # same trajectory after 20 iterations
