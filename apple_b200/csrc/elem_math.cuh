@@ -572,14 +572,16 @@ APL_HD void polar_twist(const T* F, T* R, T* L, T* sg) {
     S[3] = kc * C[3] - inv_den * (C[0] * C[3] + C[3] * C[1] + C[4] * C[5]);
     S[4] = kc * C[4] - inv_den * (C[0] * C[4] + C[3] * C[5] + C[4] * C[2]);
     S[5] = kc * C[5] - inv_den * (C[3] * C[4] + C[1] * C[5] + C[5] * C[2]);
-    // R = (I1 F - F S + cof F) / I2
+    // R = (I1 F - F S + cof F) / I2 = F (M / I2) + cof F / I2 with M = I1 - S
     const T inv_I2 = apl_rcp(I2);
+    const T N0 = (I1 - S[0]) * inv_I2, N1 = (I1 - S[1]) * inv_I2, N2 = (I1 - S[2]) * inv_I2;
+    const T N3 = -S[3] * inv_I2, N4 = -S[4] * inv_I2, N5 = -S[5] * inv_I2;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const T f0 = F[3 * i], f1 = F[3 * i + 1], f2 = F[3 * i + 2];
-        R[3 * i + 0] = (I1 * f0 - (f0 * S[0] + f1 * S[3] + f2 * S[4]) + cof[3 * i + 0]) * inv_I2;
-        R[3 * i + 1] = (I1 * f1 - (f0 * S[3] + f1 * S[1] + f2 * S[5]) + cof[3 * i + 1]) * inv_I2;
-        R[3 * i + 2] = (I1 * f2 - (f0 * S[4] + f1 * S[5] + f2 * S[2]) + cof[3 * i + 2]) * inv_I2;
+        R[3 * i + 0] = cof[3 * i + 0] * inv_I2 + f0 * N0 + f1 * N3 + f2 * N4;
+        R[3 * i + 1] = cof[3 * i + 1] * inv_I2 + f0 * N3 + f1 * N1 + f2 * N5;
+        R[3 * i + 2] = cof[3 * i + 2] * inv_I2 + f0 * N4 + f1 * N5 + f2 * N2;
     }
     // Lam = f(M), M = I1 - S, eigenvalues m = (s1 + s2) <= (s0 + s2) <= (s0 + s1), f(m) = 2 / max(m, 2).
     // Newton form on the nodes (a, b, c) = (isolated end, other end, middle):
