@@ -466,8 +466,10 @@ def main():
             fh.zero_(); gh.zero_(); hh.zero_()
             tt_streamed = time_e2e(step_streamed)
             err = max(float((x - y).abs().max() / y.abs().max()) for x, y in zip((fh, gh, hh), ref))
-            if err < 1e-4:
+            if err < 1e-4 and tt_streamed <= tt_serial:
                 api, tt, launches = "streamed", tt_streamed, 2 * len(pots)
+            elif err < 1e-4:
+                note = f"streamed entry point verified but slower here ({tt_streamed / args.steps:.4f} ms per step); serial number reported"
             else:
                 note = f"streamed entry point disagreed with the serial one (rel. err {err:.2e}); serial number reported"
         except Exception as exc:  # pragma: no cover - robustness of the benchmark line
