@@ -4,6 +4,8 @@ import torch
 
 from apple_b200 import _lib
 
+from apple_b200.warp.model._adapter import zeros_block
+
 from ._halo import HaloExchange
 from ._partition import Shard
 
@@ -43,15 +45,11 @@ class ShardedOperators:
         n = self.n_local
         names = [k for k, bit in (("grad", _lib.OP_GRAD), ("diag", _lib.OP_HESS_DIAG), ("prod", _lib.OP_HESS_PROD)) if ops & bit]
         snames = [k for k, bit in (("fun", _lib.OP_FUN), ("quad", _lib.OP_HESS_QUAD)) if ops & bit]
-        out = {}
-        if names:   # one allocation + one memset for all fields
-            block = torch.zeros((len(names), n, 3), dtype=self.dtype, device=self.device)
-            for i, k in enumerate(names):
-                out[k] = block[i]
-        scal = torch.zeros(max(len(snames), 1), dtype=self.dtype, device=self.device)
-        for i, k in enumerate(snames):
-            out[k] = scal[i:i + 1]
-        fields = [out[k] for k in names]
+        # one allocation + one memset for all outputs; every field starts at a multiple of 16 bytes
+        buf, fields, scalars = zeros_block(n, len(names), len(snames), self.dtype, self.device)
+        out = dict(zip(names, fields))
+        out.update(zip(snames, scalars))
+        scal = buf[buf.numel() - max(len(snames), 1):]     # the scalars are contiguous at the end of the block
         kw = {"zero": False} if self._split else {}    # the outputs above are already zero
         if self.overlap and fields:
             self.model.eval(ops, u, p, part=_lib.PART_BOUNDARY, **out, **kw)

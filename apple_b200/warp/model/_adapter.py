@@ -7,6 +7,17 @@ from apple_b200 import _lib
 from ._model import WarpModel
 
 
+def zeros_block(n_points: int, n_fields: int, n_scalars: int, dtype: torch.dtype, device):
+    """One allocation holding ``n_fields`` nodal fields ``(n_points, 3)`` (each starting at a multiple of 16
+    bytes, as the vector REDs of the kernels require) followed by ``n_scalars`` one-element tensors.  Zeroing
+    the outputs of a fused evaluation is then ONE memset (``buf.zero_()``) instead of one per output."""
+    stride = (3 * n_points + 3) // 4 * 4
+    buf = torch.zeros(n_fields * stride + max(n_scalars, 1), dtype=dtype, device=device)
+    fields = [buf[k * stride:k * stride + 3 * n_points].view(n_points, 3) for k in range(n_fields)]
+    scalars = [buf[n_fields * stride + k:n_fields * stride + k + 1] for k in range(n_scalars)]
+    return buf, fields, scalars
+
+
 class WarpModelAdapter:
     """Pure-function view of a ``WarpModel``, ``warp/model/_adapter.py:16-140``.
 
@@ -58,9 +69,10 @@ class WarpModelAdapter:
     def fun_grad_hess_prod(self, u: torch.Tensor, p: torch.Tensor, *, scatter=None):
         """(energy, gradient, Hessian-vector product): the fused evaluation of the headline metric."""
         u, p = u.contiguous(), p.contiguous()
-        fun, grad, prod = self._scalar(u), self._field(u), self._field(u)
+        _, (grad, prod), (fun,) = zeros_block(self.n_points, 2, 1, u.dtype, u.device)   # one memset for all outputs
         self.__wrapped__.eval(
-            _lib.OP_FUN | _lib.OP_GRAD | _lib.OP_HESS_PROD, u, p, fun=fun, grad=grad, prod=prod, scatter=scatter
+            _lib.OP_FUN | _lib.OP_GRAD | _lib.OP_HESS_PROD, u, p, fun=fun, grad=grad, prod=prod, scatter=scatter,
+            zero=False,
         )
         return fun[0], grad, prod
 
@@ -98,7 +110,9 @@ class WarpModelAdapter:
             ev_p = s_in.record_event()
         with torch.cuda.device(dev):
             cur.wait_event(ev_u)
-            model.eval(_lib.OP_FUN | _lib.OP_GRAD, st["u"], None, fun=st["fun"], grad=st["grad"], scatter=scatter)
+            st["block_a"].zero_()
+            model.eval(_lib.OP_FUN | _lib.OP_GRAD, st["u"], None, fun=st["fun"], grad=st["grad"], scatter=scatter,
+                       zero=False)
             s_out.wait_stream(cur)
             with torch.cuda.stream(s_out):
                 grad_h.copy_(st["grad"], non_blocking=True)
@@ -120,9 +134,9 @@ class WarpModelAdapter:
                 raise _lib.NativeError("fun_grad_hess_prod_host needs a model on a CUDA device (there is no CPU path)")
             n = self.n_points
             field = lambda: torch.empty((n, 3), dtype=dtype, device=dev)  # noqa: E731
+            block_a, (grad,), (fun,) = zeros_block(n, 1, 1, dtype, dev)   # outputs of the first pass: one memset
             cache[dtype] = {
-                "device": dev, "u": field(), "p": field(), "grad": field(), "prod": field(),
-                "fun": torch.empty(1, dtype=dtype, device=dev),
+                "device": dev, "u": field(), "p": field(), "grad": grad, "prod": field(), "fun": fun, "block_a": block_a,
                 "s_in": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
                 "out": (torch.empty(1, dtype=dtype).pin_memory(), torch.empty((n, 3), dtype=dtype).pin_memory(),
                         torch.empty((n, 3), dtype=dtype).pin_memory()),
@@ -132,8 +146,9 @@ class WarpModelAdapter:
     def fun_grad_hess_diag(self, u: torch.Tensor, *, scatter=None):
         """(energy, gradient, Hessian diagonal): PNCG's pass A."""
         u = u.contiguous()
-        fun, grad, diag = self._scalar(u), self._field(u), self._field(u)
+        _, (grad, diag), (fun,) = zeros_block(self.n_points, 2, 1, u.dtype, u.device)
         self.__wrapped__.eval(
-            _lib.OP_FUN | _lib.OP_GRAD | _lib.OP_HESS_DIAG, u, None, fun=fun, grad=grad, diag=diag, scatter=scatter
+            _lib.OP_FUN | _lib.OP_GRAD | _lib.OP_HESS_DIAG, u, None, fun=fun, grad=grad, diag=diag, scatter=scatter,
+            zero=False,
         )
         return fun[0], grad, diag

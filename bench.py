@@ -299,12 +299,13 @@ def main():
         adapter = WarpModelAdapter(model, n_points=V)
         ud = torch.as_tensor(u, dtype=dtype, device=dev).contiguous()
         pd = torch.as_tensor(p, dtype=dtype, device=dev).contiguous()
-        fun = torch.zeros(1, dtype=dtype, device=dev)
-        grad = torch.zeros((V, 3), dtype=dtype, device=dev)
-        prod = torch.zeros((V, 3), dtype=dtype, device=dev)
+        from apple_b200.warp.model._adapter import zeros_block
+
+        out_block, (grad, prod), (fun,) = zeros_block(V, 2, 1, dtype, dev)   # all outputs of a step in one buffer
 
         def step():
-            model.eval(OPS, ud, pd, fun=fun, grad=grad, prod=prod)
+            out_block.zero_()      # the operators accumulate (warp/model/_model.py:13-36 zeroes first): one memset
+            model.eval(OPS, ud, pd, fun=fun, grad=grad, prod=prod, zero=False)
     else:
         # strong scaling: rank r owns a contiguous chunk of the Morton-ordered tets and a local copy of
         # the vertices they touch; one halo sum (all-to-all of the shared rows) + one scalar all-reduce

@@ -139,3 +139,25 @@ def test_pcg_solves_the_hessian_system_of_the_oracle():
     _, plain = pcg(lambda v: torch.from_numpy(matvec_np(v.numpy())), torch.from_numpy(b), None, tol=1e-10,
                    maxiter=8 * n, check_every=5)
     assert plain.n_iters >= info.n_iters
+
+
+def test_zeros_block_keeps_every_field_16_byte_aligned():
+    """Outputs of a fused evaluation share one allocation (one memset); the kernels' vector REDs need every
+    nodal field to start at a multiple of 16 bytes."""
+    import torch
+
+    from apple_b200.warp.model._adapter import zeros_block
+
+    for dtype in (torch.float32, torch.float64):
+        for n in (1, 5, 205_379):
+            buf, fields, scalars = zeros_block(n, 3, 2, dtype, "cpu")
+            assert len(fields) == 3 and len(scalars) == 2
+            for f in fields:
+                assert f.shape == (n, 3) and f.is_contiguous() and f.data_ptr() % 16 == 0
+            ends = [f.data_ptr() + f.numel() * f.element_size() for f in fields]
+            assert all(e <= nxt.data_ptr() for e, nxt in zip(ends, fields[1:] + [scalars[0]]))   # disjoint, ordered
+            assert scalars[1].data_ptr() == scalars[0].data_ptr() + buf.element_size()
+            fields[1].fill_(1.0); scalars[0].fill_(2.0)
+            assert float(buf.sum()) == 3.0 * n + 2.0 and float(fields[0].sum()) == 0.0
+            buf.zero_()
+            assert float(fields[1].abs().sum()) == 0.0 and float(scalars[0]) == 0.0
