@@ -512,6 +512,17 @@ int apl_fem_eval_part(apl_fem_t* f, int part, int ops, const void* u, const void
         set_error("apl_fem_eval: an array required by `ops` is NULL");
         return APL_ERR_INVALID;
     }
+    {   // vector accesses of the kernels: 16-byte rows for ld = 4, 8-byte vector REDs for fp32 ld = 3
+        const uintptr_t in_mask = ld_in == 4 ? 15u : 0u;
+        const uintptr_t out_mask = ld_out == 4 ? 15u : 7u;
+        auto bad = [](const void* ptr, uintptr_t mask) { return ptr && ((uintptr_t)ptr & mask) != 0; };
+        if (bad(u, in_mask) || ((ops & (APL_OP_HESS_PROD | APL_OP_HESS_QUAD)) && bad(p, in_mask)) ||
+            ((ops & APL_OP_GRAD) && bad(grad, out_mask)) || ((ops & APL_OP_HESS_DIAG) && bad(diag, out_mask)) ||
+            ((ops & APL_OP_HESS_PROD) && bad(prod, out_mask))) {
+            set_error("apl_fem_eval: nodal fields must be 16-byte aligned for ld = 4 and outputs 8-byte aligned for ld = 3");
+            return APL_ERR_INVALID;
+        }
+    }
     cudaStream_t s = (cudaStream_t)stream;
     return f->dtype == APL_F32
                ? eval_typed<float>(f, ops, u, p, ld_in, fun, quad, grad, diag, prod, ld_out, scatter, s, nullptr, part)

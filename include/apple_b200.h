@@ -12,7 +12,8 @@
  *    is dtype-generic through the JAX x64 flag, warp/fem/_base.py:100-104).
  *  - Nodal fields (u, p, grad, diag, prod) are device arrays of n_points rows with a leading
  *    dimension `ld` of 3 (the reference's vec3 arrays) or 4 (16-byte padded rows; the 4th column is
- *    ignored on input and receives +0 on output).  ld == 4 arrays must be 16-byte aligned.
+ *    ignored on input and receives +0 on output).  ld == 4 arrays must be 16-byte aligned, ld == 3
+ *    OUTPUT arrays 8-byte aligned (vector reductions); misaligned pointers are rejected.
  *  - Operators ACCUMULATE into caller-zeroed outputs, exactly like WarpPotential
  *    (warp/model/_potential.py:19-32; zeroing by the caller, warp/model/_model.py:14,19,24,29,34).
  *  - Calls are stream-ordered on `stream` (a cudaStream_t passed as void*; NULL = legacy default
