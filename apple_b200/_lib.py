@@ -29,6 +29,7 @@ S_SUMS, S_ALPHA_J, S_ACC_J, S_FT_J = 20, 32, 48, 64
 
 # every symbol include/apple_b200.h declares: name -> (restype, argtypes)
 PART_ALL, PART_BOUNDARY, PART_INTERIOR = 0, 1, 2
+LAYOUT_TET, LAYOUT_PAIR = 0, 1
 
 SIGNATURES = {
     "apl_version": (c_int, []),
@@ -41,6 +42,9 @@ SIGNATURES = {
     "apl_fem_destroy": (None, [c_void_p]),
     "apl_fem_info": (c_int, [c_void_p, POINTER(c_int64)]),
     "apl_fem_host_tables": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "apl_set_layout": (c_int, [c_int]),
+    "apl_fem_layout": (c_int, [c_void_p]),
+    "apl_fem_host_corner_tables": (c_int, [c_void_p, c_void_p, c_void_p]),
     "apl_fem_host_planes": (c_int, [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64)]),
     "apl_fem_set_materials": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "apl_fem_eval": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include <cmath>
 #include <cstring>
@@ -24,11 +25,13 @@ template <typename T>
 static int pack_planes(apl_fem* f, const T* dhdX, const T* dV, const T* mu, const T* la, const T* act,
                        const T* dV2, const T* mu2, std::vector<T>& planes) {
     constexpr int VEC = 16 / (int)sizeof(T);
-    const int64_t n = f->host.n_cells;
+    const int64_t n = f->host.n_packed();
     const int nrec = f->nrec;
     planes.assign((size_t)f->nplanes * f->plane_stride * VEC, (T)0);
     for (int64_t pos = 0; pos < n; ++pos) {
         const int64_t c = f->host.order[(size_t)pos];
+        const unsigned cp = f->host.cperm[(size_t)pos];      // corner order of the packed record
+        const bool clone = f->host.clone[(size_t)pos] != 0;  // zero-volume copy: contributes nothing
         T rec[20] = {0};
         if (dhdX) {
             const T* d = dhdX + 12 * c;
@@ -43,15 +46,19 @@ static int pack_planes(apl_fem* f, const T* dhdX, const T* dV, const T* mu, cons
                           " do not sum to zero (only linear tetrahedra are supported)");
                 return APL_ERR_MESH;
             }
-            for (int k = 0; k < 9; ++k) rec[k] = d[3 + k];
+            // rows 1..3 of dhdX in the packed corner order (row 0 is minus their sum for ANY corner order)
+            for (int a = 1; a < 4; ++a) {
+                const int src = (int)((cp >> (2 * a)) & 3u);
+                for (int J = 0; J < 3; ++J) rec[3 * (a - 1) + J] = d[3 * src + J];
+            }
         }
-        rec[9] = dV ? dV[c] : (T)0;
+        rec[9] = (dV && !clone) ? dV[c] : (T)0;
         rec[10] = mu ? mu[c] : (T)0;
         rec[11] = la ? la[c] : (T)0;
         if (act)
             for (int k = 0; k < 6; ++k) rec[12 + k] = act[6 * c + k];
         if (f->kind == APL_KIND_SNH_ARAP) {  // second potential on the same cells
-            rec[12] = dV2 ? dV2[c] : (T)0;
+            rec[12] = (dV2 && !clone) ? dV2[c] : (T)0;
             rec[13] = mu2 ? mu2[c] : (T)0;
         }
         for (int k = 0; k < nrec; ++k) {
@@ -279,6 +286,8 @@ int ext_force_pncg(int dtype, int ops, int64_t k, const void* force, const int32
 
 using namespace apl;
 
+static std::atomic<int> g_default_layout{APL_LAYOUT_TET};
+
 extern "C" {
 
 int apl_version(void) { return 100; }
@@ -333,9 +342,9 @@ static int fem_create_impl(int kind, int dtype, int64_t n_cells, int64_t n_point
     f->nrec = rec_size(kind);
     const int vec = dtype == APL_F32 ? 4 : 2;
     f->nplanes = (f->nrec + vec - 1) / vec;
-    int rc = build_tiles(n_cells, n_points, cells, points, dtype == APL_F32 ? 4 : 8, f->host);
+    int rc = build_tiles(n_cells, n_points, cells, points, dtype == APL_F32 ? 4 : 8, g_default_layout.load(), f->host);
     if (rc != APL_OK) { delete f; return rc; }
-    f->plane_stride = (n_cells + 31) / 32 * 32;
+    f->plane_stride = (f->host.n_packed() + 31) / 32 * 32;
     if (f->plane_stride == 0) f->plane_stride = 32;
     const HostTables& h = f->host;
     const size_t plane_bytes = (size_t)f->nplanes * f->plane_stride * 16;
@@ -426,7 +435,25 @@ int apl_fem_info(const apl_fem_t* f, int64_t info[10]) {
     info[6] = f->dtype;
     info[7] = f->device;
     info[8] = (int64_t)f->host.tile_voff.size();
-    info[9] = 0;
+    info[9] = f->host.n_packed();
+    return APL_OK;
+}
+
+int apl_set_layout(int layout) {
+    if (layout != APL_LAYOUT_TET && layout != APL_LAYOUT_PAIR) { set_error("apl_set_layout: unknown layout"); return APL_ERR_INVALID; }
+    g_default_layout.store(layout);
+    return APL_OK;
+}
+
+int apl_fem_layout(const apl_fem_t* f) {
+    if (!f) { set_error("apl_fem_layout: NULL handle"); return APL_ERR_INVALID; }
+    return f->host.layout;
+}
+
+int apl_fem_host_corner_tables(const apl_fem_t* f, uint8_t* cperm, uint8_t* clone) {
+    if (!f) { set_error("apl_fem_host_corner_tables: NULL handle"); return APL_ERR_INVALID; }
+    if (cperm) memcpy(cperm, f->host.cperm.data(), f->host.cperm.size());
+    if (clone) memcpy(clone, f->host.clone.data(), f->host.clone.size());
     return APL_OK;
 }
 
@@ -477,9 +504,9 @@ int apl_fem_set_materials(apl_fem_t* f, const void* dV, const void* mu, const vo
         memcpy(buf.data() + (((size_t)plane * f->plane_stride + pos) * vec + lane) * esz,
                (const unsigned char*)src + (size_t)idx * esz, esz);
     };
-    for (int64_t pos = 0; pos < f->host.n_cells; ++pos) {
+    for (int64_t pos = 0; pos < f->host.n_packed(); ++pos) {
         const int64_t c = f->host.order[(size_t)pos];
-        if (dV) put(9, pos, dV, c);
+        if (dV && !f->host.clone[(size_t)pos]) put(9, pos, dV, c);
         if (mu) put(10, pos, mu, c);
         if (lambda_ && f->kind != APL_KIND_ARAP) put(11, pos, lambda_, c);
         if (activation && f->kind == APL_KIND_SNH_MUSCLE)

@@ -377,13 +377,13 @@ __device__ __forceinline__ void tile_compute(const T* rec, uchar4 lc, ushort4 s4
 // parks the 3*NOUT sums in the vertex buffer at the vertex's ascending local id.  The 16 lanes of a
 // half warp handle 16 consecutive vertices whose ranges are an odd number of slots apart, so their
 // 16- and 8-byte reads hit distinct banks.
-template <typename T, int OPS>
+template <typename T, int OPS, int NT = kTileTets>
 __device__ __forceinline__ void tile_reduce(int tid, int n_verts, const unsigned char* vperm,
                                             const unsigned short* voff, const T* sl, T* vbuf) {
     using Cfg = TileCfg<T, OPS>;
     constexpr int NOUT = Cfg::NOUT, SS = Cfg::SS;
     const int half = (tid >> 4) & 1;
-    for (int t = (tid >> 5) * 16 + (tid & 15); t < ((n_verts + 15) & ~15); t += kTileTets / 2) {
+    for (int t = (tid >> 5) * 16 + (tid & 15); t < ((n_verts + 15) & ~15); t += NT / 2) {   // NT consumer threads
         // (the bound is rounded up to 16 so that whole warps stay together for the shuffle below;
         //  out-of-range lanes have cnt = 0)
         int v = 0, s0 = 0, cnt = 0;
@@ -439,6 +439,88 @@ __device__ __forceinline__ void tile_flush(int tid, int n_verts, int gv, const T
         if constexpr (Cfg::kProd) { if (a.prod) red_row(a.prod, gv, a.ld_out, acc + k); k += 3; }
     }
 }
+
+// PAIR layout: one consumer thread evaluates two tets that share a face.  conn5 / slots5: the shared face
+// (s0, s1, s2), the apex of the first and the apex of the second tet; both records are packed in the corner order
+// (s0, s1, s2, apex), so the contributions of the three shared corners are added in registers and the pair
+// gathers 5 vertices and writes 5 slots instead of 8.
+template <typename T, int KIND, int OPS>
+__device__ __forceinline__ void tile_compute_pair(const T* recA, const T* recB, uint2 c8, uint4 s8, const T* us,
+                                                  const T* ps, bool axpy, T alpha, T* sl, double& e_acc, double& q_acc) {
+    using Cfg = TileCfg<T, OPS>;
+    constexpr int NOUT = Cfg::NOUT, SS = Cfg::SS;
+    const int l[5] = {(int)(c8.x & 0xffu), (int)((c8.x >> 8) & 0xffu), (int)((c8.x >> 16) & 0xffu), (int)(c8.x >> 24),
+                      (int)(c8.y & 0xffu)};
+    T U[5][3], P[5][3];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        T tmp[4];
+        load_slot<T, 4>(us + 4 * l[c], tmp);
+        U[c][0] = tmp[0]; U[c][1] = tmp[1]; U[c][2] = tmp[2];
+        if constexpr (Cfg::kNeedP) {
+            load_slot<T, 4>(ps + 4 * l[c], tmp);
+            P[c][0] = tmp[0]; P[c][1] = tmp[1]; P[c][2] = tmp[2];
+        } else {
+            if (axpy) {  // line-search trial point x + alpha p
+                load_slot<T, 4>(ps + 4 * l[c], tmp);
+                U[c][0] += alpha * tmp[0]; U[c][1] += alpha * tmp[1]; U[c][2] += alpha * tmp[2];
+            }
+        }
+    }
+    const int sidx[5] = {(int)(s8.x & 0xffffu), (int)(s8.x >> 16), (int)(s8.y & 0xffffu), (int)(s8.y >> 16),
+                         (int)(s8.z & 0xffffu)};
+    // packs corner c of one evaluation into a slot value
+    auto pack = [&](const T (*g)[3], const T (*dg)[3], const T (*hp)[3], int c, T* v) {
+        int k = 0;
+        if constexpr (Cfg::kGrad) { v[k] = g[c][0]; v[k + 1] = g[c][1]; v[k + 2] = g[c][2]; k += 3; }
+        if constexpr (Cfg::kDiag) { v[k] = dg[c][0]; v[k + 1] = dg[c][1]; v[k + 2] = dg[c][2]; k += 3; }
+        if constexpr (Cfg::kProd) { v[k] = hp[c][0]; v[k + 1] = hp[c][1]; v[k + 2] = hp[c][2]; k += 3; }
+#pragma unroll
+        for (int j = 3 * NOUT; j < SS; ++j) v[j] = (T)0;
+    };
+    T shared_v[3][SS > 0 ? SS : 1];
+    {   // first tet: corners (s0, s1, s2, apex A)
+        T psi = 0, quad = 0;
+        T g[4][3], dg[4][3], hp[4][3];
+        elem_eval<T, KIND, OPS>(recA, U, P, psi, quad, g, dg, hp);   // rows 0..3 of U / P
+        if constexpr (Cfg::kFun) e_acc += (double)psi;
+        if constexpr (Cfg::kQuad) q_acc += (double)quad;
+        if constexpr (NOUT > 0) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) pack(g, dg, hp, c, shared_v[c]);
+            T v[SS];
+            pack(g, dg, hp, 3, v);
+            store_slot_planes<T, SS>(sl, sidx[3], v);
+        }
+    }
+    {   // second tet: corners (s0, s1, s2, apex B)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            U[3][i] = U[4][i];
+            if constexpr (Cfg::kNeedP) P[3][i] = P[4][i];
+        }
+        T psi = 0, quad = 0;
+        T g[4][3], dg[4][3], hp[4][3];
+        elem_eval<T, KIND, OPS>(recB, U, P, psi, quad, g, dg, hp);
+        if constexpr (Cfg::kFun) e_acc += (double)psi;
+        if constexpr (Cfg::kQuad) q_acc += (double)quad;
+        if constexpr (NOUT > 0) {
+            T v[SS];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                pack(g, dg, hp, c, v);
+#pragma unroll
+                for (int j = 0; j < 3 * NOUT; ++j) v[j] += shared_v[c][j];
+                store_slot_planes<T, SS>(sl, sidx[c], v);
+            }
+            pack(g, dg, hp, 3, v);
+            store_slot_planes<T, SS>(sl, sidx[4], v);
+        }
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void consumer_sync_n() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
 // ---- TILE kernel, unpipelined (APL_SCATTER_TILE_SIMPLE) ---------------------------------------------
 
@@ -577,9 +659,13 @@ __device__ __forceinline__ void gather_row_async(unsigned dst, const T* base, in
 
 constexpr int kPipeThreads = kTileTets + 32;
 
-template <typename T, int KIND, int OPS>
+template <typename T, int KIND, int OPS, int LAYOUT = APL_LAYOUT_TET>
 struct PipeCfg {
     using Cfg = TileCfg<T, OPS>;
+    // consumer threads: one per tet, or one per pair of tets (the stage layout is the same: a pair item
+    // has 8 bytes of connectivity and 16 bytes of slot ids, i.e. 4 and 8 bytes per tet as in the TET layout)
+    static constexpr int kConsumers = LAYOUT == APL_LAYOUT_PAIR ? kTileTets / 2 : kTileTets;
+    static constexpr int kThreads = kConsumers + 32;
     static constexpr int NREC = RecSize<KIND>::value;
     static constexpr int NPL = Rec<T, NREC>::NPL;
     // one stage: per-tet static data + the gathered vertex fields (all offsets multiples of 16 bytes)
@@ -614,12 +700,14 @@ struct PipeCfg {
     static constexpr int kMinCtas = kSmemCtas < 1 ? 1 : (kSmemCtas < kWantCtas ? kSmemCtas : kWantCtas);
 };
 
-template <typename T, int KIND, int OPS>
-__global__ void __launch_bounds__(kPipeThreads, PipeCfg<T, KIND, OPS>::kMinCtas)
+template <typename T, int KIND, int OPS, int LAYOUT = APL_LAYOUT_TET>
+__global__ void __launch_bounds__(PipeCfg<T, KIND, OPS, LAYOUT>::kThreads, PipeCfg<T, KIND, OPS, LAYOUT>::kMinCtas)
     fem_pipe_kernel(const FemArgs<T> a) {
     using Cfg = TileCfg<T, OPS>;
-    using PC = PipeCfg<T, KIND, OPS>;
+    using PC = PipeCfg<T, KIND, OPS, LAYOUT>;
     constexpr int NOUT = Cfg::NOUT;
+    constexpr int NC = PC::kConsumers;             // consumer threads (warps 0 .. NC/32 - 1), producer = warp NC/32
+    constexpr bool kPair = LAYOUT == APL_LAYOUT_PAIR;
     constexpr int S = PC::kStages, SV = PC::kVring;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // [0,128): mbarriers full[S], empty[S], vfull[SV];  slot buffer;  SV vertex-table slots;  S stages
@@ -644,7 +732,7 @@ __global__ void __launch_bounds__(kPipeThreads, PipeCfg<T, KIND, OPS>::kMinCtas)
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(full(s), 33);          // 32 gather lanes + the expect_tx arrival
-            mbar_init(empty(s), kTileTets);  // every consumer thread releases the stage
+            mbar_init(empty(s), NC);         // every consumer thread releases the stage
         }
         for (int s = 0; s < SV; ++s) mbar_init(vfull(s), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -653,7 +741,7 @@ __global__ void __launch_bounds__(kPipeThreads, PipeCfg<T, KIND, OPS>::kMinCtas)
 
     const int my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-    if (warp == kTileTets / 32) {
+    if (warp == NC / 32) {
         // ================================= producer warp =================================
         // Iteration `it`: wait until stage it % S is free, issue the bulk copies of tile `it`'s static
         // data, request the vertex tables of tile `it + 1`, then gather tile `it`'s vertices (its
@@ -740,7 +828,22 @@ __global__ void __launch_bounds__(kPipeThreads, PipeCfg<T, KIND, OPS>::kMinCtas)
 #ifdef APL_PROFILE_KNOBS
             if (g_knobs & 32) { mbar_arrive(empty(s)); continue; }
 #endif
-            if (tid < n_tets) {
+            if constexpr (kPair) {
+                const int n_items = n_tets >> 1;   // item i: packed tets i and n_items + i of the tile
+                if (tid < n_items) {
+                    Rec<T, PC::NREC> ra, rb;
+#pragma unroll
+                    for (int k = 0; k < PC::NPL; ++k) {
+                        const uint4* pl = reinterpret_cast<const uint4*>(st + PC::oPlanes + (size_t)k * kTileTets * 16);
+                        ra.q[k] = pl[tid];
+                        rb.q[k] = pl[n_items + tid];
+                    }
+                    const uint2 c8 = reinterpret_cast<const uint2*>(st + PC::oConn)[tid];
+                    uint4 s8 = make_uint4(0u, 0u, 0u, 0u);
+                    if constexpr (NOUT > 0) s8 = reinterpret_cast<const uint4*>(st + PC::oSlots)[tid];
+                    tile_compute_pair<T, KIND, OPS>(ra.s, rb.s, c8, s8, us, ps, axpy, alpha, sl, e_acc, q_acc);
+                }
+            } else if (tid < n_tets) {
                 Rec<T, PC::NREC> rec;
 #pragma unroll
                 for (int k = 0; k < PC::NPL; ++k)
@@ -754,21 +857,26 @@ __global__ void __launch_bounds__(kPipeThreads, PipeCfg<T, KIND, OPS>::kMinCtas)
 #ifdef APL_PROFILE_KNOBS
                 if (!(g_knobs & 16))
 #endif
-                consumer_sync();
-                tile_reduce<T, OPS>(tid, n_verts, vt + PC::oVperm, reinterpret_cast<const unsigned short*>(vt + PC::oVoff),
-                                    sl, vbuf);
+                consumer_sync_n<NC>();
+                tile_reduce<T, OPS, NC>(tid, n_verts, vt + PC::oVperm, reinterpret_cast<const unsigned short*>(vt + PC::oVoff),
+                                        sl, vbuf);
 #ifdef APL_PROFILE_KNOBS
                 if (!(g_knobs & 16))
 #endif
-                consumer_sync();
-                const int gv = tid < n_verts ? reinterpret_cast<const int*>(vt + PC::oVerts)[tid] : 0;
-                tile_flush<T, OPS>(tid, n_verts, gv, vbuf, a);
+                consumer_sync_n<NC>();
+                if constexpr (kPair) {   // fewer consumer threads than a tile may have vertices
+                    for (int v = tid; v < n_verts; v += NC)
+                        tile_flush<T, OPS>(v, n_verts, reinterpret_cast<const int*>(vt + PC::oVerts)[v], vbuf, a);
+                } else {
+                    const int gv = tid < n_verts ? reinterpret_cast<const int*>(vt + PC::oVerts)[tid] : 0;
+                    tile_flush<T, OPS>(tid, n_verts, gv, vbuf, a);
+                }
             }
             mbar_arrive(empty(s));
         }
     }
     if constexpr (Cfg::kFun || Cfg::kQuad)
-        finish_scalars<T, kPipeThreads>(e_acc, q_acc, a.partials, a.counter, Cfg::kFun ? a.fun : nullptr,
+        finish_scalars<T, PC::kThreads>(e_acc, q_acc, a.partials, a.counter, Cfg::kFun ? a.fun : nullptr,
                                         Cfg::kQuad ? a.quad : nullptr, (Cfg::kFun && a.fun_d) ? a.fun_d + joff : nullptr,
                                         Cfg::kQuad ? a.quad_d : nullptr);
 }
@@ -850,7 +958,26 @@ int launch_one(const apl_fem* fem, const FemArgs<T>& args, int scatter, cudaStre
         cudaMemcpyToSymbolAsync(g_knobs, &k, sizeof(int), 0, cudaMemcpyHostToDevice, stream);
     }
 #endif
-    if (scatter == APL_SCATTER_TILE) {
+    if (fem->host.layout == APL_LAYOUT_PAIR) {
+        if (scatter != APL_SCATTER_TILE) {
+            set_error("apl_fem_eval: handles in the PAIR layout only implement APL_SCATTER_TILE");
+            return APL_ERR_STATE;
+        }
+        using PC = PipeCfg<T, KIND, OPS, APL_LAYOUT_PAIR>;
+        static int blocks_per_sm = -1;
+        auto kern = fem_pipe_kernel<T, KIND, OPS, APL_LAYOUT_PAIR>;
+        if (blocks_per_sm < 0) {
+            APL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)PC::kSmemBytes));
+            int b = 0;
+            APL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, PC::kThreads, PC::kSmemBytes));
+            blocks_per_sm = b > 0 ? b : 1;
+        }
+        int grid = fem->num_sms * blocks_per_sm;
+        if (grid > args.n_tiles) grid = args.n_tiles;
+        if (grid > fem->max_grid) grid = fem->max_grid;
+        kern<<<grid, PC::kThreads, PC::kSmemBytes, stream>>>(args);
+    } else if (scatter == APL_SCATTER_TILE) {
         using PC = PipeCfg<T, KIND, OPS>;
         static int blocks_per_sm = -1;
         auto kern = fem_pipe_kernel<T, KIND, OPS>;

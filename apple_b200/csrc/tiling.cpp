@@ -30,6 +30,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <thread>
+#include <unordered_map>
 #include <cstring>
 #include <numeric>
 
@@ -147,13 +148,14 @@ struct TileScratch {
 };
 
 // ---- 1. local vertex ids: balanced colouring of the gather-conflict graph -----------------------
-// tl[t][a]: provisional local id (first-touch order) of corner a of the tile's t-th tet.  Vertices read
-// by the same quarter warp for the same corner should differ in (id mod M).  new_id[provisional] is a
+// tl[t * nc + a]: provisional local id (first-touch order) of corner a of the tile's t-th item (a tet with
+// nc = 4 corners, or a face-adjacent tet pair with nc = 5: the shared face and the two apexes).  Vertices
+// read by the same quarter warp for the same corner should differ in (id mod M).  new_id[provisional] is a
 // bijection onto [0, nv) with id = 32 w + M k + colour: w = the vertex's window of 32 in ascending global id,
 // k ascending with the global id inside a (window, colour) class.
-void color_local_ids(TileScratch& ws, int nt, int nv, const uint8_t (*tl)[4], const int32_t* gid, int M,
+void color_local_ids(TileScratch& ws, int nt, int nc, int nv, const uint8_t* tl, const int32_t* gid, int M,
                      uint32_t seed, int* new_id) {
-    const int nq = (nt + 7) / 8, ng = nq * 4;
+    const int nq = (nt + 7) / 8, ng = nq * nc;
     auto& gmem = ws.gmem;
     auto& gsz = ws.gsz;
     auto& gb = ws.gb;
@@ -162,13 +164,13 @@ void color_local_ids(TileScratch& ws, int nt, int nv, const uint8_t (*tl)[4], co
     int col[kTileVerts];
     for (int v = 0; v <= nv + 1; ++v) vptr[v] = 0;
     for (int q = 0; q < nq; ++q)
-        for (int a = 0; a < 4; ++a) {
-            const int g = 4 * q + a;
+        for (int a = 0; a < nc; ++a) {
+            const int g = nc * q + a;
             gb[g].clear();
             ws.mark[g] = -1;
             int n = 0;
             for (int t = 8 * q; t < std::min(8 * q + 8, nt); ++t) {
-                const uint8_t v = tl[t][a];
+                const uint8_t v = tl[t * nc + a];
                 bool seen = false;
                 for (int k = 0; k < n; ++k) seen |= (gmem[g][k] == v);
                 if (!seen) gmem[g][n++] = v;
@@ -330,13 +332,13 @@ struct GroupSearch {
 // Bank group of a slot in a 16-byte plane = slot mod 8 per quarter warp; mod 16 per half warp for the
 // 8-byte tail plane of fp32 slots.  Greedy, then local search over swaps of two slots of the same vertex
 // (all slots of a vertex are equivalent for the reduction; pad slots are never used).
-void place_slots(TileScratch& ws, int nt, const uint8_t (*tl)[4], const int* cnt, const int* off, int n_slots,
+void place_slots(TileScratch& ws, int nt, int nc, const uint8_t* tl, const int* cnt, const int* off, int n_slots,
                  bool f64, uint32_t seed) {
     auto& bq = ws.bq;
     auto& bh = ws.bh;
     int16_t* owner = ws.owner;
     int16_t* slot_of = ws.slot_of;
-    const int nq = ((nt + 7) / 8) * 4, nh = ((nt + 15) / 16) * 4;
+    const int nq = ((nt + 7) / 8) * nc, nh = ((nt + 15) / 16) * nc, nx = nc * nt;
     const bool half = !f64;
     for (int g = 0; g < nq; ++g) bq[g].clear();
     for (int g = 0; g < nh; ++g) bh[g].clear();
@@ -345,17 +347,17 @@ void place_slots(TileScratch& ws, int nt, const uint8_t (*tl)[4], const int* cnt
     int16_t corder[4 * kTileTets];
     {
         int bucket[4 * kTileTets + 2];
-        const int nb = 4 * nt + 2;
+        const int nb = nx + 2;
         for (int i = 0; i < nb; ++i) bucket[i] = 0;
-        for (int x = 0; x < 4 * nt; ++x) ++bucket[cnt[tl[x >> 2][x & 3]] + 1];
+        for (int x = 0; x < nx; ++x) ++bucket[cnt[tl[x]] + 1];
         for (int i = 1; i < nb; ++i) bucket[i] += bucket[i - 1];
-        for (int x = 0; x < 4 * nt; ++x) corder[bucket[cnt[tl[x >> 2][x & 3]]]++] = (int16_t)x;
+        for (int x = 0; x < nx; ++x) corder[bucket[cnt[tl[x]]]++] = (int16_t)x;
     }
-    for (int i = 0; i < 4 * nt; ++i) {
-        const int x = corder[i], t = x >> 2, a = x & 3;
-        const int l = tl[t][a];
-        Banks& q = bq[(t >> 3) * 4 + a];
-        Banks& h = bh[(t >> 4) * 4 + a];
+    for (int i = 0; i < nx; ++i) {
+        const int x = corder[i], t = x / nc, a = x % nc;
+        const int l = tl[x];
+        Banks& q = bq[(t >> 3) * nc + a];
+        Banks& h = bh[(t >> 4) * nc + a];
         int best = -1, best_cost = 1 << 30;
         for (int k = 0; k < cnt[l]; ++k) {
             const int s = off[l] + k;
@@ -374,8 +376,8 @@ void place_slots(TileScratch& ws, int nt, const uint8_t (*tl)[4], const int* cnt
     }
     for (int g = 0; g < nq; ++g) bq[g].rescan(8);
     for (int g = 0; g < nh; ++g) bh[g].rescan(16);
-    auto gq_of = [](int x) { return ((x >> 2) >> 3) * 4 + (x & 3); };
-    auto gh_of = [](int x) { return ((x >> 2) >> 4) * 4 + (x & 3); };
+    auto gq_of = [nc](int x) { return ((x / nc) >> 3) * nc + (x % nc); };
+    auto gh_of = [nc](int x) { return ((x / nc) >> 4) * nc + (x % nc); };
     // wavefront change when corner x moves s -> s2 and the owner y of s2 (if any) moves s2 -> s
     auto swap_delta = [&](int x, int y, int s, int s2) {
         int d = 0;
@@ -404,7 +406,7 @@ void place_slots(TileScratch& ws, int nt, const uint8_t (*tl)[4], const int* cnt
     };
     Lcg rng(seed ^ 0x9e3779b9u);
     auto improve = [&](int x) {
-        const int l = tl[x >> 2][x & 3];
+        const int l = tl[x];
         const int len = cnt[l];
         if (len < 2) return;
         const int s = slot_of[x];
@@ -427,31 +429,166 @@ void place_slots(TileScratch& ws, int nt, const uint8_t (*tl)[4], const int* cnt
         for (int g = 0; g < nq; ++g) {
             if (bq[g].m <= 1) continue;
             ++nbad;
-            const int a = g & 3, t0 = (g >> 2) * 8, t1 = std::min(t0 + 8, nt);
+            const int a = g % nc, t0 = (g / nc) * 8, t1 = std::min(t0 + 8, nt);
             for (int t = t0; t < t1; ++t)
-                if (bq[g].m > 1 && bq[g].c[slot_of[4 * t + a] & 7] == bq[g].m) improve(4 * t + a);
+                if (bq[g].m > 1 && bq[g].c[slot_of[nc * t + a] & 7] == bq[g].m) improve(nc * t + a);
         }
         for (int g = 0; g < nh && half; ++g) {
             if (bh[g].m <= 1) continue;
             ++nbad;
-            const int a = g & 3, t0 = (g >> 2) * 16, t1 = std::min(t0 + 16, nt);
+            const int a = g % nc, t0 = (g / nc) * 16, t1 = std::min(t0 + 16, nt);
             for (int t = t0; t < t1; ++t)
-                if (bh[g].m > 1 && bh[g].c[slot_of[4 * t + a] & 15] == bh[g].m) improve(4 * t + a);
+                if (bh[g].m > 1 && bh[g].c[slot_of[nc * t + a] & 15] == bh[g].m) improve(nc * t + a);
         }
         if (nbad == 0) break;
     }
 }
 
+// ---- a closed tile: local ids, reduce order, slots -> tables ------------------------------------------
+// One ITEM per consumer thread: a tet (nc = 4 corners, conn / slots rows of 4 entries) or a face-adjacent
+// tet pair (nc = 5: shared face + two apexes, rows of 8 entries).
+struct TileRange {
+    int64_t item_start;    // first item (tet, or pair slot) of the tile
+    int32_t ni, nv;        // items, distinct vertices
+    int64_t first_touch;   // into `touched`: the tile's vertices in first-touch order
+    int64_t vert_start, voff_start;
+};
+
+void finish_tile(TileScratch& ws, HostTables& out, int64_t tile, const TileRange& r, int nc, int row, int tets_per_item,
+                 uint8_t* tl /* ni x nc provisional ids, rewritten to final ids */, const int32_t* verts, bool f64) {
+    const int ni = r.ni, nv = r.nv;
+    const int gather_mod = f64 ? 4 : 8;   // nodal rows in shared memory are 4 scalars: 16 B (fp32) / 32 B (fp64)
+    // 1. final local ids
+    int new_id[kTileVerts];
+    color_local_ids(ws, ni, nc, nv, tl, verts, gather_mod, (uint32_t)tile, new_id);
+    int cnt[kTileVerts];
+    for (int l = 0; l < nv; ++l) {
+        out.tile_verts[(size_t)r.vert_start + new_id[l]] = verts[l];
+        cnt[l] = 0;
+    }
+    for (int x = 0; x < ni * nc; ++x) {
+        tl[x] = (uint8_t)new_id[tl[x]];
+        ++cnt[tl[x]];
+    }
+    // 2. reduce order: decreasing valence (balanced trip counts within a warp), then per group of 16
+    //    the order / pads that make the range starts conflict-free
+    int perm[kTileVerts];
+    for (int l = 0; l < nv; ++l) perm[l] = l;
+    std::stable_sort(perm, perm + nv, [&](int a, int b) { return cnt[a] > cnt[b]; });
+    int start[kTileVerts + 1], padv[kTileVerts], off[kTileVerts];
+    start[0] = 0;
+    int pads_left = kSlotCap - nc * ni;   // >= nv: one pad per vertex is always affordable
+    for (int g0 = 0; g0 < nv; g0 += 16) {
+        GroupSearch gs;
+        gs.n = std::min(16, nv - g0);
+        const int allowed = pads_left - (nv - g0 - gs.n);   // keep one pad for every later vertex
+        int grp[16];
+        for (int i = 0; i < gs.n; ++i) {
+            grp[i] = perm[g0 + i];
+            gs.cnt[i] = cnt[grp[i]];
+        }
+        gs.target = gs.cnt[0] | 1;
+        bool found = false;
+        for (int attempt = 0; attempt < 2 && !found; ++attempt) {   // all planes, then the 16-byte planes only
+            if (attempt == 1 && f64) break;
+            gs.mod16 = !f64 && attempt == 0;
+            gs.budget = 1500;
+            gs.pad_budget = allowed;
+            for (int i = 0; i < gs.n; ++i) gs.taken[i] = false;
+            found = gs.dfs(0, start[g0], 0u, 0u, allowed);
+        }
+        if (found) {
+            for (int j = 0; j < gs.n; ++j) {
+                perm[g0 + j] = grp[gs.order[j]];
+                padv[g0 + j] = gs.pad[j];
+            }
+        } else {
+            for (int j = 0; j < gs.n; ++j) padv[g0 + j] = (cnt[grp[j]] & 1) ? 0 : 1;   // odd strides
+        }
+        for (int j = 0; j < gs.n; ++j) {
+            start[g0 + j + 1] = start[g0 + j] + cnt[perm[g0 + j]] + padv[g0 + j];
+            pads_left -= padv[g0 + j];
+        }
+    }
+    for (int t = 0; t < nv; ++t) {
+        off[perm[t]] = start[t];
+        out.tile_vperm[(size_t)r.vert_start + t] = (uint8_t)perm[t];
+        out.tile_voff[(size_t)r.voff_start + t] = (uint16_t)(start[t] | (padv[t] << 12));
+    }
+    out.tile_voff[(size_t)r.voff_start + nv] = (uint16_t)start[nv];
+    int32_t* hdr = out.tiles.data() + 6 * tile;
+    hdr[0] = (int32_t)(r.item_start * tets_per_item);
+    hdr[1] = ni * tets_per_item;
+    hdr[2] = (int32_t)r.vert_start;
+    hdr[3] = nv;
+    hdr[4] = (int32_t)r.voff_start;
+    hdr[5] = start[nv];
+    // 3. slot positions
+    place_slots(ws, ni, nc, tl, cnt, off, start[nv], f64, (uint32_t)tile);
+    for (int t = 0; t < ni; ++t)
+        for (int a = 0; a < nc; ++a) {
+            out.conn[(size_t)(r.item_start + t) * row + a] = tl[t * nc + a];
+            out.slots[(size_t)(r.item_start + t) * row + a] = (uint16_t)ws.slot_of[nc * t + a];
+        }
+}
+
+// global id -> provisional local id of the tile's vertices (hash table in the scratch)
+void hash_tile_verts(TileScratch& ws, const int32_t* verts, int nv) {
+    for (int i = 0; i < TileScratch::kHash; ++i) ws.hkey[i] = -1;
+    for (int l = 0; l < nv; ++l) {
+        int h = (int)(((uint32_t)verts[l] * 2654435761u) >> 23) & (TileScratch::kHash - 1);
+        while (ws.hkey[h] >= 0) h = (h + 1) & (TileScratch::kHash - 1);
+        ws.hkey[h] = verts[l];
+        ws.hval[h] = (uint8_t)l;
+    }
+}
+inline uint8_t lookup_tile_vert(const TileScratch& ws, int32_t v) {
+    int h = (int)(((uint32_t)v * 2654435761u) >> 23) & (TileScratch::kHash - 1);
+    while (ws.hkey[h] != v) h = (h + 1) & (TileScratch::kHash - 1);
+    return ws.hval[h];
+}
+
+template <typename F>
+void for_tiles_parallel(int64_t n_tiles, F&& body) {
+    int n_threads = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("APL_TILING_THREADS")) n_threads = atoi(e);
+    n_threads = std::max(1, std::min(n_threads, 32));
+    if (n_tiles < 64) n_threads = 1;
+    if (n_threads == 1) {
+        std::vector<TileScratch> ws(1);
+        for (int64_t t = 0; t < n_tiles; ++t) body(ws[0], t);
+        return;
+    }
+    std::atomic<int64_t> next{0};
+    std::vector<std::thread> pool;
+    for (int i = 0; i < n_threads; ++i)
+        pool.emplace_back([&] {
+            std::vector<TileScratch> ws(1);
+            for (;;) {
+                const int64_t t0 = next.fetch_add(16);
+                if (t0 >= n_tiles) break;
+                for (int64_t t = t0; t < std::min(t0 + 16, n_tiles); ++t) body(ws[0], t);
+            }
+        });
+    for (auto& th : pool) th.join();
+}
+
 }  // namespace
 
+static int build_tiles_pair(const int32_t* cells, bool f64, HostTables& out);
+
 int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const double* points, int elem_bytes,
-                HostTables& out) {
+                int layout, HostTables& out) {
     if (n_cells < 0 || n_points <= 0 || (!cells && n_cells > 0)) {
         set_error("build_tiles: bad sizes");
         return APL_ERR_INVALID;
     }
-    if (n_cells > (int64_t)INT32_MAX) {
-        set_error("n_cells exceeds int32 range");
+    if (n_cells > (int64_t)INT32_MAX / 2) {
+        set_error("n_cells exceeds the int32 range of the packed tables");
+        return APL_ERR_INVALID;
+    }
+    if (layout != APL_LAYOUT_TET && layout != APL_LAYOUT_PAIR) {
+        set_error("build_tiles: unknown layout");
         return APL_ERR_INVALID;
     }
     for (int64_t i = 0; i < 4 * n_cells; ++i)
@@ -461,25 +598,24 @@ int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const d
             return APL_ERR_MESH;
         }
     const bool f64 = elem_bytes == 8;
-    const int gather_mod = f64 ? 4 : 8;   // nodal rows in shared memory are 4 scalars: 16 B (fp32) / 32 B (fp64)
     out = HostTables();
+    out.layout = layout;
     out.n_cells = n_cells;
     out.n_points = n_points;
+    // Morton order of the cells (out.order holds it until the layout-specific pass rewrites it)
     out.order.resize((size_t)n_cells);
     if (points) morton_order(n_cells, n_points, cells, points, out.order);
     else std::iota(out.order.begin(), out.order.end(), (int64_t)0);
+    if (layout == APL_LAYOUT_PAIR) return build_tiles_pair(cells, f64, out);
+
     out.conn.resize((size_t)n_cells * 4);
     out.slots.resize((size_t)n_cells * 4);
+    out.cperm.assign((size_t)n_cells, (uint8_t)0xE4);   // identity corner order
+    out.clone.assign((size_t)n_cells, (uint8_t)0);
 
     // ---- pass 1 (serial): tile boundaries, the distinct vertices of every tile in first-touch order, and
     //      where each tile's tables start (vertex lists at multiples of 16 entries, offset lists at multiples
     //      of 8 entries: every per-tile table is 16-byte aligned for bulk copies)
-    struct TileRange {
-        int64_t tet_start;
-        int32_t nt, nv;
-        int64_t first_touch;   // into `touched`
-        int64_t vert_start, voff_start;
-    };
     std::vector<TileRange> ranges;
     ranges.reserve((size_t)(n_cells / kTileTets + 1));
     std::vector<int32_t> touched;   // concatenated first-touch vertex lists
@@ -529,123 +665,174 @@ int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const d
     out.tiles.assign((size_t)n_tiles * 6, 0);
 
     // ---- pass 2 (parallel over tiles): local ids, reduce order, slots
-    auto pack_tile = [&](TileScratch& ws, int64_t tile) {
+    for_tiles_parallel(n_tiles, [&](TileScratch& ws, int64_t tile) {
         const TileRange& r = ranges[(size_t)tile];
-        const int nt = r.nt, nv = r.nv;
         const int32_t* verts = touched.data() + r.first_touch;
-        // provisional (first-touch) local ids of every corner
-        uint8_t tl[kTileTets][4];
-        for (int i = 0; i < TileScratch::kHash; ++i) ws.hkey[i] = -1;
-        auto hslot = [](int32_t v) { return (int)(((uint32_t)v * 2654435761u) >> 23) & (TileScratch::kHash - 1); };
-        for (int l = 0; l < nv; ++l) {
-            int h = hslot(verts[l]);
-            while (ws.hkey[h] >= 0) h = (h + 1) & (TileScratch::kHash - 1);
-            ws.hkey[h] = verts[l];
-            ws.hval[h] = (uint8_t)l;
+        uint8_t tl[kTileTets * 4];
+        hash_tile_verts(ws, verts, r.nv);
+        for (int t = 0; t < r.ni; ++t) {
+            const int32_t* c = cells + 4 * out.order[(size_t)(r.item_start + t)];
+            for (int a = 0; a < 4; ++a) tl[4 * t + a] = lookup_tile_vert(ws, c[a]);
         }
-        for (int t = 0; t < nt; ++t) {
-            const int32_t* c = cells + 4 * out.order[(size_t)(r.tet_start + t)];
-            for (int a = 0; a < 4; ++a) {
-                int h = hslot(c[a]);
-                while (ws.hkey[h] != c[a]) h = (h + 1) & (TileScratch::kHash - 1);
-                tl[t][a] = ws.hval[h];
-            }
-        }
-        // 1. final local ids
-        int new_id[kTileVerts];
-        color_local_ids(ws, nt, nv, tl, verts, gather_mod, (uint32_t)tile, new_id);
-        int cnt[kTileVerts];
-        for (int l = 0; l < nv; ++l) {
-            out.tile_verts[(size_t)r.vert_start + new_id[l]] = verts[l];
-            cnt[l] = 0;
-        }
-        for (int t = 0; t < nt; ++t)
-            for (int a = 0; a < 4; ++a) {
-                tl[t][a] = (uint8_t)new_id[tl[t][a]];
-                ++cnt[tl[t][a]];
-            }
-        // 2. reduce order: decreasing valence (balanced trip counts within a warp), then per group of 16
-        //    the order / pads that make the range starts conflict-free
-        int perm[kTileVerts];
-        for (int l = 0; l < nv; ++l) perm[l] = l;
-        std::stable_sort(perm, perm + nv, [&](int a, int b) { return cnt[a] > cnt[b]; });
-        int start[kTileVerts + 1], padv[kTileVerts], off[kTileVerts];
-        start[0] = 0;
-        int pads_left = kSlotCap - 4 * nt;   // >= nv: one pad per vertex is always affordable
-        for (int g0 = 0; g0 < nv; g0 += 16) {
-            GroupSearch gs;
-            gs.n = std::min(16, nv - g0);
-            const int allowed = pads_left - (nv - g0 - gs.n);   // keep one pad for every later vertex
-            int grp[16];
-            for (int i = 0; i < gs.n; ++i) {
-                grp[i] = perm[g0 + i];
-                gs.cnt[i] = cnt[grp[i]];
-            }
-            gs.target = gs.cnt[0] | 1;
-            bool found = false;
-            for (int attempt = 0; attempt < 2 && !found; ++attempt) {   // all planes, then the 16-byte planes only
-                if (attempt == 1 && f64) break;
-                gs.mod16 = !f64 && attempt == 0;
-                gs.budget = 1500;
-                gs.pad_budget = allowed;
-                for (int i = 0; i < gs.n; ++i) gs.taken[i] = false;
-                found = gs.dfs(0, start[g0], 0u, 0u, allowed);
-            }
-            if (found) {
-                for (int j = 0; j < gs.n; ++j) {
-                    perm[g0 + j] = grp[gs.order[j]];
-                    padv[g0 + j] = gs.pad[j];
+        finish_tile(ws, out, tile, r, 4, 4, 1, tl, verts, f64);
+    });
+    return APL_OK;
+}
+
+// ---- PAIR layout ---------------------------------------------------------------------------------------
+// One item = two tets that share a face (one consumer thread evaluates both: 5 instead of 8 corner gathers /
+// slots).  The pairs are matched online while the Morton-ordered tets stream into the open tile (a tet joins a
+// waiting tet of the tile it shares a face with, else it waits itself); a tet that stays alone is paired with a
+// ZERO-VOLUME CLONE of itself, so the kernels need no special case.  Both tets of an item are relabelled to
+// (s0, s1, s2, apex) with the shared face first -- any corner order is valid as long as the rows of dhdX are
+// permuted with it (out.cperm, applied by the plane packer).  Packed tet positions inside a tile of ni items that
+// starts at tet position ts: item i owns ts + i (first tet) and ts + ni + i (second tet).
+static int build_tiles_pair(const int32_t* cells, bool f64, HostTables& out) {
+    constexpr int kItems = kTileTets / 2;
+    const int64_t n_cells = out.n_cells;
+    const std::vector<int64_t> morton = out.order;
+    struct Item { int64_t a, b; };   // cell ids; b < 0: a alone (clone), a < 0: filler item
+    std::vector<Item> items;
+    items.reserve((size_t)(n_cells * 6 / 10 + 16));
+    std::vector<TileRange> ranges;
+    std::vector<int32_t> touched;
+    touched.reserve((size_t)(n_cells / 2 + 16));
+    {
+        std::vector<int32_t> stamp((size_t)out.n_points, -1), lid((size_t)out.n_points, 0);
+        std::unordered_map<uint32_t, int32_t> waiting;   // sorted provisional ids of a face -> waiting item
+        int64_t item_start = 0, first = 0, vert_end = 0, voff_end = 0;
+        int32_t tile_id = 0;
+        auto close_tile = [&]() {
+            if ((int64_t)items.size() == item_start) return;
+            if (((int64_t)items.size() - item_start) % 2) items.push_back({-1, -1});   // tiles hold an even number of items
+            const int ni = (int)((int64_t)items.size() - item_start);
+            const int nv = (int)((int64_t)touched.size() - first);
+            vert_end = (vert_end + 15) / 16 * 16;
+            voff_end = (voff_end + 7) / 8 * 8;
+            ranges.push_back({item_start, ni, nv, first, vert_end, voff_end});
+            vert_end += nv;
+            voff_end += nv + 1;
+            first = (int64_t)touched.size();
+            item_start = (int64_t)items.size();
+            waiting.clear();
+            ++tile_id;
+        };
+        auto face_key = [&](const int32_t* c, int skip) {
+            int l[3], n = 0;
+            for (int a = 0; a < 4; ++a)
+                if (a != skip) l[n++] = lid[(size_t)c[a]];
+            if (l[0] > l[1]) std::swap(l[0], l[1]);
+            if (l[1] > l[2]) std::swap(l[1], l[2]);
+            if (l[0] > l[1]) std::swap(l[0], l[1]);
+            return (uint32_t)(l[0] | (l[1] << 8) | (l[2] << 16));
+        };
+        for (int64_t pos = 0; pos < n_cells; ++pos) {
+            const int64_t cell = morton[(size_t)pos];
+            const int32_t* c = cells + 4 * cell;
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                int n_new = 0;
+                for (int a = 0; a < 4; ++a) n_new += stamp[(size_t)c[a]] != tile_id;
+                const int nv_open = (int)((int64_t)touched.size() - first);
+                // a partner waiting in the open tile (only possible if all three face vertices are already in it)
+                int partner = -1;
+                if (n_new <= 1)
+                    for (int skip = 0; skip < 4 && partner < 0; ++skip) {
+                        bool in_tile = true;
+                        for (int a = 0; a < 4; ++a) in_tile &= (a == skip) || stamp[(size_t)c[a]] == tile_id;
+                        if (!in_tile) continue;
+                        auto it = waiting.find(face_key(c, skip));
+                        if (it != waiting.end() && items[(size_t)it->second].b < 0) partner = it->second;
+                    }
+                const bool full = partner < 0 && (int64_t)items.size() - item_start == kItems;
+                if (attempt == 0 && (nv_open + n_new > kTileVerts || full)) {
+                    close_tile();
+                    continue;   // retry in the fresh tile
                 }
-            } else {
-                for (int j = 0; j < gs.n; ++j) padv[g0 + j] = (cnt[grp[j]] & 1) ? 0 : 1;   // odd strides
-            }
-            for (int j = 0; j < gs.n; ++j) {
-                start[g0 + j + 1] = start[g0 + j] + cnt[perm[g0 + j]] + padv[g0 + j];
-                pads_left -= padv[g0 + j];
-            }
-        }
-        for (int t = 0; t < nv; ++t) {
-            off[perm[t]] = start[t];
-            out.tile_vperm[(size_t)r.vert_start + t] = (uint8_t)perm[t];
-            out.tile_voff[(size_t)r.voff_start + t] = (uint16_t)(start[t] | (padv[t] << 12));
-        }
-        out.tile_voff[(size_t)r.voff_start + nv] = (uint16_t)start[nv];
-        int32_t* hdr = out.tiles.data() + 6 * tile;
-        hdr[0] = (int32_t)r.tet_start;
-        hdr[1] = nt;
-        hdr[2] = (int32_t)r.vert_start;
-        hdr[3] = nv;
-        hdr[4] = (int32_t)r.voff_start;
-        hdr[5] = start[nv];
-        // 3. slot positions
-        place_slots(ws, nt, tl, cnt, off, start[nv], f64, (uint32_t)tile);
-        for (int t = 0; t < nt; ++t)
-            for (int a = 0; a < 4; ++a) {
-                out.conn[(size_t)(r.tet_start + t) * 4 + a] = tl[t][a];
-                out.slots[(size_t)(r.tet_start + t) * 4 + a] = (uint16_t)ws.slot_of[4 * t + a];
-            }
-    };
-    int n_threads = (int)std::thread::hardware_concurrency();
-    if (const char* e = getenv("APL_TILING_THREADS")) n_threads = atoi(e);
-    n_threads = std::max(1, std::min(n_threads, 32));
-    if (n_tiles < 64) n_threads = 1;
-    if (n_threads == 1) {
-        std::vector<TileScratch> ws(1);
-        for (int64_t t = 0; t < n_tiles; ++t) pack_tile(ws[0], t);
-    } else {
-        std::atomic<int64_t> next{0};
-        std::vector<std::thread> pool;
-        for (int i = 0; i < n_threads; ++i)
-            pool.emplace_back([&] {
-                std::vector<TileScratch> ws(1);
-                for (;;) {
-                    const int64_t t0 = next.fetch_add(16);
-                    if (t0 >= n_tiles) break;
-                    for (int64_t t = t0; t < std::min(t0 + 16, n_tiles); ++t) pack_tile(ws[0], t);
+                for (int a = 0; a < 4; ++a)
+                    if (stamp[(size_t)c[a]] != tile_id) {
+                        stamp[(size_t)c[a]] = tile_id;
+                        lid[(size_t)c[a]] = (int32_t)((int64_t)touched.size() - first);
+                        touched.push_back(c[a]);
+                    }
+                if (partner >= 0) {
+                    items[(size_t)partner].b = cell;
+                } else {
+                    items.push_back({cell, -1});
+                    for (int skip = 0; skip < 4; ++skip) waiting.emplace(face_key(c, skip), (int32_t)items.size() - 1);
                 }
-            });
-        for (auto& th : pool) th.join();
+                break;
+            }
+        }
+        close_tile();
+        if (vert_end + 16 > (int64_t)INT32_MAX || voff_end + 16 > (int64_t)INT32_MAX ||
+            (int64_t)items.size() > (int64_t)INT32_MAX / 2) {
+            set_error("tile tables exceed int32 range");
+            return APL_ERR_INVALID;
+        }
+        out.tile_verts.assign((size_t)vert_end + 16, 0);
+        out.tile_vperm.assign((size_t)vert_end + 16, 0);
+        out.tile_voff.assign((size_t)voff_end + 16, 0);
     }
+    const int64_t n_items = (int64_t)items.size(), n_tiles = (int64_t)ranges.size();
+    out.tiles.assign((size_t)n_tiles * 6, 0);
+    out.order.assign((size_t)n_items * 2, 0);
+    out.cperm.assign((size_t)n_items * 2, (uint8_t)0xE4);
+    out.clone.assign((size_t)n_items * 2, (uint8_t)0);
+    out.conn.assign((size_t)n_items * 8, 0);
+    out.slots.assign((size_t)n_items * 8, 0);
+
+    for_tiles_parallel(n_tiles, [&](TileScratch& ws, int64_t tile) {
+        const TileRange& r = ranges[(size_t)tile];
+        const int32_t* verts = touched.data() + r.first_touch;
+        uint8_t tl[kItems * 5];
+        hash_tile_verts(ws, verts, r.nv);
+        for (int i = 0; i < r.ni; ++i) {
+            Item it = items[(size_t)(r.item_start + i)];
+            // packed tet positions: the tile's first tets, then its second tets (lane i reads records i and ni + i:
+            // consecutive 16-byte words across the lanes of a warp for both)
+            const size_t pa = (size_t)(r.item_start * 2 + i), pb = pa + (size_t)r.ni;
+            if (it.a < 0) {   // filler: a zero-volume clone of the previous item's first tet, both halves
+                it = {items[(size_t)(r.item_start + i - 1)].a, -1};
+                out.clone[pa] = 1;
+            }
+            const int32_t* ca = cells + 4 * it.a;
+            int32_t v5[5];
+            if (it.b < 0) {   // alone: the partner is a zero-volume clone, corner order unchanged
+                out.order[pa] = out.order[pb] = it.a;
+                out.clone[pb] = 1;
+                for (int k = 0; k < 4; ++k) v5[k] = ca[k];
+                v5[4] = ca[3];
+            } else {
+                const int32_t* cb = cells + 4 * it.b;
+                out.order[pa] = it.a;
+                out.order[pb] = it.b;
+                // shared face in ascending global id, then the two apexes
+                int sa[3], sb[3], ns = 0, apex_a = -1, apex_b = -1;
+                for (int k = 0; k < 4; ++k) {
+                    int j = -1;
+                    for (int m = 0; m < 4; ++m)
+                        if (cb[m] == ca[k]) j = m;
+                    if (j >= 0 && ns < 3) { sa[ns] = k; sb[ns] = j; ++ns; }
+                    else apex_a = k;
+                }
+                for (int m = 0; m < 4; ++m) {
+                    bool shared = false;
+                    for (int k = 0; k < ns; ++k) shared |= sb[k] == m;
+                    if (!shared) apex_b = m;
+                }
+                for (int x = 0; x < 3; ++x)
+                    for (int y = x + 1; y < 3; ++y)
+                        if (ca[sa[y]] < ca[sa[x]]) { std::swap(sa[x], sa[y]); std::swap(sb[x], sb[y]); }
+                out.cperm[pa] = (uint8_t)(sa[0] | (sa[1] << 2) | (sa[2] << 4) | (apex_a << 6));
+                out.cperm[pb] = (uint8_t)(sb[0] | (sb[1] << 2) | (sb[2] << 4) | (apex_b << 6));
+                for (int k = 0; k < 3; ++k) v5[k] = ca[sa[k]];
+                v5[3] = ca[apex_a];
+                v5[4] = cb[apex_b];
+            }
+            for (int k = 0; k < 5; ++k) tl[5 * i + k] = lookup_tile_vert(ws, v5[k]);
+        }
+        finish_tile(ws, out, tile, r, 5, 8, 2, tl, verts, f64);
+    });
     return APL_OK;
 }
 

@@ -57,6 +57,14 @@ extern "C" {
 #define APL_SCATTER_ATOMIC 1 /* one thread per tet, direct gathers and 12 REDs per field (reference-like) */
 #define APL_SCATTER_TILE_SIMPLE 2 /* same tiles without the producer warp / bulk-copy pipeline */
 
+/* How the element kernels walk the mesh (chosen when a handle is created, see apl_set_layout):
+ * TET:  one consumer thread per tet (4 corner gathers, 4 reduction slots per tet);
+ * PAIR: one consumer thread per pair of tets that share a face (5 corner gathers / slots per 2 tets; a tet
+ *       without a partner in its tile is paired with a zero-volume clone of itself).  EXPERIMENTAL: only
+ *       APL_SCATTER_TILE is implemented for it. */
+#define APL_LAYOUT_TET 0
+#define APL_LAYOUT_PAIR 1
+
 typedef struct apl_fem apl_fem_t;   /* one FEM potential: replaces WarpPotentialFem (warp/fem/_base.py:39) */
 typedef struct apl_pncg apl_pncg_t; /* fused PNCG workspace (liblaf.peach.optim.PNCG, external to the reference) */
 
@@ -90,21 +98,31 @@ int apl_fem_create_snh_arap(int dtype, int64_t n_cells, int64_t n_points, const 
                             apl_fem_t** out);
 void apl_fem_destroy(apl_fem_t* fem);
 
+/* Layout of the handles created AFTERWARDS (process-wide; default APL_LAYOUT_TET).  No reference counterpart. */
+int apl_set_layout(int layout);
+int apl_fem_layout(const apl_fem_t* fem);
+
 /* info[0..9] = n_cells, n_points, n_tiles, length of tile_verts, static device bytes,
- *              kind, dtype, device, length of tile_voff, 0 */
+ *              kind, dtype, device, length of tile_voff, number of packed tet positions
+ *              (n_cells for APL_LAYOUT_TET; 2 x the number of pair items for APL_LAYOUT_PAIR) */
 int apl_fem_info(const apl_fem_t* fem, int64_t info[10]);
 
 /* Copies of the host tables (sizes from apl_fem_info); any pointer may be NULL.
  *   tiles      int32 (n_tiles,6): tet_start, n_tets, vert_start, n_verts, voff_start, 0
- *   order      int64 (n_cells,)  : packed position -> caller's cell index
- *   conn       uint8 (n_cells,4) : tile-local vertex id per corner (packed order)
- *   slots      uint16(n_cells,4) : in-tile reduction slot per corner (packed order)
+ *   order      int64 (info[9],)  : packed tet position -> caller's cell index
+ *   conn       uint8 (n_cells,4) : tile-local vertex id per corner (packed order); PAIR layout: (info[9]/2, 8),
+ *                                  entries 0..4 = shared face s0 s1 s2, apex of the first, apex of the second tet
+ *   slots      uint16(n_cells,4) : in-tile reduction slot per corner (packed order); PAIR layout: (info[9]/2, 8)
  *   tile_verts int32 (info[3])   : global vertex id per tile-local id, from vert_start
  *   tile_voff  uint16(info[8])   : per tile, n_verts+1 entries starting at voff_start: bits 0..11 first slot of
  *                                  the vertex's range (reduce order), bits 12..15 unused pad slots after it
  *   tile_vperm uint8 (info[3])   : per tile, the local ids in reduce order (groups of 16 by decreasing valence) */
 int apl_fem_host_tables(const apl_fem_t* fem, int32_t* tiles, int64_t* order, uint8_t* conn,
                         uint16_t* slots, int32_t* tile_verts, uint16_t* tile_voff, uint8_t* tile_vperm);
+/* Per packed tet position (info[9] entries each; either pointer may be NULL):
+ *   cperm uint8: corner order used by the packed record, new corner k = caller's corner (cperm >> 2k) & 3
+ *   clone uint8: 1 = zero-volume copy of a tet (fills a pair item), contributes nothing */
+int apl_fem_host_corner_tables(const apl_fem_t* fem, uint8_t* cperm, uint8_t* clone);
 
 /* Host-only handles (device = -1): copy of the packed static planes, [n_planes][plane_stride] 16-byte
  * vectors in packed cell order (record = Dm^-1 (9), dV, mu, lambda, activation (6) / second potential);

@@ -464,3 +464,97 @@ def test_mark_boundary_partitions_the_tile_headers(native_lib):
     assert np.array_equal(tables()[0], before)
     assert native_lib.apl_fem_eval_part(h, 3, 1, None, None, 3, None, None, None, None, None, 3, 0, None) != 0  # bad part
     native_lib.apl_fem_destroy(h)
+
+
+def _pair_tables(native_lib, mesh, dtype_code, dhdX, dV, mu, la):
+    """Host-only handle in the PAIR layout and all of its tables."""
+    from apple_b200 import _lib
+
+    T, V = mesh.n_cells, mesh.n_points
+    P = _lib.host_ptr
+    h = ctypes.c_void_p()
+    cells = np.ascontiguousarray(mesh.cells, dtype=np.int32); pts = np.ascontiguousarray(mesh.points)
+    assert native_lib.apl_set_layout(_lib.LAYOUT_PAIR) == 0
+    try:
+        rc = native_lib.apl_fem_create(0, dtype_code, T, V, P(cells), P(dhdX), P(dV), P(mu), P(la), None, P(pts), -1,
+                                       ctypes.byref(h))
+    finally:
+        native_lib.apl_set_layout(_lib.LAYOUT_TET)
+    assert rc == 0, native_lib.apl_last_error()
+    assert native_lib.apl_fem_layout(h) == _lib.LAYOUT_PAIR
+    info = (ctypes.c_int64 * 10)(); native_lib.apl_fem_info(h, info)
+    nt, nv, nvo, npk = info[2], info[3], info[8], info[9]
+    tiles = np.zeros((nt, 6), np.int32); order = np.zeros(npk, np.int64)
+    conn = np.zeros((npk // 2, 8), np.uint8); slots = np.zeros((npk // 2, 8), np.uint16)
+    tv = np.zeros(nv, np.int32); voff = np.zeros(nvo, np.uint16); vperm = np.zeros(nv, np.uint8)
+    cperm = np.zeros(npk, np.uint8); clone = np.zeros(npk, np.uint8)
+    native_lib.apl_fem_host_tables(h, P(tiles), P(order), P(conn), P(slots), P(tv), P(voff), P(vperm))
+    native_lib.apl_fem_host_corner_tables(h, P(cperm), P(clone))
+    npl, stride = ctypes.c_int64(), ctypes.c_int64()
+    native_lib.apl_fem_host_planes(h, None, ctypes.byref(npl), ctypes.byref(stride))
+    planes = np.zeros((npl.value, stride.value, 16 // dhdX.dtype.itemsize), dhdX.dtype)
+    native_lib.apl_fem_host_planes(h, P(planes), None, None)
+    native_lib.apl_fem_destroy(h)
+    return tiles, order, conn, slots, tv, voff, vperm, cperm, clone, planes
+
+
+def test_pair_layout_tables_assemble_the_oracle_gradient(native_lib):
+    """APL_LAYOUT_PAIR (one consumer thread per pair of face-adjacent tets): numpy emulation of what the pair
+    kernel does with the tables -- 5 gathered vertices per item, two tets evaluated in the packed corner order
+    (shared face first), contributions of the shared corners added, 5 slots per item, slot reduction and flush as
+    in the TET layout -- reproduces the oracle gradient; every cell appears exactly once as a non-clone; the packed
+    record holds the rows of dhdX in the packed corner order."""
+    from apple_b200 import _lib
+    from oracle import region
+
+    mesh, u, _ = make_case(n=7, seed=5, morton=False)
+    ora = oracle_potential("snh", mesh)
+    dhdX, dV = region.compute_grad(mesh.points, mesh.cells, mesh.cell_data["Fraction"])
+    mu, la = mesh.cell_data["mu"], mesh.cell_data["lambda"]
+    tiles, order, conn, slots, tv, voff, vperm, cperm, clone, planes = _pair_tables(native_lib, mesh, _lib.F64, dhdX, dV, mu, la)
+    T = mesh.n_cells
+    real = clone == 0
+    assert sorted(order[real].tolist()) == list(range(T))            # every cell exactly once, clones aside
+    perm = np.stack([(cperm >> (2 * k)) & 3 for k in range(4)], axis=1).astype(int)      # (n_packed, 4)
+    assert (np.sort(perm, axis=1) == np.arange(4)).all()
+    # packed record == reference arrays in the packed corner order, zero volume for clones
+    rec = planes.transpose(1, 0, 2).reshape(planes.shape[1], -1)[:order.size]
+    rows = dhdX[order][np.arange(order.size)[:, None], perm[:, 1:]]                      # rows 1..3 of the packed order
+    np.testing.assert_array_equal(rec[:, :9], rows.reshape(-1, 9))
+    np.testing.assert_array_equal(rec[:, 9], np.where(real, dV[order], 0.0))
+    np.testing.assert_array_equal(rec[:, 10], mu[order])
+    # emulation of the pair kernel's assembly
+    elem = ora.elem_grad(u)                                           # (T, 4, 3) per-corner contributions, caller's corner order
+    contrib = elem[order][np.arange(order.size)[:, None], perm] * real[:, None, None]    # packed corner order; clones: 0
+    out = np.zeros_like(u)
+    n_paired = 0
+    for (ts, n, vs, nv, vo, nslots) in tiles:
+        assert ts % 4 == 0 and n % 4 == 0 and n <= 256                # items come in even numbers: 16-byte aligned rows
+        verts = tv[vs:vs + nv]
+        it0, ni = ts // 2, n // 2
+        c5 = conn[it0:it0 + ni, :5].astype(int); s5 = slots[it0:it0 + ni, :5].astype(int)
+        A, B = np.arange(ts, ts + ni), np.arange(ts + ni, ts + n)     # the tile's first tets, then its second tets
+        cells_p = mesh.cells[order][np.arange(order.size)[:, None], perm]                # vertices in packed corner order
+        assert np.array_equal(verts[c5[:, :4]], cells_p[A])           # gather of tet A: (s0, s1, s2, apex A)
+        assert np.array_equal(verts[c5[:, [0, 1, 2, 4]]], cells_p[B])  # gather of tet B: (s0, s1, s2, apex B)
+        item = np.zeros((ni, 5, 3))
+        item[:, :3] = contrib[A][:, :3] + contrib[B][:, :3]
+        item[:, 3] = contrib[A][:, 3]
+        item[:, 4] = contrib[B][:, 3]
+        assert len(set(s5.ravel().tolist())) == 5 * ni
+        buf = np.full((nslots, 3), np.nan)
+        buf[s5.ravel()] = item.reshape(-1, 3)
+        raw = voff[vo:vo + nv + 1].astype(int)
+        start, pad = raw & 0x0fff, raw[:-1] >> 12
+        assert start[-1] == nslots <= 4 * 256 + 192
+        acc = np.zeros((nv, 3))
+        for t in range(nv):
+            cnt = start[t + 1] - start[t] - pad[t]
+            rows_ = buf[start[t]:start[t] + cnt]
+            assert cnt > 0 and not np.isnan(rows_).any()
+            acc[vperm[vs + t]] = rows_.sum(axis=0)
+        np.add.at(out, verts, acc)
+        n_paired += 2 * int((real[A] & real[B]).sum())
+    ref = np.zeros_like(u); ora.grad(u, ref)
+    np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+    assert n_paired > 0.85 * T                                        # the online matching pairs most tets
