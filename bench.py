@@ -48,6 +48,8 @@ def parse_args():
                     help="N>1 with --n 0: weak = ~975k tets per GPU (mesh grows with N), strong = the 58^3 mesh")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--scatter", default="tile", choices=["tile", "atomic", "tile_simple"])
+    ap.add_argument("--layout", default="tet", choices=["tet", "pair"],
+                    help="pair = EXPERIMENTAL: one consumer thread per pair of face-adjacent tets (tile assembly only)")
     ap.add_argument("--potentials", default="snh,arap")
     ap.add_argument("--pncg-iters", type=int, default=200)
     ap.add_argument("--no-fuse", action="store_true", help="one pass per potential (the reference's structure)")
@@ -279,6 +281,7 @@ def main():
     w = 4 if args.dtype == "f32" else 8
     config.scatter = {"tile": _lib.SCATTER_TILE, "atomic": _lib.SCATTER_ATOMIC,
                       "tile_simple": _lib.SCATTER_TILE_SIMPLE}[args.scatter]
+    config.layout = {"tet": _lib.LAYOUT_TET, "pair": _lib.LAYOUT_PAIR}[args.layout]
     kinds = args.potentials.split(",")
 
     mesh, u, p = build_mesh(args.n)
@@ -507,7 +510,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": args.scaling if world > 1 else "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": workload_name(args, mesh, kinds), "assembly": args.scatter,
+            "config": {"workload": workload_name(args, mesh, kinds), "assembly": args.scatter, "layout": args.layout,
                        "l2": "256 MiB flush write between timed steps" if not args.no_flush else "no flush",
                        "parallelism": (f"{world} ranks x contiguous Morton chunk of tets (~{T_total // world} tets per "
                                        f"GPU, {args.scaling} scaling); halo sum of grad+HVP (NCCL all-to-all of "
@@ -603,7 +606,7 @@ def sweep(args, mesh, u, p, dtype, dev, flush):
                 outs = {k: torch.zeros((V, ld), dtype=dt, device=dev) for k in ("grad", "diag", "prod")}
                 fun = torch.zeros(1, dtype=dt, device=dev); quad = torch.zeros(1, dtype=dt, device=dev)
                 for ops in (1, 2, 4, 8, 16, 7, 11, 15):
-                    for scatter in (0, 2, 1):
+                    for scatter in ((0,) if args.layout == "pair" else (0, 2, 1)):
                         ts = []
                         for i in range(8):
                             flush()

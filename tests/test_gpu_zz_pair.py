@@ -1,0 +1,118 @@
+"""GPU: the EXPERIMENTAL pair layout (one consumer thread per pair of face-adjacent tets, APL_LAYOUT_PAIR).
+
+Written when no GPU was available: the tables are validated on the CPU (numpy emulation of the kernel's table
+semantics, tests/test_native_cpu.py::test_pair_layout_tables_assemble_the_oracle_gradient) and the default-layout
+kernels are unchanged instruction for instruction, but the pair kernel itself has never run.  The tests are
+therefore non-strict xfail: a pass is reported as XPASS, a failure does not break the parity suite of the
+product (default) layout.  Remove the marker once they have passed on a B200."""
+
+import contextlib
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import KINDS, cuda_potential, make_case, oracle_potential, rel_err
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="experimental pair layout: never run on a GPU yet")]
+
+TOL = {torch.float32: 1.0e-5, torch.float64: 1.0e-10}
+
+
+@contextlib.contextmanager
+def pair_layout():
+    from apple_b200 import _lib, config
+
+    old = config.layout
+    config.layout = _lib.LAYOUT_PAIR
+    try:
+        yield
+    finally:
+        config.layout = old
+
+
+@pytest.fixture(scope="module")
+def case():
+    return make_case(n=7, seed=3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("kind", KINDS)
+def test_pair_layout_operators_match_oracle(native_lib, case, kind, dtype):
+    from apple_b200 import _lib
+
+    mesh, u, p = case
+    V = mesh.n_points
+    ora = oracle_potential(kind, mesh)
+    with pair_layout():
+        pot = cuda_potential(kind, mesh, dtype)
+    assert pot.layout == _lib.LAYOUT_PAIR
+    ud = torch.as_tensor(u, dtype=dtype, device="cuda"); pd = torch.as_tensor(p, dtype=dtype, device="cuda")
+    e, q = np.zeros(1), np.zeros(1)
+    g, d, h = (np.zeros((V, 3)) for _ in range(3))
+    ora.fun(u, e); ora.hess_quad(u, p, q); ora.grad(u, g); ora.hess_diag(u, d); ora.hess_prod(u, p, h)
+    tol = TOL[dtype]
+    for ops in (31, 11, 7, 16, 1, 2, 4, 8):
+        fun = torch.zeros(1, dtype=dtype, device="cuda"); quad = torch.zeros(1, dtype=dtype, device="cuda")
+        grad, diag, prod = (torch.zeros((V, 3), dtype=dtype, device="cuda") for _ in range(3))
+        for rep in range(2):      # accumulate semantics: the second call doubles everything
+            pot.eval(ops, ud, pd, fun=fun, quad=quad, grad=grad, diag=diag, prod=prod)
+        torch.cuda.synchronize()
+        for bit, got, ref in ((1, fun, e), (16, quad, q), (2, grad, g), (4, diag, d), (8, prod, h)):
+            if ops & bit:
+                assert rel_err(0.5 * got.cpu().numpy(), ref) < tol, (kind, dtype, ops, bit)
+    with pytest.raises(Exception):           # only the pipelined tile kernel exists for this layout
+        pot.eval(2, ud, pd, grad=torch.zeros((V, 3), dtype=dtype, device="cuda"), scatter=_lib.SCATTER_ATOMIC)
+
+
+def test_pair_layout_full_size_fused_model_and_pncg(native_lib):
+    """Config-2 size (every CTA runs many tiles): fused SNH+ARAP in the pair layout == the default layout;
+    60 fused PNCG iterations follow the same trajectory."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from bench import build_mesh
+
+    from apple_b200.common import FIXED_MASK, FIXED_VALUE
+    from apple_b200.forward import Forward, ModelBuilder
+    from apple_b200.optim import PNCG
+    from apple_b200.optim.pncg import ConvergenceCriteria
+    from apple_b200.warp.fem import fuse_potentials
+
+    mesh, u, p = build_mesh(58)
+    V = mesh.n_points
+    dtype = torch.float32
+    ud = torch.as_tensor(u, dtype=dtype, device="cuda"); pd = torch.as_tensor(p, dtype=dtype, device="cuda")
+    res, models = {}, {}
+    for name in ("tet", "pair"):
+        ctx = pair_layout() if name == "pair" else contextlib.nullcontext()
+        with ctx:
+            pots = fuse_potentials({k: cuda_potential(k, mesh, dtype, name=k) for k in ("snh", "arap")})
+        pot = list(pots.values())[0]
+        fun = torch.zeros(1, dtype=dtype, device="cuda"); quad = torch.zeros(1, dtype=dtype, device="cuda")
+        grad, diag, prod = (torch.zeros((V, 3), dtype=dtype, device="cuda") for _ in range(3))
+        pot.eval(31, ud, pd, fun=fun, quad=quad, grad=grad, diag=diag, prod=prod)
+        torch.cuda.synchronize()
+        res[name] = [x.cpu().numpy() for x in (fun, quad, grad, diag, prod)]
+        models[name] = pots
+    for a, b in zip(res["pair"], res["tet"]):
+        assert rel_err(a, b) < 2e-5
+    energies = {}
+    fixed = np.zeros((V, 3), bool); fixed[mesh.points[:, 2] == 0.0] = True
+    mesh.point_data[FIXED_MASK.vtk] = fixed
+    mesh.point_data[FIXED_VALUE.vtk] = np.zeros((V, 3))
+    u0 = np.ascontiguousarray(u); u0[fixed] = 0.0
+    for name, pots in models.items():
+        b = ModelBuilder(dtype=dtype, device="cuda")
+        b.add_vertices(mesh); b.add_fixed(mesh)
+        for pot in pots.values():
+            b.add_potential(pot)
+        crit = ConvergenceCriteria(max_steps=100, target_relative_gradient_norm=0.0)
+        fwd = Forward(b.finalize(), optimizer=PNCG(criteria=crit))
+        fwd.state.u = torch.as_tensor(u0, dtype=dtype, device="cuda")
+        opt = fwd.optimizer.init(fwd.problem, fwd.state, fwd.free)
+        opt.step(fwd.problem, fwd.state, 60)
+        assert opt.n_steps == 60
+        energies[name] = opt.line_search_state.f_alpha
+    assert abs(energies["pair"] - energies["tet"]) <= 5e-3 * abs(energies["tet"])

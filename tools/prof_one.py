@@ -12,9 +12,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--kind", default="snh"); ap.add_argument("--dtype", default="f32")
 ap.add_argument("--ops", type=int, default=11); ap.add_argument("--scatter", type=int, default=0)
 ap.add_argument("--ld", type=int, default=3); ap.add_argument("--n", type=int, default=58)
-ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--reps", type=int, default=3); ap.add_argument("--layout", default="tet")
 a = ap.parse_args()
 dt = torch.float32 if a.dtype == "f32" else torch.float64
+from apple_b200 import _lib, config
+config.layout = {"tet": _lib.LAYOUT_TET, "pair": _lib.LAYOUT_PAIR}[a.layout]
 mesh, u, p = build_mesh(a.n)
 V = mesh.n_points
 if a.kind == "fused":
