@@ -3,10 +3,12 @@
 Written when no GPU was available: the tables are validated on the CPU (numpy emulation of the kernel's table
 semantics, tests/test_native_cpu.py::test_pair_layout_tables_assemble_the_oracle_gradient) and the default-layout
 kernels are unchanged instruction for instruction, but the pair kernel itself has never run.  The tests are
-therefore non-strict xfail: a pass is reported as XPASS, a failure does not break the parity suite of the
-product (default) layout.  Remove the marker once they have passed on a B200."""
+therefore OPT-IN (APL_TEST_PAIR=1; run them under `timeout`, an unproven kernel can hang) and non-strict xfail:
+they cannot break -- or stall -- the parity suite of the product (default) layout.  Remove both markers once they
+have passed on a B200:   APL_TEST_PAIR=1 timeout 600 python -m pytest tests/test_gpu_zz_pair.py -m gpu -q"""
 
 import contextlib
+import os
 
 import numpy as np
 import pytest
@@ -14,7 +16,11 @@ import torch
 
 from helpers import KINDS, cuda_potential, make_case, oracle_potential, rel_err
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="experimental pair layout: never run on a GPU yet")]
+pytestmark = [
+    pytest.mark.gpu,
+    pytest.mark.skipif(os.environ.get("APL_TEST_PAIR") != "1", reason="experimental pair layout: opt in with APL_TEST_PAIR=1"),
+    pytest.mark.xfail(strict=False, reason="experimental pair layout: never run on a GPU yet"),
+]
 
 TOL = {torch.float32: 1.0e-5, torch.float64: 1.0e-10}
 

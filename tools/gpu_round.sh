@@ -10,10 +10,13 @@ nvidia-smi -L > $out/gpu.txt 2>&1
 python -m apple_b200.build > $out/build.log 2>&1
 
 echo "== pytest" ; timeout 1200 python -m pytest tests -m gpu -x -q > $out/pytest_${tag}.log 2>&1 ; echo "pytest rc=$?" >> $out/pytest_${tag}.log ; tail -3 $out/pytest_${tag}.log
+echo "== pair layout (experimental, opt-in)" ; APL_TEST_PAIR=1 timeout 600 python -m pytest tests/test_gpu_zz_pair.py -m gpu -q -rxX > $out/pytest_pair_${tag}.log 2>&1 ; echo "pair rc=$?" >> $out/pytest_pair_${tag}.log ; tail -5 $out/pytest_pair_${tag}.log
 echo "== smoke"  ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke_${tag}.log 2>&1 ; echo "smoke rc=$?" >> $out/smoke_${tag}.log
 echo "== bench (config 2)" ; timeout 900 python bench.py > $out/bench_${tag}_1m.json 2> $out/bench_${tag}.err ; tail -c 600 $out/bench_${tag}_1m.json
 echo "== bench (8 M tets, operators only)" ; timeout 600 python bench.py --n 117 --steps 10 --no-pncg --no-cpu-baseline > $out/bench_${tag}_8m.json 2>> $out/bench_${tag}.err
 echo "== bench (SNH alone, 8 M)" ; timeout 600 python bench.py --n 117 --steps 10 --potentials snh --no-pncg --no-cpu-baseline > $out/bench_${tag}_8m_snh.json 2>> $out/bench_${tag}.err
+echo "== bench (pair layout, config 2 and SNH 8 M)" ; timeout 600 python bench.py --layout pair --no-cpu-baseline > $out/bench_${tag}_1m_pair.json 2>> $out/bench_${tag}.err
+timeout 600 python bench.py --layout pair --n 117 --steps 10 --potentials snh --no-pncg --no-cpu-baseline > $out/bench_${tag}_8m_snh_pair.json 2>> $out/bench_${tag}.err
 echo "== reference arm" ; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_${tag}_reference.json 2>> $out/bench_${tag}.err
 
 echo "== launch list"
