@@ -6,7 +6,7 @@ consumer warps, the number of wavefronts = max over the 32 banks of distinct 4-b
 table layout (tiling.cpp) can be tuned offline and compared with ncu's
 l1tex__data_pipe_lsu_wavefronts_mem_shared_op_{ld,st}.sum.
 
-usage: python tools/smem_model.py [--n 58] [--tiles 400] [--quarter]
+usage: python tools/smem_model.py [--n 58] [--tiles 400] [--quarter] [--layout pair]
 """
 import argparse, ctypes, sys
 from pathlib import Path
@@ -44,7 +44,7 @@ def wavefronts(addr, nbytes, active=None, quarter=False):
         tot = tot + count(words[..., k * g:(k + 1) * g, :], act[..., k * g:(k + 1) * g, :])
     return tot
 
-def host_tables(n):
+def host_tables(n, layout=0):
     from apple_b200 import _lib, build
     from bench import build_mesh
     from oracle import region
@@ -54,13 +54,18 @@ def host_tables(n):
     T, V = mesh.n_cells, mesh.n_points
     one = np.ones(T); P = _lib.host_ptr; h = ctypes.c_void_p()
     cells = np.ascontiguousarray(mesh.cells, dtype=np.int32); pts = np.ascontiguousarray(mesh.points)
-    rc = L.apl_fem_create(0, _lib.F32, T, V, P(cells), P(dhdX.astype(np.float32)), P(dV.astype(np.float32)),
-                          P(one.astype(np.float32)), P(one.astype(np.float32)), None, P(pts), -1, ctypes.byref(h))
+    L.apl_set_layout(layout)
+    try:
+        rc = L.apl_fem_create(0, _lib.F32, T, V, P(cells), P(dhdX.astype(np.float32)), P(dV.astype(np.float32)),
+                              P(one.astype(np.float32)), P(one.astype(np.float32)), None, P(pts), -1, ctypes.byref(h))
+    finally:
+        L.apl_set_layout(0)
     assert rc == 0, L.apl_last_error()
     info = (ctypes.c_int64 * 10)(); L.apl_fem_info(h, info)
-    nt, nv, nvo = info[2], info[3], info[8]
-    tiles = np.zeros((nt, 6), np.int32); order = np.zeros(T, np.int64)
-    conn = np.zeros((T, 4), np.uint8); slots = np.zeros((T, 4), np.uint16)
+    nt, nv, nvo, npk = info[2], info[3], info[8], info[9]
+    tiles = np.zeros((nt, 6), np.int32); order = np.zeros(npk, np.int64)
+    rows, width = (npk // 2, 8) if layout == 1 else (T, 4)
+    conn = np.zeros((rows, width), np.uint8); slots = np.zeros((rows, width), np.uint16)
     tv = np.zeros(nv, np.int32); voff = np.zeros(nvo, np.uint16); vperm = np.zeros(nv, np.uint8)
     L.apl_fem_host_tables(h, P(tiles), P(order), P(conn), P(slots), P(tv), P(voff), P(vperm))
     L.apl_fem_destroy(h)
@@ -87,21 +92,28 @@ def global_lines(tiles, tv, max_tiles=None, row_bytes=12):
     return got / n, asc / n
 
 
-def model(tiles, conn, slots, voff, vperm, quarter=False, max_tiles=None):
+def model(tiles, conn, slots, voff, vperm, quarter=False, max_tiles=None, layout=0, n_real_tets=None):
     acc = dict(static=0, gather=0, slot_st=0, red_small=0, red_ld=0, vbuf_st=0, flush_ld=0)
     ideal = dict(acc)
     ntets = 0
     sel = tiles if max_tiles is None else tiles[np.linspace(0, len(tiles) - 1, max_tiles).astype(int)]
-    for (ts, n, vs, nv, vo, nslots) in sel:
-        ntets += n
+    nc = 5 if layout == 1 else 4                 # corners per item (a tet, or a pair of tets)
+    tpi = 2 if layout == 1 else 1                # tets per item
+    n_warps = 4 if layout == 1 else 8            # consumer warps per CTA
+    for (ts, n_t, vs, nv, vo, nslots) in sel:
+        ntets += n_t
+        n = n_t // tpi                           # items = consumer threads with work
+        it0 = ts // tpi
         nw = (n + 31) // 32
         lane_t = np.arange(nw * 32).reshape(nw, 32)
         act = lane_t < n
-        c = np.zeros((nw * 32, 4), np.int64); c[:n] = conn[ts:ts + n]
-        s = np.zeros((nw * 32, 4), np.int64); s[:n] = slots[ts:ts + n]
-        c = c.reshape(nw, 32, 4); s = s.reshape(nw, 32, 4)
-        acc["static"] += nw * (1 + 1 + 12 + 2); ideal["static"] += nw * 16
-        for k in range(4):
+        c = np.zeros((nw * 32, nc), np.int64); c[:n] = conn[it0:it0 + n, :nc]
+        s = np.zeros((nw * 32, nc), np.int64); s[:n] = slots[it0:it0 + n, :nc]
+        c = c.reshape(nw, 32, nc); s = s.reshape(nw, 32, nc)
+        # header + connectivity + record planes (3 per tet) + slot ids; the pair item reads 8 B / 16 B rows
+        static = (1 + 1 + 12 + 2) if layout == 0 else (1 + 2 + 24 + 4)
+        acc["static"] += nw * static; ideal["static"] += nw * static
+        for k in range(nc):
             g = wavefronts(c[:, :, k] * 16, 16, act, quarter).sum()
             acc["gather"] += 2 * g; ideal["gather"] += 2 * 4 * nw
             acc["slot_st"] += wavefronts(s[:, :, k] * 16, 16, act, quarter).sum() + wavefronts(s[:, :, k] * 8, 8, act, quarter).sum()
@@ -111,8 +123,8 @@ def model(tiles, conn, slots, voff, vperm, quarter=False, max_tiles=None):
         start = raw & 0x0fff; padded = raw[:-1] >> 12
         cnt = np.diff(start) - padded
         perm = vperm[vs:vs + nv].astype(np.int64)
-        for base in (0, 128):
-            for w in range(8):
+        for base in range(0, 192, 16 * n_warps):
+            for w in range(n_warps):
                 t = base + 16 * w + np.arange(16)
                 if t[0] >= ((nv + 15) & ~15): continue
                 ok = t < nv
@@ -144,10 +156,14 @@ def model(tiles, conn, slots, voff, vperm, quarter=False, max_tiles=None):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser(); ap.add_argument("--n", type=int, default=58)
     ap.add_argument("--tiles", type=int, default=400); ap.add_argument("--quarter", action="store_true")
+    ap.add_argument("--layout", default="tet", choices=["tet", "pair"])
     a = ap.parse_args()
-    tiles, conn, slots, tv, voff, vperm = host_tables(a.n)
+    layout = 1 if a.layout == "pair" else 0
+    tiles, conn, slots, tv, voff, vperm = host_tables(a.n, layout)
     print("tiles", len(tiles), "mean tets", tiles[:, 1].mean(), "mean verts", tiles[:, 3].mean(), "mean slots", tiles[:, 5].mean())
-    per, ideal = model(tiles, conn, slots, voff, vperm, a.quarter, a.tiles)
+    per, ideal = model(tiles, conn, slots, voff, vperm, a.quarter, a.tiles, layout)
+    if layout:
+        print("(pair layout: per 32 PACKED tets; clones of unpaired tets are counted as work)")
     ld = per["static"] + per["gather"] + per["red_small"] + per["red_ld"] + per["flush_ld"]
     st = per["slot_st"] + per["vbuf_st"]
     for k in per: print(f"{k:10s} {per[k]:7.2f}   ideal {ideal[k]:7.2f}")
