@@ -247,7 +247,10 @@ constexpr int kSlotsAlloc = 4 * kTileTets + kTileVerts;
 // The slot buffer is split into 16-byte planes: vector q of slot s lives at sl + (q * kNSlots + s) * 16 B.
 // One thread reading consecutive slots of "its" vertex and a warp of such threads then touch
 // neighbouring 16-byte words (see tile_reduce), instead of words a whole slot stride apart.
-template <typename T, int SS>
+// slot capacity of the PAIR layout: 5 slots per 2 tets plus one pad per vertex
+constexpr int kSlotsAllocPair = 5 * (kTileTets / 2) + kTileVerts;
+
+template <typename T, int SS, int NSLOTS = kSlotsAlloc>
 __device__ __forceinline__ void store_slot_planes(T* sl, int s, const T* v) {
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int NQ = SS / VEC;  // full 16-byte planes; fp32 may add one 8-byte tail plane
@@ -262,21 +265,21 @@ __device__ __forceinline__ void store_slot_planes(T* sl, int s, const T* v) {
             const unsigned long long b = (unsigned long long)__double_as_longlong(v[2 * q + 1]);
             w = make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
         }
-        reinterpret_cast<uint4*>(sl)[q * kSlotsAlloc + s] = w;
+        reinterpret_cast<uint4*>(sl)[q * NSLOTS + s] = w;
     }
     if constexpr (sizeof(T) == 4 && SS % 4 == 2) {
-        float2* tail = reinterpret_cast<float2*>(reinterpret_cast<uint4*>(sl) + NQ * kSlotsAlloc);
+        float2* tail = reinterpret_cast<float2*>(reinterpret_cast<uint4*>(sl) + NQ * NSLOTS);
         tail[s] = make_float2((float)v[4 * NQ], (float)v[4 * NQ + 1]);
     }
 }
 
-template <typename T, int SS>
+template <typename T, int SS, int NSLOTS = kSlotsAlloc>
 __device__ __forceinline__ void load_slot_planes(const T* sl, int s, T* v) {
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int NQ = SS / VEC;
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
-        const uint4 w = reinterpret_cast<const uint4*>(sl)[q * kSlotsAlloc + s];
+        const uint4 w = reinterpret_cast<const uint4*>(sl)[q * NSLOTS + s];
         if constexpr (sizeof(T) == 4) {
             v[4 * q] = __uint_as_float(w.x); v[4 * q + 1] = __uint_as_float(w.y);
             v[4 * q + 2] = __uint_as_float(w.z); v[4 * q + 3] = __uint_as_float(w.w);
@@ -286,7 +289,7 @@ __device__ __forceinline__ void load_slot_planes(const T* sl, int s, T* v) {
         }
     }
     if constexpr (sizeof(T) == 4 && SS % 4 == 2) {
-        const float2* tail = reinterpret_cast<const float2*>(reinterpret_cast<const uint4*>(sl) + NQ * kSlotsAlloc);
+        const float2* tail = reinterpret_cast<const float2*>(reinterpret_cast<const uint4*>(sl) + NQ * NSLOTS);
         const float2 w = tail[s];
         v[4 * NQ] = (T)w.x; v[4 * NQ + 1] = (T)w.y;
     }
@@ -377,7 +380,7 @@ __device__ __forceinline__ void tile_compute(const T* rec, uchar4 lc, ushort4 s4
 // parks the 3*NOUT sums in the vertex buffer at the vertex's ascending local id.  The 16 lanes of a
 // half warp handle 16 consecutive vertices whose ranges are an odd number of slots apart, so their
 // 16- and 8-byte reads hit distinct banks.
-template <typename T, int OPS, int NT = kTileTets>
+template <typename T, int OPS, int NT = kTileTets, int NSLOTS = kSlotsAlloc>
 __device__ __forceinline__ void tile_reduce(int tid, int n_verts, const unsigned char* vperm,
                                             const unsigned short* voff, const T* sl, T* vbuf) {
     using Cfg = TileCfg<T, OPS>;
@@ -401,7 +404,7 @@ __device__ __forceinline__ void tile_reduce(int tid, int n_verts, const unsigned
         for (int j = 0; j < 3 * NOUT; ++j) acc[j] = (T)0;
         for (int i = half; i < cnt; i += 2) {
             T val[SS];
-            load_slot_planes<T, SS>(sl, s0 + i, val);
+            load_slot_planes<T, SS, NSLOTS>(sl, s0 + i, val);
 #pragma unroll
             for (int j = 0; j < 3 * NOUT; ++j) acc[j] += val[j];
         }
@@ -490,7 +493,7 @@ __device__ __forceinline__ void tile_compute_pair(const T* recA, const T* recB, 
             for (int c = 0; c < 3; ++c) pack(g, dg, hp, c, shared_v[c]);
             T v[SS];
             pack(g, dg, hp, 3, v);
-            store_slot_planes<T, SS>(sl, sidx[3], v);
+            store_slot_planes<T, SS, kSlotsAllocPair>(sl, sidx[3], v);
         }
     }
     {   // second tet: corners (s0, s1, s2, apex B)
@@ -511,10 +514,10 @@ __device__ __forceinline__ void tile_compute_pair(const T* recA, const T* recB, 
                 pack(g, dg, hp, c, v);
 #pragma unroll
                 for (int j = 0; j < 3 * NOUT; ++j) v[j] += shared_v[c][j];
-                store_slot_planes<T, SS>(sl, sidx[c], v);
+                store_slot_planes<T, SS, kSlotsAllocPair>(sl, sidx[c], v);
             }
             pack(g, dg, hp, 3, v);
-            store_slot_planes<T, SS>(sl, sidx[4], v);
+            store_slot_planes<T, SS, kSlotsAllocPair>(sl, sidx[4], v);
         }
     }
 }
@@ -666,6 +669,8 @@ struct PipeCfg {
     // has 8 bytes of connectivity and 16 bytes of slot ids, i.e. 4 and 8 bytes per tet as in the TET layout)
     static constexpr int kConsumers = LAYOUT == APL_LAYOUT_PAIR ? kTileTets / 2 : kTileTets;
     static constexpr int kThreads = kConsumers + 32;
+    static constexpr int kNSlots = LAYOUT == APL_LAYOUT_PAIR ? kSlotsAllocPair : kSlotsAlloc;
+    static constexpr size_t kSlotBytes = (size_t)kNSlots * Cfg::SS * sizeof(T);
     static constexpr int NREC = RecSize<KIND>::value;
     static constexpr int NPL = Rec<T, NREC>::NPL;
     // one stage: per-tet static data + the gathered vertex fields (all offsets multiples of 16 bytes)
@@ -683,13 +688,13 @@ struct PipeCfg {
     static constexpr size_t kBarBytes = 128;
     // as many stages as fit the target number of CTAs per SM (>= 2 always, <= 4); vertex ring = stages + 1
     static constexpr size_t kBudget = (size_t)(sizeof(T) == 4 ? 74 : 113) * 1024 * kTileTets / 256;
-    static constexpr size_t kFixedBytes = Cfg::kSlotBytes + kBarBytes + kVtabBytes;
+    static constexpr size_t kFixedBytes = kSlotBytes + kBarBytes + kVtabBytes;
     static constexpr int kFit =
         (int)((kBudget > kFixedBytes ? kBudget - kFixedBytes : 0) / (kStageBytes + kVtabBytes));
     static constexpr int kStages = kFit < 2 ? 2 : (kFit > 4 ? 4 : kFit);
     static constexpr int kVring = kStages + 1;
     static constexpr size_t oSlotBuf = kBarBytes;
-    static constexpr size_t oVring = oSlotBuf + Cfg::kSlotBytes;
+    static constexpr size_t oVring = oSlotBuf + kSlotBytes;
     static constexpr size_t oStages = oVring + (size_t)kVring * kVtabBytes;
     static constexpr size_t kSmemBytes = oStages + (size_t)kStages * kStageBytes;
     // CTAs per SM the shared memory allows (227 KB per SM, 1 KB reserved per CTA): the register budget of
@@ -858,8 +863,8 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS, LAYOUT>::kThreads, PipeC
                 if (!(g_knobs & 16))
 #endif
                 consumer_sync_n<NC>();
-                tile_reduce<T, OPS, NC>(tid, n_verts, vt + PC::oVperm, reinterpret_cast<const unsigned short*>(vt + PC::oVoff),
-                                        sl, vbuf);
+                tile_reduce<T, OPS, NC, PC::kNSlots>(tid, n_verts, vt + PC::oVperm,
+                                                     reinterpret_cast<const unsigned short*>(vt + PC::oVoff), sl, vbuf);
 #ifdef APL_PROFILE_KNOBS
                 if (!(g_knobs & 16))
 #endif

@@ -477,7 +477,10 @@ void finish_tile(TileScratch& ws, HostTables& out, int64_t tile, const TileRange
     std::stable_sort(perm, perm + nv, [&](int a, int b) { return cnt[a] > cnt[b]; });
     int start[kTileVerts + 1], padv[kTileVerts], off[kTileVerts];
     start[0] = 0;
-    int pads_left = kSlotCap - nc * ni;   // >= nv: one pad per vertex is always affordable
+    // slot capacity of the kernels: every corner of a full tile plus one pad per vertex (fem_kernels.cuh:
+    // kSlotsAlloc / kSlotsAllocPair)
+    const int slot_cap = (nc == 5 ? 5 * (kTileTets / 2) : 4 * kTileTets) + kTileVerts;
+    int pads_left = slot_cap - nc * ni ;   // >= nv: one pad per vertex is always affordable
     for (int g0 = 0; g0 < nv; g0 += 16) {
         GroupSearch gs;
         gs.n = std::min(16, nv - g0);
