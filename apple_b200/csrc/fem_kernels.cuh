@@ -25,6 +25,14 @@
 #include "common.h"
 #include "elem_math.cuh"
 
+#ifdef APL_PROFILE_KNOBS
+namespace apl {
+__device__ int g_knobs = 0;   // profiling only (APL_KNOBS): skip REDs / reduce / slot stores / barriers / consumers
+}
+#endif
+
+#include "tile_logic.cuh"
+
 namespace apl {
 
 template <typename T>
@@ -74,10 +82,6 @@ __device__ __forceinline__ bool fem_skip(const FemArgs<T>& a, int joff) {
     if (a.skip_b >= 0 && __ldcg(a.scal + a.skip_b + joff) != 0.0) return true;
     return false;
 }
-
-#ifdef APL_PROFILE_KNOBS
-__device__ int g_knobs = 0;
-#endif
 
 // ---- small device helpers --------------------------------------------------------------------
 
@@ -136,16 +140,6 @@ __device__ __forceinline__ void red_row(double* base, int v, int ld, const doubl
     atomicAdd(q + 1, val[1]);
     atomicAdd(q + 2, val[2]);
 }
-
-template <typename T, int NREC>
-struct Rec {
-    static constexpr int VEC = 16 / (int)sizeof(T);
-    static constexpr int NPL = (NREC + VEC - 1) / VEC;
-    union {
-        uint4 q[NPL];
-        T s[NPL * VEC];
-    };
-};
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -213,207 +207,28 @@ __device__ __forceinline__ void finish_scalars(double e, double q, double* parti
     }
 }
 
-// ---- compile-time layout of one instantiation ---------------------------------------------------
-
-template <typename T, int OPS>
-struct TileCfg {
-    static constexpr bool kFun = (OPS & APL_OP_FUN) != 0;
-    static constexpr bool kGrad = (OPS & APL_OP_GRAD) != 0;
-    static constexpr bool kDiag = (OPS & APL_OP_HESS_DIAG) != 0;
-    static constexpr bool kProd = (OPS & APL_OP_HESS_PROD) != 0;
-    static constexpr bool kQuad = (OPS & APL_OP_HESS_QUAD) != 0;
-    static constexpr bool kNeedP = kProd || kQuad;
-    static constexpr int NOUT = (kGrad ? 1 : 0) + (kDiag ? 1 : 0) + (kProd ? 1 : 0);
-    // scalars per slot: 3*NOUT rounded up to whole 16-byte planes plus, for fp32, one 8-byte tail plane
-    static constexpr int SS = (NOUT == 0) ? 0
-                              : (NOUT == 1) ? 4
-                              : (sizeof(T) == 4) ? (NOUT == 2 ? 6 : 10) : (NOUT == 2 ? 6 : 10);
-    static constexpr int kNSlots = 4 * kTileTets + kTileVerts;
-    // per-vertex buffer: u (4 scalars) and p (4 scalars) during compute, then reused for the 3*NOUT
-    // reduced sums of each vertex between the reduce and the flush phase
-    static constexpr int VB = (3 * NOUT > 8) ? 12 : 8;
-    static constexpr size_t kVbufBytes = (size_t)kTileVerts * VB * sizeof(T);
-    static constexpr size_t kSlotBytes = (size_t)kNSlots * SS * sizeof(T);
-    static constexpr size_t kVoffRaw = ((size_t)(kTileVerts + 1) * 2 + 15) / 16 * 16;  // n_verts+1 uint16
-    static constexpr size_t kVoffBytes = NOUT ? kVoffRaw : 0;
-    static constexpr size_t kVpermBytes = NOUT ? (size_t)kTileVerts : 0;
-    // simple (unpipelined) kernel
-    static constexpr size_t kSmemBytes = kVbufBytes + kSlotBytes + kVoffBytes + kVpermBytes;
-};
-
-// real slots of a tile (4 per tet) plus one padding slot per vertex with an even valence
-constexpr int kSlotsAlloc = 4 * kTileTets + kTileVerts;
-
-// The slot buffer is split into 16-byte planes: vector q of slot s lives at sl + (q * kNSlots + s) * 16 B.
-// One thread reading consecutive slots of "its" vertex and a warp of such threads then touch
-// neighbouring 16-byte words (see tile_reduce), instead of words a whole slot stride apart.
-// slot capacity of the PAIR layout: 5 slots per 2 tets plus one pad per vertex
-constexpr int kSlotsAllocPair = 5 * (kTileTets / 2) + kTileVerts;
-
-template <typename T, int SS, int NSLOTS = kSlotsAlloc>
-__device__ __forceinline__ void store_slot_planes(T* sl, int s, const T* v) {
-    constexpr int VEC = 16 / (int)sizeof(T);
-    constexpr int NQ = SS / VEC;  // full 16-byte planes; fp32 may add one 8-byte tail plane
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-        uint4 w;
-        if constexpr (sizeof(T) == 4) {
-            w = make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
-                           __float_as_uint(v[4 * q + 3]));
-        } else {
-            const unsigned long long a = (unsigned long long)__double_as_longlong(v[2 * q]);
-            const unsigned long long b = (unsigned long long)__double_as_longlong(v[2 * q + 1]);
-            w = make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
-        }
-        reinterpret_cast<uint4*>(sl)[q * NSLOTS + s] = w;
-    }
-    if constexpr (sizeof(T) == 4 && SS % 4 == 2) {
-        float2* tail = reinterpret_cast<float2*>(reinterpret_cast<uint4*>(sl) + NQ * NSLOTS);
-        tail[s] = make_float2((float)v[4 * NQ], (float)v[4 * NQ + 1]);
-    }
-}
-
-template <typename T, int SS, int NSLOTS = kSlotsAlloc>
-__device__ __forceinline__ void load_slot_planes(const T* sl, int s, T* v) {
-    constexpr int VEC = 16 / (int)sizeof(T);
-    constexpr int NQ = SS / VEC;
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-        const uint4 w = reinterpret_cast<const uint4*>(sl)[q * NSLOTS + s];
-        if constexpr (sizeof(T) == 4) {
-            v[4 * q] = __uint_as_float(w.x); v[4 * q + 1] = __uint_as_float(w.y);
-            v[4 * q + 2] = __uint_as_float(w.z); v[4 * q + 3] = __uint_as_float(w.w);
-        } else {
-            v[2 * q] = __longlong_as_double((long long)(((unsigned long long)w.y << 32) | w.x));
-            v[2 * q + 1] = __longlong_as_double((long long)(((unsigned long long)w.w << 32) | w.z));
-        }
-    }
-    if constexpr (sizeof(T) == 4 && SS % 4 == 2) {
-        const float2* tail = reinterpret_cast<const float2*>(reinterpret_cast<const uint4*>(sl) + NQ * NSLOTS);
-        const float2 w = tail[s];
-        v[4 * NQ] = (T)w.x; v[4 * NQ + 1] = (T)w.y;
-    }
-}
-
-template <typename T, int SS>
-__device__ __forceinline__ void store_slot(T* dst, const T* v) {
-    if constexpr (sizeof(T) == 4) {
-        static_assert(SS % 4 == 0, "fp32 slots are whole float4s");
-#pragma unroll
-        for (int k = 0; k < SS / 4; ++k)
-            reinterpret_cast<float4*>(dst)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-    } else {
-        static_assert(SS % 2 == 0, "fp64 slots are whole double2s");
-#pragma unroll
-        for (int k = 0; k < SS / 2; ++k) reinterpret_cast<double2*>(dst)[k] = make_double2(v[2 * k], v[2 * k + 1]);
-    }
-}
-
-template <typename T, int SS>
-__device__ __forceinline__ void load_slot(const T* src, T* v) {
-    if constexpr (sizeof(T) == 4) {
-#pragma unroll
-        for (int k = 0; k < SS / 4; ++k) {
-            const float4 q = reinterpret_cast<const float4*>(src)[k];
-            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < SS / 2; ++k) {
-            const double2 q = reinterpret_cast<const double2*>(src)[k];
-            v[2 * k] = q.x; v[2 * k + 1] = q.y;
-        }
-    }
-}
-
 // ---- the three per-tile phases shared by the simple and the pipelined kernel -----------------------
 
-// One tet: gather its corners from the shared vertex buffer, evaluate, write one slot per corner.
-template <typename T, int KIND, int OPS>
-__device__ __forceinline__ void tile_compute(const T* rec, uchar4 lc, ushort4 s4, const T* us, const T* ps, bool axpy,
-                                             T alpha, T* sl, double& e_acc, double& q_acc) {
-    using Cfg = TileCfg<T, OPS>;
-    constexpr int NOUT = Cfg::NOUT, SS = Cfg::SS;
-    T uc[4][3], pc[4][3];
-    const int l[4] = {lc.x, lc.y, lc.z, lc.w};
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        T tmp[4];
-        load_slot<T, 4>(us + 4 * l[c], tmp);
-        uc[c][0] = tmp[0]; uc[c][1] = tmp[1]; uc[c][2] = tmp[2];
-        if constexpr (Cfg::kNeedP) {
-            load_slot<T, 4>(ps + 4 * l[c], tmp);
-            pc[c][0] = tmp[0]; pc[c][1] = tmp[1]; pc[c][2] = tmp[2];
-        } else {
-            if (axpy) {  // line-search trial point x + alpha p, never materialised in global memory
-                load_slot<T, 4>(ps + 4 * l[c], tmp);
-                uc[c][0] += alpha * tmp[0]; uc[c][1] += alpha * tmp[1]; uc[c][2] += alpha * tmp[2];
-            }
-        }
-    }
-    T psi = 0, quad = 0;
-    T g[4][3], dg[4][3], hp[4][3];
-    elem_eval<T, KIND, OPS>(rec, uc, pc, psi, quad, g, dg, hp);
-    if constexpr (Cfg::kFun) e_acc += (double)psi;
-    if constexpr (Cfg::kQuad) q_acc += (double)quad;
-    if constexpr (NOUT > 0) {
-        const int sidx[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            T v[SS];
-            int k = 0;
-            if constexpr (Cfg::kGrad) { v[k] = g[c][0]; v[k + 1] = g[c][1]; v[k + 2] = g[c][2]; k += 3; }
-            if constexpr (Cfg::kDiag) { v[k] = dg[c][0]; v[k + 1] = dg[c][1]; v[k + 2] = dg[c][2]; k += 3; }
-            if constexpr (Cfg::kProd) { v[k] = hp[c][0]; v[k + 1] = hp[c][1]; v[k + 2] = hp[c][2]; k += 3; }
-#pragma unroll
-            for (int j = 3 * NOUT; j < SS; ++j) v[j] = (T)0;
-#ifdef APL_PROFILE_KNOBS
-            if (g_knobs & 8) continue;
-#endif
-            store_slot_planes<T, SS>(sl, sidx[c], v);
-        }
-    }
-}
+// (tile_compute / tile_compute_pair and the per-lane part of the reduction live in tile_logic.cuh, which is
+// also compiled for the host by the test harness)
 
-// Two threads (lanes l and l+16 of a warp) together sum the slot range of one vertex, taken in valence
-// order (balanced trip counts, all consumer warps busy), combine with one shuffle, and the lower lane
-// parks the 3*NOUT sums in the vertex buffer at the vertex's ascending local id.  The 16 lanes of a
-// half warp handle 16 consecutive vertices whose ranges are an odd number of slots apart, so their
-// 16- and 8-byte reads hit distinct banks.
+// Lanes l and l+16 of a warp sum the two halves of a vertex's slot range (tile_reduce_lane), exchange with
+// one shuffle, and the lower lane parks the sums at the vertex's local id.
 template <typename T, int OPS, int NT = kTileTets, int NSLOTS = kSlotsAlloc>
 __device__ __forceinline__ void tile_reduce(int tid, int n_verts, const unsigned char* vperm,
                                             const unsigned short* voff, const T* sl, T* vbuf) {
     using Cfg = TileCfg<T, OPS>;
-    constexpr int NOUT = Cfg::NOUT, SS = Cfg::SS;
+    constexpr int NOUT = Cfg::NOUT;
     const int half = (tid >> 4) & 1;
     for (int t = (tid >> 5) * 16 + (tid & 15); t < ((n_verts + 15) & ~15); t += NT / 2) {   // NT consumer threads
         // (the bound is rounded up to 16 so that whole warps stay together for the shuffle below;
         //  out-of-range lanes have cnt = 0)
-        int v = 0, s0 = 0, cnt = 0;
-        if (t < n_verts) {
-            v = vperm[t];
-            // voff is in reduce order: bits 0..11 = first slot of the range, bits 12..15 = unused pad slots
-            // after it (tiling.cpp chooses order and pads so that the 16 lanes of a group start in
-            // distinct bank groups: conflict-free 16/8-byte loads).
-            const unsigned a0 = voff[t], a1 = voff[t + 1];
-            s0 = (int)(a0 & 0x0fffu);
-            cnt = (int)(a1 & 0x0fffu) - s0 - (int)(a0 >> 12);
-        }
+        int v;
         T acc[3 * NOUT];
-#pragma unroll
-        for (int j = 0; j < 3 * NOUT; ++j) acc[j] = (T)0;
-        for (int i = half; i < cnt; i += 2) {
-            T val[SS];
-            load_slot_planes<T, SS, NSLOTS>(sl, s0 + i, val);
-#pragma unroll
-            for (int j = 0; j < 3 * NOUT; ++j) acc[j] += val[j];
-        }
+        tile_reduce_lane<T, OPS, NSLOTS>(half, t, n_verts, vperm, voff, sl, v, acc);
 #pragma unroll
         for (int j = 0; j < 3 * NOUT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
-        if (half == 0 && t < n_verts) {
-#pragma unroll
-            for (int j = 0; j < 3 * NOUT; ++j) vbuf[v * (3 * NOUT) + j] = acc[j];
-        }
+        if (half == 0 && t < n_verts) tile_reduce_park<T, OPS>(vbuf, v, acc);
     }
 }
 
@@ -425,8 +240,7 @@ __device__ __forceinline__ void tile_flush(int tid, int n_verts, int gv, const T
     constexpr int NOUT = Cfg::NOUT;
     if (tid < n_verts) {
         T acc[3 * NOUT];
-#pragma unroll
-        for (int j = 0; j < 3 * NOUT; ++j) acc[j] = vbuf[tid * (3 * NOUT) + j];
+        tile_flush_read<T, OPS>(vbuf, tid, acc);
         int k = 0;
 #ifdef APL_PROFILE_KNOBS
         if (g_knobs & 1) return;
@@ -440,85 +254,6 @@ __device__ __forceinline__ void tile_flush(int tid, int n_verts, int gv, const T
         if constexpr (Cfg::kGrad) { if (a.grad) red_row(a.grad, gv, a.ld_out, acc + k); k += 3; }
         if constexpr (Cfg::kDiag) { if (a.diag) red_row(a.diag, gv, a.ld_out, acc + k); k += 3; }
         if constexpr (Cfg::kProd) { if (a.prod) red_row(a.prod, gv, a.ld_out, acc + k); k += 3; }
-    }
-}
-
-// PAIR layout: one consumer thread evaluates two tets that share a face.  conn5 / slots5: the shared face
-// (s0, s1, s2), the apex of the first and the apex of the second tet; both records are packed in the corner order
-// (s0, s1, s2, apex), so the contributions of the three shared corners are added in registers and the pair
-// gathers 5 vertices and writes 5 slots instead of 8.
-template <typename T, int KIND, int OPS>
-__device__ __forceinline__ void tile_compute_pair(const T* recA, const T* recB, uint2 c8, uint4 s8, const T* us,
-                                                  const T* ps, bool axpy, T alpha, T* sl, double& e_acc, double& q_acc) {
-    using Cfg = TileCfg<T, OPS>;
-    constexpr int NOUT = Cfg::NOUT, SS = Cfg::SS;
-    const int l[5] = {(int)(c8.x & 0xffu), (int)((c8.x >> 8) & 0xffu), (int)((c8.x >> 16) & 0xffu), (int)(c8.x >> 24),
-                      (int)(c8.y & 0xffu)};
-    T U[5][3], P[5][3];
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        T tmp[4];
-        load_slot<T, 4>(us + 4 * l[c], tmp);
-        U[c][0] = tmp[0]; U[c][1] = tmp[1]; U[c][2] = tmp[2];
-        if constexpr (Cfg::kNeedP) {
-            load_slot<T, 4>(ps + 4 * l[c], tmp);
-            P[c][0] = tmp[0]; P[c][1] = tmp[1]; P[c][2] = tmp[2];
-        } else {
-            if (axpy) {  // line-search trial point x + alpha p
-                load_slot<T, 4>(ps + 4 * l[c], tmp);
-                U[c][0] += alpha * tmp[0]; U[c][1] += alpha * tmp[1]; U[c][2] += alpha * tmp[2];
-            }
-        }
-    }
-    const int sidx[5] = {(int)(s8.x & 0xffffu), (int)(s8.x >> 16), (int)(s8.y & 0xffffu), (int)(s8.y >> 16),
-                         (int)(s8.z & 0xffffu)};
-    // packs corner c of one evaluation into a slot value
-    auto pack = [&](const T (*g)[3], const T (*dg)[3], const T (*hp)[3], int c, T* v) {
-        int k = 0;
-        if constexpr (Cfg::kGrad) { v[k] = g[c][0]; v[k + 1] = g[c][1]; v[k + 2] = g[c][2]; k += 3; }
-        if constexpr (Cfg::kDiag) { v[k] = dg[c][0]; v[k + 1] = dg[c][1]; v[k + 2] = dg[c][2]; k += 3; }
-        if constexpr (Cfg::kProd) { v[k] = hp[c][0]; v[k + 1] = hp[c][1]; v[k + 2] = hp[c][2]; k += 3; }
-#pragma unroll
-        for (int j = 3 * NOUT; j < SS; ++j) v[j] = (T)0;
-    };
-    T shared_v[3][SS > 0 ? SS : 1];
-    {   // first tet: corners (s0, s1, s2, apex A)
-        T psi = 0, quad = 0;
-        T g[4][3], dg[4][3], hp[4][3];
-        elem_eval<T, KIND, OPS>(recA, U, P, psi, quad, g, dg, hp);   // rows 0..3 of U / P
-        if constexpr (Cfg::kFun) e_acc += (double)psi;
-        if constexpr (Cfg::kQuad) q_acc += (double)quad;
-        if constexpr (NOUT > 0) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) pack(g, dg, hp, c, shared_v[c]);
-            T v[SS];
-            pack(g, dg, hp, 3, v);
-            store_slot_planes<T, SS, kSlotsAllocPair>(sl, sidx[3], v);
-        }
-    }
-    {   // second tet: corners (s0, s1, s2, apex B)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            U[3][i] = U[4][i];
-            if constexpr (Cfg::kNeedP) P[3][i] = P[4][i];
-        }
-        T psi = 0, quad = 0;
-        T g[4][3], dg[4][3], hp[4][3];
-        elem_eval<T, KIND, OPS>(recB, U, P, psi, quad, g, dg, hp);
-        if constexpr (Cfg::kFun) e_acc += (double)psi;
-        if constexpr (Cfg::kQuad) q_acc += (double)quad;
-        if constexpr (NOUT > 0) {
-            T v[SS];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                pack(g, dg, hp, c, v);
-#pragma unroll
-                for (int j = 0; j < 3 * NOUT; ++j) v[j] += shared_v[c][j];
-                store_slot_planes<T, SS, kSlotsAllocPair>(sl, sidx[c], v);
-            }
-            pack(g, dg, hp, 3, v);
-            store_slot_planes<T, SS, kSlotsAllocPair>(sl, sidx[4], v);
-        }
     }
 }
 

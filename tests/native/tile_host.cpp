@@ -1,0 +1,144 @@
+// TEST-ONLY harness: compiles apple_b200/csrc/tile_logic.cuh (the consumer-side logic of the element kernels:
+// record / connectivity decoding, corner gather, slot stores of the TET and the PAIR layout, per-lane slot
+// reduction, parked sums) for the HOST and replays it thread by thread, tile by tile, on the packed tables of a
+// host-only handle.  What the GPU adds on top -- the producer's bulk copies, the mbarriers, the half-warp
+// shuffle and the global REDs -- is emulated here in the obvious way.  Never part of the product library.
+#include <cstdint>
+#include <vector>
+
+#include "../../apple_b200/csrc/tile_logic.cuh"
+
+using namespace apl;
+
+template <typename T, int KIND, int OPS, int LAYOUT>
+static void run(int64_t n_tiles, const int32_t* tiles, const uint8_t* conn, const uint16_t* slots,
+                const int32_t* tile_verts, const uint16_t* tile_voff, const uint8_t* tile_vperm, const T* planes,
+                int64_t plane_stride, const T* u, const T* p, T* grad, T* diag, T* prod, double* fun, double* quad) {
+    using Cfg = TileCfg<T, OPS>;
+    constexpr int NOUT = Cfg::NOUT, SS = Cfg::SS;
+    constexpr int NREC = RecSize<KIND>::value;
+    constexpr bool kPair = LAYOUT == APL_LAYOUT_PAIR;
+    constexpr int NC = kPair ? kTileTets / 2 : kTileTets;                 // consumer threads
+    constexpr int NSLOTS = kPair ? kSlotsAllocPair : kSlotsAlloc;
+    constexpr int VEC = 16 / (int)sizeof(T);
+    std::vector<T> vbuf((size_t)kTileVerts * (Cfg::VB > 8 ? Cfg::VB : 8) + 16), sl((size_t)NSLOTS * (SS > 0 ? SS : 1) + 16);
+    double e_acc = 0, q_acc = 0;
+    for (int64_t tile = 0; tile < n_tiles; ++tile) {
+        const int32_t* h = tiles + 6 * tile;
+        const int ts = h[0], n_tets = h[1], vs = h[2], n_verts = h[3], vo = h[4];
+        // producer: gather the tile's vertices into 4-scalar rows (u, then p)
+        T* us = vbuf.data();
+        T* ps = vbuf.data() + 4 * kTileVerts;
+        for (int v = 0; v < n_verts; ++v) {
+            const int gv = tile_verts[vs + v];
+            for (int i = 0; i < 3; ++i) {
+                us[4 * v + i] = u[3 * (int64_t)gv + i];
+                ps[4 * v + i] = p[3 * (int64_t)gv + i];
+            }
+            us[4 * v + 3] = ps[4 * v + 3] = (T)0;
+        }
+        for (auto& x : sl) x = (T)(0.0 / 0.0);   // NaN: a slot that is read without having been written shows up
+        // compute phase: one consumer thread per tet / per pair
+        auto load_rec = [&](int64_t pos, Rec<T, NREC>& r) {
+            for (int k = 0; k < Rec<T, NREC>::NPL; ++k)
+                for (int j = 0; j < VEC; ++j) r.s[k * VEC + j] = planes[((size_t)k * plane_stride + pos) * VEC + j];
+        };
+        if constexpr (kPair) {
+            const int n_items = n_tets >> 1;
+            for (int tid = 0; tid < NC; ++tid) {
+                if (tid >= n_items) continue;
+                Rec<T, NREC> ra, rb;
+                load_rec(ts + tid, ra);
+                load_rec(ts + n_items + tid, rb);
+                const uint8_t* c = conn + 8 * ((size_t)ts / 2 + tid);
+                const uint16_t* s = slots + 8 * ((size_t)ts / 2 + tid);
+                uint2 c8;
+                uint4 s8;
+                std::memcpy(&c8, c, 8);
+                std::memcpy(&s8, s, 16);
+                tile_compute_pair<T, KIND, OPS>(ra.s, rb.s, c8, s8, us, ps, false, (T)0, sl.data(), e_acc, q_acc);
+            }
+        } else {
+            for (int tid = 0; tid < NC; ++tid) {
+                if (tid >= n_tets) continue;
+                Rec<T, NREC> r;
+                load_rec(ts + tid, r);
+                uchar4 lc;
+                ushort4 s4;
+                std::memcpy(&lc, conn + 4 * ((size_t)ts + tid), 4);
+                std::memcpy(&s4, slots + 4 * ((size_t)ts + tid), 8);
+                tile_compute<T, KIND, OPS>(r.s, lc, s4, us, ps, false, (T)0, sl.data(), e_acc, q_acc);
+            }
+        }
+        if constexpr (NOUT > 0) {
+            // reduce phase: warp by warp, iteration by iteration; lanes l and l + 16 exchange through the shuffle
+            const unsigned char* vperm = tile_vperm + vs;
+            const unsigned short* voff = tile_voff + vo;
+            for (int warp = 0; warp < NC / 32; ++warp)
+                for (int t0 = warp * 16; t0 < ((n_verts + 15) & ~15); t0 += NC / 2) {
+                    int v[32];
+                    T acc[32][3 * NOUT];
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int tid = 32 * warp + lane, half = (tid >> 4) & 1;
+                        tile_reduce_lane<T, OPS, NSLOTS>(half, t0 + (tid & 15), n_verts, vperm, voff, sl.data(), v[lane], acc[lane]);
+                    }
+                    for (int lane = 0; lane < 16; ++lane) {
+                        T sum[3 * NOUT];
+                        for (int j = 0; j < 3 * NOUT; ++j) sum[j] = acc[lane][j] + acc[lane + 16][j];
+                        if (t0 + lane < n_verts) tile_reduce_park<T, OPS>(vbuf.data(), v[lane], sum);
+                    }
+                }
+            // flush phase: one RED per vertex and field
+            for (int v = 0; v < n_verts; ++v) {
+                T acc[3 * NOUT];
+                tile_flush_read<T, OPS>(vbuf.data(), v, acc);
+                const int64_t gv = tile_verts[vs + v];
+                int k = 0;
+                if constexpr (Cfg::kGrad) { for (int i = 0; i < 3; ++i) grad[3 * gv + i] += acc[k + i]; k += 3; }
+                if constexpr (Cfg::kDiag) { for (int i = 0; i < 3; ++i) diag[3 * gv + i] += acc[k + i]; k += 3; }
+                if constexpr (Cfg::kProd) { for (int i = 0; i < 3; ++i) prod[3 * gv + i] += acc[k + i]; k += 3; }
+            }
+        }
+    }
+    *fun += e_acc;
+    *quad += q_acc;
+}
+
+template <typename T, int KIND, int LAYOUT>
+static int by_ops(int ops, int64_t n_tiles, const int32_t* tiles, const uint8_t* conn, const uint16_t* slots,
+                  const int32_t* tv, const uint16_t* voff, const uint8_t* vperm, const void* planes, int64_t stride,
+                  const void* u, const void* p, void* grad, void* diag, void* prod, double* fun, double* quad) {
+#define GO(O)                                                                                                    \
+    run<T, KIND, O, LAYOUT>(n_tiles, tiles, conn, slots, tv, voff, vperm, (const T*)planes, stride, (const T*)u,  \
+                            (const T*)p, (T*)grad, (T*)diag, (T*)prod, fun, quad)
+    switch (ops) {
+        case 11: GO(11); return 0;
+        case 7: GO(7); return 0;
+        case 15: GO(15); return 0;
+        case 16: GO(16); return 0;
+        case 2: GO(2); return 0;
+        default: return -1;
+    }
+#undef GO
+}
+
+// layout: APL_LAYOUT_*; kind: APL_KIND_*; ops in {2, 7, 11, 15, 16}.  Outputs are accumulated (caller zeroes).
+extern "C" int tile_emulate(int layout, int kind, int is_f64, int ops, int64_t n_tiles, const int32_t* tiles,
+                            const uint8_t* conn, const uint16_t* slots, const int32_t* tv, const uint16_t* voff,
+                            const uint8_t* vperm, const void* planes, int64_t stride, const void* u, const void* p,
+                            void* grad, void* diag, void* prod, double* fun, double* quad) {
+#define ARGS ops, n_tiles, tiles, conn, slots, tv, voff, vperm, planes, stride, u, p, grad, diag, prod, fun, quad
+#define KINDS(T, L)                                                           \
+    switch (kind) {                                                           \
+        case APL_KIND_SNH: return by_ops<T, APL_KIND_SNH, L>(ARGS);           \
+        case APL_KIND_ARAP: return by_ops<T, APL_KIND_ARAP, L>(ARGS);         \
+        case APL_KIND_SNH_ARAP: return by_ops<T, APL_KIND_SNH_ARAP, L>(ARGS); \
+        default: return by_ops<T, APL_KIND_SNH_MUSCLE, L>(ARGS);              \
+    }
+    if (layout == APL_LAYOUT_PAIR) {
+        if (is_f64) { KINDS(double, APL_LAYOUT_PAIR) } else { KINDS(float, APL_LAYOUT_PAIR) }
+    } else {
+        if (is_f64) { KINDS(double, APL_LAYOUT_TET) } else { KINDS(float, APL_LAYOUT_TET) }
+    }
+    return -1;
+}

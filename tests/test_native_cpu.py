@@ -558,3 +558,86 @@ def test_pair_layout_tables_assemble_the_oracle_gradient(native_lib):
     ref = np.zeros_like(u); ora.grad(u, ref)
     np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
     assert n_paired > 0.85 * T                                        # the online matching pairs most tets
+
+
+@pytest.fixture(scope="module")
+def tile_host(tmp_path_factory):
+    out = tmp_path_factory.mktemp("native_tile") / "tile_host.so"
+    src = ROOT / "tests" / "native" / "tile_host.cpp"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", str(out), str(src)], check=True)
+    return ctypes.CDLL(str(out))
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-11), (np.float32, 1e-5)], ids=["f64", "f32"])
+@pytest.mark.parametrize("kind", ["snh", "arap", "muscle", "snh+arap"])
+@pytest.mark.parametrize("layout", [0, 1], ids=["tet", "pair"])
+def test_consumer_logic_replayed_on_the_host_matches_oracle(native_lib, tile_host, layout, kind, dtype, tol):
+    """The consumer-side DEVICE code of the element kernels (csrc/tile_logic.cuh: record / connectivity decoding,
+    corner gather, slot stores of both layouts, per-lane slot reduction with the tile_voff decoding, parked sums)
+    compiled for the host and replayed thread by thread on the packed tables and planes of a host-only handle ==
+    the oracle's assembled energy / gradient / diagonal / HVP / quadratic form."""
+    from apple_b200 import _lib
+    from oracle import fem as ofem
+    from oracle import region
+
+    mesh, u, p = make_case(n=6, seed=9, amp=0.12)
+    T, V = mesh.n_cells, mesh.n_points
+    dhdX, dV = region.compute_grad(mesh.points, mesh.cells, mesh.cell_data["Fraction"], dtype=dtype)
+    mu, la = mesh.cell_data["mu"].astype(dtype), mesh.cell_data["lambda"].astype(dtype)
+    act = mesh.cell_data["activation"].astype(dtype)
+    m2 = mesh.copy()
+    m2.cell_data["Fraction"] = 1.0 - 0.5 * mesh.cell_data["Fraction"]
+    m2.cell_data["mu"] = mesh.cell_data["mu"][::-1].copy()
+    if kind == "snh+arap":
+        ora = ofem.Model([oracle_potential("snh", mesh), oracle_potential("arap", m2)], V)
+        dV2 = region.compute_grad(m2.points, m2.cells, m2.cell_data["Fraction"], dtype=dtype)[1]
+        mu2 = m2.cell_data["mu"].astype(dtype)
+    else:
+        ora = ofem.Model([oracle_potential(kind, mesh)], V)
+    P = _lib.host_ptr
+    cells = np.ascontiguousarray(mesh.cells, dtype=np.int32); pts = np.ascontiguousarray(mesh.points)
+    code = _lib.F32 if dtype == np.float32 else _lib.F64
+    h = ctypes.c_void_p()
+    assert native_lib.apl_set_layout(layout) == 0
+    try:
+        if kind == "snh+arap":
+            rc = native_lib.apl_fem_create_snh_arap(code, T, V, P(cells), P(dhdX), P(dV), P(mu), P(la), P(dV2), P(mu2),
+                                                    P(pts), -1, ctypes.byref(h))
+        else:
+            k = {"snh": 0, "arap": 1, "muscle": 2}[kind]
+            rc = native_lib.apl_fem_create(k, code, T, V, P(cells), P(dhdX), P(dV), P(mu), P(la), P(act), P(pts), -1,
+                                           ctypes.byref(h))
+    finally:
+        native_lib.apl_set_layout(0)
+    assert rc == 0, native_lib.apl_last_error()
+    info = (ctypes.c_int64 * 10)(); native_lib.apl_fem_info(h, info)
+    nt, nv, nvo, npk = info[2], info[3], info[8], info[9]
+    rows, width = (npk // 2, 8) if layout == 1 else (T, 4)
+    tiles = np.zeros((nt, 6), np.int32); conn = np.zeros((rows, width), np.uint8); slots = np.zeros((rows, width), np.uint16)
+    tv = np.zeros(nv, np.int32); voff = np.zeros(nvo, np.uint16); vperm = np.zeros(nv, np.uint8)
+    native_lib.apl_fem_host_tables(h, P(tiles), None, P(conn), P(slots), P(tv), P(voff), P(vperm))
+    npl, stride = ctypes.c_int64(), ctypes.c_int64()
+    native_lib.apl_fem_host_planes(h, None, ctypes.byref(npl), ctypes.byref(stride))
+    planes = np.zeros((npl.value, stride.value, 16 // np.dtype(dtype).itemsize), dtype)
+    native_lib.apl_fem_host_planes(h, P(planes), None, None)
+    native_lib.apl_fem_destroy(h)
+
+    ud, pd = np.ascontiguousarray(u, dtype), np.ascontiguousarray(p, dtype)
+    ref = {"fun": ora.fun(u), "quad": ora.hess_quad(u, p), "grad": ora.grad(u), "diag": ora.hess_diag(u),
+           "prod": ora.hess_prod(u, p)}
+    kcode = {"snh": 0, "arap": 1, "muscle": 2, "snh+arap": 3}[kind]
+    tile_host.tile_emulate.argtypes = [ctypes.c_int] * 4 + [ctypes.c_int64] + [ctypes.c_void_p] * 7 + [ctypes.c_int64] + \
+        [ctypes.c_void_p] * 7
+    for ops in (11, 7, 16, 15):
+        grad, diag, prod = (np.zeros((V, 3), dtype) for _ in range(3))
+        fun, quad = np.zeros(1), np.zeros(1)
+        rc = tile_host.tile_emulate(layout, kcode, int(dtype == np.float64), ops, nt, P(tiles), P(conn), P(slots), P(tv),
+                                    P(voff), P(vperm), P(planes), stride.value, P(ud), P(pd), P(grad), P(diag), P(prod),
+                                    P(fun), P(quad))
+        assert rc == 0
+        got = {"fun": fun[0], "quad": quad[0], "grad": grad, "diag": diag, "prod": prod}
+        for bit, name in ((1, "fun"), (16, "quad"), (2, "grad"), (4, "diag"), (8, "prod")):
+            if ops & bit:
+                a, b = np.asarray(got[name], np.float64), np.asarray(ref[name])
+                assert np.isfinite(a).all(), (name, ops)                      # a NaN = a slot read before it was written
+                assert np.abs(a - b).max() <= tol * np.abs(b).max(), (layout, kind, ops, name)
