@@ -13,8 +13,9 @@ using namespace apl;
 template <typename T, int KIND, int OPS, int LAYOUT>
 static void run(int64_t n_tiles, const int32_t* tiles, const uint8_t* conn, const uint16_t* slots,
                 const int32_t* tile_verts, const uint16_t* tile_voff, const uint8_t* tile_vperm, const T* planes,
-                int64_t plane_stride, const T* u, const T* p, T* grad, T* diag, T* prod, double* fun, double* quad) {
+                int64_t plane_stride, const T* u, const T* p, double alpha, T* grad, T* diag, T* prod, double* fun, double* quad) {
     using Cfg = TileCfg<T, OPS>;
+    const bool axpy = alpha != 0.0;   // line-search trial point u + alpha p formed in the gather (PNCG pass A)
     constexpr int NOUT = Cfg::NOUT, SS = Cfg::SS;
     constexpr int NREC = RecSize<KIND>::value;
     constexpr bool kPair = LAYOUT == APL_LAYOUT_PAIR;
@@ -56,7 +57,7 @@ static void run(int64_t n_tiles, const int32_t* tiles, const uint8_t* conn, cons
                 uint4 s8;
                 std::memcpy(&c8, c, 8);
                 std::memcpy(&s8, s, 16);
-                tile_compute_pair<T, KIND, OPS>(ra.s, rb.s, c8, s8, us, ps, false, (T)0, sl.data(), e_acc, q_acc);
+                tile_compute_pair<T, KIND, OPS>(ra.s, rb.s, c8, s8, us, ps, axpy, (T)alpha, sl.data(), e_acc, q_acc);
             }
         } else {
             for (int tid = 0; tid < NC; ++tid) {
@@ -67,7 +68,7 @@ static void run(int64_t n_tiles, const int32_t* tiles, const uint8_t* conn, cons
                 ushort4 s4;
                 std::memcpy(&lc, conn + 4 * ((size_t)ts + tid), 4);
                 std::memcpy(&s4, slots + 4 * ((size_t)ts + tid), 8);
-                tile_compute<T, KIND, OPS>(r.s, lc, s4, us, ps, false, (T)0, sl.data(), e_acc, q_acc);
+                tile_compute<T, KIND, OPS>(r.s, lc, s4, us, ps, axpy, (T)alpha, sl.data(), e_acc, q_acc);
             }
         }
         if constexpr (NOUT > 0) {
@@ -107,10 +108,10 @@ static void run(int64_t n_tiles, const int32_t* tiles, const uint8_t* conn, cons
 template <typename T, int KIND, int LAYOUT>
 static int by_ops(int ops, int64_t n_tiles, const int32_t* tiles, const uint8_t* conn, const uint16_t* slots,
                   const int32_t* tv, const uint16_t* voff, const uint8_t* vperm, const void* planes, int64_t stride,
-                  const void* u, const void* p, void* grad, void* diag, void* prod, double* fun, double* quad) {
+                  const void* u, const void* p, double alpha, void* grad, void* diag, void* prod, double* fun, double* quad) {
 #define GO(O)                                                                                                    \
     run<T, KIND, O, LAYOUT>(n_tiles, tiles, conn, slots, tv, voff, vperm, (const T*)planes, stride, (const T*)u,  \
-                            (const T*)p, (T*)grad, (T*)diag, (T*)prod, fun, quad)
+                            (const T*)p, alpha, (T*)grad, (T*)diag, (T*)prod, fun, quad)
     switch (ops) {
         case 11: GO(11); return 0;
         case 7: GO(7); return 0;
@@ -122,12 +123,13 @@ static int by_ops(int ops, int64_t n_tiles, const int32_t* tiles, const uint8_t*
 #undef GO
 }
 
-// layout: APL_LAYOUT_*; kind: APL_KIND_*; ops in {2, 7, 11, 15, 16}.  Outputs are accumulated (caller zeroes).
+// layout: APL_LAYOUT_*; kind: APL_KIND_*; ops in {2, 7, 11, 15, 16}; alpha != 0 evaluates at u + alpha p (ops without
+// hess_prod / hess_quad only, as in PNCG's trial passes).  Outputs are accumulated (caller zeroes).
 extern "C" int tile_emulate(int layout, int kind, int is_f64, int ops, int64_t n_tiles, const int32_t* tiles,
                             const uint8_t* conn, const uint16_t* slots, const int32_t* tv, const uint16_t* voff,
                             const uint8_t* vperm, const void* planes, int64_t stride, const void* u, const void* p,
-                            void* grad, void* diag, void* prod, double* fun, double* quad) {
-#define ARGS ops, n_tiles, tiles, conn, slots, tv, voff, vperm, planes, stride, u, p, grad, diag, prod, fun, quad
+                            double alpha, void* grad, void* diag, void* prod, double* fun, double* quad) {
+#define ARGS ops, n_tiles, tiles, conn, slots, tv, voff, vperm, planes, stride, u, p, alpha, grad, diag, prod, fun, quad
 #define KINDS(T, L)                                                           \
     switch (kind) {                                                           \
         case APL_KIND_SNH: return by_ops<T, APL_KIND_SNH, L>(ARGS);           \

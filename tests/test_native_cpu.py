@@ -627,13 +627,13 @@ def test_consumer_logic_replayed_on_the_host_matches_oracle(native_lib, tile_hos
            "prod": ora.hess_prod(u, p)}
     kcode = {"snh": 0, "arap": 1, "muscle": 2, "snh+arap": 3}[kind]
     tile_host.tile_emulate.argtypes = [ctypes.c_int] * 4 + [ctypes.c_int64] + [ctypes.c_void_p] * 7 + [ctypes.c_int64] + \
-        [ctypes.c_void_p] * 7
+        [ctypes.c_void_p] * 2 + [ctypes.c_double] + [ctypes.c_void_p] * 5
     for ops in (11, 7, 16, 15):
         grad, diag, prod = (np.zeros((V, 3), dtype) for _ in range(3))
         fun, quad = np.zeros(1), np.zeros(1)
         rc = tile_host.tile_emulate(layout, kcode, int(dtype == np.float64), ops, nt, P(tiles), P(conn), P(slots), P(tv),
-                                    P(voff), P(vperm), P(planes), stride.value, P(ud), P(pd), P(grad), P(diag), P(prod),
-                                    P(fun), P(quad))
+                                    P(voff), P(vperm), P(planes), stride.value, P(ud), P(pd), 0.0, P(grad), P(diag),
+                                    P(prod), P(fun), P(quad))
         assert rc == 0
         got = {"fun": fun[0], "quad": quad[0], "grad": grad, "diag": diag, "prod": prod}
         for bit, name in ((1, "fun"), (16, "quad"), (2, "grad"), (4, "diag"), (8, "prod")):
@@ -641,3 +641,13 @@ def test_consumer_logic_replayed_on_the_host_matches_oracle(native_lib, tile_hos
                 a, b = np.asarray(got[name], np.float64), np.asarray(ref[name])
                 assert np.isfinite(a).all(), (name, ops)                      # a NaN = a slot read before it was written
                 assert np.abs(a - b).max() <= tol * np.abs(b).max(), (layout, kind, ops, name)
+    # PNCG's trial pass: energy / gradient / diagonal at u + alpha p, the trial point formed inside the gather
+    alpha = 0.01
+    grad, diag, prod = (np.zeros((V, 3), dtype) for _ in range(3))
+    fun, quad = np.zeros(1), np.zeros(1)
+    assert tile_host.tile_emulate(layout, kcode, int(dtype == np.float64), 7, nt, P(tiles), P(conn), P(slots), P(tv), P(voff),
+                                  P(vperm), P(planes), stride.value, P(ud), P(pd), alpha, P(grad), P(diag), P(prod), P(fun),
+                                  P(quad)) == 0
+    ut = u + alpha * p
+    for a, b in ((fun[0], ora.fun(ut)), (grad, ora.grad(ut)), (diag, ora.hess_diag(ut))):
+        assert np.abs(np.asarray(a, np.float64) - b).max() <= 3 * tol * np.abs(b).max(), (layout, kind, "axpy")
