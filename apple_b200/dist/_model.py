@@ -37,7 +37,9 @@ class ShardedOperators:
                 flags[idx] = 1
             self.n_boundary_tiles = int(local_model.mark_boundary(flags))
             self.overlap = True
-        self._side = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        # high priority: the pack / exchange / unpack kernels become ready together with the interior pass and
+        # must get SM resources first, otherwise the persistent interior kernel would simply run ahead of them
+        self._side = torch.cuda.Stream(self.device, priority=-1) if self.device.type == "cuda" else None
 
     def eval(self, ops: int, u, p=None):
         """Returns a dict with the requested results: fun / quad (0-d tensors, global), grad / diag /
