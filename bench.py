@@ -56,6 +56,10 @@ def parse_args():
     ap.add_argument("--graph", action="store_true", help="N>1, experimental: replay each step as one CUDA graph")
     ap.add_argument("--no-overlap", action="store_true",
                     help="N>1: do not overlap the halo exchange with the interior tiles (one launch, then exchange)")
+    ap.add_argument("--no-probe", action="store_true",
+                    help="N=1: do not run the experimental pair layout in a time-limited subprocess after the measurement")
+    ap.add_argument("--probe-parity", action="store_true",
+                    help="also compare energy / gradient / HVP of the model with the C oracle (used by the pair-layout probe)")
     ap.add_argument("--no-pncg", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
@@ -432,6 +436,18 @@ def main():
                 "frac": kern[dom]["gbs"] / peak, "traffic": traffic, "kernel": f"fem_pipe_kernel<{args.dtype},{dom},fun|grad|hess_prod>",
                 "peak_source": peak_src, "frac_of_nominal_8TBs": kern[dom]["gbs"] / 8000.0, "per_kernel": kern}
 
+    parity = None
+    if world == 1 and args.probe_parity:
+        # the whole model once against the C restatement of the reference (fp64) on the full mesh
+        pots_o, _, _ = oracle_model(mesh, kinds)
+        e_o, g_o, h_o = np.zeros(1), np.zeros((V, 3)), np.zeros((V, 3))
+        for po in pots_o:
+            po.fun(u, e_o); po.grad(u, g_o); po.hess_prod(u, p, h_o)
+        step(); torch.cuda.synchronize()
+        rel = lambda a, b: float(np.abs(np.asarray(a, np.float64) - b).max() / np.abs(b).max())  # noqa: E731
+        parity = {"energy": rel(fun.cpu().numpy(), e_o), "grad": rel(grad.cpu().numpy(), g_o),
+                  "hess_prod": rel(prod.cpu().numpy(), h_o), "against": "C oracle (fp64) on the full mesh"}
+
     # ---- e2e: host buffers through the public adapter API ----
     e2e = None
     if world == 1:
@@ -510,6 +526,28 @@ def main():
     if args.sweep and rank == 0 and world == 1:
         sweep(args, mesh, u, p, dtype, dev, flush)
 
+    # ---- experimental pair layout, in a time-limited subprocess (a kernel that has never run must not be able
+    #      to stall or crash the benchmark of the product layout) ----
+    probe = None
+    if rank == 0 and world == 1 and args.layout == "tet" and not args.no_probe:
+        cmd = [sys.executable, str(ROOT / "bench.py"), "--layout", "pair", "--steps", "10", "--warmup", "3", "--no-pncg",
+               "--no-cpu-baseline", "--no-probe", "--probe-parity", "--n", str(args.n), "--dtype", args.dtype,
+               "--potentials", args.potentials]
+        try:
+            pr = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+            last = [ln for ln in pr.stdout.strip().splitlines() if ln.startswith("{")]
+            if pr.returncode == 0 and last:
+                d = json.loads(last[-1])
+                probe = {"status": "ran", "value": d["value"], "ms_per_step": d["ms_per_step"],
+                         "roofline_frac": d["roofline"]["frac"], "parity_vs_oracle": d.get("parity"),
+                         "e2e": (d.get("e2e") or {}).get("value"), "speedup_vs_tet_layout": d["value"] / value}
+            else:
+                probe = {"status": f"failed (rc {pr.returncode})", "stderr_tail": pr.stderr[-400:]}
+        except subprocess.TimeoutExpired:
+            probe = {"status": "timeout (240 s): killed"}
+        except Exception as exc:  # pragma: no cover
+            probe = {"status": f"not run ({type(exc).__name__}: {exc})"}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -531,6 +569,10 @@ def main():
             "gpu_launches": args.steps * len(pots) * (2 if (world > 1 and sharded.overlap) else 1),
             "roofline": roofline, "cpu_baseline": cpu, "pncg": pncg,
         }
+        if parity is not None:
+            line["parity"] = parity
+        if probe is not None:
+            line["experimental_pair_layout"] = probe
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
