@@ -651,3 +651,15 @@ def test_consumer_logic_replayed_on_the_host_matches_oracle(native_lib, tile_hos
     ut = u + alpha * p
     for a, b in ((fun[0], ora.fun(ut)), (grad, ora.grad(ut)), (diag, ora.hess_diag(ut))):
         assert np.abs(np.asarray(a, np.float64) - b).max() <= 3 * tol * np.abs(b).max(), (layout, kind, "axpy")
+
+
+def test_tiling_is_deterministic_across_host_thread_counts(native_lib, monkeypatch):
+    """Tiles are packed in parallel (one scratch per host thread, per-tile random seeds): the tables must not depend
+    on the number of threads -- every rank of a sharded run and every rerun sees the same layout."""
+    mesh, _, _ = make_case(n=24, seed=0)          # 270 tiles: above the threshold of the parallel path
+    out = []
+    for threads in ("1", "5"):
+        monkeypatch.setenv("APL_TILING_THREADS", threads)
+        out.append(_host_tables(native_lib, mesh))
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
