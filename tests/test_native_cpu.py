@@ -663,3 +663,57 @@ def test_tiling_is_deterministic_across_host_thread_counts(native_lib, monkeypat
         out.append(_host_tables(native_lib, mesh))
     for a, b in zip(*out):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("layout", [0, 1], ids=["tet", "pair"])
+def test_unstructured_delaunay_mesh_through_the_host_replay(native_lib, tile_host, layout):
+    """An unstructured mesh (Delaunay tetrahedralisation of random points, cells in arbitrary order, uneven
+    valences): tiles close on the vertex budget as well as on the tet count, the online pairing leaves more tets
+    alone -- the replayed consumer logic must still assemble the oracle's energy / gradient / HVP."""
+    scipy_spatial = pytest.importorskip("scipy.spatial")
+    from apple_b200 import _lib
+    from apple_b200.mesh import TetMesh
+    from oracle import fem as ofem
+    from oracle import region
+
+    rng = np.random.default_rng(1)
+    pts = rng.random((1500, 3))
+    cells = scipy_spatial.Delaunay(pts).simplices.astype(np.int32)
+    X = pts[cells]
+    vol = np.einsum("ci,ci->c", np.cross(X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]), X[:, 3] - X[:, 0])
+    cells[vol < 0] = cells[vol < 0][:, [0, 2, 1, 3]]
+    cells = np.ascontiguousarray(cells[np.abs(vol) > 1e-6])          # drop slivers (their dhdX is huge)
+    mesh = TetMesh(pts, cells)
+    T, V = mesh.n_cells, mesh.n_points
+    dhdX, dV = region.compute_grad(mesh.points, mesh.cells)
+    mu, la = rng.uniform(1, 3, T), rng.uniform(1, 9, T)
+    u, p = 0.003 * rng.standard_normal((V, 3)), rng.standard_normal((V, 3))
+    ora = ofem.Model([ofem.StableNeoHookean(mesh.cells, dhdX, dV, mu=mu, lambda_=la)], V)
+    P = _lib.host_ptr
+    h = ctypes.c_void_p()
+    native_lib.apl_set_layout(layout)
+    try:
+        rc = native_lib.apl_fem_create(0, _lib.F64, T, V, P(cells), P(dhdX), P(dV), P(mu), P(la), None,
+                                       P(np.ascontiguousarray(pts)), -1, ctypes.byref(h))
+    finally:
+        native_lib.apl_set_layout(0)
+    assert rc == 0, native_lib.apl_last_error()
+    info = (ctypes.c_int64 * 10)(); native_lib.apl_fem_info(h, info)
+    nt, nv, nvo, npk = info[2], info[3], info[8], info[9]
+    rows, width = (npk // 2, 8) if layout else (T, 4)
+    tiles = np.zeros((nt, 6), np.int32); conn = np.zeros((rows, width), np.uint8); slots = np.zeros((rows, width), np.uint16)
+    tv = np.zeros(nv, np.int32); voff = np.zeros(nvo, np.uint16); vperm = np.zeros(nv, np.uint8)
+    native_lib.apl_fem_host_tables(h, P(tiles), None, P(conn), P(slots), P(tv), P(voff), P(vperm))
+    npl, stride = ctypes.c_int64(), ctypes.c_int64()
+    native_lib.apl_fem_host_planes(h, None, ctypes.byref(npl), ctypes.byref(stride))
+    planes = np.zeros((npl.value, stride.value, 2)); native_lib.apl_fem_host_planes(h, P(planes), None, None)
+    native_lib.apl_fem_destroy(h)
+    assert (tiles[:, 3] <= 192).all() and (tiles[:, 1] <= 256).all() and tiles[:, 1].sum() == npk
+    grad, diag, prod = (np.zeros((V, 3)) for _ in range(3))
+    fun, quad = np.zeros(1), np.zeros(1)
+    tile_host.tile_emulate.argtypes = [ctypes.c_int] * 4 + [ctypes.c_int64] + [ctypes.c_void_p] * 7 + [ctypes.c_int64] + \
+        [ctypes.c_void_p] * 2 + [ctypes.c_double] + [ctypes.c_void_p] * 5
+    assert tile_host.tile_emulate(layout, 0, 1, 11, nt, P(tiles), P(conn), P(slots), P(tv), P(voff), P(vperm), P(planes),
+                                  stride.value, P(u), P(p), 0.0, P(grad), P(diag), P(prod), P(fun), P(quad)) == 0
+    for a, b in ((fun[0], ora.fun(u)), (grad, ora.grad(u)), (prod, ora.hess_prod(u, p))):
+        assert np.abs(np.asarray(a) - b).max() <= 1e-11 * np.abs(b).max()
