@@ -705,8 +705,72 @@ static int build_tiles_pair(const int32_t* cells, bool f64, HostTables& out) {
         std::unordered_map<uint32_t, int32_t> waiting;   // sorted provisional ids of a face -> waiting item
         int64_t item_start = 0, first = 0, vert_end = 0, voff_end = 0;
         int32_t tile_id = 0;
+        auto face_key = [&](const int32_t* c, int skip) {
+            int l[3], n = 0;
+            for (int a = 0; a < 4; ++a)
+                if (a != skip) l[n++] = lid[(size_t)c[a]];
+            if (l[0] > l[1]) std::swap(l[0], l[1]);
+            if (l[1] > l[2]) std::swap(l[1], l[2]);
+            if (l[0] > l[1]) std::swap(l[0], l[1]);
+            return (uint32_t)(l[0] | (l[1] << 8) | (l[2] << 16));
+        };
+        // Tets left alone by the online matching: a single s whose neighbour t is paired with t', where t' has another
+        // single neighbour s', is re-paired as (s, t), (t', s') -- one item (and one zero-volume clone) fewer.
+        std::unordered_map<uint32_t, std::pair<int32_t, int32_t>> face_tets;   // face -> the (up to two) tets of the tile
+        auto rematch = [&]() {
+            const int64_t n_it = (int64_t)items.size() - item_start;
+            auto tet_of = [&](int32_t code) { const Item& it = items[(size_t)(item_start + (code >> 1))]; return (code & 1) ? it.b : it.a; };
+            face_tets.clear();
+            for (int64_t i = 0; i < n_it; ++i)
+                for (int w = 0; w < 2; ++w) {
+                    const int64_t cell = w ? items[(size_t)(item_start + i)].b : items[(size_t)(item_start + i)].a;
+                    if (cell < 0) continue;
+                    for (int skip = 0; skip < 4; ++skip) {
+                        auto r = face_tets.emplace(face_key(cells + 4 * cell, skip), std::make_pair((int32_t)(2 * i + w), (int32_t)-1));
+                        if (!r.second && r.first->second.second < 0) r.first->second.second = (int32_t)(2 * i + w);
+                    }
+                }
+            auto neighbour = [&](int32_t code, int skip) {   // the other tet of the tile across face `skip`, or -1
+                auto it = face_tets.find(face_key(cells + 4 * tet_of(code), skip));
+                if (it == face_tets.end()) return (int32_t)-1;
+                return it->second.first == code ? it->second.second : it->second.first;
+            };
+            for (int64_t i = 0; i < n_it; ++i) {
+                Item& si = items[(size_t)(item_start + i)];
+                if (si.a < 0 || si.b >= 0) continue;                       // not a single
+                bool done = false;
+                for (int f1 = 0; f1 < 4 && !done; ++f1) {
+                    const int32_t t = neighbour((int32_t)(2 * i), f1);
+                    if (t < 0 || (t >> 1) == i) continue;
+                    Item& ti = items[(size_t)(item_start + (t >> 1))];
+                    if (ti.a < 0 || ti.b < 0) continue;                    // the neighbour is not paired
+                    const int32_t tp = t ^ 1;                              // its partner t'
+                    for (int f2 = 0; f2 < 4 && !done; ++f2) {
+                        const int32_t s2 = neighbour(tp, f2);
+                        if (s2 < 0 || (s2 >> 1) == i || (s2 >> 1) == (t >> 1)) continue;
+                        Item& s2i = items[(size_t)(item_start + (s2 >> 1))];
+                        if (s2i.a < 0 || s2i.b >= 0) continue;             // s' must be a single too
+                        const int64_t ct = tet_of(t), ctp = tet_of(tp), cs = si.a, cs2 = s2i.a;
+                        si = {cs, ct};                                     // (s, t)
+                        ti = {ctp, cs2};                                   // (t', s')
+                        s2i = {-2, -2};                                    // removed (compacted below)
+                        done = true;
+                    }
+                }
+                if (done) {   // the codes stored in face_tets are stale now: rebuild and restart the scan
+                    std::vector<Item> kept;
+                    for (int64_t k = 0; k < n_it; ++k)
+                        if (items[(size_t)(item_start + k)].a != -2) kept.push_back(items[(size_t)(item_start + k)]);
+                    items.resize((size_t)item_start);
+                    items.insert(items.end(), kept.begin(), kept.end());
+                    return true;
+                }
+            }
+            return false;
+        };
         auto close_tile = [&]() {
             if ((int64_t)items.size() == item_start) return;
+            for (int guard = 0; guard < kItems && rematch(); ++guard) {}
             if (((int64_t)items.size() - item_start) % 2) items.push_back({-1, -1});   // tiles hold an even number of items
             const int ni = (int)((int64_t)items.size() - item_start);
             const int nv = (int)((int64_t)touched.size() - first);
@@ -719,15 +783,6 @@ static int build_tiles_pair(const int32_t* cells, bool f64, HostTables& out) {
             item_start = (int64_t)items.size();
             waiting.clear();
             ++tile_id;
-        };
-        auto face_key = [&](const int32_t* c, int skip) {
-            int l[3], n = 0;
-            for (int a = 0; a < 4; ++a)
-                if (a != skip) l[n++] = lid[(size_t)c[a]];
-            if (l[0] > l[1]) std::swap(l[0], l[1]);
-            if (l[1] > l[2]) std::swap(l[1], l[2]);
-            if (l[0] > l[1]) std::swap(l[0], l[1]);
-            return (uint32_t)(l[0] | (l[1] << 8) | (l[2] << 16));
         };
         for (int64_t pos = 0; pos < n_cells; ++pos) {
             const int64_t cell = morton[(size_t)pos];
