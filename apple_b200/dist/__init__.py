@@ -10,8 +10,8 @@ the PNCG dot products) are reduced over ``counted`` (owned) entries and all-redu
 """
 
 from ._halo import HaloExchange
-from ._partition import Shard, partition_mesh
+from ._partition import Shard, partition_mesh, slab_shard
 from ._pncg import ShardedPNCG
 from ._model import ShardedOperators
 
-__all__ = ["HaloExchange", "Shard", "ShardedOperators", "ShardedPNCG", "partition_mesh"]
+__all__ = ["HaloExchange", "Shard", "ShardedOperators", "ShardedPNCG", "partition_mesh", "slab_shard"]

@@ -63,3 +63,37 @@ def partition_mesh(mesh: TetMesh, world: int, rank: int) -> Shard:
             neighbors[s] = shared.astype(np.int64)   # l2g ascending => sorted by global id
     return Shard(rank=rank, world=world, mesh=local, l2g=l2g, owned=owned, cell_range=(lo, hi),
                  neighbors=neighbors, n_global_points=V, n_global_cells=T)
+
+
+def slab_shard(n: int, world: int, rank: int, *, grading: float = 1.0, morton: bool = True) -> Shard:
+    """Rank ``rank``'s part of the ``n``^3 x 5 cube, generated WITHOUT the global mesh: the hex layers
+    ``[rank n / world, (rank + 1) n / world)`` along the first grid axis (``cube_tet_slab``), locally Morton-ordered.
+    The halo plan is analytic: a rank shares exactly the grid plane ``i = i1`` with the next rank and ``i = i0`` with
+    the previous one; the lower rank owns the shared plane.  ``shard.mesh.point_data["gid"]`` /
+    ``cell_data["gid"]`` carry the global vertex / cell ids of the full lexicographic mesh, so that per-vertex and
+    per-cell fields can be defined as functions of the global id (``apple_b200.mesh.hash_uniform``) and agree across
+    partitions.  Used for the strong-scaling sweep on meshes too large to build on every rank."""
+    from apple_b200.mesh import cube_tet_slab, morton_reorder
+
+    if world > n:
+        raise ValueError("more ranks than hex layers")
+    bounds = [r * n // world for r in range(world + 1)]
+    i0, i1 = bounds[rank], bounds[rank + 1]
+    points, cells, vgid, cgid = cube_tet_slab(n, i0, i1, grading=grading)
+    mesh = TetMesh(points, cells, point_data={"gid": vgid}, cell_data={"gid": cgid})
+    if morton:
+        mesh = morton_reorder(mesh)
+    vgid = np.asarray(mesh.point_data["gid"], dtype=np.int64)
+    plane = (n + 1) * (n + 1)
+    layer = vgid // plane                                 # grid index i of every local vertex
+    neighbors = {}
+    for other, shared_layer in ((rank - 1, i0), (rank + 1, i1)):
+        if 0 <= other < world:
+            idx = np.flatnonzero(layer == shared_layer)
+            neighbors[other] = idx[np.argsort(vgid[idx], kind="stable")].astype(np.int64)   # both sides: by global id
+    owned = np.ones(vgid.size, dtype=bool)
+    if rank > 0:
+        owned[layer == i0] = False                        # the plane shared with the previous rank is owned by it
+    return Shard(rank=rank, world=world, mesh=mesh, l2g=vgid, owned=owned,
+                 cell_range=(5 * i0 * n * n, 5 * i1 * n * n), neighbors=neighbors,
+                 n_global_points=(n + 1) ** 3, n_global_cells=5 * n ** 3)

@@ -7,12 +7,15 @@ package accepts either a ``TetMesh`` or a real ``pyvista.UnstructuredGrid``.
 """
 
 from ._mesh import TetMesh, as_tet_arrays
-from ._generate import cube_tet_mesh, embedded_tetra_mesh, morton_reorder, lumped_vertex_volume
+from ._generate import (cube_tet_mesh, cube_tet_slab, embedded_tetra_mesh, hash_uniform, lumped_vertex_volume,
+                        morton_reorder)
 
 __all__ = [
     "TetMesh",
     "as_tet_arrays",
     "cube_tet_mesh",
+    "cube_tet_slab",
+    "hash_uniform",
     "embedded_tetra_mesh",
     "lumped_vertex_volume",
     "morton_reorder",

@@ -96,6 +96,51 @@ def cube_tet_mesh(n, *, grading: float = 1.0, length: float = 1.0, morton: bool 
     return morton_reorder(mesh) if morton else mesh
 
 
+def cube_tet_slab(n: int, i0: int, i1: int, *, grading: float = 1.0, length: float = 1.0):
+    """The hex layers ``i0 <= i < i1`` (first grid axis) of ``cube_tet_mesh(n, morton=False)``, built WITHOUT the rest
+    of the cube: ``(points, cells, vertex_gid, cell_gid)`` with local vertex numbering, the global vertex ids
+    ``(i (n+1) + j) (n+1) + k`` and the global cell ids ``5 hex + t`` of the full lexicographic mesh.  A rank of a
+    sharded run generates only its slab (a 64 M-tet cube is 25 GB of numpy arrays as a whole)."""
+    def line(m):
+        if grading == 1.0:
+            return np.linspace(0.0, length, m + 1)
+        w = grading ** np.arange(m)
+        x = np.concatenate([[0.0], np.cumsum(w)])
+        return x / x[-1] * length
+
+    x = line(n)
+    X, Y, Z = np.meshgrid(x[i0:i1 + 1], x, x, indexing="ij")
+    points = np.stack([X, Y, Z], axis=-1).reshape(-1, 3)
+    ni = i1 - i0
+
+    def vid(i, j, k):          # local id of grid vertex (i0 + i, j, k)
+        return (i * (n + 1) + j) * (n + 1) + k
+
+    I, J, K = np.meshgrid(np.arange(ni), np.arange(n), np.arange(n), indexing="ij")
+    I, J, K = I.ravel(), J.ravel(), K.ravel()
+    corners = np.stack([vid(I + a, J + b, K + c) for a in (0, 1) for b in (0, 1) for c in (0, 1)], axis=1)
+    even = ((I + i0 + J + K) % 2) == 0                      # parity of the GLOBAL hex index
+    cells = np.where(even[:, None, None], corners[:, _EVEN], corners[:, _ODD]).reshape(-1, 4)
+    X4 = points[cells]
+    vol = np.einsum("ci,ci->c", np.cross(X4[:, 1] - X4[:, 0], X4[:, 2] - X4[:, 0]), X4[:, 3] - X4[:, 0])
+    neg = vol < 0
+    cells[neg] = cells[neg][:, [0, 2, 1, 3]]
+    vertex_gid = np.arange(points.shape[0], dtype=np.int64) + i0 * (n + 1) * (n + 1)
+    cell_gid = np.arange(cells.shape[0], dtype=np.int64) + 5 * i0 * n * n
+    return points, cells.astype(np.int32), vertex_gid, cell_gid
+
+
+def hash_uniform(ids, seed: int = 0) -> np.ndarray:
+    """Deterministic U[0, 1) per integer id (splitmix64): the same value for a global vertex / cell id on every
+    rank and for every partition, without generating the global array."""
+    with np.errstate(over="ignore"):
+        z = np.asarray(ids, dtype=np.uint64) + np.full(1, 0x9E3779B97F4A7C15, np.uint64) * np.uint64(seed + 1)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
+
+
 def embedded_tetra_mesh() -> TetMesh:
     """The reference's known-answer mesh: 5 points, 4 tets around an interior vertex
     (``tests/forward/test_static_simulation.py:16-55``)."""

@@ -60,6 +60,9 @@ def parse_args():
                     help="N=1: do not run the experimental pair layout in a time-limited subprocess after the measurement")
     ap.add_argument("--probe-parity", action="store_true",
                     help="also compare energy / gradient / HVP of the model with the C oracle (used by the pair-layout probe)")
+    ap.add_argument("--slab", action="store_true",
+                    help="config-5 style strong scaling: every rank GENERATES only its slab of the --n cube (no global "
+                         "mesh on any rank; fields are functions of the global ids); operators only, also at 1 GPU")
     ap.add_argument("--no-pncg", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
@@ -92,10 +95,34 @@ def build_mesh(n, seed=0):
     return mesh, np.ascontiguousarray(u), np.ascontiguousarray(p)
 
 
+def build_slab(n, world, rank):
+    """This rank's slab of the n^3 x 5 cube (apple_b200.dist.slab_shard) with the fields of `build_mesh` redefined as
+    functions of the GLOBAL vertex / cell ids, so that every partition of the same cube evaluates the same model."""
+    from apple_b200.common import lame_converter
+    from apple_b200.dist import slab_shard
+    from apple_b200.mesh import hash_uniform
+
+    shard = slab_shard(n, world, rank)
+    mesh = shard.mesh
+    cg, vg = mesh.cell_data["gid"], mesh.point_data["gid"]
+    E = 10.0 ** (4.0 + hash_uniform(cg, 1))
+    nu = 0.3 + 0.15 * hash_uniform(cg, 2)
+    la, mu = lame_converter(E, nu)
+    mesh.cell_data["mu"] = mu
+    mesh.cell_data["lambda"] = la
+    h = 1.0 / n
+    X = mesh.points
+    noise = np.stack([hash_uniform(3 * vg + k, 3) for k in range(3)], axis=1)
+    u = 0.05 * h * np.sin(7.0 * X[:, [1, 2, 0]] + 0.3) + 0.02 * h * (2.0 * noise - 1.0)
+    p = 2.0 * np.stack([hash_uniform(3 * vg + k, 4) for k in range(3)], axis=1) - 1.0
+    return shard, mesh, np.ascontiguousarray(u), np.ascontiguousarray(p)
+
+
 def workload_name(args, mesh, kinds):
     """config.workload, shared by both arms."""
-    return (f"cube {args.n}^3x5 = {mesh.n_cells} tets / {mesh.n_points} verts, {'+'.join(kinds)}, "
-            f"fused energy+grad+HVP")
+    T, V = (5 * args.n ** 3, (args.n + 1) ** 3) if getattr(args, "slab", False) else (mesh.n_cells, mesh.n_points)
+    return (f"cube {args.n}^3x5 = {T} tets / {V} verts, {'+'.join(kinds)}, fused energy+grad+HVP"
+            + (" (per-rank slab generation)" if getattr(args, "slab", False) else ""))
 
 
 def algorithmic_bytes_per_tet(kind, w, v_over_t, per_vertex_words):
@@ -294,8 +321,15 @@ def main():
     config.layout = {"tet": _lib.LAYOUT_TET, "pair": _lib.LAYOUT_PAIR}[args.layout]
     kinds = args.potentials.split(",")
 
-    mesh, u, p = build_mesh(args.n)
-    T_total, V = mesh.n_cells, mesh.n_points
+    shard = None
+    if args.slab:
+        shard, mesh, u, p = build_slab(args.n, world, rank)     # `mesh`, `u`, `p` are this rank's slab only
+        T_total, V = shard.n_global_cells, shard.n_global_points
+        args.no_pncg = args.no_cpu_baseline = args.no_probe = True
+        args.scaling = "strong"
+    else:
+        mesh, u, p = build_mesh(args.n)
+        T_total, V = mesh.n_cells, mesh.n_points
     OPS = _lib.OP_FUN | _lib.OP_GRAD | _lib.OP_HESS_PROD
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
@@ -303,7 +337,7 @@ def main():
         if not args.no_flush:
             flush_buf.fill_(1)
 
-    if world == 1:
+    if world == 1 and not args.slab:
         lo, hi = 0, T_total
         pots = {k: cuda_potential(k, mesh, dtype, name=k) for k in kinds}
         if not args.no_fuse:
@@ -324,14 +358,16 @@ def main():
         # the vertices they touch; one halo sum (all-to-all of the shared rows) + one scalar all-reduce
         from apple_b200.dist import ShardedOperators, partition_mesh
 
-        shard = partition_mesh(mesh, world, rank)
+        if shard is None:
+            shard = partition_mesh(mesh, world, rank)
+            u, p = u[shard.l2g], p[shard.l2g]
         lo, hi = shard.cell_range
         pots = {k: cuda_potential(k, shard.mesh, dtype, name=k) for k in kinds}
         if not args.no_fuse:
             pots = fuse_potentials(pots)
         sharded = ShardedOperators(WarpModel(pots), shard, dev, dtype, overlap=not args.no_overlap)
-        ud = torch.as_tensor(u[shard.l2g], dtype=dtype, device=dev).contiguous()
-        pd = torch.as_tensor(p[shard.l2g], dtype=dtype, device=dev).contiguous()
+        ud = torch.as_tensor(u, dtype=dtype, device=dev).contiguous()
+        pd = torch.as_tensor(p, dtype=dtype, device=dev).contiguous()
         fun = torch.zeros(1, dtype=dtype, device=dev)
         grad = torch.zeros((shard.n_local, 3), dtype=dtype, device=dev)
         prod = torch.zeros((shard.n_local, 3), dtype=dtype, device=dev)
@@ -409,7 +445,7 @@ def main():
 
     # ---- per-kernel roofline (each potential's fused kernel timed alone, L2 flushed) ----
     peak, peak_src = measured_peak_gbs()
-    v_over_t = (V if world == 1 else shard.n_local) / max(hi - lo, 1)
+    v_over_t = (shard.n_local if shard is not None else V) / max(hi - lo, 1)
     kern = {}
     for k, pot in pots.items():
         ts = []
@@ -437,7 +473,7 @@ def main():
                 "peak_source": peak_src, "frac_of_nominal_8TBs": kern[dom]["gbs"] / 8000.0, "per_kernel": kern}
 
     parity = None
-    if world == 1 and args.probe_parity:
+    if world == 1 and args.probe_parity and not args.slab:
         # the whole model once against the C restatement of the reference (fp64) on the full mesh
         pots_o, _, _ = oracle_model(mesh, kinds)
         e_o, g_o, h_o = np.zeros(1), np.zeros((V, 3)), np.zeros((V, 3))
@@ -450,7 +486,7 @@ def main():
 
     # ---- e2e: host buffers through the public adapter API ----
     e2e = None
-    if world == 1:
+    if world == 1 and not args.slab:
         uh = torch.as_tensor(u, dtype=dtype).pin_memory()
         ph = torch.as_tensor(p, dtype=dtype).pin_memory()
         gh = torch.empty((V, 3), dtype=dtype).pin_memory()
@@ -552,7 +588,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": args.scaling if world > 1 else "weak",
+            "scaling": args.scaling if (world > 1 or args.slab) else "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload_name(args, mesh, kinds), "assembly": args.scatter, "layout": args.layout,
                        "l2": "256 MiB flush write between timed steps" if not args.no_flush else "no flush",

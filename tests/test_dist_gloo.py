@@ -42,13 +42,21 @@ class _OracleLocalModel:
                 sub.cells, sub.dhdX, sub.dV = pot.cells[sel], pot.dhdX[sel], pot.dV[sel]
                 sub.materials = {k: np.asarray(v)[sel] for k, v in pot.materials.items()}
                 parts[part].append(sub)
-        self.m[1] = ofem.Model(parts[1], self.n_points)
-        self.m[2] = ofem.Model(parts[2], self.n_points)
+        for part in (1, 2):       # a thin slab may have no interior cells at all
+            nonempty = [q for q in parts[part] if len(q.cells)]
+            self.m[part] = ofem.Model(nonempty, self.n_points) if nonempty else None
         return n_boundary
 
     def eval(self, ops, u, p=None, *, fun=None, quad=None, grad=None, diag=None, prod=None, scatter=None, part=0,
              zero=True):
         m = self.m[part]
+        if zero:
+            for o in (fun, quad, grad, diag, prod):
+                if o is not None:
+                    o.zero_()
+        if m is None:
+            return
+        zero = False
         un = u.numpy()
         pn = None if p is None else p.numpy()
         if zero:
@@ -152,3 +160,62 @@ def test_partition_is_deterministic_and_covers_four_ranks():
             # both sides list the shared vertices in the same (global id) order
             assert np.array_equal(s.l2g[idx], other.l2g[other.neighbors[s.rank]])
     assert (owned == 1).all()
+
+
+def _slab_worker(rank, world, port, out, n):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from apple_b200 import _lib
+        from apple_b200.dist import ShardedOperators, slab_shard
+        from apple_b200.mesh import hash_uniform
+        from oracle import fem as ofem
+        from oracle import region
+
+        shard = slab_shard(n, world, rank)                       # this rank's slab only: no global mesh
+        m = shard.mesh
+        cg, vg = m.cell_data["gid"], m.point_data["gid"]
+        mu = 1.0 + 2.0 * hash_uniform(cg, 1); la = 1.0 + 8.0 * hash_uniform(cg, 2)      # functions of the GLOBAL ids
+        u = 0.01 * (np.stack([hash_uniform(3 * vg + k, 3) for k in range(3)], 1) - 0.5)
+        p = np.stack([hash_uniform(3 * vg + k, 4) for k in range(3)], 1) - 0.5
+        dhdX, dV = region.compute_grad(m.points, m.cells)
+        pots = [ofem.StableNeoHookean(m.cells, dhdX, dV, mu=mu, lambda_=la), ofem.Arap(m.cells, dhdX, dV, mu=mu)]
+        ops = ShardedOperators(_OracleLocalModel(pots, shard.n_local), shard, "cpu", torch.float64, overlap=True)
+        r = ops.eval(_lib.OP_FUN | _lib.OP_GRAD | _lib.OP_HESS_PROD, torch.from_numpy(u), torch.from_numpy(p))
+        out[rank] = {"gid": vg, "owned": shard.owned, "fun": float(r["fun"]), "grad": r["grad"].numpy(),
+                     "prod": r["prod"].numpy(), "n_cells": m.n_cells, "cells": shard.cell_range}
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_shards_generated_per_rank_match_the_whole_cube(world):
+    """slab_shard: every rank generates ONLY its hex layers of the cube (no global mesh), fields are functions of the
+    global ids; the sharded result equals the single-rank oracle on the whole cube."""
+    from apple_b200.mesh import cube_tet_mesh, hash_uniform
+    from oracle import fem as ofem
+    from oracle import region
+
+    n = 5
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_slab_worker, args=(world, _free_port(), out, n), nprocs=world, join=True)
+    full = cube_tet_mesh(n, morton=False)                        # global lexicographic mesh == the ids of the slabs
+    T, V = full.n_cells, full.n_points
+    cg, vg = np.arange(T), np.arange(V)
+    mu = 1.0 + 2.0 * hash_uniform(cg, 1); la = 1.0 + 8.0 * hash_uniform(cg, 2)
+    u = 0.01 * (np.stack([hash_uniform(3 * vg + k, 3) for k in range(3)], 1) - 0.5)
+    p = np.stack([hash_uniform(3 * vg + k, 4) for k in range(3)], 1) - 0.5
+    dhdX, dV = region.compute_grad(full.points, full.cells)
+    ref = ofem.Model([ofem.StableNeoHookean(full.cells, dhdX, dV, mu=mu, lambda_=la), ofem.Arap(full.cells, dhdX, dV, mu=mu)], V)
+    e, g, h = ref.fun(u), ref.grad(u), ref.hess_prod(u, p)
+    owners = np.zeros(V, int)
+    assert sum(out[r]["n_cells"] for r in range(world)) == T
+    for r in range(world):
+        o = out[r]
+        owners[o["gid"][o["owned"]]] += 1
+        assert abs(o["fun"] - e) <= 1e-12 * abs(e)
+        assert np.abs(o["grad"] - g[o["gid"]]).max() <= 1e-12 * np.abs(g).max()
+        assert np.abs(o["prod"] - h[o["gid"]]).max() <= 1e-12 * np.abs(h).max()
+    assert (owners == 1).all()
