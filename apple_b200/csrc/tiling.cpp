@@ -288,12 +288,12 @@ void color_local_ids(TileScratch& ws, int nt, int nc, int nv, const uint8_t* tl,
 
 // ---- 2. reduce order: conflict-free slot-range starts within every group of 16 vertices ------------
 // cnt[0..n): valences of the group's vertices (about descending).  Finds an order and per-vertex pads
-// (0..kMaxPad unused slots after the range, at most pad_budget in total) such that the n range starts are
+// (0..kMaxPad unused slots after the range, at most `pads_left` in total) such that the n range starts are
 // distinct mod 16 (8-byte plane; skipped when !mod16) and distinct mod 8 within positions 0..7 and 8..15
 // (16-byte planes).  Returns false when the bounded search fails.
 constexpr int kMaxPad = 3;
 struct GroupSearch {
-    int n, budget, pad_budget, target;
+    int n, budget, target;
     bool mod16;
     int cnt[16];
     bool taken[16];
@@ -480,7 +480,7 @@ void finish_tile(TileScratch& ws, HostTables& out, int64_t tile, const TileRange
     // slot capacity of the kernels: every corner of a full tile plus one pad per vertex (fem_kernels.cuh:
     // kSlotsAlloc / kSlotsAllocPair)
     const int slot_cap = (nc == 5 ? 5 * (kTileTets / 2) : 4 * kTileTets) + kTileVerts;
-    int pads_left = slot_cap - nc * ni ;   // >= nv: one pad per vertex is always affordable
+    int pads_left = slot_cap - nc * ni;   // >= nv: one pad per vertex is always affordable
     for (int g0 = 0; g0 < nv; g0 += 16) {
         GroupSearch gs;
         gs.n = std::min(16, nv - g0);
@@ -496,7 +496,6 @@ void finish_tile(TileScratch& ws, HostTables& out, int64_t tile, const TileRange
             if (attempt == 1 && f64) break;
             gs.mod16 = !f64 && attempt == 0;
             gs.budget = 1500;
-            gs.pad_budget = allowed;
             for (int i = 0; i < gs.n; ++i) gs.taken[i] = false;
             found = gs.dfs(0, start[g0], 0u, 0u, allowed);
         }
