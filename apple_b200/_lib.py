@@ -52,6 +52,7 @@ SIGNATURES = {
     "apl_fem_eval_part": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "apl_fem_mark_boundary": (c_int, [c_void_p, c_void_p, POINTER(c_int64)]),
+    "apl_fem_mixed_derivative_prod": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "apl_ext_force_eval": (c_int, [c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                    c_int, c_void_p]),
     "apl_field_copy": (c_int, [c_int, c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p]),

@@ -244,6 +244,82 @@ __global__ void halo_unpack_kernel(long long n_shared, const long long* __restri
     }
 }
 
+// ---- mixed derivative product (per cell, no assembly) ------------------------------------------------
+// One thread per packed tet position; gathers straight from global memory (a setup / adjoint-time operator, not
+// the hot path), works on both layouts: in the PAIR layout position j of a tile of ni items belongs to item
+// j mod ni and uses the corners (s0, s1, s2, apex of the first / second tet).
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256) fem_mixed_kernel(const int4* __restrict__ tiles, int n_tiles, int layout,
+                                                        const unsigned char* __restrict__ conn,
+                                                        const int* __restrict__ tile_verts, const uint4* __restrict__ planes,
+                                                        long long plane_stride, const int* __restrict__ order,
+                                                        const T* __restrict__ u, const T* __restrict__ p, int ld, T* d_mu,
+                                                        T* d_la, T* d_act) {
+    constexpr int NREC = RecSize<KIND>::value;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int4 h = __ldg(tiles + tile);
+        const int n_tets = h.y & 0xffff;
+        const int j = threadIdx.x;
+        if (j >= n_tets) continue;
+        const long long pos = (long long)h.x + j;
+        const int cell = __ldg(order + pos);
+        if (cell < 0) continue;   // zero-volume clone
+        int l[4];
+        if (layout == APL_LAYOUT_PAIR) {
+            const int ni = n_tets >> 1, item = j < ni ? j : j - ni;
+            const unsigned char* c = conn + 8ll * ((long long)(h.x >> 1) + item);
+            l[0] = c[0]; l[1] = c[1]; l[2] = c[2]; l[3] = j < ni ? c[3] : c[4];
+        } else {
+            const unsigned char* c = conn + 4ll * pos;
+            l[0] = c[0]; l[1] = c[1]; l[2] = c[2]; l[3] = c[3];
+        }
+        Rec<T, NREC> rec;
+#pragma unroll
+        for (int k = 0; k < Rec<T, NREC>::NPL; ++k) rec.q[k] = __ldg(planes + k * plane_stride + pos);
+        T uc[4][3], pc[4][3];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const long long gv = __ldg(tile_verts + h.z + l[c]);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                uc[c][i] = __ldg(u + gv * ld + i);
+                pc[c][i] = __ldg(p + gv * ld + i);
+            }
+        }
+        T m, la, act[6];
+        elem_mixed<T, KIND>(rec.s, uc, pc, m, la, act);
+        if (d_mu) d_mu[cell] = m;
+        if constexpr (KIND != APL_KIND_ARAP) { if (d_la) d_la[cell] = la; }
+        if constexpr (KIND == APL_KIND_SNH_MUSCLE) {
+            if (d_act)
+#pragma unroll
+                for (int k = 0; k < 6; ++k) d_act[6ll * cell + k] = act[k];
+        }
+    }
+}
+
+template <typename T>
+static int mixed_typed(apl_fem* f, const void* u, const void* p, int ld, void* d_mu, void* d_la, void* d_act,
+                       cudaStream_t stream) {
+    const int n_tiles = (int)f->host.n_tiles();
+    if (n_tiles == 0) return APL_OK;
+    int grid = f->num_sms * 8;
+    if (grid > n_tiles) grid = n_tiles;
+#define APL_MIXED(K)                                                                                              \
+    fem_mixed_kernel<T, K><<<grid, 256, 0, stream>>>((const int4*)f->d_tiles, n_tiles, f->host.layout,             \
+                                                     (const unsigned char*)f->d_conn, (const int*)f->d_tile_verts, \
+                                                     (const uint4*)f->d_planes, f->plane_stride, f->d_order,       \
+                                                     (const T*)u, (const T*)p, ld, (T*)d_mu, (T*)d_la, (T*)d_act)
+    switch (f->kind) {
+        case APL_KIND_SNH: APL_MIXED(APL_KIND_SNH); break;
+        case APL_KIND_ARAP: APL_MIXED(APL_KIND_ARAP); break;
+        default: APL_MIXED(APL_KIND_SNH_MUSCLE); break;
+    }
+#undef APL_MIXED
+    APL_CUDA_CHECK(cudaGetLastError());
+    return APL_OK;
+}
+
 static int grid_for(long long n, int block) {
     long long g = (n + block - 1) / block;
     if (g < 1) g = 1;
@@ -314,6 +390,7 @@ void apl_fem_destroy(apl_fem_t* f) {
         cudaFree(f->d_tile_voff);
         cudaFree(f->d_tile_vperm);
         cudaFree(f->d_planes);
+        cudaFree(f->d_order);
         cudaFree(f->d_partials);
         cudaFree(f->d_counter);
     }
@@ -600,6 +677,28 @@ int apl_fem_mark_boundary(apl_fem_t* f, const uint8_t* vertex_flags, int64_t* n_
         APL_CUDA_CHECK(cudaMemcpy(f->d_tiles, hdr.data(), hdr.size() * 4, cudaMemcpyHostToDevice));
     }
     return APL_OK;
+}
+
+int apl_fem_mixed_derivative_prod(apl_fem_t* f, const void* u, const void* p, int ld_in, void* d_mu, void* d_lambda,
+                                  void* d_activation, void* stream) {
+    if (!f) { set_error("apl_fem_mixed_derivative_prod: NULL handle"); return APL_ERR_INVALID; }
+    if (f->device < 0) { set_error("apl_fem_mixed_derivative_prod: handle was created host-only (device = -1)"); return APL_ERR_STATE; }
+    if (f->kind == APL_KIND_SNH_ARAP) {
+        set_error("apl_fem_mixed_derivative_prod: not available for fused potentials (evaluate the two parts separately)");
+        return APL_ERR_STATE;
+    }
+    if (!u || !p || (ld_in != 3 && ld_in != 4)) { set_error("apl_fem_mixed_derivative_prod: bad arguments"); return APL_ERR_INVALID; }
+    if (!f->d_order) {   // first use: packed tet position -> caller's cell, -1 for zero-volume clones
+        const int64_t n = f->host.n_packed();
+        std::vector<int32_t> ord((size_t)n + 1);
+        for (int64_t i = 0; i < n; ++i) ord[(size_t)i] = f->host.clone[(size_t)i] ? -1 : (int32_t)f->host.order[(size_t)i];
+        APL_CUDA_CHECK(cudaSetDevice(f->device));
+        APL_CUDA_CHECK(cudaMalloc((void**)&f->d_order, ((size_t)n + 1) * sizeof(int32_t)));
+        APL_CUDA_CHECK(cudaMemcpy(f->d_order, ord.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    return f->dtype == APL_F32 ? mixed_typed<float>(f, u, p, ld_in, d_mu, d_lambda, d_activation, s)
+                               : mixed_typed<double>(f, u, p, ld_in, d_mu, d_lambda, d_activation, s);
 }
 
 int apl_ext_force_eval(int dtype, int ops, int64_t k, const void* force, const int32_t* indices, const void* u,

@@ -62,6 +62,7 @@ struct apl_fem {
     void* d_tile_voff = nullptr;
     void* d_tile_vperm = nullptr;
     void* d_planes = nullptr;
+    int32_t* d_order = nullptr;     // packed tet position -> caller's cell (-1: clone); uploaded on first use
     double* d_partials = nullptr;   // per-CTA scalar partials (2 per CTA)
     unsigned int* d_counter = nullptr;
     int max_grid = 0;

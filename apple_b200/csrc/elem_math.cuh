@@ -749,4 +749,86 @@ APL_HD void elem_eval(const T* rec, const T (*uc)[3], const T (*pc)[3], T& psi, 
     if constexpr (kProd) vjp_rows1(D, M, hp);
 }
 
+// ------------------------------------------------------------------------------------------
+// Mixed derivative product: d/dq [ grad_u E . p ] per cell, for each material parameter q of the cell's energy
+// -- what the reference's inverse problems call `mixed_derivative_prod(state, p)` after the adjoint solve
+// (exp/2026/01/28/smas/src/31-inverse-activation-stable-neo-hookean.py:472-487; the method is absent from the
+// current src/, so the restatement below is the analytic derivative of the energies of this file).
+// With phi = vol <P(F; q), dF> (dF = p^T dhdX):
+//   SNH (on G = F A, dG = dF A; A = I for the plain energy):
+//     d phi / d mu     = vol (<G, dG> - <cof G, dG>)
+//     d phi / d lambda = vol (J_G - 1) <cof G, dG>
+//     d phi / d A      = vol (F^T M_G + dF^T P_G),  P_G = mu G + c3 cof G,  M_G = lambda <cof G, dG> cof G + mu dG + c3 X(G, dG)
+//     activation a = (a0, a1, a2 | a3 = xy, a4 = xz, a5 = yz):  d/da_k = N_kk (k < 3),  N_01 + N_10,  N_02 + N_20,  N_12 + N_21
+//   ARAP:  d phi / d mu = vol <F - R, dF>.
+// Outputs: d_mu, d_la (0 for ARAP), d_act[6] (muscle only).  The fused SNH+ARAP record has two sets of materials
+// and is not supported here (evaluate the two potentials separately).
+// ------------------------------------------------------------------------------------------
+template <typename T, int KIND>
+APL_HD void elem_mixed(const T* rec, const T (*uc)[3], const T (*pc)[3], T& d_mu, T& d_la, T* d_act) {
+    static_assert(KIND != APL_KIND_SNH_ARAP, "mixed derivatives are evaluated per potential");
+    T F[9], dF[9];
+    {
+        T e[3][3];
+        edge_diff(uc, e);
+        edge_outer(e, rec, F);
+        F[0] += (T)1; F[4] += (T)1; F[8] += (T)1;
+        edge_diff(pc, e);
+        edge_outer(e, rec, dF);
+    }
+    const T vol = rec[9], mu = rec[10];
+    d_mu = d_la = (T)0;
+    if constexpr (KIND == APL_KIND_ARAP) {
+        T R[9], L[6], sg[3];
+        polar_twist(F, R, L, sg);
+        T s = (T)0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) s += (F[k] - R[k]) * dF[k];
+        d_mu = vol * s;
+    } else {
+        const T la = rec[11];
+        T G[9], dG[9];
+        if constexpr (KIND == APL_KIND_SNH_MUSCLE) {
+            const T A[9] = {(T)1 + rec[12], rec[15], rec[16],
+                            rec[15], (T)1 + rec[13], rec[17],
+                            rec[16], rec[17], (T)1 + rec[14]};
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    G[3 * i + j] = F[3 * i] * A[j] + F[3 * i + 1] * A[3 + j] + F[3 * i + 2] * A[6 + j];
+                    dG[3 * i + j] = dF[3 * i] * A[j] + dF[3 * i + 1] * A[3 + j] + dF[3 * i + 2] * A[6 + j];
+                }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { G[k] = F[k]; dG[k] = dF[k]; }
+        }
+        T C[9];
+        const T J = cofactor(G, C);
+        const T Jm1 = J - (T)1;
+        const T cdg = ddot9(C, dG);
+        d_mu = vol * (ddot9(G, dG) - cdg);
+        d_la = vol * Jm1 * cdg;
+        if constexpr (KIND == APL_KIND_SNH_MUSCLE) {
+            const T c3 = -mu + la * Jm1;
+            T X[9], PG[9], MG[9];
+            dcofactor(G, dG, X);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                PG[k] = mu * G[k] + c3 * C[k];
+                MG[k] = la * cdg * C[k] + mu * dG[k] + c3 * X[k];
+            }
+            T N[9];   // N = F^T M_G + dF^T P_G
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int n = 0; n < 3; ++n)
+                    N[3 * m + n] = F[m] * MG[n] + F[3 + m] * MG[3 + n] + F[6 + m] * MG[6 + n] +
+                                   dF[m] * PG[n] + dF[3 + m] * PG[3 + n] + dF[6 + m] * PG[6 + n];
+            d_act[0] = vol * N[0]; d_act[1] = vol * N[4]; d_act[2] = vol * N[8];
+            d_act[3] = vol * (N[1] + N[3]); d_act[4] = vol * (N[2] + N[6]); d_act[5] = vol * (N[5] + N[7]);
+        }
+    }
+}
+
 }  // namespace apl

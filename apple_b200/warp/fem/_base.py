@@ -191,6 +191,24 @@ class WarpPotentialFem(WarpPotential):
                 )
             )
 
+    def mixed_derivative_prod(self, u, p) -> dict:
+        """``d/dq [grad_u E(u) . p]`` per cell for every material ``q`` of this potential (caller's cell order): what
+        the reference's inverse problems add to ``dL/dq`` after the adjoint solve
+        (``exp/2026/01/28/smas/src/31-inverse-activation-stable-neo-hookean.py:472-487``)."""
+        ld_in = _lib.field_ld(u, self.n_points, self.dtype, "u")
+        if _lib.field_ld(p, self.n_points, self.dtype, "p") != ld_in:
+            raise ValueError("p must have the layout of u")
+        n_cells = self.region.cells.shape[0]
+        out = {}
+        for name in self.MATERIAL_NAMES:
+            shape = (n_cells, 6) if name == "activation" else (n_cells,)
+            out[name] = torch.zeros(shape, dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().apl_fem_mixed_derivative_prod(
+                self._handle, _lib.dev_ptr(u), _lib.dev_ptr(p), ld_in, _lib.dev_ptr(out.get("mu")),
+                _lib.dev_ptr(out.get("lambda_")), _lib.dev_ptr(out.get("activation")), _lib.stream_ptr(self.device)))
+        return out
+
     def fun(self, u, output) -> None:  # _base.py:151-158
         self.eval(_lib.OP_FUN, u, fun=output)
 

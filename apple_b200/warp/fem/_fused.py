@@ -50,6 +50,9 @@ class FusedSnhArap(WarpPotentialFem):
         )
         return handle
 
+    def mixed_derivative_prod(self, u, p) -> dict:
+        raise NotImplementedError("evaluate mixed_derivative_prod on the two potentials of the fused pair separately")
+
     def set_materials(self, **kw) -> None:
         raise NotImplementedError("rebuild the fused potential after changing the materials of its parts")
 

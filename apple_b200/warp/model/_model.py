@@ -39,6 +39,11 @@ class WarpModel:
         for potential in self.potentials.values():
             potential.hess_quad(u, p, output)
 
+    def mixed_derivative_prod(self, u: torch.Tensor, p: torch.Tensor) -> dict:
+        """``{potential name: {material name: d/dq [grad E . p] per cell}}`` over the potentials that have materials."""
+        return {name: pot.mixed_derivative_prod(u, p) for name, pot in self.potentials.items()
+                if hasattr(pot, "mixed_derivative_prod")}
+
     def mark_boundary(self, vertex_flags) -> int:
         """Forwards to every potential that has element tiles; returns the total number of boundary tiles."""
         total = 0

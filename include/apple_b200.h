@@ -144,6 +144,16 @@ int apl_fem_eval(apl_fem_t* fem, int ops, const void* u, const void* p, int ld_i
                  void* quad, void* grad, void* diag, void* prod, int ld_out, int scatter,
                  void* stream);
 
+/* ---- mixed derivative product: what the reference's inverse problems call model.mixed_derivative_prod(state, p)
+ * after the adjoint solve (exp/2026/01/28/smas/src/31-inverse-activation-stable-neo-hookean.py:472-487; the method
+ * is absent from the reference's current src/, so this is the analytic derivative of the energies of this library).
+ * Per cell c:  d/dq_c [ grad_u E(u) . p ]  for the cell's own material parameters q_c.
+ * Outputs: DEVICE arrays in the CALLER's cell order, overwritten; NULL = not wanted.
+ *   d_mu (n_cells), d_lambda (n_cells; Stable Neo-Hookean kinds), d_activation (n_cells,6; muscle kind).
+ * Not available for the fused SNH+ARAP handle (evaluate its two potentials separately). */
+int apl_fem_mixed_derivative_prod(apl_fem_t* fem, const void* u, const void* p, int ld_in, void* d_mu,
+                                  void* d_lambda, void* d_activation, void* stream);
+
 /* ---- multi-GPU overlap (no reference counterpart: the reference is single-GPU) -----------------------
  * apl_fem_mark_boundary: tiles that touch a vertex with vertex_flags[v] != 0 (HOST array, n_points
  * bytes; a sharded caller flags the vertices it shares with other ranks) become "boundary" tiles and

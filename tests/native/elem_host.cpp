@@ -59,3 +59,25 @@ extern "C" void polar_twist_host(int is_f64, int path, int n, const void* F, voi
         }
     }
 }
+
+// per-cell mixed derivative products d(grad E . p)/d(mu, lambda, activation); kind 0 SNH, 1 ARAP, 2 muscle
+extern "C" void elem_mixed_host(int kind, int is_f64, int n, const void* rec, const void* uc, const void* pc, void* d_mu,
+                                void* d_la, void* d_act) {
+    auto go = [&](auto zero) {
+        using T = decltype(zero);
+        const int NR = kind == 2 ? 18 : 12;
+        for (int t = 0; t < n; ++t) {
+            const T* r = (const T*)rec + (size_t)t * NR;
+            const T(*u)[3] = (const T(*)[3])((const T*)uc + (size_t)t * 12);
+            const T(*p)[3] = (const T(*)[3])((const T*)pc + (size_t)t * 12);
+            T a[6] = {0, 0, 0, 0, 0, 0};
+            T& m = ((T*)d_mu)[t];
+            T& l = ((T*)d_la)[t];
+            if (kind == 0) apl::elem_mixed<T, APL_KIND_SNH>(r, u, p, m, l, a);
+            else if (kind == 1) apl::elem_mixed<T, APL_KIND_ARAP>(r, u, p, m, l, a);
+            else apl::elem_mixed<T, APL_KIND_SNH_MUSCLE>(r, u, p, m, l, a);
+            for (int k = 0; k < 6; ++k) ((T*)d_act)[6 * t + k] = a[k];
+        }
+    };
+    if (is_f64) go(0.0); else go(0.0f);
+}

@@ -717,3 +717,50 @@ def test_unstructured_delaunay_mesh_through_the_host_replay(native_lib, tile_hos
                                   stride.value, P(u), P(p), 0.0, P(grad), P(diag), P(prod), P(fun), P(quad)) == 0
     for a, b in ((fun[0], ora.fun(u)), (grad, ora.grad(u)), (prod, ora.hess_prod(u, p))):
         assert np.abs(np.asarray(a) - b).max() <= 1e-11 * np.abs(b).max()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_mixed_derivative_closed_forms_match_finite_differences_of_the_oracle(host_math, kind):
+    """elem_mixed (csrc/elem_math.cuh): d/dq [grad E . p] per cell for q in (mu, lambda, activation) -- the
+    reference's historical mixed_derivative_prod -- against central differences of the oracle's per-cell gradient
+    with respect to its material arrays."""
+    import copy
+
+    mesh, u, p = make_case(n=4, seed=2, amp=0.15)
+    T = mesh.n_cells
+    ora = oracle_potential(kind, mesh)
+    nrec = 18 if kind == "muscle" else 12
+    rec = np.zeros((T, nrec))
+    rec[:, :9] = ora.dhdX[:, 1:4].reshape(T, 9); rec[:, 9] = ora.dV; rec[:, 10] = ora.materials["mu"]
+    if kind != "arap":
+        rec[:, 11] = ora.materials["lambda_"]
+    if kind == "muscle":
+        rec[:, 12:] = ora.materials["activation"]
+    uc = np.ascontiguousarray(u[mesh.cells]); pc = np.ascontiguousarray(p[mesh.cells])
+    dm, dl, da = np.zeros(T), np.zeros(T), np.zeros((T, 6))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    host_math.elem_mixed_host(KINDS.index(kind), 1, T, P(rec), P(uc), P(pc), P(dm), P(dl), P(da))
+
+    def phi(pot):                                   # per-cell  grad E . p
+        return np.einsum("cai,cai->c", pot.elem_grad(u), p[mesh.cells])
+
+    def fd(name, comp=None, eps=1e-6):
+        lo, hi = copy.deepcopy(ora), copy.deepcopy(ora)
+        for pot, sign in ((hi, 1.0), (lo, -1.0)):
+            m = dict(ora.materials)
+            x = np.array(ora.materials[name], dtype=float, copy=True)
+            if comp is None:
+                x += sign * eps
+            else:
+                x[:, comp] += sign * eps
+            m[name] = x
+            pot.materials = m
+        return (phi(hi) - phi(lo)) / (2 * eps)
+
+    rel = lambda got, ref: np.abs(got - ref).max() / np.abs(ref).max()  # noqa: E731
+    assert rel(dm, fd("mu")) < 1e-6
+    if kind != "arap":
+        assert rel(dl, fd("lambda_")) < 1e-6
+    if kind == "muscle":
+        for k in range(6):
+            assert rel(da[:, k], fd("activation", k)) < 1e-6
