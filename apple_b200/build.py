@@ -33,6 +33,8 @@ COMMON = [
 ]
 if os.environ.get("APL_PROFILE_KNOBS"):  # profiling-only kernel knobs (never set for the product build)
     COMMON.append("-DAPL_PROFILE_KNOBS")
+if os.environ.get("APL_GATHER_LDG"):     # experiment: register-staged gather of ld = 3 rows in the producer warp
+    COMMON.append("-DAPL_GATHER_LDG")
 if os.environ.get("APL_TILE_TETS"):
     COMMON.append("-DAPL_TILE_TETS=" + os.environ["APL_TILE_TETS"])
 

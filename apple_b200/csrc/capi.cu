@@ -617,7 +617,11 @@ int apl_fem_eval_part(apl_fem_t* f, int part, int ops, const void* u, const void
         return APL_ERR_INVALID;
     }
     {   // vector accesses of the kernels: 16-byte rows for ld = 4, 8-byte vector REDs for fp32 ld = 3
+#ifdef APL_GATHER_LDG
+        const uintptr_t in_mask = ld_in == 4 ? 15u : 7u;   // the register-staged gather uses 8-byte loads
+#else
         const uintptr_t in_mask = ld_in == 4 ? 15u : 0u;
+#endif
         const uintptr_t out_mask = ld_out == 4 ? 15u : 7u;
         auto bad = [](const void* ptr, uintptr_t mask) { return ptr && ((uintptr_t)ptr & mask) != 0; };
         if (bad(u, in_mask) || ((ops & (APL_OP_HESS_PROD | APL_OP_HESS_QUAD)) && bad(p, in_mask)) ||

@@ -395,6 +395,35 @@ __device__ __forceinline__ void gather_row_async(unsigned dst, const T* base, in
     }
 }
 
+#ifdef APL_GATHER_LDG
+// ld = 3 row through registers: the 12-byte row of vertex gv starts at 12 gv, so either its first or its last
+// 8 bytes are 8-byte aligned (fp32; the base pointer must be 8-byte aligned, checked by apl_fem_eval in this build)
+template <typename T>
+__device__ __forceinline__ void load_row3_ldg(const T* __restrict__ base, int gv, T* r) {
+    if constexpr (sizeof(T) == 4) {
+        const char* row = reinterpret_cast<const char*>(base) + 12ll * gv;
+        const bool odd = gv & 1;
+        const float2 pr = __ldg(reinterpret_cast<const float2*>(row + (odd ? 4 : 0)));
+        const float one = __ldg(reinterpret_cast<const float*>(row + (odd ? 0 : 8)));
+        r[0] = odd ? one : pr.x;
+        r[1] = odd ? pr.x : pr.y;
+        r[2] = odd ? pr.y : one;
+    } else {
+        const T* row = base + 3ll * gv;
+        r[0] = __ldg(row); r[1] = __ldg(row + 1); r[2] = __ldg(row + 2);
+    }
+}
+template <typename T>
+__device__ __forceinline__ void store_row4(T* dst, const T* r) {
+    if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], 0.f);
+    } else {
+        *reinterpret_cast<double2*>(dst) = make_double2(r[0], r[1]);
+        *reinterpret_cast<double2*>(dst + 2) = make_double2(r[2], 0.0);
+    }
+}
+#endif
+
 constexpr int kPipeThreads = kTileTets + 32;
 
 template <typename T, int KIND, int OPS, int LAYOUT = APL_LAYOUT_TET>
@@ -542,13 +571,46 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS, LAYOUT>::kThreads, PipeC
             const int* verts = reinterpret_cast<const int*>(vring + (size_t)sv * PC::kVtabBytes + PC::oVerts);
             const unsigned us32 = st32 + (unsigned)PC::oVbuf;
             const unsigned ps32 = us32 + 4u * kTileVerts * (unsigned)sizeof(T);
-            for (int v = lane; v < n_verts; v += 32) {
-                const int gv = verts[v];
-                gather_row_async<T>(us32 + (unsigned)v * 4u * (unsigned)sizeof(T), a.u, gv, a.ld_in);
-                if constexpr (Cfg::kNeedP) gather_row_async<T>(ps32 + (unsigned)v * 4u * (unsigned)sizeof(T), a.p, gv, a.ld_in);
-                else if (axpy) gather_row_async<T>(ps32 + (unsigned)v * 4u * (unsigned)sizeof(T), a.axpy_p, gv, a.ld_in);
+#ifdef APL_GATHER_LDG
+            // EXPERIMENT (off by default, `APL_GATHER_LDG=1 python -m apple_b200.build`): 12-byte rows (ld = 3)
+            // through registers -- one 8-byte and one 4-byte load per row instead of three 4-byte cp.async, and
+            // one 16-byte shared-memory store instead of three 4-byte ones (the store is conflict-free: 32
+            // consecutive rows per warp); costs the producer one exposed global-memory latency per tile.
+            if (a.ld_in == 3) {
+                constexpr int R = kTileVerts / 32;
+                const T* pf = Cfg::kNeedP ? a.p : a.axpy_p;
+                const bool want_p = Cfg::kNeedP || axpy;
+                T ru[R][3], rp[R][3];
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const int v = lane + 32 * k;
+                    if (v < n_verts) {
+                        const int gv = verts[v];
+                        load_row3_ldg<T>(a.u, gv, ru[k]);
+                        if (want_p) load_row3_ldg<T>(pf, gv, rp[k]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const int v = lane + 32 * k;
+                    if (v < n_verts) {
+                        T* vb = reinterpret_cast<T*>(st + PC::oVbuf);
+                        store_row4<T>(vb + 4 * v, ru[k]);
+                        if (want_p) store_row4<T>(vb + 4 * kTileVerts + 4 * v, rp[k]);
+                    }
+                }
+                mbar_arrive(full(s));   // release: the stores above are visible to the consumers that acquire the phase
+            } else
+#endif
+            {
+                for (int v = lane; v < n_verts; v += 32) {
+                    const int gv = verts[v];
+                    gather_row_async<T>(us32 + (unsigned)v * 4u * (unsigned)sizeof(T), a.u, gv, a.ld_in);
+                    if constexpr (Cfg::kNeedP) gather_row_async<T>(ps32 + (unsigned)v * 4u * (unsigned)sizeof(T), a.p, gv, a.ld_in);
+                    else if (axpy) gather_row_async<T>(ps32 + (unsigned)v * 4u * (unsigned)sizeof(T), a.axpy_p, gv, a.ld_in);
+                }
+                cp_async_arrive_noinc(full(s));
             }
-            cp_async_arrive_noinc(full(s));
             h_cur = h_nxt;
             h_nxt = h_nn;
         }
