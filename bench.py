@@ -601,7 +601,9 @@ def main():
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload_name(args, mesh, kinds), "assembly": args.scatter, "layout": args.layout,
                        "l2": "256 MiB flush write between timed steps" if not args.no_flush else "no flush",
-                       "parallelism": (f"{world} ranks x contiguous Morton chunk of tets (~{T_total // world} tets per "
+                       "parallelism": (f"{world} ranks x " + ("slab of hex layers, generated per rank" if args.slab else
+                                                               "contiguous Morton chunk of tets") +
+                                       f" (~{T_total // world} tets per "
                                        f"GPU, {args.scaling} scaling); halo sum of grad+HVP (NCCL all-to-all of "
                                        f"shared rows) + scalar all-reduce per step, "
                                        f"{'replayed as one CUDA graph' if args.graph else 'plain launches'}; "
