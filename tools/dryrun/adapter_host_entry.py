@@ -1,7 +1,7 @@
 """Dry run of WarpModelAdapter.fun_grad_hess_prod_host on the CPU with torch.cuda mocked: catches Python-level
 mistakes (names, shapes, kwargs) in the stream choreography that otherwise only a GPU run would reveal."""
 import sys, types, contextlib, numpy as np, torch
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+ROOT=str(__import__('pathlib').Path(__file__).resolve().parents[2]); sys.path.insert(0,ROOT); sys.path.insert(0,ROOT+'/tests')
 import apple_b200.warp.model._adapter as A
 from apple_b200 import _lib
 from helpers import make_case, oracle_potential

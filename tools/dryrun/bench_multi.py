@@ -1,7 +1,7 @@
 """Dry run of bench.py's N>1 flow: 2 processes over gloo, torch.cuda mocked, oracle-backed fake potentials that
 implement mark_boundary / part by cell subsets."""
 import sys, os, contextlib, json, io, time, copy, numpy as np, torch, torch.distributed as dist
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+ROOT=str(__import__('pathlib').Path(__file__).resolve().parents[2]); sys.path.insert(0,ROOT); sys.path.insert(0,ROOT+'/tests')
 real_device=torch.device
 class Ev:
     def __init__(self,enable_timing=False): self.t=None

@@ -1,7 +1,7 @@
 """Dry run of bench.py's N=1 flow on the CPU: torch.cuda mocked, potentials replaced by oracle-backed fakes.
 Catches Python-level mistakes in the flow and in the JSON assembly (not performance, not kernels)."""
 import sys, contextlib, json, io, time, numpy as np, torch
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+ROOT=str(__import__('pathlib').Path(__file__).resolve().parents[2]); sys.path.insert(0,ROOT); sys.path.insert(0,ROOT+'/tests')
 real_device=torch.device
 class Ev:
     def __init__(self,enable_timing=False): self.t=None
