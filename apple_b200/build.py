@@ -35,6 +35,8 @@ if os.environ.get("APL_PROFILE_KNOBS"):  # profiling-only kernel knobs (never se
     COMMON.append("-DAPL_PROFILE_KNOBS")
 if os.environ.get("APL_GATHER_LDG"):     # experiment: register-staged gather of ld = 3 rows in the producer warp
     COMMON.append("-DAPL_GATHER_LDG")
+if os.environ.get("APL_SMEM_BUDGET_KB"):  # experiment: shared-memory budget per CTA (number of pipeline stages vs CTAs per SM)
+    COMMON.append("-DAPL_SMEM_BUDGET_KB=" + os.environ["APL_SMEM_BUDGET_KB"])
 if os.environ.get("APL_TILE_TETS"):
     COMMON.append("-DAPL_TILE_TETS=" + os.environ["APL_TILE_TETS"])
 

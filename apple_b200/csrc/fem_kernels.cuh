@@ -451,7 +451,12 @@ struct PipeCfg {
     static constexpr size_t kVtabBytes = oVoff + Cfg::kVoffRaw;
     static constexpr size_t kBarBytes = 128;
     // as many stages as fit the target number of CTAs per SM (>= 2 always, <= 4); vertex ring = stages + 1
+    // shared-memory budget per CTA that decides the number of stages (tuning experiments: -DAPL_SMEM_BUDGET_KB=...)
+#ifdef APL_SMEM_BUDGET_KB
+    static constexpr size_t kBudget = (size_t)APL_SMEM_BUDGET_KB * 1024;
+#else
     static constexpr size_t kBudget = (size_t)(sizeof(T) == 4 ? 74 : 113) * 1024 * kTileTets / 256;
+#endif
     static constexpr size_t kFixedBytes = kSlotBytes + kBarBytes + kVtabBytes;
     static constexpr int kFit =
         (int)((kBudget > kFixedBytes ? kBudget - kFixedBytes : 0) / (kStageBytes + kVtabBytes));
