@@ -47,10 +47,11 @@ def wavefronts(addr, nbytes, active=None, quarter=False):
 def host_tables(n, layout=0):
     from apple_b200 import _lib, build
     from bench import build_mesh
-    from oracle import region
+    from apple_b200.fem import Region
     build.build(); L = _lib.lib()
     mesh, _, _ = build_mesh(n)
-    dhdX, dV = region.compute_grad(mesh.points, mesh.cells)
+    reg = Region.from_pyvista(mesh, grad=True)          # the product's own rest-shape precompute (no oracle here)
+    dhdX, dV = reg.dhdX.reshape(-1, 4, 3), reg.dV.reshape(-1)
     T, V = mesh.n_cells, mesh.n_points
     one = np.ones(T); P = _lib.host_ptr; h = ctypes.c_void_p()
     cells = np.ascontiguousarray(mesh.cells, dtype=np.int32); pts = np.ascontiguousarray(mesh.points)
