@@ -95,6 +95,14 @@ def build_mesh(n, seed=0):
     return mesh, np.ascontiguousarray(u), np.ascontiguousarray(p)
 
 
+def cuda_potential(kind, mesh, dtype, **kw):
+    """A potential of the product (`apple_b200.warp.fem`) on `mesh`; nothing of oracle/ is involved."""
+    from apple_b200.warp.fem import Arap, StableNeoHookean, StableNeoHookeanMuscle
+
+    cls = {"snh": StableNeoHookean, "arap": Arap, "muscle": StableNeoHookeanMuscle}[kind]
+    return cls.from_pyvista(mesh, dtype=dtype, **kw)
+
+
 def build_slab(n, world, rank):
     """This rank's slab of the n^3 x 5 cube (apple_b200.dist.slab_shard) with the fields of `build_mesh` redefined as
     functions of the GLOBAL vertex / cell ids, so that every partition of the same cube evaluates the same model."""
@@ -299,7 +307,6 @@ def main():
     from apple_b200.mesh import TetMesh
     from apple_b200.warp.fem import fuse_potentials
     from apple_b200.warp.model import WarpModel, WarpModelAdapter
-    from helpers import cuda_potential
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -688,7 +695,6 @@ def sweep(args, mesh, u, p, dtype, dev, flush):
     import torch
 
     from apple_b200 import _lib
-    from helpers import cuda_potential
 
     V, T = mesh.n_points, mesh.n_cells
     rows = []

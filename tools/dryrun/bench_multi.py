@@ -40,10 +40,11 @@ class FakePot:
         if ops&_lib.OP_FUN: e=np.zeros(1); o.fun(un,e); fun+=float(e[0])
         if ops&_lib.OP_GRAD: g=np.zeros((V,3)); o.grad(un,g); grad+=torch.from_numpy(g).to(grad.dtype)
         if ops&_lib.OP_HESS_PROD: h=np.zeros((V,3)); o.hess_prod(un,pn,h); prod+=torch.from_numpy(h).to(prod.dtype)
-helpers.cuda_potential=lambda kind,mesh,dtype,**kw: FakePot(kind,mesh,dtype,**kw)
+_fake=lambda kind,mesh,dtype,**kw: FakePot(kind,mesh,dtype,**kw)
 import apple_b200.warp.fem as wf
 wf.fuse_potentials=lambda pots: pots
 import bench
+bench.cuda_potential=_fake
 mode=sys.argv[1]
 sys.argv=["bench.py","--gpus","2","--n","5","--steps","2","--warmup","1","--no-flush"]+(["--slab"] if mode=="slab" else [])
 buf=io.StringIO()

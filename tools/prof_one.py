@@ -5,8 +5,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 import numpy as np, torch
-from bench import build_mesh
-from helpers import cuda_potential
+from bench import build_mesh, cuda_potential
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--kind", default="snh"); ap.add_argument("--dtype", default="f32")
