@@ -40,6 +40,8 @@ SIGNATURES = {
     "apl_fem_create_snh_arap": (c_int, [c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_int, POINTER(c_void_p)]),
     "apl_fem_destroy": (None, [c_void_p]),
+    "apl_fem_create_from_mesh": (c_int, [c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(c_void_p)]),
     "apl_fem_info": (c_int, [c_void_p, POINTER(c_int64)]),
     "apl_fem_host_tables": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "apl_set_layout": (c_int, [c_int]),

@@ -46,6 +46,7 @@ def _units():
         ("tiling", "tiling.cpp", []),
         ("capi", "capi.cu", []),
         ("pncg", "pncg.cu", []),
+        ("setup", "setup.cu", []),
     ]
     for tname, t in (("f32", "float"), ("f64", "double")):
         for kind in (0, 1, 2, 3):

@@ -360,6 +360,56 @@ int ext_force_pncg(int dtype, int ops, int64_t k, const void* force, const int32
 
 }  // namespace apl
 
+namespace apl {
+// Device copies of a handle's packed tables (tile headers, connectivity, slots, vertex tables) and the
+// allocations that do not depend on the static record (planes, scalar partials).  f->host, f->nplanes,
+// f->plane_stride and f->device are set by the caller.
+int fem_upload_tables(apl_fem* f) {
+    const HostTables& h = f->host;
+    const int device = f->device;
+    const size_t plane_bytes = (size_t)f->nplanes * f->plane_stride * 16;
+    f->static_bytes = (int64_t)(plane_bytes + h.n_tiles() * 16 + h.conn.size() + h.slots.size() * 2 +
+                                h.tile_verts.size() * 5 + h.tile_voff.size() * 2);
+    APL_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    APL_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    f->num_sms = prop.multiProcessorCount;
+    f->max_grid = f->num_sms * 16;
+    auto up = [&](void** dst, const void* src, size_t bytes, size_t slack) -> cudaError_t {
+        // `slack` zeroed bytes after the data: 16-byte granular bulk copies of the last tile stay in bounds
+        cudaError_t e = cudaMalloc(dst, bytes + slack + 16);
+        if (e != cudaSuccess) return e;
+        if (slack) {
+            e = cudaMemset((char*)*dst + bytes, 0, slack + 16);
+            if (e != cudaSuccess) return e;
+        }
+        return bytes ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+    };
+    {
+        // device tile header: tet_start, n_tets | n_verts << 16, vert_start, voff_start
+        std::vector<int32_t> hdr((size_t)h.n_tiles() * 4);
+        for (int64_t t = 0; t < h.n_tiles(); ++t) {
+            const int32_t* src = h.tiles.data() + 6 * t;
+            hdr[4 * t] = src[0];
+            hdr[4 * t + 1] = src[1] | (src[3] << 16);
+            hdr[4 * t + 2] = src[2];
+            hdr[4 * t + 3] = src[4];
+        }
+        APL_CUDA_CHECK(up(&f->d_tiles, hdr.data(), hdr.size() * 4, 0));
+    }
+    APL_CUDA_CHECK(up(&f->d_conn, h.conn.data(), h.conn.size(), 64));
+    APL_CUDA_CHECK(up(&f->d_slots, h.slots.data(), h.slots.size() * 2, 64));
+    APL_CUDA_CHECK(up(&f->d_tile_verts, h.tile_verts.data(), h.tile_verts.size() * 4, 0));
+    APL_CUDA_CHECK(up(&f->d_tile_voff, h.tile_voff.data(), h.tile_voff.size() * 2, 0));
+    APL_CUDA_CHECK(up(&f->d_tile_vperm, h.tile_vperm.data(), h.tile_vperm.size(), 0));
+    APL_CUDA_CHECK(cudaMalloc(&f->d_planes, plane_bytes));
+    APL_CUDA_CHECK(cudaMalloc((void**)&f->d_partials, sizeof(double) * 2 * f->max_grid));
+    APL_CUDA_CHECK(cudaMalloc((void**)&f->d_counter, sizeof(unsigned int)));
+    APL_CUDA_CHECK(cudaMemset(f->d_counter, 0, sizeof(unsigned int)));
+    return APL_OK;
+}
+}  // namespace apl
+
 using namespace apl;
 
 static std::atomic<int> g_default_layout{APL_LAYOUT_TET};
@@ -428,53 +478,8 @@ static int fem_create_impl(int kind, int dtype, int64_t n_cells, int64_t n_point
     f->static_bytes = (int64_t)(plane_bytes + h.n_tiles() * 16 + h.conn.size() + h.slots.size() * 2 +
                                 h.tile_verts.size() * 5 + h.tile_voff.size() * 2);
     if (device >= 0) {
-        auto fail = [&](int code) { apl_fem_destroy(f); return code; };
-#define APL_TRY(expr)                                                                           \
-    do {                                                                                        \
-        cudaError_t _e = (expr);                                                                \
-        if (_e != cudaSuccess) {                                                                \
-            set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e));              \
-            return fail(APL_ERR_CUDA);                                                          \
-        }                                                                                       \
-    } while (0)
-        APL_TRY(cudaSetDevice(device));
-        cudaDeviceProp prop;
-        APL_TRY(cudaGetDeviceProperties(&prop, device));
-        f->num_sms = prop.multiProcessorCount;
-        f->max_grid = f->num_sms * 16;
-        auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
-            cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
-            if (e != cudaSuccess) return e;
-            return bytes ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
-        };
-        {
-            // device tile header: tet_start, n_tets | n_verts << 16, vert_start, voff_start
-            std::vector<int32_t> hdr((size_t)h.n_tiles() * 4);
-            for (int64_t t = 0; t < h.n_tiles(); ++t) {
-                const int32_t* src = h.tiles.data() + 6 * t;
-                hdr[4 * t] = src[0];
-                hdr[4 * t + 1] = src[1] | (src[3] << 16);
-                hdr[4 * t + 2] = src[2];
-                hdr[4 * t + 3] = src[4];
-            }
-            APL_TRY(up(&f->d_tiles, hdr.data(), hdr.size() * 4));
-        }
-        {   // +64 bytes of slack: 16-byte granular bulk copies of the last tile stay in bounds
-            std::vector<uint8_t> conn(h.conn.size() + 64, 0);
-            memcpy(conn.data(), h.conn.data(), h.conn.size());
-            std::vector<uint16_t> slots(h.slots.size() + 32, 0);
-            memcpy(slots.data(), h.slots.data(), h.slots.size() * 2);
-            APL_TRY(up(&f->d_conn, conn.data(), conn.size()));
-            APL_TRY(up(&f->d_slots, slots.data(), slots.size() * 2));
-        }
-        APL_TRY(up(&f->d_tile_verts, h.tile_verts.data(), h.tile_verts.size() * 4));
-        APL_TRY(up(&f->d_tile_voff, h.tile_voff.data(), h.tile_voff.size() * 2));
-        APL_TRY(up(&f->d_tile_vperm, h.tile_vperm.data(), h.tile_vperm.size()));
-        APL_TRY(cudaMalloc(&f->d_planes, plane_bytes));
-        APL_TRY(cudaMalloc((void**)&f->d_partials, sizeof(double) * 2 * f->max_grid));
-        APL_TRY(cudaMalloc((void**)&f->d_counter, sizeof(unsigned int)));
-        APL_TRY(cudaMemset(f->d_counter, 0, sizeof(unsigned int)));
-#undef APL_TRY
+        rc = apl::fem_upload_tables(f);
+        if (rc != APL_OK) { apl_fem_destroy(f); return rc; }
     }
     rc = (dtype == APL_F32) ? upload_planes<float>(f, dhdX, dV, mu, lambda_, activation, dV2, mu2)
                             : upload_planes<double>(f, dhdX, dV, mu, lambda_, activation, dV2, mu2);

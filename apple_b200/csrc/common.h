@@ -44,6 +44,11 @@ struct HostTables {
 int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const double* points, int elem_bytes,
                 int layout, HostTables& out);
 
+// Tiling of connectivity ALREADY in packed (Morton) order -- the device-side setup (setup.cu) sorts the cells on
+// the GPU: packed_cells[pos] is the tet at packed position pos, order[pos] the caller's index of that tet.
+int build_tiles_packed(int64_t n_cells, int64_t n_points, const int32_t* packed_cells, std::vector<int64_t>&& order,
+                       int elem_bytes, HostTables& out);
+
 }  // namespace apl
 
 struct apl_fem {

@@ -577,7 +577,155 @@ void for_tiles_parallel(int64_t n_tiles, F&& body) {
 
 }  // namespace
 
+
+// ---- pass 1: tile boundaries ---------------------------------------------------------------------------
+// The packed tets are cut into tiles chunk by chunk (chunks of kCutChunk packed positions, cut independently
+// and in parallel; a tile never spans two chunks).  A tile closes when it is full.  Vertex budget: tiles must
+// start at multiples of 4 tets (16-byte aligned byte-wide connectivity), so the budget is checked every 4 tets
+// with room for the worst case of 16 new vertices in the next 4.
+namespace {
+constexpr int64_t kCutChunk = 1 << 17;
+struct ChunkCut {
+    std::vector<TileRange> ranges;   // first_touch relative to this chunk's `touched`; vert_start / voff_start unset
+    std::vector<int32_t> touched;
+};
+
+template <typename CellAt>
+void cut_chunk(int64_t begin, int64_t end, CellAt&& cell_at, ChunkCut& out) {
+    constexpr int kH = 512;   // open-addressing set of the open tile's vertices (<= kTileVerts entries)
+    static_assert(kH >= 2 * kTileVerts, "hash set too small");
+    int32_t keys[kH];
+    auto reset = [&] { for (int i = 0; i < kH; ++i) keys[i] = -1; };
+    reset();
+    out.ranges.reserve((size_t)((end - begin) / 200 + 4));
+    out.touched.reserve((size_t)((end - begin) / 2 + 16));
+    int64_t tile_start = begin, first = 0;
+    auto close_tile = [&](int64_t tile_end) {
+        const int nt = (int)(tile_end - tile_start);
+        if (nt == 0) return;
+        const int nv = (int)((int64_t)out.touched.size() - first);
+        out.ranges.push_back({tile_start, nt, nv, first, 0, 0});
+        first = (int64_t)out.touched.size();
+        tile_start = tile_end;
+        reset();
+    };
+    for (int64_t pos = begin; pos < end; ++pos) {
+        const int32_t* c = cell_at(pos);
+        const int64_t in_tile = pos - tile_start;
+        const int nv_open = (int)((int64_t)out.touched.size() - first);
+        if (in_tile == kTileTets || (in_tile % 4 == 0 && in_tile > 0 && nv_open + 16 > kTileVerts)) close_tile(pos);
+        for (int a = 0; a < 4; ++a) {
+            const int32_t v = c[a];
+            int h = (int)(((uint32_t)v * 2654435761u) >> 23) & (kH - 1);
+            while (keys[h] >= 0 && keys[h] != v) h = (h + 1) & (kH - 1);
+            if (keys[h] < 0) {
+                keys[h] = v;
+                out.touched.push_back(v);
+            }
+        }
+    }
+    close_tile(end);
+}
+
+template <typename F>
+void parallel_for_chunks(int64_t n, F&& body) {
+    int n_threads = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("APL_TILING_THREADS")) n_threads = atoi(e);
+    n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(n_threads, 32), n));
+    if (n_threads == 1) {
+        for (int64_t i = 0; i < n; ++i) body(i);
+        return;
+    }
+    std::atomic<int64_t> next{0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t)
+        pool.emplace_back([&] {
+            for (;;) {
+                const int64_t i = next.fetch_add(1);
+                if (i >= n) break;
+                body(i);
+            }
+        });
+    for (auto& th : pool) th.join();
+}
+}  // namespace
+
 static int build_tiles_pair(const int32_t* cells, bool f64, HostTables& out);
+
+// out.order must hold the packed order (packed position -> caller's cell).  `cells` is either the caller's
+// array (cells_packed = false: the tet at packed position pos is cells[order[pos]]) or already permuted into
+// packed order (cells_packed = true: the device-side setup sorts the connectivity on the GPU).
+static int build_tiles_ordered(int64_t n_cells, int64_t n_points, const int32_t* cells, bool cells_packed, bool f64,
+                               HostTables& out) {
+    auto cell_at = [&](int64_t pos) { return cells + 4 * (cells_packed ? pos : out.order[(size_t)pos]); };
+    out.conn.resize((size_t)n_cells * 4);
+    out.slots.resize((size_t)n_cells * 4);
+    out.cperm.assign((size_t)n_cells, (uint8_t)0xE4);   // identity corner order
+    out.clone.assign((size_t)n_cells, (uint8_t)0);
+
+    // ---- pass 1 (parallel over chunks): tile boundaries and the distinct vertices of every tile in first-touch
+    //      order; then (serial, per tile) where each tile's tables start (vertex lists at multiples of 16 entries,
+    //      offset lists at multiples of 8 entries: every per-tile table is 16-byte aligned for bulk copies)
+    const int64_t n_chunks = (n_cells + kCutChunk - 1) / kCutChunk;
+    std::vector<ChunkCut> cuts((size_t)n_chunks);
+    parallel_for_chunks(n_chunks, [&](int64_t i) {
+        cut_chunk(i * kCutChunk, std::min(n_cells, (i + 1) * kCutChunk), cell_at, cuts[(size_t)i]);
+    });
+    std::vector<TileRange> ranges;
+    std::vector<int64_t> chunk_touch_start((size_t)n_chunks + 1, 0);
+    {
+        size_t n_ranges = 0;
+        for (int64_t i = 0; i < n_chunks; ++i) {
+            n_ranges += cuts[(size_t)i].ranges.size();
+            chunk_touch_start[(size_t)i + 1] = chunk_touch_start[(size_t)i] + (int64_t)cuts[(size_t)i].touched.size();
+        }
+        ranges.reserve(n_ranges);
+    }
+    std::vector<int32_t> touched((size_t)chunk_touch_start[(size_t)n_chunks]);   // concatenated first-touch vertex lists
+    parallel_for_chunks(n_chunks, [&](int64_t i) {
+        const auto& t = cuts[(size_t)i].touched;
+        if (!t.empty()) memcpy(touched.data() + chunk_touch_start[(size_t)i], t.data(), t.size() * sizeof(int32_t));
+    });
+    int64_t vert_end = 0, voff_end = 0;
+    for (int64_t i = 0; i < n_chunks; ++i) {
+        for (TileRange r : cuts[(size_t)i].ranges) {
+            vert_end = (vert_end + 15) / 16 * 16;
+            voff_end = (voff_end + 7) / 8 * 8;
+            r.first_touch += chunk_touch_start[(size_t)i];
+            r.vert_start = vert_end;
+            r.voff_start = voff_end;
+            vert_end += r.nv;
+            voff_end += r.nv + 1;
+            ranges.push_back(r);
+        }
+        ChunkCut().ranges.swap(cuts[(size_t)i].ranges);
+        std::vector<int32_t>().swap(cuts[(size_t)i].touched);
+    }
+    // + padding so that 16-byte granular bulk copies of the last tile stay in bounds
+    if (vert_end + 16 > (int64_t)INT32_MAX || voff_end + 16 > (int64_t)INT32_MAX) {
+        set_error("tile vertex table exceeds int32 range");
+        return APL_ERR_INVALID;
+    }
+    out.tile_verts.assign((size_t)vert_end + 16, 0);
+    out.tile_vperm.assign((size_t)vert_end + 16, 0);
+    out.tile_voff.assign((size_t)voff_end + 16, 0);
+    const int64_t n_tiles = (int64_t)ranges.size();
+    out.tiles.assign((size_t)n_tiles * 6, 0);
+
+    // ---- pass 2 (parallel over tiles): local ids, reduce order, slots
+    for_tiles_parallel(n_tiles, [&](TileScratch& ws, int64_t tile) {
+        const TileRange& r = ranges[(size_t)tile];
+        const int32_t* verts = touched.data() + r.first_touch;
+        uint8_t tl[kTileTets * 4];
+        hash_tile_verts(ws, verts, r.nv);
+        for (int t = 0; t < r.ni; ++t) {
+            const int32_t* c = cell_at(r.item_start + t);
+            for (int a = 0; a < 4; ++a) tl[4 * t + a] = lookup_tile_vert(ws, c[a]);
+        }
+        finish_tile(ws, out, tile, r, 4, 4, 1, tl, verts, f64);
+    });
+    return APL_OK;
+}
 
 int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const double* points, int elem_bytes,
                 int layout, HostTables& out) {
@@ -609,76 +757,27 @@ int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const d
     if (points) morton_order(n_cells, n_points, cells, points, out.order);
     else std::iota(out.order.begin(), out.order.end(), (int64_t)0);
     if (layout == APL_LAYOUT_PAIR) return build_tiles_pair(cells, f64, out);
+    return build_tiles_ordered(n_cells, n_points, cells, false, f64, out);
+}
 
-    out.conn.resize((size_t)n_cells * 4);
-    out.slots.resize((size_t)n_cells * 4);
-    out.cperm.assign((size_t)n_cells, (uint8_t)0xE4);   // identity corner order
-    out.clone.assign((size_t)n_cells, (uint8_t)0);
-
-    // ---- pass 1 (serial): tile boundaries, the distinct vertices of every tile in first-touch order, and
-    //      where each tile's tables start (vertex lists at multiples of 16 entries, offset lists at multiples
-    //      of 8 entries: every per-tile table is 16-byte aligned for bulk copies)
-    std::vector<TileRange> ranges;
-    ranges.reserve((size_t)(n_cells / kTileTets + 1));
-    std::vector<int32_t> touched;   // concatenated first-touch vertex lists
-    touched.reserve((size_t)(n_cells / 2 + 16));
-    {
-        std::vector<int32_t> stamp((size_t)n_points, -1);  // tile that last touched the vertex
-        int64_t tile_start = 0, first = 0, vert_end = 0, voff_end = 0;
-        int32_t tile_id = 0;
-        auto close_tile = [&](int64_t tile_end) {
-            const int nt = (int)(tile_end - tile_start);
-            if (nt == 0) return;
-            const int nv = (int)((int64_t)touched.size() - first);
-            vert_end = (vert_end + 15) / 16 * 16;
-            voff_end = (voff_end + 7) / 8 * 8;
-            ranges.push_back({tile_start, nt, nv, first, vert_end, voff_end});
-            vert_end += nv;
-            voff_end += nv + 1;
-            first = (int64_t)touched.size();
-            tile_start = tile_end;
-            ++tile_id;
-        };
-        for (int64_t pos = 0; pos < n_cells; ++pos) {
-            const int32_t* c = cells + 4 * out.order[(size_t)pos];
-            // A tile closes when it is full.  Vertex budget: tiles must start at multiples of 4 tets
-            // (16-byte aligned byte-wide connectivity), so the budget is checked every 4 tets with room
-            // for the worst case of 16 new vertices in the next 4.
-            const int64_t in_tile = pos - tile_start;
-            const int nv_open = (int)((int64_t)touched.size() - first);
-            if (in_tile == kTileTets || (in_tile % 4 == 0 && in_tile > 0 && nv_open + 16 > kTileVerts)) close_tile(pos);
-            for (int a = 0; a < 4; ++a)
-                if (stamp[(size_t)c[a]] != tile_id) {
-                    stamp[(size_t)c[a]] = tile_id;
-                    touched.push_back(c[a]);
-                }
-        }
-        close_tile(n_cells);
-        // + padding so that 16-byte granular bulk copies of the last tile stay in bounds
-        if (vert_end + 16 > (int64_t)INT32_MAX || voff_end + 16 > (int64_t)INT32_MAX) {
-            set_error("tile vertex table exceeds int32 range");
-            return APL_ERR_INVALID;
-        }
-        out.tile_verts.assign((size_t)vert_end + 16, 0);
-        out.tile_vperm.assign((size_t)vert_end + 16, 0);
-        out.tile_voff.assign((size_t)voff_end + 16, 0);
+// Tiling of connectivity that is ALREADY in packed order (sorted on the device, setup.cu): out.order holds the
+// permutation that produced it (packed position -> caller's cell).
+int build_tiles_packed(int64_t n_cells, int64_t n_points, const int32_t* packed_cells, std::vector<int64_t>&& order,
+                       int elem_bytes, HostTables& out) {
+    if (n_cells < 0 || n_points <= 0 || (int64_t)order.size() != n_cells) {
+        set_error("build_tiles_packed: bad sizes");
+        return APL_ERR_INVALID;
     }
-    const int64_t n_tiles = (int64_t)ranges.size();
-    out.tiles.assign((size_t)n_tiles * 6, 0);
-
-    // ---- pass 2 (parallel over tiles): local ids, reduce order, slots
-    for_tiles_parallel(n_tiles, [&](TileScratch& ws, int64_t tile) {
-        const TileRange& r = ranges[(size_t)tile];
-        const int32_t* verts = touched.data() + r.first_touch;
-        uint8_t tl[kTileTets * 4];
-        hash_tile_verts(ws, verts, r.nv);
-        for (int t = 0; t < r.ni; ++t) {
-            const int32_t* c = cells + 4 * out.order[(size_t)(r.item_start + t)];
-            for (int a = 0; a < 4; ++a) tl[4 * t + a] = lookup_tile_vert(ws, c[a]);
-        }
-        finish_tile(ws, out, tile, r, 4, 4, 1, tl, verts, f64);
-    });
-    return APL_OK;
+    if (n_cells > (int64_t)INT32_MAX / 2) {
+        set_error("n_cells exceeds the int32 range of the packed tables");
+        return APL_ERR_INVALID;
+    }
+    out = HostTables();
+    out.layout = APL_LAYOUT_TET;
+    out.n_cells = n_cells;
+    out.n_points = n_points;
+    out.order = std::move(order);
+    return build_tiles_ordered(n_cells, n_points, packed_cells, true, elem_bytes == 8, out);
 }
 
 // ---- PAIR layout ---------------------------------------------------------------------------------------

@@ -61,6 +61,7 @@ class WarpPotentialFem(WarpPotential):
             **{k: np.ascontiguousarray(getattr(materials, k), dtype=npdt) for k in self.MATERIAL_NAMES}
         )
         n_cells = self.region.cells.shape[0]
+        self.n_cells = int(n_cells)
         self.n_points = int(n_points if n_points is not None else (self.region.cells.max() + 1 if n_cells else 1))
         if self.device.type != "cuda":
             raise _lib.NativeError("apple_b200 potentials live on a CUDA device (there is no CPU path)")
@@ -121,9 +122,63 @@ class WarpPotentialFem(WarpPotential):
     def materials_from_region(cls, region: Region, requires_grad: Sequence[str]) -> SimpleNamespace:
         raise NotImplementedError
 
+    @classmethod
+    def from_device_mesh(cls, cells: torch.Tensor, points: torch.Tensor, *, fraction=None, dtype: torch.dtype | None = None,
+                         name: str | None = None, requires_grad: Sequence[str] = (), scatter: int | None = None,
+                         morton: bool = True, _second=None, **materials):
+        """Setup ENTIRELY on the GPU (``apl_fem_create_from_mesh``): ``cells`` (n_cells, 4) int32 and ``points``
+        (n_points, 3) float64 are CUDA tensors, the materials (``mu=``, ``lambda_=``, ``activation=``) and the optional
+        ``fraction`` (``cell_data["Fraction"]``) CUDA tensors of ``dtype``.  The rest shape -- what
+        ``Region.compute_grad`` (``jax/fem/region/_region.py:84-108``) and ``from_region`` (``warp/fem/_base.py:93-111``)
+        produce on the host -- is computed by a kernel straight into the packed planes; nothing but the connectivity
+        (for the tile tables) visits the host.  ``self.region`` then holds no host arrays."""
+        self = cls.__new__(cls)
+        WarpPotential.__init__(self, name=name, requires_grad=requires_grad)
+        self.dtype = dtype or config.default_dtype
+        if not (cells.is_cuda and points.is_cuda):
+            raise _lib.NativeError("from_device_mesh takes CUDA tensors (there is no CPU path)")
+        self.device = cells.device
+        self.scatter = scatter
+        if cells.dtype != torch.int32 or cells.dim() != 2 or cells.shape[1] != 4:
+            raise TypeError("cells: expected an (n_cells, 4) int32 tensor")
+        if points.dtype != torch.float64 or points.dim() != 2 or points.shape[1] != 3:
+            raise TypeError("points: expected an (n_points, 3) float64 tensor")
+        cells, points = cells.contiguous(), points.contiguous()
+        n_cells = int(cells.shape[0])
+        missing = [k for k in cls.MATERIAL_NAMES if k not in materials]
+        if missing or set(materials) - set(cls.MATERIAL_NAMES):
+            raise KeyError(f"{cls.__name__}.from_device_mesh needs exactly the materials {cls.MATERIAL_NAMES}")
+
+        def dev(a, shape):
+            if a is None:
+                return None
+            t = torch.as_tensor(a, dtype=self.dtype, device=self.device).contiguous()
+            if tuple(t.shape) != shape:
+                raise ValueError(f"expected a tensor of shape {shape}, got {tuple(t.shape)}")
+            return t
+
+        mats = {k: dev(v, (n_cells, 6) if k == "activation" else (n_cells,)) for k, v in materials.items()}
+        fraction = dev(fraction, (n_cells,))
+        second = {k: dev(v, (n_cells,)) for k, v in (_second or {}).items()}
+        self.region = SimpleNamespace(cells=None, dhdX=None, dV=None)      # no host copies on this path
+        self.materials = SimpleNamespace(**mats)
+        self.n_cells, self.n_points, self.points = n_cells, int(points.shape[0]), None
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream(self.device).synchronize()      # the setup kernels run on the default stream
+            _lib.check(_lib.lib().apl_fem_create_from_mesh(
+                cls.KIND, _lib.dtype_code(self.dtype), n_cells, self.n_points, _lib.dev_ptr(cells), _lib.dev_ptr(points),
+                _lib.dev_ptr(fraction), _lib.dev_ptr(mats.get("mu")), _lib.dev_ptr(mats.get("lambda_")),
+                _lib.dev_ptr(mats.get("activation")), _lib.dev_ptr(second.get("fraction")), _lib.dev_ptr(second.get("mu")),
+                1 if morton else 0, self.device.index if self.device.index is not None else torch.cuda.current_device(),
+                ctypes.byref(handle)))
+        self._handle = handle
+        self.layout = int(_lib.lib().apl_fem_layout(self._handle))
+        return self
+
     @property
     def launch_dim(self) -> tuple[int, int]:
-        return tuple(self.region.dhdX.shape[:2])
+        return (self.n_cells, 1)
 
     @property
     def info(self) -> dict:
@@ -137,6 +192,8 @@ class WarpPotentialFem(WarpPotential):
         """Replace per-cell materials (and/or ``dV``) without rebuilding the tiling."""
         npdt = _lib.np_dtype(self.dtype)
         arrs = {}
+        if self.region.cells is None:
+            raise NotImplementedError("set_materials: rebuild a potential created by from_device_mesh instead")
         if dV is not None:
             self.region.dV = np.ascontiguousarray(dV, dtype=npdt).reshape(self.region.dV.shape)
             arrs["dV"] = self.region.dV
@@ -198,7 +255,7 @@ class WarpPotentialFem(WarpPotential):
         ld_in = _lib.field_ld(u, self.n_points, self.dtype, "u")
         if _lib.field_ld(p, self.n_points, self.dtype, "p") != ld_in:
             raise ValueError("p must have the layout of u")
-        n_cells = self.region.cells.shape[0]
+        n_cells = self.n_cells
         out = {}
         for name in self.MATERIAL_NAMES:
             shape = (n_cells, 6) if name == "activation" else (n_cells,)

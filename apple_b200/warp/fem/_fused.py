@@ -50,6 +50,20 @@ class FusedSnhArap(WarpPotentialFem):
         )
         return handle
 
+    @classmethod
+    def from_device_mesh(cls, cells, points, *, mu, lambda_, mu_arap, fraction=None, fraction_arap=None, **kw):
+        """Fused pair built on the GPU (see ``WarpPotentialFem.from_device_mesh``): ``mu`` / ``lambda_`` / ``fraction`` are
+        the Stable Neo-Hookean half, ``mu_arap`` / ``fraction_arap`` the ARAP half."""
+        kw.setdefault("name", "snh+arap")
+        second = {"mu": mu_arap}
+        if fraction_arap is not None:
+            second["fraction"] = fraction_arap
+        self = super().from_device_mesh(cells, points, fraction=fraction, mu=mu, lambda_=lambda_, _second=second, **kw)
+        self.arap_materials = SimpleNamespace(mu=mu_arap)
+        self.arap_dV = None
+        self.parts = ("snh", "arap")
+        return self
+
     def mixed_derivative_prod(self, u, p) -> dict:
         raise NotImplementedError("evaluate mixed_derivative_prod on the two potentials of the fused pair separately")
 

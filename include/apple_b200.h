@@ -98,6 +98,25 @@ int apl_fem_create_snh_arap(int dtype, int64_t n_cells, int64_t n_points, const 
                             apl_fem_t** out);
 void apl_fem_destroy(apl_fem_t* fem);
 
+/* ---- setup from DEVICE arrays: replaces Region.compute_grad (jax/fem/region/_region.py:84-108: dXdr, drdX,
+ * dV = det / 6, dhdX = dhdr . drdX for the linear tetrahedron, jax/fem/element/_tetra.py:36-45 with the one-point
+ * rule jax/fem/quadrature/_tetra.py:12-15) TOGETHER WITH WarpPotentialFem.from_region (warp/fem/_base.py:93-111:
+ * dV *= Fraction, materials), for meshes that already live in HBM (the reference does this once per mesh on the
+ * host in JAX; at 64 M tets that is minutes, here seconds).  DEVICE arrays:
+ *   cells      int32  (n_cells,4)
+ *   points     double (n_points,3)  rest positions
+ *   fraction   dtype  (n_cells,)    cell_data["Fraction"] (warp/fem/utils/_material.py:19-23); NULL = 1
+ *   mu, lambda_, activation         as in apl_fem_create, on the device
+ *   fraction2, mu2                  the ARAP half of APL_KIND_SNH_ARAP (fraction2 NULL = 1), else NULL
+ * morton != 0 orders the tets along the Morton curve of their centroids (device radix sort, same keys and the
+ * same stable order as apl_fem_create with `points`), 0 keeps the given order.  The rest shape is evaluated in
+ * fp64 and rounded to `dtype`.  Synchronises the device (setup-time call).  A tet with zero rest volume is an
+ * error (APL_ERR_MESH), negative volumes are accepted as in the reference (region/_region.py:98-99 only warns). */
+int apl_fem_create_from_mesh(int kind, int dtype, int64_t n_cells, int64_t n_points, const int32_t* cells,
+                             const double* points, const void* fraction, const void* mu, const void* lambda_,
+                             const void* activation, const void* fraction2, const void* mu2, int morton, int device,
+                             apl_fem_t** out);
+
 /* Layout of the handles created AFTERWARDS (process-wide; default APL_LAYOUT_TET).  No reference counterpart. */
 int apl_set_layout(int layout);
 int apl_fem_layout(const apl_fem_t* fem);
