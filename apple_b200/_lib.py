@@ -12,7 +12,10 @@ from pathlib import Path
 import numpy as np
 import torch
 
-LIB_PATH = Path(__file__).resolve().parent / "libapple_b200.so"
+import os as _os
+
+# APL_LIB: a tuning-experiment build of the same sources (apple_b200/build.py); the product library otherwise
+LIB_PATH = Path(_os.environ.get("APL_LIB") or Path(__file__).resolve().parent / "libapple_b200.so")
 
 # constants of include/apple_b200.h
 OK = 0
@@ -29,7 +32,6 @@ S_SUMS, S_ALPHA_J, S_ACC_J, S_FT_J = 20, 32, 48, 64
 
 # every symbol include/apple_b200.h declares: name -> (restype, argtypes)
 PART_ALL, PART_BOUNDARY, PART_INTERIOR = 0, 1, 2
-LAYOUT_TET, LAYOUT_PAIR = 0, 1
 
 SIGNATURES = {
     "apl_version": (c_int, []),
@@ -44,9 +46,6 @@ SIGNATURES = {
                                          c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(c_void_p)]),
     "apl_fem_info": (c_int, [c_void_p, POINTER(c_int64)]),
     "apl_fem_host_tables": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "apl_set_layout": (c_int, [c_int]),
-    "apl_fem_layout": (c_int, [c_void_p]),
-    "apl_fem_host_corner_tables": (c_int, [c_void_p, c_void_p, c_void_p]),
     "apl_fem_host_planes": (c_int, [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64)]),
     "apl_fem_set_materials": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "apl_fem_eval": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -61,6 +60,13 @@ SIGNATURES = {
     "apl_halo_pack": (c_int, [c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "apl_halo_unpack": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                 c_int, c_void_p, c_void_p]),
+    "apl_xchg_create": (c_int, [c_int, c_int, c_int, c_int64, POINTER(c_void_p)]),
+    "apl_xchg_destroy": (None, [c_void_p]),
+    "apl_xchg_ipc_handle": (c_int, [c_void_p, c_void_p]),
+    "apl_xchg_connect": (c_int, [c_void_p, c_void_p]),
+    "apl_xchg_set_plan": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "apl_xchg_push": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "apl_xchg_pull": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "apl_pncg_create": (c_int, [c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
     "apl_pncg_destroy": (None, [c_void_p]),

@@ -16,8 +16,11 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
-OBJ = CSRC / "build"
-LIB = ROOT / "libapple_b200.so"
+# tuning experiments: APL_BUILD_TAG=x APL_NVCC_FLAGS="-DAPL_SLOT_BUFS=1" builds libapple_b200_x.so next to the product
+# library (own object directory); APL_LIB=<path> makes apple_b200._lib load it.  Never the product build.
+_TAG = os.environ.get("APL_BUILD_TAG", "")
+OBJ = CSRC / ("build_" + _TAG if _TAG else "build")
+LIB = ROOT / (f"libapple_b200_{_TAG}.so" if _TAG else "libapple_b200.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 COMMON = [
@@ -31,14 +34,7 @@ COMMON = [
     "-Xcompiler",
     "-O3",
 ]
-if os.environ.get("APL_PROFILE_KNOBS"):  # profiling-only kernel knobs (never set for the product build)
-    COMMON.append("-DAPL_PROFILE_KNOBS")
-if os.environ.get("APL_GATHER_LDG"):     # experiment: register-staged gather of ld = 3 rows in the producer warp
-    COMMON.append("-DAPL_GATHER_LDG")
-if os.environ.get("APL_SMEM_BUDGET_KB"):  # experiment: shared-memory budget per CTA (number of pipeline stages vs CTAs per SM)
-    COMMON.append("-DAPL_SMEM_BUDGET_KB=" + os.environ["APL_SMEM_BUDGET_KB"])
-if os.environ.get("APL_TILE_TETS"):
-    COMMON.append("-DAPL_TILE_TETS=" + os.environ["APL_TILE_TETS"])
+COMMON += os.environ.get("APL_NVCC_FLAGS", "").split()
 
 
 def _units():
@@ -47,6 +43,7 @@ def _units():
         ("capi", "capi.cu", []),
         ("pncg", "pncg.cu", []),
         ("setup", "setup.cu", []),
+        ("xchg", "xchg.cu", []),
     ]
     for tname, t in (("f32", "float"), ("f64", "double")):
         for kind in (0, 1, 2, 3):

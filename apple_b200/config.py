@@ -7,8 +7,6 @@ from . import _lib
 
 default_dtype: torch.dtype = torch.float32
 scatter: int = _lib.SCATTER_TILE  # assembly strategy of the element kernels
-layout: int = _lib.LAYOUT_TET     # how new potentials pack their mesh: one consumer thread per tet, or (EXPERIMENTAL)
-                                  # _lib.LAYOUT_PAIR: one per pair of face-adjacent tets (APL_SCATTER_TILE only)
 
 
 def default_device() -> torch.device:

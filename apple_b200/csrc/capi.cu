@@ -30,8 +30,6 @@ static int pack_planes(apl_fem* f, const T* dhdX, const T* dV, const T* mu, cons
     planes.assign((size_t)f->nplanes * f->plane_stride * VEC, (T)0);
     for (int64_t pos = 0; pos < n; ++pos) {
         const int64_t c = f->host.order[(size_t)pos];
-        const unsigned cp = f->host.cperm[(size_t)pos];      // corner order of the packed record
-        const bool clone = f->host.clone[(size_t)pos] != 0;  // zero-volume copy: contributes nothing
         T rec[20] = {0};
         if (dhdX) {
             const T* d = dhdX + 12 * c;
@@ -46,19 +44,16 @@ static int pack_planes(apl_fem* f, const T* dhdX, const T* dV, const T* mu, cons
                           " do not sum to zero (only linear tetrahedra are supported)");
                 return APL_ERR_MESH;
             }
-            // rows 1..3 of dhdX in the packed corner order (row 0 is minus their sum for ANY corner order)
-            for (int a = 1; a < 4; ++a) {
-                const int src = (int)((cp >> (2 * a)) & 3u);
-                for (int J = 0; J < 3; ++J) rec[3 * (a - 1) + J] = d[3 * src + J];
-            }
+            // rows 1..3 of dhdX (row 0 is minus their sum)
+            for (int k = 0; k < 9; ++k) rec[k] = d[3 + k];
         }
-        rec[9] = (dV && !clone) ? dV[c] : (T)0;
+        rec[9] = dV ? dV[c] : (T)0;
         rec[10] = mu ? mu[c] : (T)0;
         rec[11] = la ? la[c] : (T)0;
         if (act)
             for (int k = 0; k < 6; ++k) rec[12 + k] = act[6 * c + k];
         if (f->kind == APL_KIND_SNH_ARAP) {  // second potential on the same cells
-            rec[12] = (dV2 && !clone) ? dV2[c] : (T)0;
+            rec[12] = dV2 ? dV2[c] : (T)0;
             rec[13] = mu2 ? mu2[c] : (T)0;
         }
         for (int k = 0; k < nrec; ++k) {
@@ -246,10 +241,9 @@ __global__ void halo_unpack_kernel(long long n_shared, const long long* __restri
 
 // ---- mixed derivative product (per cell, no assembly) ------------------------------------------------
 // One thread per packed tet position; gathers straight from global memory (a setup / adjoint-time operator, not
-// the hot path), works on both layouts: in the PAIR layout position j of a tile of ni items belongs to item
-// j mod ni and uses the corners (s0, s1, s2, apex of the first / second tet).
+// the hot path).
 template <typename T, int KIND>
-__global__ void __launch_bounds__(256) fem_mixed_kernel(const int4* __restrict__ tiles, int n_tiles, int layout,
+__global__ void __launch_bounds__(256) fem_mixed_kernel(const int4* __restrict__ tiles, int n_tiles,
                                                         const unsigned char* __restrict__ conn,
                                                         const int* __restrict__ tile_verts, const uint4* __restrict__ planes,
                                                         long long plane_stride, const int* __restrict__ order,
@@ -263,16 +257,8 @@ __global__ void __launch_bounds__(256) fem_mixed_kernel(const int4* __restrict__
         if (j >= n_tets) continue;
         const long long pos = (long long)h.x + j;
         const int cell = __ldg(order + pos);
-        if (cell < 0) continue;   // zero-volume clone
-        int l[4];
-        if (layout == APL_LAYOUT_PAIR) {
-            const int ni = n_tets >> 1, item = j < ni ? j : j - ni;
-            const unsigned char* c = conn + 8ll * ((long long)(h.x >> 1) + item);
-            l[0] = c[0]; l[1] = c[1]; l[2] = c[2]; l[3] = j < ni ? c[3] : c[4];
-        } else {
-            const unsigned char* c = conn + 4ll * pos;
-            l[0] = c[0]; l[1] = c[1]; l[2] = c[2]; l[3] = c[3];
-        }
+        const unsigned char* cc = conn + 4ll * pos;
+        const int l[4] = {cc[0], cc[1], cc[2], cc[3]};
         Rec<T, NREC> rec;
 #pragma unroll
         for (int k = 0; k < Rec<T, NREC>::NPL; ++k) rec.q[k] = __ldg(planes + k * plane_stride + pos);
@@ -306,7 +292,7 @@ static int mixed_typed(apl_fem* f, const void* u, const void* p, int ld, void* d
     int grid = f->num_sms * 8;
     if (grid > n_tiles) grid = n_tiles;
 #define APL_MIXED(K)                                                                                              \
-    fem_mixed_kernel<T, K><<<grid, 256, 0, stream>>>((const int4*)f->d_tiles, n_tiles, f->host.layout,             \
+    fem_mixed_kernel<T, K><<<grid, 256, 0, stream>>>((const int4*)f->d_tiles, n_tiles,                             \
                                                      (const unsigned char*)f->d_conn, (const int*)f->d_tile_verts, \
                                                      (const uint4*)f->d_planes, f->plane_stride, f->d_order,       \
                                                      (const T*)u, (const T*)p, ld, (T*)d_mu, (T*)d_la, (T*)d_act)
@@ -412,8 +398,6 @@ int fem_upload_tables(apl_fem* f) {
 
 using namespace apl;
 
-static std::atomic<int> g_default_layout{APL_LAYOUT_TET};
-
 extern "C" {
 
 int apl_version(void) { return 100; }
@@ -469,7 +453,7 @@ static int fem_create_impl(int kind, int dtype, int64_t n_cells, int64_t n_point
     f->nrec = rec_size(kind);
     const int vec = dtype == APL_F32 ? 4 : 2;
     f->nplanes = (f->nrec + vec - 1) / vec;
-    int rc = build_tiles(n_cells, n_points, cells, points, dtype == APL_F32 ? 4 : 8, g_default_layout.load(), f->host);
+    int rc = build_tiles(n_cells, n_points, cells, points, dtype == APL_F32 ? 4 : 8, f->host);
     if (rc != APL_OK) { delete f; return rc; }
     f->plane_stride = (f->host.n_packed() + 31) / 32 * 32;
     if (f->plane_stride == 0) f->plane_stride = 32;
@@ -518,24 +502,6 @@ int apl_fem_info(const apl_fem_t* f, int64_t info[10]) {
     info[7] = f->device;
     info[8] = (int64_t)f->host.tile_voff.size();
     info[9] = f->host.n_packed();
-    return APL_OK;
-}
-
-int apl_set_layout(int layout) {
-    if (layout != APL_LAYOUT_TET && layout != APL_LAYOUT_PAIR) { set_error("apl_set_layout: unknown layout"); return APL_ERR_INVALID; }
-    g_default_layout.store(layout);
-    return APL_OK;
-}
-
-int apl_fem_layout(const apl_fem_t* f) {
-    if (!f) { set_error("apl_fem_layout: NULL handle"); return APL_ERR_INVALID; }
-    return f->host.layout;
-}
-
-int apl_fem_host_corner_tables(const apl_fem_t* f, uint8_t* cperm, uint8_t* clone) {
-    if (!f) { set_error("apl_fem_host_corner_tables: NULL handle"); return APL_ERR_INVALID; }
-    if (cperm) memcpy(cperm, f->host.cperm.data(), f->host.cperm.size());
-    if (clone) memcpy(clone, f->host.clone.data(), f->host.clone.size());
     return APL_OK;
 }
 
@@ -588,7 +554,7 @@ int apl_fem_set_materials(apl_fem_t* f, const void* dV, const void* mu, const vo
     };
     for (int64_t pos = 0; pos < f->host.n_packed(); ++pos) {
         const int64_t c = f->host.order[(size_t)pos];
-        if (dV && !f->host.clone[(size_t)pos]) put(9, pos, dV, c);
+        if (dV) put(9, pos, dV, c);
         if (mu) put(10, pos, mu, c);
         if (lambda_ && f->kind != APL_KIND_ARAP) put(11, pos, lambda_, c);
         if (activation && f->kind == APL_KIND_SNH_MUSCLE)
@@ -697,10 +663,10 @@ int apl_fem_mixed_derivative_prod(apl_fem_t* f, const void* u, const void* p, in
         return APL_ERR_STATE;
     }
     if (!u || !p || (ld_in != 3 && ld_in != 4)) { set_error("apl_fem_mixed_derivative_prod: bad arguments"); return APL_ERR_INVALID; }
-    if (!f->d_order) {   // first use: packed tet position -> caller's cell, -1 for zero-volume clones
+    if (!f->d_order) {   // first use: packed tet position -> caller's cell
         const int64_t n = f->host.n_packed();
         std::vector<int32_t> ord((size_t)n + 1);
-        for (int64_t i = 0; i < n; ++i) ord[(size_t)i] = f->host.clone[(size_t)i] ? -1 : (int32_t)f->host.order[(size_t)i];
+        for (int64_t i = 0; i < n; ++i) ord[(size_t)i] = (int32_t)f->host.order[(size_t)i];
         APL_CUDA_CHECK(cudaSetDevice(f->device));
         APL_CUDA_CHECK(cudaMalloc((void**)&f->d_order, ((size_t)n + 1) * sizeof(int32_t)));
         APL_CUDA_CHECK(cudaMemcpy(f->d_order, ord.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));

@@ -15,34 +15,32 @@ namespace apl {
 #endif
 constexpr int kTileTets = APL_TILE_TETS;   // tets per tile == consumer threads per CTA
 constexpr int kTileVerts = APL_TILE_TETS * 3 / 4;  // max distinct vertices per tile (uint8 local ids, <= 256)
+// Reduction slots of a tile: one per tet corner plus up to kSlotPads unused pad slots that keep the slot-range
+// starts of a reduce group in distinct bank groups (tiling.cpp); the kernels allocate kSlotsAlloc slots per buffer.
+constexpr int kSlotPads = APL_TILE_TETS * 5 / 8;
+constexpr int kSlotsAlloc = 4 * APL_TILE_TETS + kSlotPads;
 
 void set_error(const std::string& msg);
 
 // Host-side packed mesh (built by tiling.cpp, uploaded by capi.cu).
-// ITEM = what one consumer thread of the element kernels evaluates: one tet (APL_LAYOUT_TET) or two tets that
-// share a face (APL_LAYOUT_PAIR; item i of a tile of ni items starting at tet position ts owns the packed tet
-// positions ts + i and ts + ni + i).
 struct HostTables {
-    int layout = APL_LAYOUT_TET;
     int64_t n_cells = 0, n_points = 0;
     std::vector<int32_t> tiles;        // (n_tiles,6): tet_start, n_tets, vert_start, n_verts, voff_start, n_slots
     std::vector<int64_t> order;        // packed tet position -> caller's cell index
-    std::vector<uint8_t> cperm;        // packed tet position -> corner order: new corner k = old corner (cperm >> 2k) & 3
-    std::vector<uint8_t> clone;        // packed tet position -> 1: zero-volume copy (pads a pair item), contributes nothing
-    std::vector<uint8_t> conn;         // tile-local vertex ids: (n_cells,4) per tet / (n_items,8) per pair (5 used)
+    std::vector<uint8_t> conn;         // tile-local vertex ids, (n_cells,4)
     std::vector<uint16_t> slots;       // reduction slots, same shape
     std::vector<int32_t> tile_verts;   // global vertex id of every tile-local id (tile start padded to x16)
     std::vector<uint8_t> tile_vperm;   // same indexing: local ids in reduce order (about decreasing valence)
     std::vector<uint16_t> tile_voff;   // per tile n_verts+1 slot offsets, starting at voff_start (x8)
     int64_t n_tiles() const { return (int64_t)tiles.size() / 6; }
-    int64_t n_packed() const { return (int64_t)order.size(); }   // packed tet positions (>= n_cells for pairs)
+    int64_t n_packed() const { return (int64_t)order.size(); }   // packed tet positions
 };
 
 // cells: (n_cells,4) int32.  points: (n_points,3) double or nullptr.  elem_bytes: 4 (fp32) or 8 (fp64), the
 // scalar size of the nodal rows the kernels keep in shared memory (decides which local ids collide).
-// layout: APL_LAYOUT_TET or APL_LAYOUT_PAIR.  Returns APL_OK or error code.
+// Returns APL_OK or error code.
 int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const double* points, int elem_bytes,
-                int layout, HostTables& out);
+                HostTables& out);
 
 // Tiling of connectivity ALREADY in packed (Morton) order -- the device-side setup (setup.cu) sorts the cells on
 // the GPU: packed_cells[pos] is the tet at packed position pos, order[pos] the caller's index of that tet.
@@ -67,7 +65,7 @@ struct apl_fem {
     void* d_tile_voff = nullptr;
     void* d_tile_vperm = nullptr;
     void* d_planes = nullptr;
-    int32_t* d_order = nullptr;     // packed tet position -> caller's cell (-1: clone); uploaded on first use
+    int32_t* d_order = nullptr;     // packed tet position -> caller's cell; uploaded on first use
     double* d_partials = nullptr;   // per-CTA scalar partials (2 per CTA)
     unsigned int* d_counter = nullptr;
     int max_grid = 0;

@@ -21,15 +21,10 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <mutex>
 
 #include "common.h"
 #include "elem_math.cuh"
-
-#ifdef APL_PROFILE_KNOBS
-namespace apl {
-__device__ int g_knobs = 0;   // profiling only (APL_KNOBS): skip REDs / reduce / slot stores / barriers / consumers
-}
-#endif
 
 #include "tile_logic.cuh"
 
@@ -65,9 +60,6 @@ struct FemArgs {
     int dyn_j = 0;                   // add the device-side trial counter scal[APL_S_J] to alpha_idx, skip_b, fun_d
     double* fun_d = nullptr;         // double-precision sinks for the energy / quadratic form
     double* quad_d = nullptr;
-#ifdef APL_PROFILE_KNOBS
-    int knobs = 0;  // profiling only: 1 skip REDs, 2 plain stores instead of REDs, 4 skip reduce, 8 skip slot stores
-#endif
 };
 
 template <typename T>
@@ -242,15 +234,6 @@ __device__ __forceinline__ void tile_flush(int tid, int n_verts, int gv, const T
         T acc[3 * NOUT];
         tile_flush_read<T, OPS>(vbuf, tid, acc);
         int k = 0;
-#ifdef APL_PROFILE_KNOBS
-        if (g_knobs & 1) return;
-        if (g_knobs & 2) {
-            if constexpr (Cfg::kGrad) { T* q = a.grad + (long long)a.ld_out * gv; q[0] = acc[k]; q[1] = acc[k + 1]; q[2] = acc[k + 2]; k += 3; }
-            if constexpr (Cfg::kDiag) { T* q = a.diag + (long long)a.ld_out * gv; q[0] = acc[k]; q[1] = acc[k + 1]; q[2] = acc[k + 2]; k += 3; }
-            if constexpr (Cfg::kProd) { T* q = a.prod + (long long)a.ld_out * gv; q[0] = acc[k]; q[1] = acc[k + 1]; q[2] = acc[k + 2]; k += 3; }
-            return;
-        }
-#endif
         if constexpr (Cfg::kGrad) { if (a.grad) red_row(a.grad, gv, a.ld_out, acc + k); k += 3; }
         if constexpr (Cfg::kDiag) { if (a.diag) red_row(a.diag, gv, a.ld_out, acc + k); k += 3; }
         if constexpr (Cfg::kProd) { if (a.prod) red_row(a.prod, gv, a.ld_out, acc + k); k += 3; }
@@ -335,12 +318,23 @@ __global__ void __launch_bounds__(kTileTets, (sizeof(T) == 4 ? 2 : 1)) fem_tile_
 
 // ---- PIPELINED kernel (APL_SCATTER_TILE, the product path) ------------------------------------------
 //
-// 9 warps per CTA.  Warp 8 is the PRODUCER: for every tile it issues TMA bulk copies
-// (cp.async.bulk, completion on an mbarrier) of the tile's static planes, connectivity, slots and
-// vertex tables into the next free shared-memory stage, waits for the vertex table, and gathers the
-// tile's vertices with cp.async (LDGSTS) into the same stage.  Warps 0-7 are CONSUMERS (one thread
-// per tet): wait for the stage, compute, write slots, reduce, flush with vector REDs, release the
-// stage.  kStages tiles are in flight per CTA, so global-memory latency is off the critical path.
+// 9 warps per CTA, persistent, no CTA-wide barrier in the tile loop.
+//
+// Warp 8 is the PRODUCER: for every tile it issues TMA bulk copies (cp.async.bulk, completion on an mbarrier)
+// of the tile's static planes, connectivity, slots and vertex tables into the next free shared-memory stage,
+// waits for the vertex table, and gathers the tile's vertices into the same stage (16-byte rows: cp.async /
+// LDGSTS; 12-byte rows: one 8-byte and one 4-byte load per row through registers, one 16-byte store).
+//
+// Warps 0-7 are CONSUMERS (one thread per tet) and run two phases per tile:
+//   COMPUTE(i): wait for the stage, evaluate the tet, write each corner's contribution to its slot of slot
+//               buffer i % NB, release the stage to the producer;
+//   REDUCE(i):  two lanes per vertex sum the vertex's slot range of buffer i % NB and issue the vector REDs
+//               to global memory straight from the reducing lanes.
+// With NB = 2 slot buffers the phases are software-pipelined -- COMPUTE(i+1) runs BEFORE REDUCE(i) -- and
+// hand-offs are mbarriers (slots_full[b]: every consumer arrived after its slot stores; slots_free[b]: every
+// consumer arrived after its reduction), so a warp that finishes a phase early starts the next phase of the
+// next tile instead of idling at a barrier; warps drift apart by up to one phase.  Instantiations whose two
+// slot buffers would not fit the target CTAs per SM run the phases in order with NB = 1 (same mbarriers).
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -379,7 +373,6 @@ __device__ __forceinline__ void cp_async(unsigned dst, const void* src) {
 __device__ __forceinline__ void cp_async_arrive_noinc(unsigned bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kTileTets) : "memory"); }
 
 template <typename T>
 __device__ __forceinline__ void gather_row_async(unsigned dst, const T* base, int v, int ld) {
@@ -395,19 +388,23 @@ __device__ __forceinline__ void gather_row_async(unsigned dst, const T* base, in
     }
 }
 
-#ifdef APL_GATHER_LDG
-// ld = 3 row through registers: the 12-byte row of vertex gv starts at 12 gv, so either its first or its last
-// 8 bytes are 8-byte aligned (fp32; the base pointer must be 8-byte aligned, checked by apl_fem_eval in this build)
+// ld = 3 row through registers.  fp32: the 12-byte row of vertex gv starts at 12 gv, so either its first or its
+// last 8 bytes are 8-byte aligned when the base pointer is (the caller checks); otherwise three scalar loads.
 template <typename T>
-__device__ __forceinline__ void load_row3_ldg(const T* __restrict__ base, int gv, T* r) {
+__device__ __forceinline__ void load_row3_ldg(const T* __restrict__ base, int gv, bool base_aligned8, T* r) {
     if constexpr (sizeof(T) == 4) {
         const char* row = reinterpret_cast<const char*>(base) + 12ll * gv;
-        const bool odd = gv & 1;
-        const float2 pr = __ldg(reinterpret_cast<const float2*>(row + (odd ? 4 : 0)));
-        const float one = __ldg(reinterpret_cast<const float*>(row + (odd ? 0 : 8)));
-        r[0] = odd ? one : pr.x;
-        r[1] = odd ? pr.x : pr.y;
-        r[2] = odd ? pr.y : one;
+        if (base_aligned8) {
+            const bool odd = gv & 1;
+            const float2 pr = __ldg(reinterpret_cast<const float2*>(row + (odd ? 4 : 0)));
+            const float one = __ldg(reinterpret_cast<const float*>(row + (odd ? 0 : 8)));
+            r[0] = odd ? one : pr.x;
+            r[1] = odd ? pr.x : pr.y;
+            r[2] = odd ? pr.y : one;
+        } else {
+            const float* q = reinterpret_cast<const float*>(row);
+            r[0] = __ldg(q); r[1] = __ldg(q + 1); r[2] = __ldg(q + 2);
+        }
     } else {
         const T* row = base + 3ll * gv;
         r[0] = __ldg(row); r[1] = __ldg(row + 1); r[2] = __ldg(row + 2);
@@ -422,27 +419,32 @@ __device__ __forceinline__ void store_row4(T* dst, const T* r) {
         *reinterpret_cast<double2*>(dst + 2) = make_double2(r[2], 0.0);
     }
 }
-#endif
 
 constexpr int kPipeThreads = kTileTets + 32;
 
-template <typename T, int KIND, int OPS, int LAYOUT = APL_LAYOUT_TET>
+#ifndef APL_GATHER_LDG
+#define APL_GATHER_LDG 0   // 1: 12-byte rows through registers (measured slower: the producer waits out a global-memory latency per tile); 0: three 4-byte cp.async per row
+#endif
+#ifndef APL_SLOT_BUFS
+#define APL_SLOT_BUFS 2    // slot buffers wanted (2: software-pipelined phases; 1: phases in order)
+#endif
+
+template <typename T, int KIND, int OPS>
 struct PipeCfg {
     using Cfg = TileCfg<T, OPS>;
-    // consumer threads: one per tet, or one per pair of tets (the stage layout is the same: a pair item
-    // has 8 bytes of connectivity and 16 bytes of slot ids, i.e. 4 and 8 bytes per tet as in the TET layout)
-    static constexpr int kConsumers = LAYOUT == APL_LAYOUT_PAIR ? kTileTets / 2 : kTileTets;
+    static constexpr int kConsumers = kTileTets;   // one consumer thread per tet
     static constexpr int kThreads = kConsumers + 32;
-    static constexpr int kNSlots = LAYOUT == APL_LAYOUT_PAIR ? kSlotsAllocPair : kSlotsAlloc;
+    static constexpr int kNSlots = kSlotsAlloc;
     static constexpr size_t kSlotBytes = (size_t)kNSlots * Cfg::SS * sizeof(T);
     static constexpr int NREC = RecSize<KIND>::value;
     static constexpr int NPL = Rec<T, NREC>::NPL;
-    // one stage: per-tet static data + the gathered vertex fields (all offsets multiples of 16 bytes)
+    // one stage: per-tet static data + the gathered vertex fields u, p (all offsets multiples of 16 bytes)
+    static constexpr size_t kVbufBytes = (size_t)kTileVerts * 8 * sizeof(T);
     static constexpr size_t oPlanes = 0;
     static constexpr size_t oConn = oPlanes + (size_t)NPL * kTileTets * 16;
     static constexpr size_t oSlots = oConn + (size_t)kTileTets * 4;
     static constexpr size_t oVbuf = oSlots + (size_t)kTileTets * 8;
-    static constexpr size_t oHdr = oVbuf + Cfg::kVbufBytes;
+    static constexpr size_t oHdr = oVbuf + kVbufBytes;
     static constexpr size_t kStageBytes = oHdr + 16;
     // one vertex-table slot (requested one tile ahead of its stage): global ids, reduce order, slot offsets
     static constexpr size_t oVerts = 0;
@@ -450,50 +452,96 @@ struct PipeCfg {
     static constexpr size_t oVoff = oVperm + (size_t)kTileVerts;
     static constexpr size_t kVtabBytes = oVoff + Cfg::kVoffRaw;
     static constexpr size_t kBarBytes = 128;
-    // as many stages as fit the target number of CTAs per SM (>= 2 always, <= 4); vertex ring = stages + 1
-    // shared-memory budget per CTA that decides the number of stages (tuning experiments: -DAPL_SMEM_BUDGET_KB=...)
+    // shared memory per CTA for the wanted CTAs per SM (227 KB per SM, 1 KB reserved per CTA)
+    static constexpr int kWantCtas = (sizeof(T) == 4 ? 2 : 1) * (256 / kTileTets);
 #ifdef APL_SMEM_BUDGET_KB
     static constexpr size_t kBudget = (size_t)APL_SMEM_BUDGET_KB * 1024;
 #else
-    static constexpr size_t kBudget = (size_t)(sizeof(T) == 4 ? 74 : 113) * 1024 * kTileTets / 256;
+    static constexpr size_t kBudget = (size_t)227 * 1024 / kWantCtas - 1024;
 #endif
-    static constexpr size_t kFixedBytes = kSlotBytes + kBarBytes + kVtabBytes;
-    static constexpr int kFit =
-        (int)((kBudget > kFixedBytes ? kBudget - kFixedBytes : 0) / (kStageBytes + kVtabBytes));
-    static constexpr int kStages = kFit < 2 ? 2 : (kFit > 4 ? 4 : kFit);
-    static constexpr int kVring = kStages + 1;
+    static constexpr size_t total(int nb, int stages) {
+        return kBarBytes + (size_t)nb * kSlotBytes + (size_t)(stages + nb + 1) * kVtabBytes + (size_t)stages * kStageBytes;
+    }
+    // two slot buffers (pipelined phases) when they fit next to two stages, else one
+    static constexpr int kSlotBufs = Cfg::NOUT == 0 ? 1 : ((APL_SLOT_BUFS >= 2 && total(2, 2) <= kBudget) ? 2 : 1);
+    static constexpr int kStages = total(kSlotBufs, 4) <= kBudget ? 4 : (total(kSlotBufs, 3) <= kBudget ? 3 : 2);
+    // a vertex table lives from its request (one tile ahead of the stage) until the tile's REDUCE phase has
+    // finished in every consumer, which trails the stage release by up to kSlotBufs tiles
+    static constexpr int kVring = kStages + kSlotBufs + 1;
     static constexpr size_t oSlotBuf = kBarBytes;
-    static constexpr size_t oVring = oSlotBuf + kSlotBytes;
+    static constexpr size_t oVring = oSlotBuf + (size_t)kSlotBufs * kSlotBytes;
     static constexpr size_t oStages = oVring + (size_t)kVring * kVtabBytes;
     static constexpr size_t kSmemBytes = oStages + (size_t)kStages * kStageBytes;
-    // CTAs per SM the shared memory allows (227 KB per SM, 1 KB reserved per CTA): the register budget of
-    // __launch_bounds__ follows it, so that a kernel that is shared-memory-limited to 2 CTAs does not
-    // spill to fit a third one
+    // CTAs per SM the shared memory allows: the register budget of __launch_bounds__ follows it, so that a
+    // kernel that is shared-memory-limited does not spill to fit one more CTA
     static constexpr int kSmemCtas = (int)((size_t)227 * 1024 / (kSmemBytes + 1024));
-    static constexpr int kWantCtas = (sizeof(T) == 4 ? 3 : 1) * (256 / kTileTets);
     static constexpr int kMinCtas = kSmemCtas < 1 ? 1 : (kSmemCtas < kWantCtas ? kSmemCtas : kWantCtas);
 };
 
-template <typename T, int KIND, int OPS, int LAYOUT = APL_LAYOUT_TET>
-__global__ void __launch_bounds__(PipeCfg<T, KIND, OPS, LAYOUT>::kThreads, PipeCfg<T, KIND, OPS, LAYOUT>::kMinCtas)
+// REDUCE phase of one tile: lanes l and l+16 of a warp sum the two halves of a vertex's slot range
+// (tile_reduce_lane), exchange with one shuffle, and issue the REDs from both lanes (field f from the lane of
+// half f & 1).  Groups of 16 vertices (reduce order: about decreasing valence) are dealt to the warps round
+// robin, rotated by `rot` from tile to tile so that no warp always owns the heaviest group.
+template <typename T, int OPS, int NT, int NSLOTS>
+__device__ __forceinline__ void tile_reduce_flush(int tid, int rot, int n_verts, const unsigned char* vperm,
+                                                  const unsigned short* voff, const int* verts, const T* sl,
+                                                  const FemArgs<T>& a) {
+    using Cfg = TileCfg<T, OPS>;
+    constexpr int NOUT = Cfg::NOUT;
+    const int half = (tid >> 4) & 1;
+    const int w = ((tid >> 5) + rot) & (NT / 32 - 1);
+    T* outs[3] = {nullptr, nullptr, nullptr};
+    {
+        int k = 0;
+        if constexpr (Cfg::kGrad) outs[k++] = a.grad;
+        if constexpr (Cfg::kDiag) outs[k++] = a.diag;
+        if constexpr (Cfg::kProd) outs[k++] = a.prod;
+    }
+    for (int t = w * 16 + (tid & 15); t < ((n_verts + 15) & ~15); t += NT / 2) {
+        // (the bound is rounded up to 16 so that whole warps stay together for the shuffle below;
+        //  out-of-range lanes have cnt = 0)
+        int v;
+        T acc[3 * NOUT];
+        tile_reduce_lane<T, OPS, NSLOTS>(half, t, n_verts, vperm, voff, sl, v, acc);
+#pragma unroll
+        for (int j = 0; j < 3 * NOUT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+        if (t < n_verts) {
+            const int gv = verts[v];
+            if constexpr (NOUT == 1) {
+                if (half == 0 && outs[0]) red_row(outs[0], gv, a.ld_out, acc);
+            } else {
+                T* base = half ? outs[1] : outs[0];
+                const T val[3] = {half ? acc[3] : acc[0], half ? acc[4] : acc[1], half ? acc[5] : acc[2]};
+                if (base) red_row(base, gv, a.ld_out, val);
+                if constexpr (NOUT == 3) {
+                    if (half == 0 && outs[2]) red_row(outs[2], gv, a.ld_out, acc + 6);
+                }
+            }
+        }
+    }
+}
+
+template <typename T, int KIND, int OPS>
+__global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KIND, OPS>::kMinCtas)
     fem_pipe_kernel(const FemArgs<T> a) {
     using Cfg = TileCfg<T, OPS>;
-    using PC = PipeCfg<T, KIND, OPS, LAYOUT>;
+    using PC = PipeCfg<T, KIND, OPS>;
     constexpr int NOUT = Cfg::NOUT;
     constexpr int NC = PC::kConsumers;             // consumer threads (warps 0 .. NC/32 - 1), producer = warp NC/32
-    constexpr bool kPair = LAYOUT == APL_LAYOUT_PAIR;
-    constexpr int S = PC::kStages, SV = PC::kVring;
+    constexpr int S = PC::kStages, SV = PC::kVring, NB = PC::kSlotBufs;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // [0,128): mbarriers full[S], empty[S], vfull[SV];  slot buffer;  SV vertex-table slots;  S stages
-    static_assert(8 * (2 * S + SV) <= (int)PC::kBarBytes, "mbarrier area too small");
+    // [0,128): mbarriers full[S], empty[S], vfull[SV], slots_full[NB], slots_free[NB];  NB slot buffers;
+    // SV vertex-table slots;  S stages
+    static_assert(8 * (2 * S + SV + 2 * NB) <= (int)PC::kBarBytes, "mbarrier area too small");
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw);
-    T* sl = reinterpret_cast<T*>(smem_raw + PC::oSlotBuf);
     unsigned char* vring = smem_raw + PC::oVring;
     unsigned char* stages = smem_raw + PC::oStages;
     const unsigned bar0 = smem_u32(bars);
     auto full = [&](int s) { return bar0 + 8u * s; };
     auto empty = [&](int s) { return bar0 + 8u * (S + s); };
     auto vfull = [&](int s) { return bar0 + 8u * (2 * S + s); };
+    auto sfull = [&](int b) { return bar0 + 8u * (2 * S + SV + b); };
+    auto sfree = [&](int b) { return bar0 + 8u * (2 * S + SV + NB + b); };
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -509,6 +557,10 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS, LAYOUT>::kThreads, PipeC
             mbar_init(empty(s), NC);         // every consumer thread releases the stage
         }
         for (int s = 0; s < SV; ++s) mbar_init(vfull(s), 1);
+        for (int b = 0; b < NB; ++b) {
+            mbar_init(sfull(b), NC);
+            mbar_init(sfree(b), NC);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -539,6 +591,9 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS, LAYOUT>::kThreads, PipeC
                 bulk_g2s(vt32 + (unsigned)PC::oVoff, a.tile_voff + h.w, bo, vfull(sv));
             }
         };
+        const T* pf = Cfg::kNeedP ? a.p : a.axpy_p;     // second gathered field (nullptr: none)
+        const bool want_p = Cfg::kNeedP || axpy;
+        const bool aligned8 = (((size_t)a.u | (size_t)(want_p ? pf : a.u)) & 7u) == 0;
         int4 h_cur = load_hdr(0), h_nxt = load_hdr(1);
         if (lane == 0) request_vtab(0, h_cur);
         for (int it = 0; it < my_tiles; ++it) {
@@ -553,8 +608,8 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS, LAYOUT>::kThreads, PipeC
             h.z = __shfl_sync(0xffffffffu, h_cur.z, 0);
             h.w = __shfl_sync(0xffffffffu, h_cur.w, 0);
             const int n_tets = h.y & 0xffff, n_verts = h.y >> 16;
-            // stage s free <=> the consumers are done with tile it - S, which also frees vertex slot
-            // (it + 1) % SV (last used by tile it + 1 - SV = it - S)
+            // stage s free <=> every consumer is past COMPUTE(it - S); its REDUCE phases up to tile
+            // it - S - NB - 1 + 1 are then finished too, which frees vertex slot (it + 1) % SV
             mbar_wait(empty(s), ph ^ 1u);
             if (lane == 0) {
                 *reinterpret_cast<int4*>(st + PC::oHdr) = h;
@@ -576,43 +631,35 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS, LAYOUT>::kThreads, PipeC
             const int* verts = reinterpret_cast<const int*>(vring + (size_t)sv * PC::kVtabBytes + PC::oVerts);
             const unsigned us32 = st32 + (unsigned)PC::oVbuf;
             const unsigned ps32 = us32 + 4u * kTileVerts * (unsigned)sizeof(T);
-#ifdef APL_GATHER_LDG
-            // EXPERIMENT (off by default, `APL_GATHER_LDG=1 python -m apple_b200.build`): 12-byte rows (ld = 3)
-            // through registers -- one 8-byte and one 4-byte load per row instead of three 4-byte cp.async, and
-            // one 16-byte shared-memory store instead of three 4-byte ones (the store is conflict-free: 32
-            // consecutive rows per warp); costs the producer one exposed global-memory latency per tile.
-            if (a.ld_in == 3) {
+            if (APL_GATHER_LDG && a.ld_in == 3) {
+                // 12-byte rows through registers: all loads of the tile are issued before the first store, so
+                // one global-memory latency is exposed per tile (hidden by the stages in flight)
                 constexpr int R = kTileVerts / 32;
-                const T* pf = Cfg::kNeedP ? a.p : a.axpy_p;
-                const bool want_p = Cfg::kNeedP || axpy;
                 T ru[R][3], rp[R][3];
 #pragma unroll
                 for (int k = 0; k < R; ++k) {
                     const int v = lane + 32 * k;
                     if (v < n_verts) {
                         const int gv = verts[v];
-                        load_row3_ldg<T>(a.u, gv, ru[k]);
-                        if (want_p) load_row3_ldg<T>(pf, gv, rp[k]);
+                        load_row3_ldg<T>(a.u, gv, aligned8, ru[k]);
+                        if (want_p) load_row3_ldg<T>(pf, gv, aligned8, rp[k]);
                     }
                 }
+                T* vb = reinterpret_cast<T*>(st + PC::oVbuf);
 #pragma unroll
                 for (int k = 0; k < R; ++k) {
                     const int v = lane + 32 * k;
                     if (v < n_verts) {
-                        T* vb = reinterpret_cast<T*>(st + PC::oVbuf);
                         store_row4<T>(vb + 4 * v, ru[k]);
                         if (want_p) store_row4<T>(vb + 4 * kTileVerts + 4 * v, rp[k]);
                     }
                 }
                 mbar_arrive(full(s));   // release: the stores above are visible to the consumers that acquire the phase
-            } else
-#endif
-            {
+            } else {
                 for (int v = lane; v < n_verts; v += 32) {
                     const int gv = verts[v];
                     gather_row_async<T>(us32 + (unsigned)v * 4u * (unsigned)sizeof(T), a.u, gv, a.ld_in);
-                    if constexpr (Cfg::kNeedP) gather_row_async<T>(ps32 + (unsigned)v * 4u * (unsigned)sizeof(T), a.p, gv, a.ld_in);
-                    else if (axpy) gather_row_async<T>(ps32 + (unsigned)v * 4u * (unsigned)sizeof(T), a.axpy_p, gv, a.ld_in);
+                    if (want_p) gather_row_async<T>(ps32 + (unsigned)v * 4u * (unsigned)sizeof(T), pf, gv, a.ld_in);
                 }
                 cp_async_arrive_noinc(full(s));
             }
@@ -621,36 +668,21 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS, LAYOUT>::kThreads, PipeC
         }
     } else {
         // ================================= consumer warps ================================
-        for (int it = 0; it < my_tiles; ++it) {
+        // COMPUTE(it): returns the tile's vertex count (the header lives in the stage, which is released here)
+        auto compute = [&](int it) -> int {
             const int s = it % S;
-            const unsigned ph = (unsigned)(it / S) & 1u;
             unsigned char* st = stages + (size_t)s * PC::kStageBytes;
-            const unsigned char* vt = vring + (size_t)(it % SV) * PC::kVtabBytes;
-            mbar_wait(full(s), ph);
+            mbar_wait(full(s), (unsigned)(it / S) & 1u);
             const int4 h = *reinterpret_cast<const int4*>(st + PC::oHdr);
-            const int n_tets = h.y & 0xffff, n_verts = h.y >> 16;
-            T* vbuf = reinterpret_cast<T*>(st + PC::oVbuf);
-            const T* us = vbuf;
-            const T* ps = vbuf + 4 * kTileVerts;
-#ifdef APL_PROFILE_KNOBS
-            if (g_knobs & 32) { mbar_arrive(empty(s)); continue; }
-#endif
-            if constexpr (kPair) {
-                const int n_items = n_tets >> 1;   // item i: packed tets i and n_items + i of the tile
-                if (tid < n_items) {
-                    Rec<T, PC::NREC> ra, rb;
-#pragma unroll
-                    for (int k = 0; k < PC::NPL; ++k) {
-                        const uint4* pl = reinterpret_cast<const uint4*>(st + PC::oPlanes + (size_t)k * kTileTets * 16);
-                        ra.q[k] = pl[tid];
-                        rb.q[k] = pl[n_items + tid];
-                    }
-                    const uint2 c8 = reinterpret_cast<const uint2*>(st + PC::oConn)[tid];
-                    uint4 s8 = make_uint4(0u, 0u, 0u, 0u);
-                    if constexpr (NOUT > 0) s8 = reinterpret_cast<const uint4*>(st + PC::oSlots)[tid];
-                    tile_compute_pair<T, KIND, OPS>(ra.s, rb.s, c8, s8, us, ps, axpy, alpha, sl, e_acc, q_acc);
-                }
-            } else if (tid < n_tets) {
+            const int n_tets = h.y & 0xffff;
+            const T* us = reinterpret_cast<const T*>(st + PC::oVbuf);
+            const T* ps = us + 4 * kTileVerts;
+            T* sl = reinterpret_cast<T*>(smem_raw + PC::oSlotBuf + (size_t)(it % NB) * PC::kSlotBytes);
+            if constexpr (NOUT > 0) {
+                // slot buffer it % NB is free once every consumer has finished REDUCE(it - NB)
+                if (it >= NB) mbar_wait(sfree(it % NB), (unsigned)(it / NB - 1) & 1u);
+            }
+            if (tid < n_tets) {
                 Rec<T, PC::NREC> rec;
 #pragma unroll
                 for (int k = 0; k < PC::NPL; ++k)
@@ -660,26 +692,35 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS, LAYOUT>::kThreads, PipeC
                 if constexpr (NOUT > 0) s4 = reinterpret_cast<const ushort4*>(st + PC::oSlots)[tid];
                 tile_compute<T, KIND, OPS>(rec.s, lc, s4, us, ps, axpy, alpha, sl, e_acc, q_acc);
             }
-            if constexpr (NOUT > 0) {
-#ifdef APL_PROFILE_KNOBS
-                if (!(g_knobs & 16))
-#endif
-                consumer_sync_n<NC>();
-                tile_reduce<T, OPS, NC, PC::kNSlots>(tid, n_verts, vt + PC::oVperm,
-                                                     reinterpret_cast<const unsigned short*>(vt + PC::oVoff), sl, vbuf);
-#ifdef APL_PROFILE_KNOBS
-                if (!(g_knobs & 16))
-#endif
-                consumer_sync_n<NC>();
-                if constexpr (kPair) {   // fewer consumer threads than a tile may have vertices
-                    for (int v = tid; v < n_verts; v += NC)
-                        tile_flush<T, OPS>(v, n_verts, reinterpret_cast<const int*>(vt + PC::oVerts)[v], vbuf, a);
-                } else {
-                    const int gv = tid < n_verts ? reinterpret_cast<const int*>(vt + PC::oVerts)[tid] : 0;
-                    tile_flush<T, OPS>(tid, n_verts, gv, vbuf, a);
+            if constexpr (NOUT > 0) mbar_arrive(sfull(it % NB));
+            mbar_arrive(empty(s));
+            return h.y >> 16;
+        };
+        if constexpr (NOUT == 0) {
+            for (int it = 0; it < my_tiles; ++it) compute(it);
+        } else {
+            auto reduce = [&](int it, int n_verts) {
+                const unsigned char* vt = vring + (size_t)(it % SV) * PC::kVtabBytes;
+                const T* sl = reinterpret_cast<const T*>(smem_raw + PC::oSlotBuf + (size_t)(it % NB) * PC::kSlotBytes);
+                mbar_wait(sfull(it % NB), (unsigned)(it / NB) & 1u);
+                tile_reduce_flush<T, OPS, NC, PC::kNSlots>(tid, it, n_verts, vt + PC::oVperm,
+                                                           reinterpret_cast<const unsigned short*>(vt + PC::oVoff),
+                                                           reinterpret_cast<const int*>(vt + PC::oVerts), sl, a);
+                mbar_arrive(sfree(it % NB));
+            };
+            if constexpr (NB == 2) {
+                int nv_cur = my_tiles > 0 ? compute(0) : 0;
+                for (int it = 0; it < my_tiles; ++it) {
+                    const int nv_next = it + 1 < my_tiles ? compute(it + 1) : 0;
+                    reduce(it, nv_cur);
+                    nv_cur = nv_next;
+                }
+            } else {
+                for (int it = 0; it < my_tiles; ++it) {
+                    const int nv = compute(it);
+                    reduce(it, nv);
                 }
             }
-            mbar_arrive(empty(s));
         }
     }
     if constexpr (Cfg::kFun || Cfg::kQuad)
@@ -754,77 +795,57 @@ __global__ void __launch_bounds__(kTileTets) fem_atomic_kernel(const FemArgs<T> 
 template <typename T, int KIND>
 int launch_fem(const apl_fem* fem, int ops, const FemArgs<T>& args, int scatter, cudaStream_t stream);
 
+// Grid of a persistent kernel: resident CTAs per SM x SMs.  The opt-in to more than 48 KB of dynamic shared
+// memory and the occupancy are per DEVICE (a process may hold handles on several GPUs), so they are cached per
+// (instantiation, device) under a mutex.
+constexpr int kMaxDevices = 64;
+template <typename K>
+int resident_blocks(K kern, int device, int threads, size_t smem, int* cache, std::mutex& mu, int& out) {
+    if (device < 0 || device >= kMaxDevices) {
+        set_error("device index outside the range the launch cache supports");
+        return APL_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache[device] == 0) {
+        if (smem > 0)
+            APL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int b = 0;
+        APL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, threads, smem));
+        cache[device] = b > 0 ? b : 1;
+    }
+    out = cache[device];
+    return APL_OK;
+}
+
 template <typename T, int KIND, int OPS>
 int launch_one(const apl_fem* fem, const FemArgs<T>& args, int scatter, cudaStream_t stream) {
     using Cfg = TileCfg<T, OPS>;
     if (args.n_tiles == 0) return APL_OK;
-#ifdef APL_PROFILE_KNOBS
-    {
-        const char* e = getenv("APL_KNOBS");
-        const int k = e ? atoi(e) : 0;
-        cudaMemcpyToSymbolAsync(g_knobs, &k, sizeof(int), 0, cudaMemcpyHostToDevice, stream);
-    }
-#endif
-    if (fem->host.layout == APL_LAYOUT_PAIR) {
-        if (scatter != APL_SCATTER_TILE) {
-            set_error("apl_fem_eval: handles in the PAIR layout only implement APL_SCATTER_TILE");
-            return APL_ERR_STATE;
-        }
-        using PC = PipeCfg<T, KIND, OPS, APL_LAYOUT_PAIR>;
-        static int blocks_per_sm = -1;
-        auto kern = fem_pipe_kernel<T, KIND, OPS, APL_LAYOUT_PAIR>;
-        if (blocks_per_sm < 0) {
-            APL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)PC::kSmemBytes));
-            int b = 0;
-            APL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, PC::kThreads, PC::kSmemBytes));
-            blocks_per_sm = b > 0 ? b : 1;
-        }
-        int grid = fem->num_sms * blocks_per_sm;
+    static std::mutex mu;
+    static int cache[3][kMaxDevices] = {};
+    int blocks_per_sm = 1;
+    auto grid_of = [&](int per_sm) {
+        int grid = fem->num_sms * per_sm;
         if (grid > args.n_tiles) grid = args.n_tiles;
         if (grid > fem->max_grid) grid = fem->max_grid;
-        kern<<<grid, PC::kThreads, PC::kSmemBytes, stream>>>(args);
-    } else if (scatter == APL_SCATTER_TILE) {
+        return grid;
+    };
+    if (scatter == APL_SCATTER_TILE) {
         using PC = PipeCfg<T, KIND, OPS>;
-        static int blocks_per_sm = -1;
         auto kern = fem_pipe_kernel<T, KIND, OPS>;
-        if (blocks_per_sm < 0) {
-            APL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)PC::kSmemBytes));
-            int b = 0;
-            APL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kPipeThreads, PC::kSmemBytes));
-            blocks_per_sm = b > 0 ? b : 1;
-        }
-        int grid = fem->num_sms * blocks_per_sm;
-        if (grid > args.n_tiles) grid = args.n_tiles;
-        if (grid > fem->max_grid) grid = fem->max_grid;
-        kern<<<grid, kPipeThreads, PC::kSmemBytes, stream>>>(args);
+        int rc = resident_blocks(kern, fem->device, PC::kThreads, PC::kSmemBytes, cache[0], mu, blocks_per_sm);
+        if (rc != APL_OK) return rc;
+        kern<<<grid_of(blocks_per_sm), PC::kThreads, PC::kSmemBytes, stream>>>(args);
     } else if (scatter == APL_SCATTER_TILE_SIMPLE) {
-        static int blocks_per_sm = -1;
         auto kern = fem_tile_kernel<T, KIND, OPS>;
-        if (blocks_per_sm < 0) {
-            APL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)Cfg::kSmemBytes));
-            int b = 0;
-            APL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kTileTets, Cfg::kSmemBytes));
-            blocks_per_sm = b > 0 ? b : 1;
-        }
-        int grid = fem->num_sms * blocks_per_sm;
-        if (grid > args.n_tiles) grid = args.n_tiles;
-        if (grid > fem->max_grid) grid = fem->max_grid;
-        kern<<<grid, kTileTets, Cfg::kSmemBytes, stream>>>(args);
+        int rc = resident_blocks(kern, fem->device, kTileTets, Cfg::kSmemBytes, cache[1], mu, blocks_per_sm);
+        if (rc != APL_OK) return rc;
+        kern<<<grid_of(blocks_per_sm), kTileTets, Cfg::kSmemBytes, stream>>>(args);
     } else {
-        static int blocks_per_sm = -1;
         auto kern = fem_atomic_kernel<T, KIND, OPS>;
-        if (blocks_per_sm < 0) {
-            int b = 0;
-            APL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kTileTets, 0));
-            blocks_per_sm = b > 0 ? b : 1;
-        }
-        int grid = fem->num_sms * blocks_per_sm;
-        if (grid > args.n_tiles) grid = args.n_tiles;
-        if (grid > fem->max_grid) grid = fem->max_grid;
-        kern<<<grid, kTileTets, 0, stream>>>(args);
+        int rc = resident_blocks(kern, fem->device, kTileTets, 0, cache[2], mu, blocks_per_sm);
+        if (rc != APL_OK) return rc;
+        kern<<<grid_of(blocks_per_sm), kTileTets, 0, stream>>>(args);
     }
     APL_CUDA_CHECK(cudaGetLastError());
     return APL_OK;

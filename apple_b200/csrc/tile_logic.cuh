@@ -1,6 +1,6 @@
 // Per-tile CONSUMER logic of the element kernels -- everything between "the stage is in shared memory" and "the
 // per-vertex sums are ready for the global RED": record / connectivity decoding, the corner gather, the slot
-// stores (TET and PAIR layout), the per-lane part of the slot reduction and the parked sums.  No CUDA-only
+// stores, the per-lane part of the slot reduction and the parked sums.  No CUDA-only
 // construct is used here (the shuffle, the barriers and the REDs stay in fem_kernels.cuh), so that the very
 // same code is compiled for the HOST by tests/native/tile_host.cpp and replayed thread by thread on the packed
 // tables against the oracle (the product only ever runs it on the GPU).
@@ -59,7 +59,7 @@ struct TileCfg {
     static constexpr int SS = (NOUT == 0) ? 0
                               : (NOUT == 1) ? 4
                               : (sizeof(T) == 4) ? (NOUT == 2 ? 6 : 10) : (NOUT == 2 ? 6 : 10);
-    static constexpr int kNSlots = 4 * kTileTets + kTileVerts;
+    static constexpr int kNSlots = kSlotsAlloc;
     // per-vertex buffer: u (4 scalars) and p (4 scalars) during compute, then reused for the 3*NOUT
     // reduced sums of each vertex between the reduce and the flush phase
     static constexpr int VB = (3 * NOUT > 8) ? 12 : 8;
@@ -72,14 +72,9 @@ struct TileCfg {
     static constexpr size_t kSmemBytes = kVbufBytes + kSlotBytes + kVoffBytes + kVpermBytes;
 };
 
-// real slots of a tile (4 per tet) plus one padding slot per vertex with an even valence
-constexpr int kSlotsAlloc = 4 * kTileTets + kTileVerts;
-
 // The slot buffer is split into 16-byte planes: vector q of slot s lives at sl + (q * kNSlots + s) * 16 B.
 // One thread reading consecutive slots of "its" vertex and a warp of such threads then touch
 // neighbouring 16-byte words (see tile_reduce), instead of words a whole slot stride apart.
-// slot capacity of the PAIR layout: 5 slots per 2 tets plus one pad per vertex
-constexpr int kSlotsAllocPair = 5 * (kTileTets / 2) + kTileVerts;
 
 template <typename T, int SS, int NSLOTS = kSlotsAlloc>
 APL_TL void store_slot_planes(T* sl, int s, const T* v) {
@@ -196,9 +191,6 @@ APL_TL void tile_compute(const T* rec, uchar4 lc, ushort4 s4, const T* us, const
             if constexpr (Cfg::kProd) { v[k] = hp[c][0]; v[k + 1] = hp[c][1]; v[k + 2] = hp[c][2]; k += 3; }
 #pragma unroll
             for (int j = 3 * NOUT; j < SS; ++j) v[j] = (T)0;
-#ifdef APL_PROFILE_KNOBS
-            if (g_knobs & 8) continue;
-#endif
             store_slot_planes<T, SS>(sl, sidx[c], v);
         }
     }
@@ -249,85 +241,6 @@ APL_TL void tile_flush_read(const T* vbuf, int v, T* acc) {
     constexpr int NOUT = TileCfg<T, OPS>::NOUT;
 #pragma unroll
     for (int j = 0; j < 3 * NOUT; ++j) acc[j] = vbuf[v * (3 * NOUT) + j];
-}
-
-// PAIR layout: one consumer thread evaluates two tets that share a face.  conn5 / slots5: the shared face
-// (s0, s1, s2), the apex of the first and the apex of the second tet; both records are packed in the corner order
-// (s0, s1, s2, apex), so the contributions of the three shared corners are added in registers and the pair
-// gathers 5 vertices and writes 5 slots instead of 8.
-template <typename T, int KIND, int OPS>
-APL_TL void tile_compute_pair(const T* recA, const T* recB, uint2 c8, uint4 s8, const T* us,
-                                                  const T* ps, bool axpy, T alpha, T* sl, double& e_acc, double& q_acc) {
-    using Cfg = TileCfg<T, OPS>;
-    constexpr int NOUT = Cfg::NOUT, SS = Cfg::SS;
-    const int l[5] = {(int)(c8.x & 0xffu), (int)((c8.x >> 8) & 0xffu), (int)((c8.x >> 16) & 0xffu), (int)(c8.x >> 24),
-                      (int)(c8.y & 0xffu)};
-    T U[5][3], P[5][3];
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        T tmp[4];
-        load_slot<T, 4>(us + 4 * l[c], tmp);
-        U[c][0] = tmp[0]; U[c][1] = tmp[1]; U[c][2] = tmp[2];
-        if constexpr (Cfg::kNeedP) {
-            load_slot<T, 4>(ps + 4 * l[c], tmp);
-            P[c][0] = tmp[0]; P[c][1] = tmp[1]; P[c][2] = tmp[2];
-        } else {
-            if (axpy) {  // line-search trial point x + alpha p
-                load_slot<T, 4>(ps + 4 * l[c], tmp);
-                U[c][0] += alpha * tmp[0]; U[c][1] += alpha * tmp[1]; U[c][2] += alpha * tmp[2];
-            }
-        }
-    }
-    const int sidx[5] = {(int)(s8.x & 0xffffu), (int)(s8.x >> 16), (int)(s8.y & 0xffffu), (int)(s8.y >> 16),
-                         (int)(s8.z & 0xffffu)};
-    // packs corner c of one evaluation into a slot value
-    auto pack = [&](const T (*g)[3], const T (*dg)[3], const T (*hp)[3], int c, T* v) {
-        int k = 0;
-        if constexpr (Cfg::kGrad) { v[k] = g[c][0]; v[k + 1] = g[c][1]; v[k + 2] = g[c][2]; k += 3; }
-        if constexpr (Cfg::kDiag) { v[k] = dg[c][0]; v[k + 1] = dg[c][1]; v[k + 2] = dg[c][2]; k += 3; }
-        if constexpr (Cfg::kProd) { v[k] = hp[c][0]; v[k + 1] = hp[c][1]; v[k + 2] = hp[c][2]; k += 3; }
-#pragma unroll
-        for (int j = 3 * NOUT; j < SS; ++j) v[j] = (T)0;
-    };
-    T shared_v[3][SS > 0 ? SS : 1];
-    {   // first tet: corners (s0, s1, s2, apex A)
-        T psi = 0, quad = 0;
-        T g[4][3], dg[4][3], hp[4][3];
-        elem_eval<T, KIND, OPS>(recA, U, P, psi, quad, g, dg, hp);   // rows 0..3 of U / P
-        if constexpr (Cfg::kFun) e_acc += (double)psi;
-        if constexpr (Cfg::kQuad) q_acc += (double)quad;
-        if constexpr (NOUT > 0) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) pack(g, dg, hp, c, shared_v[c]);
-            T v[SS];
-            pack(g, dg, hp, 3, v);
-            store_slot_planes<T, SS, kSlotsAllocPair>(sl, sidx[3], v);
-        }
-    }
-    {   // second tet: corners (s0, s1, s2, apex B)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            U[3][i] = U[4][i];
-            if constexpr (Cfg::kNeedP) P[3][i] = P[4][i];
-        }
-        T psi = 0, quad = 0;
-        T g[4][3], dg[4][3], hp[4][3];
-        elem_eval<T, KIND, OPS>(recB, U, P, psi, quad, g, dg, hp);
-        if constexpr (Cfg::kFun) e_acc += (double)psi;
-        if constexpr (Cfg::kQuad) q_acc += (double)quad;
-        if constexpr (NOUT > 0) {
-            T v[SS];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                pack(g, dg, hp, c, v);
-#pragma unroll
-                for (int j = 0; j < 3 * NOUT; ++j) v[j] += shared_v[c][j];
-                store_slot_planes<T, SS, kSlotsAllocPair>(sl, sidx[c], v);
-            }
-            pack(g, dg, hp, 3, v);
-            store_slot_planes<T, SS, kSlotsAllocPair>(sl, sidx[4], v);
-        }
-    }
 }
 
 }  // namespace apl

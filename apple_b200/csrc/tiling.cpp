@@ -98,7 +98,7 @@ struct Lcg {
 
 constexpr int kGroupsQ = (kTileTets / 8) * 4;    // (quarter warp, corner) groups of a tile
 constexpr int kGroupsH = (kTileTets / 16) * 4;   // (half warp, corner) groups
-constexpr int kSlotCap = 4 * kTileTets + kTileVerts;
+constexpr int kSlotCap = kSlotsAlloc;
 static_assert(kSlotCap < 4096, "tile_voff keeps the slot offset in 12 bits");
 
 // Occupancy of the bank groups by one warp-wide access: c[r] lanes (distinct addresses) fall into bank
@@ -148,8 +148,7 @@ struct TileScratch {
 };
 
 // ---- 1. local vertex ids: balanced colouring of the gather-conflict graph -----------------------
-// tl[t * nc + a]: provisional local id (first-touch order) of corner a of the tile's t-th item (a tet with
-// nc = 4 corners, or a face-adjacent tet pair with nc = 5: the shared face and the two apexes).  Vertices
+// tl[t * nc + a]: provisional local id (first-touch order) of corner a of the tile's t-th tet (nc = 4).  Vertices
 // read by the same quarter warp for the same corner should differ in (id mod M).  new_id[provisional] is a
 // bijection onto [0, nv) with id = 32 w + M k + colour: w = the vertex's window of 32 in ascending global id,
 // k ascending with the global id inside a (window, colour) class.
@@ -445,8 +444,7 @@ void place_slots(TileScratch& ws, int nt, int nc, const uint8_t* tl, const int* 
 }
 
 // ---- a closed tile: local ids, reduce order, slots -> tables ------------------------------------------
-// One ITEM per consumer thread: a tet (nc = 4 corners, conn / slots rows of 4 entries) or a face-adjacent
-// tet pair (nc = 5: shared face + two apexes, rows of 8 entries).
+// One tet per consumer thread (nc = 4 corners, conn / slots rows of 4 entries).
 struct TileRange {
     int64_t item_start;    // first item (tet, or pair slot) of the tile
     int32_t ni, nv;        // items, distinct vertices
@@ -477,14 +475,17 @@ void finish_tile(TileScratch& ws, HostTables& out, int64_t tile, const TileRange
     std::stable_sort(perm, perm + nv, [&](int a, int b) { return cnt[a] > cnt[b]; });
     int start[kTileVerts + 1], padv[kTileVerts], off[kTileVerts];
     start[0] = 0;
-    // slot capacity of the kernels: every corner of a full tile plus one pad per vertex (fem_kernels.cuh:
-    // kSlotsAlloc / kSlotsAllocPair)
-    const int slot_cap = (nc == 5 ? 5 * (kTileTets / 2) : 4 * kTileTets) + kTileVerts;
-    int pads_left = slot_cap - nc * ni;   // >= nv: one pad per vertex is always affordable
+    // slot capacity of the kernels: every corner of a full tile plus kSlotPads pad slots (common.h: kSlotsAlloc)
+    const int slot_cap = kSlotsAlloc;
+    const int pads_total = slot_cap - nc * ni;   // >= kSlotPads
+    int pads_left = pads_total;
     for (int g0 = 0; g0 < nv; g0 += 16) {
         GroupSearch gs;
         gs.n = std::min(16, nv - g0);
-        const int allowed = pads_left - (nv - g0 - gs.n);   // keep one pad for every later vertex
+        // the pad budget is shared about in proportion: every later vertex keeps 70 % of its share of the tile's
+        // pads (the first groups have the longest ranges and gain most from conflict-free starts)
+        const int reserve = (int)((int64_t)(nv - g0 - gs.n) * pads_total * 7 / (10 * std::max(nv, 1)));
+        const int allowed = std::max(0, pads_left - reserve);
         int grp[16];
         for (int i = 0; i < gs.n; ++i) {
             grp[i] = perm[g0 + i];
@@ -505,7 +506,11 @@ void finish_tile(TileScratch& ws, HostTables& out, int64_t tile, const TileRange
                 padv[g0 + j] = gs.pad[j];
             }
         } else {
-            for (int j = 0; j < gs.n; ++j) padv[g0 + j] = (cnt[grp[j]] & 1) ? 0 : 1;   // odd strides
+            int left = allowed;
+            for (int j = 0; j < gs.n; ++j) {   // odd strides while the budget lasts
+                padv[g0 + j] = ((cnt[grp[j]] & 1) || left == 0) ? 0 : 1;
+                left -= padv[g0 + j];
+            }
         }
         for (int j = 0; j < gs.n; ++j) {
             start[g0 + j + 1] = start[g0 + j] + cnt[perm[g0 + j]] + padv[g0 + j];
@@ -650,8 +655,6 @@ void parallel_for_chunks(int64_t n, F&& body) {
 }
 }  // namespace
 
-static int build_tiles_pair(const int32_t* cells, bool f64, HostTables& out);
-
 // out.order must hold the packed order (packed position -> caller's cell).  `cells` is either the caller's
 // array (cells_packed = false: the tet at packed position pos is cells[order[pos]]) or already permuted into
 // packed order (cells_packed = true: the device-side setup sorts the connectivity on the GPU).
@@ -660,8 +663,6 @@ static int build_tiles_ordered(int64_t n_cells, int64_t n_points, const int32_t*
     auto cell_at = [&](int64_t pos) { return cells + 4 * (cells_packed ? pos : out.order[(size_t)pos]); };
     out.conn.resize((size_t)n_cells * 4);
     out.slots.resize((size_t)n_cells * 4);
-    out.cperm.assign((size_t)n_cells, (uint8_t)0xE4);   // identity corner order
-    out.clone.assign((size_t)n_cells, (uint8_t)0);
 
     // ---- pass 1 (parallel over chunks): tile boundaries and the distinct vertices of every tile in first-touch
     //      order; then (serial, per tile) where each tile's tables start (vertex lists at multiples of 16 entries,
@@ -728,17 +729,13 @@ static int build_tiles_ordered(int64_t n_cells, int64_t n_points, const int32_t*
 }
 
 int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const double* points, int elem_bytes,
-                int layout, HostTables& out) {
+                HostTables& out) {
     if (n_cells < 0 || n_points <= 0 || (!cells && n_cells > 0)) {
         set_error("build_tiles: bad sizes");
         return APL_ERR_INVALID;
     }
     if (n_cells > (int64_t)INT32_MAX / 2) {
         set_error("n_cells exceeds the int32 range of the packed tables");
-        return APL_ERR_INVALID;
-    }
-    if (layout != APL_LAYOUT_TET && layout != APL_LAYOUT_PAIR) {
-        set_error("build_tiles: unknown layout");
         return APL_ERR_INVALID;
     }
     for (int64_t i = 0; i < 4 * n_cells; ++i)
@@ -749,14 +746,12 @@ int build_tiles(int64_t n_cells, int64_t n_points, const int32_t* cells, const d
         }
     const bool f64 = elem_bytes == 8;
     out = HostTables();
-    out.layout = layout;
     out.n_cells = n_cells;
     out.n_points = n_points;
-    // Morton order of the cells (out.order holds it until the layout-specific pass rewrites it)
+    // Morton order of the cells
     out.order.resize((size_t)n_cells);
     if (points) morton_order(n_cells, n_points, cells, points, out.order);
     else std::iota(out.order.begin(), out.order.end(), (int64_t)0);
-    if (layout == APL_LAYOUT_PAIR) return build_tiles_pair(cells, f64, out);
     return build_tiles_ordered(n_cells, n_points, cells, false, f64, out);
 }
 
@@ -773,223 +768,10 @@ int build_tiles_packed(int64_t n_cells, int64_t n_points, const int32_t* packed_
         return APL_ERR_INVALID;
     }
     out = HostTables();
-    out.layout = APL_LAYOUT_TET;
     out.n_cells = n_cells;
     out.n_points = n_points;
     out.order = std::move(order);
     return build_tiles_ordered(n_cells, n_points, packed_cells, true, elem_bytes == 8, out);
-}
-
-// ---- PAIR layout ---------------------------------------------------------------------------------------
-// One item = two tets that share a face (one consumer thread evaluates both: 5 instead of 8 corner gathers /
-// slots).  The pairs are matched online while the Morton-ordered tets stream into the open tile (a tet joins a
-// waiting tet of the tile it shares a face with, else it waits itself); a tet that stays alone is paired with a
-// ZERO-VOLUME CLONE of itself, so the kernels need no special case.  Both tets of an item are relabelled to
-// (s0, s1, s2, apex) with the shared face first -- any corner order is valid as long as the rows of dhdX are
-// permuted with it (out.cperm, applied by the plane packer).  Packed tet positions inside a tile of ni items that
-// starts at tet position ts: item i owns ts + i (first tet) and ts + ni + i (second tet).
-static int build_tiles_pair(const int32_t* cells, bool f64, HostTables& out) {
-    constexpr int kItems = kTileTets / 2;
-    const int64_t n_cells = out.n_cells;
-    const std::vector<int64_t> morton = out.order;
-    struct Item { int64_t a, b; };   // cell ids; b < 0: a alone (clone), a < 0: filler item
-    std::vector<Item> items;
-    items.reserve((size_t)(n_cells * 6 / 10 + 16));
-    std::vector<TileRange> ranges;
-    std::vector<int32_t> touched;
-    touched.reserve((size_t)(n_cells / 2 + 16));
-    {
-        std::vector<int32_t> stamp((size_t)out.n_points, -1), lid((size_t)out.n_points, 0);
-        std::unordered_map<uint32_t, int32_t> waiting;   // sorted provisional ids of a face -> waiting item
-        int64_t item_start = 0, first = 0, vert_end = 0, voff_end = 0;
-        int32_t tile_id = 0;
-        auto face_key = [&](const int32_t* c, int skip) {
-            int l[3], n = 0;
-            for (int a = 0; a < 4; ++a)
-                if (a != skip) l[n++] = lid[(size_t)c[a]];
-            if (l[0] > l[1]) std::swap(l[0], l[1]);
-            if (l[1] > l[2]) std::swap(l[1], l[2]);
-            if (l[0] > l[1]) std::swap(l[0], l[1]);
-            return (uint32_t)(l[0] | (l[1] << 8) | (l[2] << 16));
-        };
-        // Tets left alone by the online matching: a single s whose neighbour t is paired with t', where t' has another
-        // single neighbour s', is re-paired as (s, t), (t', s') -- one item (and one zero-volume clone) fewer.
-        std::unordered_map<uint32_t, std::pair<int32_t, int32_t>> face_tets;   // face -> the (up to two) tets of the tile
-        auto rematch = [&]() {
-            const int64_t n_it = (int64_t)items.size() - item_start;
-            auto tet_of = [&](int32_t code) { const Item& it = items[(size_t)(item_start + (code >> 1))]; return (code & 1) ? it.b : it.a; };
-            face_tets.clear();
-            for (int64_t i = 0; i < n_it; ++i)
-                for (int w = 0; w < 2; ++w) {
-                    const int64_t cell = w ? items[(size_t)(item_start + i)].b : items[(size_t)(item_start + i)].a;
-                    if (cell < 0) continue;
-                    for (int skip = 0; skip < 4; ++skip) {
-                        auto r = face_tets.emplace(face_key(cells + 4 * cell, skip), std::make_pair((int32_t)(2 * i + w), (int32_t)-1));
-                        if (!r.second && r.first->second.second < 0) r.first->second.second = (int32_t)(2 * i + w);
-                    }
-                }
-            auto neighbour = [&](int32_t code, int skip) {   // the other tet of the tile across face `skip`, or -1
-                auto it = face_tets.find(face_key(cells + 4 * tet_of(code), skip));
-                if (it == face_tets.end()) return (int32_t)-1;
-                return it->second.first == code ? it->second.second : it->second.first;
-            };
-            for (int64_t i = 0; i < n_it; ++i) {
-                Item& si = items[(size_t)(item_start + i)];
-                if (si.a < 0 || si.b >= 0) continue;                       // not a single
-                bool done = false;
-                for (int f1 = 0; f1 < 4 && !done; ++f1) {
-                    const int32_t t = neighbour((int32_t)(2 * i), f1);
-                    if (t < 0 || (t >> 1) == i) continue;
-                    Item& ti = items[(size_t)(item_start + (t >> 1))];
-                    if (ti.a < 0 || ti.b < 0) continue;                    // the neighbour is not paired
-                    const int32_t tp = t ^ 1;                              // its partner t'
-                    for (int f2 = 0; f2 < 4 && !done; ++f2) {
-                        const int32_t s2 = neighbour(tp, f2);
-                        if (s2 < 0 || (s2 >> 1) == i || (s2 >> 1) == (t >> 1)) continue;
-                        Item& s2i = items[(size_t)(item_start + (s2 >> 1))];
-                        if (s2i.a < 0 || s2i.b >= 0) continue;             // s' must be a single too
-                        const int64_t ct = tet_of(t), ctp = tet_of(tp), cs = si.a, cs2 = s2i.a;
-                        si = {cs, ct};                                     // (s, t)
-                        ti = {ctp, cs2};                                   // (t', s')
-                        s2i = {-2, -2};                                    // removed (compacted below)
-                        done = true;
-                    }
-                }
-                if (done) {   // the codes stored in face_tets are stale now: rebuild and restart the scan
-                    std::vector<Item> kept;
-                    for (int64_t k = 0; k < n_it; ++k)
-                        if (items[(size_t)(item_start + k)].a != -2) kept.push_back(items[(size_t)(item_start + k)]);
-                    items.resize((size_t)item_start);
-                    items.insert(items.end(), kept.begin(), kept.end());
-                    return true;
-                }
-            }
-            return false;
-        };
-        auto close_tile = [&]() {
-            if ((int64_t)items.size() == item_start) return;
-            for (int guard = 0; guard < kItems && rematch(); ++guard) {}
-            if (((int64_t)items.size() - item_start) % 2) items.push_back({-1, -1});   // tiles hold an even number of items
-            const int ni = (int)((int64_t)items.size() - item_start);
-            const int nv = (int)((int64_t)touched.size() - first);
-            vert_end = (vert_end + 15) / 16 * 16;
-            voff_end = (voff_end + 7) / 8 * 8;
-            ranges.push_back({item_start, ni, nv, first, vert_end, voff_end});
-            vert_end += nv;
-            voff_end += nv + 1;
-            first = (int64_t)touched.size();
-            item_start = (int64_t)items.size();
-            waiting.clear();
-            ++tile_id;
-        };
-        for (int64_t pos = 0; pos < n_cells; ++pos) {
-            const int64_t cell = morton[(size_t)pos];
-            const int32_t* c = cells + 4 * cell;
-            for (int attempt = 0; attempt < 2; ++attempt) {
-                int n_new = 0;
-                for (int a = 0; a < 4; ++a) n_new += stamp[(size_t)c[a]] != tile_id;
-                const int nv_open = (int)((int64_t)touched.size() - first);
-                // a partner waiting in the open tile (only possible if all three face vertices are already in it)
-                int partner = -1;
-                if (n_new <= 1)
-                    for (int skip = 0; skip < 4 && partner < 0; ++skip) {
-                        bool in_tile = true;
-                        for (int a = 0; a < 4; ++a) in_tile &= (a == skip) || stamp[(size_t)c[a]] == tile_id;
-                        if (!in_tile) continue;
-                        auto it = waiting.find(face_key(c, skip));
-                        if (it != waiting.end() && items[(size_t)it->second].b < 0) partner = it->second;
-                    }
-                const bool full = partner < 0 && (int64_t)items.size() - item_start == kItems;
-                if (attempt == 0 && (nv_open + n_new > kTileVerts || full)) {
-                    close_tile();
-                    continue;   // retry in the fresh tile
-                }
-                for (int a = 0; a < 4; ++a)
-                    if (stamp[(size_t)c[a]] != tile_id) {
-                        stamp[(size_t)c[a]] = tile_id;
-                        lid[(size_t)c[a]] = (int32_t)((int64_t)touched.size() - first);
-                        touched.push_back(c[a]);
-                    }
-                if (partner >= 0) {
-                    items[(size_t)partner].b = cell;
-                } else {
-                    items.push_back({cell, -1});
-                    for (int skip = 0; skip < 4; ++skip) waiting.emplace(face_key(c, skip), (int32_t)items.size() - 1);
-                }
-                break;
-            }
-        }
-        close_tile();
-        if (vert_end + 16 > (int64_t)INT32_MAX || voff_end + 16 > (int64_t)INT32_MAX ||
-            (int64_t)items.size() > (int64_t)INT32_MAX / 2) {
-            set_error("tile tables exceed int32 range");
-            return APL_ERR_INVALID;
-        }
-        out.tile_verts.assign((size_t)vert_end + 16, 0);
-        out.tile_vperm.assign((size_t)vert_end + 16, 0);
-        out.tile_voff.assign((size_t)voff_end + 16, 0);
-    }
-    const int64_t n_items = (int64_t)items.size(), n_tiles = (int64_t)ranges.size();
-    out.tiles.assign((size_t)n_tiles * 6, 0);
-    out.order.assign((size_t)n_items * 2, 0);
-    out.cperm.assign((size_t)n_items * 2, (uint8_t)0xE4);
-    out.clone.assign((size_t)n_items * 2, (uint8_t)0);
-    out.conn.assign((size_t)n_items * 8, 0);
-    out.slots.assign((size_t)n_items * 8, 0);
-
-    for_tiles_parallel(n_tiles, [&](TileScratch& ws, int64_t tile) {
-        const TileRange& r = ranges[(size_t)tile];
-        const int32_t* verts = touched.data() + r.first_touch;
-        uint8_t tl[kItems * 5];
-        hash_tile_verts(ws, verts, r.nv);
-        for (int i = 0; i < r.ni; ++i) {
-            Item it = items[(size_t)(r.item_start + i)];
-            // packed tet positions: the tile's first tets, then its second tets (lane i reads records i and ni + i:
-            // consecutive 16-byte words across the lanes of a warp for both)
-            const size_t pa = (size_t)(r.item_start * 2 + i), pb = pa + (size_t)r.ni;
-            if (it.a < 0) {   // filler: a zero-volume clone of the previous item's first tet, both halves
-                it = {items[(size_t)(r.item_start + i - 1)].a, -1};
-                out.clone[pa] = 1;
-            }
-            const int32_t* ca = cells + 4 * it.a;
-            int32_t v5[5];
-            if (it.b < 0) {   // alone: the partner is a zero-volume clone, corner order unchanged
-                out.order[pa] = out.order[pb] = it.a;
-                out.clone[pb] = 1;
-                for (int k = 0; k < 4; ++k) v5[k] = ca[k];
-                v5[4] = ca[3];
-            } else {
-                const int32_t* cb = cells + 4 * it.b;
-                out.order[pa] = it.a;
-                out.order[pb] = it.b;
-                // shared face in ascending global id, then the two apexes
-                int sa[3], sb[3], ns = 0, apex_a = -1, apex_b = -1;
-                for (int k = 0; k < 4; ++k) {
-                    int j = -1;
-                    for (int m = 0; m < 4; ++m)
-                        if (cb[m] == ca[k]) j = m;
-                    if (j >= 0 && ns < 3) { sa[ns] = k; sb[ns] = j; ++ns; }
-                    else apex_a = k;
-                }
-                for (int m = 0; m < 4; ++m) {
-                    bool shared = false;
-                    for (int k = 0; k < ns; ++k) shared |= sb[k] == m;
-                    if (!shared) apex_b = m;
-                }
-                for (int x = 0; x < 3; ++x)
-                    for (int y = x + 1; y < 3; ++y)
-                        if (ca[sa[y]] < ca[sa[x]]) { std::swap(sa[x], sa[y]); std::swap(sb[x], sb[y]); }
-                out.cperm[pa] = (uint8_t)(sa[0] | (sa[1] << 2) | (sa[2] << 4) | (apex_a << 6));
-                out.cperm[pb] = (uint8_t)(sb[0] | (sb[1] << 2) | (sb[2] << 4) | (apex_b << 6));
-                for (int k = 0; k < 3; ++k) v5[k] = ca[sa[k]];
-                v5[3] = ca[apex_a];
-                v5[4] = cb[apex_b];
-            }
-            for (int k = 0; k < 5; ++k) tl[5 * i + k] = lookup_tile_vert(ws, v5[k]);
-        }
-        finish_tile(ws, out, tile, r, 5, 8, 2, tl, verts, f64);
-    });
-    return APL_OK;
 }
 
 }  // namespace apl

@@ -9,9 +9,10 @@ the element-wise PNCG vector updates can simply be replicated on ghosts.  Scalar
 the PNCG dot products) are reduced over ``counted`` (owned) entries and all-reduced.
 """
 
-from ._halo import HaloExchange
-from ._partition import Shard, partition_mesh, slab_shard
+from ._halo import HaloExchange, PeerHaloExchange
+from ._partition import Shard, partition_mesh, slab_shard, slab_shard_device
 from ._pncg import ShardedPNCG
 from ._model import ShardedOperators
 
-__all__ = ["HaloExchange", "Shard", "ShardedOperators", "ShardedPNCG", "partition_mesh", "slab_shard"]
+__all__ = ["HaloExchange", "PeerHaloExchange", "Shard", "ShardedOperators", "ShardedPNCG", "partition_mesh", "slab_shard",
+           "slab_shard_device"]

@@ -110,3 +110,95 @@ class HaloExchange:
     def all_reduce_(self, t: torch.Tensor) -> None:
         if self.world > 1:
             dist.all_reduce(t, group=self.group)
+
+
+class PeerHaloExchange(HaloExchange):
+    """``HaloExchange`` whose data path is peer memory over NVLink (``apl_xchg_*``, ``csrc/xchg.cu``): the shared rows
+    of up to three fields AND the partial scalars of a step travel in ONE push kernel (plain stores into the sharers'
+    receive buffers) followed by ONE pull kernel (device-side wait on epoch flags, rank-ordered sums), instead of
+    pack + NCCL all-to-all + unpack + NCCL all-reduce.  Same plan, same summation order, bit-identical results.
+    ``torch.distributed`` (any backend) is used once, at construction, to exchange the plan sizes and the CUDA IPC
+    handles.  One process per GPU, all ranks on one node."""
+
+    def __init__(self, shard: Shard, device, group=None):
+        super().__init__(shard, device, group)
+        if self.device.type != "cuda":
+            raise _lib.NativeError("PeerHaloExchange needs CUDA devices (peer memory over NVLink)")
+        import ctypes
+
+        L = _lib.lib()
+        world, rank = self.world, self.rank
+        # counts[r][s] = rows rank r shares with rank s: rank s's receive buffer holds the segments of ranks 0..world-1
+        # in rank order, so this rank's rows start at sum(counts[s][:rank]) there
+        all_counts = [None] * world
+        dist.all_gather_object(all_counts, list(self.counts), group=group)
+        peers, rows = [], []
+        for s in range(world):
+            if s == rank or self.counts[s] == 0:
+                continue
+            if all_counts[s][rank] != self.counts[s]:
+                raise RuntimeError(f"halo plan mismatch between ranks {rank} and {s}")
+            base = sum(all_counts[s][:rank])
+            peers.append(np.full(self.counts[s], s, np.int32))
+            rows.append(base + np.arange(self.counts[s], dtype=np.int64))
+        t = lambda a, dt: torch.as_tensor(a, dtype=dt, device=self.device)  # noqa: E731
+        self.send_peer = t(np.concatenate(peers) if peers else np.zeros(0, np.int32), torch.int32)
+        self.send_row = t(np.concatenate(rows) if rows else np.zeros(0, np.int64), torch.int64)
+        handle = ctypes.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        with torch.cuda.device(self.device):
+            _lib.check(L.apl_xchg_create(world, rank, dev_index, max(self.total, 1), ctypes.byref(handle)))
+            self._xchg = handle
+            mine = ctypes.create_string_buffer(64)
+            _lib.check(L.apl_xchg_ipc_handle(handle, mine))
+            blobs = [None] * world
+            dist.all_gather_object(blobs, bytes(mine.raw), group=group)
+            _lib.check(L.apl_xchg_connect(handle, ctypes.create_string_buffer(b"".join(blobs), 64 * world)))
+            _lib.check(L.apl_xchg_set_plan(handle, self.total, _lib.dev_ptr(self.send_index), _lib.dev_ptr(self.send_peer),
+                                           _lib.dev_ptr(self.send_row), self.shared.numel(), _lib.dev_ptr(self.shared),
+                                           _lib.dev_ptr(self.row_ptr), _lib.dev_ptr(self.src)))
+        dist.barrier(group=group)       # every region is mapped everywhere before the first push
+
+    def __del__(self):
+        h = getattr(self, "_xchg", None)
+        if h is not None and h.value:
+            try:
+                _lib.lib().apl_xchg_destroy(h)
+            except Exception:  # interpreter shutdown
+                pass
+            self._xchg = None
+
+    def _call(self, fn, fields, scal):
+        nf = len(fields)
+        if nf > 3:
+            raise ValueError("at most three fields per exchange")
+        dtype = fields[0].dtype if nf else scal.dtype
+        ld = int(fields[0].shape[1]) if nf else 3
+        f = [_lib.dev_ptr(x) for x in fields] + [None] * (3 - nf)
+        n_scal = 0 if scal is None else int(scal.numel())
+        with torch.cuda.device(self.device):
+            _lib.check(fn(self._xchg, _lib.dtype_code(dtype), nf, f[0], f[1], f[2], ld, _lib.dev_ptr(scal), n_scal,
+                          _lib.stream_ptr(self.device)))
+
+    def push(self, fields, scal=None) -> None:
+        self._call(_lib.lib().apl_xchg_push, fields, scal)
+
+    def pull(self, fields, scal=None) -> None:
+        self._call(_lib.lib().apl_xchg_pull, fields, scal)
+
+    def sum_(self, *fields: torch.Tensor, scal: torch.Tensor | None = None) -> None:
+        """Halo sum of ``fields`` (in place) and, in the same exchange, the global sums of the entries of ``scal``."""
+        if self.world == 1:
+            return
+        for k in range(0, max(len(fields), 1), 3):
+            part = fields[k:k + 3]
+            s = scal if k == 0 else None
+            if not part and s is None:
+                continue
+            self.push(part, s)
+            self.pull(part, s)
+
+    def all_reduce_(self, t: torch.Tensor) -> None:
+        if self.world > 1:
+            self.push((), t)
+            self.pull((), t)

@@ -6,7 +6,7 @@ from apple_b200 import _lib
 
 from apple_b200.warp.model._adapter import zeros_block
 
-from ._halo import HaloExchange
+from ._halo import HaloExchange, PeerHaloExchange
 from ._partition import Shard
 
 
@@ -18,11 +18,21 @@ class ShardedOperators:
     the CPU tests substitute the oracle).  Inputs and outputs are local nodal fields whose shared rows
     are kept consistent across ranks; scalars are global."""
 
-    def __init__(self, local_model, shard: Shard, device, dtype, group=None, overlap: bool = True):
+    def __init__(self, local_model, shard: Shard, device, dtype, group=None, overlap: bool = True,
+                 transport: str | None = None):
+        """``transport``: ``"peer"`` = halo sums and the scalar reduction through peer memory over NVLink in two small
+        kernels per evaluation (``PeerHaloExchange``; CUDA, one node), ``"nccl"`` = pack / all-to-all / unpack /
+        all-reduce through ``torch.distributed`` (any backend; with ``overlap`` the exchange runs while the interior
+        tiles are evaluated).  Default: peer memory on CUDA devices, ``torch.distributed`` otherwise."""
         self.model = local_model
         self.shard = shard
-        self.halo = HaloExchange(shard, device, group)
         self.device, self.dtype = torch.device(device), dtype
+        if transport is None:
+            transport = "peer" if (self.device.type == "cuda" and shard.world > 1) else "nccl"
+        self.transport = transport
+        self.halo = PeerHaloExchange(shard, device, group) if transport == "peer" else HaloExchange(shard, device, group)
+        if transport == "peer":
+            overlap = False      # the exchange is two small kernels behind the element pass: nothing left to hide
         self.n_local = shard.n_local
         # Split evaluation: element tiles that touch a shared vertex first, then the halo exchange of their
         # results on a side stream WHILE the interior tiles (which touch no shared vertex) are evaluated.
@@ -65,6 +75,13 @@ class ShardedOperators:
             else:                                      # CPU (gloo tests): same order, no overlap
                 self.halo.sum_(*fields)
                 self.model.eval(ops, u, p, part=_lib.PART_INTERIOR, **out, **kw)
+        elif self.transport == "peer":
+            # one element pass, then ONE push + ONE pull kernel carry the shared rows and the partial scalars
+            self.model.eval(ops, u, p, **out, **kw)
+            self.halo.sum_(*fields, scal=scal if snames else None)
+            for i, k in enumerate(snames):
+                out[k] = scal[i]
+            return out
         else:
             self.model.eval(ops, u, p, **out, **kw)
             self.halo.sum_(*fields)

@@ -25,7 +25,7 @@ class Shard:
 
     @property
     def n_local(self) -> int:
-        return self.l2g.size
+        return int(self.l2g.shape[0])
 
 
 def partition_mesh(mesh: TetMesh, world: int, rank: int) -> Shard:
@@ -94,6 +94,38 @@ def slab_shard(n: int, world: int, rank: int, *, grading: float = 1.0, morton: b
     owned = np.ones(vgid.size, dtype=bool)
     if rank > 0:
         owned[layer == i0] = False                        # the plane shared with the previous rank is owned by it
+    return Shard(rank=rank, world=world, mesh=mesh, l2g=vgid, owned=owned,
+                 cell_range=(5 * i0 * n * n, 5 * i1 * n * n), neighbors=neighbors,
+                 n_global_points=(n + 1) ** 3, n_global_cells=5 * n ** 3)
+
+
+def slab_shard_device(n: int, world: int, rank: int, device, *, grading: float = 1.0) -> Shard:
+    """``slab_shard`` with the mesh GENERATED ON THE DEVICE (``apple_b200.mesh.cube_tet_slab_device``): ``shard.mesh`` is
+    a ``DeviceMesh`` (torch tensors in HBM: points, cells, global vertex / cell ids), ``l2g`` and ``owned`` are device
+    tensors, and only the analytic halo plan (the one or two shared grid planes, a few 10^4 indices) visits the host.
+    Local vertices are numbered along a Morton curve.  For meshes that should never exist in host memory (config 5:
+    64 M tets)."""
+    import torch
+
+    from apple_b200.mesh import DeviceMesh, cube_tet_slab_device
+
+    if world > n:
+        raise ValueError("more ranks than hex layers")
+    bounds = [r * n // world for r in range(world + 1)]
+    i0, i1 = bounds[rank], bounds[rank + 1]
+    pts, cells, vgid, cgid = cube_tet_slab_device(n, i0, i1, device, grading=grading, morton_vertices=True)
+    mesh = DeviceMesh(pts, cells, vgid, cgid, (n + 1) ** 3, 5 * n ** 3)
+    plane = (n + 1) * (n + 1)
+    layer = torch.div(vgid, plane, rounding_mode="floor")
+    neighbors = {}
+    for other, shared_layer in ((rank - 1, i0), (rank + 1, i1)):
+        if 0 <= other < world:
+            idx = torch.nonzero(layer == shared_layer).reshape(-1)
+            idx = idx[torch.argsort(vgid[idx], stable=True)]                     # both sides: by global id
+            neighbors[other] = idx.cpu().numpy().astype(np.int64)
+    owned = torch.ones(vgid.numel(), dtype=torch.bool, device=vgid.device)
+    if rank > 0:
+        owned[layer == i0] = False                                               # the previous rank owns the shared plane
     return Shard(rank=rank, world=world, mesh=mesh, l2g=vgid, owned=owned,
                  cell_range=(5 * i0 * n * n, 5 * i1 * n * n), neighbors=neighbors,
                  n_global_points=(n + 1) ** 3, n_global_cells=5 * n ** 3)

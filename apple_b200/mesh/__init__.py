@@ -9,9 +9,16 @@ package accepts either a ``TetMesh`` or a real ``pyvista.UnstructuredGrid``.
 from ._mesh import TetMesh, as_tet_arrays
 from ._generate import (cube_tet_mesh, cube_tet_slab, embedded_tetra_mesh, hash_uniform, lumped_vertex_volume,
                         morton_reorder)
+from ._device import (DeviceMesh, cube_tet_mesh_device, cube_tet_slab_device, hash_uniform_device,
+                      morton_codes_device)
 
 __all__ = [
+    "DeviceMesh",
     "TetMesh",
+    "cube_tet_mesh_device",
+    "cube_tet_slab_device",
+    "hash_uniform_device",
+    "morton_codes_device",
     "as_tet_arrays",
     "cube_tet_mesh",
     "cube_tet_slab",

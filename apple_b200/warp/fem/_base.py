@@ -66,13 +66,7 @@ class WarpPotentialFem(WarpPotential):
         if self.device.type != "cuda":
             raise _lib.NativeError("apple_b200 potentials live on a CUDA device (there is no CPU path)")
         self.points = None if points is None else np.ascontiguousarray(points, dtype=np.float64)
-        L = _lib.lib()
-        _lib.check(L.apl_set_layout(int(config.layout)))     # layout of the handle created next
-        try:
-            self._handle = self._create_handle()
-        finally:
-            L.apl_set_layout(_lib.LAYOUT_TET)
-        self.layout = int(L.apl_fem_layout(self._handle))
+        self._handle = self._create_handle()
 
     def _create_handle(self) -> ctypes.c_void_p:
         handle = ctypes.c_void_p()
@@ -173,7 +167,6 @@ class WarpPotentialFem(WarpPotential):
                 1 if morton else 0, self.device.index if self.device.index is not None else torch.cuda.current_device(),
                 ctypes.byref(handle)))
         self._handle = handle
-        self.layout = int(_lib.lib().apl_fem_layout(self._handle))
         return self
 
     @property

@@ -1,19 +1,23 @@
 #!/usr/bin/env python
-"""Benchmark of the FEM-elasticity hot path (see BASELINE.json / DESIGN.md section "Measurement").
+"""Benchmark of the FEM-elasticity hot path (BASELINE.json / DESIGN.md section "Measurement").
 
-Workload (N = 1): BASELINE.json configs[1] -- synthetic 58^3 x 5 = 975,560-tet cube, Stable
-Neo-Hookean + ARAP on the same mesh, fp32.  One *step* = one fused energy + gradient +
-Hessian-vector-product evaluation of the whole model (every potential, one pass each).
+Workload, at every N: BASELINE.json configs[4] -- the synthetic 234^3 x 5 = 64,064,520-tet cube (12,977,875 vertices),
+Stable Neo-Hookean + ARAP on the same cells (fused into one pass), fp32, STRONG scaling: the mesh is fixed and rank r
+of N generates, orders, tiles and packs its slab of hex layers entirely on its GPU (nothing but the connectivity of
+the slab visits the host).  One *step* = one fused energy + gradient + Hessian-vector-product evaluation of the whole
+model, halo sums and the energy reduction included (peer memory over NVLink, `apl_xchg_*`).
 
-  value      tets/s, inputs resident in HBM, L2 flushed between timed steps
-  e2e        same metric through WarpModelAdapter.fun_grad_hess_prod_host with HOST (pinned) u, p:
-             H2D copies, kernels, D2H of energy + gradient + HVP inside the timed region
-  roofline   dominant kernel: algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
-  pncg       200 fused PNCG iterations on the same model (iterations/s)
-  cpu_baseline  the oracle (numpy restatement of the reference) on a bounded sample, host cores
+  value       tets/s, inputs resident in HBM, L2 flushed between timed steps (the working set is >> L2 anyway)
+  e2e         the same metric from HOST (pinned) u, p to HOST energy / gradient / HVP: H2D, kernels, exchange, D2H inside
+  roofline    dominant kernel: algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
+  parity      rank 0's gradient / HVP rows on three grid planes around its first slab interface (the shared plane
+              included) and the energy of a 4-layer sample against the C restatement of the reference (oracle/c, fp64)
+  hvp         Hessian-vector product alone, fp32 and fp64 (configs[4]: "fp32 and fp64 HVP throughput vs HBM roofline")
+  config2     N = 1 only: BASELINE.json configs[1] (58^3 x 5 = 975,560 tets): operators, roofline, 200 PNCG iterations
+  cpu_baseline  the C restatement of the reference on a bounded sample (4 hex layers ~ 1.1 M tets), all host threads
 
-`--impl reference` times the CPU restatement of the reference (the reference itself needs Warp/JAX,
-which are not installable here) on the same workload definition.
+`--impl reference` times that C restatement (the reference itself needs Warp / JAX, not installable here) on the
+same workload definition, in the same dtype, honouring --steps / --warmup; rank 0 only.
 """
 
 from __future__ import annotations
@@ -26,6 +30,7 @@ import sys
 import threading
 import time
 from pathlib import Path
+from types import SimpleNamespace
 
 import numpy as np
 
@@ -35,48 +40,113 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 METRIC = "tets_per_s_fused_energy_grad_hvp"
 UNIT = "tets/s"
+N_HEADLINE = 234     # BASELINE.json configs[4]
+N_CONFIG2 = 58       # BASELINE.json configs[1]
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=0, help="hexes per cube edge (5 tets per hex); 0 = 58 * gpus^(1/3)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N>1 with --n 0: weak = ~975k tets per GPU (mesh grows with N), strong = the 58^3 mesh")
+    ap.add_argument("--n", type=int, default=N_HEADLINE, help="hexes per cube edge (5 tets per hex); fixed for every N")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--scatter", default="tile", choices=["tile", "atomic", "tile_simple"])
-    ap.add_argument("--layout", default="tet", choices=["tet", "pair"],
-                    help="pair = EXPERIMENTAL: one consumer thread per pair of face-adjacent tets (tile assembly only)")
     ap.add_argument("--potentials", default="snh,arap")
     ap.add_argument("--pncg-iters", type=int, default=200)
     ap.add_argument("--no-fuse", action="store_true", help="one pass per potential (the reference's structure)")
-    ap.add_argument("--graph", action="store_true", help="N>1, experimental: replay each step as one CUDA graph")
-    ap.add_argument("--no-overlap", action="store_true",
-                    help="N>1: do not overlap the halo exchange with the interior tiles (one launch, then exchange)")
-    ap.add_argument("--no-probe", action="store_true",
-                    help="N=1: do not run the experimental pair layout in a time-limited subprocess after the measurement")
-    ap.add_argument("--probe-parity", action="store_true",
-                    help="also compare energy / gradient / HVP of the model with the C oracle (used by the pair-layout probe)")
-    ap.add_argument("--slab", action="store_true",
-                    help="config-5 style strong scaling: every rank GENERATES only its slab of the --n cube (no global "
-                         "mesh on any rank; fields are functions of the global ids); operators only, also at 1 GPU")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="N>1: halo sums through peer memory (apl_xchg_*) or pack / NCCL all-to-all / unpack / all-reduce")
+    ap.add_argument("--graph", action="store_true", help="N>1: replay each step as one CUDA graph (peer transport only)")
     ap.add_argument("--no-pncg", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-hvp", action="store_true")
+    ap.add_argument("--no-config2", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
-    ap.add_argument("--sweep", action="store_true", help="also time every operator / variant (stderr table)")
-    args = ap.parse_args()
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.n == 0:
-        args.n = 58 if (world == 1 or args.scaling == "strong") else int(round(58 * world ** (1.0 / 3.0)))
-    else:
-        args.scaling = "strong" if world > 1 else args.scaling
-    return args
+    ap.add_argument("--no-probe", action="store_true", help=argparse.SUPPRESS)   # accepted for old command lines
+    ap.add_argument("--sweep", action="store_true", help="N=1: also time every operator / variant at config 2 (stderr table)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ workload
+# Materials and fields are functions of the GLOBAL cell / vertex ids (splitmix64 hashes), so that every partition of the
+# cube -- and the host sample handed to the oracle -- evaluates the same model.
+
+def _fields(xp, hashf, X, vg, cg, n):
+    """xp = numpy or torch; X (V, 3) rest positions, vg / cg global vertex / cell ids."""
+    from apple_b200.common import lame_converter
+
+    E = 10.0 ** (4.0 + hashf(cg, 1))
+    nu = 0.3 + 0.15 * hashf(cg, 2)
+    la, mu = lame_converter(E, nu)
+    h = 1.0 / n
+    noise = xp.stack([hashf(3 * vg + k, 3) for k in range(3)], 1)
+    u = 0.05 * h * xp.sin(7.0 * X[:, [1, 2, 0]] + 0.3) + 0.02 * h * (2.0 * noise - 1.0)
+    p = 2.0 * xp.stack([hashf(3 * vg + k, 4) for k in range(3)], 1) - 1.0
+    return mu, la, u, p
+
+
+def device_workload(n, world, rank, device, dtype):
+    """This rank's slab of the n^3 x 5 cube, generated on the device, with materials and fields."""
+    import torch
+
+    from apple_b200.dist import slab_shard_device
+    from apple_b200.mesh import hash_uniform_device
+
+    shard = slab_shard_device(n, world, rank, device)
+    dm = shard.mesh
+    mu, la, u, p = _fields(torch, hash_uniform_device, dm.points, dm.vertex_gid, dm.cell_gid, n)
+    return SimpleNamespace(shard=shard, mesh=dm, mu=mu.to(dtype), la=la.to(dtype), u=u.to(dtype).contiguous(),
+                           p=p.to(dtype).contiguous())
+
+
+def device_potentials(w, kinds, dtype, fuse=True):
+    """The model's potentials built by apl_fem_create_from_mesh (setup on the GPU)."""
+    from apple_b200.warp.fem import Arap, FusedSnhArap, StableNeoHookean
+
+    dm = w.mesh
+    if fuse and sorted(kinds) == ["arap", "snh"]:
+        return {"snh+arap": FusedSnhArap.from_device_mesh(dm.cells, dm.points, mu=w.mu, lambda_=w.la, mu_arap=w.mu,
+                                                          dtype=dtype, name="snh+arap")}
+    pots = {}
+    for k in kinds:
+        if k == "snh":
+            pots[k] = StableNeoHookean.from_device_mesh(dm.cells, dm.points, mu=w.mu, lambda_=w.la, dtype=dtype, name=k)
+        elif k == "arap":
+            pots[k] = Arap.from_device_mesh(dm.cells, dm.points, mu=w.mu, dtype=dtype, name=k)
+        else:
+            raise KeyError(f"bench.py builds snh / arap potentials, not {k!r}")
+    return pots
+
+
+def host_sample(n, i0, i1):
+    """Hex layers [i0, i1) of the same cube as numpy arrays (for the oracle): TetMesh + fields, local vertex numbering,
+    `layer` = grid index i of every local vertex."""
+    from apple_b200.mesh import TetMesh, cube_tet_slab, hash_uniform
+
+    pts, cells, vg, cg = cube_tet_slab(n, i0, i1)
+    mu, la, u, p = _fields(np, hash_uniform, pts, vg, cg, n)
+    mesh = TetMesh(pts, cells, point_data={"gid": vg}, cell_data={"gid": cg, "mu": mu, "lambda": la})
+    return SimpleNamespace(mesh=mesh, u=np.ascontiguousarray(u), p=np.ascontiguousarray(p), vgid=vg,
+                           layer=vg // ((n + 1) * (n + 1)))
+
+
+def sample_layers(n, world):
+    """The 4 hex layers around rank 0's upper slab interface (N > 1; its shared plane is the third of the five grid
+    planes) or the first 4 layers (N = 1)."""
+    k = min(4, n)
+    if world == 1:
+        return 0, k
+    i1 = n // world                       # rank 0 owns hex layers [0, i1): plane i1 is shared with rank 1
+    a = max(0, min(i1 - 2, n - k))
+    return a, a + k
 
 
 def build_mesh(n, seed=0):
+    """Config-2 style HOST mesh (numpy; Morton-ordered) for the PNCG section and the tools."""
     from apple_b200.common import lame_converter
     from apple_b200.mesh import cube_tet_mesh
 
@@ -96,46 +166,23 @@ def build_mesh(n, seed=0):
 
 
 def cuda_potential(kind, mesh, dtype, **kw):
-    """A potential of the product (`apple_b200.warp.fem`) on `mesh`; nothing of oracle/ is involved."""
+    """A potential of the product (`apple_b200.warp.fem`) on a host `mesh`; nothing of oracle/ is involved."""
     from apple_b200.warp.fem import Arap, StableNeoHookean, StableNeoHookeanMuscle
 
     cls = {"snh": StableNeoHookean, "arap": Arap, "muscle": StableNeoHookeanMuscle}[kind]
     return cls.from_pyvista(mesh, dtype=dtype, **kw)
 
 
-def build_slab(n, world, rank):
-    """This rank's slab of the n^3 x 5 cube (apple_b200.dist.slab_shard) with the fields of `build_mesh` redefined as
-    functions of the GLOBAL vertex / cell ids, so that every partition of the same cube evaluates the same model."""
-    from apple_b200.common import lame_converter
-    from apple_b200.dist import slab_shard
-    from apple_b200.mesh import hash_uniform
-
-    shard = slab_shard(n, world, rank)
-    mesh = shard.mesh
-    cg, vg = mesh.cell_data["gid"], mesh.point_data["gid"]
-    E = 10.0 ** (4.0 + hash_uniform(cg, 1))
-    nu = 0.3 + 0.15 * hash_uniform(cg, 2)
-    la, mu = lame_converter(E, nu)
-    mesh.cell_data["mu"] = mu
-    mesh.cell_data["lambda"] = la
-    h = 1.0 / n
-    X = mesh.points
-    noise = np.stack([hash_uniform(3 * vg + k, 3) for k in range(3)], axis=1)
-    u = 0.05 * h * np.sin(7.0 * X[:, [1, 2, 0]] + 0.3) + 0.02 * h * (2.0 * noise - 1.0)
-    p = 2.0 * np.stack([hash_uniform(3 * vg + k, 4) for k in range(3)], axis=1) - 1.0
-    return shard, mesh, np.ascontiguousarray(u), np.ascontiguousarray(p)
+def workload_name(n, kinds):
+    return (f"cube {n}^3x5 = {5 * n ** 3} tets / {(n + 1) ** 3} verts, {'+'.join(kinds)}, fused energy+grad+HVP"
+            + (" (BASELINE.json configs[4])" if n == N_HEADLINE else ""))
 
 
-def workload_name(args, mesh, kinds):
-    """config.workload, shared by both arms."""
-    T, V = (5 * args.n ** 3, (args.n + 1) ** 3) if getattr(args, "slab", False) else (mesh.n_cells, mesh.n_points)
-    return (f"cube {args.n}^3x5 = {T} tets / {V} verts, {'+'.join(kinds)}, fused energy+grad+HVP"
-            + (" (per-rank slab generation)" if getattr(args, "slab", False) else ""))
-
-
-def algorithmic_bytes_per_tet(kind, w, v_over_t, per_vertex_words):
-    m = {"snh": 2, "arap": 1, "muscle": 8}[kind]
-    return 16 + 9 * w + w + m * w + v_over_t * per_vertex_words * w
+def bytes_per_tet(kinds, w, v_over_t, vertex_words):
+    """Algorithmic bytes per tet of one fused pass over potentials that share their cells: connectivity
+    16, Dm^-1 9w, then per potential vol + materials, plus the nodal fields touched once per vertex."""
+    m = {"snh": 2, "arap": 1, "muscle": 8}
+    return 16 + 9 * w + sum(w + m[k] * w for k in kinds) + v_over_t * vertex_words * w
 
 
 class ClockSampler:
@@ -226,67 +273,71 @@ def measured_peak_gbs():
 
 
 # ------------------------------------------------------------------------------------ reference arm
+# (oracle/ is imported below this line only: CPU baseline, reference arm and the parity check of the benchmark)
 
 
-def oracle_model(mesh, kinds, n_tets=None):
-    """The reference's operators restated in C (oracle/c, all host threads), one pass per operator per
-    potential exactly like WarpModel (warp/model/_model.py:13-36)."""
-    from helpers import oracle_potential
-    from apple_b200.mesh import TetMesh
+def oracle_model(sample, kinds, np_dtype=np.float64):
+    """The reference's operators restated in C (oracle/c, all host threads), one pass per operator per potential
+    exactly like WarpModel (warp/model/_model.py:13-36), on a host sample of the workload."""
     from oracle import cbind
+    from oracle import region as oregion
 
-    if n_tets is not None and n_tets < mesh.n_cells:
-        sub = TetMesh(mesh.points, mesh.cells[:n_tets], cell_data={k: v[:n_tets] for k, v in mesh.cell_data.items()})
-    else:
-        sub = mesh
+    mesh = sample.mesh
+    dhdX, dV = oregion.compute_grad(mesh.points, mesh.cells, None, dtype=np.float64)
     pots = []
     for k in kinds:
-        ref = oracle_potential(k, sub)  # numpy oracle: only used here to assemble dhdX / dV / materials
-        pots.append(cbind.CPotential(k, ref.cells, ref.dhdX, ref.dV, ref.materials["mu"], ref.materials.get("lambda_"),
-                                     ref.materials.get("activation")))
-    return pots, sub.n_cells, cbind.num_threads()
+        pots.append(cbind.CPotential(k, mesh.cells, dhdX, dV, mesh.cell_data["mu"],
+                                     mesh.cell_data["lambda"] if k != "arap" else None, None, dtype=np_dtype))
+    return pots, cbind.num_threads()
 
 
-def time_oracle(mesh, u, p, kinds, sample_tets, steps, warmup):
-    pots, T, threads = oracle_model(mesh, kinds, sample_tets)
-    V = mesh.n_points
+def oracle_eval(pots, sample, np_dtype=np.float64):
+    """energy, gradient, HVP of the sample: three operator passes per potential, as the reference launches them."""
+    V = sample.mesh.n_points
+    e, g, h = np.zeros(1), np.zeros((V, 3), np_dtype), np.zeros((V, 3), np_dtype)
+    for pot in pots:
+        pot.fun(sample.u, e)
+    for pot in pots:
+        pot.grad(sample.u, g)
+    for pot in pots:
+        pot.hess_prod(sample.u, sample.p, h)
+    return e, g, h
+
+
+def time_oracle(sample, kinds, steps, warmup, np_dtype):
+    pots, threads = oracle_model(sample, kinds, np_dtype)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        e, g, h = np.zeros(1), np.zeros((V, 3)), np.zeros((V, 3))
-        for pot in pots:  # fun, grad, hess_prod: three passes per potential, as the reference launches them
-            pot.fun(u, e)
-        for pot in pots:
-            pot.grad(u, g)
-        for pot in pots:
-            pot.hess_prod(u, p, h)
+        oracle_eval(pots, sample, np_dtype)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
+    T = sample.mesh.n_cells
     return T * len(times) / sum(times), T, float(np.mean(times)), threads
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     kinds = args.potentials.split(",")
-    mesh, u, p = build_mesh(args.n)
-    sample = min(mesh.n_cells, 1_000_000)
-    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
-    value, T, dt, threads = time_oracle(mesh, u, p, kinds, sample, steps, warmup)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    a, b = sample_layers(args.n, 1)
+    sample = host_sample(args.n, a, b)
+    np_dtype = np.float32 if args.dtype == "f32" else np.float64
+    value, T, dt, threads = time_oracle(sample, kinds, args.steps, args.warmup, np_dtype)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": args.scaling if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args, mesh, kinds),
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": workload_name(args.n, kinds),
                    "reference_arm": "energy + gradient + HVP as three operator passes per potential, exactly as the "
                                     "reference launches them (warp/model/_model.py:13-36); CPU restatement of the "
-                                    "reference's Warp kernels in C (oracle/c, pthreads, fp64) -- the reference itself needs "
-                                    "warp-lang / JAX, which cannot be installed here"},
+                                    f"reference's Warp kernels in C (oracle/c, pthreads, {args.dtype}) on a bounded sample "
+                                    "-- the reference itself needs warp-lang / JAX, which cannot be installed here",
+                   "launched_ranks": world},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"first {T} tets of the Morton-ordered mesh, {steps} evaluations"},
+                         "sample": f"hex layers [{a}, {b}) of the cube = {T} tets per step, {args.steps} steps"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -304,9 +355,8 @@ def main():
     import torch.distributed as dist
 
     from apple_b200 import _lib, config
-    from apple_b200.mesh import TetMesh
-    from apple_b200.warp.fem import fuse_potentials
     from apple_b200.warp.model import WarpModel, WarpModelAdapter
+    from apple_b200.warp.model._adapter import zeros_block
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -314,29 +364,14 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        try:   # NCCL kernels on a high-priority stream: the halo exchange overlaps the interior element pass
-            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
-            dist.init_process_group("nccl", device_id=dev, pg_options=opts)
-        except Exception:
-            if dist.is_initialized():
-                raise
-            dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)
     dtype = torch.float32 if args.dtype == "f32" else torch.float64
     w = 4 if args.dtype == "f32" else 8
     config.scatter = {"tile": _lib.SCATTER_TILE, "atomic": _lib.SCATTER_ATOMIC,
                       "tile_simple": _lib.SCATTER_TILE_SIMPLE}[args.scatter]
-    config.layout = {"tet": _lib.LAYOUT_TET, "pair": _lib.LAYOUT_PAIR}[args.layout]
     kinds = args.potentials.split(",")
-
-    shard = None
-    if args.slab:
-        shard, mesh, u, p = build_slab(args.n, world, rank)     # `mesh`, `u`, `p` are this rank's slab only
-        T_total, V = shard.n_global_cells, shard.n_global_points
-        args.no_pncg = args.no_cpu_baseline = args.no_probe = True
-        args.scaling = "strong"
-    else:
-        mesh, u, p = build_mesh(args.n)
-        T_total, V = mesh.n_cells, mesh.n_points
+    n = args.n
+    T_total, V_total = 5 * n ** 3, (n + 1) ** 3
     OPS = _lib.OP_FUN | _lib.OP_GRAD | _lib.OP_HESS_PROD
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
@@ -344,75 +379,51 @@ def main():
         if not args.no_flush:
             flush_buf.fill_(1)
 
-    if world == 1 and not args.slab:
-        lo, hi = 0, T_total
-        pots = {k: cuda_potential(k, mesh, dtype, name=k) for k in kinds}
-        if not args.no_fuse:
-            pots = fuse_potentials(pots)
-        model = WarpModel(pots)
-        adapter = WarpModelAdapter(model, n_points=V)
-        ud = torch.as_tensor(u, dtype=dtype, device=dev).contiguous()
-        pd = torch.as_tensor(p, dtype=dtype, device=dev).contiguous()
-        from apple_b200.warp.model._adapter import zeros_block
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
-        out_block, (grad, prod), (fun,) = zeros_block(V, 2, 1, dtype, dev)   # all outputs of a step in one buffer
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- setup: mesh, fields, potentials -- all on the device ----
+    barrier()
+    t_setup = time.perf_counter()
+    wl = device_workload(n, world, rank, dev, dtype)
+    shard = wl.shard
+    T_local, V_local = wl.mesh.n_cells, wl.mesh.n_points
+    pots = device_potentials(wl, kinds, dtype, fuse=not args.no_fuse)
+    model = WarpModel(pots)
+    ud, pd = wl.u, wl.p
+    sharded = None
+    if world > 1:
+        from apple_b200.dist import ShardedOperators
+
+        sharded = ShardedOperators(model, shard, dev, dtype, transport=args.transport, overlap=args.transport == "nccl")
+    torch.cuda.synchronize()
+    setup_s = max_over_ranks(time.perf_counter() - t_setup)
+
+    if world == 1:
+        adapter = WarpModelAdapter(model, n_points=V_local)
+        out_block, (grad, prod), (fun,) = zeros_block(V_local, 2, 1, dtype, dev)   # all outputs of a step in one buffer
 
         def step():
             out_block.zero_()      # the operators accumulate (warp/model/_model.py:13-36 zeroes first): one memset
             model.eval(OPS, ud, pd, fun=fun, grad=grad, prod=prod, zero=False)
+            return {"fun": fun, "grad": grad, "prod": prod}
     else:
-        # strong scaling: rank r owns a contiguous chunk of the Morton-ordered tets and a local copy of
-        # the vertices they touch; one halo sum (all-to-all of the shared rows) + one scalar all-reduce
-        from apple_b200.dist import ShardedOperators, partition_mesh
-
-        if shard is None:
-            shard = partition_mesh(mesh, world, rank)
-            u, p = u[shard.l2g], p[shard.l2g]
-        lo, hi = shard.cell_range
-        pots = {k: cuda_potential(k, shard.mesh, dtype, name=k) for k in kinds}
-        if not args.no_fuse:
-            pots = fuse_potentials(pots)
-        sharded = ShardedOperators(WarpModel(pots), shard, dev, dtype, overlap=not args.no_overlap)
-        ud = torch.as_tensor(u, dtype=dtype, device=dev).contiguous()
-        pd = torch.as_tensor(p, dtype=dtype, device=dev).contiguous()
-        fun = torch.zeros(1, dtype=dtype, device=dev)
-        grad = torch.zeros((shard.n_local, 3), dtype=dtype, device=dev)
-        prod = torch.zeros((shard.n_local, 3), dtype=dtype, device=dev)
-
         def eager_step():
             return sharded.eval(OPS, ud, pd)
 
-        # The split evaluation (boundary tiles -> halo exchange overlapped with the interior tiles) must give
-        # what the plain sequence gives; if it does not on this box, the plain sequence is benchmarked.
-        overlap_note = None
-        if sharded.overlap:
-            try:
-                r_split = eager_step()
-            except Exception as exc:  # pragma: no cover - a host-side error is the same on every rank
-                r_split, overlap_note = None, f"split evaluation failed ({type(exc).__name__}: {exc}); disabled"
-            sharded.overlap = False
-            r_plain = eager_step()
-            sharded.overlap = r_split is not None
-            torch.cuda.synchronize()
-            err = float("inf") if r_split is None else max(
-                float((r_split[k] - r_plain[k]).abs().max() / r_plain[k].abs().max().clamp_min(1e-30))
-                for k in ("fun", "grad", "prod"))
-            bad = torch.tensor([1.0 if not (err < 1e-4) else 0.0], device=dev)
-            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
-            if float(bad.item()) > 0:
-                sharded.overlap = False
-                overlap_note = overlap_note or (f"split evaluation disagreed with the plain one on some rank (rel. err "
-                                                f"{err:.2e} on rank 0); disabled")
-
-        # EXPERIMENTAL, opt-in (--graph): replay the step (kernels + the two NCCL collectives) as one CUDA
-        # graph.  Not validated: the one attempt on 8 GPUs hung during capture, so the default is plain
-        # launches.
         graph = None
-        if args.graph:
+        if args.graph and args.transport == "peer":
             for _ in range(3):
                 eager_step()
-            torch.cuda.synchronize()
-            dist.barrier()
+            barrier()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 graph_out = eager_step()
@@ -420,13 +431,10 @@ def main():
         def step():
             if graph is not None:
                 graph.replay()
-            else:
-                eager_step()
+                return graph_out
+            return eager_step()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    launches_per_step = len(pots) + (0 if world == 1 else (2 if args.transport == "peer" else 2 + len(pots) * int(sharded.overlap)))
 
     # clocks / throttle reasons are sampled from before the warm-up until after the last timed GPU phase
     clocks = ClockSampler(local_rank)
@@ -439,197 +447,338 @@ def main():
     t_w0 = time.perf_counter()
     for a, b in ev:
         flush()
-        a.record(); step(); b.record()
+        a.record(); res = step(); b.record()
     barrier()
     clocks.window(t_w0, time.perf_counter())
-    t_ms = sum(a.elapsed_time(b) for a, b in ev)
-    t = torch.tensor([t_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_ms = float(t.item())
+    t_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
     ms_per_step = t_ms / args.steps
     value = T_total * args.steps / (t_ms * 1e-3)
 
-    # ---- per-kernel roofline (each potential's fused kernel timed alone, L2 flushed) ----
+    # ---- per-kernel roofline (each potential's fused kernel timed alone on this rank's slab, L2 flushed) ----
     peak, peak_src = measured_peak_gbs()
-    v_over_t = (shard.n_local if shard is not None else V) / max(hi - lo, 1)
+    v_over_t = V_local / max(T_local, 1)
+    fun1 = torch.zeros(1, dtype=dtype, device=dev)
+    g1, h1 = (torch.zeros((V_local, 3), dtype=dtype, device=dev) for _ in range(2))
     kern = {}
     for k, pot in pots.items():
         ts = []
         for _ in range(max(5, min(args.steps, 20))):
             flush()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); pot.eval(OPS, ud, pd, fun=fun, grad=grad, prod=prod); b.record()
+            a.record(); pot.eval(OPS, ud, pd, fun=fun1, grad=g1, prod=h1); b.record()
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
-        dt = float(np.mean(ts)) * 1e-3
-        bpt = sum(algorithmic_bytes_per_tet(part, w, 0.0, 0) - 16 - 9 * w for part in k.split("+")) + 16 + 9 * w \
-            + v_over_t * 12 * w  # connectivity, Dm^-1 and the nodal fields are touched once per pass
-        kern[k] = {"ms": dt * 1e3, "bytes_per_tet": bpt, "gbs": bpt * (hi - lo) / dt / 1e9,
-                   "gtets_per_s": (hi - lo) / dt / 1e9}
+        dt = max_over_ranks(float(np.mean(ts))) * 1e-3      # the slowest rank's kernel
+        bpt = bytes_per_tet(k.split("+"), w, v_over_t, 12)
+        kern[k] = {"ms": dt * 1e3, "bytes_per_tet": bpt, "gbs": bpt * T_local / dt / 1e9, "gtets_per_s": T_local / dt / 1e9,
+                   "tets": T_local}
+    del g1, h1
     dom = max(kern, key=lambda k: kern[k]["ms"])
     traffic = None
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists() and world == 1:
         try:
-            traffic = json.loads(tf.read_text()).get(f"{args.dtype}:{dom}:n{args.n}")
+            traffic = json.loads(tf.read_text()).get(f"{args.dtype}:{dom}:n{n}")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["gbs"] / peak, "traffic": traffic, "kernel": f"fem_pipe_kernel<{args.dtype},{dom},fun|grad|hess_prod>",
-                "peak_source": peak_src, "frac_of_nominal_8TBs": kern[dom]["gbs"] / 8000.0, "per_kernel": kern}
+                "frac": kern[dom]["gbs"] / peak, "traffic": traffic,
+                "kernel": f"fem_pipe_kernel<{args.dtype},{dom},fun|grad|hess_prod>", "peak_source": peak_src,
+                "frac_of_nominal_8TBs": kern[dom]["gbs"] / 8000.0,
+                "note": "per GPU: this rank's slab, slowest rank" if world > 1 else None, "per_kernel": kern}
 
+    # ---- parity at size: rank 0 against the C restatement of the reference on 4 hex layers ----
     parity = None
-    if world == 1 and args.probe_parity and not args.slab:
-        # the whole model once against the C restatement of the reference (fp64) on the full mesh
-        pots_o, _, _ = oracle_model(mesh, kinds)
-        e_o, g_o, h_o = np.zeros(1), np.zeros((V, 3)), np.zeros((V, 3))
-        for po in pots_o:
-            po.fun(u, e_o); po.grad(u, g_o); po.hess_prod(u, p, h_o)
-        step(); torch.cuda.synchronize()
-        rel = lambda a, b: float(np.abs(np.asarray(a, np.float64) - b).max() / np.abs(b).max())  # noqa: E731
-        parity = {"energy": rel(fun.cpu().numpy(), e_o), "grad": rel(grad.cpu().numpy(), g_o),
-                  "hess_prod": rel(prod.cpu().numpy(), h_o), "against": "C oracle (fp64) on the full mesh"}
-
-    # ---- e2e: host buffers through the public adapter API ----
-    e2e = None
-    if world == 1 and not args.slab:
-        uh = torch.as_tensor(u, dtype=dtype).pin_memory()
-        ph = torch.as_tensor(p, dtype=dtype).pin_memory()
-        gh = torch.empty((V, 3), dtype=dtype).pin_memory()
-        hh = torch.empty((V, 3), dtype=dtype).pin_memory()
-        fh = torch.empty(1, dtype=dtype).pin_memory()
-
-        def step_streamed():
-            # the host-buffer entry point of the plugin: H2D of u, p and D2H of energy, gradient, HVP are
-            # inside, overlapped with two element passes on side streams (see its docstring)
-            adapter.fun_grad_hess_prod_host(uh, ph, out=(fh, gh, hh))
-
-        def step_serial():
-            # the same call sequence a caller with host state would write by hand: copy in, one fused
-            # pass, copy out, all on the current stream
-            u_d = uh.to(dev, non_blocking=True); p_d = ph.to(dev, non_blocking=True)
-            f, g, h = adapter.fun_grad_hess_prod(u_d, p_d)
-            fh.copy_(f.reshape(1), non_blocking=True); gh.copy_(g, non_blocking=True); hh.copy_(h, non_blocking=True)
-
-        def time_e2e(fn):
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            tt = 0.0
-            for _ in range(args.steps):
-                flush()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); fn(); b.record()
-                torch.cuda.synchronize()
-                tt += a.elapsed_time(b)
-            return tt
-
+    if not args.no_parity:
         try:
-            # the serial form is timed first and kept as the check of the streamed one (same energy / gradient /
-            # HVP in the host buffers) and as the fallback should the streamed entry point fail on this box
-            tt_serial = time_e2e(step_serial)
-            ref = (fh.clone(), gh.clone(), hh.clone())
-            api, note, launches = "serial", None, len(pots)
-            tt = tt_serial
-            try:
-                fh.zero_(); gh.zero_(); hh.zero_()
-                tt_streamed = time_e2e(step_streamed)
-                err = max(float((x - y).abs().max() / y.abs().max()) for x, y in zip((fh, gh, hh), ref))
-                if err < 1e-4 and tt_streamed <= tt_serial:
-                    api, tt, launches = "streamed", tt_streamed, 2 * len(pots)
-                elif err < 1e-4:
-                    note = f"streamed entry point verified but slower here ({tt_streamed / args.steps:.4f} ms per step); serial number reported"
-                else:
-                    note = f"streamed entry point disagreed with the serial one (rel. err {err:.2e}); serial number reported"
-            except Exception as exc:  # pragma: no cover - robustness of the benchmark line
-                note = f"streamed entry point failed ({type(exc).__name__}: {exc}); serial number reported"
-            e2e = {"value": T_total * args.steps / (tt * 1e-3), "unit": UNIT,
-                   "h2d_bytes_per_step": int(2 * V * 3 * w), "d2h_bytes_per_step": int(2 * V * 3 * w + w),
-                   "ms_per_step": tt / args.steps,
-                   "api": {"streamed": "WarpModelAdapter.fun_grad_hess_prod_host(u_host, p_host, out=host tensors): copies "
-                                       "overlapped with a fun+grad pass and a hess_prod pass on side streams",
-                           "serial": "u.to(device); p.to(device); WarpModelAdapter.fun_grad_hess_prod; copy_ to host"}[api],
-                   "gpu_launches_per_step": launches, "serial_ms_per_step": tt_serial / args.steps, "note": note}
+            parity = parity_check(args, wl, res, kinds, dtype, dev, world, rank)
+        except Exception as exc:  # pragma: no cover - keep the headline line
+            parity = {"error": f"{type(exc).__name__}: {exc}"}
+
+    # ---- e2e: host buffers through the public API ----
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e = bench_e2e(args, wl, model, sharded, adapter if world == 1 else None, dtype, dev, w, T_total, flush,
+                            max_over_ranks, barrier, len(pots))
         except Exception as exc:  # pragma: no cover - keep the headline line
             e2e = {"error": f"{type(exc).__name__}: {exc}"}
 
-    # ---- PNCG iterations/s on the same model (config 1/2 style solve: fixed base, fused path) ----
-    pncg = None
-    if world == 1 and not args.no_pncg:
+    # ---- HVP alone, fp32 and fp64 (configs[4]) ----
+    hvp = None
+    if not args.no_hvp:
         try:
-            pncg = bench_pncg(args, mesh, pots, dtype, dev, w)
-        except Exception as exc:  # pragma: no cover - the headline line must survive a failure of a secondary section
-            pncg = {"error": f"{type(exc).__name__}: {exc}"}
+            hvp = bench_hvp(args, wl, kinds, dev, world, flush, max_over_ranks, T_total, peak)
+        except Exception as exc:  # pragma: no cover
+            hvp = {"error": f"{type(exc).__name__}: {exc}"}
 
     clocks.__exit__(None, None, None)
+    # release the headline model before the secondary sections
+    del model, pots, sharded, res
+    if world == 1:
+        del adapter, out_block, grad, prod, fun
+    torch.cuda.empty_cache()
 
-    # ---- CPU baseline: the oracle on a bounded sample ----
+    # ---- config 2 (N = 1): 975,560 tets, operators + roofline + 200 PNCG iterations ----
+    config2 = None
+    if world == 1 and not args.no_config2:
+        try:
+            config2 = bench_config2(args, dtype, dev, w, flush, peak)
+        except Exception as exc:  # pragma: no cover
+            config2 = {"error": f"{type(exc).__name__}: {exc}"}
+
+    # ---- CPU baseline: the C restatement of the reference on a bounded sample, host cores of this box ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            val, Ts, dt, threads = time_oracle(mesh, u, p, kinds, min(T_total, 1_000_000), 5, 1)
+            a, b = sample_layers(n, 1)
+            np_dtype = np.float32 if args.dtype == "f32" else np.float64
+            val, Ts, dt, threads = time_oracle(host_sample(n, a, b), kinds, 5, 1, np_dtype)
             cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"first {Ts} tets of the same mesh, 5 evaluations (fun, grad, hess_prod passes per "
-                             f"potential), C restatement of the reference kernels (oracle/c), fp64"}
+                   "sample": f"hex layers [{a}, {b}) of the same cube = {Ts} tets, 5 evaluations (fun, grad, hess_prod passes "
+                             f"per potential), C restatement of the reference kernels (oracle/c), {args.dtype}"}
         except Exception as exc:  # pragma: no cover
             cpu = {"error": f"{type(exc).__name__}: {exc}"}
-
-    if args.sweep and rank == 0 and world == 1:
-        sweep(args, mesh, u, p, dtype, dev, flush)
-
-    # ---- experimental pair layout, in a time-limited subprocess (a kernel that has never run must not be able
-    #      to stall or crash the benchmark of the product layout) ----
-    probe = None
-    if rank == 0 and world == 1 and args.layout == "tet" and not args.no_probe:
-        cmd = [sys.executable, str(ROOT / "bench.py"), "--layout", "pair", "--steps", "10", "--warmup", "3", "--no-pncg",
-               "--no-cpu-baseline", "--no-probe", "--probe-parity", "--n", str(args.n), "--dtype", args.dtype,
-               "--potentials", args.potentials]
-        try:
-            pr = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
-            last = [ln for ln in pr.stdout.strip().splitlines() if ln.startswith("{")]
-            if pr.returncode == 0 and last:
-                d = json.loads(last[-1])
-                probe = {"status": "ran", "value": d["value"], "ms_per_step": d["ms_per_step"],
-                         "roofline_frac": d["roofline"]["frac"], "parity_vs_oracle": d.get("parity"),
-                         "e2e": (d.get("e2e") or {}).get("value"), "speedup_vs_tet_layout": d["value"] / value}
-            else:
-                probe = {"status": f"failed (rc {pr.returncode})", "stderr_tail": pr.stderr[-400:]}
-        except subprocess.TimeoutExpired:
-            probe = {"status": "timeout (240 s): killed"}
-        except Exception as exc:  # pragma: no cover
-            probe = {"status": f"not run ({type(exc).__name__}: {exc})"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": args.scaling if (world > 1 or args.slab) else "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": workload_name(args, mesh, kinds), "assembly": args.scatter, "layout": args.layout,
-                       "l2": "256 MiB flush write between timed steps" if not args.no_flush else "no flush",
-                       "parallelism": (f"{world} ranks x " + ("slab of hex layers, generated per rank" if args.slab else
-                                                               "contiguous Morton chunk of tets") +
-                                       f" (~{T_total // world} tets per "
-                                       f"GPU, {args.scaling} scaling); halo sum of grad+HVP (NCCL all-to-all of "
-                                       f"shared rows) + scalar all-reduce per step, "
-                                       f"{'replayed as one CUDA graph' if args.graph else 'plain launches'}; "
-                                       + (f"boundary tiles ({sharded.n_boundary_tiles} on rank 0) first, exchange "
-                                          f"overlapped with the interior tiles" if sharded.overlap else
-                                          "one element launch, then the exchange") +
-                                       (f" [{overlap_note}]" if overlap_note else ""))
-                       if world > 1 else "1 GPU"},
+            "config": {"workload": workload_name(n, kinds), "assembly": args.scatter,
+                       "l2": "256 MiB flush write between timed steps (working set per GPU >> 126 MB L2)" if not args.no_flush else "no flush",
+                       "setup": f"mesh, Morton order, tiling and static planes built on the GPU: {setup_s:.2f} s (slowest rank)",
+                       "parallelism": ("1 GPU" if world == 1 else
+                                       f"{world} ranks x slab of {n // world}+ hex layers (~{T_total // world} tets per GPU, STRONG "
+                                       f"scaling, fixed mesh); per step one element pass, then the halo sum of grad+HVP and the "
+                                       f"energy reduction "
+                                       + ("through peer memory over NVLink: one push + one pull kernel (apl_xchg_*)"
+                                          if args.transport == "peer" else
+                                          "as pack / NCCL all-to-all / unpack / all-reduce")
+                                       + ("; step replayed as one CUDA graph" if (world > 1 and graph is not None) else ""))},
+            "setup_s": setup_s,
             "clocks": clocks.summary(), "e2e": e2e,
-            "gpu_launches": args.steps * len(pots) * (2 if (world > 1 and sharded.overlap) else 1),
-            "roofline": roofline, "cpu_baseline": cpu, "pncg": pncg,
+            "gpu_launches": args.steps * launches_per_step,
+            "roofline": roofline, "parity": parity, "hvp": hvp, "cpu_baseline": cpu, "config2": config2,
+            "pncg": (config2 or {}).get("pncg") if isinstance(config2, dict) else None,
         }
-        if parity is not None:
-            line["parity"] = parity
-        if probe is not None:
-            line["experimental_pair_layout"] = probe
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_check(args, wl, res, kinds, dtype, dev, world, rank):
+    """Rank 0: gradient / HVP of the timed step on the grid planes whose sums are complete inside a 4-layer host sample
+    (for N > 1 the sample straddles rank 0's slab interface: its shared plane is halo-summed), and the energy of the
+    sample through a second GPU handle, against the C restatement of the reference (fp64)."""
+    import torch
+
+    from apple_b200 import _lib
+    from apple_b200.warp.model import WarpModel
+
+    if rank != 0:
+        return None
+    n = args.n
+    a, b = sample_layers(n, world)
+    sample = host_sample(n, a, b)
+    pots_o, _ = oracle_model(sample, kinds)
+    e_o, g_o, h_o = oracle_eval(pots_o, sample)
+    # planes a+1 .. b-1 have every incident tet inside the sample; rank 0 holds planes <= its upper interface
+    top = n if world == 1 else n // world
+    keep = (sample.layer > a) & (sample.layer < b) & (sample.layer <= top)
+    if a == 0:
+        keep |= sample.layer == 0
+    gid = sample.vgid[keep]
+    # rows of rank 0's result with those global ids
+    vg = wl.mesh.vertex_gid
+    order = torch.argsort(vg)
+    pos = torch.searchsorted(vg[order], torch.as_tensor(gid, device=dev))
+    rows = order[pos]
+    assert bool((vg[rows] == torch.as_tensor(gid, device=dev)).all())
+    rel = lambda x, y: float(np.abs(np.asarray(x, np.float64) - y).max() / np.abs(y).max())  # noqa: E731
+    out = {"grad": rel(res["grad"][rows].cpu().numpy(), g_o[keep]),
+           "hess_prod": rel(res["prod"][rows].cpu().numpy(), h_o[keep]),
+           "rows": int(keep.sum()), "planes": [int(x) for x in np.unique(sample.layer[keep])],
+           "halo_plane_included": bool(world > 1 and top in set(np.unique(sample.layer[keep]).tolist()))}
+    # energy: the sample as its own small model on this GPU
+    sw = SimpleNamespace(mesh=SimpleNamespace(cells=torch.as_tensor(sample.mesh.cells, device=dev),
+                                              points=torch.as_tensor(sample.mesh.points, device=dev)),
+                         mu=torch.as_tensor(sample.mesh.cell_data["mu"], dtype=dtype, device=dev),
+                         la=torch.as_tensor(sample.mesh.cell_data["lambda"], dtype=dtype, device=dev))
+    spots = device_potentials(sw, kinds, dtype, fuse=not args.no_fuse)
+    f = torch.zeros(1, dtype=dtype, device=dev)
+    WarpModel(spots).eval(_lib.OP_FUN, torch.as_tensor(sample.u, dtype=dtype, device=dev), None, fun=f)
+    out["energy"] = rel(f.cpu().numpy(), e_o)
+    out["against"] = (f"C restatement of the reference (oracle/c, fp64) on hex layers [{a}, {b}) = {sample.mesh.n_cells} tets; "
+                      f"tolerance of the north star: 1e-5 relative in fp32, 1e-10 in fp64")
+    out["within_tolerance"] = bool(max(out["grad"], out["hess_prod"], out["energy"]) < (1e-5 if dtype == torch.float32 else 1e-10))
+    return out
+
+
+def bench_e2e(args, wl, model, sharded, adapter, dtype, dev, w, T_total, flush, max_over_ranks, barrier, n_pots):
+    """Host (pinned) u, p in -> host energy, gradient, HVP out, copies inside the timed region; per rank its slab."""
+    import torch
+
+    from apple_b200 import _lib
+
+    V = wl.mesh.n_points
+    OPS = _lib.OP_FUN | _lib.OP_GRAD | _lib.OP_HESS_PROD
+    uh, ph = wl.u.cpu().pin_memory(), wl.p.cpu().pin_memory()
+    gh, hh = torch.empty((V, 3), dtype=dtype).pin_memory(), torch.empty((V, 3), dtype=dtype).pin_memory()
+    fh = torch.empty(1, dtype=dtype).pin_memory()
+
+    if sharded is None:
+        def step_streamed():
+            adapter.fun_grad_hess_prod_host(uh, ph, out=(fh, gh, hh))
+
+        def step_serial():
+            u_d = uh.to(dev, non_blocking=True); p_d = ph.to(dev, non_blocking=True)
+            f, g, h = adapter.fun_grad_hess_prod(u_d, p_d)
+            fh.copy_(f.reshape(1), non_blocking=True); gh.copy_(g, non_blocking=True); hh.copy_(h, non_blocking=True)
+    else:
+        def step_serial():
+            u_d = uh.to(dev, non_blocking=True); p_d = ph.to(dev, non_blocking=True)
+            r = sharded.eval(OPS, u_d, p_d)
+            fh.copy_(r["fun"].reshape(1), non_blocking=True); gh.copy_(r["grad"], non_blocking=True)
+            hh.copy_(r["prod"], non_blocking=True)
+        step_streamed = None
+
+    steps = max(3, min(args.steps, 10))
+
+    def time_it(fn):
+        for _ in range(2):
+            fn()
+        barrier()
+        tt = 0.0
+        for _ in range(steps):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            tt += a.elapsed_time(b)
+        return max_over_ranks(tt)
+
+    tt_serial = time_it(step_serial)
+    api, note, tt, launches = "serial", None, tt_serial, n_pots + (2 if sharded is not None else 0)
+    if step_streamed is not None:
+        ref = (fh.clone(), gh.clone(), hh.clone())
+        try:
+            fh.zero_(); gh.zero_(); hh.zero_()
+            tt_streamed = time_it(step_streamed)
+            err = max(float((x - y).abs().max() / y.abs().max()) for x, y in zip((fh, gh, hh), ref))
+            if err < 1e-4 and tt_streamed <= tt_serial:
+                api, tt, launches = "streamed", tt_streamed, 2 * n_pots
+            elif err < 1e-4:
+                note = f"streamed entry point verified but slower here ({tt_streamed / steps:.4f} ms per step); serial number reported"
+            else:
+                note = f"streamed entry point disagreed with the serial one (rel. err {err:.2e}); serial number reported"
+        except Exception as exc:  # pragma: no cover
+            note = f"streamed entry point failed ({type(exc).__name__}: {exc}); serial number reported"
+    return {"value": T_total * steps / (tt * 1e-3), "unit": UNIT,
+            "h2d_bytes_per_step": int(2 * V * 3 * w), "d2h_bytes_per_step": int(2 * V * 3 * w + w),
+            "bytes_are": "per rank (its slab)" if sharded is not None else "whole mesh",
+            "ms_per_step": tt / steps, "steps": steps,
+            "api": {"streamed": "WarpModelAdapter.fun_grad_hess_prod_host(u_host, p_host, out=host tensors): copies "
+                                "overlapped with a fun+grad pass and a hess_prod pass on side streams",
+                    "serial": ("u.to(device); p.to(device); " + ("ShardedOperators.eval" if sharded is not None else
+                               "WarpModelAdapter.fun_grad_hess_prod") + "; copy_ to host")}[api],
+            "gpu_launches_per_step": launches, "serial_ms_per_step": tt_serial / steps, "note": note}
+
+
+def bench_hvp(args, wl, kinds, dev, world, flush, max_over_ranks, T_total, peak):
+    """hess_prod alone (the kernel an adjoint solve repeats), fp32 and fp64, same mesh and partition."""
+    import torch
+
+    from apple_b200 import _lib
+    from apple_b200.warp.model import WarpModel
+
+    out = {}
+    V, T_local = wl.mesh.n_points, wl.mesh.n_cells
+    for name, dt, w in (("f32", torch.float32, 4), ("f64", torch.float64, 8)):
+        w2 = SimpleNamespace(shard=wl.shard, mesh=wl.mesh, mu=wl.mu.to(dt), la=wl.la.to(dt))
+        pots = device_potentials(w2, kinds, dt, fuse=not args.no_fuse)
+        model = WarpModel(pots)
+        u, p = wl.u.to(dt).contiguous(), wl.p.to(dt).contiguous()
+        if world > 1:
+            from apple_b200.dist import ShardedOperators
+
+            sh = ShardedOperators(model, wl.shard, dev, dt, transport=args.transport, overlap=False)
+            fn = lambda: sh.eval(_lib.OP_HESS_PROD, u, p)  # noqa: E731
+        else:
+            prod = torch.zeros((V, 3), dtype=dt, device=dev)
+
+            def fn():
+                prod.zero_()
+                model.eval(_lib.OP_HESS_PROD, u, p, prod=prod, zero=False)
+        for _ in range(3):
+            flush(); fn()
+        torch.cuda.synchronize()
+        reps, tt = max(5, min(args.steps, 10)), 0.0
+        for _ in range(reps):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            tt += a.elapsed_time(b)
+        dtm = max_over_ranks(tt / reps) * 1e-3
+        bpt = sum(bytes_per_tet(k.split("+"), w, V / max(T_local, 1), 9) for k in pots)   # read u, p; write Hp
+        out[name] = {"value": T_total / dtm, "unit": "tets/s", "ms_per_step": dtm * 1e3, "bytes_per_tet": bpt,
+                     "gbs_per_gpu": bpt * T_local / dtm / 1e9, "roofline_frac": bpt * T_local / dtm / 1e9 / peak}
+        del pots, model
+        torch.cuda.empty_cache()
+    out["note"] = ("one hess_prod evaluation of the whole model per step (halo sum included for N > 1), CUDA events, L2 "
+                   "flushed; algorithmic bytes = 16 + 9w + materials + (V/T) 9w per tet")
+    return out
+
+
+def bench_config2(args, dtype, dev, w, flush, peak):
+    """BASELINE.json configs[1] on one GPU: 58^3 x 5 tets, SNH + ARAP fused, operators + 200 PNCG iterations."""
+    import torch
+
+    from apple_b200 import _lib
+    from apple_b200.warp.fem import fuse_potentials
+    from apple_b200.warp.model import WarpModel
+    from apple_b200.warp.model._adapter import zeros_block
+
+    kinds = args.potentials.split(",")
+    mesh, u, p = build_mesh(N_CONFIG2)
+    T, V = mesh.n_cells, mesh.n_points
+    pots = {k: cuda_potential(k, mesh, dtype, name=k) for k in kinds}
+    if not args.no_fuse:
+        pots = fuse_potentials(pots)
+    model = WarpModel(pots)
+    ud = torch.as_tensor(u, dtype=dtype, device=dev).contiguous()
+    pd = torch.as_tensor(p, dtype=dtype, device=dev).contiguous()
+    OPS = _lib.OP_FUN | _lib.OP_GRAD | _lib.OP_HESS_PROD
+    out_block, (grad, prod), (fun,) = zeros_block(V, 2, 1, dtype, dev)
+
+    def step():
+        out_block.zero_()
+        model.eval(OPS, ud, pd, fun=fun, grad=grad, prod=prod, zero=False)
+
+    for _ in range(5):
+        flush(); step()
+    torch.cuda.synchronize()
+    tt = 0.0
+    for _ in range(args.steps):
+        flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); step(); b.record()
+        torch.cuda.synchronize()
+        tt += a.elapsed_time(b)
+    ms = tt / args.steps
+    bpt = sum(bytes_per_tet(k.split("+"), w, V / T, 12) for k in pots)
+    out = {"workload": f"cube {N_CONFIG2}^3x5 = {T} tets / {V} verts, {'+'.join(kinds)}, fused energy+grad+HVP (BASELINE.json configs[1])",
+           "value": T / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "bytes_per_tet": bpt,
+           "roofline_frac": bpt * T / (ms * 1e-3) / 1e9 / peak}
+    if not args.no_pncg:
+        try:
+            out["pncg"] = bench_pncg(args, mesh, pots, dtype, dev, w)
+        except Exception as exc:  # pragma: no cover
+            out["pncg"] = {"error": f"{type(exc).__name__}: {exc}"}
+    if args.sweep:
+        sweep(args, mesh, u, p, dtype, dev, flush)
+    return out
 
 
 def bench_pncg(args, mesh, pots, dtype, dev, w):
@@ -650,7 +799,7 @@ def bench_pncg(args, mesh, pots, dtype, dev, w):
     for pot in pots.values():
         builder.add_potential(pot)
     model = builder.finalize()
-    h = 1.0 / args.n
+    h = 1.0 / N_CONFIG2
     X = mesh.points
     u0 = np.ascontiguousarray(0.05 * h * np.sin(7.0 * X[:, [1, 2, 0]] + 0.3))
     u0[fixed] = 0.0
@@ -707,7 +856,7 @@ def sweep(args, mesh, u, p, dtype, dev, flush):
                 outs = {k: torch.zeros((V, ld), dtype=dt, device=dev) for k in ("grad", "diag", "prod")}
                 fun = torch.zeros(1, dtype=dt, device=dev); quad = torch.zeros(1, dtype=dt, device=dev)
                 for ops in (1, 2, 4, 8, 16, 7, 11, 15):
-                    for scatter in ((0,) if args.layout == "pair" else (0, 2, 1)):
+                    for scatter in (0, 2, 1):
                         ts = []
                         for i in range(8):
                             flush()

@@ -57,14 +57,6 @@ extern "C" {
 #define APL_SCATTER_ATOMIC 1 /* one thread per tet, direct gathers and 12 REDs per field (reference-like) */
 #define APL_SCATTER_TILE_SIMPLE 2 /* same tiles without the producer warp / bulk-copy pipeline */
 
-/* How the element kernels walk the mesh (chosen when a handle is created, see apl_set_layout):
- * TET:  one consumer thread per tet (4 corner gathers, 4 reduction slots per tet);
- * PAIR: one consumer thread per pair of tets that share a face (5 corner gathers / slots per 2 tets; a tet
- *       without a partner in its tile is paired with a zero-volume clone of itself).  EXPERIMENTAL: only
- *       APL_SCATTER_TILE is implemented for it. */
-#define APL_LAYOUT_TET 0
-#define APL_LAYOUT_PAIR 1
-
 typedef struct apl_fem apl_fem_t;   /* one FEM potential: replaces WarpPotentialFem (warp/fem/_base.py:39) */
 typedef struct apl_pncg apl_pncg_t; /* fused PNCG workspace (liblaf.peach.optim.PNCG, external to the reference) */
 
@@ -117,32 +109,21 @@ int apl_fem_create_from_mesh(int kind, int dtype, int64_t n_cells, int64_t n_poi
                              const void* activation, const void* fraction2, const void* mu2, int morton, int device,
                              apl_fem_t** out);
 
-/* Layout of the handles created AFTERWARDS (process-wide; default APL_LAYOUT_TET).  No reference counterpart. */
-int apl_set_layout(int layout);
-int apl_fem_layout(const apl_fem_t* fem);
-
 /* info[0..9] = n_cells, n_points, n_tiles, length of tile_verts, static device bytes,
- *              kind, dtype, device, length of tile_voff, number of packed tet positions
- *              (n_cells for APL_LAYOUT_TET; 2 x the number of pair items for APL_LAYOUT_PAIR) */
+ *              kind, dtype, device, length of tile_voff, number of packed tet positions (= n_cells) */
 int apl_fem_info(const apl_fem_t* fem, int64_t info[10]);
 
 /* Copies of the host tables (sizes from apl_fem_info); any pointer may be NULL.
  *   tiles      int32 (n_tiles,6): tet_start, n_tets, vert_start, n_verts, voff_start, 0
  *   order      int64 (info[9],)  : packed tet position -> caller's cell index
- *   conn       uint8 (n_cells,4) : tile-local vertex id per corner (packed order); PAIR layout: (info[9]/2, 8),
- *                                  entries 0..4 = shared face s0 s1 s2, apex of the first, apex of the second tet
- *   slots      uint16(n_cells,4) : in-tile reduction slot per corner (packed order); PAIR layout: (info[9]/2, 8)
+ *   conn       uint8 (n_cells,4) : tile-local vertex id per corner (packed order)
+ *   slots      uint16(n_cells,4) : in-tile reduction slot per corner (packed order)
  *   tile_verts int32 (info[3])   : global vertex id per tile-local id, from vert_start
  *   tile_voff  uint16(info[8])   : per tile, n_verts+1 entries starting at voff_start: bits 0..11 first slot of
  *                                  the vertex's range (reduce order), bits 12..15 unused pad slots after it
  *   tile_vperm uint8 (info[3])   : per tile, the local ids in reduce order (groups of 16 by decreasing valence) */
 int apl_fem_host_tables(const apl_fem_t* fem, int32_t* tiles, int64_t* order, uint8_t* conn,
                         uint16_t* slots, int32_t* tile_verts, uint16_t* tile_voff, uint8_t* tile_vperm);
-/* Per packed tet position (info[9] entries each; either pointer may be NULL):
- *   cperm uint8: corner order used by the packed record, new corner k = caller's corner (cperm >> 2k) & 3
- *   clone uint8: 1 = zero-volume copy of a tet (fills a pair item), contributes nothing */
-int apl_fem_host_corner_tables(const apl_fem_t* fem, uint8_t* cperm, uint8_t* clone);
-
 /* Host-only handles (device = -1): copy of the packed static planes, [n_planes][plane_stride] 16-byte
  * vectors in packed cell order (record = Dm^-1 (9), dV, mu, lambda, activation (6) / second potential);
  * `planes` may be NULL to query the sizes. */
@@ -212,6 +193,34 @@ int apl_halo_pack(int dtype, int64_t n, const int64_t* index, int nf, const void
 int apl_halo_unpack(int dtype, int64_t n_shared, const int64_t* shared, const int32_t* row_ptr,
                     const int64_t* src, int nf, void* f0, void* f1, void* f2, int ld, const void* recv,
                     void* stream);
+
+/* ---- halo sums through PEER MEMORY over NVLink / NVSwitch (new functionality: the reference is single-GPU) --------
+ * Replaces pack -> NCCL all-to-all -> unpack -> NCCL all-reduce (four host-launched operations) by two small kernels
+ * with a device-side hand-shake; results are bit-identical to apl_halo_pack / apl_halo_unpack with the same plan.
+ * One process per GPU of one node.  Setup: every rank creates its handle, publishes apl_xchg_ipc_handle (64 bytes)
+ * to the other ranks through any host channel, and maps theirs with apl_xchg_connect (handles: world x 64 bytes in
+ * rank order, the own entry is ignored).  The plan arrays are DEVICE arrays owned by the caller (they must outlive
+ * the handle): row i of the send list is this rank's partial on local vertex send_index[i], stored into row
+ * send_row[i] of rank send_peer[i]'s receive buffer; (shared, row_ptr, src) is the CSR of apl_halo_unpack.
+ *   apl_xchg_push: stores the shared rows of up to 3 fields (leading dimension ld) and up to 8 partial scalars
+ *                  (dtype, e.g. this rank's energy) into the peers' buffers and publishes the epoch.
+ *   apl_xchg_pull: waits on the device until every rank's push of this epoch has landed, then sums the partials of
+ *                  every shared vertex in ascending rank order into f0..f2 and the scalars, in rank order, into scal
+ *                  (overwritten with the global sums: identical bits on every rank).
+ * Every rank must call push and pull the same number of times with the same nf / n_scal (collective semantics);
+ * push and pull of one exchange may be enqueued on different streams as long as pull is ordered after push. */
+typedef struct apl_xchg apl_xchg_t;
+int apl_xchg_create(int world, int rank, int device, int64_t max_recv_rows, apl_xchg_t** out);
+void apl_xchg_destroy(apl_xchg_t* x);
+int apl_xchg_ipc_handle(apl_xchg_t* x, void* handle64);
+int apl_xchg_connect(apl_xchg_t* x, const void* handles);
+int apl_xchg_set_plan(apl_xchg_t* x, int64_t n_send, const int64_t* send_index, const int32_t* send_peer,
+                      const int64_t* send_row, int64_t n_shared, const int64_t* shared, const int32_t* row_ptr,
+                      const int64_t* src);
+int apl_xchg_push(apl_xchg_t* x, int dtype, int nf, const void* f0, const void* f1, const void* f2, int ld,
+                  const void* scal, int n_scal, void* stream);
+int apl_xchg_pull(apl_xchg_t* x, int dtype, int nf, void* f0, void* f1, void* f2, int ld, void* scal, int n_scal,
+                  void* stream);
 
 /* ---- fused PNCG workspace -------------------------------------------------------------------------
  * The optimizer the reference uses (liblaf.peach.optim.PNCG) is external to /root/reference; what is

@@ -23,7 +23,21 @@
 #include <string.h>
 #include <unistd.h>
 
+/* -DORACLE_F32 builds the same restatement in single precision (liboracle_f32.so): the reference is dtype-generic
+ * (JAX x64 flag, warp/fem/_base.py:100-104), and bench.py's reference arm runs in the dtype of the GPU arm. */
+#ifdef ORACLE_F32
+typedef float real;
+typedef uint32_t real_bits;
+#define REAL_TINY 1e-30f      /* |a_pq| below this: skip the Jacobi rotation */
+#define REAL_SMALL 1e-18f     /* column norm below this: degenerate direction */
+#define REAL_OFF_TOL 1e-13f   /* off-diagonal mass relative to trace^2 at convergence */
+#else
 typedef double real;
+typedef uint64_t real_bits;
+#define REAL_TINY 1e-300
+#define REAL_SMALL 1e-150
+#define REAL_OFF_TOL 1e-34
+#endif
 
 enum { KIND_SNH = 0, KIND_ARAP = 1, KIND_MUSCLE = 2 };
 
@@ -116,10 +130,10 @@ static void svd3_rv(real F[3][3], real U[3][3], real s[3], real V[3][3]) {
     for (int sweep = 0; sweep < 30; ++sweep) {
         real off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
         real tr = A[0][0] + A[1][1] + A[2][2];
-        if (off <= 1e-34 * tr * tr) break;
+        if (off <= REAL_OFF_TOL * tr * tr) break;
         for (int p = 0; p < 2; ++p)
             for (int q = p + 1; q < 3; ++q) {
-                if (fabs(A[p][q]) < 1e-300) continue;
+                if (fabs(A[p][q]) < REAL_TINY) continue;
                 real theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
                 real t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                 real c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
@@ -150,11 +164,11 @@ static void svd3_rv(real F[3][3], real U[3][3], real s[3], real V[3][3]) {
     real b0[3], b1[3], b2[3], u0[3], u1[3], u2[3];
     col(B, 0, b0); col(B, 1, b1); col(B, 2, b2);
     real n0 = sqrt(b0[0] * b0[0] + b0[1] * b0[1] + b0[2] * b0[2]);
-    if (n0 > 1e-150) { for (int i = 0; i < 3; ++i) u0[i] = b0[i] / n0; } else { u0[0] = 1; u0[1] = u0[2] = 0; n0 = 0; }
+    if (n0 > REAL_SMALL) { for (int i = 0; i < 3; ++i) u0[i] = b0[i] / n0; } else { u0[0] = 1; u0[1] = u0[2] = 0; n0 = 0; }
     real d = u0[0] * b1[0] + u0[1] * b1[1] + u0[2] * b1[2];
     for (int i = 0; i < 3; ++i) b1[i] -= d * u0[i];
     real n1 = sqrt(b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2]);
-    if (n1 > 1e-150) { for (int i = 0; i < 3; ++i) u1[i] = b1[i] / n1; }
+    if (n1 > REAL_SMALL) { for (int i = 0; i < 3; ++i) u1[i] = b1[i] / n1; }
     else {
         real e[3] = {0, 0, 0}; e[fabs(u0[0]) < 0.6 ? 0 : 1] = 1; cross(u0, e, u1);
         real n = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
@@ -280,13 +294,13 @@ static void hess_prod_cell(const pot_t* P, ctx_t* x, real pc[4][3], real out[4][
 }
 
 static void atomic_add(real* addr, real val) { /* wp.atomic_add on the CPU */
-    uint64_t* p = (uint64_t*)addr;
-    uint64_t old = __atomic_load_n(p, __ATOMIC_RELAXED), neu;
+    real_bits* p = (real_bits*)addr;
+    real_bits old = __atomic_load_n(p, __ATOMIC_RELAXED), neu;
     do {
         real f;
-        memcpy(&f, &old, 8);
+        memcpy(&f, &old, sizeof(real));
         f += val;
-        memcpy(&neu, &f, 8);
+        memcpy(&neu, &f, sizeof(real));
     } while (!__atomic_compare_exchange_n(p, &old, neu, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
 }
 

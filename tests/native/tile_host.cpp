@@ -1,6 +1,5 @@
 // TEST-ONLY harness: compiles apple_b200/csrc/tile_logic.cuh (the consumer-side logic of the element kernels:
-// record / connectivity decoding, corner gather, slot stores of the TET and the PAIR layout, per-lane slot
-// reduction, parked sums) for the HOST and replays it thread by thread, tile by tile, on the packed tables of a
+// record / connectivity decoding, corner gather, slot stores, per-lane slot reduction) for the HOST and replays it thread by thread, tile by tile, on the packed tables of a
 // host-only handle.  What the GPU adds on top -- the producer's bulk copies, the mbarriers, the half-warp
 // shuffle and the global REDs -- is emulated here in the obvious way.  Never part of the product library.
 #include <cstdint>
@@ -10,7 +9,7 @@
 
 using namespace apl;
 
-template <typename T, int KIND, int OPS, int LAYOUT>
+template <typename T, int KIND, int OPS>
 static void run(int64_t n_tiles, const int32_t* tiles, const uint8_t* conn, const uint16_t* slots,
                 const int32_t* tile_verts, const uint16_t* tile_voff, const uint8_t* tile_vperm, const T* planes,
                 int64_t plane_stride, const T* u, const T* p, double alpha, T* grad, T* diag, T* prod, double* fun, double* quad) {
@@ -18,9 +17,8 @@ static void run(int64_t n_tiles, const int32_t* tiles, const uint8_t* conn, cons
     const bool axpy = alpha != 0.0;   // line-search trial point u + alpha p formed in the gather (PNCG pass A)
     constexpr int NOUT = Cfg::NOUT, SS = Cfg::SS;
     constexpr int NREC = RecSize<KIND>::value;
-    constexpr bool kPair = LAYOUT == APL_LAYOUT_PAIR;
-    constexpr int NC = kPair ? kTileTets / 2 : kTileTets;                 // consumer threads
-    constexpr int NSLOTS = kPair ? kSlotsAllocPair : kSlotsAlloc;
+    constexpr int NC = kTileTets;                 // consumer threads
+    constexpr int NSLOTS = kSlotsAlloc;
     constexpr int VEC = 16 / (int)sizeof(T);
     std::vector<T> vbuf((size_t)kTileVerts * (Cfg::VB > 8 ? Cfg::VB : 8) + 16), sl((size_t)NSLOTS * (SS > 0 ? SS : 1) + 16);
     double e_acc = 0, q_acc = 0;
@@ -39,27 +37,12 @@ static void run(int64_t n_tiles, const int32_t* tiles, const uint8_t* conn, cons
             us[4 * v + 3] = ps[4 * v + 3] = (T)0;
         }
         for (auto& x : sl) x = (T)(0.0 / 0.0);   // NaN: a slot that is read without having been written shows up
-        // compute phase: one consumer thread per tet / per pair
+        // compute phase: one consumer thread per tet
         auto load_rec = [&](int64_t pos, Rec<T, NREC>& r) {
             for (int k = 0; k < Rec<T, NREC>::NPL; ++k)
                 for (int j = 0; j < VEC; ++j) r.s[k * VEC + j] = planes[((size_t)k * plane_stride + pos) * VEC + j];
         };
-        if constexpr (kPair) {
-            const int n_items = n_tets >> 1;
-            for (int tid = 0; tid < NC; ++tid) {
-                if (tid >= n_items) continue;
-                Rec<T, NREC> ra, rb;
-                load_rec(ts + tid, ra);
-                load_rec(ts + n_items + tid, rb);
-                const uint8_t* c = conn + 8 * ((size_t)ts / 2 + tid);
-                const uint16_t* s = slots + 8 * ((size_t)ts / 2 + tid);
-                uint2 c8;
-                uint4 s8;
-                std::memcpy(&c8, c, 8);
-                std::memcpy(&s8, s, 16);
-                tile_compute_pair<T, KIND, OPS>(ra.s, rb.s, c8, s8, us, ps, axpy, (T)alpha, sl.data(), e_acc, q_acc);
-            }
-        } else {
+        {
             for (int tid = 0; tid < NC; ++tid) {
                 if (tid >= n_tets) continue;
                 Rec<T, NREC> r;
@@ -72,7 +55,8 @@ static void run(int64_t n_tiles, const int32_t* tiles, const uint8_t* conn, cons
             }
         }
         if constexpr (NOUT > 0) {
-            // reduce phase: warp by warp, iteration by iteration; lanes l and l + 16 exchange through the shuffle
+            // reduce phase: warp by warp, iteration by iteration; lanes l and l + 16 exchange through the shuffle and
+            // the sums go straight to global memory (fem_kernels.cuh: tile_reduce_flush)
             const unsigned char* vperm = tile_vperm + vs;
             const unsigned short* voff = tile_voff + vo;
             for (int warp = 0; warp < NC / 32; ++warp)
@@ -84,34 +68,29 @@ static void run(int64_t n_tiles, const int32_t* tiles, const uint8_t* conn, cons
                         tile_reduce_lane<T, OPS, NSLOTS>(half, t0 + (tid & 15), n_verts, vperm, voff, sl.data(), v[lane], acc[lane]);
                     }
                     for (int lane = 0; lane < 16; ++lane) {
+                        if (t0 + lane >= n_verts) continue;
                         T sum[3 * NOUT];
                         for (int j = 0; j < 3 * NOUT; ++j) sum[j] = acc[lane][j] + acc[lane + 16][j];
-                        if (t0 + lane < n_verts) tile_reduce_park<T, OPS>(vbuf.data(), v[lane], sum);
+                        const int64_t gv = tile_verts[vs + v[lane]];
+                        int k = 0;
+                        if constexpr (Cfg::kGrad) { for (int i = 0; i < 3; ++i) grad[3 * gv + i] += sum[k + i]; k += 3; }
+                        if constexpr (Cfg::kDiag) { for (int i = 0; i < 3; ++i) diag[3 * gv + i] += sum[k + i]; k += 3; }
+                        if constexpr (Cfg::kProd) { for (int i = 0; i < 3; ++i) prod[3 * gv + i] += sum[k + i]; k += 3; }
                     }
                 }
-            // flush phase: one RED per vertex and field
-            for (int v = 0; v < n_verts; ++v) {
-                T acc[3 * NOUT];
-                tile_flush_read<T, OPS>(vbuf.data(), v, acc);
-                const int64_t gv = tile_verts[vs + v];
-                int k = 0;
-                if constexpr (Cfg::kGrad) { for (int i = 0; i < 3; ++i) grad[3 * gv + i] += acc[k + i]; k += 3; }
-                if constexpr (Cfg::kDiag) { for (int i = 0; i < 3; ++i) diag[3 * gv + i] += acc[k + i]; k += 3; }
-                if constexpr (Cfg::kProd) { for (int i = 0; i < 3; ++i) prod[3 * gv + i] += acc[k + i]; k += 3; }
-            }
         }
     }
     *fun += e_acc;
     *quad += q_acc;
 }
 
-template <typename T, int KIND, int LAYOUT>
+template <typename T, int KIND>
 static int by_ops(int ops, int64_t n_tiles, const int32_t* tiles, const uint8_t* conn, const uint16_t* slots,
                   const int32_t* tv, const uint16_t* voff, const uint8_t* vperm, const void* planes, int64_t stride,
                   const void* u, const void* p, double alpha, void* grad, void* diag, void* prod, double* fun, double* quad) {
 #define GO(O)                                                                                                    \
-    run<T, KIND, O, LAYOUT>(n_tiles, tiles, conn, slots, tv, voff, vperm, (const T*)planes, stride, (const T*)u,  \
-                            (const T*)p, alpha, (T*)grad, (T*)diag, (T*)prod, fun, quad)
+    run<T, KIND, O>(n_tiles, tiles, conn, slots, tv, voff, vperm, (const T*)planes, stride, (const T*)u,  \
+                    (const T*)p, alpha, (T*)grad, (T*)diag, (T*)prod, fun, quad)
     switch (ops) {
         case 11: GO(11); return 0;
         case 7: GO(7); return 0;
@@ -123,24 +102,20 @@ static int by_ops(int ops, int64_t n_tiles, const int32_t* tiles, const uint8_t*
 #undef GO
 }
 
-// layout: APL_LAYOUT_*; kind: APL_KIND_*; ops in {2, 7, 11, 15, 16}; alpha != 0 evaluates at u + alpha p (ops without
+// kind: APL_KIND_*; ops in {2, 7, 11, 15, 16}; alpha != 0 evaluates at u + alpha p (ops without
 // hess_prod / hess_quad only, as in PNCG's trial passes).  Outputs are accumulated (caller zeroes).
-extern "C" int tile_emulate(int layout, int kind, int is_f64, int ops, int64_t n_tiles, const int32_t* tiles,
+extern "C" int tile_emulate(int kind, int is_f64, int ops, int64_t n_tiles, const int32_t* tiles,
                             const uint8_t* conn, const uint16_t* slots, const int32_t* tv, const uint16_t* voff,
                             const uint8_t* vperm, const void* planes, int64_t stride, const void* u, const void* p,
                             double alpha, void* grad, void* diag, void* prod, double* fun, double* quad) {
 #define ARGS ops, n_tiles, tiles, conn, slots, tv, voff, vperm, planes, stride, u, p, alpha, grad, diag, prod, fun, quad
-#define KINDS(T, L)                                                           \
-    switch (kind) {                                                           \
-        case APL_KIND_SNH: return by_ops<T, APL_KIND_SNH, L>(ARGS);           \
-        case APL_KIND_ARAP: return by_ops<T, APL_KIND_ARAP, L>(ARGS);         \
-        case APL_KIND_SNH_ARAP: return by_ops<T, APL_KIND_SNH_ARAP, L>(ARGS); \
-        default: return by_ops<T, APL_KIND_SNH_MUSCLE, L>(ARGS);              \
+#define KINDS(T)                                                           \
+    switch (kind) {                                                        \
+        case APL_KIND_SNH: return by_ops<T, APL_KIND_SNH>(ARGS);           \
+        case APL_KIND_ARAP: return by_ops<T, APL_KIND_ARAP>(ARGS);         \
+        case APL_KIND_SNH_ARAP: return by_ops<T, APL_KIND_SNH_ARAP>(ARGS); \
+        default: return by_ops<T, APL_KIND_SNH_MUSCLE>(ARGS);              \
     }
-    if (layout == APL_LAYOUT_PAIR) {
-        if (is_f64) { KINDS(double, APL_LAYOUT_PAIR) } else { KINDS(float, APL_LAYOUT_PAIR) }
-    } else {
-        if (is_f64) { KINDS(double, APL_LAYOUT_TET) } else { KINDS(float, APL_LAYOUT_TET) }
-    }
+    if (is_f64) { KINDS(double) } else { KINDS(float) }
     return -1;
 }

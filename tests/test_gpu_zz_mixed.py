@@ -1,7 +1,6 @@
 """GPU: apl_fem_mixed_derivative_prod (d/dq [grad E . p] per cell; the reference's historical
-model.mixed_derivative_prod) in both layouts against central differences of the oracle.  The closed forms are
-validated on the CPU (tests/test_native_cpu.py); the kernel is a plain one-thread-per-tet gather written when no GPU
-was available, hence the non-strict xfail and the late file name."""
+model.mixed_derivative_prod) against central differences of the oracle.  The closed forms are also validated on the
+CPU (tests/test_native_cpu.py)."""
 
 import contextlib
 import copy
@@ -12,24 +11,17 @@ import torch
 
 from helpers import KINDS, cuda_potential, make_case, oracle_potential
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="kernel written without a GPU: first run")]
+pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("layout", [0, 1], ids=["tet", "pair"])
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-6), (torch.float32, 2e-4)], ids=["f64", "f32"])
 @pytest.mark.parametrize("kind", KINDS)
-def test_mixed_derivative_prod_matches_finite_differences(native_lib, kind, dtype, tol, layout):
-    from apple_b200 import config
+def test_mixed_derivative_prod_matches_finite_differences(native_lib, kind, dtype, tol):
     from apple_b200.warp.model import WarpModel
 
     mesh, u, p = make_case(n=5, seed=2, amp=0.15)
     ora = oracle_potential(kind, mesh)
-    old = config.layout
-    config.layout = layout
-    try:
-        pot = cuda_potential(kind, mesh, dtype, name=kind)
-    finally:
-        config.layout = old
+    pot = cuda_potential(kind, mesh, dtype, name=kind)
     ud = torch.as_tensor(u, dtype=dtype, device="cuda"); pd = torch.as_tensor(p, dtype=dtype, device="cuda")
     got = WarpModel({kind: pot}).mixed_derivative_prod(ud, pd)[kind]
     torch.cuda.synchronize()

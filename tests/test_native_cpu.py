@@ -466,100 +466,6 @@ def test_mark_boundary_partitions_the_tile_headers(native_lib):
     native_lib.apl_fem_destroy(h)
 
 
-def _pair_tables(native_lib, mesh, dtype_code, dhdX, dV, mu, la):
-    """Host-only handle in the PAIR layout and all of its tables."""
-    from apple_b200 import _lib
-
-    T, V = mesh.n_cells, mesh.n_points
-    P = _lib.host_ptr
-    h = ctypes.c_void_p()
-    cells = np.ascontiguousarray(mesh.cells, dtype=np.int32); pts = np.ascontiguousarray(mesh.points)
-    assert native_lib.apl_set_layout(_lib.LAYOUT_PAIR) == 0
-    try:
-        rc = native_lib.apl_fem_create(0, dtype_code, T, V, P(cells), P(dhdX), P(dV), P(mu), P(la), None, P(pts), -1,
-                                       ctypes.byref(h))
-    finally:
-        native_lib.apl_set_layout(_lib.LAYOUT_TET)
-    assert rc == 0, native_lib.apl_last_error()
-    assert native_lib.apl_fem_layout(h) == _lib.LAYOUT_PAIR
-    info = (ctypes.c_int64 * 10)(); native_lib.apl_fem_info(h, info)
-    nt, nv, nvo, npk = info[2], info[3], info[8], info[9]
-    tiles = np.zeros((nt, 6), np.int32); order = np.zeros(npk, np.int64)
-    conn = np.zeros((npk // 2, 8), np.uint8); slots = np.zeros((npk // 2, 8), np.uint16)
-    tv = np.zeros(nv, np.int32); voff = np.zeros(nvo, np.uint16); vperm = np.zeros(nv, np.uint8)
-    cperm = np.zeros(npk, np.uint8); clone = np.zeros(npk, np.uint8)
-    native_lib.apl_fem_host_tables(h, P(tiles), P(order), P(conn), P(slots), P(tv), P(voff), P(vperm))
-    native_lib.apl_fem_host_corner_tables(h, P(cperm), P(clone))
-    npl, stride = ctypes.c_int64(), ctypes.c_int64()
-    native_lib.apl_fem_host_planes(h, None, ctypes.byref(npl), ctypes.byref(stride))
-    planes = np.zeros((npl.value, stride.value, 16 // dhdX.dtype.itemsize), dhdX.dtype)
-    native_lib.apl_fem_host_planes(h, P(planes), None, None)
-    native_lib.apl_fem_destroy(h)
-    return tiles, order, conn, slots, tv, voff, vperm, cperm, clone, planes
-
-
-def test_pair_layout_tables_assemble_the_oracle_gradient(native_lib):
-    """APL_LAYOUT_PAIR (one consumer thread per pair of face-adjacent tets): numpy emulation of what the pair
-    kernel does with the tables -- 5 gathered vertices per item, two tets evaluated in the packed corner order
-    (shared face first), contributions of the shared corners added, 5 slots per item, slot reduction and flush as
-    in the TET layout -- reproduces the oracle gradient; every cell appears exactly once as a non-clone; the packed
-    record holds the rows of dhdX in the packed corner order."""
-    from apple_b200 import _lib
-    from oracle import region
-
-    mesh, u, _ = make_case(n=7, seed=5, morton=False)
-    ora = oracle_potential("snh", mesh)
-    dhdX, dV = region.compute_grad(mesh.points, mesh.cells, mesh.cell_data["Fraction"])
-    mu, la = mesh.cell_data["mu"], mesh.cell_data["lambda"]
-    tiles, order, conn, slots, tv, voff, vperm, cperm, clone, planes = _pair_tables(native_lib, mesh, _lib.F64, dhdX, dV, mu, la)
-    T = mesh.n_cells
-    real = clone == 0
-    assert sorted(order[real].tolist()) == list(range(T))            # every cell exactly once, clones aside
-    perm = np.stack([(cperm >> (2 * k)) & 3 for k in range(4)], axis=1).astype(int)      # (n_packed, 4)
-    assert (np.sort(perm, axis=1) == np.arange(4)).all()
-    # packed record == reference arrays in the packed corner order, zero volume for clones
-    rec = planes.transpose(1, 0, 2).reshape(planes.shape[1], -1)[:order.size]
-    rows = dhdX[order][np.arange(order.size)[:, None], perm[:, 1:]]                      # rows 1..3 of the packed order
-    np.testing.assert_array_equal(rec[:, :9], rows.reshape(-1, 9))
-    np.testing.assert_array_equal(rec[:, 9], np.where(real, dV[order], 0.0))
-    np.testing.assert_array_equal(rec[:, 10], mu[order])
-    # emulation of the pair kernel's assembly
-    elem = ora.elem_grad(u)                                           # (T, 4, 3) per-corner contributions, caller's corner order
-    contrib = elem[order][np.arange(order.size)[:, None], perm] * real[:, None, None]    # packed corner order; clones: 0
-    out = np.zeros_like(u)
-    n_paired = 0
-    for (ts, n, vs, nv, vo, nslots) in tiles:
-        assert ts % 4 == 0 and n % 4 == 0 and n <= 256                # items come in even numbers: 16-byte aligned rows
-        verts = tv[vs:vs + nv]
-        it0, ni = ts // 2, n // 2
-        c5 = conn[it0:it0 + ni, :5].astype(int); s5 = slots[it0:it0 + ni, :5].astype(int)
-        A, B = np.arange(ts, ts + ni), np.arange(ts + ni, ts + n)     # the tile's first tets, then its second tets
-        cells_p = mesh.cells[order][np.arange(order.size)[:, None], perm]                # vertices in packed corner order
-        assert np.array_equal(verts[c5[:, :4]], cells_p[A])           # gather of tet A: (s0, s1, s2, apex A)
-        assert np.array_equal(verts[c5[:, [0, 1, 2, 4]]], cells_p[B])  # gather of tet B: (s0, s1, s2, apex B)
-        item = np.zeros((ni, 5, 3))
-        item[:, :3] = contrib[A][:, :3] + contrib[B][:, :3]
-        item[:, 3] = contrib[A][:, 3]
-        item[:, 4] = contrib[B][:, 3]
-        assert len(set(s5.ravel().tolist())) == 5 * ni
-        buf = np.full((nslots, 3), np.nan)
-        buf[s5.ravel()] = item.reshape(-1, 3)
-        raw = voff[vo:vo + nv + 1].astype(int)
-        start, pad = raw & 0x0fff, raw[:-1] >> 12
-        assert start[-1] == nslots <= 5 * 128 + 192                   # the pair kernel's slot buffer
-        acc = np.zeros((nv, 3))
-        for t in range(nv):
-            cnt = start[t + 1] - start[t] - pad[t]
-            rows_ = buf[start[t]:start[t] + cnt]
-            assert cnt > 0 and not np.isnan(rows_).any()
-            acc[vperm[vs + t]] = rows_.sum(axis=0)
-        np.add.at(out, verts, acc)
-        n_paired += 2 * int((real[A] & real[B]).sum())
-    ref = np.zeros_like(u); ora.grad(u, ref)
-    np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
-    assert n_paired > 0.85 * T                                        # the online matching pairs most tets
-
-
 @pytest.fixture(scope="module")
 def tile_host(tmp_path_factory):
     out = tmp_path_factory.mktemp("native_tile") / "tile_host.so"
@@ -570,10 +476,9 @@ def tile_host(tmp_path_factory):
 
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-11), (np.float32, 1e-5)], ids=["f64", "f32"])
 @pytest.mark.parametrize("kind", ["snh", "arap", "muscle", "snh+arap"])
-@pytest.mark.parametrize("layout", [0, 1], ids=["tet", "pair"])
-def test_consumer_logic_replayed_on_the_host_matches_oracle(native_lib, tile_host, layout, kind, dtype, tol):
+def test_consumer_logic_replayed_on_the_host_matches_oracle(native_lib, tile_host, kind, dtype, tol):
     """The consumer-side DEVICE code of the element kernels (csrc/tile_logic.cuh: record / connectivity decoding,
-    corner gather, slot stores of both layouts, per-lane slot reduction with the tile_voff decoding, parked sums)
+    corner gather, slot stores, per-lane slot reduction with the tile_voff decoding, direct flush)
     compiled for the host and replayed thread by thread on the packed tables and planes of a host-only handle ==
     the oracle's assembled energy / gradient / diagonal / HVP / quadratic form."""
     from apple_b200 import _lib
@@ -598,21 +503,17 @@ def test_consumer_logic_replayed_on_the_host_matches_oracle(native_lib, tile_hos
     cells = np.ascontiguousarray(mesh.cells, dtype=np.int32); pts = np.ascontiguousarray(mesh.points)
     code = _lib.F32 if dtype == np.float32 else _lib.F64
     h = ctypes.c_void_p()
-    assert native_lib.apl_set_layout(layout) == 0
-    try:
-        if kind == "snh+arap":
-            rc = native_lib.apl_fem_create_snh_arap(code, T, V, P(cells), P(dhdX), P(dV), P(mu), P(la), P(dV2), P(mu2),
-                                                    P(pts), -1, ctypes.byref(h))
-        else:
-            k = {"snh": 0, "arap": 1, "muscle": 2}[kind]
-            rc = native_lib.apl_fem_create(k, code, T, V, P(cells), P(dhdX), P(dV), P(mu), P(la), P(act), P(pts), -1,
-                                           ctypes.byref(h))
-    finally:
-        native_lib.apl_set_layout(0)
+    if kind == "snh+arap":
+        rc = native_lib.apl_fem_create_snh_arap(code, T, V, P(cells), P(dhdX), P(dV), P(mu), P(la), P(dV2), P(mu2),
+                                                P(pts), -1, ctypes.byref(h))
+    else:
+        k = {"snh": 0, "arap": 1, "muscle": 2}[kind]
+        rc = native_lib.apl_fem_create(k, code, T, V, P(cells), P(dhdX), P(dV), P(mu), P(la), P(act), P(pts), -1,
+                                       ctypes.byref(h))
     assert rc == 0, native_lib.apl_last_error()
     info = (ctypes.c_int64 * 10)(); native_lib.apl_fem_info(h, info)
     nt, nv, nvo, npk = info[2], info[3], info[8], info[9]
-    rows, width = (npk // 2, 8) if layout == 1 else (T, 4)
+    rows, width = T, 4
     tiles = np.zeros((nt, 6), np.int32); conn = np.zeros((rows, width), np.uint8); slots = np.zeros((rows, width), np.uint16)
     tv = np.zeros(nv, np.int32); voff = np.zeros(nvo, np.uint16); vperm = np.zeros(nv, np.uint8)
     native_lib.apl_fem_host_tables(h, P(tiles), None, P(conn), P(slots), P(tv), P(voff), P(vperm))
@@ -626,12 +527,12 @@ def test_consumer_logic_replayed_on_the_host_matches_oracle(native_lib, tile_hos
     ref = {"fun": ora.fun(u), "quad": ora.hess_quad(u, p), "grad": ora.grad(u), "diag": ora.hess_diag(u),
            "prod": ora.hess_prod(u, p)}
     kcode = {"snh": 0, "arap": 1, "muscle": 2, "snh+arap": 3}[kind]
-    tile_host.tile_emulate.argtypes = [ctypes.c_int] * 4 + [ctypes.c_int64] + [ctypes.c_void_p] * 7 + [ctypes.c_int64] + \
+    tile_host.tile_emulate.argtypes = [ctypes.c_int] * 3 + [ctypes.c_int64] + [ctypes.c_void_p] * 7 + [ctypes.c_int64] + \
         [ctypes.c_void_p] * 2 + [ctypes.c_double] + [ctypes.c_void_p] * 5
     for ops in (11, 7, 16, 15):
         grad, diag, prod = (np.zeros((V, 3), dtype) for _ in range(3))
         fun, quad = np.zeros(1), np.zeros(1)
-        rc = tile_host.tile_emulate(layout, kcode, int(dtype == np.float64), ops, nt, P(tiles), P(conn), P(slots), P(tv),
+        rc = tile_host.tile_emulate(kcode, int(dtype == np.float64), ops, nt, P(tiles), P(conn), P(slots), P(tv),
                                     P(voff), P(vperm), P(planes), stride.value, P(ud), P(pd), 0.0, P(grad), P(diag),
                                     P(prod), P(fun), P(quad))
         assert rc == 0
@@ -640,17 +541,17 @@ def test_consumer_logic_replayed_on_the_host_matches_oracle(native_lib, tile_hos
             if ops & bit:
                 a, b = np.asarray(got[name], np.float64), np.asarray(ref[name])
                 assert np.isfinite(a).all(), (name, ops)                      # a NaN = a slot read before it was written
-                assert np.abs(a - b).max() <= tol * np.abs(b).max(), (layout, kind, ops, name)
+                assert np.abs(a - b).max() <= tol * np.abs(b).max(), (kind, ops, name)
     # PNCG's trial pass: energy / gradient / diagonal at u + alpha p, the trial point formed inside the gather
     alpha = 0.01
     grad, diag, prod = (np.zeros((V, 3), dtype) for _ in range(3))
     fun, quad = np.zeros(1), np.zeros(1)
-    assert tile_host.tile_emulate(layout, kcode, int(dtype == np.float64), 7, nt, P(tiles), P(conn), P(slots), P(tv), P(voff),
+    assert tile_host.tile_emulate(kcode, int(dtype == np.float64), 7, nt, P(tiles), P(conn), P(slots), P(tv), P(voff),
                                   P(vperm), P(planes), stride.value, P(ud), P(pd), alpha, P(grad), P(diag), P(prod), P(fun),
                                   P(quad)) == 0
     ut = u + alpha * p
     for a, b in ((fun[0], ora.fun(ut)), (grad, ora.grad(ut)), (diag, ora.hess_diag(ut))):
-        assert np.abs(np.asarray(a, np.float64) - b).max() <= 3 * tol * np.abs(b).max(), (layout, kind, "axpy")
+        assert np.abs(np.asarray(a, np.float64) - b).max() <= 3 * tol * np.abs(b).max(), (kind, "axpy")
 
 
 def test_tiling_is_deterministic_across_host_thread_counts(native_lib, monkeypatch):
@@ -665,11 +566,9 @@ def test_tiling_is_deterministic_across_host_thread_counts(native_lib, monkeypat
         assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("layout", [0, 1], ids=["tet", "pair"])
-def test_unstructured_delaunay_mesh_through_the_host_replay(native_lib, tile_host, layout):
+def test_unstructured_delaunay_mesh_through_the_host_replay(native_lib, tile_host):
     """An unstructured mesh (Delaunay tetrahedralisation of random points, cells in arbitrary order, uneven
-    valences): tiles close on the vertex budget as well as on the tet count, the online pairing leaves more tets
-    alone -- the replayed consumer logic must still assemble the oracle's energy / gradient / HVP."""
+    valences): tiles close on the vertex budget as well as on the tet count -- the replayed consumer logic must still assemble the oracle's energy / gradient / HVP."""
     scipy_spatial = pytest.importorskip("scipy.spatial")
     from apple_b200 import _lib
     from apple_b200.mesh import TetMesh
@@ -691,16 +590,12 @@ def test_unstructured_delaunay_mesh_through_the_host_replay(native_lib, tile_hos
     ora = ofem.Model([ofem.StableNeoHookean(mesh.cells, dhdX, dV, mu=mu, lambda_=la)], V)
     P = _lib.host_ptr
     h = ctypes.c_void_p()
-    native_lib.apl_set_layout(layout)
-    try:
-        rc = native_lib.apl_fem_create(0, _lib.F64, T, V, P(cells), P(dhdX), P(dV), P(mu), P(la), None,
-                                       P(np.ascontiguousarray(pts)), -1, ctypes.byref(h))
-    finally:
-        native_lib.apl_set_layout(0)
+    rc = native_lib.apl_fem_create(0, _lib.F64, T, V, P(cells), P(dhdX), P(dV), P(mu), P(la), None,
+                                   P(np.ascontiguousarray(pts)), -1, ctypes.byref(h))
     assert rc == 0, native_lib.apl_last_error()
     info = (ctypes.c_int64 * 10)(); native_lib.apl_fem_info(h, info)
     nt, nv, nvo, npk = info[2], info[3], info[8], info[9]
-    rows, width = (npk // 2, 8) if layout else (T, 4)
+    rows, width = T, 4
     tiles = np.zeros((nt, 6), np.int32); conn = np.zeros((rows, width), np.uint8); slots = np.zeros((rows, width), np.uint16)
     tv = np.zeros(nv, np.int32); voff = np.zeros(nvo, np.uint16); vperm = np.zeros(nv, np.uint8)
     native_lib.apl_fem_host_tables(h, P(tiles), None, P(conn), P(slots), P(tv), P(voff), P(vperm))
@@ -711,9 +606,9 @@ def test_unstructured_delaunay_mesh_through_the_host_replay(native_lib, tile_hos
     assert (tiles[:, 3] <= 192).all() and (tiles[:, 1] <= 256).all() and tiles[:, 1].sum() == npk
     grad, diag, prod = (np.zeros((V, 3)) for _ in range(3))
     fun, quad = np.zeros(1), np.zeros(1)
-    tile_host.tile_emulate.argtypes = [ctypes.c_int] * 4 + [ctypes.c_int64] + [ctypes.c_void_p] * 7 + [ctypes.c_int64] + \
+    tile_host.tile_emulate.argtypes = [ctypes.c_int] * 3 + [ctypes.c_int64] + [ctypes.c_void_p] * 7 + [ctypes.c_int64] + \
         [ctypes.c_void_p] * 2 + [ctypes.c_double] + [ctypes.c_void_p] * 5
-    assert tile_host.tile_emulate(layout, 0, 1, 11, nt, P(tiles), P(conn), P(slots), P(tv), P(voff), P(vperm), P(planes),
+    assert tile_host.tile_emulate(0, 1, 11, nt, P(tiles), P(conn), P(slots), P(tv), P(voff), P(vperm), P(planes),
                                   stride.value, P(u), P(p), 0.0, P(grad), P(diag), P(prod), P(fun), P(quad)) == 0
     for a, b in ((fun[0], ora.fun(u)), (grad, ora.grad(u)), (prod, ora.hess_prod(u, p))):
         assert np.abs(np.asarray(a) - b).max() <= 1e-11 * np.abs(b).max()

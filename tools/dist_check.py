@@ -21,7 +21,9 @@ for dtype, tol in ((torch.float64, 1e-10), (torch.float32, 1e-5)):
     mesh.cell_data.pop("Fraction")
     shard = partition_mesh(mesh, world, rank)
     pots = {k: cuda_potential(k, shard.mesh, dtype, name=k) for k in ("snh", "arap")}
-    ops = ShardedOperators(WarpModel(pots), shard, dev, dtype)
+    ops = ShardedOperators(WarpModel(pots), shard, dev, dtype, transport="nccl")
+    peer = ShardedOperators(WarpModel(pots), shard, dev, dtype)           # default on CUDA: peer memory (apl_xchg_*)
+    assert peer.transport == "peer" and not peer.overlap
     ul = torch.as_tensor(u[shard.l2g], dtype=dtype, device=dev).contiguous()
     pl = torch.as_tensor(p[shard.l2g], dtype=dtype, device=dev).contiguous()
     f, g, h = ops.fun_grad_hess_prod(ul, pl)
@@ -41,8 +43,42 @@ for dtype, tol in ((torch.float64, 1e-10), (torch.float32, 1e-5)):
     e2 = (rel_err(f.cpu(), f2.cpu()), float((g - g2).abs().max() / g2.abs().max()), float((h - h2).abs().max() / h2.abs().max()))
     good = good and max(e2) < 5 * tol
     print(f"rank {rank} {dtype} split vs plain evaluation: {e2[0]:.2e} {e2[1]:.2e} {e2[2]:.2e}, {ops.n_boundary_tiles} boundary tiles", flush=True)
+    # peer-memory exchange: same plan and summation order as pack / all-to-all / unpack -> the halo-summed rows agree
+    # to rounding of the element pass (fp atomics order), shared rows are bit-identical across the two sharers, and
+    # repeated evaluations (alternating buffer parity) stay consistent
+    for rep in range(3):
+        f3, g3, h3 = peer.fun_grad_hess_prod(ul, pl)
+    e3 = (rel_err(f3.cpu(), fr.cpu()), float((g3 - gr[idx]).abs().max() / gr.abs().max()), float((h3 - hr[idx]).abs().max() / hr.abs().max()))
+    good = good and max(e3) < 5 * tol
+    other = 1 - rank if world == 2 else None
+    if other is not None and other in shard.neighbors:
+        mine = g3[torch.as_tensor(shard.neighbors[other], device=dev)].contiguous()
+        theirs = torch.empty_like(mine)
+        reqs = [dist.isend(mine, other), dist.irecv(theirs, other)] if rank == 0 else [dist.irecv(theirs, other), dist.isend(mine, other)]
+        for r in reqs:
+            r.wait()
+        same = bool(torch.equal(mine, theirs))
+        good = good and same
+        print(f"rank {rank} {dtype} peer exchange: shared rows bit-identical on both sharers: {same}", flush=True)
+    print(f"rank {rank} {dtype} peer-memory exchange vs 1-GPU: {e3[0]:.2e} {e3[1]:.2e} {e3[2]:.2e}", flush=True)
     ok &= good
     print(f"rank {rank} {dtype} fused eval vs 1-GPU: energy/grad/hvp rel err {errs[0]:.2e} {errs[1]:.2e} {errs[2]:.2e} {'OK' if good else 'FAIL'}", flush=True)
+
+    # slabs generated and set up on the device (bench.py's workload) vs the whole cube on this GPU
+    from bench import device_potentials, device_workload
+    nn = 12
+    wl = device_workload(nn, world, rank, dev, dtype)
+    sops = ShardedOperators(WarpModel(device_potentials(wl, ["snh", "arap"], dtype)), wl.shard, dev, dtype)
+    fs, gs, hs = sops.fun_grad_hess_prod(wl.u, wl.p)
+    w1 = device_workload(nn, 1, 0, dev, dtype)
+    ad1 = WarpModelAdapter(WarpModel(device_potentials(w1, ["snh", "arap"], dtype)), w1.mesh.n_points)
+    f1, g1, h1 = ad1.fun_grad_hess_prod(w1.u, w1.p)
+    o1 = torch.argsort(w1.mesh.vertex_gid)
+    rows = o1[torch.searchsorted(w1.mesh.vertex_gid[o1], wl.mesh.vertex_gid)]
+    es = (rel_err(fs.cpu(), f1.cpu()), float((gs - g1[rows]).abs().max() / g1.abs().max()), float((hs - h1[rows]).abs().max() / h1.abs().max()))
+    good = max(es) < 5 * tol
+    ok &= good
+    print(f"rank {rank} {dtype} device-generated slabs vs whole cube: {es[0]:.2e} {es[1]:.2e} {es[2]:.2e} {'OK' if good else 'FAIL'}", flush=True)
 
     # PNCG: sharded vs single-GPU fused, fixed iteration count
     from apple_b200.common import FIXED_MASK, FIXED_VALUE

@@ -11,18 +11,29 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--kind", default="snh"); ap.add_argument("--dtype", default="f32")
 ap.add_argument("--ops", type=int, default=11); ap.add_argument("--scatter", type=int, default=0)
 ap.add_argument("--ld", type=int, default=3); ap.add_argument("--n", type=int, default=58)
-ap.add_argument("--reps", type=int, default=3); ap.add_argument("--layout", default="tet")
+ap.add_argument("--reps", type=int, default=3); ap.add_argument("--setup", default="host", choices=["host", "device"])
 a = ap.parse_args()
 dt = torch.float32 if a.dtype == "f32" else torch.float64
 from apple_b200 import _lib, config
-config.layout = {"tet": _lib.LAYOUT_TET, "pair": _lib.LAYOUT_PAIR}[a.layout]
-mesh, u, p = build_mesh(a.n)
-V = mesh.n_points
-if a.kind == "fused":
-    from apple_b200.warp.fem import fuse_potentials
-    pot = list(fuse_potentials({k: cuda_potential(k, mesh, dt, name=k) for k in ("snh", "arap")}).values())[0]
+import time
+t0 = time.perf_counter()
+if a.setup == "device":
+    # mesh, materials and fields generated on the GPU, potential built by apl_fem_create_from_mesh
+    from bench import device_potentials, device_workload
+    wl = device_workload(a.n, 1, 0, torch.device("cuda", 0), dt)
+    pot = list(device_potentials(wl, ["snh", "arap"] if a.kind == "fused" else [a.kind], dt, fuse=True).values())[0]
+    V, u, p = wl.mesh.n_points, wl.u.cpu().numpy(), wl.p.cpu().numpy()
+    n_cells = wl.mesh.n_cells
 else:
-    pot = cuda_potential(a.kind, mesh, dt)
+    mesh, u, p = build_mesh(a.n)
+    V, n_cells = mesh.n_points, mesh.n_cells
+    if a.kind == "fused":
+        from apple_b200.warp.fem import fuse_potentials
+        pot = list(fuse_potentials({k: cuda_potential(k, mesh, dt, name=k) for k in ("snh", "arap")}).values())[0]
+    else:
+        pot = cuda_potential(a.kind, mesh, dt)
+torch.cuda.synchronize()
+print(f"setup ({a.setup}): {time.perf_counter() - t0:.2f} s for {n_cells} tets")
 ud = torch.zeros((V, a.ld), dtype=dt, device="cuda"); ud[:, :3] = torch.as_tensor(u, dtype=dt)
 pd = torch.zeros((V, a.ld), dtype=dt, device="cuda"); pd[:, :3] = torch.as_tensor(p, dtype=dt)
 outs = {k: torch.zeros((V, a.ld), dtype=dt, device="cuda") for k in ("grad", "diag", "prod")}
@@ -35,4 +46,4 @@ for i in range(a.reps):
     e0.record()
     pot.eval(a.ops, ud, pd, fun=fun, quad=quad, grad=outs["grad"], diag=outs["diag"], prod=outs["prod"], scatter=a.scatter)
     e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
-print(a, "ms:", ts, "Gtets/s:", mesh.n_cells / min(ts) / 1e6)
+print(a, "ms:", ts, "Gtets/s:", n_cells / min(ts) / 1e6)

@@ -55,12 +55,8 @@ def host_tables(n, layout=0):
     T, V = mesh.n_cells, mesh.n_points
     one = np.ones(T); P = _lib.host_ptr; h = ctypes.c_void_p()
     cells = np.ascontiguousarray(mesh.cells, dtype=np.int32); pts = np.ascontiguousarray(mesh.points)
-    L.apl_set_layout(layout)
-    try:
-        rc = L.apl_fem_create(0, _lib.F32, T, V, P(cells), P(dhdX.astype(np.float32)), P(dV.astype(np.float32)),
-                              P(one.astype(np.float32)), P(one.astype(np.float32)), None, P(pts), -1, ctypes.byref(h))
-    finally:
-        L.apl_set_layout(0)
+    rc = L.apl_fem_create(0, _lib.F32, T, V, P(cells), P(dhdX.astype(np.float32)), P(dV.astype(np.float32)),
+                          P(one.astype(np.float32)), P(one.astype(np.float32)), None, P(pts), -1, ctypes.byref(h))
     assert rc == 0, L.apl_last_error()
     info = (ctypes.c_int64 * 10)(); L.apl_fem_info(h, info)
     nt, nv, nvo, npk = info[2], info[3], info[8], info[9]
