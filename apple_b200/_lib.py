@@ -74,6 +74,7 @@ SIGNATURES = {
     "apl_pncg_add_ext_force": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "apl_pncg_set_params": (c_int, [c_void_p, c_double, c_double, c_double, c_double, c_double, c_double, c_double,
                                     c_int, c_int, c_int]),
+    "apl_pncg_set_exchange": (c_int, [c_void_p, c_void_p]),
     "apl_pncg_current": (c_int, [c_void_p]),
     "apl_pncg_flip": (c_int, [c_void_p]),
     "apl_pncg_phase": (c_int, [c_void_p, c_int, c_int, c_void_p]),

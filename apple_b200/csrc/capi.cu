@@ -602,6 +602,15 @@ int apl_fem_eval_part(apl_fem_t* f, int part, int ops, const void* u, const void
             return APL_ERR_INVALID;
         }
     }
+    {   // launches go to the CURRENT device: it must be the one the handle's tables live on
+        int cur = -1;
+        APL_CUDA_CHECK(cudaGetDevice(&cur));
+        if (cur != f->device) {
+            set_error("apl_fem_eval: the handle lives on device " + std::to_string(f->device) +
+                      " but the current device is " + std::to_string(cur) + " (call cudaSetDevice first)");
+            return APL_ERR_STATE;
+        }
+    }
     cudaStream_t s = (cudaStream_t)stream;
     return f->dtype == APL_F32
                ? eval_typed<float>(f, ops, u, p, ld_in, fun, quad, grad, diag, prod, ld_out, scatter, s, nullptr, part)

@@ -17,7 +17,10 @@ constexpr int kTileTets = APL_TILE_TETS;   // tets per tile == consumer threads 
 constexpr int kTileVerts = APL_TILE_TETS * 3 / 4;  // max distinct vertices per tile (uint8 local ids, <= 256)
 // Reduction slots of a tile: one per tet corner plus up to kSlotPads unused pad slots that keep the slot-range
 // starts of a reduce group in distinct bank groups (tiling.cpp); the kernels allocate kSlotsAlloc slots per buffer.
-constexpr int kSlotPads = APL_TILE_TETS * 5 / 8;
+#ifndef APL_SLOT_PADS
+#define APL_SLOT_PADS (APL_TILE_TETS * 5 / 8)
+#endif
+constexpr int kSlotPads = APL_SLOT_PADS;
 constexpr int kSlotsAlloc = 4 * APL_TILE_TETS + kSlotPads;
 
 void set_error(const std::string& msg);

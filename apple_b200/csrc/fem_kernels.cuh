@@ -423,10 +423,14 @@ __device__ __forceinline__ void store_row4(T* dst, const T* r) {
 constexpr int kPipeThreads = kTileTets + 32;
 
 #ifndef APL_GATHER_LDG
-#define APL_GATHER_LDG 0   // 1: 12-byte rows through registers (measured slower: the producer waits out a global-memory latency per tile); 0: three 4-byte cp.async per row
+#define APL_GATHER_LDG 0   // 1: 12-byte rows through registers (one 8-byte + one 4-byte load per row, issued before the
+                           //    wait for the stage); 0: three 4-byte cp.async per row
 #endif
 #ifndef APL_SLOT_BUFS
 #define APL_SLOT_BUFS 2    // slot buffers wanted (2: software-pipelined phases; 1: phases in order)
+#endif
+#ifndef APL_WANT_CTAS
+#define APL_WANT_CTAS 2    // 3: fp32 kernels with a small enough tile state run three CTAs per SM (one slot buffer)
 #endif
 
 template <typename T, int KIND, int OPS>
@@ -451,23 +455,32 @@ struct PipeCfg {
     static constexpr size_t oVperm = oVerts + (size_t)kTileVerts * 4;
     static constexpr size_t oVoff = oVperm + (size_t)kTileVerts;
     static constexpr size_t kVtabBytes = oVoff + Cfg::kVoffRaw;
-    static constexpr size_t kBarBytes = 128;
-    // shared memory per CTA for the wanted CTAs per SM (227 KB per SM, 1 KB reserved per CTA)
-    static constexpr int kWantCtas = (sizeof(T) == 4 ? 2 : 1) * (256 / kTileTets);
+    // mbarriers: full[S], empty[S], vfull[S + NB + 1], slots_full[NB], slots_free[NB]
+    static constexpr size_t bar_bytes(int nb, int stages) { return ((size_t)8 * (3 * stages + 3 * nb + 1) + 15) / 16 * 16; }
+    // Shared memory per CTA for N CTAs per SM (227 KB per SM, 1 KB reserved per CTA).  fp32 kernels whose tile state
+    // is small enough run THREE CTAs per SM with one slot buffer (phases in order); the others TWO CTAs per SM (fp64:
+    // one) with two slot buffers (software-pipelined phases) when those fit next to two stages.
+    static constexpr size_t budget(int ctas) { return (size_t)227 * 1024 / ctas - 1024; }
+    static constexpr size_t total(int nb, int stages) {
+        return bar_bytes(nb, stages) + (size_t)nb * kSlotBytes + (size_t)(stages + nb + 1) * kVtabBytes +
+               (size_t)stages * kStageBytes;
+    }
 #ifdef APL_SMEM_BUDGET_KB
+    static constexpr bool kThree = false;
+    static constexpr int kWantCtas = 2;
     static constexpr size_t kBudget = (size_t)APL_SMEM_BUDGET_KB * 1024;
 #else
-    static constexpr size_t kBudget = (size_t)227 * 1024 / kWantCtas - 1024;
+    static constexpr bool kThree = sizeof(T) == 4 && kTileTets == 256 && APL_WANT_CTAS >= 3 && total(1, 2) <= budget(3);
+    static constexpr int kWantCtas = kThree ? 3 : (sizeof(T) == 4 ? 2 : 1) * (256 / kTileTets);
+    static constexpr size_t kBudget = budget(kWantCtas);
 #endif
-    static constexpr size_t total(int nb, int stages) {
-        return kBarBytes + (size_t)nb * kSlotBytes + (size_t)(stages + nb + 1) * kVtabBytes + (size_t)stages * kStageBytes;
-    }
-    // two slot buffers (pipelined phases) when they fit next to two stages, else one
-    static constexpr int kSlotBufs = Cfg::NOUT == 0 ? 1 : ((APL_SLOT_BUFS >= 2 && total(2, 2) <= kBudget) ? 2 : 1);
+    static constexpr int kSlotBufs =
+        (Cfg::NOUT == 0 || kThree) ? 1 : ((APL_SLOT_BUFS >= 2 && total(2, 2) <= kBudget) ? 2 : 1);
     static constexpr int kStages = total(kSlotBufs, 4) <= kBudget ? 4 : (total(kSlotBufs, 3) <= kBudget ? 3 : 2);
     // a vertex table lives from its request (one tile ahead of the stage) until the tile's REDUCE phase has
     // finished in every consumer, which trails the stage release by up to kSlotBufs tiles
     static constexpr int kVring = kStages + kSlotBufs + 1;
+    static constexpr size_t kBarBytes = bar_bytes(kSlotBufs, kStages);
     static constexpr size_t oSlotBuf = kBarBytes;
     static constexpr size_t oVring = oSlotBuf + (size_t)kSlotBufs * kSlotBytes;
     static constexpr size_t oStages = oVring + (size_t)kVring * kVtabBytes;
@@ -482,12 +495,16 @@ struct PipeCfg {
 // (tile_reduce_lane), exchange with one shuffle, and issue the REDs from both lanes (field f from the lane of
 // half f & 1).  Groups of 16 vertices (reduce order: about decreasing valence) are dealt to the warps round
 // robin, rotated by `rot` from tile to tile so that no warp always owns the heaviest group.
-template <typename T, int OPS, int NT, int NSLOTS>
+// ALL slot reads of the thread (at most two groups: kTileVerts <= NT) come first, then `release` (the arrival on the
+// slots-free barrier), then the REDs: an mbarrier arrival has release semantics and would otherwise wait for
+// the thread's outstanding REDs to be performed -- a round trip to L2 on the critical path of every tile.
+template <typename T, int OPS, int NT, int NSLOTS, typename Release>
 __device__ __forceinline__ void tile_reduce_flush(int tid, int rot, int n_verts, const unsigned char* vperm,
                                                   const unsigned short* voff, const int* verts, const T* sl,
-                                                  const FemArgs<T>& a) {
+                                                  const FemArgs<T>& a, Release&& release) {
     using Cfg = TileCfg<T, OPS>;
     constexpr int NOUT = Cfg::NOUT;
+    static_assert(kTileVerts <= NT, "two reduce trips per thread cover a tile");
     const int half = (tid >> 4) & 1;
     const int w = ((tid >> 5) + rot) & (NT / 32 - 1);
     T* outs[3] = {nullptr, nullptr, nullptr};
@@ -497,25 +514,33 @@ __device__ __forceinline__ void tile_reduce_flush(int tid, int rot, int n_verts,
         if constexpr (Cfg::kDiag) outs[k++] = a.diag;
         if constexpr (Cfg::kProd) outs[k++] = a.prod;
     }
-    for (int t = w * 16 + (tid & 15); t < ((n_verts + 15) & ~15); t += NT / 2) {
-        // (the bound is rounded up to 16 so that whole warps stay together for the shuffle below;
-        //  out-of-range lanes have cnt = 0)
-        int v;
-        T acc[3 * NOUT];
-        tile_reduce_lane<T, OPS, NSLOTS>(half, t, n_verts, vperm, voff, sl, v, acc);
+    const int bound = (n_verts + 15) & ~15;   // rounded up to 16 so that whole warps stay together for the shuffle
+    T acc[2][3 * NOUT];
+    int gv[2] = {-1, -1};
 #pragma unroll
-        for (int j = 0; j < 3 * NOUT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
-        if (t < n_verts) {
-            const int gv = verts[v];
-            if constexpr (NOUT == 1) {
-                if (half == 0 && outs[0]) red_row(outs[0], gv, a.ld_out, acc);
-            } else {
-                T* base = half ? outs[1] : outs[0];
-                const T val[3] = {half ? acc[3] : acc[0], half ? acc[4] : acc[1], half ? acc[5] : acc[2]};
-                if (base) red_row(base, gv, a.ld_out, val);
-                if constexpr (NOUT == 3) {
-                    if (half == 0 && outs[2]) red_row(outs[2], gv, a.ld_out, acc + 6);
-                }
+    for (int trip = 0; trip < 2; ++trip) {
+        const int t = w * 16 + (tid & 15) + trip * (NT / 2);
+        if (t < bound) {                      // warp-uniform
+            int v;
+            tile_reduce_lane<T, OPS, NSLOTS>(half, t, n_verts, vperm, voff, sl, v, acc[trip]);
+#pragma unroll
+            for (int j = 0; j < 3 * NOUT; ++j) acc[trip][j] += __shfl_xor_sync(0xffffffffu, acc[trip][j], 16);
+            if (t < n_verts) gv[trip] = verts[v];
+        }
+    }
+    release();
+#pragma unroll
+    for (int trip = 0; trip < 2; ++trip) {
+        if (gv[trip] < 0) continue;
+        const T* s = acc[trip];
+        if constexpr (NOUT == 1) {
+            if (half == 0 && outs[0]) red_row(outs[0], gv[trip], a.ld_out, s);
+        } else {
+            T* base = half ? outs[1] : outs[0];
+            const T val[3] = {half ? s[3] : s[0], half ? s[4] : s[1], half ? s[5] : s[2]};
+            if (base) red_row(base, gv[trip], a.ld_out, val);
+            if constexpr (NOUT == 3) {
+                if (half == 0 && outs[2]) red_row(outs[2], gv[trip], a.ld_out, s + 6);
             }
         }
     }
@@ -530,7 +555,7 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
     constexpr int NC = PC::kConsumers;             // consumer threads (warps 0 .. NC/32 - 1), producer = warp NC/32
     constexpr int S = PC::kStages, SV = PC::kVring, NB = PC::kSlotBufs;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // [0,128): mbarriers full[S], empty[S], vfull[SV], slots_full[NB], slots_free[NB];  NB slot buffers;
+    // mbarriers full[S], empty[S], vfull[SV], slots_full[NB], slots_free[NB];  NB slot buffers;
     // SV vertex-table slots;  S stages
     static_assert(8 * (2 * S + SV + 2 * NB) <= (int)PC::kBarBytes, "mbarrier area too small");
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -608,8 +633,28 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
             h.z = __shfl_sync(0xffffffffu, h_cur.z, 0);
             h.w = __shfl_sync(0xffffffffu, h_cur.w, 0);
             const int n_tets = h.y & 0xffff, n_verts = h.y >> 16;
+            // the tables of tile `it` were requested one iteration ago
+            const int sv = it % SV;
+            mbar_wait(vfull(sv), (unsigned)(it / SV) & 1u);
+            const int* verts = reinterpret_cast<const int*>(vring + (size_t)sv * PC::kVtabBytes + PC::oVerts);
+            const bool via_regs = APL_GATHER_LDG && a.ld_in == 3;
+            constexpr int R = APL_GATHER_LDG ? kTileVerts / 32 : 1;
+            T ru[R][3], rp[R][3];
+            if (via_regs) {
+                // 12-byte rows through registers: the loads are issued BEFORE the wait for the stage, so their
+                // latency overlaps with the time the consumers still hold it
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const int v = lane + 32 * k;
+                    if (v < n_verts) {
+                        const int gv = verts[v];
+                        load_row3_ldg<T>(a.u, gv, aligned8, ru[k]);
+                        if (want_p) load_row3_ldg<T>(pf, gv, aligned8, rp[k]);
+                    }
+                }
+            }
             // stage s free <=> every consumer is past COMPUTE(it - S); its REDUCE phases up to tile
-            // it - S - NB - 1 + 1 are then finished too, which frees vertex slot (it + 1) % SV
+            // it - S - NB are then finished too, which frees vertex slot (it + 1) % SV
             mbar_wait(empty(s), ph ^ 1u);
             if (lane == 0) {
                 *reinterpret_cast<int4*>(st + PC::oHdr) = h;
@@ -625,26 +670,9 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
                 if constexpr (NOUT > 0) bulk_g2s(st32 + (unsigned)PC::oSlots, a.slots + h.x, bs, full(s));
                 if (it + 1 < my_tiles) request_vtab(it + 1, h_nxt);
             }
-            // gather: the tables of tile `it` were requested one iteration ago
-            const int sv = it % SV;
-            mbar_wait(vfull(sv), (unsigned)(it / SV) & 1u);
-            const int* verts = reinterpret_cast<const int*>(vring + (size_t)sv * PC::kVtabBytes + PC::oVerts);
             const unsigned us32 = st32 + (unsigned)PC::oVbuf;
             const unsigned ps32 = us32 + 4u * kTileVerts * (unsigned)sizeof(T);
-            if (APL_GATHER_LDG && a.ld_in == 3) {
-                // 12-byte rows through registers: all loads of the tile are issued before the first store, so
-                // one global-memory latency is exposed per tile (hidden by the stages in flight)
-                constexpr int R = kTileVerts / 32;
-                T ru[R][3], rp[R][3];
-#pragma unroll
-                for (int k = 0; k < R; ++k) {
-                    const int v = lane + 32 * k;
-                    if (v < n_verts) {
-                        const int gv = verts[v];
-                        load_row3_ldg<T>(a.u, gv, aligned8, ru[k]);
-                        if (want_p) load_row3_ldg<T>(pf, gv, aligned8, rp[k]);
-                    }
-                }
+            if (via_regs) {
                 T* vb = reinterpret_cast<T*>(st + PC::oVbuf);
 #pragma unroll
                 for (int k = 0; k < R; ++k) {
@@ -705,8 +733,8 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
                 mbar_wait(sfull(it % NB), (unsigned)(it / NB) & 1u);
                 tile_reduce_flush<T, OPS, NC, PC::kNSlots>(tid, it, n_verts, vt + PC::oVperm,
                                                            reinterpret_cast<const unsigned short*>(vt + PC::oVoff),
-                                                           reinterpret_cast<const int*>(vt + PC::oVerts), sl, a);
-                mbar_arrive(sfree(it % NB));
+                                                           reinterpret_cast<const int*>(vt + PC::oVerts), sl, a,
+                                                           [&] { mbar_arrive(sfree(it % NB)); });
             };
             if constexpr (NB == 2) {
                 int nv_cur = my_tiles > 0 ? compute(0) : 0;

@@ -26,6 +26,8 @@
 #include "common.h"
 #include "fem_kernels.cuh"
 
+struct apl_xchg;
+
 namespace apl {
 
 int fem_eval_pncg(apl_fem* f, int ops, const void* x, const void* p, const void* axpy_p, double* scal,
@@ -34,6 +36,11 @@ int fem_eval_pncg(apl_fem* f, int ops, const void* x, const void* p, const void*
 int ext_force_pncg(int dtype, int ops, int64_t k, const void* force, const int32_t* indices, const void* x,
                    const void* axpy_p, double* scal, int alpha_idx, int skip_a, int skip_b, double* fun_d,
                    void* grad, cudaStream_t stream, int dyn_j = 0);
+
+int xchg_push_ex(apl_xchg* x, int dtype, int nf, const void* f0, const void* f1, const void* f2, int ld, const void* scal,
+                 int n_scal, int scal_f64, const double* skip_scal, int skip_a, int skip_b, int dyn_j, cudaStream_t s);
+int xchg_pull_ex(apl_xchg* x, int dtype, int nf, void* f0, void* f1, void* f2, int ld, void* scal, int n_scal,
+                 int scal_f64, const double* skip_scal, int skip_a, int skip_b, int dyn_j, cudaStream_t s);
 
 constexpr int kVecThreads = 256;
 constexpr int kNSums = 11;
@@ -372,9 +379,25 @@ struct apl_pncg {
     int graph_mode = 0;  // 0 none, 1 static trials, 2 conditional WHILE
     cudaStream_t capture_stream = nullptr;  // graphs are captured here (the legacy stream cannot capture)
     bool use_graph = false;
+    // sharded meshes: partial reductions and nodal sums of this rank are completed through peer memory right after
+    // the phase that produced them (apl_pncg_set_exchange); nullptr = single GPU
+    apl_xchg* xchg = nullptr;
 };
 
 namespace {
+
+// Completes this rank's partial results of a phase over all ranks: halo sum of up to two nodal fields (ld = 4) and
+// the global sum of n_scal workspace scalars starting at scal[idx (+ trial counter)], guarded by the same skip flags
+// as the launches that produced them.
+int exchange(apl_pncg* w, void* f0, void* f1, int idx, int n_scal, int skip_a, int skip_b, int dyn_j, cudaStream_t s) {
+    if (!w->xchg) return APL_OK;
+    const int nf = f0 ? (f1 ? 2 : 1) : 0;
+    int rc = xchg_push_ex(w->xchg, w->dtype, nf, f0, f1, nullptr, 4, w->scal + idx, n_scal, 1, w->scal, skip_a, skip_b,
+                          dyn_j, s);
+    if (rc != APL_OK) return rc;
+    return xchg_pull_ex(w->xchg, w->dtype, nf, f0, f1, nullptr, 4, w->scal + idx, n_scal, 1, w->scal, skip_a, skip_b,
+                        dyn_j, s);
+}
 
 template <typename T>
 int phase_typed(apl_pncg* w, int phase, int j, cudaStream_t s) {
@@ -392,6 +415,7 @@ int phase_typed(apl_pncg* w, int phase, int j, cudaStream_t s) {
         case APL_PHASE_REDUCE:
             pncg_reduce_kernel<T><<<w->grid, kVecThreads, 0, s>>>(w->rows, g, gz, dg, pprev, mask, w->scal,
                                                                   w->partials, w->counter);
+            if (int rc = exchange(w, nullptr, nullptr, APL_S_SUMS, kNSums, APL_S_DONE, -1, 0, s)) return rc;
             break;
         case APL_PHASE_FINALIZE:
             pncg_finalize_kernel<<<1, 1, 0, s>>>(w->scal, w->prm);
@@ -406,6 +430,8 @@ int phase_typed(apl_pncg* w, int phase, int j, cudaStream_t s) {
                                        w->scal + APL_S_PHP, nullptr, nullptr, w->scatter, s);
                 if (rc != APL_OK) return rc;
             }
+            // g.p (DIRECTION) and p.Hp (this pass) are adjacent partial sums: one exchange completes both
+            if (int rc = exchange(w, nullptr, nullptr, APL_S_GP, 2, APL_S_DONE, -1, 0, s)) return rc;
             break;
         case APL_PHASE_ALPHA:
             pncg_alpha_kernel<<<1, 1, 0, s>>>(w->scal, w->prm);
@@ -426,6 +452,7 @@ int phase_typed(apl_pncg* w, int phase, int j, cudaStream_t s) {
                                         dyn);
                 if (rc != APL_OK) return rc;
             }
+            if (int rc = exchange(w, gz, dz, APL_S_FT_J + jj, 1, APL_S_DONE, APL_S_ACC_J + jj, dyn, s)) return rc;
             if (dyn) pncg_bump_j_kernel<<<1, 1, 0, s>>>(w->scal);
             break;
         }
@@ -460,6 +487,7 @@ int phase_typed(apl_pncg* w, int phase, int j, cudaStream_t s) {
                                         -1, -1, w->scal + APL_S_F, g, s);
                 if (rc != APL_OK) return rc;
             }
+            if (int rc = exchange(w, g, dg, APL_S_F, 1, -1, -1, 0, s)) return rc;
             break;
         }
         default:
@@ -627,6 +655,13 @@ int apl_pncg_set_params(apl_pncg_t* w, double max_steps, double rtol_g, double a
     w->scatter = scatter;
     w->use_graph = use_graph != 0;
     w->graph_mode = use_graph;
+    drop_graphs(w);
+    return APL_OK;
+}
+
+int apl_pncg_set_exchange(apl_pncg_t* w, apl_xchg_t* x) {
+    if (!w) { set_error("apl_pncg_set_exchange: NULL workspace"); return APL_ERR_INVALID; }
+    w->xchg = x;
     drop_graphs(w);
     return APL_OK;
 }

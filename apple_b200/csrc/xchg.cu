@@ -3,7 +3,7 @@
 //
 // Every rank owns one device region (cudaMalloc, exported with cudaIpcGetMemHandle, mapped by every other rank):
 //   flags  [2][world]  uint64   epoch of the last completed push of rank r into this region (per buffer parity)
-//   scal   [2][world][8] double rank r's partial scalars (energy, p.Hp, ...) of that epoch
+//   scal   [2][world][16] double rank r's partial scalars (energy, p.Hp, ...) of that epoch
 //   recv   [2][rows][9]  T      rows pushed by the other ranks (their partial nodal sums on shared vertices)
 // One exchange = two small kernels (128 threads, <= 40 registers, no shared memory: they co-reside with the persistent element
 // kernel that is working on the interior tiles meanwhile):
@@ -26,7 +26,7 @@
 #include "common.h"
 
 #define APL_XCHG_MAX_WORLD 16
-#define APL_XCHG_NSCAL 8
+#define APL_XCHG_NSCAL 16
 
 struct apl_xchg {
     int world = 1, rank = 0, device = 0;
@@ -63,13 +63,33 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
+// Launches of a PNCG iteration are flag-guarded (a trial that is not needed is a no-op): the exchange that follows such
+// a launch must be a no-op too.  Every rank holds bit-identical scalars, so all ranks skip together and the epoch
+// simply does not advance.  skip == nullptr: unconditional.
+struct XchgSkip {
+    const double* scal = nullptr;   // the PNCG workspace scalars
+    int a = -1, b = -1;             // skipped if scal[a] != 0 or scal[b + joff] != 0
+    int dyn_j = 0;                  // joff = (int)scal[APL_S_J]; also added to the scalar slot exchanged
+};
+__device__ __forceinline__ bool xchg_skipped(const XchgSkip& sk, int& joff) {
+    joff = 0;
+    if (sk.scal == nullptr) return false;
+    if (sk.dyn_j) joff = (int)__ldcg(sk.scal + APL_S_J);
+    if (sk.a >= 0 && __ldcg(sk.scal + sk.a) != 0.0) return true;
+    if (sk.b >= 0 && __ldcg(sk.scal + sk.b + joff) != 0.0) return true;
+    return false;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(128) xchg_push_kernel(XchgPeers peers, int world, int rank, long long n_send,
                                                         const long long* __restrict__ idx, const int* __restrict__ peer,
                                                         const long long* __restrict__ row, int nf, const T* f0, const T* f1,
-                                                        const T* f2, int ld, const T* scal_in, int n_scal,
+                                                        const T* f2, int ld, const void* scal_in, int n_scal, int scal_f64,
                                                         size_t off_scal, size_t off_recv, size_t recv_bytes,
-                                                        const unsigned long long* epoch, unsigned int* counter) {
+                                                        const unsigned long long* epoch, unsigned int* counter,
+                                                        XchgSkip sk) {
+    int joff;
+    if (xchg_skipped(sk, joff)) return;
     const unsigned long long e = *epoch + 1ull;
     const size_t par = (size_t)(e & 1ull);
     const T* f[3] = {f0, f1, f2};
@@ -87,7 +107,8 @@ __global__ void __launch_bounds__(128) xchg_push_kernel(XchgPeers peers, int wor
     if (blockIdx.x == 0 && (int)threadIdx.x < world * n_scal) {
         const int q = threadIdx.x / n_scal, k = threadIdx.x % n_scal;
         double* slot = reinterpret_cast<double*>(peers.base[q] + off_scal) + (par * world + rank) * APL_XCHG_NSCAL;
-        slot[k] = (double)scal_in[k];
+        slot[k] = scal_f64 ? reinterpret_cast<const double*>(scal_in)[joff + k]
+                           : (double)reinterpret_cast<const T*>(scal_in)[joff + k];
     }
     __threadfence_system();
     __syncthreads();
@@ -107,9 +128,11 @@ template <typename T>
 __global__ void __launch_bounds__(128) xchg_pull_kernel(char* own, int world, int rank, long long n_shared,
                                                         const long long* __restrict__ shared,
                                                         const int* __restrict__ row_ptr, const long long* __restrict__ src,
-                                                        int nf, T* f0, T* f1, T* f2, int ld, T* scal_out, int n_scal,
-                                                        size_t off_scal, size_t off_recv, size_t recv_bytes,
-                                                        unsigned long long* epoch, unsigned int* counter) {
+                                                        int nf, T* f0, T* f1, T* f2, int ld, void* scal_out, int n_scal,
+                                                        int scal_f64, size_t off_scal, size_t off_recv, size_t recv_bytes,
+                                                        unsigned long long* epoch, unsigned int* counter, XchgSkip sk) {
+    int joff;
+    if (xchg_skipped(sk, joff)) return;
     const unsigned long long e = *epoch + 1ull;
     const size_t par = (size_t)(e & 1ull);
     if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
@@ -141,7 +164,8 @@ __global__ void __launch_bounds__(128) xchg_pull_kernel(char* own, int world, in
         const double* slots = reinterpret_cast<const double*>(own + off_scal) + par * world * APL_XCHG_NSCAL;
         double s = 0.0;
         for (int r = 0; r < world; ++r) s += __ldcg(slots + r * APL_XCHG_NSCAL + threadIdx.x);
-        scal_out[threadIdx.x] = (T)s;
+        if (scal_f64) reinterpret_cast<double*>(scal_out)[joff + threadIdx.x] = s;
+        else reinterpret_cast<T*>(scal_out)[joff + threadIdx.x] = (T)s;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -252,7 +276,7 @@ static int xchg_check(apl_xchg_t* x, int dtype, int nf, const void* f0, int ld, 
     if (!x) { set_error("apl_xchg: NULL handle"); return APL_ERR_INVALID; }
     if ((dtype != APL_F32 && dtype != APL_F64) || nf < 0 || nf > 3 || (nf > 0 && !f0) || (ld != 3 && ld != 4) ||
         n_scal < 0 || n_scal > APL_XCHG_NSCAL || (n_scal > 0 && !scal)) {
-        set_error("apl_xchg: bad arguments (up to 3 fields, up to 8 scalars)");
+        set_error("apl_xchg: bad arguments (up to 3 fields, up to 16 scalars)");
         return APL_ERR_INVALID;
     }
     for (int r = 0; r < x->world; ++r)
@@ -260,49 +284,69 @@ static int xchg_check(apl_xchg_t* x, int dtype, int nf, const void* f0, int ld, 
     return APL_OK;
 }
 
-int apl_xchg_push(apl_xchg_t* x, int dtype, int nf, const void* f0, const void* f1, const void* f2, int ld,
-                  const void* scal, int n_scal, void* stream) {
+}  // extern "C"
+
+namespace apl {
+// Internal forms used by the PNCG driver (pncg.cu): scalars may be doubles whatever the field type, and the exchange
+// can be guarded by the workspace's skip flags (skip_scal == nullptr: unconditional).
+int xchg_push_ex(apl_xchg* x, int dtype, int nf, const void* f0, const void* f1, const void* f2, int ld, const void* scal,
+                 int n_scal, int scal_f64, const double* skip_scal, int skip_a, int skip_b, int dyn_j, cudaStream_t s) {
     int rc = xchg_check(x, dtype, nf, f0, ld, n_scal, scal);
     if (rc != APL_OK) return rc;
     XchgPeers peers;
     for (int r = 0; r < APL_XCHG_MAX_WORLD; ++r) peers.base[r] = x->peer[r];
+    XchgSkip sk;
+    sk.scal = skip_scal; sk.a = skip_a; sk.b = skip_b; sk.dyn_j = dyn_j;
     const long long n = nf > 0 ? x->n_send : 0;
     const int grid = grid_rows(n);
-    cudaStream_t s = (cudaStream_t)stream;
     if (dtype == APL_F32)
         xchg_push_kernel<float><<<grid, 128, 0, s>>>(peers, x->world, x->rank, n, (const long long*)x->send_index,
                                                      x->send_peer, (const long long*)x->send_row, nf, (const float*)f0,
-                                                     (const float*)f1, (const float*)f2, ld, (const float*)scal, n_scal,
-                                                     x->off_scal, x->off_recv, x->recv_bytes, x->d_epoch, x->d_counters);
+                                                     (const float*)f1, (const float*)f2, ld, scal, n_scal, scal_f64,
+                                                     x->off_scal, x->off_recv, x->recv_bytes, x->d_epoch, x->d_counters, sk);
     else
         xchg_push_kernel<double><<<grid, 128, 0, s>>>(peers, x->world, x->rank, n, (const long long*)x->send_index,
                                                       x->send_peer, (const long long*)x->send_row, nf, (const double*)f0,
-                                                      (const double*)f1, (const double*)f2, ld, (const double*)scal,
-                                                      n_scal, x->off_scal, x->off_recv, x->recv_bytes, x->d_epoch,
-                                                      x->d_counters);
+                                                      (const double*)f1, (const double*)f2, ld, scal, n_scal, scal_f64,
+                                                      x->off_scal, x->off_recv, x->recv_bytes, x->d_epoch, x->d_counters,
+                                                      sk);
     APL_CUDA_CHECK(cudaGetLastError());
     return APL_OK;
 }
 
-int apl_xchg_pull(apl_xchg_t* x, int dtype, int nf, void* f0, void* f1, void* f2, int ld, void* scal, int n_scal,
-                  void* stream) {
+int xchg_pull_ex(apl_xchg* x, int dtype, int nf, void* f0, void* f1, void* f2, int ld, void* scal, int n_scal,
+                 int scal_f64, const double* skip_scal, int skip_a, int skip_b, int dyn_j, cudaStream_t s) {
     int rc = xchg_check(x, dtype, nf, f0, ld, n_scal, scal);
     if (rc != APL_OK) return rc;
+    XchgSkip sk;
+    sk.scal = skip_scal; sk.a = skip_a; sk.b = skip_b; sk.dyn_j = dyn_j;
     const long long n = nf > 0 ? x->n_shared : 0;
     const int grid = grid_rows(n);
-    cudaStream_t s = (cudaStream_t)stream;
     if (dtype == APL_F32)
         xchg_pull_kernel<float><<<grid, 128, 0, s>>>(x->base, x->world, x->rank, n, (const long long*)x->shared, x->row_ptr,
                                                      (const long long*)x->src, nf, (float*)f0, (float*)f1, (float*)f2, ld,
-                                                     (float*)scal, n_scal, x->off_scal, x->off_recv, x->recv_bytes,
-                                                     x->d_epoch, x->d_counters + 1);
+                                                     scal, n_scal, scal_f64, x->off_scal, x->off_recv, x->recv_bytes,
+                                                     x->d_epoch, x->d_counters + 1, sk);
     else
         xchg_pull_kernel<double><<<grid, 128, 0, s>>>(x->base, x->world, x->rank, n, (const long long*)x->shared,
                                                       x->row_ptr, (const long long*)x->src, nf, (double*)f0, (double*)f1,
-                                                      (double*)f2, ld, (double*)scal, n_scal, x->off_scal, x->off_recv,
-                                                      x->recv_bytes, x->d_epoch, x->d_counters + 1);
+                                                      (double*)f2, ld, scal, n_scal, scal_f64, x->off_scal, x->off_recv,
+                                                      x->recv_bytes, x->d_epoch, x->d_counters + 1, sk);
     APL_CUDA_CHECK(cudaGetLastError());
     return APL_OK;
+}
+}  // namespace apl
+
+extern "C" {
+
+int apl_xchg_push(apl_xchg_t* x, int dtype, int nf, const void* f0, const void* f1, const void* f2, int ld,
+                  const void* scal, int n_scal, void* stream) {
+    return apl::xchg_push_ex(x, dtype, nf, f0, f1, f2, ld, scal, n_scal, 0, nullptr, -1, -1, 0, (cudaStream_t)stream);
+}
+
+int apl_xchg_pull(apl_xchg_t* x, int dtype, int nf, void* f0, void* f1, void* f2, int ld, void* scal, int n_scal,
+                  void* stream) {
+    return apl::xchg_pull_ex(x, dtype, nf, f0, f1, f2, ld, scal, n_scal, 0, nullptr, -1, -1, 0, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -34,6 +34,8 @@ def partition_mesh(mesh: TetMesh, world: int, rank: int) -> Shard:
     Deterministic and identical on every rank (each rank computes the full ownership table from the
     connectivity; at 64M tets this is a few seconds of numpy and is setup-time work)."""
     T, V = mesh.n_cells, mesh.n_points
+    if not 1 <= world <= 64:
+        raise ValueError("partition_mesh keeps the ranks touching a vertex in a 64-bit mask: 1 <= world <= 64")
     bounds = [r * T // world for r in range(world + 1)]
     lo, hi = bounds[rank], bounds[rank + 1]
     cells = mesh.cells[lo:hi]

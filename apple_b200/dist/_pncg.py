@@ -8,22 +8,34 @@ import torch
 from apple_b200 import _lib, config
 from apple_b200.optim._pncg import ConvergenceCriteria, LineSearch, _classify
 
-from ._halo import HaloExchange
+from ._halo import HaloExchange, PeerHaloExchange
 from ._partition import Shard
 
 
 class ShardedPNCG:
-    """PNCG on a sharded mesh: the native phases of ``apple_b200/csrc/pncg.cu`` with the collectives
-    the path really needs between them (one halo sum per trial pass, three tiny all-reduces per
-    iteration).  Same recurrences as the single-GPU fused path; vector updates are replicated on
-    ghost vertices (their inputs are bit-identical on all sharers), reductions count owned entries."""
+    """PNCG on a sharded mesh: the native phases of ``apple_b200/csrc/pncg.cu`` with the exchanges the path really
+    needs between them (one halo sum per trial pass, three tiny all-reduces per iteration).  Same recurrences as the
+    single-GPU fused path; vector updates are replicated on ghost vertices (their inputs are bit-identical on all
+    sharers), reductions count owned entries.
+
+    ``transport="peer"`` (default on CUDA): the exchanges are peer-memory kernels attached to the native workspace
+    (``apl_pncg_set_exchange``), so ``iterate`` is ``apl_pncg_iterate`` -- the whole sharded iteration, line search
+    included, runs on the device (optionally as a CUDA graph, ``use_graph`` as in the single-GPU path) and the host
+    reads the scalars once per call.  ``transport="nccl"``: the phases are driven from the host with
+    ``torch.distributed`` collectives between them (one tiny D2H per line-search trial); kept for backends without
+    peer memory."""
 
     def __init__(self, potentials, ext_forces, shard: Shard, free_mask_local: torch.Tensor, u0_local: torch.Tensor,
                  *, criteria: ConvergenceCriteria | None = None, line_search: LineSearch | None = None, group=None,
-                 scatter: int | None = None):
+                 scatter: int | None = None, transport: str | None = None, use_graph: int = 0):
         self.shard = shard
         self.device, self.dtype = u0_local.device, u0_local.dtype
-        self.halo = HaloExchange(shard, self.device, group)
+        if transport is None:
+            transport = "peer" if (self.device.type == "cuda" and shard.world > 1) else "nccl"
+        if shard.world == 1 and self.device.type == "cuda":
+            transport = "local"        # nothing to exchange: the single-GPU device path
+        self.transport = transport
+        self.halo = PeerHaloExchange(shard, self.device, group) if transport == "peer" else HaloExchange(shard, self.device, group)
         self.criteria = criteria or ConvergenceCriteria()
         self.line_search = line_search or LineSearch()
         n = shard.n_local
@@ -46,19 +58,33 @@ class ShardedPNCG:
             _lib.dev_ptr(self.d[1]), _lib.dev_ptr(self.mask), _lib.dev_ptr(self.scal), ctypes.byref(handle)))
         self._handle = handle
         self._keep = list(potentials) + list(ext_forces)
+        for pot in list(potentials) + list(ext_forces):
+            if pot.dtype != self.dtype:
+                raise TypeError(f"potential {pot.name} is {pot.dtype}, state is {self.dtype}")
         for pot in potentials:
             _lib.check(L.apl_pncg_add_fem(handle, pot._handle))
         for ef in ext_forces:
+            # Loads are applied on every rank that lists the vertex and then halo-SUMMED: a load on a shared vertex must
+            # be listed by exactly one rank (its owner), or it is counted once per sharer.
+            if ef.indices.numel() and not bool(owned[ef.indices.long()].all()):
+                raise ValueError(f"sharded external force {ef.name}: list every loaded vertex on its OWNING rank only "
+                                 "(shard.owned); a load on a ghost copy would be counted once per sharer")
             _lib.check(L.apl_pncg_add_ext_force(handle, ef.indices.shape[0], _lib.dev_ptr(ef.materials.force),
                                                 _lib.dev_ptr(ef.indices)))
         c, ls = self.criteria, self.line_search
         sc = scatter if scatter is not None else config.scatter
         _lib.check(L.apl_pncg_set_params(handle, float(c.max_steps), float(c.target_relative_gradient_norm),
                                          float(c.absolute_gradient_norm), float(c.max_failed_line_searches),
-                                         float(ls.overstep), 1.0, float(ls.armijo), int(ls.max_steps), int(sc), 0))
-        self._phase(_lib.PHASE_INIT)
-        self.halo.sum_(self.g[0], self.d[0])
-        self.halo.all_reduce_(self.scal[_lib.S_F:_lib.S_F + 1])
+                                         float(ls.overstep), 1.0, float(ls.armijo), int(ls.max_steps), int(sc),
+                                         int(use_graph) if transport in ("peer", "local") else 0))
+        if transport in ("peer", "local"):
+            if transport == "peer":
+                _lib.check(L.apl_pncg_set_exchange(handle, self.halo._xchg))
+            self._phase(_lib.PHASE_INIT)           # f, g, diag at x, completed over the ranks on the device
+        else:
+            self._phase(_lib.PHASE_INIT)
+            self.halo.sum_(self.g[0], self.d[0])
+            self.halo.all_reduce_(self.scal[_lib.S_F:_lib.S_F + 1])
         self.n_steps = 0
 
     def __del__(self):
@@ -81,6 +107,13 @@ class ShardedPNCG:
 
     def iterate(self, n_iters: int) -> float:
         """Runs up to ``n_iters`` iterations; returns the DONE code (0 = still running)."""
+        if self.transport in ("peer", "local"):
+            # everything on the device; iterations after DONE are no-ops on every rank
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().apl_pncg_iterate(self._handle, int(n_iters), _lib.stream_ptr(self.device)))
+            s = self._read()
+            self.n_steps = int(s[_lib.S_K])
+            return float(s[_lib.S_DONE])
         S = _lib
         J = self.line_search.max_steps
         L = _lib.lib()

@@ -199,6 +199,10 @@ class _FusedState(_StateBase):
                     raise TypeError(f"potential {pot.name} is {pot.dtype}, state is {self.dtype}")
                 _lib.check(L.apl_pncg_add_fem(handle, pot._handle))
             else:
+                if pot.dtype != self.dtype:
+                    raise TypeError(f"potential {pot.name} is {pot.dtype}, state is {self.dtype}")
+                if getattr(pot, "_max_index", -1) >= n:
+                    raise IndexError(f"potential {pot.name} loads vertex {pot._max_index}, the model has {n} points")
                 _lib.check(L.apl_pncg_add_ext_force(handle, pot.indices.shape[0], _lib.dev_ptr(pot.materials.force),
                                                     _lib.dev_ptr(pot.indices)))
             self._keep.append(pot)

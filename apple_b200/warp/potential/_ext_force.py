@@ -26,6 +26,10 @@ class ExternalForce(WarpPotential):
         )
         if self.materials.force.shape != (self.indices.shape[0], 3):
             raise ValueError("force must have shape (len(indices), 3)")
+        idx = np.asarray(indices)
+        if idx.size and int(idx.min()) < 0:
+            raise IndexError("ExternalForce: negative vertex index")
+        self._max_index = int(idx.max()) if idx.size else -1
 
     @classmethod
     def from_pyvista(cls, obj, **kwargs):  # :55-61
@@ -38,8 +42,14 @@ class ExternalForce(WarpPotential):
         ops &= _lib.OP_FUN | _lib.OP_GRAD  # Hessian operators are no-ops (:80-90)
         if not ops or part == _lib.PART_INTERIOR:   # a split evaluation applies the loads with the boundary part
             return
-        ld_in = int(u.shape[1])
-        ld_out = int(grad.shape[1]) if (ops & _lib.OP_GRAD) else 3
+        # the kernel reinterprets raw pointers as `self.dtype`: a field of another dtype / layout must not get through
+        n_points = int(u.shape[0]) if u.dim() == 2 else -1
+        ld_in = _lib.field_ld(u, n_points, self.dtype, "u")
+        ld_out = _lib.field_ld(grad, n_points, self.dtype, "grad") if (ops & _lib.OP_GRAD) else 3
+        if (ops & _lib.OP_FUN) and (fun is None or fun.dtype != self.dtype or fun.numel() < 1):
+            raise TypeError(f"fun: expected a ({self.dtype}) tensor with one element")
+        if self._max_index >= n_points:
+            raise IndexError(f"ExternalForce loads vertex {self._max_index}, the field has {n_points} points")
         with torch.cuda.device(self.device):
             _lib.check(
                 _lib.lib().apl_ext_force_eval(

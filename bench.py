@@ -512,6 +512,14 @@ def main():
         except Exception as exc:  # pragma: no cover
             hvp = {"error": f"{type(exc).__name__}: {exc}"}
 
+    # ---- PNCG iterations/s on the same (sharded) mesh ----
+    pncg_big = None
+    if not args.no_pncg:
+        try:
+            pncg_big = bench_pncg_sharded(args, wl, pots, dtype, dev, w, world, max_over_ranks, barrier)
+        except Exception as exc:  # pragma: no cover
+            pncg_big = {"error": f"{type(exc).__name__}: {exc}"}
+
     clocks.__exit__(None, None, None)
     # release the headline model before the secondary sections
     del model, pots, sharded, res
@@ -560,7 +568,7 @@ def main():
             "clocks": clocks.summary(), "e2e": e2e,
             "gpu_launches": args.steps * launches_per_step,
             "roofline": roofline, "parity": parity, "hvp": hvp, "cpu_baseline": cpu, "config2": config2,
-            "pncg": (config2 or {}).get("pncg") if isinstance(config2, dict) else None,
+            "pncg": {"headline_mesh": pncg_big, "config2": (config2 or {}).get("pncg") if isinstance(config2, dict) else None},
         }
         print(json.dumps(line))
     if world > 1:
@@ -728,6 +736,53 @@ def bench_hvp(args, wl, kinds, dev, world, flush, max_over_ranks, T_total, peak)
         torch.cuda.empty_cache()
     out["note"] = ("one hess_prod evaluation of the whole model per step (halo sum included for N > 1), CUDA events, L2 "
                    "flushed; algorithmic bytes = 16 + 9w + materials + (V/T) 9w per tet")
+    return out
+
+
+def bench_pncg_sharded(args, wl, pots, dtype, dev, w, world, max_over_ranks, barrier):
+    """PNCG iterations/s on the benchmark mesh itself (all ranks): fixed base z = 0, device-side iteration with the
+    peer-memory exchanges inside the native workspace, WHILE-node CUDA graph per iteration."""
+    import torch
+
+    from apple_b200.dist import ShardedPNCG
+    from apple_b200.optim.pncg import ConvergenceCriteria
+
+    n = args.n
+    X = wl.mesh.points
+    free = torch.ones((wl.mesh.n_points, 3), dtype=torch.bool, device=dev)
+    free[X[:, 2] == 0.0] = False
+    h = 1.0 / n
+    u0 = (0.05 * h * torch.sin(7.0 * X[:, [1, 2, 0]] + 0.3)).to(dtype)
+    u0[~free] = 0.0
+    iters = max(10, min(args.pncg_iters, 50))
+    crit = ConvergenceCriteria(max_steps=iters + 30, target_relative_gradient_norm=0.0)
+    out = {}
+    for graph in (2, 0):
+        sp = ShardedPNCG(list(pots.values()), [], wl.shard, free, u0, criteria=crit, transport=args.transport if world > 1 else None,
+                         use_graph=graph)
+        sp.iterate(10)                                  # warm-up: graph capture
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        sp.iterate(iters)                               # one host read of the scalars at the end
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        dt = max_over_ranks(max(e0.elapsed_time(e1) * 1e-3, wall))
+        s = sp._read()
+        from apple_b200 import _lib
+
+        out[{2: "graph_while", 0: "eager"}[graph]] = {
+            "iters": iters, "seconds": dt, "iters_per_s": iters / dt, "accepted_total": int(s[_lib.S_N_ACCEPTED]),
+            "energy": float(s[_lib.S_F]), "transport": sp.transport}
+        del sp
+        torch.cuda.empty_cache()
+    out["iters_per_s"] = max(v["iters_per_s"] for v in out.values())
+    T_total = 5 * n ** 3
+    out["tets_per_s_equivalent"] = out["iters_per_s"] * 2 * T_total     # two element passes per iteration (A and B)
+    out["note"] = (f"{iters} iterations after 10 warm-up iterations on the {T_total}-tet mesh; max over ranks of CUDA-event / "
+                   "wall time around enqueue-and-sync; every exchange of the iteration is a device-side peer-memory kernel pair")
     return out
 
 

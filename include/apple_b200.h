@@ -202,7 +202,7 @@ int apl_halo_unpack(int dtype, int64_t n_shared, const int64_t* shared, const in
  * rank order, the own entry is ignored).  The plan arrays are DEVICE arrays owned by the caller (they must outlive
  * the handle): row i of the send list is this rank's partial on local vertex send_index[i], stored into row
  * send_row[i] of rank send_peer[i]'s receive buffer; (shared, row_ptr, src) is the CSR of apl_halo_unpack.
- *   apl_xchg_push: stores the shared rows of up to 3 fields (leading dimension ld) and up to 8 partial scalars
+ *   apl_xchg_push: stores the shared rows of up to 3 fields (leading dimension ld) and up to 16 partial scalars
  *                  (dtype, e.g. this rank's energy) into the peers' buffers and publishes the epoch.
  *   apl_xchg_pull: waits on the device until every rank's push of this epoch has landed, then sums the partials of
  *                  every shared vertex in ascending rank order into f0..f2 and the scalars, in rank order, into scal
@@ -284,6 +284,13 @@ int apl_pncg_add_ext_force(apl_pncg_t* ws, int64_t k, const void* force, const i
 int apl_pncg_set_params(apl_pncg_t* ws, double max_steps, double rtol_g, double atol_g, double max_fails,
                         double overstep, double max_step, double c1, int max_halvings, int scatter,
                         int use_graph);
+/* Sharded meshes (new functionality): with an exchange attached, every phase completes its partial results over all
+ * ranks on the device, right after the kernels that produced them -- the 11 sums of REDUCE, (g.p, p.Hp) after PASS_B,
+ * and per trial the halo sum of g', diag' with the trial energy (one push + one pull kernel each, guarded by the same
+ * skip flags as the trial) -- so apl_pncg_iterate runs the sharded iteration, CUDA graphs included, with no host round
+ * trip and no host-launched collective.  `mask` bit 1 must be clear on ghost copies; every rank must enqueue the same
+ * phases (the scalars are bit-identical on all ranks, so all ranks take the same decisions).  NULL detaches. */
+int apl_pncg_set_exchange(apl_pncg_t* ws, apl_xchg_t* x);
 int apl_pncg_current(const apl_pncg_t* ws);
 int apl_pncg_flip(apl_pncg_t* ws);
 /* Enqueue one phase (for callers that interleave collectives between phases: sharded meshes). */

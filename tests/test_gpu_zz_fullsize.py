@@ -138,3 +138,97 @@ def test_full_size_pncg_iterations_decrease_the_energy(native_lib, config2):
         assert opt.relative_grad_norm < 0.05
         runs[mode] = energies
     assert abs(runs[2][0] - runs[0][0]) <= 5e-3 * abs(runs[0][0])      # same trajectory after 20 iterations
+
+
+def test_config4_muscle_model_full_size_matches_c_oracle(native_lib):
+    """BASELINE.json configs[3] at its size: 74^3 x 5 = 2,026,120 tets, three potentials on one mesh in the pattern of
+    /root/reference/exp/2026/05/06/toy/src/21-smas-prestrain-stable-neo-hookean-muscle.py:228-240 -- fat (Stable
+    Neo-Hookean, Fraction = 1 - s), muscle (Stable Neo-Hookean x 1e3 with an activation field, Fraction = s) -- plus the
+    adjoint-side operator: the model's hess_prod.  Energy / gradient / diagonal / HVP of the SUM against the C
+    restatement of the reference (fp64, whole mesh)."""
+    from apple_b200 import _lib
+    from apple_b200.mesh import cube_tet_mesh
+    from apple_b200.warp.model import WarpModel
+    from oracle import cbind, region as oregion
+
+    n = 74
+    mesh = cube_tet_mesh(n, morton=True)
+    T, V = mesh.n_cells, mesh.n_points
+    assert T == 2_026_120
+    rng = np.random.default_rng(1)
+    cx = mesh.points[mesh.cells].mean(axis=1)
+    s = np.clip(0.5 + 0.5 * np.sin(6.0 * cx[:, 0]) * np.cos(5.0 * cx[:, 1]), 0.05, 0.95)      # muscle fraction field
+    mu = 10.0 ** rng.uniform(3.0, 4.0, T)
+    la = 10.0 ** rng.uniform(3.5, 4.5, T)
+    act = 0.05 * rng.standard_normal((T, 6))
+    slab = np.abs(cx[:, 2] - 0.5) < 0.1                                                        # prestrained slab
+    act[slab, :3] = np.array([1.2, 1.3 ** -2, 1.2]) - 1.0
+    act[slab, 3:] = 0.0
+    h = 1.0 / n
+    X = mesh.points
+    u = 0.05 * h * np.sin(7.0 * X[:, [1, 2, 0]] + 0.3) + 0.02 * h * rng.uniform(-1, 1, X.shape)
+    p = rng.uniform(-1, 1, X.shape)
+    dhdX, dV = oregion.compute_grad(mesh.points, mesh.cells)
+    fat_o = cbind.CPotential("snh", mesh.cells, dhdX, (1.0 - s) * dV, mu, la)
+    mus_o = cbind.CPotential("muscle", mesh.cells, dhdX, s * dV, 1e3 * mu, 1e3 * la, act)
+    e = np.zeros(1)
+    g, d, hp = (np.zeros((V, 3)) for _ in range(3))
+    for o in (fat_o, mus_o):
+        o.fun(u, e); o.grad(u, g); o.hess_diag(u, d); o.hess_prod(u, p, hp)
+    for dtype, tol in ((torch.float32, 1e-5), (torch.float64, 1e-10)):
+        fat_m, mus_m = mesh.copy(), mesh.copy()
+        fat_m.cell_data.update({"mu": mu, "lambda": la, "Fraction": 1.0 - s})
+        mus_m.cell_data.update({"mu": 1e3 * mu, "lambda": 1e3 * la, "Fraction": s, "activation": act})
+        model = WarpModel({"fat": cuda_potential("snh", fat_m, dtype, name="fat"),
+                           "muscle": cuda_potential("muscle", mus_m, dtype, name="muscle")})
+        ud = torch.as_tensor(u, dtype=dtype, device="cuda"); pd = torch.as_tensor(p, dtype=dtype, device="cuda")
+        fun = torch.zeros(1, dtype=dtype, device="cuda")
+        grad, diag, prod = (torch.zeros((V, 3), dtype=dtype, device="cuda") for _ in range(3))
+        model.eval(_lib.OP_FUN | _lib.OP_GRAD | _lib.OP_HESS_DIAG | _lib.OP_HESS_PROD, ud, pd, fun=fun, grad=grad,
+                   diag=diag, prod=prod)
+        torch.cuda.synchronize()
+        assert rel_err(fun.cpu(), e) < tol, dtype
+        assert rel_err(grad.cpu(), g) < tol, dtype
+        assert rel_err(diag.cpu(), d) < tol, dtype
+        assert rel_err(prod.cpu(), hp) < tol, dtype
+        # the adjoint solve's matvec alone, accumulated over the potentials exactly like WarpModel.hess_prod
+        out = torch.zeros((V, 3), dtype=dtype, device="cuda")
+        model.hess_prod(ud, pd, out)
+        torch.cuda.synchronize()
+        assert rel_err(out.cpu(), hp) < tol, dtype
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 2e-5)], ids=["f64", "f32"])
+def test_arap_on_compressed_and_inverted_elements(native_lib, dtype, tol):
+    """ARAP away from the comfortable regime: strongly compressed, near-flat and INVERTED tets take the robust
+    branch of csrc/elem_math.cuh (polar_twist falls back to the Jacobi SVD in the rotation-variant convention of
+    warp/math/_rotation.py:9-13: U, V proper rotations, the smallest singular value carries the sign of det F).  The
+    oracle's svd_rv restates the same convention with numpy's SVD; Warp's own wp.svd3 is unverifiable here
+    (SURVEY.md appendix C.1), so this pins the library to the oracle, not to Warp, on these elements."""
+    from helpers import make_case, oracle_potential
+
+    mesh, u, p = make_case(n=6, seed=11, amp=0.05)
+    V = mesh.n_points
+    rng = np.random.default_rng(5)
+    X = mesh.points
+    # squash the cube to 15 % of its height around z = 0.5, shear it, and push one plane of vertices through its neighbours
+    u = u.copy()
+    u[:, 2] += -0.85 * (X[:, 2] - 0.5)
+    u[:, 0] += 0.4 * X[:, 2]
+    layer = np.isclose(X[:, 2], X[:, 2][np.argsort(X[:, 2])[V // 2]])
+    u[layer, 2] += 0.25                                                   # inverts the tets above that plane
+    u += 0.01 * rng.standard_normal(u.shape)
+    ora = oracle_potential("arap", mesh)
+    J = np.linalg.det(ora._F(u).reshape(-1, 3, 3))
+    assert (J < 0).sum() > 20 and (np.abs(J) < 0.2).sum() > 50          # the case really contains such elements
+    pot = cuda_potential("arap", mesh, dtype)
+    ud = torch.as_tensor(u, dtype=dtype, device="cuda"); pd = torch.as_tensor(p, dtype=dtype, device="cuda")
+    fun, quad, grad, diag, prod = _eval(pot, 31, ud, pd, dtype, V)
+    e, q = np.zeros(1), np.zeros(1)
+    g, d, hp = (np.zeros((V, 3)) for _ in range(3))
+    ora.fun(u, e); ora.hess_quad(u, p, q); ora.grad(u, g); ora.hess_diag(u, d); ora.hess_prod(u, p, hp)
+    assert rel_err(fun.cpu(), e) < tol
+    assert rel_err(grad.cpu(), g) < tol
+    assert rel_err(diag.cpu(), d) < 10 * tol        # the twist rates 2 / max(s_i + s_j, 2) kink where s_i + s_j = 2
+    assert rel_err(prod.cpu(), hp) < 10 * tol
+    assert rel_err(quad.cpu(), q) < 10 * tol

@@ -98,13 +98,18 @@ for dtype, tol in ((torch.float64, 1e-10), (torch.float32, 1e-5)):
     fwd.state.u = torch.as_tensor(u0, dtype=dtype, device=dev)
     sol = fwd.step()
     free_local = torch.as_tensor(~fixed[shard.l2g], device=dev)
-    sp = ShardedPNCG(list(pots.values()), [], shard, free_local, torch.as_tensor(u0[shard.l2g], dtype=dtype, device=dev), criteria=crit)
-    res = sp.solve(check_every=iters)
-    eu = float((sp.u_local - fwd.state.u[idx]).abs().max() / fwd.state.u.abs().max())
     ptol = 1e-8 if dtype == torch.float64 else 2e-4
-    good = eu < ptol and res["n_steps"] == sol.stats["n_steps"] and abs(res["fun"] - sol.stats["fun"]) <= 10 * ptol * abs(sol.stats["fun"])
-    ok &= good
-    print(f"rank {rank} {dtype} PNCG {res['n_steps']} its: |u-u1|/|u1| = {eu:.2e}, f = {res['fun']:.10e} vs {sol.stats['fun']:.10e}, accepted {res['n_accepted']} vs {sol.stats['n_accepted']} {'OK' if good else 'FAIL'}", flush=True)
+    # device-side sharded iteration (peer-memory exchanges inside apl_pncg_iterate; plain launches, static graph, WHILE
+    # graph) and the host-driven NCCL path
+    for transport, graph in (("peer", 0), ("peer", 1), ("peer", 2), ("nccl", 0)):
+        sp = ShardedPNCG(list(pots.values()), [], shard, free_local, torch.as_tensor(u0[shard.l2g], dtype=dtype, device=dev),
+                         criteria=crit, transport=transport, use_graph=graph)
+        res = sp.solve(check_every=iters)
+        eu = float((sp.u_local - fwd.state.u[idx]).abs().max() / fwd.state.u.abs().max())
+        good = eu < ptol and res["n_steps"] == sol.stats["n_steps"] and abs(res["fun"] - sol.stats["fun"]) <= 10 * ptol * abs(sol.stats["fun"])
+        ok &= good
+        print(f"rank {rank} {dtype} PNCG[{transport}, graph {graph}] {res['n_steps']} its: |u-u1|/|u1| = {eu:.2e}, f = {res['fun']:.10e} vs {sol.stats['fun']:.10e}, accepted {res['n_accepted']} vs {sol.stats['n_accepted']} {'OK' if good else 'FAIL'}", flush=True)
+        del sp
 flag = torch.tensor([1.0 if ok else 0.0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()
