@@ -107,6 +107,17 @@ __device__ __forceinline__ void load_row<double>(const double* __restrict__ base
     }
 }
 
+// Scalar REDs as explicit PTX: `atomicAdd` with an unused result compiles to ATOMG ... PT, RZ here, which still
+// allocates a WRITE scoreboard that clears only when L2 answers -- every consumer warp then stalled for the whole
+// atomic round trip at the back edge of the tile loop (ncu r2d: 23 % of all stall samples on that branch).  `red` has
+// no destination: only the operand-read scoreboard, released when the LSU has taken the request.
+__device__ __forceinline__ void red_add(float* q, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(q), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add(double* q, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(q), "d"(v) : "memory");
+}
+
 // out[v, 0:3] += val[0:3]  -- one vector RED where the layout allows it
 __device__ __forceinline__ void red_row(float* base, int v, int ld, const float* val) {
     if (ld == 4) {
@@ -118,9 +129,9 @@ __device__ __forceinline__ void red_row(float* base, int v, int ld, const float*
         float* q = base + 3ll * v;
         if ((v & 1) == 0) {  // 3v even -> (x,y) is 8-byte aligned
             asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(q), "f"(val[0]), "f"(val[1]) : "memory");
-            atomicAdd(q + 2, val[2]);
+            red_add(q + 2, val[2]);
         } else {  // 3v+1 even -> (y,z) is 8-byte aligned
-            atomicAdd(q, val[0]);
+            red_add(q, val[0]);
             asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(q + 1), "f"(val[1]), "f"(val[2]) : "memory");
         }
     }
@@ -128,9 +139,9 @@ __device__ __forceinline__ void red_row(float* base, int v, int ld, const float*
 
 __device__ __forceinline__ void red_row(double* base, int v, int ld, const double* val) {
     double* q = base + (long long)ld * v;
-    atomicAdd(q, val[0]);
-    atomicAdd(q + 1, val[1]);
-    atomicAdd(q + 2, val[2]);
+    red_add(q, val[0]);
+    red_add(q + 1, val[1]);
+    red_add(q + 2, val[2]);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -346,9 +357,21 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
 __device__ __forceinline__ void mbar_arrive(unsigned bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+#ifndef APL_WAIT_HINT_NS
+#define APL_WAIT_HINT_NS 0   // > 0: suspend-time hint of mbarrier.try_wait (fewer spin instructions competing for issue slots)
+#endif
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     unsigned ok;
     do {
+#if APL_WAIT_HINT_NS > 0
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"((unsigned)APL_WAIT_HINT_NS)
+            : "memory");
+#else
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -356,6 +379,7 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
             : "=r"(ok)
             : "r"(bar), "r"(parity)
             : "memory");
+#endif
     } while (!ok);
 }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
@@ -804,9 +828,9 @@ __global__ void __launch_bounds__(kTileTets) fem_atomic_kernel(const FemArgs<T> 
                 const long long o = (long long)a.ld_out * gv[c];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    if constexpr (Cfg::kGrad) { if (a.grad) atomicAdd(a.grad + o + i, g[c][i]); }
-                    if constexpr (Cfg::kDiag) { if (a.diag) atomicAdd(a.diag + o + i, dg[c][i]); }
-                    if constexpr (Cfg::kProd) { if (a.prod) atomicAdd(a.prod + o + i, hp[c][i]); }
+                    if constexpr (Cfg::kGrad) { if (a.grad) red_add(a.grad + o + i, g[c][i]); }
+                    if constexpr (Cfg::kDiag) { if (a.diag) red_add(a.diag + o + i, dg[c][i]); }
+                    if constexpr (Cfg::kProd) { if (a.prod) red_add(a.prod + o + i, hp[c][i]); }
                 }
             }
         }
