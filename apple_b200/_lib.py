@@ -22,8 +22,10 @@ OK = 0
 F32, F64 = 0, 1
 KIND_SNH, KIND_ARAP, KIND_SNH_MUSCLE, KIND_SNH_ARAP = 0, 1, 2, 3
 OP_FUN, OP_GRAD, OP_HESS_DIAG, OP_HESS_PROD, OP_HESS_QUAD = 1, 2, 4, 8, 16
+OP_HESS_OFFD, OP_PSD = 32, 64      # opt-in supersets: vertex-block off-diagonals, eigenvalue-clamped Hessian
 SCATTER_TILE, SCATTER_ATOMIC, SCATTER_TILE_SIMPLE = 0, 1, 2
 PNCG_NSCAL = 96
+PCG_NSCAL = 16
 S_F, S_F_PREV, S_GP, S_PHP, S_ALPHA, S_BETA, S_GNORM2, S_GNORM2_FIRST = 0, 1, 2, 3, 4, 5, 6, 7
 S_ACCEPTED, S_LS_STEPS, S_K, S_N_ACCEPTED, S_DIAG_MEAN, S_GPG, S_DONE, S_FAILS, S_F_NEW, S_J = 8, 9, 10, 11, 12, 13, 15, 16, 17, 18
 S_SUMS, S_ALPHA_J, S_ACC_J, S_FT_J = 20, 32, 48, 64
@@ -74,11 +76,19 @@ SIGNATURES = {
     "apl_pncg_add_ext_force": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "apl_pncg_set_params": (c_int, [c_void_p, c_double, c_double, c_double, c_double, c_double, c_double, c_double,
                                     c_int, c_int, c_int]),
+    "apl_pncg_set_block_jacobi": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "apl_pncg_set_exchange": (c_int, [c_void_p, c_void_p]),
     "apl_pncg_current": (c_int, [c_void_p]),
     "apl_pncg_flip": (c_int, [c_void_p]),
     "apl_pncg_phase": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "apl_pncg_iterate": (c_int, [c_void_p, c_int, c_void_p]),
+    "apl_pcg_create": (c_int, [c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, POINTER(c_void_p)]),
+    "apl_pcg_destroy": (None, [c_void_p]),
+    "apl_pcg_add_fem": (c_int, [c_void_p, c_void_p]),
+    "apl_pcg_set_params": (c_int, [c_void_p, c_double, c_double, c_int64, c_int, c_int, c_int]),
+    "apl_pcg_init": (c_int, [c_void_p, c_int, c_void_p]),
+    "apl_pcg_iterate": (c_int, [c_void_p, c_int, c_void_p]),
 }
 
 _lib = None

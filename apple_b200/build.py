@@ -42,6 +42,7 @@ def _units():
         ("tiling", "tiling.cpp", []),
         ("capi", "capi.cu", []),
         ("pncg", "pncg.cu", []),
+        ("pcg", "pcg.cu", []),
         ("setup", "setup.cu", []),
         ("xchg", "xchg.cu", []),
     ]

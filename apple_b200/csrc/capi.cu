@@ -122,7 +122,7 @@ static int eval_typed(apl_fem* f, int ops, const void* u, const void* p, int ld_
     a.ld_in = ld_in;
     a.grad = (ops & APL_OP_GRAD) ? (T*)grad : nullptr;
     a.diag = (ops & APL_OP_HESS_DIAG) ? (T*)diag : nullptr;
-    a.prod = (ops & APL_OP_HESS_PROD) ? (T*)prod : nullptr;
+    a.prod = (ops & (APL_OP_HESS_PROD | APL_OP_HESS_OFFD)) ? (T*)prod : nullptr;
     a.ld_out = ld_out;
     a.fun = (ops & APL_OP_FUN) ? (T*)fun : nullptr;
     a.quad = (ops & APL_OP_HESS_QUAD) ? (T*)quad : nullptr;
@@ -317,14 +317,16 @@ static int grid_for(long long n, int block) {
 
 int fem_eval_pncg(apl_fem* f, int ops, const void* x, const void* p, const void* axpy_p, double* scal,
                   int alpha_idx, int skip_a, int skip_b, double* fun_d, double* quad_d, void* grad, void* diag,
-                  int scatter, cudaStream_t stream, int dyn_j) {
+                  int scatter, cudaStream_t stream, int dyn_j, void* third) {
     PncgExtras ex;
     ex.axpy_p = axpy_p; ex.scal = scal; ex.alpha_idx = alpha_idx; ex.skip_a = skip_a; ex.skip_b = skip_b;
     ex.dyn_j = dyn_j;
     ex.fun_d = fun_d; ex.quad_d = quad_d;
+    if (f->kind == APL_KIND_ARAP) ops &= ~APL_OP_PSD;
+    // `third`: the hess_prod output or the vertex-block off-diagonals (APL_OP_HESS_OFFD), ld = 4 like the others
     return f->dtype == APL_F32
-               ? eval_typed<float>(f, ops, x, p, 4, nullptr, nullptr, grad, diag, nullptr, 4, scatter, stream, &ex)
-               : eval_typed<double>(f, ops, x, p, 4, nullptr, nullptr, grad, diag, nullptr, 4, scatter, stream, &ex);
+               ? eval_typed<float>(f, ops, x, p, 4, nullptr, nullptr, grad, diag, third, 4, scatter, stream, &ex)
+               : eval_typed<double>(f, ops, x, p, 4, nullptr, nullptr, grad, diag, third, 4, scatter, stream, &ex);
 }
 
 int ext_force_pncg(int dtype, int ops, int64_t k, const void* force, const int32_t* indices, const void* x,
@@ -572,7 +574,12 @@ int apl_fem_eval_part(apl_fem_t* f, int part, int ops, const void* u, const void
         set_error("apl_fem_eval_part: unknown part");
         return APL_ERR_INVALID;
     }
-    if (ops <= 0 || ops > 31) { set_error("apl_fem_eval: ops must be a non-empty OR of APL_OP_*"); return APL_ERR_INVALID; }
+    if (ops <= 0 || ops > 127 || !(ops & 63)) { set_error("apl_fem_eval: ops must be a non-empty OR of APL_OP_*"); return APL_ERR_INVALID; }
+    if ((ops & APL_OP_HESS_OFFD) && (ops & (APL_OP_HESS_PROD | APL_OP_HESS_QUAD))) {
+        set_error("apl_fem_eval: APL_OP_HESS_OFFD shares the `prod` output and combines with FUN, GRAD and HESS_DIAG only");
+        return APL_ERR_INVALID;
+    }
+    if ((ops & APL_OP_PSD) && f->kind == APL_KIND_ARAP) ops &= ~APL_OP_PSD;   // ARAP: the clamped twist rates are the projection
     if ((ld_in != 3 && ld_in != 4) || (ld_out != 3 && ld_out != 4)) {
         set_error("apl_fem_eval: leading dimensions must be 3 or 4");
         return APL_ERR_INVALID;
@@ -583,7 +590,7 @@ int apl_fem_eval_part(apl_fem_t* f, int part, int ops, const void* u, const void
     }
     if (!u || ((ops & (APL_OP_HESS_PROD | APL_OP_HESS_QUAD)) && !p) || ((ops & APL_OP_FUN) && !fun) ||
         ((ops & APL_OP_HESS_QUAD) && !quad) || ((ops & APL_OP_GRAD) && !grad) ||
-        ((ops & APL_OP_HESS_DIAG) && !diag) || ((ops & APL_OP_HESS_PROD) && !prod)) {
+        ((ops & APL_OP_HESS_DIAG) && !diag) || ((ops & (APL_OP_HESS_PROD | APL_OP_HESS_OFFD)) && !prod)) {
         set_error("apl_fem_eval: an array required by `ops` is NULL");
         return APL_ERR_INVALID;
     }
@@ -597,7 +604,7 @@ int apl_fem_eval_part(apl_fem_t* f, int part, int ops, const void* u, const void
         auto bad = [](const void* ptr, uintptr_t mask) { return ptr && ((uintptr_t)ptr & mask) != 0; };
         if (bad(u, in_mask) || ((ops & (APL_OP_HESS_PROD | APL_OP_HESS_QUAD)) && bad(p, in_mask)) ||
             ((ops & APL_OP_GRAD) && bad(grad, out_mask)) || ((ops & APL_OP_HESS_DIAG) && bad(diag, out_mask)) ||
-            ((ops & APL_OP_HESS_PROD) && bad(prod, out_mask))) {
+            ((ops & (APL_OP_HESS_PROD | APL_OP_HESS_OFFD)) && bad(prod, out_mask))) {
             set_error("apl_fem_eval: nodal fields must be 16-byte aligned for ld = 4 and outputs 8-byte aligned for ld = 3");
             return APL_ERR_INVALID;
         }

@@ -36,6 +36,8 @@
 #define APL_OP_HESS_DIAG 4
 #define APL_OP_HESS_PROD 8
 #define APL_OP_HESS_QUAD 16
+#define APL_OP_HESS_OFFD 32  // off-diagonal entries (xy, xz, yz) of the 3x3 vertex blocks of the Hessian (block Jacobi)
+#define APL_OP_PSD 64        // modifier: Hessian terms of the Stable Neo-Hookean kinds use the eigenvalue-clamped d2Psi/dF2
 
 namespace apl {
 
@@ -395,17 +397,148 @@ APL_HD void put(T& dst, T v) {
     else dst = v;
 }
 
+// Negative part of the spectrum of d2Psi/dF2 of the Stable Neo-Hookean energy, analytically (opt-in APL_OP_PSD; a
+// superset of the reference, whose only safeguards are the clamps of warp/fem/_base.py:317-320,379-380).
+//   H_F = mu 1 + lambda g g^T + c3 H_J,   g = vec cof F,  H_J dF = X(F, dF),  c3 = -mu + lambda (J - 1).
+// With F = U diag(s) V^T (U, V rotations) and dF = U A V^T, H_J acts on A pair-wise: on the off-diagonal pair (i, j)
+// with third index k it maps (A_ij, A_ji) to -s_k (A_ji, A_ij), so
+//   twist  modes  U (E_ij - E_ji)/sqrt2 V^T   have eigenvalue  mu + c3 s_k,
+//   flip   modes  U (E_ij + E_ji)/sqrt2 V^T   have eigenvalue  mu - c3 s_k      (both orthogonal to g),
+// and the three scaling modes U diag(e) V^T are the eigenvectors of the 3x3 matrix
+//   A_s = mu 1 + c3 [[0, s2, s1], [s2, 0, s0], [s1, s0, 0]] + lambda gh gh^T,   gh = (s1 s2, s0 s2, s0 s1).
+// SnhNeg holds the frame and min(eigenvalue, 0) of all nine modes; H_F^+ = H_F - sum_i neg_i q_i q_i^T.
+template <typename T>
+struct SnhNeg {
+    T U[9], V[9];
+    T tw[3], fl[3];   // min(eigenvalue, 0) of the twist / flip mode about axis k
+    T sc[3], S[9];    // min(eigenvalue, 0) of the scaling modes, eigenvectors = columns of S
+};
+
+template <typename T>
+APL_HD void snh_negative_modes(const T* F, T mu, T la, T c3, SnhNeg<T>& n) {
+    T sg[3];
+    svd3_rv(F, n.U, sg, n.V);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const T a = mu + c3 * sg[k], b = mu - c3 * sg[k];
+        n.tw[k] = a < (T)0 ? a : (T)0;
+        n.fl[k] = b < (T)0 ? b : (T)0;
+    }
+    const T gh[3] = {sg[1] * sg[2], sg[0] * sg[2], sg[0] * sg[1]};
+    T A[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) A[3 * i + j] = la * gh[i] * gh[j] + (i == j ? mu : c3 * sg[3 - i - j]);
+    n.S[0] = 1; n.S[1] = 0; n.S[2] = 0; n.S[3] = 0; n.S[4] = 1; n.S[5] = 0; n.S[6] = 0; n.S[7] = 0; n.S[8] = 1;
+    constexpr int kMaxSweeps = (sizeof(T) == 4) ? 6 : 10;
+    const T scale = fabs(A[0]) + fabs(A[4]) + fabs(A[8]) + fabs(A[1]) + fabs(A[2]) + fabs(A[5]);
+    const T eps = (sizeof(T) == 4) ? (T)2.4e-7 : (T)8.9e-16;
+    const T tol = eps * eps * scale * scale;
+#pragma unroll 1
+    for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
+        jacobi_rotate(A, n.S, 0, 1);
+        jacobi_rotate(A, n.S, 0, 2);
+        jacobi_rotate(A, n.S, 1, 2);
+        const T off = A[1] * A[1] + A[2] * A[2] + A[5] * A[5];
+        if (apl_all_done(off <= tol)) break;
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m) n.sc[m] = A[4 * m] < (T)0 ? A[4 * m] : (T)0;
+}
+
+// C = sum_i neg_i <q_i, dF> q_i (3x3, row-major) and r = sum_i neg_i <q_i, dF>^2 (<= 0)
+template <typename T>
+APL_HD T snh_negative_apply(const SnhNeg<T>& n, const T* dF, T* C) {
+    T A[9], W[9];   // A = U^T dF V
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) W[3 * i + j] = n.U[i] * dF[j] + n.U[3 + i] * dF[3 + j] + n.U[6 + i] * dF[6 + j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) A[3 * i + j] = W[3 * i] * n.V[j] + W[3 * i + 1] * n.V[3 + j] + W[3 * i + 2] * n.V[6 + j];
+    T Ch[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    T r = (T)0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int i = (k + 1) % 3, j = (k + 2) % 3;
+        const T t = (T)0.5 * (A[3 * i + j] - A[3 * j + i]), f = (T)0.5 * (A[3 * i + j] + A[3 * j + i]);
+        // <q,dF> q = (A_ij -+ A_ji)/2 (E_ij -+ E_ji);  <q,dF>^2 = 2 t^2 resp. 2 f^2
+        Ch[3 * i + j] = n.tw[k] * t + n.fl[k] * f;
+        Ch[3 * j + i] = -n.tw[k] * t + n.fl[k] * f;
+        r += (T)2 * (n.tw[k] * t * t + n.fl[k] * f * f);
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        const T c = n.S[m] * A[0] + n.S[3 + m] * A[4] + n.S[6 + m] * A[8];
+        const T w = n.sc[m] * c;
+        Ch[0] += w * n.S[m]; Ch[4] += w * n.S[3 + m]; Ch[8] += w * n.S[6 + m];
+        r += w * c;
+    }
+    // C = U Ch V^T
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) W[3 * i + j] = n.U[3 * i] * Ch[j] + n.U[3 * i + 1] * Ch[3 + j] + n.U[3 * i + 2] * Ch[6 + j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) C[3 * i + j] = W[3 * i] * n.V[3 * j] + W[3 * i + 1] * n.V[3 * j + 1] + W[3 * i + 2] * n.V[3 * j + 2];
+    return r;
+}
+
+// K = sum_i neg_i (q_i d)(q_i d)^T for a row d of dhdX, packed [xx, yy, zz, xy, xz, yz] (negative semi-definite)
+template <typename T>
+APL_HD void snh_negative_block(const SnhNeg<T>& n, const T* d, T* K) {
+    const T dh[3] = {n.V[0] * d[0] + n.V[3] * d[1] + n.V[6] * d[2], n.V[1] * d[0] + n.V[4] * d[1] + n.V[7] * d[2],
+                     n.V[2] * d[0] + n.V[5] * d[1] + n.V[8] * d[2]};   // V^T d
+    T Kh[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int i = (k + 1) % 3, j = (k + 2) % 3;
+        // twist: z_i = d_j / sqrt2, z_j = -d_i / sqrt2;  flip: z_i = d_j / sqrt2, z_j = d_i / sqrt2
+        const T a = (T)0.5 * (n.tw[k] + n.fl[k]), b = (T)0.5 * (n.fl[k] - n.tw[k]);
+        Kh[3 * i + i] += a * dh[j] * dh[j];
+        Kh[3 * j + j] += a * dh[i] * dh[i];
+        Kh[3 * i + j] += b * dh[i] * dh[j];
+        Kh[3 * j + i] += b * dh[i] * dh[j];
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        const T z[3] = {n.S[m] * dh[0], n.S[3 + m] * dh[1], n.S[6 + m] * dh[2]};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Kh[3 * i + j] += n.sc[m] * z[i] * z[j];
+    }
+    // K = U Kh U^T
+    T W[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) W[3 * i + j] = n.U[3 * i] * Kh[j] + n.U[3 * i + 1] * Kh[3 + j] + n.U[3 * i + 2] * Kh[6 + j];
+    auto kij = [&](int i, int j) { return W[3 * i] * n.U[3 * j] + W[3 * i + 1] * n.U[3 * j + 1] + W[3 * i + 2] * n.U[3 * j + 2]; };
+    K[0] = kij(0, 0); K[1] = kij(1, 1); K[2] = kij(2, 2); K[3] = kij(0, 1); K[4] = kij(0, 2); K[5] = kij(1, 2);
+}
+
 // Stable Neo-Hookean (warp/fem/_stable_neo_hookean.py:17-103) on F with dhdX block D.
+// od (OP_HESS_OFFD): off-diagonal entries (xy, xz, yz) of the vertex blocks  vol (mu |D_a|^2 1 + lambda w_a w_a^T),
+// w_a = row a of dhdX cof(F)^T (the h6 term has no block-diagonal part: func/_hess_diag.py:69-72).
 template <typename T, int OPS, bool ACC>
 APL_HD void snh_terms(const T* F, const T* dF, const T* D, T vol, T mu, T la, T& psi, T& quad, T* P, T* M,
-                      T dg[4][3]) {
+                      T dg[4][3], T od[4][3]) {
     constexpr bool kFun = (OPS & APL_OP_FUN) != 0, kGrad = (OPS & APL_OP_GRAD) != 0;
     constexpr bool kDiag = (OPS & APL_OP_HESS_DIAG) != 0, kProd = (OPS & APL_OP_HESS_PROD) != 0;
-    constexpr bool kQuad = (OPS & APL_OP_HESS_QUAD) != 0;
+    constexpr bool kQuad = (OPS & APL_OP_HESS_QUAD) != 0, kOffd = (OPS & APL_OP_HESS_OFFD) != 0;
+    constexpr bool kPsd = (OPS & APL_OP_PSD) != 0 && (kDiag || kOffd || kProd || kQuad);
     T C[9];
     const T J = cofactor(F, C);
     const T Jm1 = J - (T)1;
     const T c3 = -mu + la * Jm1;
+    SnhNeg<T> neg;
+    if constexpr (kPsd) snh_negative_modes(F, mu, la, c3, neg);
     if constexpr (kFun) {
         const T I2 = ddot9(F, F);
         put<ACC>(psi, vol * ((T)0.5 * mu * (I2 - (T)3) - mu * Jm1 + (T)0.5 * la * Jm1 * Jm1));
@@ -415,27 +548,46 @@ APL_HD void snh_terms(const T* F, const T* dF, const T* D, T vol, T mu, T la, T&
 #pragma unroll
         for (int k = 0; k < 9; ++k) put<ACC>(P[k], a * F[k] + b * C[k]);
     }
-    if constexpr (kDiag) {
+    if constexpr (kDiag || kOffd) {
         T W[4][3], n[4];
         vjp_rows(D, C, (T)1, W);
         row_norms(D, n);
+        const T Dr[4][3] = {{-(D[0] + D[3] + D[6]), -(D[1] + D[4] + D[7]), -(D[2] + D[5] + D[8])},
+                            {D[0], D[1], D[2]}, {D[3], D[4], D[5]}, {D[6], D[7], D[8]}};
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 4; ++a) {
+            T K[6] = {0, 0, 0, 0, 0, 0};
+            if constexpr (kPsd) snh_negative_block(neg, Dr[a], K);
+            if constexpr (kDiag) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
-                put<ACC>(dg[a][i], apl_max(vol * (la * W[a][i] * W[a][i] + mu * n[a]), (T)0));
+                for (int i = 0; i < 3; ++i)
+                    put<ACC>(dg[a][i], apl_max(vol * (la * W[a][i] * W[a][i] + mu * n[a] - K[i]), (T)0));
+            }
+            if constexpr (kOffd) {
+                put<ACC>(od[a][0], vol * (la * W[a][0] * W[a][1] - K[3]));
+                put<ACC>(od[a][1], vol * (la * W[a][0] * W[a][2] - K[4]));
+                put<ACC>(od[a][2], vol * (la * W[a][1] * W[a][2] - K[5]));
+            }
+        }
     }
     if constexpr (kProd || kQuad) {
         T X[9];
         dcofactor(F, dF, X);
         const T s = ddot9(C, dF);
+        T Cn[9];
+        T rn = (T)0;
+        if constexpr (kPsd) rn = snh_negative_apply(neg, dF, Cn);
         if constexpr (kProd) {
             const T a = vol * la * s, b = vol * mu, c = vol * c3;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) put<ACC>(M[k], a * C[k] + b * dF[k] + c * X[k]);
+            for (int k = 0; k < 9; ++k) {
+                T m = a * C[k] + b * dF[k] + c * X[k];
+                if constexpr (kPsd) m -= vol * Cn[k];
+                put<ACC>(M[k], m);
+            }
         }
         if constexpr (kQuad) {
-            const T q = la * s * s + mu * ddot9(dF, dF) + c3 * ddot9(dF, X);
+            const T q = la * s * s + mu * ddot9(dF, dF) + c3 * ddot9(dF, X) - rn;
             put<ACC>(quad, apl_max(vol * q, (T)0));
         }
     }
@@ -623,10 +775,11 @@ APL_HD void sym_mul(const T* L, T x0, T x1, T x2, T& y0, T& y1, T& y2) {
 //   p^T H p = mu (|dF|^2 - a^T Lam a / 2),   H p = mu (dF - R [b]_x),  b = Lam a / 2  (row i of R [b]_x = r_i x b),
 //   (dhdX Q_k^T)[a][i] = w_k . (D_a x r_i) / sqrt2, hence diag[a][i] = mu (|D_a|^2 - z^T Lam z / 2), z = D_a x r_i.
 template <typename T, int OPS, bool ACC>
-APL_HD void arap_terms(const T* F, const T* dF, const T* D, T vol, T mu, T& psi, T& quad, T* P, T* M, T dg[4][3]) {
+APL_HD void arap_terms(const T* F, const T* dF, const T* D, T vol, T mu, T& psi, T& quad, T* P, T* M, T dg[4][3],
+                       T od[4][3]) {
     constexpr bool kFun = (OPS & APL_OP_FUN) != 0, kGrad = (OPS & APL_OP_GRAD) != 0;
     constexpr bool kDiag = (OPS & APL_OP_HESS_DIAG) != 0, kProd = (OPS & APL_OP_HESS_PROD) != 0;
-    constexpr bool kQuad = (OPS & APL_OP_HESS_QUAD) != 0;
+    constexpr bool kQuad = (OPS & APL_OP_HESS_QUAD) != 0, kOffd = (OPS & APL_OP_HESS_OFFD) != 0;
     T R[9], L[6], sg[3];
     polar_twist(F, R, L, sg);
     if constexpr (kFun || kGrad) {
@@ -642,23 +795,36 @@ APL_HD void arap_terms(const T* F, const T* dF, const T* D, T vol, T mu, T& psi,
             for (int k = 0; k < 9; ++k) put<ACC>(P[k], a * E[k]);
         }
     }
-    if constexpr (kDiag) {
+    if constexpr (kDiag || kOffd) {
+        // vertex block (i, j) = mu vol (|D_a|^2 delta_ij - z_i^T Lam z_j / 2),  z_i = D_a x r_i
         T n[4];
         row_norms(D, n);
         const T Dr[4][3] = {{-(D[0] + D[3] + D[6]), -(D[1] + D[4] + D[7]), -(D[2] + D[5] + D[8])},
                             {D[0], D[1], D[2]}, {D[3], D[4], D[5]}, {D[6], D[7], D[8]}};
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 4; ++a) {
+            T z[3][3], y[3][3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                const T z0 = Dr[a][1] * R[3 * i + 2] - Dr[a][2] * R[3 * i + 1];
-                const T z1 = Dr[a][2] * R[3 * i + 0] - Dr[a][0] * R[3 * i + 2];
-                const T z2 = Dr[a][0] * R[3 * i + 1] - Dr[a][1] * R[3 * i + 0];
-                T y0, y1, y2;
-                sym_mul(L, z0, z1, z2, y0, y1, y2);
-                const T h4 = (T)0.5 * (z0 * y0 + z1 * y1 + z2 * y2);
-                put<ACC>(dg[a][i], apl_max(vol * mu * (n[a] - h4), (T)0));
+                z[i][0] = Dr[a][1] * R[3 * i + 2] - Dr[a][2] * R[3 * i + 1];
+                z[i][1] = Dr[a][2] * R[3 * i + 0] - Dr[a][0] * R[3 * i + 2];
+                z[i][2] = Dr[a][0] * R[3 * i + 1] - Dr[a][1] * R[3 * i + 0];
+                sym_mul(L, z[i][0], z[i][1], z[i][2], y[i][0], y[i][1], y[i][2]);
             }
+            if constexpr (kDiag) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const T h4 = (T)0.5 * (z[i][0] * y[i][0] + z[i][1] * y[i][1] + z[i][2] * y[i][2]);
+                    put<ACC>(dg[a][i], apl_max(vol * mu * (n[a] - h4), (T)0));
+                }
+            }
+            if constexpr (kOffd) {
+                const T s = (T)-0.5 * vol * mu;
+                put<ACC>(od[a][0], s * (z[0][0] * y[1][0] + z[0][1] * y[1][1] + z[0][2] * y[1][2]));
+                put<ACC>(od[a][1], s * (z[0][0] * y[2][0] + z[0][1] * y[2][1] + z[0][2] * y[2][2]));
+                put<ACC>(od[a][2], s * (z[1][0] * y[2][0] + z[1][1] * y[2][1] + z[1][2] * y[2][2]));
+            }
+        }
     }
     if constexpr (kProd || kQuad) {
         // A = R^T dF; a = (A21 - A12, A02 - A20, A10 - A01)
@@ -695,6 +861,8 @@ APL_HD void arap_terms(const T* F, const T* dF, const T* D, T vol, T mu, T& psi,
 //                             rec = [D(9), vol_snh, mu_snh, lambda_snh, vol_arap, mu_arap]
 // Outputs: psi, quad (scalars), g = dhdX P^T, dg, hp = dhdX M^T, all volume-weighted and clamped as in
 // warp/fem/_base.py:243-383 (diag per entry, quad per cell -- per potential for the fused kind).
+// OP_HESS_OFFD (never together with OP_HESS_PROD) returns the off-diagonal entries (xy, xz, yz) of the 3x3 vertex
+// blocks in hp; with dg they are the block-Jacobi preconditioner.
 // ------------------------------------------------------------------------------------------
 template <typename T, int KIND, int OPS>
 APL_HD void elem_eval(const T* rec, const T (*uc)[3], const T (*pc)[3], T& psi, T& quad, T g[4][3], T dg[4][3],
@@ -735,15 +903,16 @@ APL_HD void elem_eval(const T* rec, const T (*uc)[3], const T (*pc)[3], T& psi, 
         edge_diff(pc, e);
         edge_outer(e, D, dF);
     }
+    static_assert(!((OPS & APL_OP_HESS_OFFD) && kProd), "hess_offd and hess_prod share an output");
     T P[9], M[9];
     if constexpr (KIND == APL_KIND_SNH || KIND == APL_KIND_SNH_MUSCLE) {
-        snh_terms<T, OPS, false>(F, dF, D, rec[9], rec[10], rec[11], psi, quad, P, M, dg);
+        snh_terms<T, OPS, false>(F, dF, D, rec[9], rec[10], rec[11], psi, quad, P, M, dg, hp);
     } else if constexpr (KIND == APL_KIND_ARAP) {
-        arap_terms<T, OPS, false>(F, dF, D, rec[9], rec[10], psi, quad, P, M, dg);
+        arap_terms<T, OPS, false>(F, dF, D, rec[9], rec[10], psi, quad, P, M, dg, hp);
     } else {
         static_assert(KIND == APL_KIND_SNH_ARAP, "unknown energy kind");
-        snh_terms<T, OPS, false>(F, dF, D, rec[9], rec[10], rec[11], psi, quad, P, M, dg);
-        arap_terms<T, OPS, true>(F, dF, D, rec[12], rec[13], psi, quad, P, M, dg);
+        snh_terms<T, OPS, false>(F, dF, D, rec[9], rec[10], rec[11], psi, quad, P, M, dg, hp);
+        arap_terms<T, OPS, true>(F, dF, D, rec[12], rec[13], psi, quad, P, M, dg, hp);
     }
     if constexpr (kGrad) vjp_rows1(D, P, g);
     if constexpr (kProd) vjp_rows1(D, M, hp);

@@ -888,6 +888,9 @@ int launch_one(const apl_fem* fem, const FemArgs<T>& args, int scatter, cudaStre
         int rc = resident_blocks(kern, fem->device, PC::kThreads, PC::kSmemBytes, cache[0], mu, blocks_per_sm);
         if (rc != APL_OK) return rc;
         kern<<<grid_of(blocks_per_sm), PC::kThreads, PC::kSmemBytes, stream>>>(args);
+    } else if constexpr ((OPS & (APL_OP_HESS_OFFD | APL_OP_PSD)) != 0) {
+        set_error("apl_fem_eval: APL_OP_HESS_OFFD / APL_OP_PSD are implemented by the TILE assembly only");
+        return APL_ERR_INVALID;
     } else if (scatter == APL_SCATTER_TILE_SIMPLE) {
         auto kern = fem_tile_kernel<T, KIND, OPS>;
         int rc = resident_blocks(kern, fem->device, kTileTets, Cfg::kSmemBytes, cache[1], mu, blocks_per_sm);
@@ -905,6 +908,36 @@ int launch_one(const apl_fem* fem, const FemArgs<T>& args, int scatter, cudaStre
 
 template <typename T, int KIND>
 int launch_fem_impl(const apl_fem* fem, int ops, const FemArgs<T>& args, int scatter, cudaStream_t stream) {
+    // Opt-in supersets (include/apple_b200.h): vertex-block off-diagonals and the eigenvalue-clamped Hessian exist in
+    // the TILE assembly only, in the combinations the block-Jacobi PNCG and the projected products need.
+    if (ops & (APL_OP_HESS_OFFD | APL_OP_PSD)) {
+        if (KIND == APL_KIND_ARAP) ops &= ~APL_OP_PSD;   // the clamped twist rates already are the projection
+        if (!(ops & (APL_OP_HESS_DIAG | APL_OP_HESS_OFFD | APL_OP_HESS_PROD | APL_OP_HESS_QUAD))) ops &= ~APL_OP_PSD;
+    }
+    if (ops & (APL_OP_HESS_OFFD | APL_OP_PSD)) {
+        if (scatter != APL_SCATTER_TILE) {
+            set_error("apl_fem_eval: APL_OP_HESS_OFFD / APL_OP_PSD are implemented by the TILE assembly only");
+            return APL_ERR_INVALID;
+        }
+        constexpr int BLK = APL_OP_FUN | APL_OP_GRAD | APL_OP_HESS_DIAG | APL_OP_HESS_OFFD;
+        const int psd = ops & APL_OP_PSD, base = ops & ~APL_OP_PSD;
+        if (base & APL_OP_HESS_OFFD) {
+            if (base & ~BLK) {
+                set_error("apl_fem_eval: APL_OP_HESS_OFFD combines with FUN, GRAD and HESS_DIAG only");
+                return APL_ERR_INVALID;
+            }
+            return psd ? launch_one<T, KIND, BLK | APL_OP_PSD>(fem, args, scatter, stream)
+                       : launch_one<T, KIND, BLK>(fem, args, scatter, stream);
+        }
+        // PSD without OFFD: the quadratic form alone (PNCG pass B), or any of fun / grad / diag / prod in one pass
+        if (base & APL_OP_HESS_QUAD) {
+            int rc = launch_one<T, KIND, APL_OP_HESS_QUAD | APL_OP_PSD>(fem, args, scatter, stream);
+            if (rc != APL_OK) return rc;
+            ops = base & ~APL_OP_HESS_QUAD;
+            if (!(ops & (APL_OP_HESS_DIAG | APL_OP_HESS_PROD))) return launch_fem_impl<T, KIND>(fem, ops, args, scatter, stream);
+        }
+        return launch_one<T, KIND, 15 | APL_OP_PSD>(fem, args, scatter, stream);
+    }
     // hess_quad never shares a pass with vector outputs here: PNCG needs it alone (pass B)
     if ((ops & APL_OP_HESS_QUAD) && ops != APL_OP_HESS_QUAD) {
         int rc = launch_one<T, KIND, APL_OP_HESS_QUAD>(fem, args, scatter, stream);

@@ -25,6 +25,7 @@
 
 #include "common.h"
 #include "fem_kernels.cuh"
+#include "vec_ops.cuh"
 
 struct apl_xchg;
 
@@ -32,7 +33,7 @@ namespace apl {
 
 int fem_eval_pncg(apl_fem* f, int ops, const void* x, const void* p, const void* axpy_p, double* scal,
                   int alpha_idx, int skip_a, int skip_b, double* fun_d, double* quad_d, void* grad, void* diag,
-                  int scatter, cudaStream_t stream, int dyn_j = 0);
+                  int scatter, cudaStream_t stream, int dyn_j = 0, void* third = nullptr);
 int ext_force_pncg(int dtype, int ops, int64_t k, const void* force, const int32_t* indices, const void* x,
                    const void* axpy_p, double* scal, int alpha_idx, int skip_a, int skip_b, double* fun_d,
                    void* grad, cudaStream_t stream, int dyn_j = 0);
@@ -42,84 +43,35 @@ int xchg_push_ex(apl_xchg* x, int dtype, int nf, const void* f0, const void* f1,
 int xchg_pull_ex(apl_xchg* x, int dtype, int nf, void* f0, void* f1, void* f2, int ld, void* scal, int n_scal,
                  int scal_f64, const double* skip_scal, int skip_a, int skip_b, int dyn_j, cudaStream_t s);
 
-constexpr int kVecThreads = 256;
 constexpr int kNSums = 11;
 
-template <typename T>
-__device__ __forceinline__ void ld4(const T* __restrict__ base, long long row, T v[4]) {
-    if constexpr (sizeof(T) == 4) {
-        const float4 q = reinterpret_cast<const float4*>(base)[row];
-        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    } else {
-        const double2 a = reinterpret_cast<const double2*>(base)[2 * row];
-        const double2 b = reinterpret_cast<const double2*>(base)[2 * row + 1];
-        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-    }
+// Block-Jacobi (opt-in, apl_pncg_set_block_jacobi): the preconditioner is the inverse of the 3x3 vertex blocks of the
+// Hessian, diag = (xx, yy, zz) and offd = (xy, xz, yz), restricted to the vertex's FREE components (rows / columns of
+// fixed components are replaced by the identity).  inv = [xx, yy, zz, xy, xz, yz] of the inverse; false when the
+// restricted block is not positive definite (the caller then applies the reference's scalar rule to that vertex).
+__device__ __forceinline__ bool block_inverse(const double d[3], const double o[3], const bool fr[3], double inv[6]) {
+    const double a00 = fr[0] ? d[0] : 1.0, a11 = fr[1] ? d[1] : 1.0, a22 = fr[2] ? d[2] : 1.0;
+    const double a01 = (fr[0] && fr[1]) ? o[0] : 0.0, a02 = (fr[0] && fr[2]) ? o[1] : 0.0, a12 = (fr[1] && fr[2]) ? o[2] : 0.0;
+    const double c00 = a11 * a22 - a12 * a12, c01 = a02 * a12 - a01 * a22, c02 = a01 * a12 - a02 * a11;
+    const double m2 = a00 * a11 - a01 * a01;
+    const double det = a00 * c00 + a01 * c01 + a02 * c02;
+    if (!(a00 > 0.0 && m2 > 0.0 && det > 0.0) || !isfinite(det)) return false;
+    const double r = 1.0 / det;
+    inv[0] = c00 * r; inv[1] = (a00 * a22 - a02 * a02) * r; inv[2] = m2 * r;
+    inv[3] = c01 * r; inv[4] = c02 * r; inv[5] = (a01 * a02 - a00 * a12) * r;
+    return true;
 }
-
-template <typename T>
-__device__ __forceinline__ void st4(T* __restrict__ base, long long row, const T v[4]) {
-    if constexpr (sizeof(T) == 4) {
-        reinterpret_cast<float4*>(base)[row] = make_float4(v[0], v[1], v[2], v[3]);
-    } else {
-        reinterpret_cast<double2*>(base)[2 * row] = make_double2(v[0], v[1]);
-        reinterpret_cast<double2*>(base)[2 * row + 1] = make_double2(v[2], v[3]);
-    }
+__device__ __forceinline__ void sym_apply(const double inv[6], const double x[3], double y[3]) {
+    y[0] = inv[0] * x[0] + inv[3] * x[1] + inv[4] * x[2];
+    y[1] = inv[3] * x[0] + inv[1] * x[1] + inv[5] * x[2];
+    y[2] = inv[4] * x[0] + inv[5] * x[1] + inv[2] * x[2];
 }
-
-// Grid-wide deterministic sum of NS doubles per thread -> out[0..NS) (overwritten by the last CTA).
-template <int NS>
-__device__ __forceinline__ void grid_reduce(double (&v)[NS], double* partials, unsigned int* counter, double* out) {
-    constexpr int NW = kVecThreads / 32;
-    __shared__ double red[NS][NW];
-    __shared__ bool is_last;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        const double w = warp_sum(v[s]);
-        if (lane == 0) red[s][wid] = w;
-    }
-    __syncthreads();
-    if (tid < NS) {
-        double s = 0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) s += red[tid][w];
-        partials[(size_t)blockIdx.x * NS + tid] = s;
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned int done = atomicAdd(counter, 1u);
-        is_last = (done == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    for (int s = 0; s < NS; ++s) {
-        double acc = 0;
-        for (int b = tid; b < (int)gridDim.x; b += kVecThreads) acc += __ldcg(partials + (size_t)b * NS + s);
-        acc = warp_sum(acc);
-        __syncthreads();
-        if (lane == 0) red[0][wid] = acc;
-        __syncthreads();
-        if (tid == 0) {
-            double t = 0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) t += red[0][w];
-            out[s] = t;
-        }
-    }
-    if (tid == 0) *counter = 0u;
-}
-
-// mask bits: 1 = free DOF (updated), 2 = counted in reductions (owned by this rank)
-#define APL_M_FREE 1
-#define APL_M_COUNT 2
 
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads) pncg_reduce_kernel(long long rows, const T* __restrict__ g,
                                                                  const T* __restrict__ gprev,
                                                                  const T* __restrict__ diag,
+                                                                 const T* __restrict__ offd,
                                                                  const T* __restrict__ pprev,
                                                                  const uchar4* __restrict__ mask, double* scal,
                                                                  double* partials, unsigned int* counter) {
@@ -134,6 +86,36 @@ __global__ void __launch_bounds__(kVecThreads) pncg_reduce_kernel(long long rows
         if (((m4.x | m4.y | m4.z | m4.w) & APL_M_COUNT) == 0) continue;
         T gv[4], gp[4], dv[4], pp[4];
         ld4(g, r, gv); ld4(gprev, r, gp); ld4(diag, r, dv); ld4(pprev, r, pp);
+        bool blocked = false;
+        if (offd) {
+            T ov[4];
+            ld4(offd, r, ov);
+            const bool fr[3] = {(m[0] & APL_M_FREE) != 0, (m[1] & APL_M_FREE) != 0, (m[2] & APL_M_FREE) != 0};
+            const double d3[3] = {(double)dv[0], (double)dv[1], (double)dv[2]};
+            const double o3[3] = {(double)ov[0], (double)ov[1], (double)ov[2]};
+            double inv[6];
+            if (block_inverse(d3, o3, fr, inv)) {
+                blocked = true;
+                double gi[3], yi[3], Pg[3], Py[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    gi[c] = fr[c] ? (double)gv[c] : 0.0;
+                    yi[c] = fr[c] ? (double)gv[c] - (double)gp[c] : 0.0;
+                }
+                sym_apply(inv, gi, Pg);
+                sym_apply(inv, yi, Py);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (!fr[c]) continue;
+                    s[0] += 1.0; s[1] += fabs(d3[c]);
+                    s[2] += gi[c] * Py[c]; s[4] += yi[c] * Py[c]; s[6] += gi[c] * Pg[c];
+                    s[8] += gi[c] * (double)pp[c];
+                    s[9] += yi[c] * (double)pp[c];
+                    s[10] += gi[c] * gi[c];
+                }
+            }
+        }
+        if (blocked) continue;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             if ((m[c] & (APL_M_FREE | APL_M_COUNT)) != (APL_M_FREE | APL_M_COUNT)) continue;
@@ -207,8 +189,10 @@ __global__ void pncg_finalize_kernel(double* scal, PncgParams prm) {
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads) pncg_direction_kernel(long long rows, const T* __restrict__ g,
                                                                     const T* __restrict__ diag,
+                                                                    const T* __restrict__ offd,
                                                                     const T* __restrict__ pprev, T* __restrict__ p,
                                                                     T* __restrict__ gz, T* __restrict__ dz,
+                                                                    T* __restrict__ oz,
                                                                     const uchar4* __restrict__ mask, double* scal,
                                                                     double* partials, unsigned int* counter) {
     if (__ldcg(scal + APL_S_DONE) != 0.0) return;
@@ -222,20 +206,46 @@ __global__ void __launch_bounds__(kVecThreads) pncg_direction_kernel(long long r
         const unsigned char m[4] = {m4.x, m4.y, m4.z, m4.w};
         T gv[4], dv[4], pp[4], pv[4];
         ld4(g, r, gv); ld4(diag, r, dv); ld4(pprev, r, pp);
+        bool blocked = false;
+        if (offd) {
+            T ov[4];
+            ld4(offd, r, ov);
+            const bool fr[3] = {(m[0] & APL_M_FREE) != 0, (m[1] & APL_M_FREE) != 0, (m[2] & APL_M_FREE) != 0};
+            const double d3[3] = {(double)dv[0], (double)dv[1], (double)dv[2]};
+            const double o3[3] = {(double)ov[0], (double)ov[1], (double)ov[2]};
+            double inv[6];
+            if (block_inverse(d3, o3, fr, inv)) {
+                blocked = true;
+                const double gi[3] = {fr[0] ? (double)gv[0] : 0.0, fr[1] ? (double)gv[1] : 0.0, fr[2] ? (double)gv[2] : 0.0};
+                double Pg[3];
+                sym_apply(inv, gi, Pg);
+                const bool counted = ((m4.x | m4.y | m4.z) & APL_M_COUNT) != 0;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            double pi = 0.0;
-            if (m[c] & APL_M_FREE) {
-                double d = fabs((double)dv[c]);
-                if (!(d > 0.0)) d = mean;
-                pi = -(double)gv[c] / d + beta * (double)pp[c];
-                if (m[c] & APL_M_COUNT) s[0] += (double)gv[c] * pi;
+                for (int c = 0; c < 3; ++c) {
+                    const double pi = fr[c] ? -Pg[c] + beta * (double)pp[c] : 0.0;
+                    if (counted) s[0] += gi[c] * pi;
+                    pv[c] = (T)pi;
+                }
+                pv[3] = (T)0;
             }
-            pv[c] = (T)pi;
+        }
+        if (!blocked) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                double pi = 0.0;
+                if (m[c] & APL_M_FREE) {
+                    double d = fabs((double)dv[c]);
+                    if (!(d > 0.0)) d = mean;
+                    pi = -(double)gv[c] / d + beta * (double)pp[c];
+                    if (m[c] & APL_M_COUNT) s[0] += (double)gv[c] * pi;
+                }
+                pv[c] = (T)pi;
+            }
         }
         st4(p, r, pv);
         st4(gz, r, zero);
         st4(dz, r, zero);
+        if (oz) st4(oz, r, zero);
     }
     grid_reduce<1>(s, partials, counter, scal + APL_S_GP);
 }
@@ -263,7 +273,7 @@ __global__ void pncg_bump_j_kernel(double* scal) {
 // outcome drives a CUDA-graph WHILE node: condition 1 = run another trial.
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads) pncg_ls_kernel(long long rows, int j, int last, T* __restrict__ gz,
-                                                             T* __restrict__ dz, double* scal, PncgParams prm,
+                                                             T* __restrict__ dz, T* __restrict__ oz, double* scal, PncgParams prm,
                                                              cudaGraphConditionalHandle cond, int use_cond) {
     if (__ldcg(scal + APL_S_DONE) != 0.0) return;
     if (j < 0) {
@@ -297,6 +307,7 @@ __global__ void __launch_bounds__(kVecThreads) pncg_ls_kernel(long long rows, in
          r += (long long)gridDim.x * kVecThreads) {
         st4(gz, r, zero);
         st4(dz, r, zero);
+        if (oz) st4(oz, r, zero);
     }
 }
 
@@ -304,7 +315,8 @@ template <typename T>
 __global__ void __launch_bounds__(kVecThreads) pncg_commit_kernel(long long rows, int jfinal, T* __restrict__ x,
                                                                  const T* __restrict__ p, const T* __restrict__ g,
                                                                  T* __restrict__ gz, const T* __restrict__ diag,
-                                                                 T* __restrict__ dz, double* scal) {
+                                                                 T* __restrict__ dz, const T* __restrict__ offd,
+                                                                 T* __restrict__ oz, double* scal) {
     if (__ldcg(scal + APL_S_DONE) != 0.0) return;
     if (jfinal < 0) jfinal = (int)__ldcg(scal + APL_S_J);  // conditional-graph line search: trials run so far
     const bool accepted = __ldcg(scal + APL_S_ACC_J + jfinal) > 0.0;
@@ -338,6 +350,7 @@ __global__ void __launch_bounds__(kVecThreads) pncg_commit_kernel(long long rows
             T v[4];
             ld4(g, r, v); st4(gz, r, v);
             ld4(diag, r, v); st4(dz, r, v);
+            if (oz) { ld4(offd, r, v); st4(oz, r, v); }
         }
     }
 }
@@ -363,6 +376,8 @@ struct apl_pncg {
     void* p[2] = {nullptr, nullptr};
     void* g[2] = {nullptr, nullptr};
     void* d[2] = {nullptr, nullptr};
+    void* o[2] = {nullptr, nullptr};   // vertex-block off-diagonals (block Jacobi, opt-in); nullptr = scalar Jacobi
+    int psd = 0;                       // APL_OP_PSD in the Hessian passes
     const uint8_t* mask = nullptr;
     double* scal = nullptr;
     double* partials = nullptr;
@@ -389,13 +404,14 @@ namespace {
 // Completes this rank's partial results of a phase over all ranks: halo sum of up to two nodal fields (ld = 4) and
 // the global sum of n_scal workspace scalars starting at scal[idx (+ trial counter)], guarded by the same skip flags
 // as the launches that produced them.
-int exchange(apl_pncg* w, void* f0, void* f1, int idx, int n_scal, int skip_a, int skip_b, int dyn_j, cudaStream_t s) {
+int exchange(apl_pncg* w, void* f0, void* f1, int idx, int n_scal, int skip_a, int skip_b, int dyn_j, cudaStream_t s,
+             void* f2 = nullptr) {
     if (!w->xchg) return APL_OK;
-    const int nf = f0 ? (f1 ? 2 : 1) : 0;
-    int rc = xchg_push_ex(w->xchg, w->dtype, nf, f0, f1, nullptr, 4, w->scal + idx, n_scal, 1, w->scal, skip_a, skip_b,
+    const int nf = f0 ? (f1 ? (f2 ? 3 : 2) : 1) : 0;
+    int rc = xchg_push_ex(w->xchg, w->dtype, nf, f0, f1, f2, 4, w->scal + idx, n_scal, 1, w->scal, skip_a, skip_b,
                           dyn_j, s);
     if (rc != APL_OK) return rc;
-    return xchg_pull_ex(w->xchg, w->dtype, nf, f0, f1, nullptr, 4, w->scal + idx, n_scal, 1, w->scal, skip_a, skip_b,
+    return xchg_pull_ex(w->xchg, w->dtype, nf, f0, f1, f2, 4, w->scal + idx, n_scal, 1, w->scal, skip_a, skip_b,
                         dyn_j, s);
 }
 
@@ -409,11 +425,15 @@ int phase_typed(apl_pncg* w, int phase, int j, cudaStream_t s) {
     T* dz = (T*)w->d[o];
     T* p = (T*)w->p[c];
     T* pprev = (T*)w->p[o];
+    T* og = (T*)w->o[c];      // block off-diagonals at the current iterate / of the trial (nullptr: scalar Jacobi)
+    T* oz = (T*)w->o[o];
+    const int ops_a = APL_OP_FUN | APL_OP_GRAD | APL_OP_HESS_DIAG | (og ? APL_OP_HESS_OFFD : 0) | (w->psd ? APL_OP_PSD : 0);
+    const int ops_b = APL_OP_HESS_QUAD | (w->psd ? APL_OP_PSD : 0);
     const uchar4* mask = (const uchar4*)w->mask;
     const int J = w->prm.max_halvings;
     switch (phase) {
         case APL_PHASE_REDUCE:
-            pncg_reduce_kernel<T><<<w->grid, kVecThreads, 0, s>>>(w->rows, g, gz, dg, pprev, mask, w->scal,
+            pncg_reduce_kernel<T><<<w->grid, kVecThreads, 0, s>>>(w->rows, g, gz, dg, og, pprev, mask, w->scal,
                                                                   w->partials, w->counter);
             if (int rc = exchange(w, nullptr, nullptr, APL_S_SUMS, kNSums, APL_S_DONE, -1, 0, s)) return rc;
             break;
@@ -421,12 +441,12 @@ int phase_typed(apl_pncg* w, int phase, int j, cudaStream_t s) {
             pncg_finalize_kernel<<<1, 1, 0, s>>>(w->scal, w->prm);
             break;
         case APL_PHASE_DIRECTION:
-            pncg_direction_kernel<T><<<w->grid, kVecThreads, 0, s>>>(w->rows, g, dg, pprev, p, gz, dz, mask, w->scal,
-                                                                     w->partials, w->counter);
+            pncg_direction_kernel<T><<<w->grid, kVecThreads, 0, s>>>(w->rows, g, dg, og, pprev, p, gz, dz, oz, mask,
+                                                                     w->scal, w->partials, w->counter);
             break;
         case APL_PHASE_PASS_B:
             for (apl_fem* f : w->fems) {
-                int rc = fem_eval_pncg(f, APL_OP_HESS_QUAD, x, p, nullptr, w->scal, 0, APL_S_DONE, -1, nullptr,
+                int rc = fem_eval_pncg(f, ops_b, x, p, nullptr, w->scal, 0, APL_S_DONE, -1, nullptr,
                                        w->scal + APL_S_PHP, nullptr, nullptr, w->scatter, s);
                 if (rc != APL_OK) return rc;
             }
@@ -441,9 +461,9 @@ int phase_typed(apl_pncg* w, int phase, int j, cudaStream_t s) {
             if (j < -1 || j > J) { set_error("apl_pncg_phase: trial index out of range"); return APL_ERR_INVALID; }
             const int dyn = j < 0 ? 1 : 0, jj = dyn ? 0 : j;
             for (apl_fem* f : w->fems) {
-                int rc = fem_eval_pncg(f, APL_OP_FUN | APL_OP_GRAD | APL_OP_HESS_DIAG, x, nullptr, p, w->scal,
+                int rc = fem_eval_pncg(f, ops_a, x, nullptr, p, w->scal,
                                        APL_S_ALPHA_J + jj, APL_S_DONE, APL_S_ACC_J + jj, w->scal + APL_S_FT_J + jj,
-                                       nullptr, gz, dz, w->scatter, s, dyn);
+                                       nullptr, gz, dz, w->scatter, s, dyn, oz);
                 if (rc != APL_OK) return rc;
             }
             for (const auto& e : w->exts) {
@@ -452,24 +472,24 @@ int phase_typed(apl_pncg* w, int phase, int j, cudaStream_t s) {
                                         dyn);
                 if (rc != APL_OK) return rc;
             }
-            if (int rc = exchange(w, gz, dz, APL_S_FT_J + jj, 1, APL_S_DONE, APL_S_ACC_J + jj, dyn, s)) return rc;
+            if (int rc = exchange(w, gz, dz, APL_S_FT_J + jj, 1, APL_S_DONE, APL_S_ACC_J + jj, dyn, s, oz)) return rc;
             if (dyn) pncg_bump_j_kernel<<<1, 1, 0, s>>>(w->scal);
             break;
         }
         case APL_PHASE_LS: {
             if (j < -1 || j > J) { set_error("apl_pncg_phase: trial index out of range"); return APL_ERR_INVALID; }
             if (j < 0) {
-                pncg_ls_kernel<T><<<w->grid, kVecThreads, 0, s>>>(w->rows, -1, 0, gz, dz, w->scal, w->prm,
+                pncg_ls_kernel<T><<<w->grid, kVecThreads, 0, s>>>(w->rows, -1, 0, gz, dz, oz, w->scal, w->prm,
                                                                    w->cond[w->cur], 1);
             } else {
                 const int last = (j == J) ? 1 : 0;
-                pncg_ls_kernel<T><<<last ? 1 : w->grid, last ? 32 : kVecThreads, 0, s>>>(w->rows, j, last, gz, dz,
+                pncg_ls_kernel<T><<<last ? 1 : w->grid, last ? 32 : kVecThreads, 0, s>>>(w->rows, j, last, gz, dz, oz,
                                                                                        w->scal, w->prm, 0, 0);
             }
             break;
         }
         case APL_PHASE_COMMIT:
-            pncg_commit_kernel<T><<<w->grid, kVecThreads, 0, s>>>(w->rows, j < 0 ? -1 : J + 1, x, p, g, gz, dg, dz,
+            pncg_commit_kernel<T><<<w->grid, kVecThreads, 0, s>>>(w->rows, j < 0 ? -1 : J + 1, x, p, g, gz, dg, dz, og, oz,
                                                                   w->scal);
             break;
         case APL_PHASE_INIT: {
@@ -477,9 +497,10 @@ int phase_typed(apl_pncg* w, int phase, int j, cudaStream_t s) {
             APL_CUDA_CHECK(cudaMemsetAsync(w->scal, 0, sizeof(double) * APL_PNCG_NSCAL, s));
             pncg_zero2_kernel<T><<<w->grid, kVecThreads, 0, s>>>(w->rows, g, dg);
             pncg_zero2_kernel<T><<<w->grid, kVecThreads, 0, s>>>(w->rows, gz, pprev);
+            if (og) pncg_zero2_kernel<T><<<w->grid, kVecThreads, 0, s>>>(w->rows, og, oz);
             for (apl_fem* f : w->fems) {
-                int rc = fem_eval_pncg(f, APL_OP_FUN | APL_OP_GRAD | APL_OP_HESS_DIAG, x, nullptr, nullptr, w->scal, 0,
-                                       -1, -1, w->scal + APL_S_F, nullptr, g, dg, w->scatter, s);
+                int rc = fem_eval_pncg(f, ops_a, x, nullptr, nullptr, w->scal, 0,
+                                       -1, -1, w->scal + APL_S_F, nullptr, g, dg, w->scatter, s, 0, og);
                 if (rc != APL_OK) return rc;
             }
             for (const auto& e : w->exts) {
@@ -487,7 +508,7 @@ int phase_typed(apl_pncg* w, int phase, int j, cudaStream_t s) {
                                         -1, -1, w->scal + APL_S_F, g, s);
                 if (rc != APL_OK) return rc;
             }
-            if (int rc = exchange(w, g, dg, APL_S_F, 1, -1, -1, 0, s)) return rc;
+            if (int rc = exchange(w, g, dg, APL_S_F, 1, -1, -1, 0, s, og)) return rc;
             break;
         }
         default:
@@ -655,6 +676,18 @@ int apl_pncg_set_params(apl_pncg_t* w, double max_steps, double rtol_g, double a
     w->scatter = scatter;
     w->use_graph = use_graph != 0;
     w->graph_mode = use_graph;
+    drop_graphs(w);
+    return APL_OK;
+}
+
+int apl_pncg_set_block_jacobi(apl_pncg_t* w, void* o0, void* o1, int psd) {
+    if (!w) { set_error("apl_pncg_set_block_jacobi: NULL workspace"); return APL_ERR_INVALID; }
+    if ((o0 == nullptr) != (o1 == nullptr)) { set_error("apl_pncg_set_block_jacobi: give both buffers or none"); return APL_ERR_INVALID; }
+    if ((o0 || psd) && w->scatter != APL_SCATTER_TILE) {
+        set_error("apl_pncg_set_block_jacobi: block Jacobi / PSD projection need the TILE assembly");
+        return APL_ERR_INVALID;
+    }
+    w->o[0] = o0; w->o[1] = o1; w->psd = psd ? 1 : 0;
     drop_graphs(w);
     return APL_OK;
 }

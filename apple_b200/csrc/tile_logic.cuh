@@ -51,9 +51,10 @@ struct TileCfg {
     static constexpr bool kFun = (OPS & APL_OP_FUN) != 0;
     static constexpr bool kGrad = (OPS & APL_OP_GRAD) != 0;
     static constexpr bool kDiag = (OPS & APL_OP_HESS_DIAG) != 0;
-    static constexpr bool kProd = (OPS & APL_OP_HESS_PROD) != 0;
+    // third nodal output: H p (HESS_PROD) or the off-diagonals of the vertex blocks (HESS_OFFD) -- never both
+    static constexpr bool kProd = (OPS & (APL_OP_HESS_PROD | APL_OP_HESS_OFFD)) != 0;
     static constexpr bool kQuad = (OPS & APL_OP_HESS_QUAD) != 0;
-    static constexpr bool kNeedP = kProd || kQuad;
+    static constexpr bool kNeedP = (OPS & (APL_OP_HESS_PROD | APL_OP_HESS_QUAD)) != 0;
     static constexpr int NOUT = (kGrad ? 1 : 0) + (kDiag ? 1 : 0) + (kProd ? 1 : 0);
     // scalars per slot: 3*NOUT rounded up to whole 16-byte planes plus, for fp32, one 8-byte tail plane
     static constexpr int SS = (NOUT == 0) ? 0

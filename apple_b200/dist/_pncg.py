@@ -27,7 +27,8 @@ class ShardedPNCG:
 
     def __init__(self, potentials, ext_forces, shard: Shard, free_mask_local: torch.Tensor, u0_local: torch.Tensor,
                  *, criteria: ConvergenceCriteria | None = None, line_search: LineSearch | None = None, group=None,
-                 scatter: int | None = None, transport: str | None = None, use_graph: int = 0):
+                 scatter: int | None = None, transport: str | None = None, use_graph: int = 0,
+                 preconditioner: str = "jacobi", psd: bool = False):
         self.shard = shard
         self.device, self.dtype = u0_local.device, u0_local.dtype
         if transport is None:
@@ -77,6 +78,13 @@ class ShardedPNCG:
                                          float(c.absolute_gradient_norm), float(c.max_failed_line_searches),
                                          float(ls.overstep), 1.0, float(ls.armijo), int(ls.max_steps), int(sc),
                                          int(use_graph) if transport in ("peer", "local") else 0))
+        if preconditioner not in ("jacobi", "block"):
+            raise ValueError("preconditioner must be 'jacobi' or 'block'")
+        self.o = [new(), new()] if preconditioner == "block" else [None, None]
+        if preconditioner == "block" or psd:
+            if transport not in ("peer", "local"):
+                raise NotImplementedError("block Jacobi / PSD projection: peer-memory or single-GPU transport only")
+            _lib.check(L.apl_pncg_set_block_jacobi(handle, _lib.dev_ptr(self.o[0]), _lib.dev_ptr(self.o[1]), int(bool(psd))))
         if transport in ("peer", "local"):
             if transport == "peer":
                 _lib.check(L.apl_pncg_set_exchange(handle, self.halo._xchg))

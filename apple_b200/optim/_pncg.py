@@ -60,7 +60,15 @@ class LineSearch:
 class PNCG(Optimizer):
     def __init__(self, criteria: ConvergenceCriteria | None = None, line_search: LineSearch | None = None, *,
                  fused: bool = True, check_every: int | None = None, use_graph: bool | int = 2,
-                 scatter: int | None = None):
+                 scatter: int | None = None, preconditioner: str = "jacobi", psd: bool = False):
+        """``preconditioner``: ``"jacobi"`` -- the reference's scalar rule on the clamped Hessian diagonal (bench
+        ``:407-410``; the parity default) -- or ``"block"``, the opt-in 3x3 block Jacobi on the vertex blocks of the
+        Hessian.  ``psd=True`` (opt-in): passes A and B use the eigenvalue-clamped element Hessians.  Both are fused-path
+        features (``apl_pncg_set_block_jacobi``)."""
+        if preconditioner not in ("jacobi", "block"):
+            raise ValueError("preconditioner must be 'jacobi' or 'block'")
+        self.preconditioner = preconditioner
+        self.psd = bool(psd)
         self.criteria = criteria if criteria is not None else ConvergenceCriteria()
         self.line_search = line_search if line_search is not None else LineSearch()
         self.fused = fused
@@ -81,6 +89,8 @@ class PNCG(Optimizer):
     def init(self, problem, state, free):
         if self.fused and _fused_supported(problem):
             return _FusedState(self, problem, state, free)
+        if self.preconditioner != "jacobi" or self.psd:
+            raise NotImplementedError("block Jacobi / PSD projection exist on the fused PNCG path only")
         return _GenericState(self, problem, state, free)
 
     def step(self, problem, state, opt_state):
@@ -214,6 +224,9 @@ class _FusedState(_StateBase):
             handle, float(c.max_steps), float(c.target_relative_gradient_norm), float(c.absolute_gradient_norm),
             float(c.max_failed_line_searches), float(ls.overstep), 1.0, float(ls.armijo), int(ls.max_steps),
             int(scatter), int(opt.use_graph) if opt.use_graph in (0, 1, 2) else int(bool(opt.use_graph))))
+        self.o = [new(), new()] if opt.preconditioner == "block" else [None, None]
+        if opt.preconditioner == "block" or opt.psd:
+            _lib.check(L.apl_pncg_set_block_jacobi(handle, _lib.dev_ptr(self.o[0]), _lib.dev_ptr(self.o[1]), int(opt.psd)))
         with torch.cuda.device(self.device):
             _lib.check(L.apl_pncg_phase(handle, _lib.PHASE_INIT, 0, _lib.stream_ptr(self.device)))
 

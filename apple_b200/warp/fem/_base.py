@@ -214,14 +214,23 @@ class WarpPotentialFem(WarpPotential):
         return int(n.value)
 
     # ---- operators ----
-    def eval(self, ops: int, u, p=None, *, fun=None, quad=None, grad=None, diag=None, prod=None, scatter=None,
+    def eval(self, ops: int, u, p=None, *, fun=None, quad=None, grad=None, diag=None, prod=None, offd=None, scatter=None,
              part: int = 0) -> None:
+        """Any OR of the operator bits in ONE pass.  ``offd`` (``OP_HESS_OFFD``, opt-in): the off-diagonal entries
+        (xy, xz, yz) of the 3x3 vertex blocks; it travels through the ``prod`` slot of the C ABI, so it excludes
+        ``OP_HESS_PROD`` / ``OP_HESS_QUAD``.  ``OP_PSD`` (opt-in) switches the Hessian terms to the eigenvalue-clamped
+        ``d2Psi/dF2``."""
+        if ops & _lib.OP_HESS_OFFD:
+            if ops & (_lib.OP_HESS_PROD | _lib.OP_HESS_QUAD) or prod is not None:
+                raise ValueError("OP_HESS_OFFD combines with OP_FUN, OP_GRAD and OP_HESS_DIAG only")
+            prod = offd
         ld_in = _lib.field_ld(u, self.n_points, self.dtype, "u")
         if ops & (_lib.OP_HESS_PROD | _lib.OP_HESS_QUAD):
             if p is None or _lib.field_ld(p, self.n_points, self.dtype, "p") != ld_in:
                 raise ValueError("p must be given with the same layout as u for hess_prod / hess_quad")
         ld_out = None
-        for name, out, bit in (("grad", grad, _lib.OP_GRAD), ("diag", diag, _lib.OP_HESS_DIAG), ("prod", prod, _lib.OP_HESS_PROD)):
+        for name, out, bit in (("grad", grad, _lib.OP_GRAD), ("diag", diag, _lib.OP_HESS_DIAG),
+                               ("prod", prod, _lib.OP_HESS_PROD | _lib.OP_HESS_OFFD)):
             if ops & bit:
                 ld = _lib.field_ld(out, self.n_points, self.dtype, name)
                 if ld_out is not None and ld != ld_out:
@@ -258,6 +267,19 @@ class WarpPotentialFem(WarpPotential):
                 self._handle, _lib.dev_ptr(u), _lib.dev_ptr(p), ld_in, _lib.dev_ptr(out.get("mu")),
                 _lib.dev_ptr(out.get("lambda_")), _lib.dev_ptr(out.get("activation")), _lib.stream_ptr(self.device)))
         return out
+
+    def hess_block(self, u, diag, offd, *, psd: bool = False) -> None:
+        """Opt-in superset of ``hess_diag``: the 3x3 vertex blocks of the assembled Hessian, accumulated as their
+        diagonals ``diag[v] = (xx, yy, zz)`` -- the same numbers ``hess_diag`` returns -- and off-diagonals
+        ``offd[v] = (xy, xz, yz)``.  ``psd=True``: blocks of the eigenvalue-clamped element Hessians."""
+        self.eval(_lib.OP_HESS_DIAG | _lib.OP_HESS_OFFD | (_lib.OP_PSD if psd else 0), u, diag=diag, offd=offd)
+
+    def hess_prod_psd(self, u, p, output) -> None:
+        """``hess_prod`` with the analytic PSD projection of every element Hessian (opt-in; a descent-safe product)."""
+        self.eval(_lib.OP_HESS_PROD | _lib.OP_PSD, u, p, prod=output)
+
+    def hess_quad_psd(self, u, p, output) -> None:
+        self.eval(_lib.OP_HESS_QUAD | _lib.OP_PSD, u, p, quad=output)
 
     def fun(self, u, output) -> None:  # _base.py:151-158
         self.eval(_lib.OP_FUN, u, fun=output)

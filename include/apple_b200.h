@@ -50,6 +50,18 @@ extern "C" {
 #define APL_OP_HESS_DIAG 4  /* WarpPotentialFem.hess_diag  warp/fem/_base.py:169-176, kernel :293-324 */
 #define APL_OP_HESS_PROD 8  /* WarpPotentialFem.hess_prod  warp/fem/_base.py:178-185, kernel :326-351 */
 #define APL_OP_HESS_QUAD 16 /* WarpPotentialFem.hess_quad  warp/fem/_base.py:187-194, kernel :353-383 */
+/* Opt-in supersets of the reference (BASELINE.json north star: "3x3-block Hessian diagonal", "analytic PSD
+ * eigen-projection"); default behaviour and parity are unchanged when the bits are clear.  TILE assembly only.
+ *  HESS_OFFD  off-diagonal entries (xy, xz, yz) of the 3x3 VERTEX BLOCKS of the assembled Hessian, accumulated into the
+ *             `prod` argument of apl_fem_eval (so never together with HESS_PROD / HESS_QUAD); with HESS_DIAG -- whose
+ *             entries are the block diagonals, the clamp of warp/fem/_base.py:317-320 kept -- it is the block-Jacobi
+ *             preconditioner.  Combines with FUN, GRAD, HESS_DIAG.
+ *  PSD        modifier: the Hessian terms (diag, offd, prod, quad) of the Stable Neo-Hookean kinds use d2Psi/dF2 with its
+ *             negative eigenvalues set to zero, from the ANALYTIC eigen-system (3 twist, 3 flip, 3 scaling modes in the
+ *             SVD frame of F); a superset of the clamps at warp/fem/_base.py:317-320,379-380, which stay in place.  ARAP:
+ *             no-op, its clamped twist rates (warp/fem/func/_misc.py:31-43) already are the projection. */
+#define APL_OP_HESS_OFFD 32
+#define APL_OP_PSD 64
 
 /* assembly strategy */
 #define APL_SCATTER_TILE 0   /* TMA/mbarrier-pipelined tiles: shared-memory gather, in-tile slot reduction, one
@@ -284,6 +296,14 @@ int apl_pncg_add_ext_force(apl_pncg_t* ws, int64_t k, const void* force, const i
 int apl_pncg_set_params(apl_pncg_t* ws, double max_steps, double rtol_g, double atol_g, double max_fails,
                         double overstep, double max_step, double c1, int max_halvings, int scatter,
                         int use_graph);
+/* OPT-IN superset of the reference's preconditioner (scalar Jacobi on the clamped diagonal, restated from
+ * benches/bench_pncg_branching_backends.py:407-410): 3x3 BLOCK Jacobi.  o0 / o1 are caller-owned device arrays
+ * (n_points, 4) of dtype holding the off-diagonals (xy, xz, yz) of the vertex blocks at the current / trial point; pass
+ * A then evaluates FUN | GRAD | HESS_DIAG | HESS_OFFD and REDUCE / DIRECTION apply the inverse of every vertex block
+ * restricted to its free components (a block that is not positive definite falls back to the scalar rule).  psd != 0:
+ * passes A and B use the eigenvalue-clamped element Hessians (APL_OP_PSD).  NULL, NULL, 0 restores the reference
+ * behaviour.  Call before APL_PHASE_INIT. */
+int apl_pncg_set_block_jacobi(apl_pncg_t* ws, void* o0, void* o1, int psd);
 /* Sharded meshes (new functionality): with an exchange attached, every phase completes its partial results over all
  * ranks on the device, right after the kernels that produced them -- the 11 sums of REDUCE, (g.p, p.Hp) after PASS_B,
  * and per trial the halo sum of g', diag' with the trial energy (one push + one pull kernel each, guarded by the same
@@ -297,6 +317,31 @@ int apl_pncg_flip(apl_pncg_t* ws);
 int apl_pncg_phase(apl_pncg_t* ws, int phase, int j, void* stream);
 /* Enqueue n_iters complete iterations (phases 1..8 and the role flip); never synchronises. */
 int apl_pncg_iterate(apl_pncg_t* ws, int n_iters, void* stream);
+
+/* ---- fused adjoint solve: Jacobi-preconditioned conjugate gradients on hess_prod -------------------------
+ * Replaces  jax.scipy.sparse.linalg.cg(lambda p: model.hess_prod(u, p), -dLdu, tol=1e-5, atol=1e-15,
+ *                                       maxiter=n_free // 10, M=lambda x: P * x),  P = 1 / model.hess_diag(u)
+ * of the reference's inverse problems (exp/2025/09/24/inverse-grin/src/35-inverse-small-reg.py:223-260), where every
+ * matvec is an FFI callback and the vector algebra is XLA ops; here one iteration is five launches (matvec, p.Ap,
+ * {x, r update + r.Mr + r.r}, a 1-thread step, direction) replayed as a CUDA graph, scalars on the device.
+ * All vectors are caller-owned DEVICE arrays (n_points, 4) of dtype: u (the state), x (solution, in: x0 unless
+ * x_is_zero), b (right-hand side), r / p / Ap (work), diag (model.hess_diag(u), raw: |d| is taken and non-positive
+ * entries replaced by the mean of the positive ones); mask as in apl_pncg_create (bit 0 = free DOF; fixed DOFs of x
+ * stay untouched and are excluded from every product).  scal: APL_PCG_NSCAL device doubles:
+ *   [0] r.Mr  [1] p.Ap  [3] r.r  [4] b.b  [5] done: 0 running, 1 converged (|r| <= max(tol |b|, atol)), 2 max_iters,
+ *   3 breakdown (p.Ap <= 0: H indefinite along p, or a non-finite value)  [6] iterations  [7] beta  [8] target^2. */
+#define APL_PCG_NSCAL 16
+typedef struct apl_pcg apl_pcg_t;
+int apl_pcg_create(int dtype, int64_t n_points, int device, const void* u, void* x, const void* b, void* r, void* p,
+                   void* Ap, const void* diag, const uint8_t* mask, double* scal, apl_pcg_t** out);
+void apl_pcg_destroy(apl_pcg_t* ws);
+int apl_pcg_add_fem(apl_pcg_t* ws, apl_fem_t* fem);
+/* psd != 0: the matvec is the PSD-projected product (APL_OP_PSD) -- the operator is then positive semi-definite by
+ * construction, what the reference asserts with lx.positive_semidefinite_tag (:248) */
+int apl_pcg_set_params(apl_pcg_t* ws, double tol, double atol, int64_t max_iters, int psd, int scatter, int use_graph);
+int apl_pcg_init(apl_pcg_t* ws, int x_is_zero, void* stream);
+/* enqueue n_iters iterations (no-ops once scal[5] != 0); never synchronises */
+int apl_pcg_iterate(apl_pcg_t* ws, int n_iters, void* stream);
 
 #ifdef __cplusplus
 }

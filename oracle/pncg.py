@@ -55,6 +55,13 @@ class ForwardProblem:
     def hess_quad(self, x, p):  # :56-59
         return self.model.hess_quad(self.before_trial(x), self.dof_map.to_full_grad(p))
 
+    def hess_quad_psd(self, x, p):
+        """opt-in superset: the quadratic form of the PSD-projected element Hessians (``oracle/hessian.py``)"""
+        from . import hessian as ohess
+
+        u, pf = self.before_trial(x), self.dof_map.to_full_grad(p)
+        return sum(ohess.hess_quad(pot, u, pf, psd=True) for pot in self.model.potentials if hasattr(pot, "cells"))
+
 
 def make_preconditioner(hess_diag):
     """bench :407-410."""
@@ -65,13 +72,68 @@ def make_preconditioner(hess_diag):
     return 1.0 / d
 
 
+class _Diagonal:
+    """The reference's preconditioner as an operator (``P * v``)."""
+
+    def __init__(self, P):
+        self.P = P
+
+    def __call__(self, v):
+        return self.P * v
+
+
+class BlockJacobi:
+    """OPT-IN superset (not in the reference; BASELINE.json north star): inverse of the 3x3 vertex blocks of the
+    assembled Hessian restricted to each vertex's free components; a block that is not positive definite falls back to
+    the reference's scalar rule (bench ``:407-410``) on that vertex.  Blocks come from ``oracle/hessian.py``; their
+    diagonal is the model's (clamped) ``hess_diag``."""
+
+    def __init__(self, problem, x, psd=False):
+        from . import hessian as ohess
+
+        dm, model = problem.dof_map, problem.model
+        u = problem.before_trial(x)
+        V = dm.n_points
+        B = np.zeros((V, 3, 3))
+        for pot in model.potentials:
+            if hasattr(pot, "cells"):
+                B += ohess.vertex_blocks(pot, u, V, psd=psd)
+        d = model.hess_diag(u) if not psd else np.stack([B[:, 0, 0], B[:, 1, 1], B[:, 2, 2]], 1)
+        free = np.zeros(V * 3, bool)
+        free[dm.free_indices] = True
+        free = free.reshape(V, 3)
+        A = B.copy()
+        for c in range(3):
+            A[:, c, c] = d[:, c]
+        A = np.where(free[:, :, None] & free[:, None, :], A, 0.0)
+        for c in range(3):
+            A[~free[:, c], c, c] = 1.0
+        m2 = A[:, 0, 0] * A[:, 1, 1] - A[:, 0, 1] ** 2
+        det = np.linalg.det(A)
+        self.spd = (A[:, 0, 0] > 0) & (m2 > 0) & (det > 0)
+        self.inv = np.zeros_like(A)
+        self.inv[self.spd] = np.linalg.inv(A[self.spd])
+        dabs = np.abs(d)
+        pos = (dabs > 0) & free
+        mean = dabs[pos].mean() if pos.any() else 1.0
+        self.scalar = 1.0 / np.where(dabs > 0, dabs, mean)
+        self.dm = dm
+
+    def __call__(self, v):
+        full = self.dm.to_full_grad(v)
+        out = np.where(self.spd[:, None], np.einsum("vij,vj->vi", self.inv, full), self.scalar * full)
+        return self.dm.to_free(out)
+
+
 def dai_kou_beta(g, g_prev, p_prev, P):
-    """bench :663-679."""
+    """bench :663-679 (``P`` an operator: ``P(y)``; a plain array is the reference's diagonal)."""
+    if not callable(P):
+        P = _Diagonal(P)
     y = g - g_prev
     yp = np.vdot(y, p_prev)
     if not abs(yp) > 1.0e-12:
         return np.inf
-    Py = P * y
+    Py = P(y)
     return np.vdot(g, Py) / yp - (np.vdot(y, Py) / yp) * (np.vdot(p_prev, g) / yp)
 
 
@@ -98,6 +160,8 @@ def minimize(
     armijo=1.0e-4,
     rtol_grad=0.0,
     history=None,
+    block_jacobi=False,
+    psd=False,
 ):
     """PNCG loop, bench :254-329 with the fused operator calls spelled out per appendix B.
 
@@ -119,17 +183,17 @@ def minimize(
             history.append((k, float(f), float(gnorm)))
         if gnorm <= rtol_grad * g0_norm:
             break
-        P = make_preconditioner(problem.hess_diag(x))
+        P = BlockJacobi(problem, x, psd) if block_jacobi else _Diagonal(make_preconditioner(problem.hess_diag(x)))
         beta = dai_kou_beta(g, g_prev, p_prev, P)
         if k == 0 or not np.isfinite(beta) or abs(beta) > 10.0:  # bench :288-289
             beta = 0.0
-        steepest = -P * g
+        steepest = -P(g)
         p = steepest + beta * p_prev
         gp = np.vdot(g, p)
         if not (np.isfinite(gp) and gp < 0.0):  # bench :292-303
             beta, p = 0.0, steepest
             gp = np.vdot(g, p)
-        pHp = problem.hess_quad(x, p)
+        pHp = problem.hess_quad_psd(x, p) if psd else problem.hess_quad(x, p)
         alpha = initial_alpha(gp, pHp, overstep)
         alpha = min(alpha, problem.max_step_size(x, p))  # _problem.py:29-34
         # bench :413-456

@@ -81,3 +81,41 @@ extern "C" void elem_mixed_host(int kind, int is_f64, int n, const void* rec, co
     };
     if (is_f64) go(0.0); else go(0.0f);
 }
+
+// Opt-in supersets (block Jacobi, PSD projection).  sel 0: DIAG|OFFD, 1: DIAG|OFFD|PSD, 2: PROD|QUAD|PSD.
+// dg (n,4,3) = block diagonals, hp (n,4,3) = block off-diagonals (xy, xz, yz) for sel 0/1; hp = H+ p, quad = max(p H+ p, 0) for sel 2.
+template <typename T, int KIND, int OPS>
+static void run_ops(int n, const T* rec, const T* uc, const T* pc, T* quad, T* dg, T* hp) {
+    constexpr int NR = apl::RecSize<KIND>::value;
+    for (int t = 0; t < n; ++t) {
+        T G[4][3], DG[4][3] = {}, HP[4][3] = {};
+        T psi = 0, q = 0;
+        apl::elem_eval<T, KIND, OPS>(rec + (size_t)t * NR, (const T(*)[3])(uc + (size_t)t * 12),
+                                     (const T(*)[3])(pc + (size_t)t * 12), psi, q, G, DG, HP);
+        quad[t] = q;
+        for (int a = 0; a < 4; ++a)
+            for (int i = 0; i < 3; ++i) {
+                dg[t * 12 + a * 3 + i] = DG[a][i];
+                hp[t * 12 + a * 3 + i] = HP[a][i];
+            }
+    }
+}
+
+extern "C" void elem_eval_ops_host(int kind, int is_f64, int sel, int n, const void* rec, const void* uc, const void* pc,
+                                   void* quad, void* dg, void* hp) {
+    auto go = [&](auto zero) {
+        using T = decltype(zero);
+#define CALL(K, O) run_ops<T, K, O>(n, (const T*)rec, (const T*)uc, (const T*)pc, (T*)quad, (T*)dg, (T*)hp)
+#define SEL(K)                                                                     \
+    if (sel == 0) CALL(K, APL_OP_HESS_DIAG | APL_OP_HESS_OFFD);                    \
+    else if (sel == 1) CALL(K, APL_OP_HESS_DIAG | APL_OP_HESS_OFFD | APL_OP_PSD);  \
+    else CALL(K, APL_OP_HESS_PROD | APL_OP_HESS_QUAD | APL_OP_PSD)
+        if (kind == APL_KIND_SNH) { SEL(APL_KIND_SNH); }
+        else if (kind == APL_KIND_ARAP) { SEL(APL_KIND_ARAP); }
+        else if (kind == APL_KIND_SNH_ARAP) { SEL(APL_KIND_SNH_ARAP); }
+        else { SEL(APL_KIND_SNH_MUSCLE); }
+#undef SEL
+#undef CALL
+    };
+    if (is_f64) go(0.0); else go(0.0f);
+}

@@ -166,7 +166,7 @@ def test_config4_muscle_model_full_size_matches_c_oracle(native_lib):
     act[slab, 3:] = 0.0
     h = 1.0 / n
     X = mesh.points
-    u = 0.05 * h * np.sin(7.0 * X[:, [1, 2, 0]] + 0.3) + 0.02 * h * rng.uniform(-1, 1, X.shape)
+    u = np.ascontiguousarray(0.05 * h * np.sin(7.0 * X[:, [1, 2, 0]] + 0.3) + 0.02 * h * rng.uniform(-1, 1, X.shape))
     p = rng.uniform(-1, 1, X.shape)
     dhdX, dV = oregion.compute_grad(mesh.points, mesh.cells)
     fat_o = cbind.CPotential("snh", mesh.cells, dhdX, (1.0 - s) * dV, mu, la)

@@ -1,0 +1,106 @@
+"""GPU parity of the opt-in supersets (include/apple_b200.h: APL_OP_HESS_OFFD, APL_OP_PSD,
+apl_pncg_set_block_jacobi) through the C ABI against the brute-force oracle of oracle/hessian.py.  Default behaviour
+(bits clear) is covered by the other suites and must be unchanged."""
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import KINDS, cuda_potential, make_case, oracle_potential, rel_err
+from oracle import hessian as ohess
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1.0e-5, torch.float64: 1.0e-10}
+
+
+@pytest.mark.parametrize("ld", [3, 4])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("kind", KINDS)
+def test_vertex_blocks_and_psd_operators_match_dense_oracle(native_lib, kind, dtype, ld):
+    from apple_b200 import _lib
+
+    mesh, u, p = make_case(n=7, seed=3, amp=0.6)
+    V = mesh.n_points
+    ora = oracle_potential(kind, mesh)
+    pot = cuda_potential(kind, mesh, dtype)
+    tol = TOL[dtype]
+
+    def dev(a):
+        t = torch.zeros((V, ld), dtype=dtype, device="cuda"); t[:, :3] = torch.as_tensor(a, dtype=dtype); return t
+
+    ud, pd = dev(u), dev(p)
+    new = lambda: torch.zeros((V, ld), dtype=dtype, device="cuda")  # noqa: E731
+    for psd in (False, True):
+        blocks = ohess.vertex_blocks(ora, u, V, psd=psd)
+        diag, offd, grad = new(), new(), new()
+        fun = torch.zeros(1, dtype=dtype, device="cuda")
+        # the PNCG pass A of the block-Jacobi mode: energy + gradient + blocks in one pass
+        pot.eval(_lib.OP_FUN | _lib.OP_GRAD | _lib.OP_HESS_DIAG | _lib.OP_HESS_OFFD | (_lib.OP_PSD if psd else 0), ud,
+                 fun=fun, grad=grad, diag=diag, offd=offd)
+        scale = np.abs(blocks).max()
+        rd = np.stack([blocks[:, 0, 0], blocks[:, 1, 1], blocks[:, 2, 2]], 1)
+        ro = np.stack([blocks[:, 0, 1], blocks[:, 0, 2], blocks[:, 1, 2]], 1)
+        assert np.abs(diag[:, :3].cpu().numpy() - rd).max() < tol * scale, psd
+        assert np.abs(offd[:, :3].cpu().numpy() - ro).max() < tol * scale, psd
+        g = np.zeros((V, 3)); ora.grad(u, g)
+        e = np.zeros(1); ora.fun(u, e)
+        assert rel_err(grad[:, :3].cpu(), g) < tol and rel_err(fun.cpu(), e) < tol
+        d2, o2 = new(), new()
+        pot.hess_block(ud, d2, o2, psd=psd)
+        assert torch.equal(d2, diag) or rel_err(d2.cpu(), diag.cpu()) < tol
+        if not psd:   # the block diagonal IS hess_diag
+            hd = new(); pot.hess_diag(ud, hd)
+            assert rel_err(diag[:, :3].cpu(), hd[:, :3].cpu()) < tol
+    out = new(); pot.hess_prod_psd(ud, pd, out)
+    assert rel_err(out[:, :3].cpu(), ohess.hess_prod(ora, u, p, V, psd=True)) < tol
+    q = torch.zeros(1, dtype=dtype, device="cuda"); pot.hess_quad_psd(ud, pd, q)
+    assert rel_err(q.cpu(), ohess.hess_quad(ora, u, p, psd=True)) < tol
+    # projected products are descent-safe: p . H+ p >= 0 element-wise, so the per-cell clamp is inactive
+    assert float((out[:, :3].double() * pd[:, :3].double()).sum()) == pytest.approx(float(q), rel=50 * tol)
+
+
+def test_superset_bits_are_rejected_where_they_do_not_apply(native_lib):
+    from apple_b200 import _lib
+
+    mesh, u, p = make_case(n=4, seed=1)
+    V = mesh.n_points
+    pot = cuda_potential("snh", mesh, torch.float64)
+    ud = torch.as_tensor(u, device="cuda"); pd = torch.as_tensor(p, device="cuda")
+    out = torch.zeros((V, 3), dtype=torch.float64, device="cuda")
+    with pytest.raises(ValueError):
+        pot.eval(_lib.OP_HESS_OFFD | _lib.OP_HESS_PROD, ud, pd, prod=out, offd=out)
+    with pytest.raises(_lib.NativeError):      # the atomic baseline has no block / PSD variant
+        pot.eval(_lib.OP_HESS_DIAG | _lib.OP_HESS_OFFD, ud, diag=out, offd=out.clone(), scatter=_lib.SCATTER_ATOMIC)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-8), (torch.float32, 1e-4)], ids=["f64", "f32"])
+@pytest.mark.parametrize("psd", [False, True], ids=["block", "block+psd"])
+def test_block_jacobi_pncg_matches_oracle(native_lib, dtype, tol, psd):
+    """Fixed iteration count with the 3x3 block preconditioner (and the PSD passes): displacements, energy and the
+    number of accepted steps against the oracle's PNCG with oracle/pncg.py: BlockJacobi."""
+    from test_gpu_pncg import _cube_problem
+
+    from apple_b200.forward import Forward
+    from apple_b200.optim import PNCG
+    from apple_b200.optim.pncg import ConvergenceCriteria
+    from oracle import pncg as opncg
+
+    model, oproblem = _cube_problem(dtype, n=6)
+    iters = 30
+    crit = ConvergenceCriteria(max_steps=iters, target_relative_gradient_norm=0.0)
+    runs = {}
+    for mode in (0, 2):
+        forward = Forward(model, optimizer=PNCG(criteria=crit, check_every=8, preconditioner="block", psd=psd, use_graph=mode))
+        solution = forward.step()
+        assert solution.stats["n_steps"] == iters and solution.stats["fused"]
+        runs[mode] = (forward.state.u.cpu().numpy(), solution)
+    x_ref, info = opncg.minimize(oproblem, np.zeros(oproblem.dof_map.n_free), max_steps=iters, block_jacobi=True, psd=psd)
+    u_ref = oproblem.dof_map.to_full(x_ref)
+    for mode in (0, 2):
+        assert rel_err(runs[mode][0], u_ref) < tol, mode
+        assert rel_err(runs[mode][1].stats["fun"], info["fun"]) < 10 * tol
+        assert runs[mode][1].stats["n_accepted"] == info["n_accepted"]
+    # and the default (scalar Jacobi) run is a different trajectory: the option really changes the preconditioner
+    base = Forward(model, optimizer=PNCG(criteria=crit, check_every=8)); base.step()
+    assert rel_err(base.state.u.cpu(), u_ref) > 10 * tol
