@@ -104,3 +104,67 @@ def test_block_jacobi_pncg_matches_oracle(native_lib, dtype, tol, psd):
     # and the default (scalar Jacobi) run is a different trajectory: the option really changes the preconditioner
     base = Forward(model, optimizer=PNCG(criteria=crit, check_every=8)); base.step()
     assert rel_err(base.state.u.cpu(), u_ref) > 10 * tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-8), (torch.float32, 1e-5)], ids=["f64", "f32"])
+def test_fused_pcg_matches_host_driven_pcg_and_oracle_residual(native_lib, dtype, tol):
+    """apl_pcg_* (fused adjoint solve: masked DOFs, device scalars, CUDA graph) against the generic torch-driven PCG over
+    the same hess_prod kernel, and the solution's residual evaluated with the ORACLE's Hessian-vector product
+    (pattern of exp/2025/09/24/inverse-grin/src/35-inverse-small-reg.py:253-260)."""
+    from test_gpu_pncg import _cube_problem
+
+    from apple_b200.forward import Forward
+    from apple_b200.optim import adjoint_solve
+
+    model, oproblem = _cube_problem(dtype, n=5, kinds=("snh",), gravity=True, spd=True)
+    forward = Forward(model)
+    n = model.n_free
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal(n)
+    rhs = torch.as_tensor(b, dtype=dtype, device=forward.state.u.device)
+    runs = {}
+    for name, kw in (("graph", dict(fused=True, use_graph=True)), ("eager", dict(fused=True, use_graph=False)),
+                     ("generic", dict(fused=False))):
+        x, info = adjoint_solve(forward.problem, forward.state, rhs, tol=tol, maxiter=4 * n, **kw)
+        assert info.converged, name
+        runs[name] = (x.double().cpu().numpy(), info)
+        res = oproblem.hess_prod(np.zeros(n), runs[name][0]) - b
+        assert np.linalg.norm(res) <= (10 if dtype == torch.float64 else 30) * tol * np.linalg.norm(b), name
+    assert abs(runs["graph"][1].n_iters - runs["generic"][1].n_iters) <= 8 + runs["generic"][1].n_iters // 10
+    assert runs["graph"][1].n_iters == runs["eager"][1].n_iters
+    assert rel_err(runs["graph"][0], runs["generic"][0]) < 100 * tol
+    # warm start: the solution as x0 converges immediately
+    x0 = torch.as_tensor(runs["graph"][0], dtype=dtype, device=rhs.device)
+    _, info = adjoint_solve(forward.problem, forward.state, rhs, tol=10 * tol, maxiter=4 * n, x0=x0)
+    assert info.converged and info.n_iters <= 2
+
+
+def test_fused_pcg_reports_breakdown_on_indefinite_hessian_and_psd_fixes_it(native_lib):
+    """At a strongly deformed state the true SNH Hessian is indefinite: CG hits a direction of non-positive curvature
+    (done = 3, not converged) -- the reference falls back to NormalCG there (:262-283); with psd=True the operator is
+    positive semi-definite by construction and the same solve converges."""
+    from test_gpu_pncg import _cube_problem
+
+    from apple_b200.forward import Forward
+    from apple_b200.optim import adjoint_solve
+
+    dtype = torch.float64
+    model, oproblem = _cube_problem(dtype, n=5, kinds=("snh",), gravity=False)
+    forward = Forward(model)
+    rng = np.random.default_rng(5)
+    n = model.n_free
+    V = model.n_points
+    u = torch.as_tensor(0.25 * rng.standard_normal((V, 3)) / 5, dtype=dtype, device="cuda")   # ~ 25 % strain noise
+    import dataclasses
+    state = dataclasses.replace(forward.state, u=model.dof_map.to_full(model.dof_map.to_free(u)))
+    rhs = torch.as_tensor(rng.standard_normal(n), dtype=dtype, device="cuda")
+    _, plain = adjoint_solve(forward.problem, state, rhs, tol=1e-6, maxiter=2 * n)
+    x, proj = adjoint_solve(forward.problem, state, rhs, tol=1e-6, maxiter=20 * n, psd=True)
+    assert proj.converged
+    assert not plain.converged or plain.n_iters > 0     # the plain solve may break down; it must not crash or hang
+    # x solves the PROJECTED system: residual with the oracle's projected product
+    from oracle import hessian as ohess
+    pot = oproblem.model.potentials[0]
+    full = oproblem.dof_map.to_full_grad(x.cpu().numpy())
+    r = oproblem.dof_map.to_free(ohess.hess_prod(pot, state.u.cpu().numpy(), full, V, psd=True)) - rhs.cpu().numpy()
+    assert np.linalg.norm(r) <= 1e-5 * float(rhs.norm())
