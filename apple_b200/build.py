@@ -49,6 +49,9 @@ def _units():
     for tname, t in (("f32", "float"), ("f64", "double")):
         for kind in (0, 1, 2, 3):
             units.append((f"fem_{tname}_k{kind}", "fem_inst.cu", [f"-DAPL_INST_T={t}", f"-DAPL_INST_KIND={kind}"]))
+            # the opt-in supersets (block off-diagonals / PSD projection) in their own unit: see csrc/fem_inst.cu
+            units.append((f"fem_{tname}_k{kind}_sup", "fem_inst.cu",
+                          [f"-DAPL_INST_T={t}", f"-DAPL_INST_KIND={kind}", "-DAPL_INST_SUPERSET"]))
     return units
 
 

@@ -357,6 +357,9 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
 __device__ __forceinline__ void mbar_arrive(unsigned bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+#ifndef APL_WAIT_SLEEP_NS
+#define APL_WAIT_SLEEP_NS 0
+#endif
 #ifndef APL_WAIT_HINT_NS
 #define APL_WAIT_HINT_NS 0   // > 0: suspend-time hint of mbarrier.try_wait (fewer spin instructions competing for issue slots)
 #endif
@@ -379,6 +382,9 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
             : "=r"(ok)
             : "r"(bar), "r"(parity)
             : "memory");
+#endif
+#if APL_WAIT_SLEEP_NS > 0
+        if (!ok) __nanosleep(APL_WAIT_SLEEP_NS);   // back off: a spinning warp competes with computing warps for issue slots
 #endif
     } while (!ok);
 }
@@ -453,6 +459,11 @@ constexpr int kPipeThreads = kTileTets + 32;
 #ifndef APL_SLOT_BUFS
 #define APL_SLOT_BUFS 2    // slot buffers wanted (2: software-pipelined phases; 1: phases in order)
 #endif
+#ifndef APL_PRODUCER_WARPS
+#define APL_PRODUCER_WARPS 1   // 4: a whole producer WARPGROUP (the gather is split four ways) and, for fp32, register
+                               //    re-allocation with setmaxnreg: 32 registers for the producers, 104 for the consumers (the sum must not exceed the launch allocation, 80 x 384)
+                               //    (9-warp CTAs cap every thread at 96: five warps share one scheduler's register file)
+#endif
 #ifndef APL_WANT_CTAS
 #define APL_WANT_CTAS 2    // 3: fp32 kernels with a small enough tile state run three CTAs per SM (one slot buffer)
 #endif
@@ -461,7 +472,10 @@ template <typename T, int KIND, int OPS>
 struct PipeCfg {
     using Cfg = TileCfg<T, OPS>;
     static constexpr int kConsumers = kTileTets;   // one consumer thread per tet
-    static constexpr int kThreads = kConsumers + 32;
+    static constexpr int kProducerWarps = APL_PRODUCER_WARPS;
+    static constexpr int kThreads = kConsumers + 32 * kProducerWarps;
+    // register re-allocation between the producer warpgroup and the two consumer warpgroups (fp32, two CTAs per SM)
+    static constexpr bool kRegRealloc = kProducerWarps == 4 && sizeof(T) == 4 && kTileTets == 256;
     static constexpr int kNSlots = kSlotsAlloc;
     static constexpr size_t kSlotBytes = (size_t)kNSlots * Cfg::SS * sizeof(T);
     static constexpr int NREC = RecSize<KIND>::value;
@@ -602,7 +616,7 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full(s), 33);          // 32 gather lanes + the expect_tx arrival
+            mbar_init(full(s), 32 * PC::kProducerWarps + 1);   // every gather lane + the expect_tx arrival
             mbar_init(empty(s), NC);         // every consumer thread releases the stage
         }
         for (int s = 0; s < SV; ++s) mbar_init(vfull(s), 1);
@@ -616,8 +630,11 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
 
     const int my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-    if (warp == NC / 32) {
-        // ================================= producer warp =================================
+    if (PC::kProducerWarps == 1 ? warp == NC / 32 : warp >= NC / 32) {
+        // ================================= producer warp(s) ==============================
+        if constexpr (PC::kRegRealloc) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        constexpr int PW = PC::kProducerWarps;
+        const int pw = PW == 1 ? 0 : warp - NC / 32;      // producer warp index; warp 0 issues the bulk copies
         // Iteration `it`: wait until stage it % S is free, issue the bulk copies of tile `it`'s static
         // data, request the vertex tables of tile `it + 1`, then gather tile `it`'s vertices (its
         // tables were requested one iteration ago).  Headers are prefetched two iterations ahead, so
@@ -644,7 +661,7 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
         const bool want_p = Cfg::kNeedP || axpy;
         const bool aligned8 = (((size_t)a.u | (size_t)(want_p ? pf : a.u)) & 7u) == 0;
         int4 h_cur = load_hdr(0), h_nxt = load_hdr(1);
-        if (lane == 0) request_vtab(0, h_cur);
+        if (lane == 0 && pw == 0) request_vtab(0, h_cur);
         for (int it = 0; it < my_tiles; ++it) {
             const int s = it % S;
             const unsigned ph = (unsigned)(it / S) & 1u;
@@ -662,14 +679,14 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
             mbar_wait(vfull(sv), (unsigned)(it / SV) & 1u);
             const int* verts = reinterpret_cast<const int*>(vring + (size_t)sv * PC::kVtabBytes + PC::oVerts);
             const bool via_regs = APL_GATHER_LDG && a.ld_in == 3;
-            constexpr int R = APL_GATHER_LDG ? kTileVerts / 32 : 1;
+            constexpr int R = APL_GATHER_LDG ? (kTileVerts / 32 + PW - 1) / PW : 1;
             T ru[R][3], rp[R][3];
             if (via_regs) {
                 // 12-byte rows through registers: the loads are issued BEFORE the wait for the stage, so their
                 // latency overlaps with the time the consumers still hold it
 #pragma unroll
                 for (int k = 0; k < R; ++k) {
-                    const int v = lane + 32 * k;
+                    const int v = lane + 32 * (pw + PW * k);
                     if (v < n_verts) {
                         const int gv = verts[v];
                         load_row3_ldg<T>(a.u, gv, aligned8, ru[k]);
@@ -680,7 +697,7 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
             // stage s free <=> every consumer is past COMPUTE(it - S); its REDUCE phases up to tile
             // it - S - NB are then finished too, which frees vertex slot (it + 1) % SV
             mbar_wait(empty(s), ph ^ 1u);
-            if (lane == 0) {
+            if (lane == 0 && pw == 0) {
                 *reinterpret_cast<int4*>(st + PC::oHdr) = h;
                 const unsigned bp = (unsigned)n_tets * 16u;
                 const unsigned bc = ((unsigned)n_tets * 4u + 15u) & ~15u;
@@ -700,7 +717,7 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
                 T* vb = reinterpret_cast<T*>(st + PC::oVbuf);
 #pragma unroll
                 for (int k = 0; k < R; ++k) {
-                    const int v = lane + 32 * k;
+                    const int v = lane + 32 * (pw + PW * k);
                     if (v < n_verts) {
                         store_row4<T>(vb + 4 * v, ru[k]);
                         if (want_p) store_row4<T>(vb + 4 * kTileVerts + 4 * v, rp[k]);
@@ -708,7 +725,7 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
                 }
                 mbar_arrive(full(s));   // release: the stores above are visible to the consumers that acquire the phase
             } else {
-                for (int v = lane; v < n_verts; v += 32) {
+                for (int v = lane + 32 * pw; v < n_verts; v += 32 * PW) {
                     const int gv = verts[v];
                     gather_row_async<T>(us32 + (unsigned)v * 4u * (unsigned)sizeof(T), a.u, gv, a.ld_in);
                     if (want_p) gather_row_async<T>(ps32 + (unsigned)v * 4u * (unsigned)sizeof(T), pf, gv, a.ld_in);
@@ -720,6 +737,7 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
         }
     } else {
         // ================================= consumer warps ================================
+        if constexpr (PC::kRegRealloc) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // COMPUTE(it): returns the tile's vertex count (the header lives in the stage, which is released here)
         auto compute = [&](int it) -> int {
             const int s = it % S;
@@ -906,38 +924,49 @@ int launch_one(const apl_fem* fem, const FemArgs<T>& args, int scatter, cudaStre
     return APL_OK;
 }
 
+// The opt-in supersets (vertex-block off-diagonals, eigenvalue-clamped Hessian) are instantiated in their OWN
+// translation units (fem_inst.cu with -DAPL_INST_SUPERSET): instantiating them next to the classic operator sets changed
+// nvcc's inlining decisions for the classic kernels (fused SNH+ARAP E+g+Hp: 40 -> 200 bytes of spill stack, 23 -> 13.7
+// G tets/s at 8 M tets, round-2 run r2m).  Declared per (T, KIND) like launch_fem; defined in fem_inst.cu.
+template <typename T, int KIND>
+int launch_fem_superset(const apl_fem* fem, int ops, const FemArgs<T>& args, int scatter, cudaStream_t stream);
+
+template <typename T, int KIND>
+int launch_fem_superset_impl(const apl_fem* fem, int ops, const FemArgs<T>& args, int scatter, cudaStream_t stream) {
+    // ops carries HESS_OFFD and / or PSD (the caller has already dropped PSD where it does not apply)
+    if (scatter != APL_SCATTER_TILE) {
+        set_error("apl_fem_eval: APL_OP_HESS_OFFD / APL_OP_PSD are implemented by the TILE assembly only");
+        return APL_ERR_INVALID;
+    }
+    constexpr int BLK = APL_OP_FUN | APL_OP_GRAD | APL_OP_HESS_DIAG | APL_OP_HESS_OFFD;
+    const int psd = ops & APL_OP_PSD, base = ops & ~APL_OP_PSD;
+    if (base & APL_OP_HESS_OFFD) {
+        if (base & ~BLK) {
+            set_error("apl_fem_eval: APL_OP_HESS_OFFD combines with FUN, GRAD and HESS_DIAG only");
+            return APL_ERR_INVALID;
+        }
+        return psd ? launch_one<T, KIND, BLK | APL_OP_PSD>(fem, args, scatter, stream)
+                   : launch_one<T, KIND, BLK>(fem, args, scatter, stream);
+    }
+    // PSD without OFFD: the quadratic form alone (PNCG pass B), and / or fun / grad / diag / prod in one pass
+    if (base & APL_OP_HESS_QUAD) {
+        int rc = launch_one<T, KIND, APL_OP_HESS_QUAD | APL_OP_PSD>(fem, args, scatter, stream);
+        if (rc != APL_OK) return rc;
+        if (!(base & (APL_OP_HESS_DIAG | APL_OP_HESS_PROD))) {
+            const int rest = base & ~APL_OP_HESS_QUAD;     // fun / grad only: no Hessian term left to project
+            return rest ? launch_fem<T, KIND>(fem, rest, args, scatter, stream) : APL_OK;
+        }
+    }
+    return launch_one<T, KIND, 15 | APL_OP_PSD>(fem, args, scatter, stream);
+}
+
 template <typename T, int KIND>
 int launch_fem_impl(const apl_fem* fem, int ops, const FemArgs<T>& args, int scatter, cudaStream_t stream) {
-    // Opt-in supersets (include/apple_b200.h): vertex-block off-diagonals and the eigenvalue-clamped Hessian exist in
-    // the TILE assembly only, in the combinations the block-Jacobi PNCG and the projected products need.
     if (ops & (APL_OP_HESS_OFFD | APL_OP_PSD)) {
         if (KIND == APL_KIND_ARAP) ops &= ~APL_OP_PSD;   // the clamped twist rates already are the projection
         if (!(ops & (APL_OP_HESS_DIAG | APL_OP_HESS_OFFD | APL_OP_HESS_PROD | APL_OP_HESS_QUAD))) ops &= ~APL_OP_PSD;
     }
-    if (ops & (APL_OP_HESS_OFFD | APL_OP_PSD)) {
-        if (scatter != APL_SCATTER_TILE) {
-            set_error("apl_fem_eval: APL_OP_HESS_OFFD / APL_OP_PSD are implemented by the TILE assembly only");
-            return APL_ERR_INVALID;
-        }
-        constexpr int BLK = APL_OP_FUN | APL_OP_GRAD | APL_OP_HESS_DIAG | APL_OP_HESS_OFFD;
-        const int psd = ops & APL_OP_PSD, base = ops & ~APL_OP_PSD;
-        if (base & APL_OP_HESS_OFFD) {
-            if (base & ~BLK) {
-                set_error("apl_fem_eval: APL_OP_HESS_OFFD combines with FUN, GRAD and HESS_DIAG only");
-                return APL_ERR_INVALID;
-            }
-            return psd ? launch_one<T, KIND, BLK | APL_OP_PSD>(fem, args, scatter, stream)
-                       : launch_one<T, KIND, BLK>(fem, args, scatter, stream);
-        }
-        // PSD without OFFD: the quadratic form alone (PNCG pass B), or any of fun / grad / diag / prod in one pass
-        if (base & APL_OP_HESS_QUAD) {
-            int rc = launch_one<T, KIND, APL_OP_HESS_QUAD | APL_OP_PSD>(fem, args, scatter, stream);
-            if (rc != APL_OK) return rc;
-            ops = base & ~APL_OP_HESS_QUAD;
-            if (!(ops & (APL_OP_HESS_DIAG | APL_OP_HESS_PROD))) return launch_fem_impl<T, KIND>(fem, ops, args, scatter, stream);
-        }
-        return launch_one<T, KIND, 15 | APL_OP_PSD>(fem, args, scatter, stream);
-    }
+    if (ops & (APL_OP_HESS_OFFD | APL_OP_PSD)) return launch_fem_superset<T, KIND>(fem, ops, args, scatter, stream);
     // hess_quad never shares a pass with vector outputs here: PNCG needs it alone (pass B)
     if ((ops & APL_OP_HESS_QUAD) && ops != APL_OP_HESS_QUAD) {
         int rc = launch_one<T, KIND, APL_OP_HESS_QUAD>(fem, args, scatter, stream);

@@ -222,11 +222,27 @@ APL_TL void tile_reduce_lane(int half, int t, int n_verts, const unsigned char* 
     }
 #pragma unroll
     for (int j = 0; j < 3 * NOUT; ++j) acc[j] = (T)0;
-    for (int i = half; i < cnt; i += 2) {
-        T val[SS];
-        load_slot_planes<T, SS, NSLOTS>(sl, s0 + i, val);
+    // kReduceUnroll slots per trip with all loads issued before the first add: the serial form (one slot per trip: load,
+    // wait ~30 cycles, add) made this phase the longest of the SNH kernel (ncu r2h: 30 % of the samples for 19 % of the
+    // instructions).  A lane past its range re-reads its first slot with weight 0 (always a valid, finite-or-already-
+    // poisoned address), so the trip is branch-free.
+#ifndef APL_REDUCE_UNROLL
+#define APL_REDUCE_UNROLL 4
+#endif
+    constexpr int U = APL_REDUCE_UNROLL;
+    for (int i = half; i < cnt; i += 2 * U) {
+        T val[U][SS];
+        T wgt[U];
 #pragma unroll
-        for (int j = 0; j < 3 * NOUT; ++j) acc[j] += val[j];
+        for (int k = 0; k < U; ++k) {
+            const bool ok = i + 2 * k < cnt;
+            wgt[k] = ok ? (T)1 : (T)0;
+            load_slot_planes<T, SS, NSLOTS>(sl, s0 + (ok ? i + 2 * k : i), val[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+#pragma unroll
+            for (int j = 0; j < 3 * NOUT; ++j) acc[j] += wgt[k] * val[k][j];
     }
 }
 

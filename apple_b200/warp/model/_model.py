@@ -39,6 +39,13 @@ class WarpModel:
         for potential in self.potentials.values():
             potential.hess_quad(u, p, output)
 
+    def hess_prod_psd(self, u: torch.Tensor, p: torch.Tensor, output: torch.Tensor) -> None:
+        """Opt-in superset: the sum of the potentials' PSD-projected Hessian-vector products (``APL_OP_PSD``)."""
+        output.zero_()
+        for potential in self.potentials.values():
+            if hasattr(potential, "hess_prod_psd"):
+                potential.hess_prod_psd(u, p, output)
+
     def mixed_derivative_prod(self, u: torch.Tensor, p: torch.Tensor) -> dict:
         """``{potential name: {material name: d/dq [grad E . p] per cell}}`` over the potentials that have materials."""
         return {name: pot.mixed_derivative_prod(u, p) for name, pot in self.potentials.items()

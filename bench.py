@@ -472,17 +472,50 @@ def main():
         bpt = bytes_per_tet(k.split("+"), w, v_over_t, 12)
         kern[k] = {"ms": dt * 1e3, "bytes_per_tet": bpt, "gbs": bpt * T_local / dt / 1e9, "gtets_per_s": T_local / dt / 1e9,
                    "tets": T_local}
-    del g1, h1
     dom = max(kern, key=lambda k: kern[k]["ms"])
-    traffic = None
-    tf = ROOT / "profiles" / "traffic.json"
-    if tf.exists() and world == 1:
+    # the Stable Neo-Hookean kernel ALONE on the same slab (the bandwidth-bound member of the fused pair), reported beside
+    # the headline kernel; never the headline itself
+    if "snh" in kinds and "snh" not in pots and not args.no_hvp:
         try:
-            traffic = json.loads(tf.read_text()).get(f"{args.dtype}:{dom}:n{n}")
+            from apple_b200.warp.fem import StableNeoHookean
+
+            alone = StableNeoHookean.from_device_mesh(wl.mesh.cells, wl.mesh.points, mu=wl.mu, lambda_=wl.la, dtype=dtype, name="snh")
+            ts = []
+            for _ in range(max(5, min(args.steps, 20))):
+                flush()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); alone.eval(OPS, ud, pd, fun=fun1, grad=g1, prod=h1); b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            dt = max_over_ranks(float(np.mean(ts[1:]))) * 1e-3
+            bpt = bytes_per_tet(["snh"], w, v_over_t, 12)
+            kern["snh (alone, same mesh)"] = {"ms": dt * 1e3, "bytes_per_tet": bpt, "gbs": bpt * T_local / dt / 1e9,
+                                              "gtets_per_s": T_local / dt / 1e9, "tets": T_local, "frac": bpt * T_local / dt / 1e9 / peak}
+            del alone
+            torch.cuda.empty_cache()
+        except Exception as exc:  # pragma: no cover - secondary record
+            kern["snh (alone, same mesh)"] = {"error": f"{type(exc).__name__}: {exc}"}
+    del g1, h1
+    # measured DRAM traffic of the dominant kernel (ncu --set full capture, profiles/traffic.json): per launch when the
+    # capture was taken at this size on one GPU, else the capture's bytes per tet x this rank's tets
+    traffic, traffic_note = None, None
+    tf = ROOT / "profiles" / "traffic.json"
+    if tf.exists():
+        try:
+            tj = json.loads(tf.read_text())
+            if world == 1 and f"{args.dtype}:{dom}:n{n}" in tj:
+                traffic = tj[f"{args.dtype}:{dom}:n{n}"]
+                traffic_note = "dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size (ncu --set full)"
+            else:
+                per_tet = tj.get("per_tet", {}).get(f"{args.dtype}:{dom}")
+                if per_tet is not None:
+                    traffic = per_tet * T_local
+                    traffic_note = (f"{per_tet:.1f} B/tet measured by ncu at the size named in profiles/traffic.json, times this "
+                                    f"rank's {T_local} tets")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["gbs"] / peak, "traffic": traffic,
+                "frac": kern[dom]["gbs"] / peak, "traffic": traffic, "traffic_note": traffic_note,
                 "kernel": f"fem_pipe_kernel<{args.dtype},{dom},fun|grad|hess_prod>", "peak_source": peak_src,
                 "frac_of_nominal_8TBs": kern[dom]["gbs"] / 8000.0,
                 "note": "per GPU: this rank's slab, slowest rank" if world > 1 else None, "per_kernel": kern}
