@@ -919,6 +919,152 @@ APL_HD void elem_eval(const T* rec, const T (*uc)[3], const T (*pc)[3], T& psi, 
 }
 
 // ------------------------------------------------------------------------------------------
+// Packed fp32 pairs.  Blackwell issues two fp32 lanes per instruction (SASS FFMA2 / FADD2 / FMUL2, PTX *.f32x2) with an
+// optional SCALAR BROADCAST operand; the fp32 FLOP rate is the same as with scalar FFMA (measured: profiles/
+// r2i_ubench_f32x2.txt, 72.4 vs 69.7 TFLOP/s) but every pair costs ONE issue slot -- and these kernels are bound by
+// instruction issue and the shared-memory pipe, not by the FMA pipe (26-41 % busy).  The two lanes carry the SAME
+// operation on two quantities of ONE tet that share the dhdX factor:
+//   {F, dF} = {u, p}^T dhdX          (deformation gradient of the state and of the direction)
+//   {g, Hp} = dhdX {P, M}^T          (nodal forces of the stress and of its tangent)
+// so no data has to be shuffled between threads or registers: the gathered vertex rows are stored INTERLEAVED in shared
+// memory ([ux uy px py | uz pz - -]) and the slots hold [gx gy hx hy | gz hz], both produced / consumed as they come.
+// The 3x3 stress / tangent algebra in between stays scalar.
+// ------------------------------------------------------------------------------------------
+struct f32x2 {
+    float lo, hi;
+};
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ unsigned long long p2_bits(f32x2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.lo), "f"(a.hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 p2_from(unsigned long long r) {
+    f32x2 a;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a.lo), "=f"(a.hi) : "l"(r));
+    return a;
+}
+#endif
+APL_HD f32x2 p2_make(float a, float b) { f32x2 r; r.lo = a; r.hi = b; return r; }
+APL_HD f32x2 p2_add(f32x2 a, f32x2 b) {
+#if defined(__CUDA_ARCH__)
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(p2_bits(a)), "l"(p2_bits(b)));
+    return p2_from(r);
+#else
+    return p2_make(a.lo + b.lo, a.hi + b.hi);
+#endif
+}
+APL_HD f32x2 p2_sub(f32x2 a, f32x2 b) {
+#if defined(__CUDA_ARCH__)
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(p2_bits(a)), "l"(p2_bits(b)));
+    return p2_from(r);
+#else
+    return p2_make(a.lo - b.lo, a.hi - b.hi);
+#endif
+}
+// a * s (s broadcast to both lanes)
+APL_HD f32x2 p2_mul_s(f32x2 a, float s) {
+#if defined(__CUDA_ARCH__)
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(p2_bits(a)), "l"(p2_bits(p2_make(s, s))));
+    return p2_from(r);
+#else
+    return p2_make(a.lo * s, a.hi * s);
+#endif
+}
+// a * s + c (s broadcast to both lanes)
+APL_HD f32x2 p2_fma_s(f32x2 a, float s, f32x2 c) {
+#if defined(__CUDA_ARCH__)
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(p2_bits(a)), "l"(p2_bits(p2_make(s, s))), "l"(p2_bits(c)));
+    return p2_from(r);
+#else
+    return p2_make(std::fma(a.lo, s, c.lo), std::fma(a.hi, s, c.hi));
+#endif
+}
+
+// One tetrahedron, fp32, operator set that reads BOTH nodal fields (hess_prod / hess_quad), packed:
+//   u01[c] = (u_x, u_y), p01[c] = (p_x, p_y), upz[c] = (u_z, p_z) of corner c  ->  {F, dF} in 27 packed instructions;
+// PACK_OUT (operator sets {grad, hess_prod} (+ fun)): g01[c] = (g_x, g_y), h01[c] = (Hp_x, Hp_y), gzhz[c] = (g_z, Hp_z)
+// from {P, M} in 36 packed instructions; otherwise the scalar outputs g, dg, hp of elem_eval.
+// Same arithmetic as elem_eval, element for element.
+template <int KIND, int OPS, bool PACK_OUT>
+APL_HD void elem_eval_packed(const float* rec, const f32x2 u01[4], const f32x2 p01[4], const f32x2 upz[4], float& psi,
+                             float& quad, f32x2 g01[4], f32x2 h01[4], f32x2 gzhz[4], float g[4][3], float dg[4][3],
+                             float hp[4][3]) {
+    static_assert((OPS & (APL_OP_HESS_PROD | APL_OP_HESS_QUAD)) != 0, "the packed form pairs the state with the direction");
+    static_assert(!PACK_OUT || ((OPS & APL_OP_GRAD) && (OPS & APL_OP_HESS_PROD) &&
+                                !(OPS & (APL_OP_HESS_DIAG | APL_OP_HESS_OFFD))), "packed outputs: grad + hess_prod");
+    float D[9], A[9];
+    if constexpr (KIND == APL_KIND_SNH_MUSCLE) {
+        const float Am[9] = {1.0f + rec[12], rec[15], rec[16], rec[15], 1.0f + rec[13], rec[17], rec[16], rec[17], 1.0f + rec[14]};
+#pragma unroll
+        for (int k = 0; k < 9; ++k) A[k] = Am[k];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int J = 0; J < 3; ++J) D[3 * a + J] = rec[3 * a] * A[J] + rec[3 * a + 1] * A[3 + J] + rec[3 * a + 2] * A[6 + J];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { D[k] = rec[k]; A[k] = (k % 4 == 0) ? 1.0f : 0.0f; }
+    }
+    // edge differences of (u_x, u_y), (p_x, p_y), (u_z, p_z)
+    f32x2 eu[3], ep[3], ez[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        eu[a] = p2_sub(u01[a + 1], u01[0]);
+        ep[a] = p2_sub(p01[a + 1], p01[0]);
+        ez[a] = p2_sub(upz[a + 1], upz[0]);
+    }
+    // {F[J], F[3+J]}, {dF[J], dF[3+J]}, {F[6+J], dF[6+J]} = sum_a e[a] * D[3a+J]
+    float F[9], dF[9];
+#pragma unroll
+    for (int J = 0; J < 3; ++J) {
+        const f32x2 f = p2_fma_s(eu[2], D[6 + J], p2_fma_s(eu[1], D[3 + J], p2_mul_s(eu[0], D[J])));
+        const f32x2 d = p2_fma_s(ep[2], D[6 + J], p2_fma_s(ep[1], D[3 + J], p2_mul_s(ep[0], D[J])));
+        const f32x2 z = p2_fma_s(ez[2], D[6 + J], p2_fma_s(ez[1], D[3 + J], p2_mul_s(ez[0], D[J])));
+        F[J] = f.lo + A[J]; F[3 + J] = f.hi + A[3 + J]; F[6 + J] = z.lo + A[6 + J];
+        dF[J] = d.lo; dF[3 + J] = d.hi; dF[6 + J] = z.hi;
+    }
+    float P[9], M[9];
+    float ods[4][3];   // (no packed operator set has hess_offd)
+    if constexpr (KIND == APL_KIND_SNH || KIND == APL_KIND_SNH_MUSCLE) {
+        snh_terms<float, OPS, false>(F, dF, D, rec[9], rec[10], rec[11], psi, quad, P, M, dg, ods);
+    } else if constexpr (KIND == APL_KIND_ARAP) {
+        arap_terms<float, OPS, false>(F, dF, D, rec[9], rec[10], psi, quad, P, M, dg, ods);
+    } else {
+        snh_terms<float, OPS, false>(F, dF, D, rec[9], rec[10], rec[11], psi, quad, P, M, dg, ods);
+        arap_terms<float, OPS, true>(F, dF, D, rec[12], rec[13], psi, quad, P, M, dg, ods);
+    }
+    if constexpr (PACK_OUT) {
+        // nodal forces: out[a][i] = sum_J D[3(a-1)+J] X[3i+J]; rows (x, y) of P and of M, and row z of both, as pairs
+        f32x2 Pp[3], Mp[3], Zp[3];
+#pragma unroll
+        for (int J = 0; J < 3; ++J) {
+            Pp[J] = p2_make(P[J], P[3 + J]);
+            Mp[J] = p2_make(M[J], M[3 + J]);
+            Zp[J] = p2_make(P[6 + J], M[6 + J]);
+        }
+#pragma unroll
+        for (int a = 1; a < 4; ++a) {
+            const float* d = D + 3 * (a - 1);
+            g01[a] = p2_fma_s(Pp[2], d[2], p2_fma_s(Pp[1], d[1], p2_mul_s(Pp[0], d[0])));
+            h01[a] = p2_fma_s(Mp[2], d[2], p2_fma_s(Mp[1], d[1], p2_mul_s(Mp[0], d[0])));
+            gzhz[a] = p2_fma_s(Zp[2], d[2], p2_fma_s(Zp[1], d[1], p2_mul_s(Zp[0], d[0])));
+        }
+        const f32x2 zero = p2_make(0.0f, 0.0f);
+        g01[0] = p2_sub(p2_sub(p2_sub(zero, g01[1]), g01[2]), g01[3]);
+        h01[0] = p2_sub(p2_sub(p2_sub(zero, h01[1]), h01[2]), h01[3]);
+        gzhz[0] = p2_sub(p2_sub(p2_sub(zero, gzhz[1]), gzhz[2]), gzhz[3]);
+    } else {
+        if constexpr ((OPS & APL_OP_GRAD) != 0) vjp_rows1(D, P, g);
+        if constexpr ((OPS & APL_OP_HESS_PROD) != 0) vjp_rows1(D, M, hp);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Mixed derivative product: d/dq [ grad_u E . p ] per cell, for each material parameter q of the cell's energy
 // -- what the reference's inverse problems call `mixed_derivative_prod(state, p)` after the adjoint solve
 // (exp/2026/01/28/smas/src/31-inverse-activation-stable-neo-hookean.py:472-487; the method is absent from the

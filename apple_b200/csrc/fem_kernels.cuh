@@ -393,6 +393,10 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// DRAM -> L2 only (no shared memory needed): lets the producer run the static stream several tiles ahead of the stages
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 template <int BYTES>
 __device__ __forceinline__ void cp_async(unsigned dst, const void* src) {
     if constexpr (BYTES == 16)
@@ -415,6 +419,29 @@ __device__ __forceinline__ void gather_row_async(unsigned dst, const T* base, in
         cp_async<sizeof(T)>(dst, src);
         cp_async<sizeof(T)>(dst + sizeof(T), src + 1);
         cp_async<sizeof(T)>(dst + 2 * sizeof(T), src + 2);
+    }
+}
+
+// Packed layout (TileCfg::kPackedIn): row v of the first array is [ux uy px py] (16 bytes), row v of the second array,
+// kTileVerts * 16 bytes further, is [uz pz] (8 bytes).  dst = address of the first array.
+__device__ __forceinline__ void gather_row_packed(unsigned dst, const float* u, const float* p, int v, int lv, int ld) {
+    const unsigned a = dst + 16u * (unsigned)lv, b = dst + 16u * (unsigned)kTileVerts + 8u * (unsigned)lv;
+    if (ld == 4) {
+        const float* su = u + 4ll * v;
+        const float* sp = p + 4ll * v;
+        cp_async<8>(a, su);
+        cp_async<8>(a + 8, sp);
+        cp_async<4>(b, su + 2);
+        cp_async<4>(b + 4, sp + 2);
+    } else {
+        const float* su = u + 3ll * v;
+        const float* sp = p + 3ll * v;
+        cp_async<4>(a, su);
+        cp_async<4>(a + 4, su + 1);
+        cp_async<4>(a + 8, sp);
+        cp_async<4>(a + 12, sp + 1);
+        cp_async<4>(b, su + 2);
+        cp_async<4>(b + 4, sp + 2);
     }
 }
 
@@ -460,9 +487,21 @@ constexpr int kPipeThreads = kTileTets + 32;
 #define APL_SLOT_BUFS 2    // slot buffers wanted (2: software-pipelined phases; 1: phases in order)
 #endif
 #ifndef APL_PRODUCER_WARPS
-#define APL_PRODUCER_WARPS 1   // 4: a whole producer WARPGROUP (the gather is split four ways) and, for fp32, register
-                               //    re-allocation with setmaxnreg: 32 registers for the producers, 104 for the consumers (the sum must not exceed the launch allocation, 80 x 384)
-                               //    (9-warp CTAs cap every thread at 96: five warps share one scheduler's register file)
+#define APL_PRODUCER_WARPS 1   // producer warps of the kernels that do not spill
+#endif
+#ifndef APL_PRODUCER_WARPS_FUSED
+#define APL_PRODUCER_WARPS_FUSED 4   // fp32 SNH+ARAP kernels: a whole producer WARPGROUP (the gather is split four ways)
+                                     // and register re-allocation with setmaxnreg: 32 registers for the producers, 104 for
+                                     // the consumers (the sum must not exceed the launch allocation, 80 x 384).  A 9-warp
+                                     // CTA caps every thread at 96 registers (five warps share one scheduler's file) and
+                                     // the fused kernels spill there; measured +3.7 % (run r2n).  The other kernels do
+                                     // not spill and lose 2-5 % to the extra warps.
+#endif
+#ifndef APL_L2_PREFETCH
+#define APL_L2_PREFETCH 0   // 1: bulk L2 prefetch of tile it + 2's static stream; 2: also the vertex rows of tile it + 1.
+                            // NEGATIVE result, kept as a knob: interleaved A/B on one box (run r2q, G tets/s, 0 / 1 / 2):
+                            // SNH 8 M 37.0 / 35.6 / 31.8, SNH 64 M 39.2 / 37.6 / 33.2, SNH+ARAP 64 M 25.5 / 25.2 / 24.5, HVP
+                            // alone 45.1 / 40.1 / 35.3 -- the bulk copies of the stages already keep enough bytes in flight.
 #endif
 #ifndef APL_WANT_CTAS
 #define APL_WANT_CTAS 2    // 3: fp32 kernels with a small enough tile state run three CTAs per SM (one slot buffer)
@@ -472,7 +511,8 @@ template <typename T, int KIND, int OPS>
 struct PipeCfg {
     using Cfg = TileCfg<T, OPS>;
     static constexpr int kConsumers = kTileTets;   // one consumer thread per tet
-    static constexpr int kProducerWarps = APL_PRODUCER_WARPS;
+    static constexpr int kProducerWarps =
+        (KIND == APL_KIND_SNH_ARAP && sizeof(T) == 4 && kTileTets == 256) ? APL_PRODUCER_WARPS_FUSED : APL_PRODUCER_WARPS;
     static constexpr int kThreads = kConsumers + 32 * kProducerWarps;
     // register re-allocation between the producer warpgroup and the two consumer warpgroups (fp32, two CTAs per SM)
     static constexpr bool kRegRealloc = kProducerWarps == 4 && sizeof(T) == 4 && kTileTets == 256;
@@ -536,7 +576,7 @@ struct PipeCfg {
 // ALL slot reads of the thread (at most two groups: kTileVerts <= NT) come first, then `release` (the arrival on the
 // slots-free barrier), then the REDs: an mbarrier arrival has release semantics and would otherwise wait for
 // the thread's outstanding REDs to be performed -- a round trip to L2 on the critical path of every tile.
-template <typename T, int OPS, int NT, int NSLOTS, typename Release>
+template <typename T, int OPS, int NT, int NSLOTS, bool PACKED_SLOTS, typename Release>
 __device__ __forceinline__ void tile_reduce_flush(int tid, int rot, int n_verts, const unsigned char* vperm,
                                                   const unsigned short* voff, const int* verts, const T* sl,
                                                   const FemArgs<T>& a, Release&& release) {
@@ -575,7 +615,10 @@ __device__ __forceinline__ void tile_reduce_flush(int tid, int rot, int n_verts,
             if (half == 0 && outs[0]) red_row(outs[0], gv[trip], a.ld_out, s);
         } else {
             T* base = half ? outs[1] : outs[0];
-            const T val[3] = {half ? s[3] : s[0], half ? s[4] : s[1], half ? s[5] : s[2]};
+            // slot order: [g(3), second field(3)], or packed [gx gy hx hy gz hz] (tile_compute_packed)
+            constexpr bool PK = Cfg::kPacked && PACKED_SLOTS;
+            const T val[3] = {half ? s[PK ? 2 : 3] : s[0], half ? s[PK ? 3 : 4] : s[PK ? 1 : 1],
+                              half ? s[5] : s[PK ? 4 : 2]};
             if (base) red_row(base, gv[trip], a.ld_out, val);
             if constexpr (NOUT == 3) {
                 if (half == 0 && outs[2]) red_row(outs[2], gv[trip], a.ld_out, s + 6);
@@ -660,14 +703,14 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
         const T* pf = Cfg::kNeedP ? a.p : a.axpy_p;     // second gathered field (nullptr: none)
         const bool want_p = Cfg::kNeedP || axpy;
         const bool aligned8 = (((size_t)a.u | (size_t)(want_p ? pf : a.u)) & 7u) == 0;
-        int4 h_cur = load_hdr(0), h_nxt = load_hdr(1);
+        int4 h_cur = load_hdr(0), h_nxt = load_hdr(1), h_nn = load_hdr(2);
         if (lane == 0 && pw == 0) request_vtab(0, h_cur);
         for (int it = 0; it < my_tiles; ++it) {
             const int s = it % S;
             const unsigned ph = (unsigned)(it / S) & 1u;
             unsigned char* st = stages + (size_t)s * PC::kStageBytes;
             const unsigned st32 = smem_u32(st);
-            const int4 h_nn = load_hdr(it + 2);
+            const int4 h_n3 = load_hdr(it + 3);   // three tiles ahead: consumed (L2 prefetch) one iteration later
             int4 h;
             h.x = __shfl_sync(0xffffffffu, h_cur.x, 0);
             h.y = __shfl_sync(0xffffffffu, h_cur.y, 0);
@@ -678,7 +721,7 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
             const int sv = it % SV;
             mbar_wait(vfull(sv), (unsigned)(it / SV) & 1u);
             const int* verts = reinterpret_cast<const int*>(vring + (size_t)sv * PC::kVtabBytes + PC::oVerts);
-            const bool via_regs = APL_GATHER_LDG && a.ld_in == 3;
+            const bool via_regs = APL_GATHER_LDG && a.ld_in == 3 && !Cfg::kPackedIn;
             constexpr int R = APL_GATHER_LDG ? (kTileVerts / 32 + PW - 1) / PW : 1;
             T ru[R][3], rp[R][3];
             if (via_regs) {
@@ -710,6 +753,19 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
                 bulk_g2s(st32 + (unsigned)PC::oConn, a.conn + h.x, bc, full(s));
                 if constexpr (NOUT > 0) bulk_g2s(st32 + (unsigned)PC::oSlots, a.slots + h.x, bs, full(s));
                 if (it + 1 < my_tiles) request_vtab(it + 1, h_nxt);
+#if APL_L2_PREFETCH
+                // experiment (off by default, see APL_L2_PREFETCH): tile it + 2's static stream pulled into L2 two tile
+                // periods before its bulk copies are issued
+                if (it + 2 < my_tiles) {
+                    const unsigned nt2 = (unsigned)(h_nn.y & 0xffff), nv2 = (unsigned)(h_nn.y >> 16);
+                    const unsigned pb = nt2 * 16u;
+#pragma unroll
+                    for (int k = 0; k < PC::NPL; ++k) bulk_prefetch_l2(a.planes + k * a.plane_stride + h_nn.x, pb);
+                    bulk_prefetch_l2(a.conn + h_nn.x, (nt2 * 4u + 15u) & ~15u);
+                    if constexpr (NOUT > 0) bulk_prefetch_l2(a.slots + h_nn.x, (nt2 * 8u + 15u) & ~15u);
+                    bulk_prefetch_l2(a.tile_verts + h_nn.z, (nv2 * 4u + 15u) & ~15u);
+                }
+#endif
             }
             const unsigned us32 = st32 + (unsigned)PC::oVbuf;
             const unsigned ps32 = us32 + 4u * kTileVerts * (unsigned)sizeof(T);
@@ -727,13 +783,35 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
             } else {
                 for (int v = lane + 32 * pw; v < n_verts; v += 32 * PW) {
                     const int gv = verts[v];
-                    gather_row_async<T>(us32 + (unsigned)v * 4u * (unsigned)sizeof(T), a.u, gv, a.ld_in);
-                    if (want_p) gather_row_async<T>(ps32 + (unsigned)v * 4u * (unsigned)sizeof(T), pf, gv, a.ld_in);
+                    if constexpr (Cfg::kPackedIn) {
+                        gather_row_packed(us32, (const float*)a.u, (const float*)pf, gv, v, a.ld_in);
+                    } else {
+                        gather_row_async<T>(us32 + (unsigned)v * 4u * (unsigned)sizeof(T), a.u, gv, a.ld_in);
+                        if (want_p) gather_row_async<T>(ps32 + (unsigned)v * 4u * (unsigned)sizeof(T), pf, gv, a.ld_in);
+                    }
                 }
                 cp_async_arrive_noinc(full(s));
             }
+#if APL_L2_PREFETCH >= 2
+            // The vertex rows of tile it + 1 into L2 now (its table was requested above and the producer has nothing else
+            // to do until the next stage frees up): the gather of the next iteration then hits L2 instead of DRAM.  Matters
+            // when the nodal fields do not fit the 126 MB L2 (64 M tets: 2 x 156 MB).
+            if (it + 1 < my_tiles) {
+                const int sv1 = (it + 1) % SV;
+                mbar_wait(vfull(sv1), (unsigned)((it + 1) / SV) & 1u);
+                const int* verts1 = reinterpret_cast<const int*>(vring + (size_t)sv1 * PC::kVtabBytes + PC::oVerts);
+                const int nv1 = __shfl_sync(0xffffffffu, h_nxt.y, 0) >> 16;
+                const size_t row = (size_t)a.ld_in * sizeof(T);
+                for (int v = lane + 32 * pw; v < nv1; v += 32 * PW) {
+                    const size_t off = (size_t)verts1[v] * row;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(a.u) + off));
+                    if (want_p) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(pf) + off));
+                }
+            }
+#endif
             h_cur = h_nxt;
             h_nxt = h_nn;
+            h_nn = h_n3;
         }
     } else {
         // ================================= consumer warps ================================
@@ -760,7 +838,10 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
                 const uchar4 lc = reinterpret_cast<const uchar4*>(st + PC::oConn)[tid];
                 ushort4 s4 = make_ushort4(0, 0, 0, 0);
                 if constexpr (NOUT > 0) s4 = reinterpret_cast<const ushort4*>(st + PC::oSlots)[tid];
-                tile_compute<T, KIND, OPS>(rec.s, lc, s4, us, ps, axpy, alpha, sl, e_acc, q_acc);
+                if constexpr (Cfg::kPackedIn)
+                    tile_compute_packed<KIND, OPS>(rec.s, lc, s4, (const float*)us, (float*)sl, e_acc, q_acc);
+                else
+                    tile_compute<T, KIND, OPS>(rec.s, lc, s4, us, ps, axpy, alpha, sl, e_acc, q_acc);
             }
             if constexpr (NOUT > 0) mbar_arrive(sfull(it % NB));
             mbar_arrive(empty(s));
@@ -773,7 +854,7 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
                 const unsigned char* vt = vring + (size_t)(it % SV) * PC::kVtabBytes;
                 const T* sl = reinterpret_cast<const T*>(smem_raw + PC::oSlotBuf + (size_t)(it % NB) * PC::kSlotBytes);
                 mbar_wait(sfull(it % NB), (unsigned)(it / NB) & 1u);
-                tile_reduce_flush<T, OPS, NC, PC::kNSlots>(tid, it, n_verts, vt + PC::oVperm,
+                tile_reduce_flush<T, OPS, NC, PC::kNSlots, true>(tid, it, n_verts, vt + PC::oVperm,
                                                            reinterpret_cast<const unsigned short*>(vt + PC::oVoff),
                                                            reinterpret_cast<const int*>(vt + PC::oVerts), sl, a,
                                                            [&] { mbar_arrive(sfree(it % NB)); });

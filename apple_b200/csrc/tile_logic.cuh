@@ -56,6 +56,15 @@ struct TileCfg {
     static constexpr bool kQuad = (OPS & APL_OP_HESS_QUAD) != 0;
     static constexpr bool kNeedP = (OPS & (APL_OP_HESS_PROD | APL_OP_HESS_QUAD)) != 0;
     static constexpr int NOUT = (kGrad ? 1 : 0) + (kDiag ? 1 : 0) + (kProd ? 1 : 0);
+    // packed fp32 forms (elem_math.cuh: elem_eval_packed).  kPackedIn: the operator set reads u AND p -> interleaved
+    // vertex rows [ux uy px py | uz pz - -] and {F, dF} in packed instructions; kPacked: in addition the nodal outputs are
+    // exactly {grad, hess_prod} -> slots [gx gy hx hy | gz hz] from packed {g, Hp}.
+#ifndef APL_PACKED
+#define APL_PACKED 1
+#endif
+    static constexpr bool kPackedIn = APL_PACKED && sizeof(T) == 4 && kNeedP && (OPS & APL_OP_PSD) == 0;
+    static constexpr bool kPacked = kPackedIn && kGrad && (OPS & APL_OP_HESS_PROD) != 0 &&
+                                    (OPS & (APL_OP_HESS_DIAG | APL_OP_HESS_OFFD)) == 0;
     // scalars per slot: 3*NOUT rounded up to whole 16-byte planes plus, for fp32, one 8-byte tail plane
     static constexpr int SS = (NOUT == 0) ? 0
                               : (NOUT == 1) ? 4
@@ -197,6 +206,52 @@ APL_TL void tile_compute(const T* rec, uchar4 lc, ushort4 s4, const T* us, const
     }
 }
 
+// Packed form of tile_compute (TileCfg::kPackedIn): vb holds the tile's vertices as kTileVerts rows [ux uy px py]
+// followed by kTileVerts rows [uz pz].
+template <int KIND, int OPS>
+APL_TL void tile_compute_packed(const float* rec, uchar4 lc, ushort4 s4, const float* vb, float* sl, double& e_acc,
+                                double& q_acc) {
+    using Cfg = TileCfg<float, OPS>;
+    constexpr int NOUT = Cfg::NOUT, SS = Cfg::SS;
+    static_assert(Cfg::kPackedIn && (!Cfg::kPacked || SS == 6), "packed slots are one 16-byte plane plus the 8-byte tail");
+    const int l[4] = {lc.x, lc.y, lc.z, lc.w};
+    f32x2 u01[4], p01[4], upz[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        // 16-byte rows [ux uy px py] (same bank pattern as the scalar form's u rows, which the tile tables make
+        // conflict-free) followed by 8-byte rows [uz pz]; 32-byte interleaved rows doubled the bank conflicts (run r2o)
+        const float4 q = *reinterpret_cast<const float4*>(vb + 4 * l[c]);
+        const float2 r = *reinterpret_cast<const float2*>(vb + 4 * kTileVerts + 2 * l[c]);
+        u01[c] = p2_make(q.x, q.y);
+        p01[c] = p2_make(q.z, q.w);
+        upz[c] = p2_make(r.x, r.y);
+    }
+    float psi = 0, quad = 0;
+    f32x2 g01[4], h01[4], gzhz[4];
+    float g[4][3], dg[4][3], hp[4][3];
+    elem_eval_packed<KIND, OPS, Cfg::kPacked>(rec, u01, p01, upz, psi, quad, g01, h01, gzhz, g, dg, hp);
+    if constexpr (Cfg::kFun) e_acc += (double)psi;
+    if constexpr (Cfg::kQuad) q_acc += (double)quad;
+    if constexpr (NOUT > 0) {
+        const int sidx[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float v[SS];
+            if constexpr (Cfg::kPacked) {
+                v[0] = g01[c].lo; v[1] = g01[c].hi; v[2] = h01[c].lo; v[3] = h01[c].hi; v[4] = gzhz[c].lo; v[5] = gzhz[c].hi;
+            } else {
+                int k = 0;
+                if constexpr (Cfg::kGrad) { v[k] = g[c][0]; v[k + 1] = g[c][1]; v[k + 2] = g[c][2]; k += 3; }
+                if constexpr (Cfg::kDiag) { v[k] = dg[c][0]; v[k + 1] = dg[c][1]; v[k + 2] = dg[c][2]; k += 3; }
+                if constexpr (Cfg::kProd) { v[k] = hp[c][0]; v[k + 1] = hp[c][1]; v[k + 2] = hp[c][2]; k += 3; }
+#pragma unroll
+                for (int j = 3 * NOUT; j < SS; ++j) v[j] = 0.0f;
+            }
+            store_slot_planes<float, SS>(sl, sidx[c], v);
+        }
+    }
+}
+
 // Two threads (lanes l and l+16 of a warp) together sum the slot range of one vertex, taken in valence
 // order (balanced trip counts, all consumer warps busy), combine with one shuffle, and the lower lane
 // parks the 3*NOUT sums in the vertex buffer at the vertex's local id.  The 16 lanes of a half warp
@@ -222,12 +277,12 @@ APL_TL void tile_reduce_lane(int half, int t, int n_verts, const unsigned char* 
     }
 #pragma unroll
     for (int j = 0; j < 3 * NOUT; ++j) acc[j] = (T)0;
-    // kReduceUnroll slots per trip with all loads issued before the first add: the serial form (one slot per trip: load,
-    // wait ~30 cycles, add) made this phase the longest of the SNH kernel (ncu r2h: 30 % of the samples for 19 % of the
-    // instructions).  A lane past its range re-reads its first slot with weight 0 (always a valid, finite-or-already-
-    // poisoned address), so the trip is branch-free.
+    // APL_REDUCE_UNROLL slots per trip with all loads issued before the first add (a lane past its range re-reads its
+    // first slot with weight 0, so the trip is branch-free).  Measured (run r2n, 8 M tets, G tets/s, U = 1 / 2 / 4):
+    // SNH 33.7 / 32.9 / 32.3, SNH+ARAP 23.3 / 22.6 / 23.0 -- the phase holds 30 % of the SNH kernel's stall samples, but
+    // batching its loads does not shorten it (other warps already cover the latency), so the default stays serial.
 #ifndef APL_REDUCE_UNROLL
-#define APL_REDUCE_UNROLL 4
+#define APL_REDUCE_UNROLL 1
 #endif
     constexpr int U = APL_REDUCE_UNROLL;
     for (int i = half; i < cnt; i += 2 * U) {

@@ -36,6 +36,15 @@ static void run(int64_t n_tiles, const int32_t* tiles, const uint8_t* conn, cons
             }
             us[4 * v + 3] = ps[4 * v + 3] = (T)0;
         }
+        if constexpr (Cfg::kPackedIn) {   // rows [ux uy px py], then rows [uz pz] (fem_kernels.cuh: gather_row_packed)
+            for (int v = 0; v < n_verts; ++v) {
+                const int gv = tile_verts[vs + v];
+                T* ra = vbuf.data() + 4 * v;
+                T* rb = vbuf.data() + 4 * kTileVerts + 2 * v;
+                ra[0] = u[3 * (int64_t)gv]; ra[1] = u[3 * (int64_t)gv + 1]; ra[2] = p[3 * (int64_t)gv]; ra[3] = p[3 * (int64_t)gv + 1];
+                rb[0] = u[3 * (int64_t)gv + 2]; rb[1] = p[3 * (int64_t)gv + 2];
+            }
+        }
         for (auto& x : sl) x = (T)(0.0 / 0.0);   // NaN: a slot that is read without having been written shows up
         // compute phase: one consumer thread per tet
         auto load_rec = [&](int64_t pos, Rec<T, NREC>& r) {
@@ -51,7 +60,10 @@ static void run(int64_t n_tiles, const int32_t* tiles, const uint8_t* conn, cons
                 ushort4 s4;
                 std::memcpy(&lc, conn + 4 * ((size_t)ts + tid), 4);
                 std::memcpy(&s4, slots + 4 * ((size_t)ts + tid), 8);
-                tile_compute<T, KIND, OPS>(r.s, lc, s4, us, ps, axpy, (T)alpha, sl.data(), e_acc, q_acc);
+                if constexpr (Cfg::kPackedIn)
+                    tile_compute_packed<KIND, OPS>((const float*)r.s, lc, s4, (const float*)vbuf.data(), (float*)sl.data(), e_acc, q_acc);
+                else
+                    tile_compute<T, KIND, OPS>(r.s, lc, s4, us, ps, axpy, (T)alpha, sl.data(), e_acc, q_acc);
             }
         }
         if constexpr (NOUT > 0) {
@@ -72,6 +84,11 @@ static void run(int64_t n_tiles, const int32_t* tiles, const uint8_t* conn, cons
                         T sum[3 * NOUT];
                         for (int j = 0; j < 3 * NOUT; ++j) sum[j] = acc[lane][j] + acc[lane + 16][j];
                         const int64_t gv = tile_verts[vs + v[lane]];
+                        if constexpr (Cfg::kPacked) {   // slots hold [gx gy hx hy | gz hz] (tile_reduce_flush maps them back)
+                            const T g3[3] = {sum[0], sum[1], sum[4]}, h3[3] = {sum[2], sum[3], sum[5]};
+                            for (int i = 0; i < 3; ++i) { grad[3 * gv + i] += g3[i]; prod[3 * gv + i] += h3[i]; }
+                            continue;
+                        }
                         int k = 0;
                         if constexpr (Cfg::kGrad) { for (int i = 0; i < 3; ++i) grad[3 * gv + i] += sum[k + i]; k += 3; }
                         if constexpr (Cfg::kDiag) { for (int i = 0; i < 3; ++i) diag[3 * gv + i] += sum[k + i]; k += 3; }

@@ -131,7 +131,9 @@ def test_fused_pcg_matches_host_driven_pcg_and_oracle_residual(native_lib, dtype
         res = oproblem.hess_prod(np.zeros(n), runs[name][0]) - b
         assert np.linalg.norm(res) <= (10 if dtype == torch.float64 else 30) * tol * np.linalg.norm(b), name
     assert abs(runs["graph"][1].n_iters - runs["generic"][1].n_iters) <= 8 + runs["generic"][1].n_iters // 10
-    assert runs["graph"][1].n_iters == runs["eager"][1].n_iters
+    # same recurrences; the REDs of hess_prod land in a different order from launch to launch, so in fp32 the iteration at
+    # which |r| crosses the threshold may differ by one or two
+    assert abs(runs["graph"][1].n_iters - runs["eager"][1].n_iters) <= (0 if dtype == torch.float64 else 3)
     assert rel_err(runs["graph"][0], runs["generic"][0]) < 100 * tol
     # warm start: the solution as x0 converges immediately
     x0 = torch.as_tensor(runs["graph"][0], dtype=dtype, device=rhs.device)
