@@ -147,7 +147,11 @@ class PeerHaloExchange(HaloExchange):
         handle = ctypes.c_void_p()
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         with torch.cuda.device(self.device):
-            _lib.check(L.apl_xchg_create(world, rank, dev_index, max(self.total, 1), ctypes.byref(handle)))
+            # the SAME capacity on every rank: a push addresses the peer's second receive buffer with the local buffer
+            # size (csrc/xchg.cu), so regions of different sizes (end ranks of a slab partition share one plane, middle
+            # ranks two) would be written out of bounds
+            max_rows = max(max(sum(c) for c in all_counts), 1)
+            _lib.check(L.apl_xchg_create(world, rank, dev_index, max_rows, ctypes.byref(handle)))
             self._xchg = handle
             mine = ctypes.create_string_buffer(64)
             _lib.check(L.apl_xchg_ipc_handle(handle, mine))

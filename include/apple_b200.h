@@ -221,6 +221,8 @@ int apl_halo_unpack(int dtype, int64_t n_shared, const int64_t* shared, const in
  *                  (overwritten with the global sums: identical bits on every rank).
  * Every rank must call push and pull the same number of times with the same nf / n_scal (collective semantics);
  * push and pull of one exchange may be enqueued on different streams as long as pull is ordered after push. */
+/* max_recv_rows: capacity of one receive buffer in shared rows; it MUST be the same number on every rank (use the
+ * largest number of rows any rank receives): the two receive buffers of a region are addressed with it from the peers. */
 typedef struct apl_xchg apl_xchg_t;
 int apl_xchg_create(int world, int rank, int device, int64_t max_recv_rows, apl_xchg_t** out);
 void apl_xchg_destroy(apl_xchg_t* x);

@@ -17,3 +17,20 @@ def test_two_gpu_sharding_matches_single_gpu(native_lib):
            "127.0.0.1", "--master-port", "29517", str(ROOT / "tools" / "dist_check.py")]
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0 and "DIST_CHECK PASS" in proc.stdout, proc.stdout[-3000:] + proc.stderr[-3000:]
+
+
+def test_four_ranks_sharing_the_visible_gpus_match_the_whole_cube(native_lib):
+    """Middle ranks of a slab partition have TWO neighbours and larger receive buffers than the end ranks -- a case a
+    2-GPU run never sees (a 4-GPU bench run of round 2 faulted there: the peers' second receive buffer was addressed
+    with the local buffer size).  CUDA IPC works between processes on one device, so four ranks (gloo for the host
+    plumbing) share whatever GPUs are visible: sharded fused evaluation and 20 sharded PNCG iterations on
+    device-generated slabs against the whole cube (tools/peer_check.py)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "4", "--master-addr", "127.0.0.1",
+           "--master-port", "29557", str(root / "tools" / "peer_check.py")]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
+    assert proc.returncode == 0 and "PEER_CHECK PASS" in proc.stdout, proc.stdout[-3000:] + proc.stderr[-3000:]

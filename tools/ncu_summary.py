@@ -34,7 +34,9 @@ def main():
     rd, wr = get("dram__bytes_read.sum"), get("dram__bytes_write.sum")
     print(f"{d[k]}: {dur} (unit {units[names.index('gpu__time_duration.sum')]}), registers {get('launch__registers_per_thread')}")
     if rd is not None and wr is not None:
-        print(f"  dram read+write: {rd + wr:.4g} {units[names.index('dram__bytes_read.sum')]}")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = rd * scale[units[names.index("dram__bytes_read.sum")]] + wr * scale[units[names.index("dram__bytes_write.sum")]]
+        print(f"  dram read+write: {tot / 1e6:.1f} MB" + (f" = {tot / n_tets:.1f} B per tet" if n_tets else ""))
     for name in ("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum",
                  "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
                  "smsp__inst_executed.sum"):
