@@ -19,7 +19,7 @@ class ShardedOperators:
     are kept consistent across ranks; scalars are global."""
 
     def __init__(self, local_model, shard: Shard, device, dtype, group=None, overlap: bool = True,
-                 transport: str | None = None):
+                 transport: str | None = None, peer_overlap: bool = False):
         """``transport``: ``"peer"`` = halo sums and the scalar reduction through peer memory over NVLink in two small
         kernels per evaluation (``PeerHaloExchange``; CUDA, one node), ``"nccl"`` = pack / all-to-all / unpack /
         all-reduce through ``torch.distributed`` (any backend; with ``overlap`` the exchange runs while the interior
@@ -31,14 +31,22 @@ class ShardedOperators:
             transport = "peer" if (self.device.type == "cuda" and shard.world > 1) else "nccl"
         self.transport = transport
         self.halo = PeerHaloExchange(shard, device, group) if transport == "peer" else HaloExchange(shard, device, group)
-        if transport == "peer":
-            overlap = False      # the exchange is two small kernels behind the element pass: nothing left to hide
+        # peer transport: the exchange is two small kernels behind the element pass.  The boundary-first form below
+        # (peer_overlap=True) is OPT-IN: measured at 2 GPUs / 64 M tets it is slower (1.367 vs 1.339 ms per step, run
+        # r2z3): the small boundary launch and the second, scalar-only exchange cost more than the hidden wait.
+        peer_overlap = transport == "peer" and peer_overlap
+        if transport == "peer" and not peer_overlap:
+            overlap = False
         self.n_local = shard.n_local
         # Split evaluation: element tiles that touch a shared vertex first, then the halo exchange of their
         # results on a side stream WHILE the interior tiles (which touch no shared vertex) are evaluated.
         self._split = hasattr(local_model, "mark_boundary")
         self.overlap = False
         self.n_boundary_tiles = 0
+        # peer transport: boundary tiles first, PUSH their shared rows, interior tiles, PULL -- the peers' rows and flags
+        # arrive while the interior pass runs, so the pull does not wait (and rank skew is absorbed); the partial scalars,
+        # complete only after the interior pass, follow in a second, tiny exchange
+        self.peer_overlap = False
         if overlap and self._split and shard.world > 1 and self.halo.total > 0:
             import numpy as np
 
@@ -46,7 +54,8 @@ class ShardedOperators:
             for idx in shard.neighbors.values():
                 flags[idx] = 1
             self.n_boundary_tiles = int(local_model.mark_boundary(flags))
-            self.overlap = True
+            self.overlap = not peer_overlap
+            self.peer_overlap = peer_overlap
         # high priority: the pack / exchange / unpack kernels become ready together with the interior pass and
         # must get SM resources first, otherwise the persistent interior kernel would simply run ahead of them
         self._side = torch.cuda.Stream(self.device, priority=-1) if self.device.type == "cuda" else None
@@ -75,6 +84,16 @@ class ShardedOperators:
             else:                                      # CPU (gloo tests): same order, no overlap
                 self.halo.sum_(*fields)
                 self.model.eval(ops, u, p, part=_lib.PART_INTERIOR, **out, **kw)
+        elif self.peer_overlap and fields:
+            self.model.eval(ops, u, p, part=_lib.PART_BOUNDARY, **out, **kw)
+            self.halo.push(fields)
+            self.model.eval(ops, u, p, part=_lib.PART_INTERIOR, **out, **kw)
+            self.halo.pull(fields)
+            if snames:
+                self.halo.all_reduce_(scal)
+                for i, k in enumerate(snames):
+                    out[k] = scal[i]
+            return out
         elif self.transport == "peer":
             # one element pass, then ONE push + ONE pull kernel carry the shared rows and the partial scalars
             self.model.eval(ops, u, p, **out, **kw)

@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="N>1: halo sums through peer memory (apl_xchg_*) or pack / NCCL all-to-all / unpack / all-reduce")
     ap.add_argument("--graph", action="store_true", help="N>1: replay each step as one CUDA graph (peer transport only)")
+    ap.add_argument("--peer-overlap", action="store_true",
+                    help="N>1, peer transport: boundary tiles, push, interior tiles, pull (default: one pass, then the exchange)")
     ap.add_argument("--no-pncg", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
@@ -403,9 +405,11 @@ def main():
     if world > 1:
         from apple_b200.dist import ShardedOperators
 
-        sharded = ShardedOperators(model, shard, dev, dtype, transport=args.transport, overlap=args.transport == "nccl")
+        sharded = ShardedOperators(model, shard, dev, dtype, transport=args.transport, overlap=args.transport == "nccl",
+                                   peer_overlap=args.peer_overlap)
     torch.cuda.synchronize()
     setup_s = max_over_ranks(time.perf_counter() - t_setup)
+    sharded_peer_overlap = bool(sharded is not None and sharded.peer_overlap)
 
     if world == 1:
         adapter = WarpModelAdapter(model, n_points=V_local)
@@ -434,7 +438,12 @@ def main():
                 return graph_out
             return eager_step()
 
-    launches_per_step = len(pots) + (0 if world == 1 else (2 if args.transport == "peer" else 2 + len(pots) * int(sharded.overlap)))
+    if world == 1:
+        launches_per_step = len(pots)
+    elif args.transport == "peer":    # element pass(es) + push + pull (+ the scalar push + pull of the overlapped form)
+        launches_per_step = len(pots) * (2 if sharded.peer_overlap else 1) + (4 if sharded.peer_overlap else 2)
+    else:
+        launches_per_step = len(pots) + 2 + len(pots) * int(sharded.overlap)
 
     # clocks / throttle reasons are sampled from before the warm-up until after the last timed GPU phase
     clocks = ClockSampler(local_rank)
@@ -593,7 +602,9 @@ def main():
                                        f"{world} ranks x slab of {n // world}+ hex layers (~{T_total // world} tets per GPU, STRONG "
                                        f"scaling, fixed mesh); per step one element pass, then the halo sum of grad+HVP and the "
                                        f"energy reduction "
-                                       + ("through peer memory over NVLink: one push + one pull kernel (apl_xchg_*)"
+                                       + (("through peer memory over NVLink (apl_xchg_*): boundary tiles, push, interior tiles, pull, "
+                                           "then one push + pull of the partial scalars" if sharded_peer_overlap else
+                                           "through peer memory over NVLink: one push + one pull kernel (apl_xchg_*)")
                                           if args.transport == "peer" else
                                           "as pack / NCCL all-to-all / unpack / all-reduce")
                                        + ("; step replayed as one CUDA graph" if (world > 1 and graph is not None) else ""))},

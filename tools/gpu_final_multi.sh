@@ -11,9 +11,9 @@ if [ "$N" = "2" ]; then
   echo "== dist_check"; run 400 29533 tools/dist_check.py > $out/dist_${tag}.log 2>&1; echo "dist rc=$?" >> $out/dist_${tag}.log; grep -v "^W\|^\[W\|Warning" $out/dist_${tag}.log | tail -12
 fi
 echo "== bench $N GPUs (64 M tets, strong scaling)"
-( time run 600 29535 bench.py --gpus $N > $out/bench_${tag}_g${N}.json 2> $out/bench_${tag}_g${N}.err ) 2> $out/time_${tag}_g${N}.txt; tail -c 500 $out/bench_${tag}_g${N}.json; tail -3 $out/bench_${tag}_g${N}.err; cat $out/time_${tag}_g${N}.txt
+( time run 240 29535 bench.py --gpus $N > $out/bench_${tag}_g${N}.json 2> $out/bench_${tag}_g${N}.err ) 2> $out/time_${tag}_g${N}.txt; tail -c 500 $out/bench_${tag}_g${N}.json; tail -3 $out/bench_${tag}_g${N}.err; cat $out/time_${tag}_g${N}.txt
 echo "== config 3 on $N GPUs"
-run 300 29541 tools/bench_configs.py --config 3 > $out/config3_g${N}_${tag}.json 2> $out/config3_${tag}_g${N}.err; tail -c 400 $out/config3_g${N}_${tag}.json
+run 150 29541 tools/bench_configs.py --config 3 > $out/config3_g${N}_${tag}.json 2> $out/config3_${tag}_g${N}.err; tail -c 400 $out/config3_g${N}_${tag}.json
 if [ "$N" = "2" ]; then
   echo "== launch list of one sharded step (rank 0 under ncu is not supported for multi-rank: skipped)"
 fi

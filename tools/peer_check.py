@@ -24,7 +24,7 @@ ok = True
 for dtype, tol in ((torch.float64, 1e-10), (torch.float32, 1e-5)):
     wl = device_workload(n, world, rank, dev, dtype)
     pots = device_potentials(wl, ["snh", "arap"], dtype)
-    ops = ShardedOperators(WarpModel(pots), wl.shard, dev, dtype, transport="peer")
+    ops = ShardedOperators(WarpModel(pots), wl.shard, dev, dtype, transport="peer", peer_overlap=dtype == torch.float64)
     whole = device_workload(n, 1, 0, dev, dtype)
     wp = device_potentials(whole, ["snh", "arap"], dtype)
     V = whole.mesh.n_points
