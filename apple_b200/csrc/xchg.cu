@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(128) xchg_pull_kernel(char* own, int world, in
 int grid_rows(long long n) {
     long long g = (n + 127) / 128;
     if (g < 1) g = 1;
-    if (g > 128) g = 128;   // small on purpose: these kernels share the SMs with the interior element pass
+    if (g > 592) g = 592;   // 4 blocks of 128 threads per SM: one or two rows per thread at the benchmark's plane sizes (the
+                            // kernels run AFTER the element pass by default; a grid of 128 blocks cost ~10 us per kernel)
     return (int)g;
 }
 

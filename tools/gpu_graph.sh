@@ -4,7 +4,7 @@ tag=${1:-r2z}; N=${2:-2}
 out=gpurun_out
 mkdir -p $out
 run() { timeout $1 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $2 "${@:3}"; }
-for mode in "" "--no-overlap"; do
+for mode in ""; do
   echo "== bench $N GPUs $mode"
   run 200 29561 bench.py --gpus $N --steps 40 --warmup 5 --no-hvp --no-pncg --no-e2e $mode > $out/bench_graph_${tag}_g${N}${mode}.json 2> $out/bench_graph_${tag}.err
   python -c "
