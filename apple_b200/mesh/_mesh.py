@@ -34,6 +34,19 @@ class TetMesh:
     def cells_dict(self) -> dict:
         return {VTK_TETRA: self.cells}
 
+    @classmethod
+    def load(cls, path) -> "TetMesh":
+        """``pv.read(path)`` for ``.vtu`` files of linear tetrahedra (``apple_b200/mesh/_vtu.py``)."""
+        from ._vtu import read_vtu
+
+        return read_vtu(path)
+
+    def save(self, path, *, binary: bool = True, compress: bool = False) -> None:
+        """``mesh.save(path)`` of pyvista: VTK XML UnstructuredGrid with every point / cell data array."""
+        from ._vtu import write_vtu
+
+        write_vtu(self, path, binary=binary, compress=compress)
+
     def copy(self) -> "TetMesh":
         return TetMesh(
             self.points.copy(),
