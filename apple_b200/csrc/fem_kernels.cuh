@@ -503,6 +503,9 @@ constexpr int kPipeThreads = kTileTets + 32;
                             // SNH 8 M 37.0 / 35.6 / 31.8, SNH 64 M 39.2 / 37.6 / 33.2, SNH+ARAP 64 M 25.5 / 25.2 / 24.5, HVP
                             // alone 45.1 / 40.1 / 35.3 -- the bulk copies of the stages already keep enough bytes in flight.
 #endif
+#ifndef APL_PRODUCER_PARK
+#define APL_PRODUCER_PARK 1
+#endif
 #ifndef APL_WANT_CTAS
 #define APL_WANT_CTAS 2    // 3: fp32 kernels with a small enough tile state run three CTAs per SM (one slot buffer)
 #endif
@@ -719,7 +722,12 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
             const int n_tets = h.y & 0xffff, n_verts = h.y >> 16;
             // the tables of tile `it` were requested one iteration ago
             const int sv = it % SV;
-            mbar_wait(vfull(sv), (unsigned)(it / SV) & 1u);
+            // With a producer WARPGROUP only warp 0 polls the mbarriers; the other three park at a hardware barrier (a
+            // parked warp issues nothing, a polling one competes with the consumers for issue slots: the fused kernels'
+            // four polling producer warps accounted for a third of all issued instructions, ncu r2z).
+            constexpr bool kPark = PW > 1 && APL_PRODUCER_PARK;
+            static_assert(!(kPark && APL_GATHER_LDG), "the register-staged gather reads the vertex table before the hand-shake");
+            if (!kPark || pw == 0) mbar_wait(vfull(sv), (unsigned)(it / SV) & 1u);
             const int* verts = reinterpret_cast<const int*>(vring + (size_t)sv * PC::kVtabBytes + PC::oVerts);
             const bool via_regs = APL_GATHER_LDG && a.ld_in == 3 && !Cfg::kPackedIn;
             constexpr int R = APL_GATHER_LDG ? (kTileVerts / 32 + PW - 1) / PW : 1;
@@ -739,7 +747,8 @@ __global__ void __launch_bounds__(PipeCfg<T, KIND, OPS>::kThreads, PipeCfg<T, KI
             }
             // stage s free <=> every consumer is past COMPUTE(it - S); its REDUCE phases up to tile
             // it - S - NB are then finished too, which frees vertex slot (it + 1) % SV
-            mbar_wait(empty(s), ph ^ 1u);
+            if (!kPark || pw == 0) mbar_wait(empty(s), ph ^ 1u);
+            if constexpr (kPark) asm volatile("bar.sync 2, %0;" ::"n"(32 * PW) : "memory");
             if (lane == 0 && pw == 0) {
                 *reinterpret_cast<int4*>(st + PC::oHdr) = h;
                 const unsigned bp = (unsigned)n_tets * 16u;
