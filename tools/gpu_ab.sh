@@ -4,12 +4,13 @@
 #   gpurun --timeout 900 -- bash tools/gpu_ab.sh <tag> default x y        # "default" = the product library
 # Every run under a SHORT timeout: a hung variant must not burn GPU minutes.
 tag=${1:-ab}; shift
+variants=("$@")
 out=gpurun_out
 mkdir -p $out
 for round in 1 2; do
 for cfg in "snh 117 3 f32 11" "fused 117 3 f32 11" "snh 234 3 f32 11" "fused 234 3 f32 11" "snh 117 3 f32 8" "fused 58 3 f32 11"; do
-  for v in "$@"; do
-    set -- $cfg "$@"; kind=$1; n=$2; ld=$3; dt=$4; ops=$5; shift 5
+  read -r kind n ld dt ops <<< "$cfg"
+  for v in "${variants[@]}"; do
     lib=""; [ $v != default ] && lib=$PWD/apple_b200/libapple_b200_$v.so
     echo "== round$round $v $kind n=$n ld=$ld $dt ops=$ops"
     APL_LIB=$lib timeout 120 python tools/prof_one.py --kind $kind --ops $ops --n $n --ld $ld --dtype $dt --reps 8 --setup device 2>&1 | tail -1 | grep -o "Gtets.*" || echo "FAILED/TIMEOUT"
