@@ -31,7 +31,7 @@
 struct apl_xchg {
     int world = 1, rank = 0, device = 0;
     int64_t max_rows = 0;            // capacity of one recv buffer, in rows of 9 scalars
-    size_t off_scal = 0, off_recv = 0, recv_bytes = 0, total_bytes = 0;
+    size_t off_hdr = 0, off_scal = 0, off_recv = 0, recv_bytes = 0, total_bytes = 0;
     char* base = nullptr;            // own region
     char* peer[APL_XCHG_MAX_WORLD] = {};   // every rank's region in this process's address space (own included)
     bool opened[APL_XCHG_MAX_WORLD] = {};
@@ -212,7 +212,9 @@ int apl_xchg_create(int world, int rank, int device, int64_t max_rows, apl_xchg_
     }
     apl_xchg* x = new apl_xchg();
     x->world = world; x->rank = rank; x->device = device; x->max_rows = max_rows;
-    x->off_scal = ((size_t)2 * world * 8 + 255) / 256 * 256;
+    // [flags][capacity header, 256 bytes][scalars][two receive buffers]
+    x->off_hdr = ((size_t)2 * world * 8 + 255) / 256 * 256;
+    x->off_scal = x->off_hdr + 256;
     x->off_recv = x->off_scal + ((size_t)2 * world * APL_XCHG_NSCAL * 8 + 255) / 256 * 256;
     x->recv_bytes = ((size_t)max_rows * 9 * 8 + 255) / 256 * 256;
     x->total_bytes = x->off_recv + 2 * x->recv_bytes + 256;
@@ -225,6 +227,10 @@ int apl_xchg_create(int world, int rank, int device, int64_t max_rows, apl_xchg_
     if (e != cudaSuccess) return fail("cudaSetDevice", e);
     if ((e = cudaMalloc((void**)&x->base, x->total_bytes)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMemset(x->base, 0, x->total_bytes)) != cudaSuccess) return fail("cudaMemset", e);
+    // the capacity is published in the region: peers address the second receive buffer with THEIR recv_bytes, so
+    // apl_xchg_connect refuses regions of a different capacity instead of letting a push write out of bounds
+    if ((e = cudaMemcpy(x->base + x->off_hdr, &x->max_rows, sizeof(int64_t), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail("cudaMemcpy", e);
     if ((e = cudaMalloc((void**)&x->d_epoch, 8)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMemset(x->d_epoch, 0, 8)) != cudaSuccess) return fail("cudaMemset", e);
     if ((e = cudaMalloc((void**)&x->d_counters, 8)) != cudaSuccess) return fail("cudaMalloc", e);
@@ -256,6 +262,13 @@ int apl_xchg_connect(apl_xchg_t* x, const void* handles) {
         APL_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
         x->peer[r] = (char*)p;
         x->opened[r] = true;
+        int64_t cap = -1;
+        APL_CUDA_CHECK(cudaMemcpy(&cap, x->peer[r] + x->off_hdr, sizeof(int64_t), cudaMemcpyDeviceToHost));
+        if (cap != x->max_rows) {
+            set_error("apl_xchg_connect: rank " + std::to_string(r) + " was created with max_recv_rows = " + std::to_string(cap) +
+                      ", this rank with " + std::to_string(x->max_rows) + " (the capacity must be the same on every rank)");
+            return APL_ERR_INVALID;
+        }
     }
     return APL_OK;
 }

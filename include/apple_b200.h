@@ -222,7 +222,8 @@ int apl_halo_unpack(int dtype, int64_t n_shared, const int64_t* shared, const in
  * Every rank must call push and pull the same number of times with the same nf / n_scal (collective semantics);
  * push and pull of one exchange may be enqueued on different streams as long as pull is ordered after push. */
 /* max_recv_rows: capacity of one receive buffer in shared rows; it MUST be the same number on every rank (use the
- * largest number of rows any rank receives): the two receive buffers of a region are addressed with it from the peers. */
+ * largest number of rows any rank receives): the two receive buffers of a region are addressed with it from the peers;
+ * apl_xchg_connect compares the capacities published in the regions and fails with APL_ERR_INVALID on a mismatch. */
 typedef struct apl_xchg apl_xchg_t;
 int apl_xchg_create(int world, int rank, int device, int64_t max_recv_rows, apl_xchg_t** out);
 void apl_xchg_destroy(apl_xchg_t* x);
