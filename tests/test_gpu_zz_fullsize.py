@@ -232,3 +232,48 @@ def test_arap_on_compressed_and_inverted_elements(native_lib, dtype, tol):
     assert rel_err(diag.cpu(), d) < 10 * tol        # the twist rates 2 / max(s_i + s_j, 2) kink where s_i + s_j = 2
     assert rel_err(prod.cpu(), hp) < 10 * tol
     assert rel_err(quad.cpu(), q) < 10 * tol
+
+
+def test_config3_graded_mesh_full_size_matches_c_oracle(native_lib):
+    """BASELINE.json configs[2] at its size: 117^3 x 5 = 8,008,065 tets on rectilinear coordinates graded by 1.02 per layer
+    (rest volumes span three decades, dhdX differs per tet), Stable Neo-Hookean with materials over two decades.  The
+    potential is built by the DEVICE setup (apl_fem_create_from_mesh: rest shape, Morton sort and planes on the GPU);
+    energy / gradient / diagonal / HVP against the C restatement of the reference on the whole mesh, fp32 and fp64."""
+    from apple_b200 import _lib
+    from apple_b200.mesh import cube_tet_mesh
+    from apple_b200.warp.fem import StableNeoHookean
+    from oracle import cbind, region as oregion
+
+    mesh = cube_tet_mesh(117, grading=1.02, morton=True)
+    T, V = mesh.n_cells, mesh.n_points
+    assert T == 8_008_065
+    rng = np.random.default_rng(2)
+    mu, la = 10.0 ** rng.uniform(3, 5, T), 10.0 ** rng.uniform(3, 5, T)
+    X = mesh.points
+    # a smooth field with up to 5 % strain whatever the local cell size (a displacement scaled by the finest layer would
+    # strain the coarse cells by 1e-4, where the fp32 energy mu/2 (I2 - 3) - ... of ANY implementation of the reference's
+    # formula is rounding noise)
+    u = np.ascontiguousarray((0.05 / 7.0) * np.sin(7.0 * X[:, [1, 2, 0]] + 0.3))
+    p = rng.uniform(-1, 1, X.shape)
+    dhdX, dV = oregion.compute_grad(mesh.points, mesh.cells)
+    assert dV.max() > 1000 * dV.min() > 0
+    cp = cbind.CPotential("snh", mesh.cells, dhdX, dV, mu, la)
+    e = np.zeros(1)
+    g, d, hp = (np.zeros((V, 3)) for _ in range(3))
+    cp.fun(u, e); cp.grad(u, g); cp.hess_diag(u, d); cp.hess_prod(u, p, hp)
+    del cp, dhdX
+    cells_d = torch.as_tensor(mesh.cells, device="cuda")
+    points_d = torch.as_tensor(mesh.points, device="cuda")
+    for dtype, tol in ((torch.float32, 1e-5), (torch.float64, 1e-10)):
+        pot = StableNeoHookean.from_device_mesh(cells_d, points_d, mu=torch.as_tensor(mu, dtype=dtype, device="cuda"),
+                                                lambda_=torch.as_tensor(la, dtype=dtype, device="cuda"), dtype=dtype)
+        ud = torch.as_tensor(u, dtype=dtype, device="cuda"); pd = torch.as_tensor(p, dtype=dtype, device="cuda")
+        fun, _, grad, diag, prod = _eval(pot, _lib.OP_FUN | _lib.OP_GRAD | _lib.OP_HESS_DIAG | _lib.OP_HESS_PROD, ud, pd, dtype, V)
+        assert rel_err(fun.cpu(), e) < tol, dtype
+        assert rel_err(grad.cpu(), g) < tol, dtype
+        assert rel_err(diag.cpu(), d) < tol, dtype
+        assert rel_err(prod.cpu(), hp) < tol, dtype
+        fun, _, grad, _, prod = _eval(pot, 11, ud, pd, dtype, V)           # the metric kernel (packed pairs in fp32)
+        assert rel_err(fun.cpu(), e) < tol and rel_err(grad.cpu(), g) < tol and rel_err(prod.cpu(), hp) < tol, dtype
+        del pot
+        torch.cuda.empty_cache()
