@@ -1047,6 +1047,9 @@ int launch_fem_superset_impl(const apl_fem* fem, int ops, const FemArgs<T>& args
             return rest ? launch_fem<T, KIND>(fem, rest, args, scatter, stream) : APL_OK;
         }
     }
+    // no hess_prod left (fun / grad / diag only, e.g. PNCG pass A with the PSD option but the scalar preconditioner): the
+    // block instantiation, whose operator set does not read p (its off-diagonal output is NULL and skipped)
+    if (!(base & APL_OP_HESS_PROD)) return launch_one<T, KIND, BLK | APL_OP_PSD>(fem, args, scatter, stream);
     return launch_one<T, KIND, 15 | APL_OP_PSD>(fem, args, scatter, stream);
 }
 

@@ -52,6 +52,10 @@ def test_vertex_blocks_and_psd_operators_match_dense_oracle(native_lib, kind, dt
         if not psd:   # the block diagonal IS hess_diag
             hd = new(); pot.hess_diag(ud, hd)
             assert rel_err(diag[:, :3].cpu(), hd[:, :3].cpu()) < tol
+    # PSD diagonal alone (no p given: PNCG pass A with the scalar preconditioner and psd=True) == diagonal of the PSD blocks
+    dpsd = new(); pot.eval(_lib.OP_HESS_DIAG | _lib.OP_PSD, ud, diag=dpsd)
+    bp = ohess.vertex_blocks(ora, u, V, psd=True)
+    assert np.abs(dpsd[:, :3].cpu().numpy() - np.stack([bp[:, 0, 0], bp[:, 1, 1], bp[:, 2, 2]], 1)).max() < tol * np.abs(bp).max()
     out = new(); pot.hess_prod_psd(ud, pd, out)
     assert rel_err(out[:, :3].cpu(), ohess.hess_prod(ora, u, p, V, psd=True)) < tol
     q = torch.zeros(1, dtype=dtype, device="cuda"); pot.hess_quad_psd(ud, pd, q)
@@ -72,6 +76,23 @@ def test_superset_bits_are_rejected_where_they_do_not_apply(native_lib):
         pot.eval(_lib.OP_HESS_OFFD | _lib.OP_HESS_PROD, ud, pd, prod=out, offd=out)
     with pytest.raises(_lib.NativeError):      # the atomic baseline has no block / PSD variant
         pot.eval(_lib.OP_HESS_DIAG | _lib.OP_HESS_OFFD, ud, diag=out, offd=out.clone(), scatter=_lib.SCATTER_ATOMIC)
+
+
+def test_psd_passes_with_the_scalar_preconditioner(native_lib):
+    """PNCG(psd=True) without the block preconditioner: pass A = fun | grad | PSD diagonal (no direction field), pass B =
+    PSD quadratic form; same minimiser as the default run."""
+    from test_gpu_pncg import _cube_problem
+
+    from apple_b200.forward import Forward
+    from apple_b200.optim import PNCG
+    from apple_b200.optim.pncg import ConvergenceCriteria
+
+    model, _ = _cube_problem(torch.float64, n=5)
+    crit = ConvergenceCriteria(max_steps=400, target_relative_gradient_norm=1e-6)
+    a = Forward(model, optimizer=PNCG(criteria=crit, psd=True)); sa = a.step()
+    b = Forward(model, optimizer=PNCG(criteria=crit)); sb = b.step()
+    assert sa.success and sb.success
+    assert rel_err(a.state.u.cpu(), b.state.u.cpu()) < 1e-4
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-8), (torch.float32, 1e-4)], ids=["f64", "f32"])
