@@ -191,3 +191,36 @@ def test_fused_pcg_reports_breakdown_on_indefinite_hessian_and_psd_fixes_it(nati
     full = oproblem.dof_map.to_full_grad(x.cpu().numpy())
     r = oproblem.dof_map.to_free(ohess.hess_prod(pot, state.u.cpu().numpy(), full, V, psd=True)) - rhs.cpu().numpy()
     assert np.linalg.norm(r) <= 1e-5 * float(rhs.norm())
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_fused_snh_arap_supersets_equal_the_sum_of_its_parts(native_lib, dtype):
+    """The fused SNH+ARAP handle (config 2 / 5's model) with the opt-in bits: vertex blocks, PSD blocks, PSD product and PSD
+    quadratic form equal the sums over the two separate potentials (each validated against the oracle above)."""
+    from apple_b200.warp.fem import fuse_potentials
+
+    mesh, u, p = make_case(n=7, seed=4, amp=0.6)
+    mesh.cell_data.pop("Fraction")
+    V = mesh.n_points
+    tol = TOL[dtype]
+    parts = {k: cuda_potential(k, mesh, dtype, name=k) for k in ("snh", "arap")}
+    fused = list(fuse_potentials({k: cuda_potential(k, mesh, dtype, name=k) for k in ("snh", "arap")}).values())
+    assert len(fused) == 1
+    fused = fused[0]
+    ud = torch.as_tensor(u, dtype=dtype, device="cuda"); pd = torch.as_tensor(p, dtype=dtype, device="cuda")
+    new = lambda: torch.zeros((V, 3), dtype=dtype, device="cuda")  # noqa: E731
+    for psd in (False, True):
+        d0, o0, d1, o1 = new(), new(), new(), new()
+        fused.hess_block(ud, d0, o0, psd=psd)
+        for pot in parts.values():
+            pot.hess_block(ud, d1, o1, psd=psd)
+        assert rel_err(d0.cpu(), d1.cpu()) < 10 * tol and rel_err(o0.cpu(), o1.cpu()) < 10 * tol, psd
+    h0, h1 = new(), new()
+    fused.hess_prod_psd(ud, pd, h0)
+    q0, q1 = torch.zeros(1, dtype=dtype, device="cuda"), torch.zeros(1, dtype=dtype, device="cuda")
+    fused.hess_quad_psd(ud, pd, q0)
+    for pot in parts.values():
+        pot.hess_prod_psd(ud, pd, h1)
+        pot.hess_quad_psd(ud, pd, q1)
+    assert rel_err(h0.cpu(), h1.cpu()) < 10 * tol
+    assert rel_err(q0.cpu(), q1.cpu()) < 10 * tol
