@@ -4,7 +4,8 @@
 // Every rank owns one device region (cudaMalloc, exported with cudaIpcGetMemHandle, mapped by every other rank):
 //   flags  [2][world]  uint64   epoch of the last completed push of rank r into this region (per buffer parity)
 //   scal   [2][world][16] double rank r's partial scalars (energy, p.Hp, ...) of that epoch
-//   recv   [2][rows][9]  T      rows pushed by the other ranks (their partial nodal sums on shared vertices)
+//   recv   [2][rows]     rows pushed by the other ranks (their partial nodal sums on shared vertices: 3 nf scalars
+//                        padded to whole 16-byte vectors, written with 16-byte stores)
 // One exchange = two small kernels (128 threads, <= 40 registers, no shared memory: they co-reside with the persistent element
 // kernel that is working on the interior tiles meanwhile):
 //   PUSH  every shared row of this rank's partial results is stored straight into the sharers' recv buffers, the
@@ -30,7 +31,7 @@
 
 struct apl_xchg {
     int world = 1, rank = 0, device = 0;
-    int64_t max_rows = 0;            // capacity of one recv buffer, in rows of 9 scalars
+    int64_t max_rows = 0;            // capacity of one recv buffer, in rows (80 bytes each)
     size_t off_hdr = 0, off_scal = 0, off_recv = 0, recv_bytes = 0, total_bytes = 0;
     char* base = nullptr;            // own region
     char* peer[APL_XCHG_MAX_WORLD] = {};   // every rank's region in this process's address space (own included)
@@ -80,6 +81,10 @@ __device__ __forceinline__ bool xchg_skipped(const XchgSkip& sk, int& joff) {
     return false;
 }
 
+// bytes of one row of the receive buffers: 3 nf scalars padded to whole 16-byte vectors (<= 80 for nf = 3 doubles)
+template <typename T>
+__host__ __device__ __forceinline__ size_t xchg_row_bytes(int nf) { return ((size_t)3 * nf * sizeof(T) + 15) / 16 * 16; }
+
 template <typename T>
 __global__ void __launch_bounds__(128) xchg_push_kernel(XchgPeers peers, int world, int rank, long long n_send,
                                                         const long long* __restrict__ idx, const int* __restrict__ peer,
@@ -93,16 +98,29 @@ __global__ void __launch_bounds__(128) xchg_push_kernel(XchgPeers peers, int wor
     const unsigned long long e = *epoch + 1ull;
     const size_t par = (size_t)(e & 1ull);
     const T* f[3] = {f0, f1, f2};
+    // One row = the 3 nf values of a shared vertex, padded to a multiple of 16 bytes and written with 16-byte stores:
+    // scalar 4-byte stores over NVLink made this kernel 33 us for 55 k rows (tools/xchg_timing.py, run r2z).
+    const size_t rs = xchg_row_bytes<T>(nf);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_send;
          i += (long long)gridDim.x * blockDim.x) {
         const long long v = idx[i];
-        T* dst = reinterpret_cast<T*>(peers.base[peer[i]] + off_recv + par * recv_bytes) + row[i] * (long long)(3 * nf);
-        for (int k = 0; k < nf; ++k) {
-            const T* r = f[k] + v * ld;
-            dst[3 * k] = r[0];
-            dst[3 * k + 1] = r[1];
-            dst[3 * k + 2] = r[2];
+        union { T t[12]; uint4 q[sizeof(T) == 4 ? 3 : 6]; } buf;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) buf.t[j] = (T)0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (k < nf) {
+                const T* r = f[k] + v * ld;
+                buf.t[3 * k] = r[0];
+                buf.t[3 * k + 1] = r[1];
+                buf.t[3 * k + 2] = r[2];
+            }
         }
+        uint4* dst = reinterpret_cast<uint4*>(peers.base[peer[i]] + off_recv + par * recv_bytes + (size_t)row[i] * rs);
+        const int nq = (int)(rs / 16);
+#pragma unroll
+        for (int c = 0; c < (sizeof(T) == 4 ? 3 : 6); ++c)
+            if (c < nq) dst[c] = buf.q[c];
     }
     if (blockIdx.x == 0 && (int)threadIdx.x < world * n_scal) {
         const int q = threadIdx.x / n_scal, k = threadIdx.x % n_scal;
@@ -140,7 +158,8 @@ __global__ void __launch_bounds__(128) xchg_pull_kernel(char* own, int world, in
         while (ld_acquire_sys(flag) < e) __nanosleep(64);
     }
     __syncthreads();
-    const T* recv = reinterpret_cast<const T*>(own + off_recv + par * recv_bytes);
+    const char* recv = own + off_recv + par * recv_bytes;
+    const size_t rs = xchg_row_bytes<T>(nf);
     T* f[3] = {f0, f1, f2};
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_shared;
          i += (long long)gridDim.x * blockDim.x) {
@@ -153,7 +172,7 @@ __global__ void __launch_bounds__(128) xchg_pull_kernel(char* own, int world, in
                 if (j < 0) {
                     a0 += mine[0]; a1 += mine[1]; a2 += mine[2];
                 } else {
-                    const T* r = recv + (j * nf + k) * 3;
+                    const T* r = reinterpret_cast<const T*>(recv + (size_t)j * rs) + 3 * k;
                     a0 += __ldcg(r); a1 += __ldcg(r + 1); a2 += __ldcg(r + 2);
                 }
             }
@@ -216,7 +235,7 @@ int apl_xchg_create(int world, int rank, int device, int64_t max_rows, apl_xchg_
     x->off_hdr = ((size_t)2 * world * 8 + 255) / 256 * 256;
     x->off_scal = x->off_hdr + 256;
     x->off_recv = x->off_scal + ((size_t)2 * world * APL_XCHG_NSCAL * 8 + 255) / 256 * 256;
-    x->recv_bytes = ((size_t)max_rows * 9 * 8 + 255) / 256 * 256;
+    x->recv_bytes = ((size_t)max_rows * 80 + 255) / 256 * 256;   // rows of up to 3 fields of doubles, padded to 80 bytes
     x->total_bytes = x->off_recv + 2 * x->recv_bytes + 256;
     auto fail = [&](const char* what, cudaError_t e) {
         set_error(std::string(what) + ": " + cudaGetErrorString(e));
