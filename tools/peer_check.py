@@ -57,7 +57,16 @@ for dtype, tol in ((torch.float64, 1e-10), (torch.float32, 1e-5)):
     good = err < (1e-8 if dtype == torch.float64 else 2e-4) and abs(fa - fb) <= 1e-4 * abs(fb)
     ok = ok and good
     print(f"rank {rank}/{world} {dtype} sharded PNCG 20 its: |u-u1|/|u1| = {err:.2e}, f = {fa:.8e} vs {fb:.8e} {'OK' if good else 'FAIL'}", flush=True)
-    del sp, s1, ops
+    # block Jacobi: three fields (g', diag', block off-diagonals) travel in one exchange
+    sb = ShardedPNCG(list(pots.values()), [], wl.shard, free, u0, criteria=crit, use_graph=2, preconditioner="block")
+    sb.iterate(10)
+    s1b = ShardedPNCG(list(wp.values()), [], whole.shard, freew, u0w, criteria=crit, use_graph=2, preconditioner="block")
+    s1b.iterate(10)
+    errb = float((sb.x[:, :3] - s1b.x[:, :3][gid]).abs().max() / s1b.x[:, :3].abs().max())
+    goodb = errb < (1e-8 if dtype == torch.float64 else 2e-4)
+    ok = ok and goodb
+    print(f"rank {rank}/{world} {dtype} sharded block-Jacobi PNCG 10 its: |u-u1|/|u1| = {errb:.2e} {'OK' if goodb else 'FAIL'}", flush=True)
+    del sp, s1, sb, s1b, ops
 flag = torch.tensor([1.0 if ok else 0.0])
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
